@@ -1,0 +1,208 @@
+// eb_capi.cpp -- the extern "C" surface declared in include/edlib.h and include/edlib_b200.h.
+// Thin: argument checks, one process-wide engine behind a mutex (the reference API is
+// re-entrant and is called with the GIL released, ref bindings/python/edlib.pyx:128-129), and
+// the two pure-host helpers that carry no DP work (config constructors, CIGAR run-length
+// encoding, free).
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/edlib.h"
+#include "../../include/edlib_b200.h"
+#include "eb_engine.h"
+
+namespace eb {
+Backend* create_backend(std::string* err);  // provided by the backend object linked into this library
+}
+
+namespace {
+
+std::mutex g_mu;
+eb::Backend* g_backend = nullptr;
+eb::Engine* g_engine = nullptr;
+std::string g_initError;
+bool g_initTried = false;
+
+eb::Engine* engine_locked() {
+    if (!g_initTried) {
+        g_initTried = true;
+        g_backend = eb::create_backend(&g_initError);
+        if (g_backend) g_engine = new eb::Engine(g_backend);
+    }
+    return g_engine;
+}
+
+void fail_results(EdlibAlignResult* results, int n) {
+    for (int i = 0; i < n; ++i) {
+        memset(&results[i], 0, sizeof(results[i]));
+        results[i].status = EDLIB_STATUS_ERROR;
+        results[i].editDistance = -1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ref edlib.cpp:1465-1475
+EDLIB_API EdlibAlignConfig edlibNewAlignConfig(int k, EdlibAlignMode mode, EdlibAlignTask task,
+                                               const EdlibEqualityPair* additionalEqualities,
+                                               int additionalEqualitiesLength) {
+    EdlibAlignConfig c;
+    c.k = k;
+    c.mode = mode;
+    c.task = task;
+    c.additionalEqualities = additionalEqualities;
+    c.additionalEqualitiesLength = additionalEqualitiesLength;
+    return c;
+}
+
+// ref edlib.cpp:1477-1479
+EDLIB_API EdlibAlignConfig edlibDefaultAlignConfig(void) {
+    return edlibNewAlignConfig(-1, EDLIB_MODE_NW, EDLIB_TASK_DISTANCE, NULL, 0);
+}
+
+// ref edlib.cpp:1481-1485
+EDLIB_API void edlibFreeAlignResult(EdlibAlignResult result) {
+    free(result.endLocations);
+    free(result.startLocations);
+    free(result.alignment);
+}
+
+EDLIB_API int edlibAlignBatch(const char* const* queries, const int* queryLengths,
+                              const char* const* targets, const int* targetLengths,
+                              int numPairs, const EdlibAlignConfig config, EdlibAlignResult* results) {
+    if (numPairs < 0 || (numPairs > 0 && (!queries || !queryLengths || !targets || !targetLengths || !results)))
+        return EDLIB_STATUS_ERROR;
+    if (numPairs == 0) return EDLIB_STATUS_OK;
+    std::lock_guard<std::mutex> lock(g_mu);
+    eb::Engine* e = engine_locked();
+    if (!e) {  // no usable device: fail loudly, there is no CPU path
+        fail_results(results, numPairs);
+        return EDLIB_STATUS_ERROR;
+    }
+    eb::BatchInput in{queries, queryLengths, targets, targetLengths, numPairs, config};
+    return e->align_batch(in, results);
+}
+
+// ref edlib.cpp:146-301
+EDLIB_API EdlibAlignResult edlibAlign(const char* query, int queryLength, const char* target, int targetLength,
+                                      const EdlibAlignConfig config) {
+    EdlibAlignResult r;
+    const char* q = query ? query : "";
+    const char* t = target ? target : "";
+    edlibAlignBatch(&q, &queryLength, &t, &targetLength, 1, config, &r);
+    return r;
+}
+
+// ref edlib.cpp:303-350.  Pure formatting of an existing edit script (no DP): kept on the host.
+EDLIB_API char* edlibAlignmentToCigar(const unsigned char* alignment, int alignmentLength, EdlibCigarFormat cigarFormat) {
+    if (cigarFormat != EDLIB_CIGAR_EXTENDED && cigarFormat != EDLIB_CIGAR_STANDARD) return NULL;
+    const char* sym = (cigarFormat == EDLIB_CIGAR_EXTENDED) ? "=IDX" : "MIDM";
+    std::string out;
+    int i = 0;
+    while (i < alignmentLength) {
+        if (alignment[i] > 3) return NULL;
+        const char c = sym[alignment[i]];
+        int run = 0;
+        while (i < alignmentLength && alignment[i] <= 3 && sym[alignment[i]] == c) {
+            ++run;
+            ++i;
+        }
+        out += std::to_string(run);
+        out += c;
+    }
+    char* res = static_cast<char*>(malloc(out.size() + 1));
+    if (!res) return NULL;
+    memcpy(res, out.c_str(), out.size() + 1);
+    return res;
+}
+
+// ---- include/edlib_b200.h ------------------------------------------------------------------
+
+EDLIB_API const char* edlibB200LastError(void) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    static std::string copy;
+    copy = g_engine ? g_engine->lastError : g_initError;
+    return copy.c_str();
+}
+
+EDLIB_API int edlibB200Available(void) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    return engine_locked() ? 1 : 0;
+}
+
+EDLIB_API EdlibB200Batch* edlibB200BatchPrepare(const char* const* queries, const int* queryLengths,
+                                                const char* const* targets, const int* targetLengths,
+                                                int numPairs, const EdlibAlignConfig config) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    eb::Engine* e = engine_locked();
+    if (!e || numPairs <= 0) return NULL;
+    try {
+        eb::BatchInput in{queries, queryLengths, targets, targetLengths, numPairs, config};
+        return reinterpret_cast<EdlibB200Batch*>(e->prepare(in));
+    } catch (const std::exception& ex) {
+        e->lastError = ex.what();
+        return NULL;
+    }
+}
+
+EDLIB_API int edlibB200BatchCompute(EdlibB200Batch* batch, EdlibB200Stats* statsOut) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    eb::Engine* e = engine_locked();
+    if (!e || !batch) return EDLIB_STATUS_ERROR;
+    try {
+        e->stats = eb::EngineStats();
+        e->compute(reinterpret_cast<eb::Prepared*>(batch));
+    } catch (const std::exception& ex) {
+        e->lastError = ex.what();
+        return EDLIB_STATUS_ERROR;
+    }
+    if (statsOut) {
+        statsOut->kernelMs = e->stats.kernelMs;
+        statsOut->k1Ms = e->stats.k1Ms;
+        statsOut->launches = e->stats.launches;
+        statsOut->h2dBytes = e->stats.h2dBytes;
+        statsOut->d2hBytes = e->stats.d2hBytes;
+        statsOut->k1Cells = e->stats.k1Cells;
+        statsOut->wCells = e->stats.wCells;
+    }
+    return EDLIB_STATUS_OK;
+}
+
+EDLIB_API int edlibB200BatchResults(EdlibB200Batch* batch, EdlibAlignResult* results) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    eb::Engine* e = engine_locked();
+    if (!e || !batch || !results) return EDLIB_STATUS_ERROR;
+    try {
+        e->materialize(reinterpret_cast<eb::Prepared*>(batch), results);
+    } catch (const std::exception& ex) {
+        e->lastError = ex.what();
+        return EDLIB_STATUS_ERROR;
+    }
+    return EDLIB_STATUS_OK;
+}
+
+EDLIB_API void edlibB200BatchFree(EdlibB200Batch* batch) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_engine && batch) g_engine->release(reinterpret_cast<eb::Prepared*>(batch));
+}
+
+EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!s) return;
+    memset(s, 0, sizeof(*s));
+    if (!g_engine) return;
+    s->kernelMs = g_engine->stats.kernelMs;
+    s->k1Ms = g_engine->stats.k1Ms;
+    s->launches = g_engine->stats.launches;
+    s->h2dBytes = g_engine->stats.h2dBytes;
+    s->d2hBytes = g_engine->stats.d2hBytes;
+    s->k1Cells = g_engine->stats.k1Cells;
+    s->wCells = g_engine->stats.wCells;
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// eb_common.h -- types shared by the host engine and the kernels.
+//
+// Bit layout used by every kernel (differs from the reference on purpose):
+//   * bit-vectors are arrays of 32-bit words; query row r lives at global bit  g = r + off,
+//     off = 32*nWords - m, i.e. the query is pushed DOWN so that its last row m-1 always sits
+//     at bit 31 of the last word.  The reference pads at the bottom with W wildcard rows and
+//     reads scores W columns late (ref edlib.cpp:188, 374, 670, 681-693); top padding needs no
+//     position shift and lets every kernel read D[m-1][c] from a fixed bit.
+//   * padding bits (g < off): vertical deltas 0 (Pv = Mv = 0); Eq = 1 in HW mode (wildcard
+//     rows keep D == 0, so the first real row sees the HW boundary D[-1][c] = 0) and Eq = 0 in
+//     SHW/NW mode (then Ph is 1 on every padding bit and, with the "| 1" shifted in at bit 0,
+//     the first real row sees the NW/SHW boundary delta +1; Pv/Mv stay 0 on the padding bits).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define EB_HD __host__ __device__ __forceinline__
+#define EB_D __device__ __forceinline__
+#else
+#define EB_HD inline
+#define EB_D inline
+#endif
+
+namespace eb {
+
+struct U2 { uint32_t x, y; };  // {Pv, Ph} of one (column, word) in the stored matrix
+
+constexpr int KPOS = 4;  // end positions kept inline per record; the rest go to the overflow list
+
+// Per-sweep result record (device -> host).  best > bound means "nothing within the bound".
+struct Rec {
+    int best;       // min over tracked columns of D[m-1][c] (or the sentinel it started from)
+    int cnt;        // number of tracked columns attaining `best`
+    int last;       // last such column
+    int rsv;
+    int pos[KPOS];  // first KPOS such columns, ascending
+};
+
+// Overflow entry for columns beyond KPOS; stale entries (score > final best) are dropped on host.
+struct Ovf {
+    int rec;    // index of the Rec it belongs to
+    int score;
+    int pos;
+};
+
+enum Mode : int { MODE_NW = 0, MODE_SHW = 1, MODE_HW = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// K1: lane-per-alignment sweep of many short queries over ONE shared target.
+// ---------------------------------------------------------------------------------------------
+struct K1Params {
+    const uint8_t* tcodes;   // encoded target (dense codes), 16-byte aligned, padded to 16
+    int n;                   // target length
+    const uint8_t* qcodes;   // all encoded queries
+    const uint64_t* qoff;    // [pair] offset into qcodes
+    const int* qlen;         // [pair]
+    const int* readList;     // [numReads] pair indices handled by this launch
+    const int* kInit;        // [numReads] initial `best` sentinel (bound + 1)
+    int numReads;
+    int mode;                // Mode
+    int ncodes;              // alphabet size of the batch
+    const uint8_t* eqtab;    // ncodes x ncodes match table, or nullptr for identity
+    int chunks;              // target chunks (HW only; 1 otherwise)
+    int chunkLen;            // multiple of 16
+    int halo;                // columns swept before a chunk without tracking (>= 2*max m)
+    Rec* recs;               // [chunks][numReads]
+    Ovf* ovf;
+    int* ovfCount;
+    int ovfCap;
+};
+
+// ---------------------------------------------------------------------------------------------
+// W: warp-per-alignment sweep (any query length, any alphabet, per-job target window).
+// ---------------------------------------------------------------------------------------------
+enum WFlags : int {
+    WF_QREV = 1,      // read the query backwards
+    WF_TREV = 2,      // read the target backwards (tBase is then the FIRST symbol read)
+    WF_SLIDE = 4,     // NW only: one 1024*R-row window sliding down the k-band
+    WF_STORE = 8,     // store Pv/Ph of every column for the traceback kernel
+    WF_STOPCOL = 16,  // NW: dump the score column at stopCol and stop (Hirschberg halves)
+};
+
+struct WJob {
+    uint64_t qOff;     // into qcodes; with WF_QREV the query is q[qOff+m-1 .. qOff] reversed
+    uint64_t tOff;     // into tcodes; first symbol read (see WF_TREV)
+    uint64_t peqOff;   // into peq (words): ncodes * nWp words, row-major [code][word]
+    uint64_t auxOff;   // into mat (U2 entries) when WF_STORE; into colOut (ints) when WF_STOPCOL
+    uint64_t hbufOff;  // into hbuf (bytes): 2*n bytes when the job needs more than one strip
+    int m, n;
+    int nWp;           // padded word count: multiple of R, >= ceil(m/32)
+    int mode;          // Mode
+    int flags;         // WFlags
+    int kInit;         // HW/SHW: initial best sentinel; NW: unused
+    int dhi;           // WF_SLIDE: largest diagonal c - r inside the band
+    int stopCol;       // WF_STOPCOL: column whose scores are dumped
+    int rec;           // index of the output Rec
+    int rsv;
+};
+
+struct WParams {
+    const WJob* jobs;
+    int numJobs;
+    const uint8_t* qcodes;
+    const uint8_t* tcodes;
+    const uint32_t* peq;
+    uint8_t* hbuf;
+    U2* mat;
+    int* colOut;
+    Rec* recs;
+    Ovf* ovf;
+    int* ovfCount;
+    int ovfCap;
+};
+
+// Query-profile build for W jobs (one Peq per job).
+struct PeqParams {
+    const WJob* jobs;
+    int numJobs;
+    const uint8_t* qcodes;
+    uint32_t* peq;
+    int ncodes;
+    const uint8_t* eqtab;  // or nullptr
+};
+
+// Traceback over a stored matrix (one thread per job).
+struct TbJob {
+    uint64_t matOff;   // U2 entries, [column][nWp]
+    uint64_t peqOff;   // Peq of the (forward) query
+    uint64_t tOff;     // target window start in tcodes
+    uint64_t outOff;   // into ops: m+n bytes reserved; ops are written back-to-front
+    int m, n, nWp;
+    int rsv;
+};
+struct TbParams {
+    const TbJob* jobs;
+    int numJobs;
+    const U2* mat;
+    const uint32_t* peq;
+    const uint8_t* tcodes;
+    uint8_t* ops;
+    int* opsStart;     // [job] index of the first op inside the job's reserved area
+    int* opsLen;       // [job]
+};
+
+// Presence / alphabet kernels.
+struct MaskItem {
+    uint64_t off;            // into raw
+    int len;                 // <= 65536 (long sequences are split by the host)
+    int dst;                 // which 256-bit set receives the bytes seen
+};
+struct MaskParams {
+    const uint8_t* raw;      // raw bytes as uploaded
+    const MaskItem* items;
+    int numItems;
+    uint32_t* masks;         // [numSets][8] 256-bit presence sets, zeroed by the host
+    int unionSet;            // set that additionally receives every byte seen (or -1)
+};
+struct EncodeParams {
+    uint8_t* data;           // encoded in place
+    uint64_t numBytes;
+    const uint8_t* map;      // [256] byte -> code
+};
+
+}  // namespace eb

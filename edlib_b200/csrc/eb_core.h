@@ -1,0 +1,671 @@
+// eb_core.h -- the kernel BODIES, written once and compiled twice:
+//   * by nvcc for sm_100a (eb_kernels.cu wraps them in __global__ functions), and
+//   * by g++ for the host SIMT emulation the CPU test-suite uses to check the kernel logic
+//     (tests/emul/): per-thread bodies run in a loop, warp-cooperative bodies are instantiated
+//     on a 32-wide vector backend.  The emulation is test infrastructure, never a product path.
+//
+// Reference functions re-expressed here (all in reference edlib/src/edlib.cpp):
+//   calculateBlock 412-447 -> k1_step / w_sweep column step (32-bit words, multi-word carries)
+//   buildPeq 358-384       -> K1PeqBuild / peq_build_job
+//   myersCalcEditDistanceSemiGlobal 550-704, myersCalcEditDistanceNW 730-928 -> k1_* / w_sweep
+//   obtainAlignmentTraceback 942-1141 -> traceback_job
+#pragma once
+#include "eb_common.h"
+
+#if defined(__CUDA_ARCH__)
+#define EB_UNROLL _Pragma("unroll")
+#else
+#define EB_UNROLL
+#endif
+
+namespace eb {
+
+// ---------------------------------------------------------------------------------------------
+// Small primitives with a device and a host spelling
+// ---------------------------------------------------------------------------------------------
+
+// (hi << 1) | (lo >> 31): one bit moving up across a word boundary.
+EB_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, 1);
+#else
+    return (hi << 1) | (lo >> 31);
+#endif
+}
+
+EB_HD int atomic_add_int(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    int old = *p;
+    *p = old + v;
+    return old;
+#endif
+}
+
+EB_HD void atomic_or_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+
+// S = T + P over NW 32-bit words with the carry rippling from word 0 upward.  On the device the
+// whole chain is ONE asm statement so that nothing can be scheduled between the add.cc/addc.cc
+// links (IADD3 / IADD3.X in SASS).
+template <int NW>
+struct AddChain {
+    static EB_HD void run(uint32_t (&S)[NW], const uint32_t (&T)[NW], const uint32_t (&P)[NW]) {
+        uint32_t carry = 0;
+        EB_UNROLL
+        for (int w = 0; w < NW; ++w) {
+            uint64_t s = (uint64_t)T[w] + P[w] + carry;
+            S[w] = (uint32_t)s;
+            carry = (uint32_t)(s >> 32);
+        }
+    }
+};
+#if defined(__CUDA_ARCH__)
+template <>
+struct AddChain<1> {
+    static EB_HD void run(uint32_t (&S)[1], const uint32_t (&T)[1], const uint32_t (&P)[1]) { S[0] = T[0] + P[0]; }
+};
+template <>
+struct AddChain<2> {
+    static EB_HD void run(uint32_t (&S)[2], const uint32_t (&T)[2], const uint32_t (&P)[2]) {
+        asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;"
+            : "=r"(S[0]), "=r"(S[1]) : "r"(T[0]), "r"(T[1]), "r"(P[0]), "r"(P[1]));
+    }
+};
+template <>
+struct AddChain<3> {
+    static EB_HD void run(uint32_t (&S)[3], const uint32_t (&T)[3], const uint32_t (&P)[3]) {
+        asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
+            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2])
+            : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(P[0]), "r"(P[1]), "r"(P[2]));
+    }
+};
+template <>
+struct AddChain<4> {
+    static EB_HD void run(uint32_t (&S)[4], const uint32_t (&T)[4], const uint32_t (&P)[4]) {
+        asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, %9;\n\taddc.cc.u32 %2, %6, %10;\n\taddc.u32 %3, %7, %11;"
+            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3])
+            : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]));
+    }
+};
+template <>
+struct AddChain<5> {
+    static EB_HD void run(uint32_t (&S)[5], const uint32_t (&T)[5], const uint32_t (&P)[5]) {
+        asm("add.cc.u32 %0, %5, %10;\n\taddc.cc.u32 %1, %6, %11;\n\taddc.cc.u32 %2, %7, %12;\n\t"
+            "addc.cc.u32 %3, %8, %13;\n\taddc.u32 %4, %9, %14;"
+            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4])
+            : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]),
+              "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]));
+    }
+};
+template <>
+struct AddChain<6> {
+    static EB_HD void run(uint32_t (&S)[6], const uint32_t (&T)[6], const uint32_t (&P)[6]) {
+        asm("add.cc.u32 %0, %6, %12;\n\taddc.cc.u32 %1, %7, %13;\n\taddc.cc.u32 %2, %8, %14;\n\t"
+            "addc.cc.u32 %3, %9, %15;\n\taddc.cc.u32 %4, %10, %16;\n\taddc.u32 %5, %11, %17;"
+            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5])
+            : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]),
+              "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]));
+    }
+};
+template <>
+struct AddChain<7> {
+    static EB_HD void run(uint32_t (&S)[7], const uint32_t (&T)[7], const uint32_t (&P)[7]) {
+        asm("add.cc.u32 %0, %7, %14;\n\taddc.cc.u32 %1, %8, %15;\n\taddc.cc.u32 %2, %9, %16;\n\t"
+            "addc.cc.u32 %3, %10, %17;\n\taddc.cc.u32 %4, %11, %18;\n\taddc.cc.u32 %5, %12, %19;\n\t"
+            "addc.u32 %6, %13, %20;"
+            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5]), "=r"(S[6])
+            : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]),
+              "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]), "r"(P[6]));
+    }
+};
+template <>
+struct AddChain<8> {
+    static EB_HD void run(uint32_t (&S)[8], const uint32_t (&T)[8], const uint32_t (&P)[8]) {
+        asm("add.cc.u32 %0, %8, %16;\n\taddc.cc.u32 %1, %9, %17;\n\taddc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\taddc.cc.u32 %4, %12, %20;\n\taddc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\taddc.u32 %7, %15, %23;"
+            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5]), "=r"(S[6]), "=r"(S[7])
+            : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]),
+              "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]), "r"(P[6]), "r"(P[7]));
+    }
+};
+#endif
+
+// Pv word for the column before the first one: ones on real rows, zeros on padding bits.
+EB_HD uint32_t init_pv_word(int wordIdx, int off) {
+    const int lo = wordIdx * 32;
+    if (off <= lo) return ~0u;
+    if (off >= lo + 32) return 0u;
+    return ~0u << (off - lo);
+}
+
+// =============================================================================================
+// K1 -- one alignment per thread, query words in registers, Peq rows in shared memory
+// =============================================================================================
+
+// One DP column for one query held in NW 32-bit words.  Same recurrences as the reference's
+// calculateBlock (cpp:421-444) but over ONE NW*32-bit integer: the add carry and the <<1 carry
+// cross word boundaries natively, so no per-block hin/hout is needed.  TOP_ONE selects the
+// horizontal delta entering above row 0: +1 for NW/SHW (cpp:779, 584), 0 for HW.
+template <int NW, bool TOP_ONE>
+EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score) {
+    uint32_t T[NW], S[NW], Ph[NW], Mh[NW];
+    EB_UNROLL
+    for (int w = 0; w < NW; ++w) T[w] = Eq[w] & Pv[w];
+    AddChain<NW>::run(S, T, Pv);
+    EB_UNROLL
+    for (int w = 0; w < NW; ++w) {
+        const uint32_t Xh = (S[w] ^ Pv[w]) | Eq[w];
+        Ph[w] = Mv[w] | ~(Xh | Pv[w]);
+        Mh[w] = Pv[w] & Xh;
+    }
+    // the last query row is bit 31 of the last word (top padding, see eb_common.h)
+    score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
+    EB_UNROLL
+    for (int w = NW - 1; w >= 0; --w) {
+        const uint32_t Phs = w ? funnel_l1(Ph[w - 1 < 0 ? 0 : w - 1], Ph[w]) : ((Ph[0] << 1) | (TOP_ONE ? 1u : 0u));
+        const uint32_t Mhs = w ? funnel_l1(Mh[w - 1 < 0 ? 0 : w - 1], Mh[w]) : (Mh[0] << 1);
+        const uint32_t Xv = Eq[w] | Mv[w];
+        Pv[w] = Mhs | ~(Xv | Phs);
+        Mv[w] = Phs & Xv;
+    }
+}
+
+// Per-thread K1 state that lives across target tiles.
+template <int NW>
+struct K1State {
+    uint32_t Pv[NW], Mv[NW];
+    int score;  // D[m-1][c] of the last column swept
+    int best;   // running minimum (starts at the bound sentinel)
+    int cnt;    // columns attaining best so far
+};
+
+template <int NW>
+EB_HD void k1_init(K1State<NW>& st, int m, int kInit) {
+    const int off = 32 * NW - m;
+    EB_UNROLL
+    for (int w = 0; w < NW; ++w) {
+        st.Pv[w] = init_pv_word(w, off);
+        st.Mv[w] = 0;
+    }
+    st.score = m;  // D[m-1][-1] = m  (ref cpp:576, 760)
+    st.best = kInit;
+    st.cnt = 0;
+}
+
+// Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
+template <int NW>
+EB_HD void k1_event(K1State<NW>& st, int column, Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
+    if (st.score < st.best) {
+        st.best = st.score;
+        st.cnt = 0;
+    }
+    if (st.cnt < KPOS) {
+        rec->pos[st.cnt] = column;
+    } else {
+        const int slot = atomic_add_int(ovfCount, 1);
+        if (slot < ovfCap) {
+            ovf[slot].rec = recIdx;
+            ovf[slot].score = st.score;
+            ovf[slot].pos = column;
+        }
+    }
+    rec->last = column;
+    st.cnt++;
+}
+
+// Sweeps `count` consecutive target symbols starting at absolute column cAbs.  `Acc` hands out
+// the Eq words of a symbol (shared memory on the device).  With TRACK the running minimum and
+// its columns are recorded; without it only the state advances (halo columns of a chunk).
+template <int NW, bool TOP_ONE, bool TRACK, class Acc>
+EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const uint8_t* syms, int count, int cAbs,
+                      Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
+    int i = 0;
+    // head: until the symbol pointer is 4-byte aligned
+    while (i < count && ((uintptr_t)(syms + i) & 3u)) {
+        uint32_t Eq[NW];
+        acc.load(syms[i], Eq);
+        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
+        if (TRACK && st.score <= st.best) k1_event<NW>(st, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+        ++i;
+    }
+    // body: four symbols per 32-bit read
+    for (; i + 4 <= count; i += 4) {
+        const uint32_t four = *reinterpret_cast<const uint32_t*>(syms + i);
+        EB_UNROLL
+        for (int j = 0; j < 4; ++j) {
+            uint32_t Eq[NW];
+            acc.load((four >> (8 * j)) & 0xffu, Eq);
+            k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
+            if (TRACK && st.score <= st.best) k1_event<NW>(st, cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
+        }
+    }
+    for (; i < count; ++i) {
+        uint32_t Eq[NW];
+        acc.load(syms[i], Eq);
+        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
+        if (TRACK && st.score <= st.best) k1_event<NW>(st, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+    }
+}
+
+// Query profile for one K1 thread (ref buildPeq cpp:358-384 with top padding instead of the
+// bottom wildcard rows).  `Acc::store(code, w, bits)` writes one Eq word.
+template <int NW, class Acc>
+EB_HD void k1_build_peq(Acc& acc, const uint8_t* q, int m, int mode, int ncodes, const uint8_t* eqtab) {
+    const int off = 32 * NW - m;
+    const uint32_t padBit = (mode == MODE_HW) ? 1u : 0u;
+    for (int code = 0; code < ncodes; ++code) {
+        for (int w = 0; w < NW; ++w) {
+            uint32_t bits = 0;
+            for (int b = 0; b < 32; ++b) {
+                const int g = w * 32 + b;
+                uint32_t bit;
+                if (g < off) {
+                    bit = padBit;
+                } else {
+                    const int qc = q[g - off];
+                    bit = eqtab ? (eqtab[qc * ncodes + code] ? 1u : 0u) : (qc == code ? 1u : 0u);
+                }
+                bits |= bit << b;
+            }
+            acc.store(code, w, bits);
+        }
+    }
+}
+
+// Chunk geometry of a K1 launch: chunk j owns columns [cs, ce) and starts sweeping at hs.
+struct K1Chunk {
+    int hs, cs, ce;
+};
+EB_HD K1Chunk k1_chunk(const K1Params& p, int chunk) {
+    K1Chunk g;
+    long long cs = (long long)chunk * p.chunkLen;
+    long long ce = cs + p.chunkLen;
+    if (cs > p.n) cs = p.n;
+    if (ce > p.n) ce = p.n;
+    long long hs = cs - p.halo;
+    if (hs < 0) hs = 0;
+    hs &= ~15LL;  // keep tile copies 16-byte aligned; a longer halo is still exact
+    g.hs = (int)hs;
+    g.cs = (int)cs;
+    g.ce = (int)ce;
+    return g;
+}
+
+// Whole K1 work item for one thread when the target is directly addressable (host emulation,
+// and the reference shape for the device kernel, which adds shared-memory tiling around it).
+template <int NW, class Acc>
+EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
+    const int pair = p.readList[slot];
+    const int m = p.qlen[pair];
+    const uint8_t* q = p.qcodes + p.qoff[pair];
+    const int recIdx = chunk * p.numReads + slot;
+    Rec* rec = p.recs + recIdx;
+    k1_build_peq<NW>(acc, q, m, p.mode, p.ncodes, p.eqtab);
+    K1State<NW> st;
+    k1_init<NW>(st, m, p.kInit[slot]);
+    const K1Chunk g = k1_chunk(p, chunk);
+    if (p.mode == MODE_HW) {
+        k1_columns<NW, false, false>(st, acc, p.tcodes + g.hs, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true>(st, acc, p.tcodes + g.cs, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+    } else if (p.mode == MODE_SHW) {
+        k1_columns<NW, true, true>(st, acc, p.tcodes + g.cs, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+    } else {
+        k1_columns<NW, true, false>(st, acc, p.tcodes + g.cs, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        st.best = st.score;  // NW: the bottom-right cell (ref cpp:916)
+        st.cnt = 1;
+        rec->last = p.n - 1;
+        rec->pos[0] = p.n - 1;
+    }
+    rec->best = st.best;
+    rec->cnt = st.cnt;
+}
+
+// =============================================================================================
+// W -- one alignment per warp.  Lane l holds R consecutive words (a "chunk"); the 32 chunks of
+// a warp form a window of 1024*R rows.  A query taller than the window is swept in strips
+// (fixed windows stacked vertically, the horizontal deltas of a strip's bottom row feeding the
+// next strip), or -- NW with a k-band narrower than the window -- by ONE window sliding down
+// the band.  The backend B supplies the warp primitives (device: shuffles/votes; host
+// emulation: 32-wide vectors).  All control flow is warp-uniform.
+// =============================================================================================
+
+struct InitPvFn {
+    int off;
+    EB_HD uint32_t operator()(uint32_t wordIdx) const { return init_pv_word((int)wordIdx, off); }
+};
+struct InitSbFn {  // D at the bottom row of a chunk in column -1: rows above it that are real
+    int off, rowsPerChunk;
+    EB_HD uint32_t operator()(uint32_t chunkIdx) const {
+        const long long v = (long long)(chunkIdx + 1) * rowsPerChunk - off;
+        return v > 0 ? (uint32_t)v : 0u;
+    }
+};
+
+template <class B, int R>
+EB_HD void w_sweep(const WParams& P, int jobIdx) {
+    using U = typename B::U;
+    using Pr = typename B::P;
+    const WJob J = P.jobs[jobIdx];
+    const int m = J.m, n = J.n, nWp = J.nWp;
+    const int off = 32 * nWp - m;
+    const int chunksTotal = nWp / R;
+    const bool slide = (J.flags & WF_SLIDE) != 0;
+    const bool store = (J.flags & WF_STORE) != 0;
+    const bool stopcol = (J.flags & WF_STOPCOL) != 0;
+    const bool trev = (J.flags & WF_TREV) != 0;
+    const int strips = slide ? 1 : (chunksTotal + 31) / 32;
+    const uint8_t* tptr = P.tcodes + J.tOff;
+    const uint32_t* peq = P.peq + J.peqOff;
+    const U lane = B::lane();
+    const Pr isTop = (lane == 0u);
+    const Pr isBot = (lane == 31u);
+    const int topOne = (J.mode != MODE_HW) ? 1 : 0;
+    Rec* rec = P.recs + J.rec;
+    int bestU = J.kInit, cntU = 0;
+    const int rowsPerChunk = 32 * R;
+
+    for (int strip = 0; strip < strips; ++strip) {
+        int topChunk = strip * 32;
+        const bool lastStrip = (strip == strips - 1);
+        const bool track = lastStrip && J.mode != MODE_NW && !stopcol;
+        const uint8_t* hin = nullptr;
+        uint8_t* hout = nullptr;
+        if (strips > 1) {
+            uint8_t* h0 = P.hbuf + J.hbufOff;
+            uint8_t* h1 = h0 + n;
+            if (strip > 0) hin = (strip & 1) ? h0 : h1;
+            if (!lastStrip) hout = (strip & 1) ? h1 : h0;
+        }
+        U Pv[R], Mv[R];
+        EB_UNROLL
+        for (int i = 0; i < R; ++i) {
+            Pv[i] = B::map((U(topChunk) + lane) * U(R) + U(i), InitPvFn{off});
+            Mv[i] = U(0u);
+        }
+        U sb = B::map(U(topChunk) + lane, InitSbFn{off, rowsPerChunk});
+        U symsV = U(0u), hinV = U(0u);
+
+        for (int c = 0; c < n; ++c) {
+            if ((c & 31) == 0) {  // 32 target symbols (and strip inputs) per refill, one per lane
+                const U idx = U(c) + lane;
+                const Pr ok = idx < U(n);
+                symsV = trev ? B::gather8_neg(tptr, idx, ok) : B::gather8(tptr, idx, ok);
+                if (hin) hinV = B::gather8(hin, idx, ok);
+            }
+            const int sym = (int)B::bcast(symsV, c & 31);
+            if (slide) {
+                const int want = c - J.dhi + off;
+                const int wantChunk = want > 0 ? want / rowsPerChunk : 0;
+                while (topChunk < wantChunk) {  // drop the top chunk, open a fresh one at the bottom
+                    const uint32_t old31 = B::bcast(sb, 31);
+                    EB_UNROLL
+                    for (int i = 0; i < R; ++i) {
+                        Pv[i] = B::sel(isBot, U(~0u), B::shfl_down1(Pv[i]));
+                        Mv[i] = B::sel(isBot, U(0u), B::shfl_down1(Mv[i]));
+                    }
+                    sb = B::sel(isBot, U(old31 + (uint32_t)rowsPerChunk), B::shfl_down1(sb));
+                    ++topChunk;
+                }
+            }
+            const int ownerLane = chunksTotal - 1 - topChunk;  // lane whose chunk ends at row m-1
+
+            // Eq words of this lane's chunk for the column's symbol
+            U Eq[R], EqX[R];
+            const uint32_t* peqRow = peq + (size_t)sym * nWp;
+            EB_UNROLL
+            for (int i = 0; i < R; ++i) {
+                const U widx = (U(topChunk) + lane) * U(R) + U(i);
+                Eq[i] = B::gather32(peqRow, widx, widx < U(nWp));
+            }
+            // horizontal delta entering the window's top row
+            int hinP, hinM;
+            if (hin) {
+                const int hv = (int)B::bcast(hinV, c & 31);
+                hinP = hv & 1;
+                hinM = (hv >> 1) & 1;
+            } else if (slide && topChunk > 0) {
+                hinP = 1;  // rows above a sliding window are outside the band: pessimistic +1 (ref cpp:779)
+                hinM = 0;
+            } else {
+                hinP = topOne;
+                hinM = 0;
+            }
+            // (Eq & Pv) + Pv over the whole window: ripple inside the lane, ballot across lanes
+            U S[R];
+            U carry = U(0u);
+            Pr allOnes = (lane == lane);
+            EB_UNROLL
+            for (int i = 0; i < R; ++i) {
+                U e = Eq[i];
+                if (i == 0) e = e | B::sel(isTop, U((uint32_t)hinM), U(0u));  // ref cpp:423
+                EqX[i] = e;
+                const U t = e & Pv[i];
+                U s = t + Pv[i];
+                const U c1 = B::toU(s < t);
+                s = s + carry;
+                const U c2 = B::toU(s < carry);
+                carry = c1 | c2;
+                S[i] = s;
+                allOnes = allOnes & (s == U(~0u));
+            }
+            const uint32_t G = B::ballot(carry != U(0u));
+            const uint32_t Pg = B::ballot(allOnes);
+            const uint32_t cinMask = ((G | Pg) + G) ^ Pg;  // bit l = carry entering lane l
+            U cin = (U(cinMask) >> lane) & U(1u);
+            EB_UNROLL
+            for (int i = 0; i < R; ++i) {
+                S[i] = S[i] + cin;
+                cin = cin & B::toU(S[i] == U(0u));
+            }
+            U Ph[R], Mh[R];
+            EB_UNROLL
+            for (int i = 0; i < R; ++i) {
+                const U Xh = (S[i] ^ Pv[i]) | EqX[i];
+                Ph[i] = Mv[i] | ~(Xh | Pv[i]);
+                Mh[i] = Pv[i] & Xh;
+            }
+            const U hp = Ph[R - 1] >> 31, hm = Mh[R - 1] >> 31;  // delta leaving this chunk's bottom row
+            const U inP = B::sel(isTop, U((uint32_t)hinP), B::shfl_up1(hp));
+            const U inM = B::sel(isTop, U((uint32_t)hinM), B::shfl_up1(hm));
+            EB_UNROLL
+            for (int i = R - 1; i >= 0; --i) {
+                const U Phs = (Ph[i] << 1) | (i ? (Ph[i ? i - 1 : 0] >> 31) : inP);
+                const U Mhs = (Mh[i] << 1) | (i ? (Mh[i ? i - 1 : 0] >> 31) : inM);
+                const U Xv = Eq[i] | Mv[i];
+                Pv[i] = Mhs | ~(Xv | Phs);
+                Mv[i] = Phs & Xv;
+            }
+            sb = sb + hp - hm;
+
+            if (store) {
+                EB_UNROLL
+                for (int i = 0; i < R; ++i) {
+                    const U widx = (U(topChunk) + lane) * U(R) + U(i);
+                    B::scatterU2(P.mat + J.auxOff, U((uint32_t)c * (uint32_t)nWp) + widx, Pv[i], Ph[i], widx < U(nWp));
+                }
+            }
+            if (hout) B::scatter8(hout, U((uint32_t)c), hp | (hm << 1), isBot);
+            if (track) {
+                const Pr ev = (lane == U((uint32_t)ownerLane)) & (sb <= U((uint32_t)bestU));
+                if (B::any(ev)) {  // ref cpp:658-673
+                    const int s = (int)B::bcast(sb, ownerLane);
+                    if (s < bestU) {
+                        bestU = s;
+                        cntU = 0;
+                    }
+                    if (cntU < KPOS) {
+                        B::store_uniform(&rec->pos[cntU], c);
+                    } else {
+                        const int slot = B::atomic_add_uniform(P.ovfCount, 1);
+                        if (slot < P.ovfCap) {
+                            B::store_uniform(&P.ovf[slot].rec, J.rec);
+                            B::store_uniform(&P.ovf[slot].score, s);
+                            B::store_uniform(&P.ovf[slot].pos, c);
+                        }
+                    }
+                    B::store_uniform(&rec->last, c);
+                    ++cntU;
+                }
+            }
+            if (stopcol && c == J.stopCol) {
+                // Dump D[r][c] for the rows inside the window (ref cpp:896-908 keeps the stop
+                // column); later strips still need their rows, so only this strip's sweep ends.
+                B::dump_column(P.colOut + J.auxOff, Pv, Mv, sb, topChunk, R, off, m);
+                break;
+            }
+        }
+        if (lastStrip) {
+            if (stopcol) {
+                B::store_uniform(&rec->best, -1);
+                B::store_uniform(&rec->cnt, 0);
+            } else if (J.mode == MODE_NW) {
+                const int ownerLane = chunksTotal - 1 - topChunk;
+                const int s = (int)B::bcast(sb, ownerLane);
+                B::store_uniform(&rec->best, s);  // ref cpp:916: bottom-right cell
+                B::store_uniform(&rec->cnt, 1);
+                B::store_uniform(&rec->last, n - 1);
+                B::store_uniform(&rec->pos[0], n - 1);
+            } else {
+                B::store_uniform(&rec->best, bestU);
+                B::store_uniform(&rec->cnt, cntU);
+            }
+        }
+    }
+}
+
+// Scalar helper used by both backends' dump_column: writes the scores of one lane's chunk.
+// Bits are walked from the chunk's bottom row upward (ref getBlockCellValues cpp:470-482).
+template <int R>
+EB_HD void dump_chunk_scores(int* out, const uint32_t* Pv, const uint32_t* Mv, uint32_t sb,
+                             int chunkIdx, int off, int m) {
+    int score = (int)sb;
+    for (int i = R - 1; i >= 0; --i) {
+        for (int b = 31; b >= 0; --b) {
+            const long long g = ((long long)chunkIdx * R + i) * 32 + b;
+            const long long r = g - off;
+            if (r >= 0 && r < m) out[r] = score;
+            score -= (int)((Pv[i] >> b) & 1u);
+            score += (int)((Mv[i] >> b) & 1u);
+        }
+    }
+}
+
+// Query profile of one W job: lanes stride over the words (ref buildPeq cpp:358-384, top
+// padding instead of bottom wildcards, optional reversed query for cpp:232-234).
+EB_HD void peq_build_words(const PeqParams& p, int jobIdx, int firstWord, int wordStride) {
+    const WJob J = p.jobs[jobIdx];
+    const int off = 32 * J.nWp - J.m;
+    const uint32_t padBit = (J.mode == MODE_HW) ? 1u : 0u;
+    const uint8_t* q = p.qcodes + J.qOff;
+    const bool rev = (J.flags & WF_QREV) != 0;
+    uint32_t* dst = p.peq + J.peqOff;
+    for (int w = firstWord; w < J.nWp; w += wordStride) {
+        for (int code = 0; code < p.ncodes; ++code) {
+            uint32_t bits = 0;
+            for (int b = 0; b < 32; ++b) {
+                const int g = w * 32 + b;
+                uint32_t bit;
+                if (g < off) {
+                    bit = padBit;
+                } else {
+                    const int r = g - off;
+                    const int qc = rev ? q[J.m - 1 - r] : q[r];
+                    bit = p.eqtab ? (p.eqtab[qc * p.ncodes + code] ? 1u : 0u) : (qc == code ? 1u : 0u);
+                }
+                bits |= bit << b;
+            }
+            dst[(size_t)code * J.nWp + w] = bits;
+        }
+    }
+}
+
+// Traceback over the stored {Pv, Ph} matrix of an NW sweep (restates obtainAlignmentTraceback,
+// ref cpp:942-1141): from the bottom-right cell prefer UP (vertical delta +1 -> INSERT,
+// cpp:1020), then LEFT (horizontal delta +1 -> DELETE, cpp:1054), else the diagonal, which is a
+// MATCH exactly when the symbols are equal (cpp:1086 decides by score; equal symbols <=> equal
+// scores on a diagonal step that is neither UP- nor LEFT-explained).  Edges run out as in
+// cpp:1025-1029, 1059-1065, 1090-1103.  Ops are written back-to-front, so no final reverse.
+EB_HD void traceback_job(const TbParams& p, int jobIdx) {
+    const TbJob J = p.jobs[jobIdx];
+    const U2* mat = p.mat + J.matOff;
+    const uint32_t* peq = p.peq + J.peqOff;
+    const uint8_t* t = p.tcodes + J.tOff;
+    uint8_t* ops = p.ops + J.outOff;
+    const int off = 32 * J.nWp - J.m;
+    int w = J.m + J.n;  // next write position + 1
+    int r = J.m - 1, c = J.n - 1;
+    for (;;) {
+        const int g = r + off;
+        const U2 e = mat[(size_t)c * J.nWp + (g >> 5)];
+        const uint32_t bit = 1u << (g & 31);
+        if (e.x & bit) {  // up
+            ops[--w] = 1;
+            if (--r < 0) {
+                for (int i = 0; i <= c; ++i) ops[--w] = 2;
+                break;
+            }
+        } else if (e.y & bit) {  // left
+            ops[--w] = 2;
+            if (--c < 0) {
+                for (int i = 0; i <= r; ++i) ops[--w] = 1;
+                break;
+            }
+        } else {
+            const uint32_t eq = peq[(size_t)t[c] * J.nWp + (g >> 5)] & bit;
+            ops[--w] = eq ? 0 : 3;
+            --r;
+            --c;
+            if (c < 0) {
+                for (int i = 0; i <= r; ++i) ops[--w] = 1;
+                break;
+            }
+            if (r < 0) {
+                for (int i = 0; i <= c; ++i) ops[--w] = 2;
+                break;
+            }
+        }
+    }
+    p.opsStart[jobIdx] = w;
+    p.opsLen[jobIdx] = J.m + J.n - w;
+}
+
+// Presence set of one item (<= 64 KiB of raw bytes), OR-ed into its destination set.
+EB_HD void mask_item(const MaskParams& p, int itemIdx, int first, int stride) {
+    const MaskItem it = p.items[itemIdx];
+    uint32_t local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint8_t* s = p.raw + it.off;
+    for (int i = first; i < it.len; i += stride) {
+        const uint32_t b = s[i];
+        local[b >> 5] |= 1u << (b & 31);
+    }
+    for (int k = 0; k < 8; ++k)
+        if (local[k]) {
+            atomic_or_u32(&p.masks[(size_t)it.dst * 8 + k], local[k]);
+            if (p.unionSet >= 0) atomic_or_u32(&p.masks[(size_t)p.unionSet * 8 + k], local[k]);
+        }
+}
+
+// alphabetLength of one pair: distinct byte values in query and target together
+// (ref transformSequences cpp:1437-1461 counts them while recoding).
+EB_HD int alpha_len_pair(const uint32_t* masks, int qset, int tset) {
+    int c = 0;
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t v = masks[(size_t)qset * 8 + k] | masks[(size_t)tset * 8 + k];
+#if defined(__CUDA_ARCH__)
+        c += __popc(v);
+#else
+        c += __builtin_popcount(v);
+#endif
+    }
+    return c;
+}
+
+}  // namespace eb

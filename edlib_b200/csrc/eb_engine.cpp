@@ -1,0 +1,927 @@
+// eb_engine.cpp -- batch planner / orchestrator (see eb_engine.h).
+//
+// Pipeline of one batch (reference driver: edlibAlign, ref edlib.cpp:146-301):
+//   prepare : pack + upload raw bytes, byte-presence sets on the device (-> alphabetLength per
+//             pair, ref cpp:1417-1462), dense code map, in-place encoding, equality table
+//             (ref cpp:63-94)
+//   compute : distance + end locations  (K1 lane-per-alignment for groups that share a target,
+//             W warp-per-alignment otherwise; ref cpp:199-225)
+//             start locations           (reversed SHW sweeps, ref cpp:228-272)
+//             alignment path            (stored-matrix NW sweep + traceback kernel inside the
+//                                        reference's 1 MiB rule, ref cpp:276-289, 1161-1213)
+//   materialize : malloc'd arrays per result (ownership as ref edlib.h:177,186,205)
+#include "eb_engine.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace eb {
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+EngineTunables::EngineTunables() {
+    k1MinGroup = env_int("EDLIB_B200_K1_MIN_GROUP", k1MinGroup);
+    k1MinChunk = env_int("EDLIB_B200_K1_MIN_CHUNK", k1MinChunk);
+    ovfCap = env_int("EDLIB_B200_OVF_CAP", ovfCap);
+    const int sliceMb = env_int("EDLIB_B200_SLICE_MB", 0);
+    if (sliceMb > 0) sliceBytes = (size_t)sliceMb << 20;
+}
+
+namespace {
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+template <class T>
+struct DevBuf {
+    Backend* be = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(Backend* b, size_t count) { alloc(b, count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { reset(); }
+    void alloc(Backend* b, size_t count) {
+        reset();
+        be = b;
+        n = count;
+        p = static_cast<T*>(be->alloc(std::max<size_t>(count, 1) * sizeof(T)));
+    }
+    void reset() {
+        if (p) be->free(p);
+        p = nullptr;
+        n = 0;
+    }
+    void upload(const T* src, size_t count) { be->h2d(p, src, count * sizeof(T)); }
+    void download(T* dst, size_t count) { be->d2h(dst, p, count * sizeof(T)); }
+};
+
+struct Target {
+    const char* ptr;
+    int len;
+    uint64_t off;  // into the packed sequence buffer
+};
+
+// One warp-per-alignment sweep as seen by the host.
+struct WTask {
+    uint64_t qOff = 0, tOff = 0;
+    int m = 0, n = 0, mode = 0, flags = 0, kInit = 0, dhi = 0, stopCol = -1;
+    int R = 1, nWp = 0;
+    int pair = -1, tag = 0;
+    Rec rec{};
+    std::vector<int> extra;  // positions past KPOS that attain rec.best, ascending
+    long long opsOff = -1;   // into the ops pool (WF_STORE)
+    int opsLen = 0;
+    long long colOff = -1;   // into the column pool (WF_STOPCOL)
+};
+
+struct WPlan {
+    int R, nWp;
+    bool slide;
+    int dhi;
+};
+
+// Window shape of a W job.  Short queries (<= 1024 rows) always fit one fixed window, which is
+// exact for any k.  Longer NW jobs with a bound use one window sliding down the Ukkonen band
+// (cells with |d| + |delta - d| <= k, d = c - r: ref cpp:755, 799-830 keep the same cells) when
+// the band is at most half of the query; everything else is swept unbanded in strips.
+WPlan plan_w(int m, int n, int mode, int kBound) {
+    WPlan pl;
+    const int nW = ceil_div(m, 32);
+    pl.slide = false;
+    pl.dhi = 0;
+    if (nW <= 32) {
+        pl.R = 1;
+        pl.nWp = nW;
+        return pl;
+    }
+    pl.nWp = (int)round_up((size_t)nW, 8);
+    if (mode == MODE_NW && kBound >= 0) {
+        const int d = n - m;
+        const int ad = d < 0 ? -d : d;
+        const long long h = ((long long)kBound - ad) / 2;
+        const long long dlo = std::min(0, d) - h, dhi = std::max(0, d) + h;
+        const long long height = dhi - dlo + 1;
+        for (int R = 1; R <= 8; R *= 2) {
+            if (height + 32LL * R <= 1024LL * R && 64 * R <= nW) {
+                pl.R = R;
+                pl.slide = true;
+                pl.dhi = (int)dhi;
+                return pl;
+            }
+        }
+    }
+    pl.R = 8;
+    for (int R = 2; R <= 8; R *= 2)
+        if (32 * R >= pl.nWp) {
+            pl.R = R;
+            break;
+        }
+    return pl;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Prepared batch
+// ---------------------------------------------------------------------------------------------
+class Prepared {
+public:
+    Backend* be = nullptr;
+    int N = 0;
+    EdlibAlignConfig cfg{};
+    int mode = MODE_NW;  // normalised: anything that is not SHW/HW runs as NW (ref cpp:205-215)
+    std::vector<int> qlen, tlen, tidx;
+    std::vector<uint64_t> qoff;
+    std::vector<Target> tg;
+    DevBuf<uint8_t> dSeq;
+    DevBuf<uint64_t> dQoff;
+    DevBuf<int> dQlen;
+    DevBuf<uint8_t> dEqtab;
+    bool hasEq = false;
+    int ncodes = 0;
+    std::vector<int> alphaLen;
+
+    // results
+    std::vector<int> ed;            // distance or -1
+    std::vector<uint8_t> special;   // 1: an empty sequence (ref cpp:166-184)
+    std::vector<long long> endStart;
+    std::vector<int> endCount;
+    std::vector<int> endPool, startPool;
+    std::vector<long long> alnStart;  // -1: none
+    std::vector<int> alnLen;
+    std::vector<uint8_t> alnPool;
+    bool computed = false;
+};
+
+// ---------------------------------------------------------------------------------------------
+// prepare
+// ---------------------------------------------------------------------------------------------
+Prepared* Engine::prepare(const BatchInput& in) {
+    Backend* be = be_;
+    Prepared* p = new Prepared();
+    try {
+        p->be = be;
+        p->N = in.numPairs;
+        p->cfg = in.config;
+        p->mode = (in.config.mode == EDLIB_MODE_SHW) ? MODE_SHW : (in.config.mode == EDLIB_MODE_HW) ? MODE_HW : MODE_NW;
+        const int N = p->N;
+        p->qlen.assign(in.queryLengths, in.queryLengths + N);
+        p->tlen.assign(in.targetLengths, in.targetLengths + N);
+        p->tidx.resize(N);
+        p->qoff.resize(N);
+        for (int i = 0; i < N; ++i)
+            if (p->qlen[i] < 0 || p->tlen[i] < 0) throw std::runtime_error("negative sequence length");
+
+        // identical (pointer, length) targets are uploaded and encoded once
+        struct Key {
+            const char* ptr;
+            int len;
+            bool operator==(const Key& o) const { return ptr == o.ptr && len == o.len; }
+        };
+        struct KeyHash {
+            size_t operator()(const Key& k) const { return std::hash<const void*>()(k.ptr) * 31 + (size_t)k.len; }
+        };
+        std::unordered_map<Key, int, KeyHash> seen;
+        for (int i = 0; i < N; ++i) {
+            Key k{in.targets[i], in.targetLengths[i]};
+            auto it = seen.find(k);
+            if (it == seen.end()) {
+                it = seen.emplace(k, (int)p->tg.size()).first;
+                p->tg.push_back(Target{k.ptr, k.len, 0});
+            }
+            p->tidx[i] = it->second;
+        }
+        const int T = (int)p->tg.size();
+
+        // pack: queries back to back, then every target 16-aligned with >= 16 bytes of slack
+        size_t total = 0;
+        for (int i = 0; i < N; ++i) {
+            p->qoff[i] = total;
+            total += (size_t)p->qlen[i];
+        }
+        total = round_up(total, 16);
+        for (int t = 0; t < T; ++t) {
+            p->tg[t].off = total;
+            total += round_up((size_t)p->tg[t].len, 16) + 16;
+        }
+        total += 16;
+        uint8_t* stage = static_cast<uint8_t*>(be->alloc_host(total));
+        {
+            size_t pos = 0;
+            for (int i = 0; i < N; ++i) {
+                if (p->qlen[i]) memcpy(stage + pos, in.queries[i], (size_t)p->qlen[i]);
+                pos += (size_t)p->qlen[i];
+            }
+            size_t end = p->tg.empty() ? total : p->tg[0].off;
+            memset(stage + pos, 0, end - pos);
+            for (int t = 0; t < T; ++t) {
+                const Target& g = p->tg[t];
+                if (g.len) memcpy(stage + g.off, g.ptr, (size_t)g.len);
+                const size_t next = (t + 1 < T) ? p->tg[t + 1].off : total;
+                memset(stage + g.off + g.len, 0, next - g.off - (size_t)g.len);
+            }
+        }
+        p->dSeq.alloc(be, total);
+        p->dSeq.upload(stage, total);
+        stats.h2dBytes += (long long)total;
+        p->dQoff.alloc(be, N);
+        p->dQoff.upload(p->qoff.data(), N);
+        p->dQlen.alloc(be, N);
+        p->dQlen.upload(p->qlen.data(), N);
+
+        // byte-presence sets: one per query, one per distinct target, one union for the batch
+        std::vector<MaskItem> items;
+        items.reserve((size_t)N + T);
+        auto add_items = [&](uint64_t off, int len, int dst) {
+            for (int s = 0; s < len; s += 65536) items.push_back(MaskItem{off + (uint64_t)s, std::min(65536, len - s), dst});
+        };
+        for (int i = 0; i < N; ++i) add_items(p->qoff[i], p->qlen[i], i);
+        for (int t = 0; t < T; ++t) add_items(p->tg[t].off, p->tg[t].len, N + t);
+        const int unionSet = N + T;
+        DevBuf<uint32_t> dMasks(be, (size_t)(N + T + 1) * 8);
+        be->zero(dMasks.p, (size_t)(N + T + 1) * 8 * sizeof(uint32_t));
+        DevBuf<MaskItem> dItems(be, items.size());
+        if (!items.empty()) {
+            dItems.upload(items.data(), items.size());
+            MaskParams mp{p->dSeq.p, dItems.p, (int)items.size(), dMasks.p, unionSet};
+            be->launch_mask(mp);
+        }
+        DevBuf<int> dTset(be, N), dAlpha(be, N);
+        {
+            std::vector<int> tset(N);
+            for (int i = 0; i < N; ++i) tset[i] = N + p->tidx[i];
+            dTset.upload(tset.data(), N);
+        }
+        be->launch_alpha_len(dMasks.p, nullptr, dTset.p, N, dAlpha.p);
+        p->alphaLen.resize(N);
+        dAlpha.download(p->alphaLen.data(), N);
+        uint32_t uni[8];
+        be->d2h(uni, dMasks.p + (size_t)unionSet * 8, sizeof(uni));
+        stats.d2hBytes += (long long)N * 4 + 32;
+
+        // dense codes in ascending byte order; absent bytes (padding) map to code 0
+        uint8_t map[256];
+        memset(map, 0, sizeof(map));
+        int byteOfCode[256];
+        p->ncodes = 0;
+        for (int b = 0; b < 256; ++b)
+            if (uni[b >> 5] >> (b & 31) & 1u) {
+                byteOfCode[p->ncodes] = b;
+                map[b] = (uint8_t)p->ncodes++;
+            }
+        if (p->ncodes == 0) p->ncodes = 1;
+        DevBuf<uint8_t> dMap(be, 256);
+        dMap.upload(map, 256);
+        EncodeParams ep{p->dSeq.p, (uint64_t)total, dMap.p};
+        be->launch_encode(ep);
+
+        // equality table over codes (ref cpp:63-94); a pair naming an absent byte changes nothing
+        if (in.config.additionalEqualities && in.config.additionalEqualitiesLength > 0) {
+            const int s = p->ncodes;
+            std::vector<uint8_t> eq((size_t)s * s, 0);
+            for (int i = 0; i < s; ++i) eq[(size_t)i * s + i] = 1;
+            bool any = false;
+            for (int i = 0; i < in.config.additionalEqualitiesLength; ++i) {
+                const int a = (unsigned char)in.config.additionalEqualities[i].first;
+                const int b = (unsigned char)in.config.additionalEqualities[i].second;
+                const bool ha = uni[a >> 5] >> (a & 31) & 1u, hb = uni[b >> 5] >> (b & 31) & 1u;
+                if (ha && hb) {
+                    eq[(size_t)map[a] * s + map[b]] = eq[(size_t)map[b] * s + map[a]] = 1;
+                    any = true;
+                }
+            }
+            if (any) {
+                p->dEqtab.alloc(be, eq.size());
+                p->dEqtab.upload(eq.data(), eq.size());
+                p->hasEq = true;
+            }
+        }
+        (void)byteOfCode;
+        be->sync();
+        be->free_host(stage);
+    } catch (...) {
+        delete p;
+        throw;
+    }
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// W runner: executes a list of tasks in memory-bounded slices
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct WRunner {
+    Engine* eng;
+    Backend* be;
+    Prepared* p;
+    std::vector<uint8_t>* opsPool = nullptr;
+    std::vector<int>* colPool = nullptr;
+
+    size_t task_bytes(const WTask& t) const {
+        size_t b = (size_t)p->ncodes * t.nWp * 4 + sizeof(WJob) + sizeof(Rec);
+        if (t.flags & WF_STORE) b += (size_t)t.n * t.nWp * 8 + (size_t)t.m + t.n + 64;
+        if (t.flags & WF_STOPCOL) b += (size_t)t.m * 4;
+        if (!(t.flags & WF_SLIDE) && t.nWp / t.R > 32) b += 2 * (size_t)t.n;
+        return b;
+    }
+
+    void run(std::vector<WTask>& tasks) {
+        std::vector<int> order(tasks.size());
+        for (size_t i = 0; i < tasks.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tasks[a].R < tasks[b].R; });
+        size_t i = 0;
+        while (i < order.size()) {
+            const int R = tasks[order[i]].R;
+            size_t bytes = 0, j = i;
+            while (j < order.size() && tasks[order[j]].R == R) {
+                const size_t tb = task_bytes(tasks[order[j]]);
+                if (j > i && bytes + tb > eng->tun.sliceBytes) break;
+                bytes += tb;
+                ++j;
+            }
+            std::vector<int> slice(order.begin() + i, order.begin() + j);
+            run_slice(tasks, slice, R, eng->tun.ovfCap, false);
+            i = j;
+        }
+    }
+
+    void run_slice(std::vector<WTask>& tasks, const std::vector<int>& slice, int R, int ovfCap, bool isRetry) {
+        const int J = (int)slice.size();
+        std::vector<WJob> jobs(J);
+        uint64_t peqWords = 0, matEntries = 0, colInts = 0, hbytes = 0, opsBytes = 0;
+        std::vector<TbJob> tb;
+        std::vector<int> tbTask;
+        for (int s = 0; s < J; ++s) {
+            WTask& t = tasks[slice[s]];
+            WJob& j = jobs[s];
+            memset(&j, 0, sizeof(j));
+            j.qOff = t.qOff;
+            j.tOff = t.tOff;
+            j.m = t.m;
+            j.n = t.n;
+            j.nWp = t.nWp;
+            j.mode = t.mode;
+            j.flags = t.flags;
+            j.kInit = t.kInit;
+            j.dhi = t.dhi;
+            j.stopCol = t.stopCol;
+            j.rec = s;
+            j.peqOff = peqWords;
+            peqWords += (uint64_t)p->ncodes * t.nWp;
+            if (t.flags & WF_STORE) {
+                j.auxOff = matEntries;
+                TbJob b;
+                memset(&b, 0, sizeof(b));
+                b.matOff = matEntries;
+                b.peqOff = j.peqOff;
+                b.tOff = t.tOff;
+                b.outOff = opsBytes;
+                b.m = t.m;
+                b.n = t.n;
+                b.nWp = t.nWp;
+                tb.push_back(b);
+                tbTask.push_back(slice[s]);
+                matEntries += (uint64_t)t.n * t.nWp;
+                opsBytes += (uint64_t)t.m + t.n;
+            } else if (t.flags & WF_STOPCOL) {
+                j.auxOff = colInts;
+                colInts += (uint64_t)t.m;
+            }
+            if (!(t.flags & WF_SLIDE) && t.nWp / R > 32) {
+                j.hbufOff = hbytes;
+                hbytes += 2 * (uint64_t)t.n;
+            }
+        }
+        DevBuf<WJob> dJobs(be, J);
+        dJobs.upload(jobs.data(), J);
+        DevBuf<uint32_t> dPeq(be, peqWords);
+        DevBuf<U2> dMat(be, matEntries);
+        DevBuf<int> dCol(be, colInts);
+        DevBuf<uint8_t> dH(be, hbytes);
+        DevBuf<Rec> dRecs(be, J);
+        be->zero(dRecs.p, (size_t)J * sizeof(Rec));
+        DevBuf<Ovf> dOvf(be, (size_t)ovfCap);
+        DevBuf<int> dOvfCount(be, 1);
+        be->zero(dOvfCount.p, sizeof(int));
+        if (colInts) {
+            std::vector<int> big(colInts, 0x3f3f3f3f);  // rows outside a sliding window: "far above any k"
+            dCol.upload(big.data(), colInts);
+        }
+        PeqParams pp{dJobs.p, J, p->dSeq.p, dPeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr};
+        be->launch_peq(pp);
+        WParams wp{dJobs.p, J, p->dSeq.p, p->dSeq.p, dPeq.p, dH.p, dMat.p, dCol.p, dRecs.p, dOvf.p, dOvfCount.p, ovfCap};
+        be->launch_w(wp, R);
+
+        DevBuf<TbJob> dTb;
+        DevBuf<uint8_t> dOps;
+        DevBuf<int> dOpsStart, dOpsLen;
+        if (!tb.empty()) {
+            dTb.alloc(be, tb.size());
+            dTb.upload(tb.data(), tb.size());
+            dOps.alloc(be, opsBytes);
+            dOpsStart.alloc(be, tb.size());
+            dOpsLen.alloc(be, tb.size());
+            TbParams tp{dTb.p, (int)tb.size(), dMat.p, dPeq.p, p->dSeq.p, dOps.p, dOpsStart.p, dOpsLen.p};
+            be->launch_traceback(tp);
+        }
+
+        std::vector<Rec> recs(J);
+        dRecs.download(recs.data(), J);
+        int ovfCount = 0;
+        dOvfCount.download(&ovfCount, 1);
+        eng->stats.d2hBytes += (long long)J * (long long)sizeof(Rec) + 4;
+        for (int s = 0; s < J; ++s) tasks[slice[s]].rec = recs[s];
+        const bool truncated = ovfCount > ovfCap;
+        if (ovfCount > 0 && !truncated) {
+            std::vector<Ovf> ov(ovfCount);
+            dOvf.download(ov.data(), ovfCount);
+            eng->stats.d2hBytes += (long long)ovfCount * (long long)sizeof(Ovf);
+            for (int s = 0; s < J; ++s) tasks[slice[s]].extra.clear();
+            for (const Ovf& o : ov) {
+                WTask& t = tasks[slice[o.rec]];
+                if (o.score == t.rec.best) t.extra.push_back(o.pos);
+            }
+        }
+        if (!tb.empty()) {
+            std::vector<int> st(tb.size()), ln(tb.size());
+            dOpsStart.download(st.data(), tb.size());
+            dOpsLen.download(ln.data(), tb.size());
+            std::vector<uint8_t> ops(opsBytes);
+            dOps.download(ops.data(), opsBytes);
+            eng->stats.d2hBytes += (long long)opsBytes + 8LL * (long long)tb.size();
+            for (size_t k = 0; k < tb.size(); ++k) {
+                WTask& t = tasks[tbTask[k]];
+                t.opsOff = (long long)opsPool->size();
+                t.opsLen = ln[k];
+                opsPool->insert(opsPool->end(), ops.begin() + tb[k].outOff + st[k], ops.begin() + tb[k].outOff + st[k] + ln[k]);
+            }
+        }
+        if (colInts) {
+            std::vector<int> cols(colInts);
+            dCol.download(cols.data(), colInts);
+            eng->stats.d2hBytes += (long long)colInts * 4;
+            for (int s = 0; s < J; ++s) {
+                WTask& t = tasks[slice[s]];
+                if (t.flags & WF_STOPCOL) {
+                    t.colOff = (long long)colPool->size();
+                    colPool->insert(colPool->end(), cols.begin() + jobs[s].auxOff, cols.begin() + jobs[s].auxOff + t.m);
+                }
+            }
+        }
+        if (truncated) {
+            // Exact-size second pass for the tasks whose lists did not fit: with the sentinel set
+            // to the known best only the final positions are emitted.
+            if (isRetry) throw std::runtime_error("overflow list truncated twice");
+            std::vector<int> again;
+            long long need = 0;
+            for (int s = 0; s < J; ++s) {
+                WTask& t = tasks[slice[s]];
+                if (t.rec.cnt > KPOS) {
+                    again.push_back(slice[s]);
+                    need += t.rec.cnt - KPOS;
+                    t.kInit = t.rec.best;
+                }
+            }
+            if (need > 0x7fffffffLL / 2) throw std::runtime_error("end-location list too large");
+            run_slice(tasks, again, R, (int)need + 16, true);
+        }
+    }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// compute
+// ---------------------------------------------------------------------------------------------
+void Engine::compute(Prepared* p) {
+    Backend* be = be_;
+    be->reset_timing();
+    const int N = p->N;
+    const int mode = p->mode;
+    const int k = p->cfg.k;
+    p->ed.assign(N, -1);
+    p->special.assign(N, 0);
+    p->endStart.assign(N, 0);
+    p->endCount.assign(N, 0);
+    p->endPool.clear();
+    p->startPool.clear();
+    p->alnStart.assign(N, -1);
+    p->alnLen.assign(N, 0);
+    p->alnPool.clear();
+    stats.k1Cells = stats.wCells = 0;
+
+    // per-pair sweep outcome before the "-1" rule
+    std::vector<int> best(N, -1), cnt(N, 0);
+    std::vector<std::vector<int>> posOf;  // only filled for W-path pairs and K1 multi-chunk/overflow pairs
+    posOf.resize(N);
+
+    // ---- classification -----------------------------------------------------------------
+    std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, nw32) -> pairs
+    std::vector<int> wPairs;
+    for (int i = 0; i < N; ++i) {
+        const int m = p->qlen[i], n = p->tlen[i];
+        if (m == 0 || n == 0) {
+            p->special[i] = 1;
+            continue;
+        }
+        if (mode == MODE_NW && k >= 0 && k < abs(n - m)) continue;  // ref cpp:744
+        if (m <= 256)
+            groups[std::make_pair(p->tidx[i], ceil_div(m, 32))].push_back(i);
+        else
+            wPairs.push_back(i);
+    }
+
+    // ---- K1 groups ----------------------------------------------------------------------
+    for (auto& kv : groups) {
+        std::vector<int>& list = kv.second;
+        if ((int)list.size() < tun.k1MinGroup) {
+            wPairs.insert(wPairs.end(), list.begin(), list.end());
+            continue;
+        }
+        const int t = kv.first.first, nw = kv.first.second;
+        const Target& tg = p->tg[t];
+        const int G = (int)list.size();
+        const int n = tg.len;
+        int chunks = 1, chunkLen = (int)round_up((size_t)n, 16);
+        const int halo = 64 * nw;
+        if (mode == MODE_HW) {
+            const long long wantThreads = (long long)be->sm_count() * 2048;
+            const int minChunk = std::max(tun.k1MinChunk, 8 * halo);
+            long long c = (wantThreads + G - 1) / G;
+            c = std::min<long long>(c, n / minChunk);
+            if (c < 1) c = 1;
+            chunkLen = (int)round_up((size_t)ceil_div(n, (int)c), 16);
+            chunks = ceil_div(n, chunkLen);
+        }
+        std::vector<int> kInit(G);
+        for (int s = 0; s < G; ++s) {
+            const int m = p->qlen[list[s]];
+            kInit[s] = ((k < 0 || k > m) ? m : k) + 1;  // distances never exceed m in HW/SHW (ref cpp:566-568)
+        }
+        std::vector<Rec> recs;
+        std::vector<Ovf> ovf;
+        int ovfCap = tun.ovfCap;
+        std::vector<int> slots(G);
+        for (int s = 0; s < G; ++s) slots[s] = s;
+        auto launch = [&](const std::vector<int>& sub, const std::vector<int>& subK, int cap, std::vector<Rec>& outRecs,
+                          std::vector<Ovf>& outOvf) -> bool {
+            const int g = (int)sub.size();
+            std::vector<int> rl(g);
+            for (int s = 0; s < g; ++s) rl[s] = list[sub[s]];
+            DevBuf<int> dList(be, g), dK(be, g);
+            dList.upload(rl.data(), g);
+            dK.upload(subK.data(), g);
+            DevBuf<Rec> dRecs(be, (size_t)g * chunks);
+            be->zero(dRecs.p, (size_t)g * chunks * sizeof(Rec));
+            DevBuf<Ovf> dOvf(be, (size_t)cap);
+            DevBuf<int> dCount(be, 1);
+            be->zero(dCount.p, sizeof(int));
+            K1Params kp;
+            memset(&kp, 0, sizeof(kp));
+            kp.tcodes = p->dSeq.p + tg.off;
+            kp.n = n;
+            kp.qcodes = p->dSeq.p;
+            kp.qoff = p->dQoff.p;
+            kp.qlen = p->dQlen.p;
+            kp.readList = dList.p;
+            kp.kInit = dK.p;
+            kp.numReads = g;
+            kp.mode = mode;
+            kp.ncodes = p->ncodes;
+            kp.eqtab = p->hasEq ? p->dEqtab.p : nullptr;
+            kp.chunks = chunks;
+            kp.chunkLen = chunkLen;
+            kp.halo = halo;
+            kp.recs = dRecs.p;
+            kp.ovf = dOvf.p;
+            kp.ovfCount = dCount.p;
+            kp.ovfCap = cap;
+            be->launch_k1(kp, nw);
+            outRecs.resize((size_t)g * chunks);
+            dRecs.download(outRecs.data(), outRecs.size());
+            int count = 0;
+            dCount.download(&count, 1);
+            stats.d2hBytes += (long long)outRecs.size() * (long long)sizeof(Rec) + 4;
+            outOvf.clear();
+            if (count > cap) return false;
+            if (count > 0) {
+                outOvf.resize(count);
+                dOvf.download(outOvf.data(), count);
+                stats.d2hBytes += (long long)count * (long long)sizeof(Ovf);
+            }
+            return true;
+        };
+        bool ok = launch(slots, kInit, ovfCap, recs, ovf);
+        for (int s = 0; s < G; ++s) stats.k1Cells += (long long)p->qlen[list[s]] * n;
+
+        // merge chunks: the minimum wins; positions of the chunks attaining it, in chunk order
+        auto merge = [&](const std::vector<int>& sub, const std::vector<Rec>& rr, const std::vector<Ovf>& oo, bool haveOvf) {
+            const int g = (int)sub.size();
+            std::unordered_map<int, std::vector<int>> extra;  // rec index -> overflow positions
+            if (haveOvf)
+                for (const Ovf& o : oo)
+                    if (o.score == rr[o.rec].best) extra[o.rec].push_back(o.pos);
+            for (int s = 0; s < g; ++s) {
+                const int pair = list[sub[s]];
+                int b = 0x7fffffff;
+                long long total = 0;
+                for (int c = 0; c < chunks; ++c) {
+                    const Rec& r = rr[(size_t)c * g + s];
+                    if (r.cnt > 0 && r.best < b) {
+                        b = r.best;
+                        total = 0;
+                    }
+                    if (r.cnt > 0 && r.best == b) total += r.cnt;
+                }
+                best[pair] = (total > 0) ? b : 0x7fffffff;
+                cnt[pair] = (int)std::min<long long>(total, 0x7fffffff);
+                std::vector<int>& dst = posOf[pair];
+                dst.clear();
+                if (total == 0 || !haveOvf) continue;
+                for (int c = 0; c < chunks; ++c) {
+                    const Rec& r = rr[(size_t)c * g + s];
+                    if (r.cnt <= 0 || r.best != b) continue;
+                    for (int q = 0; q < std::min(r.cnt, KPOS); ++q) dst.push_back(r.pos[q]);
+                    if (r.cnt > KPOS) {
+                        const std::vector<int>& ex = extra[(int)((size_t)c * g + s)];
+                        dst.insert(dst.end(), ex.begin(), ex.end());
+                    }
+                }
+            }
+        };
+        merge(slots, recs, ovf, ok);
+        if (!ok) {
+            // overflow list truncated: second pass over the affected reads with exact capacity
+            std::vector<int> sub, subK;
+            long long need = 0;
+            for (int s = 0; s < G; ++s) {
+                bool big = false;
+                for (int c = 0; c < chunks; ++c) {
+                    const Rec& r = recs[(size_t)c * G + s];
+                    if (r.cnt > KPOS) {
+                        big = true;
+                        need += r.cnt - KPOS;
+                    }
+                }
+                if (big) {
+                    sub.push_back(s);
+                    subK.push_back(best[list[s]] == 0x7fffffff ? kInit[s] : best[list[s]]);
+                }
+            }
+            // reads without overflow keep their inline positions
+            std::vector<Ovf> none;
+            merge(slots, recs, none, true);
+            if (need > 0x7fffffffLL / 2) throw std::runtime_error("end-location list too large");
+            std::vector<Rec> recs2;
+            std::vector<Ovf> ovf2;
+            if (!launch(sub, subK, (int)need + 16, recs2, ovf2)) throw std::runtime_error("overflow list truncated twice");
+            merge(sub, recs2, ovf2, true);
+        }
+    }
+
+    // ---- W distance pass ------------------------------------------------------------------
+    std::vector<uint8_t> opsPool;
+    std::vector<int> colPool;
+    WRunner runner{this, be, p, &opsPool, &colPool};
+    {
+        std::vector<int> pending = wPairs;
+        int kRound = 64;  // ref cpp:201: the doubling schedule only matters for speed
+        while (!pending.empty()) {
+            std::vector<WTask> tasks;
+            std::vector<int> later;
+            for (int pair : pending) {
+                const int m = p->qlen[pair], n = p->tlen[pair];
+                int bound = -1;
+                if (mode == MODE_NW) {
+                    if (k >= 0) {
+                        bound = k;
+                    } else if (ceil_div(m, 32) > 32) {
+                        bound = kRound;
+                        if (bound < abs(n - m)) {
+                            later.push_back(pair);
+                            continue;
+                        }
+                    }
+                }
+                WPlan pl = plan_w(m, n, mode, bound);
+                WTask t;
+                t.pair = pair;
+                t.qOff = p->qoff[pair];
+                t.tOff = p->tg[p->tidx[pair]].off;
+                t.m = m;
+                t.n = n;
+                t.mode = mode;
+                t.flags = pl.slide ? WF_SLIDE : 0;
+                t.dhi = pl.dhi;
+                t.R = pl.R;
+                t.nWp = pl.nWp;
+                t.kInit = ((k < 0 || k > m) ? m : k) + 1;
+                t.tag = pl.slide ? bound : -1;  // a sliding result is only valid when <= bound
+                tasks.push_back(std::move(t));
+            }
+            runner.run(tasks);
+            for (WTask& t : tasks) {
+                stats.wCells += (long long)t.m * t.n;
+                if (t.tag >= 0 && t.rec.best > t.tag) {  // outside the band of this round
+                    if (k < 0) later.push_back(t.pair);
+                    else best[t.pair] = 0x7fffffff;
+                    continue;
+                }
+                best[t.pair] = t.rec.cnt > 0 ? t.rec.best : 0x7fffffff;
+                cnt[t.pair] = t.rec.cnt;
+                std::vector<int>& dst = posOf[t.pair];
+                dst.clear();
+                for (int q = 0; q < std::min(t.rec.cnt, KPOS); ++q) dst.push_back(t.rec.pos[q]);
+                dst.insert(dst.end(), t.extra.begin(), t.extra.end());
+            }
+            pending.swap(later);
+            if (kRound < (1 << 29)) kRound *= 2;
+        }
+    }
+
+    // ---- distances and end locations ------------------------------------------------------
+    for (int i = 0; i < N; ++i) {
+        if (p->special[i]) continue;
+        const int m = p->qlen[i], n = p->tlen[i];
+        p->endStart[i] = (long long)p->endPool.size();
+        if (best[i] < 0 || best[i] == 0x7fffffff) continue;  // rejected up front or nothing tracked
+        if (k >= 0 && best[i] > k) continue;
+        if (mode == MODE_NW) {
+            p->ed[i] = best[i];
+            p->endPool.push_back(n - 1);  // ref cpp:221-225
+            p->endCount[i] = 1;
+            continue;
+        }
+        if (best[i] > m) continue;
+        p->ed[i] = best[i];
+        // ref cpp:670, 681-693: the padded bottom cell of column W-1 shows up as end location -1
+        const int W64 = ceil_div(m, 64) * 64 - m;
+        if (best[i] == m && W64 > 0) p->endPool.push_back(-1);
+        if ((int)posOf[i].size() != cnt[i]) throw std::runtime_error("internal: end-location count mismatch");
+        p->endPool.insert(p->endPool.end(), posOf[i].begin(), posOf[i].end());
+        p->endCount[i] = (int)(p->endPool.size() - (size_t)p->endStart[i]);
+        std::vector<int>().swap(posOf[i]);
+    }
+
+    // ---- start locations (ref cpp:228-272) ------------------------------------------------
+    const bool wantLoc = p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH;
+    if (wantLoc) {
+        p->startPool.assign(p->endPool.size(), 0);
+        if (mode == MODE_HW) {
+            std::vector<WTask> tasks;
+            std::vector<long long> slotOf;
+            for (int i = 0; i < N; ++i) {
+                if (p->ed[i] < 0) continue;
+                const int m = p->qlen[i];
+                for (int q = 0; q < p->endCount[i]; ++q) {
+                    const long long slot = p->endStart[i] + q;
+                    const int e = p->endPool[(size_t)slot];
+                    if (e < 0) continue;  // ref cpp:237-249: start 0
+                    WTask t;
+                    t.pair = i;
+                    t.qOff = p->qoff[i];
+                    t.tOff = p->tg[p->tidx[i]].off + (uint64_t)e;  // first symbol read, walking backward
+                    t.m = m;
+                    t.n = (int)std::min<long long>((long long)e + 1, (long long)m + p->ed[i]);
+                    t.mode = MODE_SHW;
+                    t.flags = WF_QREV | WF_TREV;
+                    t.kInit = p->ed[i] + 1;
+                    WPlan pl = plan_w(t.m, t.n, MODE_SHW, -1);
+                    t.R = pl.R;
+                    t.nWp = pl.nWp;
+                    tasks.push_back(std::move(t));
+                    slotOf.push_back(slot);
+                }
+            }
+            runner.run(tasks);
+            for (size_t j = 0; j < tasks.size(); ++j) {
+                const WTask& t = tasks[j];
+                if (t.rec.cnt <= 0 || t.rec.best != p->ed[t.pair]) throw std::runtime_error("internal: start-location sweep disagrees");
+                const int e = p->endPool[(size_t)slotOf[j]];
+                p->startPool[(size_t)slotOf[j]] = e - t.rec.last;  // ref cpp:260
+            }
+        }
+    }
+
+    // ---- alignment path (ref cpp:276-289, 1161-1213) --------------------------------------
+    if (p->cfg.task == EDLIB_TASK_PATH) {
+        std::vector<WTask> tasks;
+        for (int i = 0; i < N; ++i) {
+            if (p->ed[i] < 0) continue;
+            const int m = p->qlen[i];
+            const int s0 = p->startPool[(size_t)p->endStart[i]], e0 = p->endPool[(size_t)p->endStart[i]];
+            const int wn = e0 - s0 + 1;
+            if (wn <= 0) {  // ref cpp:1168-1175: empty target slice -> m insertions
+                p->alnStart[i] = (long long)p->alnPool.size();
+                p->alnLen[i] = m;
+                p->alnPool.insert(p->alnPool.end(), (size_t)m, (uint8_t)EDLIB_EDOP_INSERT);
+                continue;
+            }
+            const long long matrixBytes = 20LL * ceil_div(m, 64) * wn + 8LL * wn;  // ref cpp:1188-1190
+            if (matrixBytes >= 1024 * 1024) throw std::runtime_error("PATH beyond the stored-matrix regime (Hirschberg) is not built yet");
+            WTask t;
+            t.pair = i;
+            t.qOff = p->qoff[i];
+            t.tOff = p->tg[p->tidx[i]].off + (uint64_t)s0;
+            t.m = m;
+            t.n = wn;
+            t.mode = MODE_NW;
+            t.flags = WF_STORE;
+            WPlan pl = plan_w(m, wn, MODE_NW, -1);
+            t.R = pl.R;
+            t.nWp = pl.nWp;
+            tasks.push_back(std::move(t));
+        }
+        runner.run(tasks);
+        for (const WTask& t : tasks) {
+            if (t.rec.best != p->ed[t.pair]) throw std::runtime_error("internal: path sweep disagrees with the distance");
+            p->alnStart[t.pair] = (long long)p->alnPool.size();
+            p->alnLen[t.pair] = t.opsLen;
+            p->alnPool.insert(p->alnPool.end(), opsPool.begin() + t.opsOff, opsPool.begin() + t.opsOff + t.opsLen);
+        }
+    }
+
+    be->sync();
+    stats.kernelMs = be->kernel_ms(nullptr);
+    stats.k1Ms = be->kernel_ms("k1");
+    stats.launches = be->launches();
+    p->computed = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// materialize / release / one-shot
+// ---------------------------------------------------------------------------------------------
+void Engine::materialize(Prepared* p, EdlibAlignResult* results) {
+    const int N = p->N;
+    for (int i = 0; i < N; ++i) {
+        EdlibAlignResult& r = results[i];
+        memset(&r, 0, sizeof(r));
+        r.status = EDLIB_STATUS_OK;
+        r.editDistance = -1;
+        r.alphabetLength = p->alphaLen[i];
+        const int m = p->qlen[i], n = p->tlen[i];
+        if (p->special[i]) {  // ref cpp:166-184
+            const int rawMode = (int)p->cfg.mode;
+            if (rawMode == EDLIB_MODE_NW || rawMode == EDLIB_MODE_SHW || rawMode == EDLIB_MODE_HW) {
+                r.editDistance = rawMode == EDLIB_MODE_NW ? std::max(m, n) : m;
+                r.endLocations = static_cast<int*>(malloc(sizeof(int)));
+                r.endLocations[0] = rawMode == EDLIB_MODE_NW ? n - 1 : -1;
+                r.numLocations = 1;
+            } else {
+                r.status = EDLIB_STATUS_ERROR;
+            }
+            continue;
+        }
+        if (p->ed[i] < 0) continue;
+        r.editDistance = p->ed[i];
+        const int c = p->endCount[i];
+        r.numLocations = c;
+        r.endLocations = static_cast<int*>(malloc(sizeof(int) * (size_t)std::max(c, 1)));
+        memcpy(r.endLocations, p->endPool.data() + p->endStart[i], sizeof(int) * (size_t)c);
+        if (!p->startPool.empty() || p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH) {
+            r.startLocations = static_cast<int*>(malloc(sizeof(int) * (size_t)std::max(c, 1)));
+            memcpy(r.startLocations, p->startPool.data() + p->endStart[i], sizeof(int) * (size_t)c);
+        }
+        if (p->alnStart[i] >= 0) {
+            r.alignmentLength = p->alnLen[i];
+            r.alignment = static_cast<unsigned char*>(malloc((size_t)std::max(p->alnLen[i], 1)));
+            memcpy(r.alignment, p->alnPool.data() + p->alnStart[i], (size_t)p->alnLen[i]);
+        }
+    }
+}
+
+void Engine::release(Prepared* p) { delete p; }
+
+int Engine::align_batch(const BatchInput& in, EdlibAlignResult* results) {
+    Prepared* p = nullptr;
+    stats = EngineStats();
+    try {
+        p = prepare(in);
+        compute(p);
+        materialize(p, results);
+        release(p);
+        return EDLIB_STATUS_OK;
+    } catch (const std::exception& e) {
+        lastError = e.what();
+        if (p) release(p);
+        for (int i = 0; i < in.numPairs; ++i) {
+            memset(&results[i], 0, sizeof(results[i]));
+            results[i].status = EDLIB_STATUS_ERROR;
+            results[i].editDistance = -1;
+        }
+        return EDLIB_STATUS_ERROR;
+    }
+}
+
+}  // namespace eb

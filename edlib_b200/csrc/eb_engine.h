@@ -1,0 +1,91 @@
+// eb_engine.h -- host side of the batched engine: planning, device orchestration and
+// materialisation of EdlibAlignResult.  It restates the reference DRIVER (edlibAlign,
+// ref edlib.cpp:146-301) as a batch pipeline; every DP cell is computed by the kernels in
+// eb_core.h through a Backend.  The only Backend in the product library is the CUDA one
+// (eb_kernels.cu); there is no CPU compute path.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/edlib.h"
+#include "eb_common.h"
+
+namespace eb {
+
+// Device services + kernel launches.  All pointers handed to launch_* are device pointers.
+struct Backend {
+    virtual ~Backend() {}
+    virtual void* alloc(size_t bytes) = 0;  // >= 256-byte aligned; throws on failure
+    virtual void free(void* p) = 0;
+    virtual void* alloc_host(size_t bytes) = 0;  // staging memory (pinned on CUDA)
+    virtual void free_host(void* p) = 0;
+    virtual void h2d(void* dst, const void* src, size_t bytes) = 0;
+    virtual void d2h(void* dst, const void* src, size_t bytes) = 0;  // synchronising
+    virtual void zero(void* dst, size_t bytes) = 0;
+    virtual void sync() = 0;
+    virtual int sm_count() = 0;
+    virtual void launch_mask(const MaskParams& p) = 0;
+    virtual void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int numPairs, int* out) = 0;
+    virtual void launch_encode(const EncodeParams& p) = 0;
+    virtual void launch_k1(const K1Params& p, int nw32) = 0;
+    virtual void launch_peq(const PeqParams& p) = 0;
+    virtual void launch_w(const WParams& p, int R) = 0;
+    virtual void launch_traceback(const TbParams& p) = 0;
+    // timing of the launches issued since the last reset (device time, ms) and their count
+    virtual void reset_timing() = 0;
+    virtual double kernel_ms(const char* nameOrNull) = 0;
+    virtual int launches() = 0;
+};
+
+struct BatchInput {
+    const char* const* queries;
+    const int* queryLengths;
+    const char* const* targets;
+    const int* targetLengths;
+    int numPairs;
+    EdlibAlignConfig config;
+};
+
+struct EngineTunables {
+    int k1MinGroup = 32;          // pairs sharing one target before the lane-per-alignment kernel is used
+    int k1MinChunk = 8192;        // smallest target chunk (columns) when one HW sweep is split
+    int ovfCap = 1 << 20;         // overflow entries per launch before the exact-size retry
+    size_t sliceBytes = 1ull << 30;  // device memory budget of one slice of W jobs
+    EngineTunables();             // reads EDLIB_B200_* environment overrides (used by tests)
+};
+
+struct EngineStats {
+    double kernelMs = 0;   // device time of all launches of the last compute()
+    double k1Ms = 0;       // ... of the K1 launches alone
+    int launches = 0;
+    long long h2dBytes = 0, d2hBytes = 0;
+    long long k1Cells = 0;  // nominal cells (sum m*n) handled by K1
+    long long wCells = 0;   // nominal cells of the distance pass handled by W
+};
+
+class Prepared;  // a batch whose inputs are resident on the device
+
+class Engine {
+public:
+    explicit Engine(Backend* be) : be_(be) {}
+    // One-shot: prepare + compute + materialise.  Returns EDLIB_STATUS_OK / EDLIB_STATUS_ERROR.
+    int align_batch(const BatchInput& in, EdlibAlignResult* results);
+
+    // Staged form (bench "inputs resident in HBM" measurement, multi-GPU shards):
+    Prepared* prepare(const BatchInput& in);                 // upload, alphabet, encode
+    void compute(Prepared* p);                               // every kernel; records come back to the host
+    void materialize(Prepared* p, EdlibAlignResult* results);  // malloc the per-pair arrays
+    void release(Prepared* p);
+
+    EngineTunables tun;
+    EngineStats stats;
+    std::string lastError;
+
+private:
+    Backend* be_;
+};
+
+}  // namespace eb

@@ -1,0 +1,58 @@
+/*
+ * edlib_b200.h -- engine-specific additions to the edlib C ABI (plain C, no CUDA or torch
+ * types).  Nothing here exists in the reference; the reference-facing surface is edlib.h.
+ *
+ * The staged calls split edlibAlignBatch() into its three phases so that a caller (bench.py,
+ * a multi-GPU driver running one process per device) can keep a batch resident in HBM and
+ * time the device work alone:
+ *
+ *     b = edlibB200BatchPrepare(...)    pack + upload + alphabet/encoding kernels
+ *     edlibB200BatchCompute(b, &st)     every DP kernel; may be repeated on the same batch
+ *     edlibB200BatchResults(b, res)     malloc'd EdlibAlignResult per pair (as edlibAlignBatch)
+ *     edlibB200BatchFree(b)
+ *
+ * All calls use the CUDA device that is current for the calling thread at the first call
+ * (cudaSetDevice / torch.cuda.set_device before it); one process drives one GPU.
+ */
+#ifndef EDLIB_B200_H
+#define EDLIB_B200_H
+
+#include "edlib.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct EdlibB200Batch EdlibB200Batch; /* opaque */
+
+typedef struct {
+    double kernelMs;      /* device time of all kernel launches of the last compute (CUDA events) */
+    double k1Ms;          /* ... of the lane-per-alignment sweep kernel alone */
+    int launches;         /* kernel launches of the last compute */
+    int reserved;
+    long long h2dBytes;   /* host->device bytes since the batch was prepared */
+    long long d2hBytes;   /* device->host bytes */
+    long long k1Cells;    /* nominal DP cells (sum queryLength*targetLength) swept by that kernel */
+    long long wCells;     /* nominal DP cells of the distance pass swept by the warp kernel */
+} EdlibB200Stats;
+
+/* 1 when a CUDA device and the kernels are usable, else 0 (then every align call fails). */
+EDLIB_API int edlibB200Available(void);
+
+/* Text of the last engine error on this process (valid until the next call). */
+EDLIB_API const char* edlibB200LastError(void);
+
+EDLIB_API EdlibB200Batch* edlibB200BatchPrepare(const char* const* queries, const int* queryLengths,
+                                                const char* const* targets, const int* targetLengths,
+                                                int numPairs, const EdlibAlignConfig config);
+EDLIB_API int edlibB200BatchCompute(EdlibB200Batch* batch, EdlibB200Stats* statsOut);
+EDLIB_API int edlibB200BatchResults(EdlibB200Batch* batch, EdlibAlignResult* results);
+EDLIB_API void edlibB200BatchFree(EdlibB200Batch* batch);
+
+/* Stats of the most recent edlibAlign / edlibAlignBatch / BatchCompute on this process. */
+EDLIB_API void edlibB200LastStats(EdlibB200Stats* statsOut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDLIB_B200_H */

@@ -1,0 +1,130 @@
+// TEST INFRASTRUCTURE -- host SIMT emulation of the kernels (NOT a product path).
+//
+// Implements eb::Backend by running the very same kernel bodies (edlib_b200/csrc/eb_core.h)
+// that eb_kernels.cu launches on the GPU: per-thread bodies in plain loops, warp bodies on the
+// 32-wide vector backend of host_warp.h.  Linked with eb_engine.cpp + eb_capi.cpp into
+// tests/emul/libedlib_emul.so, it lets the CPU test-suite check the kernel logic and the host
+// planner against the reference build without a GPU.  The product library never contains it.
+#include <stdlib.h>
+#include <string.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "eb_core.h"
+#include "eb_engine.h"
+#include "host_warp.h"
+
+namespace ebhost {
+template <int R>
+void HostWarp::dump_column(int* out, const U (&Pv)[R], const U (&Mv)[R], const U& sb, int topChunk, int, int off, int m) {
+    for (int l = 0; l < 32; ++l) {
+        uint32_t pv[R], mv[R];
+        for (int i = 0; i < R; ++i) {
+            pv[i] = Pv[i].x[l];
+            mv[i] = Mv[i].x[l];
+        }
+        eb::dump_chunk_scores<R>(out, pv, mv, sb.x[l], topChunk + l, off, m);
+    }
+}
+}  // namespace ebhost
+
+namespace {
+
+using namespace eb;
+
+// Peq rows of one emulated K1 thread: plain array [code][word].
+template <int NW>
+struct HostPeqAcc {
+    std::vector<uint32_t> w;
+    void store(int code, int word, uint32_t bits) { w[(size_t)code * NW + word] = bits; }
+    void load(uint32_t code, uint32_t (&Eq)[NW]) const {
+        for (int i = 0; i < NW; ++i) Eq[i] = w[(size_t)code * NW + i];
+    }
+};
+
+template <int NW>
+void emul_k1(const K1Params& p) {
+    HostPeqAcc<NW> acc;
+    acc.w.assign((size_t)p.ncodes * NW, 0);
+    for (int chunk = 0; chunk < p.chunks; ++chunk)
+        for (int slot = 0; slot < p.numReads; ++slot) k1_thread<NW>(p, slot, chunk, acc);
+}
+
+struct EmulBackend : Backend {
+    int launchesCount = 0;
+    void* alloc(size_t bytes) override {
+        void* p = nullptr;
+        if (posix_memalign(&p, 256, bytes ? bytes : 1)) throw std::runtime_error("emul alloc failed");
+        memset(p, 0xA5, bytes);  // poison: device memory is never implicitly zero
+        return p;
+    }
+    void free(void* p) override { ::free(p); }
+    void* alloc_host(size_t bytes) override { return malloc(bytes ? bytes : 1); }
+    void free_host(void* p) override { ::free(p); }
+    void h2d(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
+    void d2h(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
+    void zero(void* d, size_t n) override { memset(d, 0, n); }
+    void sync() override {}
+    int sm_count() override {
+        const char* s = getenv("EDLIB_EMUL_SMS");
+        return s ? atoi(s) : 2;
+    }
+    void launch_mask(const MaskParams& p) override {
+        ++launchesCount;
+        for (int i = 0; i < p.numItems; ++i) mask_item(p, i, 0, 1);
+    }
+    void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int n, int* out) override {
+        ++launchesCount;
+        for (int i = 0; i < n; ++i) out[i] = alpha_len_pair(masks, qset ? qset[i] : i, tset[i]);
+    }
+    void launch_encode(const EncodeParams& p) override {
+        ++launchesCount;
+        for (uint64_t i = 0; i < p.numBytes; ++i) p.data[i] = p.map[p.data[i]];
+    }
+    void launch_k1(const K1Params& p, int nw) override {
+        ++launchesCount;
+        switch (nw) {
+            case 1: emul_k1<1>(p); break;
+            case 2: emul_k1<2>(p); break;
+            case 3: emul_k1<3>(p); break;
+            case 4: emul_k1<4>(p); break;
+            case 5: emul_k1<5>(p); break;
+            case 6: emul_k1<6>(p); break;
+            case 7: emul_k1<7>(p); break;
+            case 8: emul_k1<8>(p); break;
+            default: throw std::runtime_error("bad K1 word class");
+        }
+    }
+    void launch_peq(const PeqParams& p) override {
+        ++launchesCount;
+        for (int j = 0; j < p.numJobs; ++j)
+            for (int lane = 0; lane < 32; ++lane) peq_build_words(p, j, lane, 32);
+    }
+    void launch_w(const WParams& p, int R) override {
+        ++launchesCount;
+        for (int j = 0; j < p.numJobs; ++j) {
+            switch (R) {
+                case 1: w_sweep<ebhost::HostWarp, 1>(p, j); break;
+                case 2: w_sweep<ebhost::HostWarp, 2>(p, j); break;
+                case 4: w_sweep<ebhost::HostWarp, 4>(p, j); break;
+                case 8: w_sweep<ebhost::HostWarp, 8>(p, j); break;
+                default: throw std::runtime_error("bad W chunk size");
+            }
+        }
+    }
+    void launch_traceback(const TbParams& p) override {
+        ++launchesCount;
+        for (int j = 0; j < p.numJobs; ++j) traceback_job(p, j);
+    }
+    void reset_timing() override { launchesCount = 0; }
+    double kernel_ms(const char*) override { return 0.0; }
+    int launches() override { return launchesCount; }
+};
+
+}  // namespace
+
+namespace eb {
+Backend* create_backend(std::string*) { return new EmulBackend(); }
+}  // namespace eb
