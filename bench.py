@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the batched edit-distance hot path.
+
+Workload at N GPUs (weak scaling): BASELINE.json configs[1] per GPU -- 1,000,000 x 150 bp DNA reads
+(3 % sub/ins/del) aligned HW (infix), EDLIB_TASK_DISTANCE, k = -1, to ONE shared 5,000,000 bp target;
+synthetic, seeded (edlib_b200/workloads.py).  One "step" = one pass of the hot path over the batch.
+
+  value   nominal GCUPS  = sum(queryLength * targetLength) / time / 1e9 over all ranks, with the batch
+          already resident in HBM (edlibB200BatchCompute: every kernel + the device->host read of the
+          result records), wall time bracketed by barrier + synchronize, max over ranks.
+  e2e     same metric through the reference-facing call edlibAlignBatch() with HOST buffers
+          (pack + H2D + kernels + D2H + per-result malloc inside the timed region).
+  roofline  dominant kernel (k1_kernel) algorithmic bytes / its CUDA-event time, against the measured
+          HBM peak in MEASURED_PEAKS.json.  The path is integer-issue bound, so the second
+          figure `int_lane_ops_per_s` is reported next to it.
+  cpu_baseline  the reference build (oracle/_ref) timed on this box's host cores on a bounded sample.
+
+`--impl reference` times the reference's own CPU implementation instead (same metric and config).
+Multi-GPU: launched by torchrun, one rank per GPU; the shared target is NCCL-broadcast from rank 0, every
+rank aligns its own shard of reads, the per-read distances are gathered on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from edlib_b200 import workloads  # noqa: E402
+from edlib_b200._ffi import AlignConfig, AlignResult, EdlibLib, make_config, product_path  # noqa: E402
+
+READ_LEN = 150
+TARGET_LEN = 5_000_000
+MODE_HW, TASK_DISTANCE = 2, 0
+
+
+class Stats(C.Structure):  # include/edlib_b200.h EdlibB200Stats
+    _fields_ = [("kernelMs", C.c_double), ("k1Ms", C.c_double), ("launches", C.c_int), ("reserved", C.c_int),
+                ("h2dBytes", C.c_longlong), ("d2hBytes", C.c_longlong), ("k1Cells", C.c_longlong),
+                ("wCells", C.c_longlong)]
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_sample(target_bytes, reads, seconds_goal, threads):
+    """Times the reference build's edlibAlign (oracle/_ref) on the first S reads of the batch with one
+    Python thread per host core (ctypes releases the GIL during the call).  Returns (gcups, S, wall)."""
+    from concurrent.futures import ThreadPoolExecutor
+    ref_so = os.path.join(REPO, "oracle", "_ref", "libedlib_ref.so")
+    kind = "reference"
+    if os.path.exists(ref_so):
+        lib = EdlibLib(ref_so, prefix="edlib")
+    else:  # the restated algorithm (oracle port) when the reference build did not travel
+        lib = EdlibLib(os.path.join(REPO, "oracle", "liboracle.so"), prefix="oracle")
+        kind = "port"
+    cfg, _ = make_config(-1, MODE_HW, TASK_DISTANCE)
+    n = len(target_bytes)
+
+    def one(i):
+        r = lib.align_raw(reads[i].tobytes(), target_bytes, cfg)
+        ed = r.editDistance
+        lib.free(r)
+        return ed
+
+    with ThreadPoolExecutor(threads) as ex:
+        t0 = time.time()
+        list(ex.map(one, range(threads)))  # calibration: one read per thread
+        per = max(time.time() - t0, 1e-3)
+        sample = int(min(len(reads), max(threads, seconds_goal / per * threads)))
+        t0 = time.time()
+        eds = list(ex.map(one, range(sample)))
+        wall = time.time() - t0
+    gcups = sample * READ_LEN * n / wall / 1e9
+    return gcups, sample, wall, kind, eds
+
+
+def pointer_arrays(reads, target):
+    n = reads.shape[0]
+    qptr = (reads.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(reads.shape[1])).astype(np.uint64)
+    qlen = np.full(n, reads.shape[1], dtype=np.int32)
+    tptr = np.full(n, target.ctypes.data, dtype=np.uint64)
+    tlen = np.full(n, target.shape[0], dtype=np.int32)
+    return qptr, qlen, tptr, tlen
+
+
+def as_pp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_char_p))
+
+
+def as_pi(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+RESULT_DTYPE = np.dtype([("status", "<i4"), ("editDistance", "<i4"), ("endLocations", "<u8"), ("startLocations", "<u8"),
+                         ("numLocations", "<i4"), ("pad0", "<i4"), ("alignment", "<u8"), ("alignmentLength", "<i4"),
+                         ("alphabetLength", "<i4")])
+assert RESULT_DTYPE.itemsize == 48
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = host_threads()
+    target, reads = workloads.reads_vs_target(min(args.reads, 200_000), READ_LEN, TARGET_LEN, seed=42)
+    tb = target.tobytes()
+    per_step_goal = 6.0
+    times, samples = [], []
+    kind = "reference"
+    for step in range(args.warmup + args.steps):
+        g, s, wall, kind, _ = cpu_reference_sample(tb, reads, per_step_goal, threads)
+        if step >= args.warmup:
+            times.append(wall)
+            samples.append(s)
+    cells = sum(samples) * READ_LEN * TARGET_LEN
+    total = sum(times)
+    value = cells / total / 1e9
+    line = {
+        "impl": "reference", "metric": "GCUPS", "value": value, "unit": "GCUPS (nominal cells/s / 1e9)",
+        "alignments_per_s": sum(samples) / total, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[1]: %d bp reads HW distance k=-1 vs one %d bp target; each step = bounded sample of "
+                               "%d reads of the same batch on %d host threads" % (READ_LEN, TARGET_LEN, samples[-1], threads)},
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": threads, "kind": kind,
+                         "sample": "%d reads per step x %d steps" % (samples[-1], args.steps)},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU (default: the named config)")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = EdlibLib(product_path(), has_batch=True)
+    L = lib.lib
+    L.edlibB200SetDevice.argtypes = [C.c_int]
+    assert L.edlibB200SetDevice(local_rank) == 0
+    assert L.edlibB200Available() == 1, "CUDA path unavailable"
+    L.edlibB200BatchPrepare.restype = C.c_void_p
+    L.edlibB200BatchPrepare.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_int),
+                                        C.c_int, AlignConfig]
+    L.edlibB200BatchCompute.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.edlibB200BatchResults.argtypes = [C.c_void_p, C.c_void_p]
+    L.edlibB200BatchFree.argtypes = [C.c_void_p]
+    L.edlibB200FreeResults.argtypes = [C.c_void_p, C.c_int]
+    L.edlibB200LastStats.argtypes = [C.POINTER(Stats)]
+    L.edlibB200LastError.restype = C.c_char_p
+
+    # ---- workload: shared target from rank 0 (one NCCL broadcast), own shard of reads per rank ----
+    n_reads = args.reads
+    if rank == 0:
+        target = workloads.random_dna(TARGET_LEN, 1)
+    else:
+        target = np.empty(TARGET_LEN, dtype=np.uint8)
+    if world > 1:
+        tt = torch.from_numpy(target).to(dev)
+        dist.broadcast(tt, src=0)
+        target = tt.cpu().numpy()
+    reads = np.empty((n_reads, READ_LEN), dtype=np.uint8)
+    workloads._synth().synth_reads(target.ctypes.data, TARGET_LEN, reads.ctypes.data, n_reads, READ_LEN, 0.03, 42 + rank)
+    qptr, qlen, tptr, tlen = pointer_arrays(reads, target)
+    cfg, _ = make_config(-1, MODE_HW, TASK_DISTANCE)
+    cells_rank = float(n_reads) * READ_LEN * TARGET_LEN
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    # ---- value: batch resident in HBM ---------------------------------------------------------------
+    batch = L.edlibB200BatchPrepare(as_pp(qptr), as_pi(qlen), as_pp(tptr), as_pi(tlen), n_reads, cfg)
+    assert batch, L.edlibB200LastError()
+    st = Stats()
+    for _ in range(args.warmup):
+        flush_l2()
+        assert L.edlibB200BatchCompute(batch, C.byref(st)) == 0, L.edlibB200LastError()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    k1_ms, kernel_ms, launches, step_s = [], [], 0, []
+    for _ in range(args.steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        assert L.edlibB200BatchCompute(batch, C.byref(st)) == 0, L.edlibB200LastError()
+        torch.cuda.synchronize()
+        step_s.append(time.perf_counter() - t0)
+        k1_ms.append(st.k1Ms)
+        kernel_ms.append(st.kernelMs)
+        launches += st.launches
+    barrier()
+    clocks = sampler.stop()
+    elapsed = torch.tensor([sum(step_s)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed = float(elapsed.item())
+
+    # results of the resident batch (also the gather of per-read distances to rank 0)
+    res = np.zeros(n_reads, dtype=RESULT_DTYPE)
+    assert L.edlibB200BatchResults(batch, res.ctypes.data) == 0
+    eds = res["editDistance"].copy()
+    nloc = res["numLocations"].copy()
+    assert (res["status"] == 0).all()
+    L.edlibB200FreeResults(res.ctypes.data, n_reads)
+    L.edlibB200BatchFree(batch)
+    if world > 1:
+        mine = torch.from_numpy(eds).to(dev)
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+
+    # ---- e2e: reference-facing call with host buffers ------------------------------------------------
+    e2e_s, h2d, d2h = [], 0, 0
+    for it in range(1 + args.e2e_steps):  # one untimed warm-up
+        res = np.zeros(n_reads, dtype=RESULT_DTYPE)
+        barrier()
+        t0 = time.perf_counter()
+        rc = L.edlibAlignBatch(as_pp(qptr), as_pi(qlen), as_pp(tptr), as_pi(tlen), n_reads, cfg,
+                               C.cast(res.ctypes.data, C.POINTER(AlignResult)))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert rc == 0 and (res["editDistance"] == eds).all()
+        L.edlibB200LastStats(C.byref(st))
+        h2d, d2h = st.h2dBytes, st.d2hBytes
+        L.edlibB200FreeResults(res.ctypes.data, n_reads)
+        if it > 0:
+            e2e_s.append(dt)
+    e2e_t = torch.tensor([sum(e2e_s)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * cells_rank * args.e2e_steps / float(e2e_t.item()) / 1e9
+
+    # ---- CPU baseline (rank 0, N = 1 only) and parity of the sample -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        g, sample, wall, kind, ref_eds = cpu_reference_sample(target.tobytes(), reads, args.cpu_seconds, threads)
+        assert list(eds[:sample]) == ref_eds, "GPU distances differ from the reference on the CPU sample"
+        cpu = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind,
+               "sample": "first %d reads of the batch, %.1f s wall, bit-exact vs GPU" % (sample, wall)}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = world * cells_rank * args.steps / elapsed / 1e9
+        # algorithmic bytes of the dominant kernel per launch: every alignment consumes its
+        # query and its whole target, and writes editDistance, numLocations and its end locations
+        bytes_alg = float(n_reads) * (READ_LEN + TARGET_LEN + 8) + 4.0 * float(nloc.sum())
+        k1 = float(np.mean(k1_ms)) / 1000.0
+        achieved = bytes_alg / k1 / 1e9
+        # integer work actually issued: 5 x 32-bit words per column, ~10 lane-ops per word
+        lane_ops = float(n_reads) * TARGET_LEN * 5 * 10
+        line = {
+            "metric": "GCUPS", "value": value, "unit": "GCUPS (nominal cells/s / 1e9)",
+            "alignments_per_s": world * n_reads * args.steps / elapsed,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d x %d bp reads (3%% sub/ins/del), HW, EDLIB_TASK_DISTANCE, k=-1, vs one "
+                                   "%d bp target, per GPU" % (n_reads, READ_LEN, TARGET_LEN),
+                       "l2": "256 MiB write between steps (reads 150 MB > L2; the 5 MB target is meant to stay L2-resident)",
+                       "parallelism": "reads sharded over %d rank(s); target broadcast once" % world},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k1_kernel<5,HW>", "kernel_ms": k1 * 1000.0,
+                         "bytes_algorithmic": bytes_alg, "int_lane_ops_per_s": lane_ops / k1,
+                         "note": "integer-issue bound (see DESIGN.md): HBM fraction is low by construction"},
+            "cpu_baseline": cpu,
+            "mean_edit_distance": float(eds.mean()), "mean_num_locations": float(nloc.mean()),
+            "kernel_ms_per_step": float(np.mean(kernel_ms)),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

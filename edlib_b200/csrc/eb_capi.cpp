@@ -16,6 +16,7 @@
 
 namespace eb {
 Backend* create_backend(std::string* err);  // provided by the backend object linked into this library
+int select_device(int device, std::string* err);  // 0 on success
 }
 
 namespace {
@@ -128,6 +129,23 @@ EDLIB_API const char* edlibB200LastError(void) {
     static std::string copy;
     copy = g_engine ? g_engine->lastError : g_initError;
     return copy.c_str();
+}
+
+EDLIB_API int edlibB200SetDevice(int device) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_initTried) return EDLIB_STATUS_ERROR;
+    return eb::select_device(device, &g_initError) == 0 ? EDLIB_STATUS_OK : EDLIB_STATUS_ERROR;
+}
+
+EDLIB_API void edlibB200FreeResults(EdlibAlignResult* results, int n) {
+    if (!results) return;
+    for (int i = 0; i < n; ++i) {
+        free(results[i].endLocations);
+        free(results[i].startLocations);
+        free(results[i].alignment);
+        results[i].endLocations = results[i].startLocations = NULL;
+        results[i].alignment = NULL;
+    }
 }
 
 EDLIB_API int edlibB200Available(void) {

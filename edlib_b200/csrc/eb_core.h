@@ -202,9 +202,9 @@ EB_HD void k1_init(K1State<NW>& st, int m, int kInit) {
 
 // Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
 template <int NW>
-EB_HD void k1_event(K1State<NW>& st, int column, Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
-    if (st.score < st.best) {
-        st.best = st.score;
+EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
+    if (score < st.best) {
+        st.best = score;
         st.cnt = 0;
     }
     if (st.cnt < KPOS) {
@@ -213,7 +213,7 @@ EB_HD void k1_event(K1State<NW>& st, int column, Rec* rec, int recIdx, Ovf* ovf,
         const int slot = atomic_add_int(ovfCount, 1);
         if (slot < ovfCap) {
             ovf[slot].rec = recIdx;
-            ovf[slot].score = st.score;
+            ovf[slot].score = score;
             ovf[slot].pos = column;
         }
     }
@@ -221,37 +221,57 @@ EB_HD void k1_event(K1State<NW>& st, int column, Rec* rec, int recIdx, Ovf* ovf,
     st.cnt++;
 }
 
+// Target symbols addressed through a plain pointer (host emulation; any directly addressable
+// target).  The device kernel substitutes a reader over its shared-memory tile.
+struct PtrSyms {
+    const uint8_t* p;
+    EB_HD bool aligned4(int i) const { return (((uintptr_t)(p + i)) & 3u) == 0; }
+    EB_HD uint32_t read1(int i) const { return p[i]; }
+    EB_HD uint32_t read4(int i) const { return *reinterpret_cast<const uint32_t*>(p + i); }
+};
+
 // Sweeps `count` consecutive target symbols starting at absolute column cAbs.  `Acc` hands out
-// the Eq words of a symbol (shared memory on the device).  With TRACK the running minimum and
-// its columns are recorded; without it only the state advances (halo columns of a chunk).
-template <int NW, bool TOP_ONE, bool TRACK, class Acc>
-EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const uint8_t* syms, int count, int cAbs,
+// the Eq words of a symbol (shared memory on the device), `Syms` the symbols.  With TRACK the
+// running minimum and its columns are recorded; without it only the state advances (halo
+// columns of a chunk).  Columns go four at a time: the four last-row scores stay in registers
+// and are compared against the running minimum once per group (events are rare).
+template <int NW, bool TOP_ONE, bool TRACK, class Acc, class Syms>
+EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int count, int cAbs,
                       Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     int i = 0;
-    // head: until the symbol pointer is 4-byte aligned
-    while (i < count && ((uintptr_t)(syms + i) & 3u)) {
+    while (i < count && !syms.aligned4(i)) {  // head: until the symbols are 4-byte aligned
         uint32_t Eq[NW];
-        acc.load(syms[i], Eq);
+        acc.load(syms.read1(i), Eq);
         k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
-        if (TRACK && st.score <= st.best) k1_event<NW>(st, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+        if (TRACK && st.score <= st.best) k1_event<NW>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
         ++i;
     }
-    // body: four symbols per 32-bit read
-    for (; i + 4 <= count; i += 4) {
-        const uint32_t four = *reinterpret_cast<const uint32_t*>(syms + i);
+    for (; i + 4 <= count; i += 4) {  // body: four symbols per 32-bit read
+        const uint32_t four = syms.read4(i);
+        int sc[4];
         EB_UNROLL
         for (int j = 0; j < 4; ++j) {
             uint32_t Eq[NW];
             acc.load((four >> (8 * j)) & 0xffu, Eq);
             k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
-            if (TRACK && st.score <= st.best) k1_event<NW>(st, cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
+            sc[j] = st.score;
+        }
+        if (TRACK) {
+            int lo = sc[0] < sc[1] ? sc[0] : sc[1];
+            const int lo2 = sc[2] < sc[3] ? sc[2] : sc[3];
+            lo = lo < lo2 ? lo : lo2;
+            if (lo <= st.best) {
+                EB_UNROLL
+                for (int j = 0; j < 4; ++j)
+                    if (sc[j] <= st.best) k1_event<NW>(st, sc[j], cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
+            }
         }
     }
-    for (; i < count; ++i) {
+    for (; i < count; ++i) {  // tail
         uint32_t Eq[NW];
-        acc.load(syms[i], Eq);
+        acc.load(syms.read1(i), Eq);
         k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
-        if (TRACK && st.score <= st.best) k1_event<NW>(st, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+        if (TRACK && st.score <= st.best) k1_event<NW>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
     }
 }
 
@@ -313,12 +333,12 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     k1_init<NW>(st, m, p.kInit[slot]);
     const K1Chunk g = k1_chunk(p, chunk);
     if (p.mode == MODE_HW) {
-        k1_columns<NW, false, false>(st, acc, p.tcodes + g.hs, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_columns<NW, false, true>(st, acc, p.tcodes + g.cs, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_SHW) {
-        k1_columns<NW, true, true>(st, acc, p.tcodes + g.cs, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else {
-        k1_columns<NW, true, false>(st, acc, p.tcodes + g.cs, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, true, false>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
         st.best = st.score;  // NW: the bottom-right cell (ref cpp:916)
         st.cnt = 1;
         rec->last = p.n - 1;

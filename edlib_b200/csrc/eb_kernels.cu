@@ -1,0 +1,514 @@
+// eb_kernels.cu -- sm_100a kernels and the CUDA Backend of the engine.
+//
+//   k1_kernel<NW,MODE>  lane-per-alignment Myers sweep over one shared target (the hot path):
+//                       query bit-vectors in registers, per-thread Peq rows in shared memory,
+//                       the target streamed HBM/L2 -> shared memory by 1-D TMA bulk copies
+//                       (cp.async.bulk + mbarrier, double buffered) and consumed by every
+//                       thread of the CTA as 32-bit broadcast reads.
+//   w_kernel<R>         warp-per-alignment sweep (long queries, per-pair targets, band, strips)
+//   peq_kernel, traceback_kernel, mask_kernel, alpha_len_kernel, encode_kernel
+//
+// The bodies live in eb_core.h (shared with the host emulation used by the CPU tests).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "eb_core.h"
+#include "eb_engine.h"
+
+namespace eb {
+
+// ---------------------------------------------------------------------------------------------
+// Device warp backend for w_sweep
+// ---------------------------------------------------------------------------------------------
+// (Members are __host__ __device__ only because w_sweep is; the host bodies are never run.)
+#if defined(__CUDA_ARCH__)
+#define EB_DEV(expr, fallback) expr
+#else
+#define EB_DEV(expr, fallback) fallback
+#endif
+struct DevWarp {
+    using U = uint32_t;
+    using P = bool;
+    static constexpr unsigned FULL = 0xffffffffu;
+    static EB_HD U lane() { return EB_DEV(threadIdx.x & 31u, 0u); }
+    template <class F>
+    static EB_HD U map(U a, F f) { return f(a); }
+    static EB_HD U sel(P p, U a, U b) { return p ? a : b; }
+    static EB_HD U toU(P p) { return p ? 1u : 0u; }
+    static EB_HD uint32_t ballot(P p) { return EB_DEV(__ballot_sync(FULL, p), (uint32_t)p); }
+    static EB_HD bool any(P p) { return EB_DEV(__any_sync(FULL, p) != 0, p); }
+    static EB_HD U shfl_up1(U a) { return EB_DEV(__shfl_up_sync(FULL, a, 1), a); }
+    static EB_HD U shfl_down1(U a) { return EB_DEV(__shfl_down_sync(FULL, a, 1), a); }
+    static EB_HD uint32_t bcast(U a, int src) { return EB_DEV(__shfl_sync(FULL, a, src), a + 0u * (uint32_t)src); }
+    static EB_HD U gather8(const uint8_t* base, U idx, P ok) { return ok ? (U)base[idx] : 0u; }
+    static EB_HD U gather8_neg(const uint8_t* base, U idx, P ok) { return ok ? (U) * (base - (ptrdiff_t)idx) : 0u; }
+    static EB_HD U gather32(const uint32_t* base, U idx, P ok) { return ok ? EB_DEV(__ldg(base + idx), base[idx]) : 0u; }
+    static EB_HD void scatterU2(U2* base, U idx, U a, U b, P ok) {
+        if (ok) {
+            U2 v;
+            v.x = a;
+            v.y = b;
+            *reinterpret_cast<uint2*>(base + idx) = *reinterpret_cast<uint2*>(&v);
+        }
+    }
+    static EB_HD void scatter8(uint8_t* base, U idx, U v, P ok) {
+        if (ok) base[idx] = (uint8_t)v;
+    }
+    static EB_HD void store_uniform(int* p, int v) {
+        if (lane() == 0) *p = v;
+    }
+    static EB_HD int atomic_add_uniform(int* p, int v) {
+        int r = 0;
+        if (lane() == 0) r = atomic_add_int(p, v);
+        return (int)bcast((U)r, 0);
+    }
+    template <int R>
+    static EB_HD void dump_column(int* out, const U (&Pv)[R], const U (&Mv)[R], U sb, int topChunk, int, int off, int m) {
+        dump_chunk_scores<R>(out, Pv, Mv, sb, topChunk + (int)lane(), off, m);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------
+constexpr int K1_TILE = 4096;  // target bytes per shared-memory stage (two stages)
+
+// Per-thread Peq rows in shared memory, addressed with explicit 32-bit shared addresses so the
+// inner loop is LDS with register+immediate addressing and no generic-address arithmetic.
+// Region of one code: [ A: nthreads x 16 B (words 0..3, one LDS.128) | B: nthreads x 4*(NW-4) B
+// (words 4.., contiguous per thread) ].  Consecutive threads touch consecutive 16 B slots of A
+// and slots of 4/8/12/16 B of B: both patterns are bank-conflict free.
+template <int NW>
+struct SmemPeqAcc {
+    static constexpr int NWB = NW > 4 ? NW - 4 : 0;
+    uint32_t a0;          // shared address of this thread's A slot for code 0
+    uint32_t b0;          // shared address of this thread's B slot for code 0
+    uint32_t codeStride;  // bytes per code region
+    EB_D void store(int code, int w, uint32_t bits) {
+        const uint32_t addr = (w < 4 ? a0 + 4u * w : b0 + 4u * (w - 4)) + (uint32_t)code * codeStride;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+    }
+    EB_D void load(uint32_t code, uint32_t (&Eq)[NW]) const {
+        const uint32_t off = code * codeStride;
+        uint32_t x, y, z, w;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a0 + off));
+        Eq[0] = x;
+        if (NW > 1) Eq[NW > 1 ? 1 : 0] = y;
+        if (NW > 2) Eq[NW > 2 ? 2 : 0] = z;
+        if (NW > 3) Eq[NW > 3 ? 3 : 0] = w;
+        if (NWB == 1) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq[NW > 4 ? 4 : 0]) : "r"(b0 + off));
+        } else if (NWB == 2) {
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(Eq[NW > 4 ? 4 : 0]), "=r"(Eq[NW > 5 ? 5 : 0]) : "r"(b0 + off));
+        } else if (NWB == 3) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq[NW > 4 ? 4 : 0]) : "r"(b0 + off));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(Eq[NW > 5 ? 5 : 0]) : "r"(b0 + off));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(Eq[NW > 6 ? 6 : 0]) : "r"(b0 + off));
+        } else if (NWB == 4) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(Eq[NW > 4 ? 4 : 0]), "=r"(Eq[NW > 5 ? 5 : 0]), "=r"(Eq[NW > 6 ? 6 : 0]), "=r"(Eq[NW > 7 ? 7 : 0])
+                         : "r"(b0 + off));
+        }
+    }
+};
+
+// Target symbols of the current tile, read as warp-uniform (broadcast) shared loads.
+struct SmemSyms {
+    uint32_t addr;  // shared address of the first symbol
+    EB_D bool aligned4(int i) const { return ((addr + (uint32_t)i) & 3u) == 0; }
+    EB_D uint32_t read1(int i) const {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr + (uint32_t)i));
+        return v;
+    }
+    EB_D uint32_t read4(int i) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr + (uint32_t)i));
+        return v;
+    }
+};
+
+EB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+EB_D void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+EB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+EB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier (UBLKCP in SASS).
+EB_D void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int NW, int MODE>
+__global__ void k1_kernel(const K1Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    // layout: [tile0 | tile1 | mbar0 mbar1 | PeqA | PeqB]
+    uint8_t* tile[2] = {smem, smem + K1_TILE};
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * K1_TILE);
+    unsigned char* peqBase = smem + 2 * K1_TILE + 64;
+
+    const int slot = blockIdx.x * nthreads + tid;
+    const int chunk = blockIdx.y;
+    const bool active = slot < p.numReads;
+    const K1Chunk g = k1_chunk(p, chunk);
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int total = g.ce - g.hs;  // columns this CTA sweeps, starting at a 16-byte aligned offset
+    const int numTiles = (total + K1_TILE - 1) / K1_TILE;
+    auto issue = [&](int i) {
+        const int begin = i * K1_TILE;
+        int bytes = total - begin;
+        if (bytes > K1_TILE) bytes = K1_TILE;
+        bytes = (bytes + 15) & ~15;  // the encoded target is padded with >= 16 spare bytes
+        mbar_expect_tx(&bar[i & 1], (uint32_t)bytes);
+        tma_load_1d(tile[i & 1], p.tcodes + g.hs + begin, (uint32_t)bytes, &bar[i & 1]);
+    };
+    if (tid == 0 && numTiles > 0) issue(0);
+
+    SmemPeqAcc<NW> acc;
+    acc.codeStride = (uint32_t)nthreads * (16u + 4u * SmemPeqAcc<NW>::NWB);
+    acc.a0 = smem_u32(peqBase) + 16u * tid;
+    acc.b0 = smem_u32(peqBase) + 16u * nthreads + 4u * SmemPeqAcc<NW>::NWB * tid;
+    const uint32_t tileAddr[2] = {smem_u32(smem), smem_u32(smem) + (uint32_t)K1_TILE};
+    K1State<NW> st;
+    Rec* rec = nullptr;
+    int recIdx = 0;
+    if (active) {
+        const int pair = p.readList[slot];
+        const int m = p.qlen[pair];
+        k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE, p.ncodes, p.eqtab);
+        k1_init<NW>(st, m, p.kInit[slot]);
+        recIdx = chunk * p.numReads + slot;
+        rec = p.recs + recIdx;
+    }
+
+    for (int i = 0; i < numTiles; ++i) {
+        if (tid == 0 && i + 1 < numTiles) issue(i + 1);  // its buffer was released by the barrier below
+        mbar_wait(&bar[i & 1], (uint32_t)((i >> 1) & 1));
+        if (active) {
+            const int a = g.hs + i * K1_TILE;                       // absolute column of tile byte 0
+            const int b = min(a + K1_TILE, g.ce);
+            const uint32_t sa = tileAddr[i & 1];
+            if (MODE == MODE_HW) {
+                const int mid = min(max(g.cs, a), b);               // columns before cs are halo
+                if (mid > a) k1_columns<NW, false, false>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (b > mid) k1_columns<NW, false, true>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+            } else if (MODE == MODE_SHW) {
+                k1_columns<NW, true, true>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+            } else {
+                k1_columns<NW, true, false>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+            }
+        }
+        __syncthreads();  // everyone is done with tile i before its buffer is refilled
+    }
+    if (active) {
+        if (MODE == MODE_NW) {
+            st.best = st.score;
+            st.cnt = 1;
+            rec->last = p.n - 1;
+            rec->pos[0] = p.n - 1;
+        }
+        rec->best = st.best;
+        rec->cnt = st.cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// W and the small kernels
+// ---------------------------------------------------------------------------------------------
+constexpr int W_WARPS = 4;
+
+template <int R>
+__global__ void __launch_bounds__(W_WARPS * 32) w_kernel(const WParams p) {
+    const int job = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
+    if (job >= p.numJobs) return;
+    w_sweep<DevWarp, R>(p, job);
+}
+
+__global__ void peq_kernel(const PeqParams p) {
+    const int job = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
+    if (job >= p.numJobs) return;
+    peq_build_words(p, job, threadIdx.x & 31, 32);
+}
+
+__global__ void traceback_kernel(const TbParams p) {
+    const int job = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job < p.numJobs) traceback_job(p, job);
+}
+
+__global__ void mask_kernel(const MaskParams p) {
+    const int item = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
+    if (item >= p.numItems) return;
+    mask_item(p, item, threadIdx.x & 31, 32);
+}
+
+__global__ void alpha_len_kernel(const uint32_t* masks, const int* qset, const int* tset, int n, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = alpha_len_pair(masks, qset ? qset[i] : i, tset[i]);
+}
+
+__global__ void encode_kernel(const EncodeParams p) {
+    __shared__ uint8_t map[256];
+    if (threadIdx.x < 256) map[threadIdx.x] = p.map[threadIdx.x];
+    __syncthreads();
+    const uint64_t nvec = p.numBytes / 16;
+    uint4* v = reinterpret_cast<uint4*>(p.data);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 x = v[i];
+        uint32_t* w = reinterpret_cast<uint32_t*>(&x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t a = w[k];
+            w[k] = (uint32_t)map[a & 255u] | ((uint32_t)map[(a >> 8) & 255u] << 8) | ((uint32_t)map[(a >> 16) & 255u] << 16) |
+                   ((uint32_t)map[a >> 24] << 24);
+        }
+        v[i] = x;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (uint64_t i = nvec * 16; i < p.numBytes; ++i) p.data[i] = map[p.data[i]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA backend
+// ---------------------------------------------------------------------------------------------
+#define EB_CUDA(call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct CudaBackend : Backend {
+    cudaStream_t stream = nullptr;
+    int sms = 0;
+    int maxSmemOptin = 0;
+    struct Timed {
+        const char* name;
+        cudaEvent_t a, b;
+    };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> pool;
+    int launchCount = 0;
+
+    CudaBackend() {
+        int dev = 0;
+        EB_CUDA(cudaGetDevice(&dev));
+        cudaDeviceProp prop;
+        EB_CUDA(cudaGetDeviceProperties(&prop, dev));
+        sms = prop.multiProcessorCount;
+        maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
+        EB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
+    ~CudaBackend() override {
+        for (auto& t : timed) {
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
+        }
+        for (auto e : pool) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    void* alloc(size_t bytes) override {
+        void* p = nullptr;
+        EB_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        return p;
+    }
+    void free(void* p) override { cudaFree(p); }
+    void* alloc_host(size_t bytes) override {
+        void* p = nullptr;
+        EB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault));
+        return p;
+    }
+    void free_host(void* p) override { cudaFreeHost(p); }
+    void h2d(void* d, const void* s, size_t n) override {
+        if (n) EB_CUDA(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream));
+    }
+    void d2h(void* d, const void* s, size_t n) override {
+        if (n) EB_CUDA(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream));
+        EB_CUDA(cudaStreamSynchronize(stream));
+    }
+    void zero(void* d, size_t n) override {
+        if (n) EB_CUDA(cudaMemsetAsync(d, 0, n, stream));
+    }
+    void sync() override { EB_CUDA(cudaStreamSynchronize(stream)); }
+    int sm_count() override { return sms; }
+
+    cudaEvent_t get_event() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        EB_CUDA(cudaEventCreate(&e));
+        return e;
+    }
+    struct Scope {
+        CudaBackend* be;
+        Timed t;
+        Scope(CudaBackend* b, const char* name) : be(b) {
+            t.name = name;
+            t.a = be->get_event();
+            t.b = be->get_event();
+            cudaEventRecord(t.a, be->stream);
+        }
+        ~Scope() {
+            cudaEventRecord(t.b, be->stream);
+            be->timed.push_back(t);
+            be->launchCount++;
+        }
+    };
+    static void check_launch(const char* what) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw std::runtime_error(std::string(what) + " launch: " + cudaGetErrorString(e));
+    }
+
+    void launch_mask(const MaskParams& p) override {
+        Scope s(this, "mask");
+        mask_kernel<<<(p.numItems + W_WARPS - 1) / W_WARPS, W_WARPS * 32, 0, stream>>>(p);
+        check_launch("mask");
+    }
+    void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int n, int* out) override {
+        Scope s(this, "alpha");
+        alpha_len_kernel<<<(n + 255) / 256, 256, 0, stream>>>(masks, qset, tset, n, out);
+        check_launch("alpha_len");
+    }
+    void launch_encode(const EncodeParams& p) override {
+        Scope s(this, "encode");
+        const uint64_t nvec = p.numBytes / 16;
+        int blocks = (int)std::min<uint64_t>((nvec + 255) / 256, (uint64_t)sms * 8);
+        if (blocks < 1) blocks = 1;
+        encode_kernel<<<blocks, 256, 0, stream>>>(p);
+        check_launch("encode");
+    }
+
+    template <int NW, int MODE>
+    void launch_k1_t(const K1Params& p) {
+        const size_t perThread = (size_t)p.ncodes * (16 + 4 * (NW > 4 ? NW - 4 : 0));
+        const size_t fixed = 2 * K1_TILE + 64;
+        int block = 256;
+        // four CTAs of 256 threads per SM when the alphabet is small; shrink the CTA otherwise
+        while (block > 32 && fixed + perThread * block > 56 * 1024) block >>= 1;
+        const size_t smem = fixed + perThread * block;
+        if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
+        EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((p.numReads + block - 1) / block, p.chunks);
+        k1_kernel<NW, MODE><<<grid, block, smem, stream>>>(p);
+        check_launch("k1");
+    }
+    template <int NW>
+    void launch_k1_m(const K1Params& p) {
+        if (p.mode == MODE_HW) launch_k1_t<NW, MODE_HW>(p);
+        else if (p.mode == MODE_SHW) launch_k1_t<NW, MODE_SHW>(p);
+        else launch_k1_t<NW, MODE_NW>(p);
+    }
+    void launch_k1(const K1Params& p, int nw) override {
+        Scope s(this, "k1");
+        switch (nw) {
+            case 1: launch_k1_m<1>(p); break;
+            case 2: launch_k1_m<2>(p); break;
+            case 3: launch_k1_m<3>(p); break;
+            case 4: launch_k1_m<4>(p); break;
+            case 5: launch_k1_m<5>(p); break;
+            case 6: launch_k1_m<6>(p); break;
+            case 7: launch_k1_m<7>(p); break;
+            case 8: launch_k1_m<8>(p); break;
+            default: throw std::runtime_error("bad K1 word class");
+        }
+    }
+    void launch_peq(const PeqParams& p) override {
+        Scope s(this, "peq");
+        peq_kernel<<<(p.numJobs + W_WARPS - 1) / W_WARPS, W_WARPS * 32, 0, stream>>>(p);
+        check_launch("peq");
+    }
+    void launch_w(const WParams& p, int R) override {
+        Scope s(this, "w");
+        const int blocks = (p.numJobs + W_WARPS - 1) / W_WARPS;
+        switch (R) {
+            case 1: w_kernel<1><<<blocks, W_WARPS * 32, 0, stream>>>(p); break;
+            case 2: w_kernel<2><<<blocks, W_WARPS * 32, 0, stream>>>(p); break;
+            case 4: w_kernel<4><<<blocks, W_WARPS * 32, 0, stream>>>(p); break;
+            case 8: w_kernel<8><<<blocks, W_WARPS * 32, 0, stream>>>(p); break;
+            default: throw std::runtime_error("bad W chunk size");
+        }
+        check_launch("w");
+    }
+    void launch_traceback(const TbParams& p) override {
+        Scope s(this, "traceback");
+        traceback_kernel<<<(p.numJobs + 127) / 128, 128, 0, stream>>>(p);
+        check_launch("traceback");
+    }
+    void reset_timing() override {
+        for (auto& t : timed) {
+            pool.push_back(t.a);
+            pool.push_back(t.b);
+        }
+        timed.clear();
+        launchCount = 0;
+    }
+    double kernel_ms(const char* name) override {
+        cudaStreamSynchronize(stream);
+        double total = 0;
+        for (auto& t : timed) {
+            if (name && strcmp(name, t.name) != 0) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) total += ms;
+        }
+        return total;
+    }
+    int launches() override { return launchCount; }
+};
+
+int select_device(int device, std::string* err) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        if (err) *err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    return 0;
+}
+
+Backend* create_backend(std::string* err) {
+    try {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            if (err) *err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+            return nullptr;
+        }
+        return new CudaBackend();
+    } catch (const std::exception& ex) {
+        if (err) *err = ex.what();
+        return nullptr;
+    }
+}
+
+}  // namespace eb

@@ -36,6 +36,14 @@ typedef struct {
     long long wCells;     /* nominal DP cells of the distance pass swept by the warp kernel */
 } EdlibB200Stats;
 
+/* Selects the CUDA device this process will use; call before any other entry point (one
+ * process drives one GPU).  Returns EDLIB_STATUS_OK, or EDLIB_STATUS_ERROR if the engine was
+ * already initialised on another device or the device does not exist. */
+EDLIB_API int edlibB200SetDevice(int device);
+
+/* free() the arrays of `n` results at once (same effect as n edlibFreeAlignResult calls). */
+EDLIB_API void edlibB200FreeResults(EdlibAlignResult* results, int n);
+
 /* 1 when a CUDA device and the kernels are usable, else 0 (then every align call fails). */
 EDLIB_API int edlibB200Available(void);
 

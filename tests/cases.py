@@ -1,0 +1,110 @@
+"""Seeded case generators shared by the CPU (emulation) and GPU parity tests."""
+import random
+
+from helpers import mutate, rand_seq
+
+
+def single_pair_cases(seed, count):
+    """Small mixed cases: every mode/task, explicit and free k, odd alphabets, equalities,
+    empty sequences, query lengths around the 32/64-bit word boundaries."""
+    rng = random.Random(seed)
+    for _ in range(count):
+        asz = rng.choice([1, 2, 4, 4, 4, 10, 20])
+        alpha = bytes(rng.sample(range(256), asz))
+        m = rng.choice([0, 1, 2, 5, 31, 32, 33, 63, 64, 65, 100, 128, 129, 150, 200]) if rng.random() < 0.5 else rng.randrange(0, 300)
+        if rng.random() < 0.4:
+            t = rand_seq(rng, rng.randrange(0, 600), alpha)
+            q = rand_seq(rng, m, alpha)
+        else:
+            t = rand_seq(rng, rng.randrange(1, 800), alpha)
+            if len(t) > 1:
+                a = rng.randrange(0, len(t))
+                b = rng.randrange(a, min(len(t), a + 300))
+                q = mutate(rng, t[a:b], rng.choice([0.0, 0.03, 0.1, 0.3]), alpha)
+            else:
+                q = rand_seq(rng, m, alpha)
+        mode = rng.randrange(3)
+        task = rng.randrange(3)
+        k = rng.choice([-1, -1, 0, 1, 2, 5, 10, 50, 1000])
+        eqs = None
+        if rng.random() < 0.2 and asz >= 2:
+            eqs = [(bytes([rng.choice(alpha)]), bytes([rng.choice(alpha)])) for _ in range(rng.randrange(1, 4))]
+        yield dict(q=q, t=t, k=k, mode=mode, task=task, eqs=eqs)
+
+
+def batch_cases(seed, count):
+    """Batches that share a few targets (the reference's own batch shape, aligner.cpp:162-170)."""
+    rng = random.Random(seed)
+    for _ in range(count):
+        asz = rng.choice([1, 2, 4, 4, 4, 10])
+        alpha = bytes(rng.sample(range(256), asz))
+        targets = [rand_seq(rng, rng.choice([rng.randrange(1, 200), rng.randrange(200, 3000)]), alpha)
+                   for _ in range(rng.randrange(1, 4))]
+        npairs = rng.choice([5, 40, 100, 300])
+        qs, ts = [], []
+        for _ in range(npairs):
+            t = rng.choice(targets)
+            if rng.random() < 0.5 and len(t) > 2:
+                a = rng.randrange(0, len(t))
+                b = rng.randrange(a, min(len(t), a + rng.choice([20, 150, 250, 400])))
+                q = mutate(rng, t[a:b], rng.choice([0.0, 0.03, 0.1, 0.3]), alpha)
+            else:
+                q = rand_seq(rng, rng.choice([0, 1, 31, 32, 33, 64, 100, 150, 256, 257, 300]), alpha)
+            qs.append(q)
+            ts.append(t)
+        mode = rng.randrange(3)
+        task = rng.randrange(3)
+        k = rng.choice([-1, -1, 0, 2, 10, 50, 1000])
+        eqs = None
+        if rng.random() < 0.2 and asz >= 2:
+            eqs = [(bytes([rng.choice(alpha)]), bytes([rng.choice(alpha)])) for _ in range(rng.randrange(1, 4))]
+        yield dict(qs=qs, ts=ts, k=k, mode=mode, task=task, eqs=eqs)
+
+
+def long_cases(seed, count):
+    """Queries taller than one 1024-row window: sliding band, strips, k doubling."""
+    rng = random.Random(seed)
+    for _ in range(count):
+        alpha = bytes(rng.sample(range(256), rng.choice([2, 4, 4, 10])))
+        kind = rng.randrange(4)
+        if kind == 0:
+            n = rng.choice([1100, 2100, 3000, 5000, 9000])
+            t = rand_seq(rng, n, alpha)
+            q = mutate(rng, t, rng.choice([0.01, 0.03, 0.1]), alpha)
+            mode, k = 0, rng.choice([-1, 50, 200, 500, 2000])
+        elif kind == 1:
+            n = rng.choice([3000, 6000])
+            t = rand_seq(rng, n, alpha)
+            a = rng.randrange(0, n - 2600)
+            q = mutate(rng, t[a:a + rng.choice([1030, 1100, 2500])], 0.05, alpha)
+            mode, k = rng.choice([1, 2]), rng.choice([-1, 100, 1000])
+        elif kind == 2:
+            q = rand_seq(rng, rng.choice([8200, 9000, 17000]), alpha)
+            t = rand_seq(rng, rng.randrange(50, 400), alpha)
+            mode, k = rng.randrange(3), -1
+        else:
+            q = rand_seq(rng, rng.randrange(1025, 4000), alpha)
+            t = rand_seq(rng, rng.randrange(1025, 4000), alpha)
+            mode, k = 0, rng.choice([-1, 100, 3000])
+        yield dict(q=q, t=t, k=k, mode=mode, task=rng.choice([0, 1]), eqs=None)
+
+
+# Hand vectors with known answers from the reference's own tests:
+# bindings/python/test.py:6-73 and test/runTests.cpp:427-570, plus API probes measured on the
+# reference build.  (query, target, mode, task, k, equalities) -> expected fields.
+KNOWN = [
+    (b"telephone", b"elephant", "NW", "path", -1, None,
+     dict(editDistance=3, endLocations=[7], startLocations=[0], alphabetLength=8, cigar="1I5=1X1=1X")),
+    (b"AACG", b"TCAACCTG", "HW", "path", -1, None,
+     dict(editDistance=1, endLocations=[4, 5], startLocations=[2, 2], cigar="3=1I")),
+    (b"TAAGGATGGTCCCATTC", b"AAGGGGTCTCATATC", "NW", "path", -1, None,
+     dict(editDistance=5, endLocations=[14], cigar="1I4=2I4=1X3=1D2=")),
+    (b"AA", b"B", "HW", "path", -1, None,
+     dict(editDistance=2, endLocations=[-1, 0], startLocations=[0, 0], cigar="2I")),
+    (b"AA", b"B", "SHW", "path", -1, None, dict(editDistance=2)),
+    (b"ACGT", b"", "NW", "distance", -1, None, dict(editDistance=4, endLocations=[-1])),
+    (b"", b"ACGT", "NW", "distance", -1, None, dict(editDistance=4, endLocations=[3])),
+    (b"", b"ACGT", "HW", "path", -1, None, dict(editDistance=0, endLocations=[-1], startLocations=None, alignment=None)),
+    (b"GCATATCAATAAGCGGAGGA", b"TAACAAGGTTTCCGTAGGTGAACCTGCGGAAGGATCATTATTGAATTATATCTT", "HW", "locations", -1,
+     [(b"R", b"A"), (b"R", b"G"), (b"M", b"A"), (b"M", b"C"), (b"W", b"A"), (b"W", b"T")], dict()),
+]

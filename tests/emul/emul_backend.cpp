@@ -127,4 +127,5 @@ struct EmulBackend : Backend {
 
 namespace eb {
 Backend* create_backend(std::string*) { return new EmulBackend(); }
+int select_device(int, std::string*) { return 0; }
 }  // namespace eb

@@ -1,0 +1,71 @@
+"""CPU tests of the host engine + kernel LOGIC: the real planner (eb_engine.cpp) drives the real
+kernel bodies (eb_core.h) through the host SIMT emulation backend (tests/emul/), and every
+result field is compared with the reference build / oracle.  No GPU involved; the product
+library is not used here (its CUDA path is covered by the -m gpu tests)."""
+import os
+import subprocess
+
+import pytest
+
+import parity
+from edlib_b200._ffi import REPO, EdlibLib
+
+EMUL_DIR = os.path.join(REPO, "tests", "emul")
+
+
+def load_emul(env=None):
+    subprocess.run(["make", "-s", "-C", EMUL_DIR], check=True)
+    return EdlibLib(os.path.join(EMUL_DIR, "libedlib_emul.so"), has_batch=True)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return load_emul()
+
+
+def test_known_and_golden(emul):
+    parity.run_known(emul)
+    assert parity.run_golden(emul) > 200
+
+
+def test_single_pairs(emul):
+    assert parity.run_single(emul, 11, 1500) == 1500
+
+
+def test_batches_shared_targets(emul):
+    assert parity.run_batches(emul, 12, 30) > 1000
+
+
+def test_long_queries(emul):
+    import cases
+    assert parity.run_single(emul, 13, 40, gen=cases.long_cases) == 40
+
+
+def test_chunked_sweeps_and_overflow_retry():
+    """Same batches with tiny chunk / overflow limits so that target chunking with halo, the
+    overflow list and its exact-size second pass are all exercised (separate process: the
+    tunables are read once per process)."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 14, 30))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    env = dict(os.environ, EDLIB_B200_K1_MIN_CHUNK="64", EDLIB_EMUL_SMS="64", EDLIB_B200_OVF_CAP="3",
+               EDLIB_B200_K1_MIN_GROUP="4", EDLIB_B200_SLICE_MB="1")
+    out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+    assert int(out.stdout.strip().splitlines()[-1]) > 1000
+
+
+def test_many_end_locations(emul):
+    """Repeats: every column is an end location (ref runTests-style 'A*64 vs B*70' shapes)."""
+    chk = parity.checker()
+    for q, t, mode in [(b"A" * 64, b"B" * 70, 2), (b"A" * 10, b"A" * 300, 2), (b"AC" * 20, b"AC" * 200, 2),
+                       (b"A" * 33, b"A" * 100, 1), (b"A" * 5, b"C" * 9, 2)]:
+        for task in (0, 1, 2):
+            assert emul.align(q, t, -1, mode, task) == chk.align(q, t, -1, mode, task)
+    qs = [b"A" * 10] * 40
+    t = b"A" * 500
+    st, res = emul.align_batch(qs, [t] * 40, -1, 2, 1)
+    exp = chk.align(qs[0], t, -1, 2, 1)
+    assert st == 0 and all(r == exp for r in res)
