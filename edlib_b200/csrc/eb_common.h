@@ -36,7 +36,9 @@ struct Rec {
     int pos[KPOS];  // first KPOS such columns, ascending
 };
 
-// Overflow entry for columns beyond KPOS; stale entries (score > final best) are dropped on host.
+// Overflow entry for columns beyond KPOS.  The list is only armed (ovfCap > 0) in the second
+// pass over the few sweeps that have more than KPOS end positions; that pass starts from the
+// known minimum, so every entry is a final position and the capacity is known exactly.
 struct Ovf {
     int rec;    // index of the Rec it belongs to
     int score;

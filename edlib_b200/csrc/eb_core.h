@@ -209,7 +209,7 @@ EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx
     }
     if (st.cnt < KPOS) {
         rec->pos[st.cnt] = column;
-    } else {
+    } else if (ovfCap > 0) {  // second pass only: the list then holds final positions exclusively
         const int slot = atomic_add_int(ovfCount, 1);
         if (slot < ovfCap) {
             ovf[slot].rec = recIdx;
@@ -523,7 +523,7 @@ EB_HD void w_sweep(const WParams& P, int jobIdx) {
                     }
                     if (cntU < KPOS) {
                         B::store_uniform(&rec->pos[cntU], c);
-                    } else {
+                    } else if (P.ovfCap > 0) {  // second pass only (see k1_event)
                         const int slot = B::atomic_add_uniform(P.ovfCount, 1);
                         if (slot < P.ovfCap) {
                             B::store_uniform(&P.ovf[slot].rec, J.rec);

@@ -77,6 +77,7 @@ struct WTask {
     int m = 0, n = 0, mode = 0, flags = 0, kInit = 0, dhi = 0, stopCol = -1;
     int R = 1, nWp = 0;
     int pair = -1, tag = 0;
+    bool wantPositions = false;  // the caller needs every end position, not just best/cnt/last
     Rec rec{};
     std::vector<int> extra;  // positions past KPOS that attain rec.best, ascending
     long long opsOff = -1;   // into the ops pool (WF_STORE)
@@ -351,12 +352,14 @@ struct WRunner {
                 ++j;
             }
             std::vector<int> slice(order.begin() + i, order.begin() + j);
-            run_slice(tasks, slice, R, eng->tun.ovfCap, false);
+            run_slice(tasks, slice, R, 0);
             i = j;
         }
     }
 
-    void run_slice(std::vector<WTask>& tasks, const std::vector<int>& slice, int R, int ovfCap, bool isRetry) {
+    // ovfCap == 0: first pass (no position list).  ovfCap > 0: second pass over the tasks whose
+    // end-location lists exceed KPOS, started from their known minimum with an exact-size list.
+    void run_slice(std::vector<WTask>& tasks, const std::vector<int>& slice, int R, int ovfCap) {
         const int J = (int)slice.size();
         std::vector<WJob> jobs(J);
         uint64_t peqWords = 0, matEntries = 0, colInts = 0, hbytes = 0, opsBytes = 0;
@@ -411,7 +414,7 @@ struct WRunner {
         DevBuf<uint8_t> dH(be, hbytes);
         DevBuf<Rec> dRecs(be, J);
         be->zero(dRecs.p, (size_t)J * sizeof(Rec));
-        DevBuf<Ovf> dOvf(be, (size_t)ovfCap);
+        DevBuf<Ovf> dOvf(be, (size_t)std::max(ovfCap, 1));
         DevBuf<int> dOvfCount(be, 1);
         be->zero(dOvfCount.p, sizeof(int));
         if (colInts) {
@@ -442,10 +445,10 @@ struct WRunner {
         dOvfCount.download(&ovfCount, 1);
         eng->stats.d2hBytes += (long long)J * (long long)sizeof(Rec) + 4;
         for (int s = 0; s < J; ++s) tasks[slice[s]].rec = recs[s];
-        const bool truncated = ovfCount > ovfCap;
-        if (ovfCount > 0 && !truncated) {
+        if (ovfCap > 0) {
+            if (ovfCount > ovfCap) throw std::runtime_error("internal: end-location list larger than counted");
             std::vector<Ovf> ov(ovfCount);
-            dOvf.download(ov.data(), ovfCount);
+            if (ovfCount) dOvf.download(ov.data(), ovfCount);
             eng->stats.d2hBytes += (long long)ovfCount * (long long)sizeof(Ovf);
             for (int s = 0; s < J; ++s) tasks[slice[s]].extra.clear();
             for (const Ovf& o : ov) {
@@ -479,22 +482,19 @@ struct WRunner {
                 }
             }
         }
-        if (truncated) {
-            // Exact-size second pass for the tasks whose lists did not fit: with the sentinel set
-            // to the known best only the final positions are emitted.
-            if (isRetry) throw std::runtime_error("overflow list truncated twice");
+        if (ovfCap == 0) {
             std::vector<int> again;
             long long need = 0;
             for (int s = 0; s < J; ++s) {
                 WTask& t = tasks[slice[s]];
-                if (t.rec.cnt > KPOS) {
+                if (t.wantPositions && t.rec.cnt > KPOS) {
                     again.push_back(slice[s]);
                     need += t.rec.cnt - KPOS;
                     t.kInit = t.rec.best;
                 }
             }
-            if (need > 0x7fffffffLL / 2) throw std::runtime_error("end-location list too large");
-            run_slice(tasks, again, R, (int)need + 16, true);
+            if (need > 0x7fffffffLL / 4) throw std::runtime_error("end-location list too large");
+            if (!again.empty()) run_slice(tasks, again, R, (int)need + 16);
         }
     }
 };
@@ -553,29 +553,27 @@ void Engine::compute(Prepared* p) {
         const Target& tg = p->tg[t];
         const int G = (int)list.size();
         const int n = tg.len;
-        int chunks = 1, chunkLen = (int)round_up((size_t)n, 16);
         const int halo = 64 * nw;
-        if (mode == MODE_HW) {
+
+        // Chunk geometry: a HW sweep may be cut into target chunks (each re-started 2*m columns
+        // early, exact because no HW path spans more than 2*m target symbols) so that a small
+        // group still fills the machine.
+        auto geometry = [&](int g, int& chunks, int& chunkLen) {
+            chunks = 1;
+            chunkLen = (int)round_up((size_t)n, 16);
+            if (mode != MODE_HW) return;
             const long long wantThreads = (long long)be->sm_count() * 2048;
             const int minChunk = std::max(tun.k1MinChunk, 8 * halo);
-            long long c = (wantThreads + G - 1) / G;
+            long long c = (wantThreads + g - 1) / g;
             c = std::min<long long>(c, n / minChunk);
             if (c < 1) c = 1;
             chunkLen = (int)round_up((size_t)ceil_div(n, (int)c), 16);
             chunks = ceil_div(n, chunkLen);
-        }
-        std::vector<int> kInit(G);
-        for (int s = 0; s < G; ++s) {
-            const int m = p->qlen[list[s]];
-            kInit[s] = ((k < 0 || k > m) ? m : k) + 1;  // distances never exceed m in HW/SHW (ref cpp:566-568)
-        }
-        std::vector<Rec> recs;
-        std::vector<Ovf> ovf;
-        int ovfCap = tun.ovfCap;
-        std::vector<int> slots(G);
-        for (int s = 0; s < G; ++s) slots[s] = s;
-        auto launch = [&](const std::vector<int>& sub, const std::vector<int>& subK, int cap, std::vector<Rec>& outRecs,
-                          std::vector<Ovf>& outOvf) -> bool {
+        };
+
+        // One launch over the reads `sub` (indices into `list`) with sentinels subK.
+        auto launch = [&](const std::vector<int>& sub, const std::vector<int>& subK, int chunks, int chunkLen, int cap,
+                          std::vector<Rec>& outRecs, std::vector<Ovf>& outOvf) {
             const int g = (int)sub.size();
             std::vector<int> rl(g);
             for (int s = 0; s < g; ++s) rl[s] = list[sub[s]];
@@ -584,7 +582,7 @@ void Engine::compute(Prepared* p) {
             dK.upload(subK.data(), g);
             DevBuf<Rec> dRecs(be, (size_t)g * chunks);
             be->zero(dRecs.p, (size_t)g * chunks * sizeof(Rec));
-            DevBuf<Ovf> dOvf(be, (size_t)cap);
+            DevBuf<Ovf> dOvf(be, (size_t)std::max(cap, 1));
             DevBuf<int> dCount(be, 1);
             be->zero(dCount.p, sizeof(int));
             K1Params kp;
@@ -610,27 +608,27 @@ void Engine::compute(Prepared* p) {
             be->launch_k1(kp, nw);
             outRecs.resize((size_t)g * chunks);
             dRecs.download(outRecs.data(), outRecs.size());
-            int count = 0;
-            dCount.download(&count, 1);
-            stats.d2hBytes += (long long)outRecs.size() * (long long)sizeof(Rec) + 4;
+            stats.d2hBytes += (long long)outRecs.size() * (long long)sizeof(Rec);
             outOvf.clear();
-            if (count > cap) return false;
-            if (count > 0) {
+            if (cap > 0) {
+                int count = 0;
+                dCount.download(&count, 1);
+                if (count > cap) throw std::runtime_error("internal: end-location list larger than counted");
                 outOvf.resize(count);
-                dOvf.download(outOvf.data(), count);
-                stats.d2hBytes += (long long)count * (long long)sizeof(Ovf);
+                if (count) dOvf.download(outOvf.data(), count);
+                stats.d2hBytes += (long long)count * (long long)sizeof(Ovf) + 4;
             }
-            return true;
         };
-        bool ok = launch(slots, kInit, ovfCap, recs, ovf);
-        for (int s = 0; s < G; ++s) stats.k1Cells += (long long)p->qlen[list[s]] * n;
 
-        // merge chunks: the minimum wins; positions of the chunks attaining it, in chunk order
-        auto merge = [&](const std::vector<int>& sub, const std::vector<Rec>& rr, const std::vector<Ovf>& oo, bool haveOvf) {
+        // Merge the chunks of every read: the minimum wins; its columns are the inline positions
+        // of the chunks attaining it (ascending by construction) plus, in a second pass, the
+        // listed ones.  Returns the reads whose lists are incomplete (some chunk holds > KPOS).
+        auto merge = [&](const std::vector<int>& sub, int chunks, const std::vector<Rec>& rr, const std::vector<Ovf>* oo,
+                         std::vector<int>& incomplete, long long& missing) {
             const int g = (int)sub.size();
-            std::unordered_map<int, std::vector<int>> extra;  // rec index -> overflow positions
-            if (haveOvf)
-                for (const Ovf& o : oo)
+            std::unordered_map<int, std::vector<int>> extra;  // rec index -> listed positions
+            if (oo)
+                for (const Ovf& o : *oo)
                     if (o.score == rr[o.rec].best) extra[o.rec].push_back(o.pos);
             for (int s = 0; s < g; ++s) {
                 const int pair = list[sub[s]];
@@ -645,48 +643,61 @@ void Engine::compute(Prepared* p) {
                     if (r.cnt > 0 && r.best == b) total += r.cnt;
                 }
                 best[pair] = (total > 0) ? b : 0x7fffffff;
-                cnt[pair] = (int)std::min<long long>(total, 0x7fffffff);
+                if (total > 0x7fffffffLL / 4) throw std::runtime_error("end-location list too large");
+                cnt[pair] = (int)total;
                 std::vector<int>& dst = posOf[pair];
                 dst.clear();
-                if (total == 0 || !haveOvf) continue;
+                if (total == 0) continue;
+                bool complete = true;
                 for (int c = 0; c < chunks; ++c) {
                     const Rec& r = rr[(size_t)c * g + s];
                     if (r.cnt <= 0 || r.best != b) continue;
                     for (int q = 0; q < std::min(r.cnt, KPOS); ++q) dst.push_back(r.pos[q]);
                     if (r.cnt > KPOS) {
-                        const std::vector<int>& ex = extra[(int)((size_t)c * g + s)];
-                        dst.insert(dst.end(), ex.begin(), ex.end());
+                        if (oo) {
+                            const std::vector<int>& ex = extra[(int)((size_t)c * g + s)];
+                            dst.insert(dst.end(), ex.begin(), ex.end());
+                        } else {
+                            complete = false;
+                        }
                     }
+                }
+                if (!complete) {
+                    incomplete.push_back(sub[s]);
+                    missing += total;
                 }
             }
         };
-        merge(slots, recs, ovf, ok);
-        if (!ok) {
-            // overflow list truncated: second pass over the affected reads with exact capacity
-            std::vector<int> sub, subK;
-            long long need = 0;
-            for (int s = 0; s < G; ++s) {
-                bool big = false;
-                for (int c = 0; c < chunks; ++c) {
-                    const Rec& r = recs[(size_t)c * G + s];
-                    if (r.cnt > KPOS) {
-                        big = true;
-                        need += r.cnt - KPOS;
-                    }
-                }
-                if (big) {
-                    sub.push_back(s);
-                    subK.push_back(best[list[s]] == 0x7fffffff ? kInit[s] : best[list[s]]);
-                }
-            }
-            // reads without overflow keep their inline positions
-            std::vector<Ovf> none;
-            merge(slots, recs, none, true);
-            if (need > 0x7fffffffLL / 2) throw std::runtime_error("end-location list too large");
+
+        int chunks = 1, chunkLen = 0;
+        geometry(G, chunks, chunkLen);
+        std::vector<int> slots(G), kInit(G);
+        for (int s = 0; s < G; ++s) {
+            slots[s] = s;
+            const int m = p->qlen[list[s]];
+            kInit[s] = ((k < 0 || k > m) ? m : k) + 1;  // distances never exceed m in HW/SHW (ref cpp:566-568)
+            stats.k1Cells += (long long)m * n;
+        }
+        std::vector<Rec> recs;
+        std::vector<Ovf> ovf;
+        std::vector<int> incomplete;
+        long long missing = 0;
+        launch(slots, kInit, chunks, chunkLen, 0, recs, ovf);
+        merge(slots, chunks, recs, nullptr, incomplete, missing);
+        if (!incomplete.empty()) {
+            // Second pass over the few reads with more than KPOS end positions in one chunk:
+            // start from the known minimum so that only final positions are recorded, with a
+            // list sized from the counts of the first pass, on a finer chunking of the target.
+            std::vector<int> subK(incomplete.size());
+            for (size_t s = 0; s < incomplete.size(); ++s) subK[s] = best[list[incomplete[s]]];
+            int chunks2 = 1, chunkLen2 = 0;
+            geometry((int)incomplete.size(), chunks2, chunkLen2);
             std::vector<Rec> recs2;
             std::vector<Ovf> ovf2;
-            if (!launch(sub, subK, (int)need + 16, recs2, ovf2)) throw std::runtime_error("overflow list truncated twice");
-            merge(sub, recs2, ovf2, true);
+            std::vector<int> still;
+            long long dummy = 0;
+            launch(incomplete, subK, chunks2, chunkLen2, (int)missing + 16, recs2, ovf2);
+            merge(incomplete, chunks2, recs2, &ovf2, still, dummy);
         }
     }
 
@@ -728,6 +739,7 @@ void Engine::compute(Prepared* p) {
                 t.nWp = pl.nWp;
                 t.kInit = ((k < 0 || k > m) ? m : k) + 1;
                 t.tag = pl.slide ? bound : -1;  // a sliding result is only valid when <= bound
+                t.wantPositions = (mode != MODE_NW);
                 tasks.push_back(std::move(t));
             }
             runner.run(tasks);
