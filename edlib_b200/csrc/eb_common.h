@@ -69,6 +69,7 @@ struct K1Params {
     Ovf* ovf;
     int* ovfCount;
     int ovfCap;
+    uint32_t two;            // the constant 2, passed as data so ptxas keeps IMADs (eb_core.h: mad_lo)
 };
 
 // ---------------------------------------------------------------------------------------------

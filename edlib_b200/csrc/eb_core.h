@@ -154,8 +154,31 @@ EB_HD uint32_t init_pv_word(int wordIdx, int off) {
 // calculateBlock (cpp:421-444) but over ONE NW*32-bit integer: the add carry and the <<1 carry
 // cross word boundaries natively, so no per-block hin/hout is needed.  TOP_ONE selects the
 // horizontal delta entering above row 0: +1 for NW/SHW (cpp:779, 584), 0 for HW.
-template <int NW, bool TOP_ONE>
-EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score) {
+// x*two + c and its high half, kept as integer multiply-adds (IMAD / IMAD.HI, FMA pipe).  `two`
+// is the constant 2 delivered through the kernel parameters so that ptxas cannot strength-reduce
+// the products back into shifts: the sweep is bound by the ALU pipe (LOP3/SHF/IADD3), the FMA
+// pipe is idle, so the <<1 of the horizontal delta words is moved over there.
+EB_HD uint32_t mad_lo(uint32_t x, uint32_t two, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(two), "r"(c));
+    return r;
+#else
+    return x * two + c;
+#endif
+}
+EB_HD uint32_t mul_hi(uint32_t x, uint32_t two) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(two));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)x * two) >> 32);
+#endif
+}
+
+template <int NW, bool TOP_ONE, bool FMA_SHIFT = false>
+EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score, uint32_t two = 2u) {
     uint32_t T[NW], S[NW], Ph[NW], Mh[NW];
     EB_UNROLL
     for (int w = 0; w < NW; ++w) T[w] = Eq[w] & Pv[w];
@@ -166,15 +189,30 @@ EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[
         Ph[w] = Mv[w] | ~(Xh | Pv[w]);
         Mh[w] = Pv[w] & Xh;
     }
-    // the last query row is bit 31 of the last word (top padding, see eb_common.h)
-    score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
-    EB_UNROLL
-    for (int w = NW - 1; w >= 0; --w) {
-        const uint32_t Phs = w ? funnel_l1(Ph[w - 1 < 0 ? 0 : w - 1], Ph[w]) : ((Ph[0] << 1) | (TOP_ONE ? 1u : 0u));
-        const uint32_t Mhs = w ? funnel_l1(Mh[w - 1 < 0 ? 0 : w - 1], Mh[w]) : (Mh[0] << 1);
-        const uint32_t Xv = Eq[w] | Mv[w];
-        Pv[w] = Mhs | ~(Xv | Phs);
-        Mv[w] = Phs & Xv;
+    if (FMA_SHIFT) {
+        uint32_t cP = TOP_ONE ? 1u : 0u, cM = 0u;
+        EB_UNROLL
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t Phs = mad_lo(Ph[w], two, cP);
+            const uint32_t Mhs = mad_lo(Mh[w], two, cM);
+            cP = mul_hi(Ph[w], two);
+            cM = mul_hi(Mh[w], two);
+            const uint32_t Xv = Eq[w] | Mv[w];
+            Pv[w] = Mhs | ~(Xv | Phs);
+            Mv[w] = Phs & Xv;
+        }
+        score += (int)cP - (int)cM;  // bit 31 of the last word = delta of the last query row
+    } else {
+        // the last query row is bit 31 of the last word (top padding, see eb_common.h)
+        score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
+        EB_UNROLL
+        for (int w = NW - 1; w >= 0; --w) {
+            const uint32_t Phs = w ? funnel_l1(Ph[w - 1 < 0 ? 0 : w - 1], Ph[w]) : ((Ph[0] << 1) | (TOP_ONE ? 1u : 0u));
+            const uint32_t Mhs = w ? funnel_l1(Mh[w - 1 < 0 ? 0 : w - 1], Mh[w]) : (Mh[0] << 1);
+            const uint32_t Xv = Eq[w] | Mv[w];
+            Pv[w] = Mhs | ~(Xv | Phs);
+            Mv[w] = Phs & Xv;
+        }
     }
 }
 
@@ -185,6 +223,7 @@ struct K1State {
     int score;  // D[m-1][c] of the last column swept
     int best;   // running minimum (starts at the bound sentinel)
     int cnt;    // columns attaining best so far
+    uint32_t two;  // the constant 2, opaque to ptxas (see mad_lo)
 };
 
 template <int NW>
@@ -198,6 +237,7 @@ EB_HD void k1_init(K1State<NW>& st, int m, int kInit) {
     st.score = m;  // D[m-1][-1] = m  (ref cpp:576, 760)
     st.best = kInit;
     st.cnt = 0;
+    st.two = 2u;
 }
 
 // Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
@@ -235,14 +275,14 @@ struct PtrSyms {
 // running minimum and its columns are recorded; without it only the state advances (halo
 // columns of a chunk).  Columns go four at a time: the four last-row scores stay in registers
 // and are compared against the running minimum once per group (events are rare).
-template <int NW, bool TOP_ONE, bool TRACK, class Acc, class Syms>
+template <int NW, bool TOP_ONE, bool TRACK, bool FMA_SHIFT = false, class Acc, class Syms>
 EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int count, int cAbs,
                       Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     int i = 0;
     while (i < count && !syms.aligned4(i)) {  // head: until the symbols are 4-byte aligned
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
-        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
+        k1_step<NW, TOP_ONE, FMA_SHIFT>(st.Pv, st.Mv, Eq, st.score, st.two);
         if (TRACK && st.score <= st.best) k1_event<NW>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
         ++i;
     }
@@ -253,7 +293,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
         for (int j = 0; j < 4; ++j) {
             uint32_t Eq[NW];
             acc.load((four >> (8 * j)) & 0xffu, Eq);
-            k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
+            k1_step<NW, TOP_ONE, FMA_SHIFT>(st.Pv, st.Mv, Eq, st.score, st.two);
             sc[j] = st.score;
         }
         if (TRACK) {
@@ -270,7 +310,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
     for (; i < count; ++i) {  // tail
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
-        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
+        k1_step<NW, TOP_ONE, FMA_SHIFT>(st.Pv, st.Mv, Eq, st.score, st.two);
         if (TRACK && st.score <= st.best) k1_event<NW>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
     }
 }
@@ -331,10 +371,11 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     k1_build_peq<NW>(acc, q, m, p.mode, p.ncodes, p.eqtab);
     K1State<NW> st;
     k1_init<NW>(st, m, p.kInit[slot]);
+    st.two = p.two;
     const K1Chunk g = k1_chunk(p, chunk);
     if (p.mode == MODE_HW) {
-        k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, false, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_SHW) {
         k1_columns<NW, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else {

@@ -605,6 +605,7 @@ void Engine::compute(Prepared* p) {
             kp.ovf = dOvf.p;
             kp.ovfCount = dCount.p;
             kp.ovfCap = cap;
+            kp.two = 2u;
             be->launch_k1(kp, nw);
             outRecs.resize((size_t)g * chunks);
             dRecs.download(outRecs.data(), outRecs.size());

@@ -11,6 +11,7 @@
 // The bodies live in eb_core.h (shared with the host emulation used by the CPU tests).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -161,7 +162,7 @@ EB_D void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
                  : "memory");
 }
 
-template <int NW, int MODE>
+template <int NW, int MODE, bool FMA_SHIFT>
 __global__ void k1_kernel(const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -208,6 +209,7 @@ __global__ void k1_kernel(const K1Params p) {
         const int m = p.qlen[pair];
         k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE, p.ncodes, p.eqtab);
         k1_init<NW>(st, m, p.kInit[slot]);
+        st.two = p.two;
         recIdx = chunk * p.numReads + slot;
         rec = p.recs + recIdx;
     }
@@ -221,12 +223,12 @@ __global__ void k1_kernel(const K1Params p) {
             const uint32_t sa = tileAddr[i & 1];
             if (MODE == MODE_HW) {
                 const int mid = min(max(g.cs, a), b);               // columns before cs are halo
-                if (mid > a) k1_columns<NW, false, false>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-                if (b > mid) k1_columns<NW, false, true>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (mid > a) k1_columns<NW, false, false, FMA_SHIFT>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (b > mid) k1_columns<NW, false, true, FMA_SHIFT>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             } else if (MODE == MODE_SHW) {
-                k1_columns<NW, true, true>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                k1_columns<NW, true, true, FMA_SHIFT>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             } else {
-                k1_columns<NW, true, false>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                k1_columns<NW, true, false, FMA_SHIFT>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             }
         }
         __syncthreads();  // everyone is done with tile i before its buffer is refilled
@@ -318,8 +320,11 @@ struct CudaBackend : Backend {
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> pool;
     int launchCount = 0;
+    bool fmaShift = true;  // EDLIB_B200_K1_FMA_SHIFT=0 selects the funnel-shift variant (A/B measurements)
 
     CudaBackend() {
+        const char* v = getenv("EDLIB_B200_K1_FMA_SHIFT");
+        if (v && *v) fmaShift = atoi(v) != 0;
         int dev = 0;
         EB_CUDA(cudaGetDevice(&dev));
         cudaDeviceProp prop;
@@ -410,8 +415,8 @@ struct CudaBackend : Backend {
         check_launch("encode");
     }
 
-    template <int NW, int MODE>
-    void launch_k1_t(const K1Params& p) {
+    template <int NW, int MODE, bool FMA_SHIFT>
+    void launch_k1_v(const K1Params& p) {
         const size_t perThread = (size_t)p.ncodes * (16 + 4 * (NW > 4 ? NW - 4 : 0));
         const size_t fixed = 2 * K1_TILE + 64;
         int block = 256;
@@ -419,10 +424,15 @@ struct CudaBackend : Backend {
         while (block > 32 && fixed + perThread * block > 56 * 1024) block >>= 1;
         const size_t smem = fixed + perThread * block;
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
-        EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE, FMA_SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
-        k1_kernel<NW, MODE><<<grid, block, smem, stream>>>(p);
+        k1_kernel<NW, MODE, FMA_SHIFT><<<grid, block, smem, stream>>>(p);
         check_launch("k1");
+    }
+    template <int NW, int MODE>
+    void launch_k1_t(const K1Params& p) {
+        if (fmaShift) launch_k1_v<NW, MODE, true>(p);
+        else launch_k1_v<NW, MODE, false>(p);
     }
     template <int NW>
     void launch_k1_m(const K1Params& p) {
