@@ -558,16 +558,32 @@ void Engine::compute(Prepared* p) {
         // Chunk geometry: a HW sweep may be cut into target chunks (each re-started 2*m columns
         // early, exact because no HW path spans more than 2*m target symbols) so that a small
         // group still fills the machine.
+        int blockThreads = 256, residentCtas = 1;
+        be->k1_shape(nw, p->ncodes, &blockThreads, &residentCtas);
         auto geometry = [&](int g, int& chunks, int& chunkLen) {
             chunks = 1;
             chunkLen = (int)round_up((size_t)n, 16);
             if (mode != MODE_HW) return;
-            const long long wantThreads = (long long)be->sm_count() * 2048;
             const int minChunk = std::max(tun.k1MinChunk, 8 * halo);
-            long long c = (wantThreads + g - 1) / g;
-            c = std::min<long long>(c, n / minChunk);
-            if (c < 1) c = 1;
-            chunkLen = (int)round_up((size_t)ceil_div(n, (int)c), 16);
+            const long long maxChunks = std::max<long long>(1, n / minChunk);
+            const long long tiles = ceil_div(g, blockThreads);
+            // Few CTAs: cut until the device is covered twice.  Many CTAs: pick the cut (<= 8) whose
+            // last wave is fullest (CTA count close to a multiple of what is resident at once).
+            long long best = 1;
+            if (tiles < 2LL * residentCtas) {
+                best = std::min(maxChunks, (2LL * residentCtas + tiles - 1) / tiles);
+            } else {
+                double bestEff = 0;
+                for (long long c = 1; c <= std::min<long long>(8, maxChunks); ++c) {
+                    const double waves = (double)(tiles * c) / residentCtas;
+                    const double eff = waves / (double)((tiles * c + residentCtas - 1) / residentCtas);
+                    if (eff > bestEff + 0.005) {
+                        bestEff = eff;
+                        best = c;
+                    }
+                }
+            }
+            chunkLen = (int)round_up((size_t)ceil_div(n, (int)best), 16);
             chunks = ceil_div(n, chunkLen);
         };
 

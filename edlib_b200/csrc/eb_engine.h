@@ -27,6 +27,9 @@ struct Backend {
     virtual void zero(void* dst, size_t bytes) = 0;
     virtual void sync() = 0;
     virtual int sm_count() = 0;
+    // Launch shape of the lane-per-alignment kernel for a word class / alphabet size: threads per
+    // CTA and how many CTAs are resident on the whole device at once (for wave-aware chunking).
+    virtual void k1_shape(int nw32, int ncodes, int* blockThreads, int* residentCtas) = 0;
     virtual void launch_mask(const MaskParams& p) = 0;
     virtual void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int numPairs, int* out) = 0;
     virtual void launch_encode(const EncodeParams& p) = 0;

@@ -415,19 +415,51 @@ struct CudaBackend : Backend {
         check_launch("encode");
     }
 
+    // CTA size and dynamic shared memory of a K1 launch: four CTAs of 256 threads per SM when the
+    // alphabet is small; the CTA shrinks when the per-thread Peq rows would not fit.
+    static void k1_block(int nw, int ncodes, int* block, size_t* smem) {
+        const size_t perThread = (size_t)ncodes * (16 + 4 * (nw > 4 ? nw - 4 : 0));
+        const size_t fixed = 2 * K1_TILE + 64;
+        int b = 256;
+        while (b > 32 && fixed + perThread * b > 44 * 1024) b >>= 1;
+        *block = b;
+        *smem = fixed + perThread * b;
+    }
     template <int NW, int MODE, bool FMA_SHIFT>
     void launch_k1_v(const K1Params& p) {
-        const size_t perThread = (size_t)p.ncodes * (16 + 4 * (NW > 4 ? NW - 4 : 0));
-        const size_t fixed = 2 * K1_TILE + 64;
-        int block = 256;
-        // four CTAs of 256 threads per SM when the alphabet is small; shrink the CTA otherwise
-        while (block > 32 && fixed + perThread * block > 56 * 1024) block >>= 1;
-        const size_t smem = fixed + perThread * block;
+        int block;
+        size_t smem;
+        k1_block(NW, p.ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
         EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE, FMA_SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
         k1_kernel<NW, MODE, FMA_SHIFT><<<grid, block, smem, stream>>>(p);
         check_launch("k1");
+    }
+    template <int NW>
+    int k1_occupancy(int block, size_t smem) {
+        int perSm = 0;
+        cudaFuncSetAttribute(k1_kernel<NW, MODE_HW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_kernel<NW, MODE_HW, false>, block, smem) != cudaSuccess) perSm = 1;
+        return perSm < 1 ? 1 : perSm;
+    }
+    void k1_shape(int nw, int ncodes, int* blockThreads, int* residentCtas) override {
+        int block;
+        size_t smem;
+        k1_block(nw, ncodes, &block, &smem);
+        int perSm = 1;
+        switch (nw) {
+            case 1: perSm = k1_occupancy<1>(block, smem); break;
+            case 2: perSm = k1_occupancy<2>(block, smem); break;
+            case 3: perSm = k1_occupancy<3>(block, smem); break;
+            case 4: perSm = k1_occupancy<4>(block, smem); break;
+            case 5: perSm = k1_occupancy<5>(block, smem); break;
+            case 6: perSm = k1_occupancy<6>(block, smem); break;
+            case 7: perSm = k1_occupancy<7>(block, smem); break;
+            default: perSm = k1_occupancy<8>(block, smem); break;
+        }
+        *blockThreads = block;
+        *residentCtas = perSm * sms;
     }
     template <int NW, int MODE>
     void launch_k1_t(const K1Params& p) {

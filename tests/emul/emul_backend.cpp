@@ -71,6 +71,10 @@ struct EmulBackend : Backend {
         const char* s = getenv("EDLIB_EMUL_SMS");
         return s ? atoi(s) : 2;
     }
+    void k1_shape(int, int, int* blockThreads, int* residentCtas) override {
+        *blockThreads = 32;
+        *residentCtas = sm_count() * 4;
+    }
     void launch_mask(const MaskParams& p) override {
         ++launchesCount;
         for (int i = 0; i < p.numItems; ++i) mask_item(p, i, 0, 1);
