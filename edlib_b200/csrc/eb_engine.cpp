@@ -843,41 +843,163 @@ void Engine::compute(Prepared* p) {
         }
     }
 
-    // ---- alignment path (ref cpp:276-289, 1161-1213) --------------------------------------
+    // ---- alignment path (ref cpp:276-289, 1161-1213, 1231-1396) ---------------------------
+    // obtainAlignment as a level-synchronous tree: a node is an NW sub-problem (query slice,
+    // target slice, known score).  Inside the reference's 1 MiB rule (cpp:1188-1190) it is a
+    // leaf: matrix-storing sweep + traceback kernel.  Otherwise it is split like
+    // obtainAlignmentHirschberg: the score column left of the target's middle from a forward
+    // sweep and the one right of it from a reversed sweep (both on the device, cpp:1252-1260),
+    // the split row chosen by the reference's candidate order (cpp:1321-1353), both halves
+    // becoming nodes of the next level (cpp:1372-1380).  All nodes of a level run in one batch.
     if (p->cfg.task == EDLIB_TASK_PATH) {
-        std::vector<WTask> tasks;
+        struct Node {
+            int pair;
+            uint64_t qOff, tOff;
+            int m, n, best;
+            int left = -1, right = -1;
+            long long opsOff = -1;  // into opsPool (leaf) ...
+            int opsLen = 0;
+            int fillOp = -1;        // ... or a run of one op (empty side, cpp:1168-1175)
+        };
+        std::vector<Node> nodes;
+        std::vector<int> rootOf(N, -1), frontier, leaves;
         for (int i = 0; i < N; ++i) {
             if (p->ed[i] < 0) continue;
-            const int m = p->qlen[i];
             const int s0 = p->startPool[(size_t)p->endStart[i]], e0 = p->endPool[(size_t)p->endStart[i]];
-            const int wn = e0 - s0 + 1;
-            if (wn <= 0) {  // ref cpp:1168-1175: empty target slice -> m insertions
-                p->alnStart[i] = (long long)p->alnPool.size();
-                p->alnLen[i] = m;
-                p->alnPool.insert(p->alnPool.end(), (size_t)m, (uint8_t)EDLIB_EDOP_INSERT);
-                continue;
-            }
-            const long long matrixBytes = 20LL * ceil_div(m, 64) * wn + 8LL * wn;  // ref cpp:1188-1190
-            if (matrixBytes >= 1024 * 1024) throw std::runtime_error("PATH beyond the stored-matrix regime (Hirschberg) is not built yet");
-            WTask t;
-            t.pair = i;
-            t.qOff = p->qoff[i];
-            t.tOff = p->tg[p->tidx[i]].off + (uint64_t)s0;
-            t.m = m;
-            t.n = wn;
-            t.mode = MODE_NW;
-            t.flags = WF_STORE;
-            WPlan pl = plan_w(m, wn, MODE_NW, -1);
-            t.R = pl.R;
-            t.nWp = pl.nWp;
-            tasks.push_back(std::move(t));
+            Node nd;
+            nd.pair = i;
+            nd.qOff = p->qoff[i];
+            nd.tOff = p->tg[p->tidx[i]].off + (uint64_t)s0;
+            nd.m = p->qlen[i];
+            nd.n = e0 - s0 + 1;
+            nd.best = p->ed[i];
+            rootOf[i] = (int)nodes.size();
+            frontier.push_back((int)nodes.size());
+            nodes.push_back(nd);
         }
-        runner.run(tasks);
-        for (const WTask& t : tasks) {
-            if (t.rec.best != p->ed[t.pair]) throw std::runtime_error("internal: path sweep disagrees with the distance");
-            p->alnStart[t.pair] = (long long)p->alnPool.size();
-            p->alnLen[t.pair] = t.opsLen;
-            p->alnPool.insert(p->alnPool.end(), opsPool.begin() + t.opsOff, opsPool.begin() + t.opsOff + t.opsLen);
+        while (!frontier.empty()) {
+            std::vector<int> split;
+            for (int id : frontier) {
+                Node& nd = nodes[id];
+                if (nd.m == 0 || nd.n <= 0) {
+                    nd.fillOp = (nd.m == 0) ? EDLIB_EDOP_DELETE : EDLIB_EDOP_INSERT;
+                    nd.opsLen = nd.m + std::max(nd.n, 0);
+                    continue;
+                }
+                const long long matrixBytes = 20LL * ceil_div(nd.m, 64) * nd.n + 8LL * nd.n;  // cpp:1188-1190
+                if (matrixBytes < 1024 * 1024) leaves.push_back(id);
+                else split.push_back(id);
+            }
+            frontier.clear();
+            if (split.empty()) break;
+            std::vector<WTask> tasks;
+            tasks.reserve(split.size() * 2);
+            for (int id : split) {
+                const Node& nd = nodes[id];
+                const int leftW = nd.n / 2, rightW = nd.n - leftW;  // cpp:1247-1248
+                const WPlan pl = plan_w(nd.m, nd.n, MODE_NW, nd.best);  // band of the WHOLE node
+                WTask f;
+                f.pair = id;
+                f.qOff = nd.qOff;
+                f.tOff = nd.tOff;
+                f.m = nd.m;
+                f.n = leftW;
+                f.mode = MODE_NW;
+                f.flags = WF_STOPCOL | (pl.slide ? WF_SLIDE : 0);
+                f.dhi = pl.dhi;
+                f.stopCol = leftW - 1;
+                f.R = pl.R;
+                f.nWp = pl.nWp;
+                WTask r = f;
+                r.tOff = nd.tOff + (uint64_t)nd.n - 1;  // reversed: first symbol read is the last one
+                r.n = rightW;
+                r.flags |= WF_QREV | WF_TREV;
+                r.stopCol = rightW - 1;
+                tasks.push_back(std::move(f));
+                tasks.push_back(std::move(r));
+            }
+            runner.run(tasks);
+            for (size_t s = 0; s < split.size(); ++s) {
+                const int id = split[s];
+                const Node nd = nodes[id];
+                const int leftW = nd.n / 2, rightW = nd.n - leftW;
+                const int* colF = colPool.data() + tasks[2 * s].colOff;      // D_fwd[r][leftW-1]
+                const int* colR = colPool.data() + tasks[2 * s + 1].colOff;  // D_rev[r'][rightW-1]
+                auto L = [&](int h) { return h == 0 ? leftW : colF[h - 1]; };       // q[0..h) vs left half
+                auto Rr = [&](int sfx) { return sfx == 0 ? rightW : colR[sfx - 1]; };  // suffix of length sfx vs right half
+                int h = -1;
+                for (int cand = 1; cand <= nd.m - 1 && h < 0; ++cand)  // cpp:1327-1335
+                    if (L(cand) + Rr(nd.m - cand) == nd.best) h = cand;
+                if (h < 0 && L(0) + Rr(nd.m) == nd.best) h = 0;       // cpp:1337-1344
+                if (h < 0 && L(nd.m) + Rr(0) == nd.best) h = nd.m;    // cpp:1345-1353
+                if (h < 0) throw std::runtime_error("internal: Hirschberg split not found");
+                Node a, b;
+                a.pair = b.pair = nd.pair;
+                a.qOff = nd.qOff;
+                a.tOff = nd.tOff;
+                a.m = h;
+                a.n = leftW;
+                a.best = L(h);
+                b.qOff = nd.qOff + (uint64_t)h;
+                b.tOff = nd.tOff + (uint64_t)leftW;
+                b.m = nd.m - h;
+                b.n = rightW;
+                b.best = Rr(nd.m - h);
+                nodes[id].left = (int)nodes.size();
+                frontier.push_back((int)nodes.size());
+                nodes.push_back(a);
+                nodes[id].right = (int)nodes.size();
+                frontier.push_back((int)nodes.size());
+                nodes.push_back(b);
+            }
+            colPool.clear();
+        }
+        {
+            std::vector<WTask> tasks;
+            tasks.reserve(leaves.size());
+            for (int id : leaves) {
+                const Node& nd = nodes[id];
+                WTask t;
+                t.pair = id;
+                t.qOff = nd.qOff;
+                t.tOff = nd.tOff;
+                t.m = nd.m;
+                t.n = nd.n;
+                t.mode = MODE_NW;
+                t.flags = WF_STORE;
+                const WPlan pl = plan_w(nd.m, nd.n, MODE_NW, -1);
+                t.R = pl.R;
+                t.nWp = pl.nWp;
+                tasks.push_back(std::move(t));
+            }
+            runner.run(tasks);
+            for (const WTask& t : tasks) {
+                Node& nd = nodes[t.pair];
+                if (t.rec.best != nd.best) throw std::runtime_error("internal: path sweep disagrees with the distance");
+                nd.opsOff = t.opsOff;
+                nd.opsLen = t.opsLen;
+            }
+        }
+        // in-order concatenation (cpp:1388-1391)
+        std::vector<int> stack;
+        for (int i = 0; i < N; ++i) {
+            if (rootOf[i] < 0) continue;
+            p->alnStart[i] = (long long)p->alnPool.size();
+            stack.assign(1, rootOf[i]);
+            while (!stack.empty()) {
+                const int id = stack.back();
+                stack.pop_back();
+                const Node& nd = nodes[id];
+                if (nd.left >= 0) {
+                    stack.push_back(nd.right);
+                    stack.push_back(nd.left);
+                } else if (nd.fillOp >= 0) {
+                    p->alnPool.insert(p->alnPool.end(), (size_t)nd.opsLen, (uint8_t)nd.fillOp);
+                } else {
+                    p->alnPool.insert(p->alnPool.end(), opsPool.begin() + nd.opsOff, opsPool.begin() + nd.opsOff + nd.opsLen);
+                }
+            }
+            p->alnLen[i] = (int)(p->alnPool.size() - (size_t)p->alnStart[i]);
         }
     }
 

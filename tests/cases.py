@@ -89,6 +89,27 @@ def long_cases(seed, count):
         yield dict(q=q, t=t, k=k, mode=mode, task=rng.choice([0, 1]), eqs=None)
 
 
+def path_cases(seed, count):
+    """PATH beyond the reference's 1 MiB stored-matrix rule (Hirschberg, edlib.cpp:1188-1211):
+    short query vs long target (runTests.cpp random shapes), similar long pairs, infix reads."""
+    rng = random.Random(seed)
+    for _ in range(count):
+        alpha = bytes(rng.sample(range(256), rng.choice([2, 4, 4, 10])))
+        kind = rng.random()
+        if kind < 0.3:
+            q = rand_seq(rng, rng.randrange(50, 350), alpha)
+            t = rand_seq(rng, rng.randrange(9000, 14000), alpha)
+        elif kind < 0.7:
+            t = rand_seq(rng, rng.randrange(800, 4000), alpha)
+            q = mutate(rng, t, rng.choice([0.01, 0.05, 0.2, 0.5]), alpha)
+        else:
+            n = rng.randrange(2000, 12000)
+            t = rand_seq(rng, n, alpha)
+            a = rng.randrange(0, n - 600)
+            q = mutate(rng, t[a:a + rng.randrange(300, 2000)], 0.1, alpha)
+        yield dict(q=q, t=t, k=-1, mode=rng.choice([0, 0, 1, 2]), task=2, eqs=None)
+
+
 # Hand vectors with known answers from the reference's own tests (SURVEY.md section 8c):
 # bindings/python/test.py:6-73 and test/runTests.cpp:427-570, plus API probes measured on the
 # reference build.  (query, target, mode, task, k, equalities) -> expected fields.

@@ -57,6 +57,11 @@ def test_chunked_sweeps_and_overflow_retry():
     assert int(out.stdout.strip().splitlines()[-1]) > 1000
 
 
+def test_paths_beyond_the_stored_matrix_rule(emul):
+    import cases
+    assert parity.run_single(emul, 15, 60, gen=cases.path_cases) == 60
+
+
 def test_many_end_locations(emul):
     """Repeats: every column is an end location (ref runTests-style 'A*64 vs B*70' shapes)."""
     chk = parity.checker()

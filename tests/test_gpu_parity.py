@@ -35,6 +35,11 @@ def test_long_queries(lib):
     assert parity.run_single(lib, 23, 40, gen=cases.long_cases) == 40
 
 
+def test_paths_beyond_the_stored_matrix_rule(lib):
+    import cases
+    assert parity.run_single(lib, 15, 60, gen=cases.path_cases) == 60
+
+
 def test_many_end_locations(lib):
     chk = parity.checker()
     for q, t, mode in [(b"A" * 64, b"B" * 70, 2), (b"A" * 10, b"A" * 300, 2), (b"AC" * 20, b"AC" * 200, 2),
