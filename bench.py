@@ -33,7 +33,7 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-from edlib_b200 import workloads  # noqa: E402
+from edlib_b200 import sharding, workloads  # noqa: E402
 from edlib_b200._ffi import AlignConfig, AlignResult, EdlibLib, make_config, product_path  # noqa: E402
 
 READ_LEN = 150
@@ -240,14 +240,9 @@ def main():
 
     # ---- workload: shared target from rank 0 (one NCCL broadcast), own shard of reads per rank ----
     n_reads = args.reads
-    if rank == 0:
-        target = workloads.random_dna(TARGET_LEN, 1)
-    else:
-        target = np.empty(TARGET_LEN, dtype=np.uint8)
+    target = workloads.random_dna(TARGET_LEN, 1) if rank == 0 else None
     if world > 1:
-        tt = torch.from_numpy(target).to(dev)
-        dist.broadcast(tt, src=0)
-        target = tt.cpu().numpy()
+        target = sharding.broadcast_target(target, TARGET_LEN, dev)  # the single NCCL broadcast of the path
     reads = np.empty((n_reads, READ_LEN), dtype=np.uint8)
     workloads._synth().synth_reads(target.ctypes.data, TARGET_LEN, reads.ctypes.data, n_reads, READ_LEN, 0.03, 42 + rank)
     qptr, qlen, tptr, tlen = pointer_arrays(reads, target)
@@ -302,9 +297,9 @@ def main():
     L.edlibB200FreeResults(res.ctypes.data, n_reads)
     L.edlibB200BatchFree(batch)
     if world > 1:
-        mine = torch.from_numpy(eds).to(dev)
-        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, gathered, dst=0)
+        all_eds = sharding.gather_int32(eds, dev)  # the gather of results on rank 0
+        if rank == 0:
+            assert len(all_eds) == world * n_reads
 
     # ---- e2e: reference-facing call with host buffers ------------------------------------------------
     e2e_s, h2d, d2h = [], 0, 0

@@ -523,8 +523,10 @@ void Engine::compute(Prepared* p) {
 
     // per-pair sweep outcome before the "-1" rule
     std::vector<int> best(N, -1), cnt(N, 0);
-    std::vector<std::vector<int>> posOf;  // only filled for W-path pairs and K1 multi-chunk/overflow pairs
-    posOf.resize(N);
+    std::vector<long long> posStart(N, -1);  // end columns of pair i: posPool[posStart[i] .. +posLen[i])
+    std::vector<int> posLen(N, 0);
+    std::vector<int> posPool;
+    posPool.reserve((size_t)N + 16);
 
     // ---- classification -----------------------------------------------------------------
     std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, nw32) -> pairs
@@ -662,8 +664,9 @@ void Engine::compute(Prepared* p) {
                 best[pair] = (total > 0) ? b : 0x7fffffff;
                 if (total > 0x7fffffffLL / 4) throw std::runtime_error("end-location list too large");
                 cnt[pair] = (int)total;
-                std::vector<int>& dst = posOf[pair];
-                dst.clear();
+                std::vector<int>& dst = posPool;
+                posStart[pair] = (long long)posPool.size();
+                posLen[pair] = 0;
                 if (total == 0) continue;
                 bool complete = true;
                 for (int c = 0; c < chunks; ++c) {
@@ -679,6 +682,7 @@ void Engine::compute(Prepared* p) {
                         }
                     }
                 }
+                posLen[pair] = (int)((long long)posPool.size() - posStart[pair]);
                 if (!complete) {
                     incomplete.push_back(sub[s]);
                     missing += total;
@@ -769,10 +773,10 @@ void Engine::compute(Prepared* p) {
                 }
                 best[t.pair] = t.rec.cnt > 0 ? t.rec.best : 0x7fffffff;
                 cnt[t.pair] = t.rec.cnt;
-                std::vector<int>& dst = posOf[t.pair];
-                dst.clear();
-                for (int q = 0; q < std::min(t.rec.cnt, KPOS); ++q) dst.push_back(t.rec.pos[q]);
-                dst.insert(dst.end(), t.extra.begin(), t.extra.end());
+                posStart[t.pair] = (long long)posPool.size();
+                for (int q = 0; q < std::min(t.rec.cnt, KPOS); ++q) posPool.push_back(t.rec.pos[q]);
+                posPool.insert(posPool.end(), t.extra.begin(), t.extra.end());
+                posLen[t.pair] = (int)((long long)posPool.size() - posStart[t.pair]);
             }
             pending.swap(later);
             if (kRound < (1 << 29)) kRound *= 2;
@@ -797,10 +801,9 @@ void Engine::compute(Prepared* p) {
         // ref cpp:670, 681-693: the padded bottom cell of column W-1 shows up as end location -1
         const int W64 = ceil_div(m, 64) * 64 - m;
         if (best[i] == m && W64 > 0) p->endPool.push_back(-1);
-        if ((int)posOf[i].size() != cnt[i]) throw std::runtime_error("internal: end-location count mismatch");
-        p->endPool.insert(p->endPool.end(), posOf[i].begin(), posOf[i].end());
+        if (posLen[i] != cnt[i]) throw std::runtime_error("internal: end-location count mismatch");
+        p->endPool.insert(p->endPool.end(), posPool.begin() + posStart[i], posPool.begin() + posStart[i] + posLen[i]);
         p->endCount[i] = (int)(p->endPool.size() - (size_t)p->endStart[i]);
-        std::vector<int>().swap(posOf[i]);
     }
 
     // ---- start locations (ref cpp:228-272) ------------------------------------------------

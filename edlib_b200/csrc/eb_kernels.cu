@@ -332,6 +332,10 @@ struct CudaBackend : Backend {
         sms = prop.multiProcessorCount;
         maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
         EB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        cudaMemPool_t mp;
+        EB_CUDA(cudaDeviceGetDefaultMemPool(&mp, dev));
+        uint64_t keep = UINT64_MAX;
+        EB_CUDA(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     ~CudaBackend() override {
         for (auto& t : timed) {
@@ -339,20 +343,47 @@ struct CudaBackend : Backend {
             cudaEventDestroy(t.b);
         }
         for (auto e : pool) cudaEventDestroy(e);
+        for (auto& b : hostBlocks) cudaFreeHost(b.p);
         if (stream) cudaStreamDestroy(stream);
     }
+    // Device memory comes from the stream-ordered pool (cudaMallocAsync) with an unlimited release
+    // threshold: after the first batch every alloc/free is a pool hit, ordered on the one stream all
+    // work is issued on, so no cudaMalloc/cudaFree (device-wide syncs) remain on the call path.
     void* alloc(size_t bytes) override {
         void* p = nullptr;
-        EB_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        EB_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, stream));
         return p;
     }
-    void free(void* p) override { cudaFree(p); }
+    void free(void* p) override { cudaFreeAsync(p, stream); }
+    // Pinned staging blocks are kept and reused (cudaHostAlloc is slow and synchronising).
+    struct HostBlock {
+        void* p;
+        size_t bytes;
+        bool used;
+    };
+    std::vector<HostBlock> hostBlocks;
     void* alloc_host(size_t bytes) override {
+        for (auto& b : hostBlocks)
+            if (!b.used && b.bytes >= bytes) {
+                b.used = true;
+                return b.p;
+            }
+        for (size_t i = 0; i < hostBlocks.size(); ++i)  // drop an unused smaller block before growing
+            if (!hostBlocks[i].used) {
+                cudaFreeHost(hostBlocks[i].p);
+                hostBlocks.erase(hostBlocks.begin() + i);
+                break;
+            }
         void* p = nullptr;
-        EB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault));
+        const size_t want = bytes + bytes / 4 + 4096;
+        EB_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        hostBlocks.push_back(HostBlock{p, want, true});
         return p;
     }
-    void free_host(void* p) override { cudaFreeHost(p); }
+    void free_host(void* p) override {
+        for (auto& b : hostBlocks)
+            if (b.p == p) b.used = false;
+    }
     void h2d(void* d, const void* s, size_t n) override {
         if (n) EB_CUDA(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream));
     }
@@ -443,7 +474,15 @@ struct CudaBackend : Backend {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_kernel<NW, MODE_HW, false>, block, smem) != cudaSuccess) perSm = 1;
         return perSm < 1 ? 1 : perSm;
     }
+    std::vector<int> shapeCache;  // [nw*1024 + ncodes] -> block | resident << 12, 0 = unknown
     void k1_shape(int nw, int ncodes, int* blockThreads, int* residentCtas) override {
+        if (shapeCache.empty()) shapeCache.assign(9 * 1024, 0);
+        const int key = nw * 1024 + (ncodes < 1024 ? ncodes : 1023);
+        if (ncodes < 1023 && shapeCache[key]) {
+            *blockThreads = shapeCache[key] & 0xfff;
+            *residentCtas = shapeCache[key] >> 12;
+            return;
+        }
         int block;
         size_t smem;
         k1_block(nw, ncodes, &block, &smem);
@@ -460,6 +499,7 @@ struct CudaBackend : Backend {
         }
         *blockThreads = block;
         *residentCtas = perSm * sms;
+        if (ncodes < 1023) shapeCache[key] = block | ((perSm * sms) << 12);
     }
     template <int NW, int MODE>
     void launch_k1_t(const K1Params& p) {
