@@ -44,7 +44,7 @@ MODE_HW, TASK_DISTANCE = 2, 0
 class Stats(C.Structure):  # include/edlib_b200.h EdlibB200Stats
     _fields_ = [("kernelMs", C.c_double), ("k1Ms", C.c_double), ("launches", C.c_int), ("reserved", C.c_int),
                 ("h2dBytes", C.c_longlong), ("d2hBytes", C.c_longlong), ("k1Cells", C.c_longlong),
-                ("wCells", C.c_longlong)]
+                ("wCells", C.c_longlong), ("filterDecided", C.c_longlong), ("filterFallback", C.c_longlong)]
 
 
 def measured_peaks():
@@ -281,6 +281,7 @@ def main():
         k1_ms.append(st.k1Ms)
         kernel_ms.append(st.kernelMs)
         launches += st.launches
+        filt = (st.filterDecided, st.filterFallback)
     barrier()
     clocks = sampler.stop()
     elapsed = torch.tensor([sum(step_s)], dtype=torch.float64, device=dev)
@@ -354,11 +355,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k1_kernel<5,HW>", "kernel_ms": k1 * 1000.0,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k1_kernel (all launches of a step: 64-row prefix sweep k1_kernel<2,HW,range> + full-width "
+                                   "k1_kernel<5,HW> over the undecided reads)", "kernel_ms": k1 * 1000.0,
                          "bytes_algorithmic": bytes_alg, "int_lane_ops_per_s": lane_ops / k1,
                          "note": "integer-issue bound (see DESIGN.md): HBM fraction is low by construction"},
             "cpu_baseline": cpu,
             "mean_edit_distance": float(eds.mean()), "mean_num_locations": float(nloc.mean()),
+            "filter": {"decided": int(filt[0]), "fallback": int(filt[1])},
             "kernel_ms_per_step": float(np.mean(kernel_ms)),
         }
         print(json.dumps(line))

@@ -187,6 +187,8 @@ EDLIB_API int edlibB200BatchCompute(EdlibB200Batch* batch, EdlibB200Stats* stats
         statsOut->d2hBytes = e->stats.d2hBytes;
         statsOut->k1Cells = e->stats.k1Cells;
         statsOut->wCells = e->stats.wCells;
+        statsOut->filterDecided = e->stats.filterDecided;
+        statsOut->filterFallback = e->stats.filterFallback;
     }
     return EDLIB_STATUS_OK;
 }
@@ -221,6 +223,8 @@ EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {
     s->d2hBytes = g_engine->stats.d2hBytes;
     s->k1Cells = g_engine->stats.k1Cells;
     s->wCells = g_engine->stats.wCells;
+    s->filterDecided = g_engine->stats.filterDecided;
+    s->filterFallback = g_engine->stats.filterFallback;
 }
 
 }  // extern "C"

@@ -70,6 +70,9 @@ struct K1Params {
     int* ovfCount;
     int ovfCap;
     uint32_t two;            // the constant 2, passed as data so ptxas keeps IMADs (eb_core.h: mad_lo)
+    int prefixLen;           // > 0: sweep only the first prefixLen rows of every query (candidate filter)
+    int rangeMode;           // 1: record {count, first, last} of the columns whose score is <= kInit
+                             //    (Rec.cnt, Rec.pos[0], Rec.last) instead of the running minimum
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -97,7 +100,7 @@ struct WJob {
     int dhi;           // WF_SLIDE: largest diagonal c - r inside the band
     int stopCol;       // WF_STOPCOL: column whose scores are dumped
     int rec;           // index of the output Rec
-    int rsv;
+    int trackFrom;     // HW/SHW: first column whose score may be recorded (earlier ones are halo)
 };
 
 struct WParams {

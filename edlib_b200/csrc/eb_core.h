@@ -241,8 +241,14 @@ EB_HD void k1_init(K1State<NW>& st, int m, int kInit) {
 }
 
 // Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
-template <int NW>
+template <int NW, bool RANGE = false>
 EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
+    if (RANGE) {  // candidate filter: every column at or below the fixed threshold, as a range
+        if (st.cnt == 0) rec->pos[0] = column;
+        rec->last = column;
+        st.cnt++;
+        return;
+    }
     if (score < st.best) {
         st.best = score;
         st.cnt = 0;
@@ -275,7 +281,7 @@ struct PtrSyms {
 // running minimum and its columns are recorded; without it only the state advances (halo
 // columns of a chunk).  Columns go four at a time: the four last-row scores stay in registers
 // and are compared against the running minimum once per group (events are rare).
-template <int NW, bool TOP_ONE, bool TRACK, bool FMA_SHIFT = false, class Acc, class Syms>
+template <int NW, bool TOP_ONE, bool TRACK, bool FMA_SHIFT = false, bool RANGE = false, class Acc, class Syms>
 EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int count, int cAbs,
                       Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     int i = 0;
@@ -283,7 +289,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
         k1_step<NW, TOP_ONE, FMA_SHIFT>(st.Pv, st.Mv, Eq, st.score, st.two);
-        if (TRACK && st.score <= st.best) k1_event<NW>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+        if (TRACK && st.score <= st.best) k1_event<NW, RANGE>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
         ++i;
     }
     for (; i + 4 <= count; i += 4) {  // body: four symbols per 32-bit read
@@ -303,7 +309,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
             if (lo <= st.best) {
                 EB_UNROLL
                 for (int j = 0; j < 4; ++j)
-                    if (sc[j] <= st.best) k1_event<NW>(st, sc[j], cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
+                    if (sc[j] <= st.best) k1_event<NW, RANGE>(st, sc[j], cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
             }
         }
     }
@@ -311,7 +317,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
         k1_step<NW, TOP_ONE, FMA_SHIFT>(st.Pv, st.Mv, Eq, st.score, st.two);
-        if (TRACK && st.score <= st.best) k1_event<NW>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+        if (TRACK && st.score <= st.best) k1_event<NW, RANGE>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
     }
 }
 
@@ -364,7 +370,7 @@ EB_HD K1Chunk k1_chunk(const K1Params& p, int chunk) {
 template <int NW, class Acc>
 EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     const int pair = p.readList[slot];
-    const int m = p.qlen[pair];
+    const int m = p.prefixLen > 0 ? p.prefixLen : p.qlen[pair];
     const uint8_t* q = p.qcodes + p.qoff[pair];
     const int recIdx = chunk * p.numReads + slot;
     Rec* rec = p.recs + recIdx;
@@ -373,7 +379,10 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     k1_init<NW>(st, m, p.kInit[slot]);
     st.two = p.two;
     const K1Chunk g = k1_chunk(p, chunk);
-    if (p.mode == MODE_HW) {
+    if (p.mode == MODE_HW && p.rangeMode) {
+        k1_columns<NW, false, false, true, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+    } else if (p.mode == MODE_HW) {
         k1_columns<NW, false, false, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
         k1_columns<NW, false, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_SHW) {
@@ -554,7 +563,7 @@ EB_HD void w_sweep(const WParams& P, int jobIdx) {
                 }
             }
             if (hout) B::scatter8(hout, U((uint32_t)c), hp | (hm << 1), isBot);
-            if (track) {
+            if (track && c >= J.trackFrom) {
                 const Pr ev = (lane == U((uint32_t)ownerLane)) & (sb <= U((uint32_t)bestU));
                 if (B::any(ev)) {  // ref cpp:658-673
                     const int s = (int)B::bcast(sb, ownerLane);

@@ -31,6 +31,10 @@ EngineTunables::EngineTunables() {
     k1MinGroup = env_int("EDLIB_B200_K1_MIN_GROUP", k1MinGroup);
     k1MinChunk = env_int("EDLIB_B200_K1_MIN_CHUNK", k1MinChunk);
     ovfCap = env_int("EDLIB_B200_OVF_CAP", ovfCap);
+    filterK0 = env_int("EDLIB_B200_FILTER_K0", filterK0);
+    filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
+    filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
+    filterMinTarget = env_int("EDLIB_B200_FILTER_MIN_TARGET", filterMinTarget);
     const int sliceMb = env_int("EDLIB_B200_SLICE_MB", 0);
     if (sliceMb > 0) sliceBytes = (size_t)sliceMb << 20;
 }
@@ -74,7 +78,7 @@ struct Target {
 // One warp-per-alignment sweep as seen by the host.
 struct WTask {
     uint64_t qOff = 0, tOff = 0;
-    int m = 0, n = 0, mode = 0, flags = 0, kInit = 0, dhi = 0, stopCol = -1;
+    int m = 0, n = 0, mode = 0, flags = 0, kInit = 0, dhi = 0, stopCol = -1, trackFrom = 0;
     int R = 1, nWp = 0;
     int pair = -1, tag = 0;
     bool wantPositions = false;  // the caller needs every end position, not just best/cnt/last
@@ -379,6 +383,7 @@ struct WRunner {
             j.kInit = t.kInit;
             j.dhi = t.dhi;
             j.stopCol = t.stopCol;
+            j.trackFrom = t.trackFrom;
             j.rec = s;
             j.peqOff = peqWords;
             peqWords += (uint64_t)p->ncodes * t.nWp;
@@ -520,6 +525,7 @@ void Engine::compute(Prepared* p) {
     p->alnLen.assign(N, 0);
     p->alnPool.clear();
     stats.k1Cells = stats.wCells = 0;
+    stats.filterDecided = stats.filterFallback = 0;
 
     // per-pair sweep outcome before the "-1" rule
     std::vector<int> best(N, -1), cnt(N, 0);
@@ -555,18 +561,17 @@ void Engine::compute(Prepared* p) {
         const Target& tg = p->tg[t];
         const int G = (int)list.size();
         const int n = tg.len;
-        const int halo = 64 * nw;
 
         // Chunk geometry: a HW sweep may be cut into target chunks (each re-started 2*m columns
         // early, exact because no HW path spans more than 2*m target symbols) so that a small
         // group still fills the machine.
-        int blockThreads = 256, residentCtas = 1;
-        be->k1_shape(nw, p->ncodes, &blockThreads, &residentCtas);
-        auto geometry = [&](int g, int& chunks, int& chunkLen) {
+        auto geometry = [&](int g, int nwL, int& chunks, int& chunkLen) {
+            int blockThreads = 256, residentCtas = 1;
+            be->k1_shape(nwL, p->ncodes, &blockThreads, &residentCtas);
             chunks = 1;
             chunkLen = (int)round_up((size_t)n, 16);
             if (mode != MODE_HW) return;
-            const int minChunk = std::max(tun.k1MinChunk, 8 * halo);
+            const int minChunk = std::max(tun.k1MinChunk, 8 * 64 * nwL);
             const long long maxChunks = std::max<long long>(1, n / minChunk);
             const long long tiles = ceil_div(g, blockThreads);
             // Few CTAs: cut until the device is covered twice.  Many CTAs: pick the cut (<= 8) whose
@@ -589,9 +594,9 @@ void Engine::compute(Prepared* p) {
             chunks = ceil_div(n, chunkLen);
         };
 
-        // One launch over the reads `sub` (indices into `list`) with sentinels subK.
-        auto launch = [&](const std::vector<int>& sub, const std::vector<int>& subK, int chunks, int chunkLen, int cap,
-                          std::vector<Rec>& outRecs, std::vector<Ovf>& outOvf) {
+        // One launch over the reads `sub` (indices into `list`) with sentinels / thresholds subK.
+        auto launch = [&](const std::vector<int>& sub, const std::vector<int>& subK, int nwL, int chunks, int chunkLen, int cap,
+                          int prefixLen, int rangeMode, std::vector<Rec>& outRecs, std::vector<Ovf>& outOvf) {
             const int g = (int)sub.size();
             std::vector<int> rl(g);
             for (int s = 0; s < g; ++s) rl[s] = list[sub[s]];
@@ -618,13 +623,15 @@ void Engine::compute(Prepared* p) {
             kp.eqtab = p->hasEq ? p->dEqtab.p : nullptr;
             kp.chunks = chunks;
             kp.chunkLen = chunkLen;
-            kp.halo = halo;
+            kp.halo = 64 * nwL;
             kp.recs = dRecs.p;
             kp.ovf = dOvf.p;
             kp.ovfCount = dCount.p;
             kp.ovfCap = cap;
             kp.two = 2u;
-            be->launch_k1(kp, nw);
+            kp.prefixLen = prefixLen;
+            kp.rangeMode = rangeMode;
+            be->launch_k1(kp, nwL);
             outRecs.resize((size_t)g * chunks);
             dRecs.download(outRecs.data(), outRecs.size());
             stats.d2hBytes += (long long)outRecs.size() * (long long)sizeof(Rec);
@@ -690,35 +697,140 @@ void Engine::compute(Prepared* p) {
             }
         };
 
-        int chunks = 1, chunkLen = 0;
-        geometry(G, chunks, chunkLen);
-        std::vector<int> slots(G), kInit(G);
+        std::vector<int> bound(G);  // largest distance that still counts as found, per read
         for (int s = 0; s < G; ++s) {
-            slots[s] = s;
             const int m = p->qlen[list[s]];
-            kInit[s] = ((k < 0 || k > m) ? m : k) + 1;  // distances never exceed m in HW/SHW (ref cpp:566-568)
+            bound[s] = (k < 0 || k > m) ? m : k;  // distances never exceed m in HW/SHW (ref cpp:566-568)
             stats.k1Cells += (long long)m * n;
         }
-        std::vector<Rec> recs;
-        std::vector<Ovf> ovf;
-        std::vector<int> incomplete;
-        long long missing = 0;
-        launch(slots, kInit, chunks, chunkLen, 0, recs, ovf);
-        merge(slots, chunks, recs, nullptr, incomplete, missing);
-        if (!incomplete.empty()) {
-            // Second pass over the few reads with more than KPOS end positions in one chunk:
-            // start from the known minimum so that only final positions are recorded, with a
-            // list sized from the counts of the first pass, on a finer chunking of the target.
-            std::vector<int> subK(incomplete.size());
-            for (size_t s = 0; s < incomplete.size(); ++s) subK[s] = best[list[incomplete[s]]];
-            int chunks2 = 1, chunkLen2 = 0;
-            geometry((int)incomplete.size(), chunks2, chunkLen2);
-            std::vector<Rec> recs2;
-            std::vector<Ovf> ovf2;
-            std::vector<int> still;
-            long long dummy = 0;
-            launch(incomplete, subK, chunks2, chunkLen2, (int)missing + 16, recs2, ovf2);
-            merge(incomplete, chunks2, recs2, &ovf2, still, dummy);
+
+        // ---- candidate filter (HW): prefix sweep, then windows around the candidates ----------
+        std::vector<int> direct;  // reads that take the plain full sweep
+        direct.reserve(G);
+        const int P = 64;
+        if (mode == MODE_HW && tun.filterK0 > 0 && n >= tun.filterMinTarget) {
+            std::vector<int> cand, thr;
+            for (int s = 0; s < G; ++s) {
+                if (p->qlen[list[s]] >= std::max(tun.filterMinLen, P + 1)) {
+                    cand.push_back(s);
+                    thr.push_back(std::min(tun.filterK0, bound[s]));
+                } else {
+                    direct.push_back(s);
+                }
+            }
+            if (!cand.empty()) {
+                int chunksA = 1, chunkLenA = 0;
+                geometry((int)cand.size(), 2, chunksA, chunkLenA);
+                std::vector<Rec> ra;
+                std::vector<Ovf> none;
+                launch(cand, thr, 2, chunksA, chunkLenA, 0, P, 1, ra, none);
+                const int g = (int)cand.size();
+                std::vector<WTask> tasks;
+                std::vector<int> taskSlot;
+                auto undecided = [&](int s, int t) {  // the filter cannot decide: bound above its threshold?
+                    if (t == bound[s]) {
+                        best[list[s]] = 0x7fffffff;   // nothing within the caller's k: final
+                        cnt[list[s]] = 0;
+                        stats.filterDecided++;
+                    } else {
+                        direct.push_back(s);
+                        stats.filterFallback++;
+                    }
+                };
+                for (int i = 0; i < g; ++i) {
+                    const int s = cand[i];
+                    const int pair = list[s], m = p->qlen[pair], t = thr[i];
+                    long long total = 0;
+                    int first = 0x7fffffff, last = -1;
+                    for (int c = 0; c < chunksA; ++c) {
+                        const Rec& r = ra[(size_t)c * g + i];
+                        if (r.cnt <= 0) continue;
+                        total += r.cnt;
+                        first = std::min(first, r.pos[0]);
+                        last = std::max(last, r.last);
+                    }
+                    // An alignment with distance d <= t ending at column e passes, after its first P rows,
+                    // through a column c' with prefix score <= d and e in [c'+(m-P)-d, c'+(m-P)+d].
+                    const long long lo = (long long)first + (m - P) - t;
+                    long long hi = (long long)last + (m - P) + t;
+                    if (hi > n - 1) hi = n - 1;
+                    if (total == 0 || lo > hi) {
+                        undecided(s, t);
+                        continue;
+                    }
+                    if (last - first > tun.filterSpread) {
+                        direct.push_back(s);
+                        stats.filterFallback++;
+                        continue;
+                    }
+                    const long long ws = std::max<long long>(0, lo - 2LL * m);  // HW restart: exact after 2m columns
+                    WTask w;
+                    w.pair = pair;
+                    w.tag = (int)ws;
+                    w.qOff = p->qoff[pair];
+                    w.tOff = tg.off + (uint64_t)ws;
+                    w.m = m;
+                    w.n = (int)(hi - ws + 1);
+                    w.mode = MODE_HW;
+                    w.kInit = t + 1;
+                    w.trackFrom = (int)(lo - ws);
+                    w.wantPositions = true;
+                    const WPlan pl = plan_w(m, w.n, MODE_HW, -1);
+                    w.R = pl.R;
+                    w.nWp = pl.nWp;
+                    tasks.push_back(std::move(w));
+                    taskSlot.push_back(s);
+                }
+                WRunner fr{this, be, p, nullptr, nullptr};
+                fr.run(tasks);
+                for (size_t j = 0; j < tasks.size(); ++j) {
+                    const WTask& w = tasks[j];
+                    const int s = taskSlot[j];
+                    const int t = w.kInit - 1;
+                    if (w.rec.cnt <= 0 || w.rec.best > t) {  // the window minimum is above the threshold
+                        undecided(s, t);
+                        continue;
+                    }
+                    stats.filterDecided++;
+                    best[w.pair] = w.rec.best;
+                    cnt[w.pair] = w.rec.cnt;
+                    posStart[w.pair] = (long long)posPool.size();
+                    for (int q = 0; q < std::min(w.rec.cnt, KPOS); ++q) posPool.push_back(w.rec.pos[q] + w.tag);
+                    for (int e : w.extra) posPool.push_back(e + w.tag);
+                    posLen[w.pair] = (int)((long long)posPool.size() - posStart[w.pair]);
+                }
+            }
+        } else {
+            for (int s = 0; s < G; ++s) direct.push_back(s);
+        }
+
+        // ---- plain full sweep of the remaining reads ------------------------------------------
+        if (!direct.empty()) {
+            int chunks = 1, chunkLen = 0;
+            geometry((int)direct.size(), nw, chunks, chunkLen);
+            std::vector<int> kInit(direct.size());
+            for (size_t s = 0; s < direct.size(); ++s) kInit[s] = bound[direct[s]] + 1;
+            std::vector<Rec> recs;
+            std::vector<Ovf> ovf;
+            std::vector<int> incomplete;
+            long long missing = 0;
+            launch(direct, kInit, nw, chunks, chunkLen, 0, 0, 0, recs, ovf);
+            merge(direct, chunks, recs, nullptr, incomplete, missing);
+            if (!incomplete.empty()) {
+                // Second pass over the few reads with more than KPOS end positions in one chunk:
+                // start from the known minimum so that only final positions are recorded, with a
+                // list sized from the counts of the first pass, on a finer chunking of the target.
+                std::vector<int> subK(incomplete.size());
+                for (size_t s = 0; s < incomplete.size(); ++s) subK[s] = best[list[incomplete[s]]];
+                int chunks2 = 1, chunkLen2 = 0;
+                geometry((int)incomplete.size(), nw, chunks2, chunkLen2);
+                std::vector<Rec> recs2;
+                std::vector<Ovf> ovf2;
+                std::vector<int> still;
+                long long dummy = 0;
+                launch(incomplete, subK, nw, chunks2, chunkLen2, (int)missing + 16, 0, 0, recs2, ovf2);
+                merge(incomplete, chunks2, recs2, &ovf2, still, dummy);
+            }
         }
     }
 

@@ -57,6 +57,13 @@ struct EngineTunables {
     int k1MinChunk = 8192;        // smallest target chunk (columns) when one HW sweep is split
     int ovfCap = 1 << 20;         // overflow entries per launch before the exact-size retry
     size_t sliceBytes = 1ull << 30;  // device memory budget of one slice of W jobs
+    // Candidate filter for HW sweeps of reads over a shared target (0 disables): a 64-row prefix
+    // sweep finds the columns where the prefix matches within filterK0; only windows around them
+    // are swept with the whole read; reads the filter cannot decide take the plain full sweep.
+    int filterK0 = 12;
+    int filterMinLen = 96;        // shortest query worth filtering
+    int filterSpread = 1024;      // widest candidate range verified as one window
+    int filterMinTarget = 65536;  // shortest target worth filtering
     EngineTunables();             // reads EDLIB_B200_* environment overrides (used by tests)
 };
 
@@ -67,6 +74,7 @@ struct EngineStats {
     long long h2dBytes = 0, d2hBytes = 0;
     long long k1Cells = 0;  // nominal cells (sum m*n) handled by K1
     long long wCells = 0;   // nominal cells of the distance pass handled by W
+    long long filterDecided = 0, filterFallback = 0;
 };
 
 class Prepared;  // a batch whose inputs are resident on the device

@@ -162,7 +162,7 @@ EB_D void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
                  : "memory");
 }
 
-template <int NW, int MODE, bool FMA_SHIFT>
+template <int NW, int MODE, bool FMA_SHIFT, bool RANGE = false>
 __global__ void k1_kernel(const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -206,7 +206,7 @@ __global__ void k1_kernel(const K1Params p) {
     int recIdx = 0;
     if (active) {
         const int pair = p.readList[slot];
-        const int m = p.qlen[pair];
+        const int m = p.prefixLen > 0 ? p.prefixLen : p.qlen[pair];
         k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE, p.ncodes, p.eqtab);
         k1_init<NW>(st, m, p.kInit[slot]);
         st.two = p.two;
@@ -223,8 +223,8 @@ __global__ void k1_kernel(const K1Params p) {
             const uint32_t sa = tileAddr[i & 1];
             if (MODE == MODE_HW) {
                 const int mid = min(max(g.cs, a), b);               // columns before cs are halo
-                if (mid > a) k1_columns<NW, false, false, FMA_SHIFT>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-                if (b > mid) k1_columns<NW, false, true, FMA_SHIFT>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (mid > a) k1_columns<NW, false, false, FMA_SHIFT, RANGE>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (b > mid) k1_columns<NW, false, true, FMA_SHIFT, RANGE>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             } else if (MODE == MODE_SHW) {
                 k1_columns<NW, true, true, FMA_SHIFT>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             } else {
@@ -506,6 +506,22 @@ struct CudaBackend : Backend {
         if (fmaShift) launch_k1_v<NW, MODE, true>(p);
         else launch_k1_v<NW, MODE, false>(p);
     }
+    // candidate-filter sweep: 64-row prefixes (two words), HW, range recording
+    void launch_k1_range(const K1Params& p) {
+        int block;
+        size_t smem;
+        k1_block(2, p.ncodes, &block, &smem);
+        if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
+        dim3 grid((p.numReads + block - 1) / block, p.chunks);
+        if (fmaShift) {
+            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k1_kernel<2, MODE_HW, true, true><<<grid, block, smem, stream>>>(p);
+        } else {
+            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k1_kernel<2, MODE_HW, false, true><<<grid, block, smem, stream>>>(p);
+        }
+        check_launch("k1 range");
+    }
     template <int NW>
     void launch_k1_m(const K1Params& p) {
         if (p.mode == MODE_HW) launch_k1_t<NW, MODE_HW>(p);
@@ -514,6 +530,11 @@ struct CudaBackend : Backend {
     }
     void launch_k1(const K1Params& p, int nw) override {
         Scope s(this, "k1");
+        if (p.rangeMode) {
+            if (nw != 2 || p.mode != MODE_HW) throw std::runtime_error("range mode needs the 2-word HW kernel");
+            launch_k1_range(p);
+            return;
+        }
         switch (nw) {
             case 1: launch_k1_m<1>(p); break;
             case 2: launch_k1_m<2>(p); break;

@@ -34,6 +34,8 @@ typedef struct {
     long long d2hBytes;   /* device->host bytes */
     long long k1Cells;    /* nominal DP cells (sum queryLength*targetLength) swept by that kernel */
     long long wCells;     /* nominal DP cells of the distance pass swept by the warp kernel */
+    long long filterDecided;  /* alignments settled by the candidate filter (prefix sweep + window) */
+    long long filterFallback; /* alignments the filter could not decide (took the plain full sweep) */
 } EdlibB200Stats;
 
 /* Selects the CUDA device this process will use; call before any other entry point (one

@@ -110,6 +110,34 @@ def path_cases(seed, count):
         yield dict(q=q, t=t, k=-1, mode=rng.choice([0, 0, 1, 2]), task=2, eqs=None)
 
 
+def filter_cases(seed, count):
+    """HW batches of reads (>= 96 bp) over one shared target: clean hits, hits above the filter
+    threshold, unrelated reads, exact copies inside a repeated target segment (several far-apart
+    candidate clusters), explicit and free k -- every branch of the candidate filter."""
+    rng = random.Random(seed)
+    alpha = b"ACGT"
+    for _ in range(count):
+        t = rand_seq(rng, rng.choice([3000, 8000, 20000]), alpha)
+        if rng.random() < 0.3:
+            t = t[:1500] + t[100:700] + t[1500:]
+        qs = []
+        for _ in range(rng.choice([8, 40, 100])):
+            L = rng.choice([96, 100, 128, 150, 150, 200, 256])
+            r = rng.random()
+            if r < 0.7:
+                a = rng.randrange(0, len(t) - L - 10)
+                q = mutate(rng, t[a:a + L + 8], rng.choice([0, 0.02, 0.05, 0.12, 0.3]), alpha)[:L]
+            elif r < 0.85:
+                q = rand_seq(rng, L, alpha)
+            else:
+                a = rng.randrange(0, max(1, len(t) - L))
+                q = t[a:a + L]
+            if len(q) < 96:
+                q = q + rand_seq(rng, 96 - len(q), alpha)
+            qs.append(q)
+        yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 3, 10, 40]), mode=2, task=rng.randrange(3), eqs=None)
+
+
 # Hand vectors with known answers from the reference's own tests (SURVEY.md section 8c):
 # bindings/python/test.py:6-73 and test/runTests.cpp:427-570, plus API probes measured on the
 # reference build.  (query, target, mode, task, k, equalities) -> expected fields.

@@ -62,6 +62,22 @@ def test_paths_beyond_the_stored_matrix_rule(emul):
     assert parity.run_single(emul, 15, 60, gen=cases.path_cases) == 60
 
 
+def test_candidate_filter_all_branches():
+    """Prefix filter + window verification + fallbacks, forced on for small targets (separate
+    process: tunables are read once), in two settings incl. a tight threshold/spread."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 16, 25, gen=cases.filter_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra in ({}, {"EDLIB_B200_FILTER_K0": "4", "EDLIB_B200_FILTER_SPREAD": "64", "EDLIB_B200_K1_MIN_CHUNK": "64",
+                       "EDLIB_EMUL_SMS": "64"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 500
+
+
 def test_many_end_locations(emul):
     """Repeats: every column is an end location (ref runTests-style 'A*64 vs B*70' shapes)."""
     chk = parity.checker()

@@ -40,6 +40,22 @@ def test_paths_beyond_the_stored_matrix_rule(lib):
     assert parity.run_single(lib, 15, 60, gen=cases.path_cases) == 60
 
 
+def test_candidate_filter_all_branches():
+    """Same as the CPU test of that name, on the GPU: the filter forced on for small targets."""
+    import subprocess
+    from edlib_b200._ffi import REPO
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases\n"
+        "from helpers import product\n"
+        "print(parity.run_batches(product(), 26, 40, gen=cases.filter_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra in ({}, {"EDLIB_B200_FILTER_K0": "4", "EDLIB_B200_FILTER_SPREAD": "64", "EDLIB_B200_K1_MIN_CHUNK": "64"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 500
+
+
 def test_many_end_locations(lib):
     chk = parity.checker()
     for q, t, mode in [(b"A" * 64, b"B" * 70, 2), (b"A" * 10, b"A" * 300, 2), (b"AC" * 20, b"AC" * 200, 2),
