@@ -574,20 +574,19 @@ void Engine::compute(Prepared* p) {
             const int minChunk = std::max(tun.k1MinChunk, 8 * 64 * nwL);
             const long long maxChunks = std::max<long long>(1, n / minChunk);
             const long long tiles = ceil_div(g, blockThreads);
-            // Few CTAs: cut until the device is covered twice.  Many CTAs: pick the cut (<= 8) whose
-            // last wave is fullest (CTA count close to a multiple of what is resident at once).
+            // CTAs run in waves of `residentCtas`; all CTAs of a launch cost the same, so the launch
+            // takes ceil(waves) CTA-times.  Pick the cut (<= 64 chunks) with the best
+            // (fullness of the last wave) x (1 - halo overhead); more, shorter CTAs fill waves better.
             long long best = 1;
-            if (tiles < 2LL * residentCtas) {
-                best = std::min(maxChunks, (2LL * residentCtas + tiles - 1) / tiles);
-            } else {
-                double bestEff = 0;
-                for (long long c = 1; c <= std::min<long long>(8, maxChunks); ++c) {
-                    const double waves = (double)(tiles * c) / residentCtas;
-                    const double eff = waves / (double)((tiles * c + residentCtas - 1) / residentCtas);
-                    if (eff > bestEff + 0.005) {
-                        bestEff = eff;
-                        best = c;
-                    }
+            double bestScore = -1;
+            for (long long c = 1; c <= std::min<long long>(64, maxChunks); ++c) {
+                const double waves = (double)(tiles * c) / residentCtas;
+                const double eff = waves / (double)((tiles * c + residentCtas - 1) / residentCtas);
+                const double len = (double)n / (double)c;
+                const double score = eff * (len / (len + 64.0 * nwL));
+                if (score > bestScore + 0.002) {
+                    bestScore = score;
+                    best = c;
                 }
             }
             chunkLen = (int)round_up((size_t)ceil_div(n, (int)best), 16);
