@@ -75,14 +75,14 @@ template <>
 struct AddChain<2> {
     static EB_HD void run(uint32_t (&S)[2], const uint32_t (&T)[2], const uint32_t (&P)[2]) {
         asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;"
-            : "=r"(S[0]), "=r"(S[1]) : "r"(T[0]), "r"(T[1]), "r"(P[0]), "r"(P[1]));
+            : "=&r"(S[0]), "=&r"(S[1]) : "r"(T[0]), "r"(T[1]), "r"(P[0]), "r"(P[1]));
     }
 };
 template <>
 struct AddChain<3> {
     static EB_HD void run(uint32_t (&S)[3], const uint32_t (&T)[3], const uint32_t (&P)[3]) {
         asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
-            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2])
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2])
             : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(P[0]), "r"(P[1]), "r"(P[2]));
     }
 };
@@ -90,7 +90,7 @@ template <>
 struct AddChain<4> {
     static EB_HD void run(uint32_t (&S)[4], const uint32_t (&T)[4], const uint32_t (&P)[4]) {
         asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, %9;\n\taddc.cc.u32 %2, %6, %10;\n\taddc.u32 %3, %7, %11;"
-            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3])
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3])
             : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]));
     }
 };
@@ -99,7 +99,7 @@ struct AddChain<5> {
     static EB_HD void run(uint32_t (&S)[5], const uint32_t (&T)[5], const uint32_t (&P)[5]) {
         asm("add.cc.u32 %0, %5, %10;\n\taddc.cc.u32 %1, %6, %11;\n\taddc.cc.u32 %2, %7, %12;\n\t"
             "addc.cc.u32 %3, %8, %13;\n\taddc.u32 %4, %9, %14;"
-            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4])
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4])
             : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]),
               "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]));
     }
@@ -109,7 +109,7 @@ struct AddChain<6> {
     static EB_HD void run(uint32_t (&S)[6], const uint32_t (&T)[6], const uint32_t (&P)[6]) {
         asm("add.cc.u32 %0, %6, %12;\n\taddc.cc.u32 %1, %7, %13;\n\taddc.cc.u32 %2, %8, %14;\n\t"
             "addc.cc.u32 %3, %9, %15;\n\taddc.cc.u32 %4, %10, %16;\n\taddc.u32 %5, %11, %17;"
-            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5])
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5])
             : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]),
               "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]));
     }
@@ -120,7 +120,7 @@ struct AddChain<7> {
         asm("add.cc.u32 %0, %7, %14;\n\taddc.cc.u32 %1, %8, %15;\n\taddc.cc.u32 %2, %9, %16;\n\t"
             "addc.cc.u32 %3, %10, %17;\n\taddc.cc.u32 %4, %11, %18;\n\taddc.cc.u32 %5, %12, %19;\n\t"
             "addc.u32 %6, %13, %20;"
-            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5]), "=r"(S[6])
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "=&r"(S[6])
             : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]),
               "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]), "r"(P[6]));
     }
@@ -131,9 +131,444 @@ struct AddChain<8> {
         asm("add.cc.u32 %0, %8, %16;\n\taddc.cc.u32 %1, %9, %17;\n\taddc.cc.u32 %2, %10, %18;\n\t"
             "addc.cc.u32 %3, %11, %19;\n\taddc.cc.u32 %4, %12, %20;\n\taddc.cc.u32 %5, %13, %21;\n\t"
             "addc.cc.u32 %6, %14, %22;\n\taddc.u32 %7, %15, %23;"
-            : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5]), "=r"(S[6]), "=r"(S[7])
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "=&r"(S[6]), "=&r"(S[7])
             : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]),
               "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]), "r"(P[6]), "r"(P[7]));
+    }
+};
+#endif
+
+// out = (in << 1) | topBit over NW words as an add-with-carry chain (x + x), and the bit that
+// falls off the top -- the horizontal delta of the LAST query row -- added to (MINUS: subtracted
+// from) `score` by the final carry instruction: one IADD3/IADD3.X per word and nothing else,
+// instead of funnel shifts plus a separate bit extraction (both on the saturated ALU pipe).
+template <int NW, bool TOP_ONE, bool MINUS>
+struct ShiftChain {
+    static EB_HD void run(uint32_t (&out)[NW], const uint32_t (&in)[NW], int& score) {
+        uint32_t carry = TOP_ONE ? 1u : 0u;
+        EB_UNROLL
+        for (int w = 0; w < NW; ++w) {
+            out[w] = (in[w] << 1) | carry;
+            carry = in[w] >> 31;
+        }
+        score += MINUS ? -(int)carry : (int)carry;
+    }
+};
+#if defined(__CUDA_ARCH__)
+template <>
+struct ShiftChain<1, false, false> {
+    static EB_HD void run(uint32_t (&out)[1], const uint32_t (&in)[1], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %2, %2;\n\t"
+            "addc.u32 %1, %1, 0;\n\t}"
+            : "=&r"(out[0]), "+r"(score)
+            : "r"(in[0]));
+    }
+};
+template <>
+struct ShiftChain<1, false, true> {
+    static EB_HD void run(uint32_t (&out)[1], const uint32_t (&in)[1], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %2, %2;\n\t"
+            "subc.u32 %1, %1, 0;\n\t}"
+            : "=&r"(out[0]), "+r"(score)
+            : "r"(in[0]));
+    }
+};
+template <>
+struct ShiftChain<1, true, false> {
+    static EB_HD void run(uint32_t (&out)[1], const uint32_t (&in)[1], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %2, %2;\n\t"
+            "addc.u32 %1, %1, 0;\n\t}"
+            : "=&r"(out[0]), "+r"(score)
+            : "r"(in[0]));
+    }
+};
+template <>
+struct ShiftChain<1, true, true> {
+    static EB_HD void run(uint32_t (&out)[1], const uint32_t (&in)[1], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %2, %2;\n\t"
+            "subc.u32 %1, %1, 0;\n\t}"
+            : "=&r"(out[0]), "+r"(score)
+            : "r"(in[0]));
+    }
+};
+template <>
+struct ShiftChain<2, false, false> {
+    static EB_HD void run(uint32_t (&out)[2], const uint32_t (&in)[2], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %3, %3;\n\t"
+            "addc.cc.u32 %1, %4, %4;\n\t"
+            "addc.u32 %2, %2, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]));
+    }
+};
+template <>
+struct ShiftChain<2, false, true> {
+    static EB_HD void run(uint32_t (&out)[2], const uint32_t (&in)[2], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %3, %3;\n\t"
+            "addc.cc.u32 %1, %4, %4;\n\t"
+            "subc.u32 %2, %2, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]));
+    }
+};
+template <>
+struct ShiftChain<2, true, false> {
+    static EB_HD void run(uint32_t (&out)[2], const uint32_t (&in)[2], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %3, %3;\n\t"
+            "addc.cc.u32 %1, %4, %4;\n\t"
+            "addc.u32 %2, %2, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]));
+    }
+};
+template <>
+struct ShiftChain<2, true, true> {
+    static EB_HD void run(uint32_t (&out)[2], const uint32_t (&in)[2], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %3, %3;\n\t"
+            "addc.cc.u32 %1, %4, %4;\n\t"
+            "subc.u32 %2, %2, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]));
+    }
+};
+template <>
+struct ShiftChain<3, false, false> {
+    static EB_HD void run(uint32_t (&out)[3], const uint32_t (&in)[3], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %4, %4;\n\t"
+            "addc.cc.u32 %1, %5, %5;\n\t"
+            "addc.cc.u32 %2, %6, %6;\n\t"
+            "addc.u32 %3, %3, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]));
+    }
+};
+template <>
+struct ShiftChain<3, false, true> {
+    static EB_HD void run(uint32_t (&out)[3], const uint32_t (&in)[3], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %4, %4;\n\t"
+            "addc.cc.u32 %1, %5, %5;\n\t"
+            "addc.cc.u32 %2, %6, %6;\n\t"
+            "subc.u32 %3, %3, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]));
+    }
+};
+template <>
+struct ShiftChain<3, true, false> {
+    static EB_HD void run(uint32_t (&out)[3], const uint32_t (&in)[3], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %4, %4;\n\t"
+            "addc.cc.u32 %1, %5, %5;\n\t"
+            "addc.cc.u32 %2, %6, %6;\n\t"
+            "addc.u32 %3, %3, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]));
+    }
+};
+template <>
+struct ShiftChain<3, true, true> {
+    static EB_HD void run(uint32_t (&out)[3], const uint32_t (&in)[3], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %4, %4;\n\t"
+            "addc.cc.u32 %1, %5, %5;\n\t"
+            "addc.cc.u32 %2, %6, %6;\n\t"
+            "subc.u32 %3, %3, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]));
+    }
+};
+template <>
+struct ShiftChain<4, false, false> {
+    static EB_HD void run(uint32_t (&out)[4], const uint32_t (&in)[4], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %5, %5;\n\t"
+            "addc.cc.u32 %1, %6, %6;\n\t"
+            "addc.cc.u32 %2, %7, %7;\n\t"
+            "addc.cc.u32 %3, %8, %8;\n\t"
+            "addc.u32 %4, %4, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]));
+    }
+};
+template <>
+struct ShiftChain<4, false, true> {
+    static EB_HD void run(uint32_t (&out)[4], const uint32_t (&in)[4], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %5, %5;\n\t"
+            "addc.cc.u32 %1, %6, %6;\n\t"
+            "addc.cc.u32 %2, %7, %7;\n\t"
+            "addc.cc.u32 %3, %8, %8;\n\t"
+            "subc.u32 %4, %4, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]));
+    }
+};
+template <>
+struct ShiftChain<4, true, false> {
+    static EB_HD void run(uint32_t (&out)[4], const uint32_t (&in)[4], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %5, %5;\n\t"
+            "addc.cc.u32 %1, %6, %6;\n\t"
+            "addc.cc.u32 %2, %7, %7;\n\t"
+            "addc.cc.u32 %3, %8, %8;\n\t"
+            "addc.u32 %4, %4, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]));
+    }
+};
+template <>
+struct ShiftChain<4, true, true> {
+    static EB_HD void run(uint32_t (&out)[4], const uint32_t (&in)[4], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %5, %5;\n\t"
+            "addc.cc.u32 %1, %6, %6;\n\t"
+            "addc.cc.u32 %2, %7, %7;\n\t"
+            "addc.cc.u32 %3, %8, %8;\n\t"
+            "subc.u32 %4, %4, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]));
+    }
+};
+template <>
+struct ShiftChain<5, false, false> {
+    static EB_HD void run(uint32_t (&out)[5], const uint32_t (&in)[5], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %6, %6;\n\t"
+            "addc.cc.u32 %1, %7, %7;\n\t"
+            "addc.cc.u32 %2, %8, %8;\n\t"
+            "addc.cc.u32 %3, %9, %9;\n\t"
+            "addc.cc.u32 %4, %10, %10;\n\t"
+            "addc.u32 %5, %5, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]));
+    }
+};
+template <>
+struct ShiftChain<5, false, true> {
+    static EB_HD void run(uint32_t (&out)[5], const uint32_t (&in)[5], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %6, %6;\n\t"
+            "addc.cc.u32 %1, %7, %7;\n\t"
+            "addc.cc.u32 %2, %8, %8;\n\t"
+            "addc.cc.u32 %3, %9, %9;\n\t"
+            "addc.cc.u32 %4, %10, %10;\n\t"
+            "subc.u32 %5, %5, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]));
+    }
+};
+template <>
+struct ShiftChain<5, true, false> {
+    static EB_HD void run(uint32_t (&out)[5], const uint32_t (&in)[5], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %6, %6;\n\t"
+            "addc.cc.u32 %1, %7, %7;\n\t"
+            "addc.cc.u32 %2, %8, %8;\n\t"
+            "addc.cc.u32 %3, %9, %9;\n\t"
+            "addc.cc.u32 %4, %10, %10;\n\t"
+            "addc.u32 %5, %5, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]));
+    }
+};
+template <>
+struct ShiftChain<5, true, true> {
+    static EB_HD void run(uint32_t (&out)[5], const uint32_t (&in)[5], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %6, %6;\n\t"
+            "addc.cc.u32 %1, %7, %7;\n\t"
+            "addc.cc.u32 %2, %8, %8;\n\t"
+            "addc.cc.u32 %3, %9, %9;\n\t"
+            "addc.cc.u32 %4, %10, %10;\n\t"
+            "subc.u32 %5, %5, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]));
+    }
+};
+template <>
+struct ShiftChain<6, false, false> {
+    static EB_HD void run(uint32_t (&out)[6], const uint32_t (&in)[6], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %7, %7;\n\t"
+            "addc.cc.u32 %1, %8, %8;\n\t"
+            "addc.cc.u32 %2, %9, %9;\n\t"
+            "addc.cc.u32 %3, %10, %10;\n\t"
+            "addc.cc.u32 %4, %11, %11;\n\t"
+            "addc.cc.u32 %5, %12, %12;\n\t"
+            "addc.u32 %6, %6, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]));
+    }
+};
+template <>
+struct ShiftChain<6, false, true> {
+    static EB_HD void run(uint32_t (&out)[6], const uint32_t (&in)[6], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %7, %7;\n\t"
+            "addc.cc.u32 %1, %8, %8;\n\t"
+            "addc.cc.u32 %2, %9, %9;\n\t"
+            "addc.cc.u32 %3, %10, %10;\n\t"
+            "addc.cc.u32 %4, %11, %11;\n\t"
+            "addc.cc.u32 %5, %12, %12;\n\t"
+            "subc.u32 %6, %6, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]));
+    }
+};
+template <>
+struct ShiftChain<6, true, false> {
+    static EB_HD void run(uint32_t (&out)[6], const uint32_t (&in)[6], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %7, %7;\n\t"
+            "addc.cc.u32 %1, %8, %8;\n\t"
+            "addc.cc.u32 %2, %9, %9;\n\t"
+            "addc.cc.u32 %3, %10, %10;\n\t"
+            "addc.cc.u32 %4, %11, %11;\n\t"
+            "addc.cc.u32 %5, %12, %12;\n\t"
+            "addc.u32 %6, %6, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]));
+    }
+};
+template <>
+struct ShiftChain<6, true, true> {
+    static EB_HD void run(uint32_t (&out)[6], const uint32_t (&in)[6], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %7, %7;\n\t"
+            "addc.cc.u32 %1, %8, %8;\n\t"
+            "addc.cc.u32 %2, %9, %9;\n\t"
+            "addc.cc.u32 %3, %10, %10;\n\t"
+            "addc.cc.u32 %4, %11, %11;\n\t"
+            "addc.cc.u32 %5, %12, %12;\n\t"
+            "subc.u32 %6, %6, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]));
+    }
+};
+template <>
+struct ShiftChain<7, false, false> {
+    static EB_HD void run(uint32_t (&out)[7], const uint32_t (&in)[7], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %8, %8;\n\t"
+            "addc.cc.u32 %1, %9, %9;\n\t"
+            "addc.cc.u32 %2, %10, %10;\n\t"
+            "addc.cc.u32 %3, %11, %11;\n\t"
+            "addc.cc.u32 %4, %12, %12;\n\t"
+            "addc.cc.u32 %5, %13, %13;\n\t"
+            "addc.cc.u32 %6, %14, %14;\n\t"
+            "addc.u32 %7, %7, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]));
+    }
+};
+template <>
+struct ShiftChain<7, false, true> {
+    static EB_HD void run(uint32_t (&out)[7], const uint32_t (&in)[7], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %8, %8;\n\t"
+            "addc.cc.u32 %1, %9, %9;\n\t"
+            "addc.cc.u32 %2, %10, %10;\n\t"
+            "addc.cc.u32 %3, %11, %11;\n\t"
+            "addc.cc.u32 %4, %12, %12;\n\t"
+            "addc.cc.u32 %5, %13, %13;\n\t"
+            "addc.cc.u32 %6, %14, %14;\n\t"
+            "subc.u32 %7, %7, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]));
+    }
+};
+template <>
+struct ShiftChain<7, true, false> {
+    static EB_HD void run(uint32_t (&out)[7], const uint32_t (&in)[7], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %8, %8;\n\t"
+            "addc.cc.u32 %1, %9, %9;\n\t"
+            "addc.cc.u32 %2, %10, %10;\n\t"
+            "addc.cc.u32 %3, %11, %11;\n\t"
+            "addc.cc.u32 %4, %12, %12;\n\t"
+            "addc.cc.u32 %5, %13, %13;\n\t"
+            "addc.cc.u32 %6, %14, %14;\n\t"
+            "addc.u32 %7, %7, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]));
+    }
+};
+template <>
+struct ShiftChain<7, true, true> {
+    static EB_HD void run(uint32_t (&out)[7], const uint32_t (&in)[7], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %8, %8;\n\t"
+            "addc.cc.u32 %1, %9, %9;\n\t"
+            "addc.cc.u32 %2, %10, %10;\n\t"
+            "addc.cc.u32 %3, %11, %11;\n\t"
+            "addc.cc.u32 %4, %12, %12;\n\t"
+            "addc.cc.u32 %5, %13, %13;\n\t"
+            "addc.cc.u32 %6, %14, %14;\n\t"
+            "subc.u32 %7, %7, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]));
+    }
+};
+template <>
+struct ShiftChain<8, false, false> {
+    static EB_HD void run(uint32_t (&out)[8], const uint32_t (&in)[8], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %9, %9;\n\t"
+            "addc.cc.u32 %1, %10, %10;\n\t"
+            "addc.cc.u32 %2, %11, %11;\n\t"
+            "addc.cc.u32 %3, %12, %12;\n\t"
+            "addc.cc.u32 %4, %13, %13;\n\t"
+            "addc.cc.u32 %5, %14, %14;\n\t"
+            "addc.cc.u32 %6, %15, %15;\n\t"
+            "addc.cc.u32 %7, %16, %16;\n\t"
+            "addc.u32 %8, %8, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
+    }
+};
+template <>
+struct ShiftChain<8, false, true> {
+    static EB_HD void run(uint32_t (&out)[8], const uint32_t (&in)[8], int& score) {
+        asm("{\n\tadd.cc.u32 %0, %9, %9;\n\t"
+            "addc.cc.u32 %1, %10, %10;\n\t"
+            "addc.cc.u32 %2, %11, %11;\n\t"
+            "addc.cc.u32 %3, %12, %12;\n\t"
+            "addc.cc.u32 %4, %13, %13;\n\t"
+            "addc.cc.u32 %5, %14, %14;\n\t"
+            "addc.cc.u32 %6, %15, %15;\n\t"
+            "addc.cc.u32 %7, %16, %16;\n\t"
+            "subc.u32 %8, %8, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
+    }
+};
+template <>
+struct ShiftChain<8, true, false> {
+    static EB_HD void run(uint32_t (&out)[8], const uint32_t (&in)[8], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %9, %9;\n\t"
+            "addc.cc.u32 %1, %10, %10;\n\t"
+            "addc.cc.u32 %2, %11, %11;\n\t"
+            "addc.cc.u32 %3, %12, %12;\n\t"
+            "addc.cc.u32 %4, %13, %13;\n\t"
+            "addc.cc.u32 %5, %14, %14;\n\t"
+            "addc.cc.u32 %6, %15, %15;\n\t"
+            "addc.cc.u32 %7, %16, %16;\n\t"
+            "addc.u32 %8, %8, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
+    }
+};
+template <>
+struct ShiftChain<8, true, true> {
+    static EB_HD void run(uint32_t (&out)[8], const uint32_t (&in)[8], int& score) {
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
+            "addc.cc.u32 %0, %9, %9;\n\t"
+            "addc.cc.u32 %1, %10, %10;\n\t"
+            "addc.cc.u32 %2, %11, %11;\n\t"
+            "addc.cc.u32 %3, %12, %12;\n\t"
+            "addc.cc.u32 %4, %13, %13;\n\t"
+            "addc.cc.u32 %5, %14, %14;\n\t"
+            "addc.cc.u32 %6, %15, %15;\n\t"
+            "addc.cc.u32 %7, %16, %16;\n\t"
+            "subc.u32 %8, %8, 0;\n\t}"
+            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(score)
+            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
     }
 };
 #endif
@@ -177,7 +612,9 @@ EB_HD uint32_t mul_hi(uint32_t x, uint32_t two) {
 #endif
 }
 
-template <int NW, bool TOP_ONE, bool FMA_SHIFT = false>
+// SHV selects how the <<1 of the horizontal delta words is done: 0 funnel shifts, 1 integer
+// multiply-adds (FMA pipe; IMAD.HI turned out quarter-rate on B200), 2 add-with-carry chains.
+template <int NW, bool TOP_ONE, int SHV = 0>
 EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score, uint32_t two = 2u) {
     uint32_t T[NW], S[NW], Ph[NW], Mh[NW];
     EB_UNROLL
@@ -189,7 +626,17 @@ EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[
         Ph[w] = Mv[w] | ~(Xh | Pv[w]);
         Mh[w] = Pv[w] & Xh;
     }
-    if (FMA_SHIFT) {
+    if (SHV == 2) {
+        uint32_t Phs[NW], Mhs[NW];
+        ShiftChain<NW, TOP_ONE, false>::run(Phs, Ph, score);
+        ShiftChain<NW, false, true>::run(Mhs, Mh, score);
+        EB_UNROLL
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t Xv = Eq[w] | Mv[w];
+            Pv[w] = Mhs[w] | ~(Xv | Phs[w]);
+            Mv[w] = Phs[w] & Xv;
+        }
+    } else if (SHV == 1) {
         uint32_t cP = TOP_ONE ? 1u : 0u, cM = 0u;
         EB_UNROLL
         for (int w = 0; w < NW; ++w) {
@@ -281,25 +728,24 @@ struct PtrSyms {
 // running minimum and its columns are recorded; without it only the state advances (halo
 // columns of a chunk).  Columns go four at a time: the four last-row scores stay in registers
 // and are compared against the running minimum once per group (events are rare).
-template <int NW, bool TOP_ONE, bool TRACK, bool FMA_SHIFT = false, bool RANGE = false, class Acc, class Syms>
+template <int NW, bool TOP_ONE, bool TRACK, int SHV = 0, bool RANGE = false, class Acc, class Syms>
 EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int count, int cAbs,
                       Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     int i = 0;
     while (i < count && !syms.aligned4(i)) {  // head: until the symbols are 4-byte aligned
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
-        k1_step<NW, TOP_ONE, FMA_SHIFT>(st.Pv, st.Mv, Eq, st.score, st.two);
+        k1_step<NW, TOP_ONE, SHV>(st.Pv, st.Mv, Eq, st.score, st.two);
         if (TRACK && st.score <= st.best) k1_event<NW, RANGE>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
         ++i;
     }
-    for (; i + 4 <= count; i += 4) {  // body: four symbols per 32-bit read
-        const uint32_t four = syms.read4(i);
+    for (; i + 4 <= count; i += 4) {  // body: groups of four columns (byte reads: LSU, not ALU, work)
         int sc[4];
         EB_UNROLL
         for (int j = 0; j < 4; ++j) {
             uint32_t Eq[NW];
-            acc.load((four >> (8 * j)) & 0xffu, Eq);
-            k1_step<NW, TOP_ONE, FMA_SHIFT>(st.Pv, st.Mv, Eq, st.score, st.two);
+            acc.load(syms.read1(i + j), Eq);
+            k1_step<NW, TOP_ONE, SHV>(st.Pv, st.Mv, Eq, st.score, st.two);
             sc[j] = st.score;
         }
         if (TRACK) {
@@ -316,7 +762,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
     for (; i < count; ++i) {  // tail
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
-        k1_step<NW, TOP_ONE, FMA_SHIFT>(st.Pv, st.Mv, Eq, st.score, st.two);
+        k1_step<NW, TOP_ONE, SHV>(st.Pv, st.Mv, Eq, st.score, st.two);
         if (TRACK && st.score <= st.best) k1_event<NW, RANGE>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
     }
 }
@@ -380,13 +826,13 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     st.two = p.two;
     const K1Chunk g = k1_chunk(p, chunk);
     if (p.mode == MODE_HW && p.rangeMode) {
-        k1_columns<NW, false, false, true, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_columns<NW, false, true, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, false, 2, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true, 2, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_HW) {
-        k1_columns<NW, false, false, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_columns<NW, false, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, false, 1>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true, 1>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_SHW) {
-        k1_columns<NW, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, true, true, 2>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else {
         k1_columns<NW, true, false>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
         st.best = st.score;  // NW: the bottom-right cell (ref cpp:916)

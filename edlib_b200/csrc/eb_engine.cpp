@@ -12,10 +12,12 @@
 //   materialize : malloc'd arrays per result (ownership as ref edlib.h:177,186,205)
 #include "eb_engine.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <stdexcept>
 #include <unordered_map>
@@ -40,6 +42,19 @@ EngineTunables::EngineTunables() {
 }
 
 namespace {
+
+// EDLIB_B200_TRACE=1: wall-clock of the host phases to stderr (diagnostics only).
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("EDLIB_B200_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[edlib_b200] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
@@ -173,6 +188,7 @@ public:
 // ---------------------------------------------------------------------------------------------
 Prepared* Engine::prepare(const BatchInput& in) {
     Backend* be = be_;
+    Trace trace;
     Prepared* p = new Prepared();
     try {
         p->be = be;
@@ -236,6 +252,7 @@ Prepared* Engine::prepare(const BatchInput& in) {
                 memset(stage + g.off + g.len, 0, next - g.off - (size_t)g.len);
             }
         }
+        trace.mark("prepare: pack");
         p->dSeq.alloc(be, total);
         p->dSeq.upload(stage, total);
         stats.h2dBytes += (long long)total;
@@ -314,6 +331,7 @@ Prepared* Engine::prepare(const BatchInput& in) {
         (void)byteOfCode;
         be->sync();
         be->free_host(stage);
+        trace.mark("prepare: upload+alphabet");
     } catch (...) {
         delete p;
         throw;
@@ -511,6 +529,7 @@ struct WRunner {
 // ---------------------------------------------------------------------------------------------
 void Engine::compute(Prepared* p) {
     Backend* be = be_;
+    Trace trace;
     be->reset_timing();
     const int N = p->N;
     const int mode = p->mode;
@@ -722,7 +741,9 @@ void Engine::compute(Prepared* p) {
                 geometry((int)cand.size(), 2, chunksA, chunkLenA);
                 std::vector<Rec> ra;
                 std::vector<Ovf> none;
+                trace.mark("compute: classify");
                 launch(cand, thr, 2, chunksA, chunkLenA, 0, P, 1, ra, none);
+                trace.mark("filter: prefix sweep");
                 const int g = (int)cand.size();
                 std::vector<WTask> tasks;
                 std::vector<int> taskSlot;
@@ -781,7 +802,9 @@ void Engine::compute(Prepared* p) {
                     taskSlot.push_back(s);
                 }
                 WRunner fr{this, be, p, nullptr, nullptr};
+                trace.mark("filter: window tasks");
                 fr.run(tasks);
+                trace.mark("filter: window sweeps");
                 for (size_t j = 0; j < tasks.size(); ++j) {
                     const WTask& w = tasks[j];
                     const int s = taskSlot[j];
@@ -803,6 +826,7 @@ void Engine::compute(Prepared* p) {
             for (int s = 0; s < G; ++s) direct.push_back(s);
         }
 
+        trace.mark("filter: collect");
         // ---- plain full sweep of the remaining reads ------------------------------------------
         if (!direct.empty()) {
             int chunks = 1, chunkLen = 0;
@@ -833,6 +857,7 @@ void Engine::compute(Prepared* p) {
         }
     }
 
+    trace.mark("compute: K1 groups done");
     // ---- W distance pass ------------------------------------------------------------------
     std::vector<uint8_t> opsPool;
     std::vector<int> colPool;
@@ -894,6 +919,7 @@ void Engine::compute(Prepared* p) {
         }
     }
 
+    trace.mark("compute: W distance pass");
     // ---- distances and end locations ------------------------------------------------------
     for (int i = 0; i < N; ++i) {
         if (p->special[i]) continue;
@@ -917,6 +943,7 @@ void Engine::compute(Prepared* p) {
         p->endCount[i] = (int)(p->endPool.size() - (size_t)p->endStart[i]);
     }
 
+    trace.mark("compute: end locations");
     // ---- start locations (ref cpp:228-272) ------------------------------------------------
     const bool wantLoc = p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH;
     if (wantLoc) {
@@ -1117,6 +1144,7 @@ void Engine::compute(Prepared* p) {
         }
     }
 
+    trace.mark("compute: starts + paths");
     be->sync();
     stats.kernelMs = be->kernel_ms(nullptr);
     stats.k1Ms = be->kernel_ms("k1");
@@ -1128,6 +1156,7 @@ void Engine::compute(Prepared* p) {
 // materialize / release / one-shot
 // ---------------------------------------------------------------------------------------------
 void Engine::materialize(Prepared* p, EdlibAlignResult* results) {
+    Trace trace;
     const int N = p->N;
     for (int i = 0; i < N; ++i) {
         EdlibAlignResult& r = results[i];
@@ -1164,6 +1193,7 @@ void Engine::materialize(Prepared* p, EdlibAlignResult* results) {
             memcpy(r.alignment, p->alnPool.data() + p->alnStart[i], (size_t)p->alnLen[i]);
         }
     }
+    trace.mark("materialize");
 }
 
 void Engine::release(Prepared* p) { delete p; }

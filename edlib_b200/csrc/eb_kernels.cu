@@ -162,7 +162,7 @@ EB_D void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
                  : "memory");
 }
 
-template <int NW, int MODE, bool FMA_SHIFT, bool RANGE = false>
+template <int NW, int MODE, int SHV, bool RANGE = false>
 __global__ void k1_kernel(const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -223,12 +223,12 @@ __global__ void k1_kernel(const K1Params p) {
             const uint32_t sa = tileAddr[i & 1];
             if (MODE == MODE_HW) {
                 const int mid = min(max(g.cs, a), b);               // columns before cs are halo
-                if (mid > a) k1_columns<NW, false, false, FMA_SHIFT, RANGE>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-                if (b > mid) k1_columns<NW, false, true, FMA_SHIFT, RANGE>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (mid > a) k1_columns<NW, false, false, SHV, RANGE>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (b > mid) k1_columns<NW, false, true, SHV, RANGE>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             } else if (MODE == MODE_SHW) {
-                k1_columns<NW, true, true, FMA_SHIFT>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                k1_columns<NW, true, true, SHV>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             } else {
-                k1_columns<NW, true, false, FMA_SHIFT>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                k1_columns<NW, true, false, SHV>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             }
         }
         __syncthreads();  // everyone is done with tile i before its buffer is refilled
@@ -320,11 +320,11 @@ struct CudaBackend : Backend {
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> pool;
     int launchCount = 0;
-    bool fmaShift = true;  // EDLIB_B200_K1_FMA_SHIFT=0 selects the funnel-shift variant (A/B measurements)
+    int shiftVariant = 2;  // EDLIB_B200_K1_SHIFT: 0 funnel shifts, 1 IMAD/IMAD.HI, 2 carry chains (A/B measurements)
 
     CudaBackend() {
-        const char* v = getenv("EDLIB_B200_K1_FMA_SHIFT");
-        if (v && *v) fmaShift = atoi(v) != 0;
+        const char* v = getenv("EDLIB_B200_K1_SHIFT");
+        if (v && *v) shiftVariant = atoi(v);
         int dev = 0;
         EB_CUDA(cudaGetDevice(&dev));
         cudaDeviceProp prop;
@@ -456,22 +456,22 @@ struct CudaBackend : Backend {
         *block = b;
         *smem = fixed + perThread * b;
     }
-    template <int NW, int MODE, bool FMA_SHIFT>
+    template <int NW, int MODE, int SHV>
     void launch_k1_v(const K1Params& p) {
         int block;
         size_t smem;
         k1_block(NW, p.ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
-        EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE, FMA_SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE, SHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
-        k1_kernel<NW, MODE, FMA_SHIFT><<<grid, block, smem, stream>>>(p);
+        k1_kernel<NW, MODE, SHV><<<grid, block, smem, stream>>>(p);
         check_launch("k1");
     }
     template <int NW>
     int k1_occupancy(int block, size_t smem) {
         int perSm = 0;
-        cudaFuncSetAttribute(k1_kernel<NW, MODE_HW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_kernel<NW, MODE_HW, false>, block, smem) != cudaSuccess) perSm = 1;
+        cudaFuncSetAttribute(k1_kernel<NW, MODE_HW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_kernel<NW, MODE_HW, 0>, block, smem) != cudaSuccess) perSm = 1;
         return perSm < 1 ? 1 : perSm;
     }
     std::vector<int> shapeCache;  // [nw*1024 + ncodes] -> block | resident << 12, 0 = unknown
@@ -503,8 +503,9 @@ struct CudaBackend : Backend {
     }
     template <int NW, int MODE>
     void launch_k1_t(const K1Params& p) {
-        if (fmaShift) launch_k1_v<NW, MODE, true>(p);
-        else launch_k1_v<NW, MODE, false>(p);
+        if (shiftVariant == 2) launch_k1_v<NW, MODE, 2>(p);
+        else if (shiftVariant == 1) launch_k1_v<NW, MODE, 1>(p);
+        else launch_k1_v<NW, MODE, 0>(p);
     }
     // candidate-filter sweep: 64-row prefixes (two words), HW, range recording
     void launch_k1_range(const K1Params& p) {
@@ -513,12 +514,15 @@ struct CudaBackend : Backend {
         k1_block(2, p.ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
-        if (fmaShift) {
-            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k1_kernel<2, MODE_HW, true, true><<<grid, block, smem, stream>>>(p);
+        if (shiftVariant == 2) {
+            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k1_kernel<2, MODE_HW, 2, true><<<grid, block, smem, stream>>>(p);
+        } else if (shiftVariant == 1) {
+            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k1_kernel<2, MODE_HW, 1, true><<<grid, block, smem, stream>>>(p);
         } else {
-            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k1_kernel<2, MODE_HW, false, true><<<grid, block, smem, stream>>>(p);
+            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k1_kernel<2, MODE_HW, 0, true><<<grid, block, smem, stream>>>(p);
         }
         check_launch("k1 range");
     }
