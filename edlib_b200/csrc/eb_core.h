@@ -138,441 +138,6 @@ struct AddChain<8> {
 };
 #endif
 
-// out = (in << 1) | topBit over NW words as an add-with-carry chain (x + x), and the bit that
-// falls off the top -- the horizontal delta of the LAST query row -- added to (MINUS: subtracted
-// from) `score` by the final carry instruction: one IADD3/IADD3.X per word and nothing else,
-// instead of funnel shifts plus a separate bit extraction (both on the saturated ALU pipe).
-template <int NW, bool TOP_ONE, bool MINUS>
-struct ShiftChain {
-    static EB_HD void run(uint32_t (&out)[NW], const uint32_t (&in)[NW], int& score) {
-        uint32_t carry = TOP_ONE ? 1u : 0u;
-        EB_UNROLL
-        for (int w = 0; w < NW; ++w) {
-            out[w] = (in[w] << 1) | carry;
-            carry = in[w] >> 31;
-        }
-        score += MINUS ? -(int)carry : (int)carry;
-    }
-};
-#if defined(__CUDA_ARCH__)
-template <>
-struct ShiftChain<1, false, false> {
-    static EB_HD void run(uint32_t (&out)[1], const uint32_t (&in)[1], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %2, %2;\n\t"
-            "addc.u32 %1, %1, 0;\n\t}"
-            : "=&r"(out[0]), "+r"(score)
-            : "r"(in[0]));
-    }
-};
-template <>
-struct ShiftChain<1, false, true> {
-    static EB_HD void run(uint32_t (&out)[1], const uint32_t (&in)[1], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %2, %2;\n\t"
-            "subc.u32 %1, %1, 0;\n\t}"
-            : "=&r"(out[0]), "+r"(score)
-            : "r"(in[0]));
-    }
-};
-template <>
-struct ShiftChain<1, true, false> {
-    static EB_HD void run(uint32_t (&out)[1], const uint32_t (&in)[1], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %2, %2;\n\t"
-            "addc.u32 %1, %1, 0;\n\t}"
-            : "=&r"(out[0]), "+r"(score)
-            : "r"(in[0]));
-    }
-};
-template <>
-struct ShiftChain<1, true, true> {
-    static EB_HD void run(uint32_t (&out)[1], const uint32_t (&in)[1], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %2, %2;\n\t"
-            "subc.u32 %1, %1, 0;\n\t}"
-            : "=&r"(out[0]), "+r"(score)
-            : "r"(in[0]));
-    }
-};
-template <>
-struct ShiftChain<2, false, false> {
-    static EB_HD void run(uint32_t (&out)[2], const uint32_t (&in)[2], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %3, %3;\n\t"
-            "addc.cc.u32 %1, %4, %4;\n\t"
-            "addc.u32 %2, %2, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]));
-    }
-};
-template <>
-struct ShiftChain<2, false, true> {
-    static EB_HD void run(uint32_t (&out)[2], const uint32_t (&in)[2], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %3, %3;\n\t"
-            "addc.cc.u32 %1, %4, %4;\n\t"
-            "subc.u32 %2, %2, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]));
-    }
-};
-template <>
-struct ShiftChain<2, true, false> {
-    static EB_HD void run(uint32_t (&out)[2], const uint32_t (&in)[2], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %3, %3;\n\t"
-            "addc.cc.u32 %1, %4, %4;\n\t"
-            "addc.u32 %2, %2, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]));
-    }
-};
-template <>
-struct ShiftChain<2, true, true> {
-    static EB_HD void run(uint32_t (&out)[2], const uint32_t (&in)[2], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %3, %3;\n\t"
-            "addc.cc.u32 %1, %4, %4;\n\t"
-            "subc.u32 %2, %2, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]));
-    }
-};
-template <>
-struct ShiftChain<3, false, false> {
-    static EB_HD void run(uint32_t (&out)[3], const uint32_t (&in)[3], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %4, %4;\n\t"
-            "addc.cc.u32 %1, %5, %5;\n\t"
-            "addc.cc.u32 %2, %6, %6;\n\t"
-            "addc.u32 %3, %3, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]));
-    }
-};
-template <>
-struct ShiftChain<3, false, true> {
-    static EB_HD void run(uint32_t (&out)[3], const uint32_t (&in)[3], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %4, %4;\n\t"
-            "addc.cc.u32 %1, %5, %5;\n\t"
-            "addc.cc.u32 %2, %6, %6;\n\t"
-            "subc.u32 %3, %3, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]));
-    }
-};
-template <>
-struct ShiftChain<3, true, false> {
-    static EB_HD void run(uint32_t (&out)[3], const uint32_t (&in)[3], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %4, %4;\n\t"
-            "addc.cc.u32 %1, %5, %5;\n\t"
-            "addc.cc.u32 %2, %6, %6;\n\t"
-            "addc.u32 %3, %3, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]));
-    }
-};
-template <>
-struct ShiftChain<3, true, true> {
-    static EB_HD void run(uint32_t (&out)[3], const uint32_t (&in)[3], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %4, %4;\n\t"
-            "addc.cc.u32 %1, %5, %5;\n\t"
-            "addc.cc.u32 %2, %6, %6;\n\t"
-            "subc.u32 %3, %3, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]));
-    }
-};
-template <>
-struct ShiftChain<4, false, false> {
-    static EB_HD void run(uint32_t (&out)[4], const uint32_t (&in)[4], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %5, %5;\n\t"
-            "addc.cc.u32 %1, %6, %6;\n\t"
-            "addc.cc.u32 %2, %7, %7;\n\t"
-            "addc.cc.u32 %3, %8, %8;\n\t"
-            "addc.u32 %4, %4, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]));
-    }
-};
-template <>
-struct ShiftChain<4, false, true> {
-    static EB_HD void run(uint32_t (&out)[4], const uint32_t (&in)[4], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %5, %5;\n\t"
-            "addc.cc.u32 %1, %6, %6;\n\t"
-            "addc.cc.u32 %2, %7, %7;\n\t"
-            "addc.cc.u32 %3, %8, %8;\n\t"
-            "subc.u32 %4, %4, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]));
-    }
-};
-template <>
-struct ShiftChain<4, true, false> {
-    static EB_HD void run(uint32_t (&out)[4], const uint32_t (&in)[4], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %5, %5;\n\t"
-            "addc.cc.u32 %1, %6, %6;\n\t"
-            "addc.cc.u32 %2, %7, %7;\n\t"
-            "addc.cc.u32 %3, %8, %8;\n\t"
-            "addc.u32 %4, %4, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]));
-    }
-};
-template <>
-struct ShiftChain<4, true, true> {
-    static EB_HD void run(uint32_t (&out)[4], const uint32_t (&in)[4], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %5, %5;\n\t"
-            "addc.cc.u32 %1, %6, %6;\n\t"
-            "addc.cc.u32 %2, %7, %7;\n\t"
-            "addc.cc.u32 %3, %8, %8;\n\t"
-            "subc.u32 %4, %4, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]));
-    }
-};
-template <>
-struct ShiftChain<5, false, false> {
-    static EB_HD void run(uint32_t (&out)[5], const uint32_t (&in)[5], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %6, %6;\n\t"
-            "addc.cc.u32 %1, %7, %7;\n\t"
-            "addc.cc.u32 %2, %8, %8;\n\t"
-            "addc.cc.u32 %3, %9, %9;\n\t"
-            "addc.cc.u32 %4, %10, %10;\n\t"
-            "addc.u32 %5, %5, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]));
-    }
-};
-template <>
-struct ShiftChain<5, false, true> {
-    static EB_HD void run(uint32_t (&out)[5], const uint32_t (&in)[5], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %6, %6;\n\t"
-            "addc.cc.u32 %1, %7, %7;\n\t"
-            "addc.cc.u32 %2, %8, %8;\n\t"
-            "addc.cc.u32 %3, %9, %9;\n\t"
-            "addc.cc.u32 %4, %10, %10;\n\t"
-            "subc.u32 %5, %5, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]));
-    }
-};
-template <>
-struct ShiftChain<5, true, false> {
-    static EB_HD void run(uint32_t (&out)[5], const uint32_t (&in)[5], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %6, %6;\n\t"
-            "addc.cc.u32 %1, %7, %7;\n\t"
-            "addc.cc.u32 %2, %8, %8;\n\t"
-            "addc.cc.u32 %3, %9, %9;\n\t"
-            "addc.cc.u32 %4, %10, %10;\n\t"
-            "addc.u32 %5, %5, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]));
-    }
-};
-template <>
-struct ShiftChain<5, true, true> {
-    static EB_HD void run(uint32_t (&out)[5], const uint32_t (&in)[5], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %6, %6;\n\t"
-            "addc.cc.u32 %1, %7, %7;\n\t"
-            "addc.cc.u32 %2, %8, %8;\n\t"
-            "addc.cc.u32 %3, %9, %9;\n\t"
-            "addc.cc.u32 %4, %10, %10;\n\t"
-            "subc.u32 %5, %5, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]));
-    }
-};
-template <>
-struct ShiftChain<6, false, false> {
-    static EB_HD void run(uint32_t (&out)[6], const uint32_t (&in)[6], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %7, %7;\n\t"
-            "addc.cc.u32 %1, %8, %8;\n\t"
-            "addc.cc.u32 %2, %9, %9;\n\t"
-            "addc.cc.u32 %3, %10, %10;\n\t"
-            "addc.cc.u32 %4, %11, %11;\n\t"
-            "addc.cc.u32 %5, %12, %12;\n\t"
-            "addc.u32 %6, %6, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]));
-    }
-};
-template <>
-struct ShiftChain<6, false, true> {
-    static EB_HD void run(uint32_t (&out)[6], const uint32_t (&in)[6], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %7, %7;\n\t"
-            "addc.cc.u32 %1, %8, %8;\n\t"
-            "addc.cc.u32 %2, %9, %9;\n\t"
-            "addc.cc.u32 %3, %10, %10;\n\t"
-            "addc.cc.u32 %4, %11, %11;\n\t"
-            "addc.cc.u32 %5, %12, %12;\n\t"
-            "subc.u32 %6, %6, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]));
-    }
-};
-template <>
-struct ShiftChain<6, true, false> {
-    static EB_HD void run(uint32_t (&out)[6], const uint32_t (&in)[6], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %7, %7;\n\t"
-            "addc.cc.u32 %1, %8, %8;\n\t"
-            "addc.cc.u32 %2, %9, %9;\n\t"
-            "addc.cc.u32 %3, %10, %10;\n\t"
-            "addc.cc.u32 %4, %11, %11;\n\t"
-            "addc.cc.u32 %5, %12, %12;\n\t"
-            "addc.u32 %6, %6, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]));
-    }
-};
-template <>
-struct ShiftChain<6, true, true> {
-    static EB_HD void run(uint32_t (&out)[6], const uint32_t (&in)[6], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %7, %7;\n\t"
-            "addc.cc.u32 %1, %8, %8;\n\t"
-            "addc.cc.u32 %2, %9, %9;\n\t"
-            "addc.cc.u32 %3, %10, %10;\n\t"
-            "addc.cc.u32 %4, %11, %11;\n\t"
-            "addc.cc.u32 %5, %12, %12;\n\t"
-            "subc.u32 %6, %6, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]));
-    }
-};
-template <>
-struct ShiftChain<7, false, false> {
-    static EB_HD void run(uint32_t (&out)[7], const uint32_t (&in)[7], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %8, %8;\n\t"
-            "addc.cc.u32 %1, %9, %9;\n\t"
-            "addc.cc.u32 %2, %10, %10;\n\t"
-            "addc.cc.u32 %3, %11, %11;\n\t"
-            "addc.cc.u32 %4, %12, %12;\n\t"
-            "addc.cc.u32 %5, %13, %13;\n\t"
-            "addc.cc.u32 %6, %14, %14;\n\t"
-            "addc.u32 %7, %7, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]));
-    }
-};
-template <>
-struct ShiftChain<7, false, true> {
-    static EB_HD void run(uint32_t (&out)[7], const uint32_t (&in)[7], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %8, %8;\n\t"
-            "addc.cc.u32 %1, %9, %9;\n\t"
-            "addc.cc.u32 %2, %10, %10;\n\t"
-            "addc.cc.u32 %3, %11, %11;\n\t"
-            "addc.cc.u32 %4, %12, %12;\n\t"
-            "addc.cc.u32 %5, %13, %13;\n\t"
-            "addc.cc.u32 %6, %14, %14;\n\t"
-            "subc.u32 %7, %7, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]));
-    }
-};
-template <>
-struct ShiftChain<7, true, false> {
-    static EB_HD void run(uint32_t (&out)[7], const uint32_t (&in)[7], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %8, %8;\n\t"
-            "addc.cc.u32 %1, %9, %9;\n\t"
-            "addc.cc.u32 %2, %10, %10;\n\t"
-            "addc.cc.u32 %3, %11, %11;\n\t"
-            "addc.cc.u32 %4, %12, %12;\n\t"
-            "addc.cc.u32 %5, %13, %13;\n\t"
-            "addc.cc.u32 %6, %14, %14;\n\t"
-            "addc.u32 %7, %7, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]));
-    }
-};
-template <>
-struct ShiftChain<7, true, true> {
-    static EB_HD void run(uint32_t (&out)[7], const uint32_t (&in)[7], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %8, %8;\n\t"
-            "addc.cc.u32 %1, %9, %9;\n\t"
-            "addc.cc.u32 %2, %10, %10;\n\t"
-            "addc.cc.u32 %3, %11, %11;\n\t"
-            "addc.cc.u32 %4, %12, %12;\n\t"
-            "addc.cc.u32 %5, %13, %13;\n\t"
-            "addc.cc.u32 %6, %14, %14;\n\t"
-            "subc.u32 %7, %7, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]));
-    }
-};
-template <>
-struct ShiftChain<8, false, false> {
-    static EB_HD void run(uint32_t (&out)[8], const uint32_t (&in)[8], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %9, %9;\n\t"
-            "addc.cc.u32 %1, %10, %10;\n\t"
-            "addc.cc.u32 %2, %11, %11;\n\t"
-            "addc.cc.u32 %3, %12, %12;\n\t"
-            "addc.cc.u32 %4, %13, %13;\n\t"
-            "addc.cc.u32 %5, %14, %14;\n\t"
-            "addc.cc.u32 %6, %15, %15;\n\t"
-            "addc.cc.u32 %7, %16, %16;\n\t"
-            "addc.u32 %8, %8, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
-    }
-};
-template <>
-struct ShiftChain<8, false, true> {
-    static EB_HD void run(uint32_t (&out)[8], const uint32_t (&in)[8], int& score) {
-        asm("{\n\tadd.cc.u32 %0, %9, %9;\n\t"
-            "addc.cc.u32 %1, %10, %10;\n\t"
-            "addc.cc.u32 %2, %11, %11;\n\t"
-            "addc.cc.u32 %3, %12, %12;\n\t"
-            "addc.cc.u32 %4, %13, %13;\n\t"
-            "addc.cc.u32 %5, %14, %14;\n\t"
-            "addc.cc.u32 %6, %15, %15;\n\t"
-            "addc.cc.u32 %7, %16, %16;\n\t"
-            "subc.u32 %8, %8, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
-    }
-};
-template <>
-struct ShiftChain<8, true, false> {
-    static EB_HD void run(uint32_t (&out)[8], const uint32_t (&in)[8], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %9, %9;\n\t"
-            "addc.cc.u32 %1, %10, %10;\n\t"
-            "addc.cc.u32 %2, %11, %11;\n\t"
-            "addc.cc.u32 %3, %12, %12;\n\t"
-            "addc.cc.u32 %4, %13, %13;\n\t"
-            "addc.cc.u32 %5, %14, %14;\n\t"
-            "addc.cc.u32 %6, %15, %15;\n\t"
-            "addc.cc.u32 %7, %16, %16;\n\t"
-            "addc.u32 %8, %8, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
-    }
-};
-template <>
-struct ShiftChain<8, true, true> {
-    static EB_HD void run(uint32_t (&out)[8], const uint32_t (&in)[8], int& score) {
-        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, 0xffffffff, 1;\n\t"
-            "addc.cc.u32 %0, %9, %9;\n\t"
-            "addc.cc.u32 %1, %10, %10;\n\t"
-            "addc.cc.u32 %2, %11, %11;\n\t"
-            "addc.cc.u32 %3, %12, %12;\n\t"
-            "addc.cc.u32 %4, %13, %13;\n\t"
-            "addc.cc.u32 %5, %14, %14;\n\t"
-            "addc.cc.u32 %6, %15, %15;\n\t"
-            "addc.cc.u32 %7, %16, %16;\n\t"
-            "subc.u32 %8, %8, 0;\n\t}"
-            : "=&r"(out[0]), "=&r"(out[1]), "=&r"(out[2]), "=&r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(score)
-            : "r"(in[0]), "r"(in[1]), "r"(in[2]), "r"(in[3]), "r"(in[4]), "r"(in[5]), "r"(in[6]), "r"(in[7]));
-    }
-};
-#endif
-
 // Pv word for the column before the first one: ones on real rows, zeros on padding bits.
 EB_HD uint32_t init_pv_word(int wordIdx, int off) {
     const int lo = wordIdx * 32;
@@ -612,8 +177,10 @@ EB_HD uint32_t mul_hi(uint32_t x, uint32_t two) {
 #endif
 }
 
-// SHV selects how the <<1 of the horizontal delta words is done: 0 funnel shifts, 1 integer
-// multiply-adds (FMA pipe; IMAD.HI turned out quarter-rate on B200), 2 add-with-carry chains.
+// SHV selects where the helper work around the LOP3 core runs (the sweep is bound by the ALU pipe,
+// profiles/r01_pipe_microbench.txt): 0 = funnel shifts + bit extraction on the ALU pipe;
+// 1 = the <<1 as integer multiply-adds on the FMA pipe (IMAD.HI is quarter-rate on B200, measured
+// slower); 3 = funnel shifts, but the last-row delta bits via IMAD.HI on the otherwise idle FMA pipe.
 template <int NW, bool TOP_ONE, int SHV = 0>
 EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score, uint32_t two = 2u) {
     uint32_t T[NW], S[NW], Ph[NW], Mh[NW];
@@ -626,17 +193,7 @@ EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[
         Ph[w] = Mv[w] | ~(Xh | Pv[w]);
         Mh[w] = Pv[w] & Xh;
     }
-    if (SHV == 2) {
-        uint32_t Phs[NW], Mhs[NW];
-        ShiftChain<NW, TOP_ONE, false>::run(Phs, Ph, score);
-        ShiftChain<NW, false, true>::run(Mhs, Mh, score);
-        EB_UNROLL
-        for (int w = 0; w < NW; ++w) {
-            const uint32_t Xv = Eq[w] | Mv[w];
-            Pv[w] = Mhs[w] | ~(Xv | Phs[w]);
-            Mv[w] = Phs[w] & Xv;
-        }
-    } else if (SHV == 1) {
+    if (SHV == 1) {
         uint32_t cP = TOP_ONE ? 1u : 0u, cM = 0u;
         EB_UNROLL
         for (int w = 0; w < NW; ++w) {
@@ -651,7 +208,8 @@ EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[
         score += (int)cP - (int)cM;  // bit 31 of the last word = delta of the last query row
     } else {
         // the last query row is bit 31 of the last word (top padding, see eb_common.h)
-        score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
+        if (SHV == 3) score += (int)mul_hi(Ph[NW - 1], two) - (int)mul_hi(Mh[NW - 1], two);
+        else score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
         EB_UNROLL
         for (int w = NW - 1; w >= 0; --w) {
             const uint32_t Phs = w ? funnel_l1(Ph[w - 1 < 0 ? 0 : w - 1], Ph[w]) : ((Ph[0] << 1) | (TOP_ONE ? 1u : 0u));
@@ -826,13 +384,13 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     st.two = p.two;
     const K1Chunk g = k1_chunk(p, chunk);
     if (p.mode == MODE_HW && p.rangeMode) {
-        k1_columns<NW, false, false, 2, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_columns<NW, false, true, 2, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, false, 3, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true, 3, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_HW) {
         k1_columns<NW, false, false, 1>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
         k1_columns<NW, false, true, 1>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_SHW) {
-        k1_columns<NW, true, true, 2>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, true, true, 3>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else {
         k1_columns<NW, true, false>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
         st.best = st.score;  // NW: the bottom-right cell (ref cpp:916)

@@ -320,7 +320,7 @@ struct CudaBackend : Backend {
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> pool;
     int launchCount = 0;
-    int shiftVariant = 2;  // EDLIB_B200_K1_SHIFT: 0 funnel shifts, 1 IMAD/IMAD.HI, 2 carry chains (A/B measurements)
+    int shiftVariant = 0;  // EDLIB_B200_K1_SHIFT: kernel variant for A/B measurements (see k1_step)
 
     CudaBackend() {
         const char* v = getenv("EDLIB_B200_K1_SHIFT");
@@ -503,7 +503,7 @@ struct CudaBackend : Backend {
     }
     template <int NW, int MODE>
     void launch_k1_t(const K1Params& p) {
-        if (shiftVariant == 2) launch_k1_v<NW, MODE, 2>(p);
+        if (shiftVariant == 3) launch_k1_v<NW, MODE, 3>(p);
         else if (shiftVariant == 1) launch_k1_v<NW, MODE, 1>(p);
         else launch_k1_v<NW, MODE, 0>(p);
     }
@@ -514,9 +514,9 @@ struct CudaBackend : Backend {
         k1_block(2, p.ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
-        if (shiftVariant == 2) {
-            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k1_kernel<2, MODE_HW, 2, true><<<grid, block, smem, stream>>>(p);
+        if (shiftVariant == 3) {
+            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k1_kernel<2, MODE_HW, 3, true><<<grid, block, smem, stream>>>(p);
         } else if (shiftVariant == 1) {
             EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k1_kernel<2, MODE_HW, 1, true><<<grid, block, smem, stream>>>(p);
