@@ -75,6 +75,24 @@ struct K1Params {
                              //    (Rec.cnt, Rec.pos[0], Rec.last) instead of the running minimum
 };
 
+// K1W: lane-per-alignment HW sweep of each query over ITS OWN window of the shared target (the
+// verification step of the candidate filter).  Columns before trackFrom are halo.
+struct K1WParams {
+    const uint8_t* tcodes;   // encoded target
+    const uint8_t* qcodes;
+    const uint64_t* qoff;    // [pair]
+    const int* qlen;         // [pair]
+    const int* readList;     // [numReads] pair indices
+    const int* kInit;        // [numReads] initial best sentinel (threshold + 1)
+    const int* winStart;     // [numReads] first target column swept
+    const int* winLen;       // [numReads] columns swept
+    const int* trackFrom;    // [numReads] first column (relative to winStart) whose score may be recorded
+    int numReads;
+    int ncodes;
+    const uint8_t* eqtab;
+    Rec* recs;               // [numReads]; positions are absolute target columns
+};
+
 // ---------------------------------------------------------------------------------------------
 // W: warp-per-alignment sweep (any query length, any alphabet, per-job target window).
 // ---------------------------------------------------------------------------------------------

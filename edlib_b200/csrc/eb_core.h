@@ -402,6 +402,23 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     rec->cnt = st.cnt;
 }
 
+// One K1W work item: the whole query over its own target window, symbols read straight from
+// global memory (each lane walks its own window; the target is L2-resident).
+template <int NW, class Acc>
+EB_HD void k1w_thread(const K1WParams& p, int slot, Acc& acc) {
+    const int pair = p.readList[slot];
+    const int m = p.qlen[pair];
+    Rec* rec = p.recs + slot;
+    k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE_HW, p.ncodes, p.eqtab);
+    K1State<NW> st;
+    k1_init<NW>(st, m, p.kInit[slot]);
+    const int ws = p.winStart[slot], tf = p.trackFrom[slot], len = p.winLen[slot];
+    k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + ws}, tf, ws, rec, slot, nullptr, nullptr, 0);
+    k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
+    rec->best = st.best;
+    rec->cnt = st.cnt;
+}
+
 // =============================================================================================
 // W -- one alignment per warp.  Lane l holds R consecutive words (a "chunk"); the 32 chunks of
 // a warp form a window of 1024*R rows.  A query taller than the window is swept in strips

@@ -745,8 +745,7 @@ void Engine::compute(Prepared* p) {
                 launch(cand, thr, 2, chunksA, chunkLenA, 0, P, 1, ra, none);
                 trace.mark("filter: prefix sweep");
                 const int g = (int)cand.size();
-                std::vector<WTask> tasks;
-                std::vector<int> taskSlot;
+                std::vector<int> vSlot, vPair, vK, vWs, vLen, vTf;  // windows to verify
                 auto undecided = [&](int s, int t) {  // the filter cannot decide: bound above its threshold?
                     if (t == bound[s]) {
                         best[list[s]] = 0x7fffffff;   // nothing within the caller's k: final
@@ -784,42 +783,64 @@ void Engine::compute(Prepared* p) {
                         continue;
                     }
                     const long long ws = std::max<long long>(0, lo - 2LL * m);  // HW restart: exact after 2m columns
-                    WTask w;
-                    w.pair = pair;
-                    w.tag = (int)ws;
-                    w.qOff = p->qoff[pair];
-                    w.tOff = tg.off + (uint64_t)ws;
-                    w.m = m;
-                    w.n = (int)(hi - ws + 1);
-                    w.mode = MODE_HW;
-                    w.kInit = t + 1;
-                    w.trackFrom = (int)(lo - ws);
-                    w.wantPositions = true;
-                    const WPlan pl = plan_w(m, w.n, MODE_HW, -1);
-                    w.R = pl.R;
-                    w.nWp = pl.nWp;
-                    tasks.push_back(std::move(w));
-                    taskSlot.push_back(s);
+                    vSlot.push_back(s);
+                    vPair.push_back(pair);
+                    vK.push_back(t + 1);
+                    vWs.push_back((int)ws);
+                    vLen.push_back((int)(hi - ws + 1));
+                    vTf.push_back((int)(lo - ws));
                 }
-                WRunner fr{this, be, p, nullptr, nullptr};
-                trace.mark("filter: window tasks");
-                fr.run(tasks);
-                trace.mark("filter: window sweeps");
-                for (size_t j = 0; j < tasks.size(); ++j) {
-                    const WTask& w = tasks[j];
-                    const int s = taskSlot[j];
-                    const int t = w.kInit - 1;
-                    if (w.rec.cnt <= 0 || w.rec.best > t) {  // the window minimum is above the threshold
-                        undecided(s, t);
-                        continue;
+                trace.mark("filter: windows planned");
+                const int V = (int)vSlot.size();
+                if (V > 0) {
+                    // Whole reads over their windows, one read per thread (k1w_kernel).
+                    DevBuf<int> dPair(be, V), dK(be, V), dWs(be, V), dLen(be, V), dTf(be, V);
+                    dPair.upload(vPair.data(), V);
+                    dK.upload(vK.data(), V);
+                    dWs.upload(vWs.data(), V);
+                    dLen.upload(vLen.data(), V);
+                    dTf.upload(vTf.data(), V);
+                    DevBuf<Rec> dRecs(be, V);
+                    be->zero(dRecs.p, (size_t)V * sizeof(Rec));
+                    K1WParams wp;
+                    memset(&wp, 0, sizeof(wp));
+                    wp.tcodes = p->dSeq.p + tg.off;
+                    wp.qcodes = p->dSeq.p;
+                    wp.qoff = p->dQoff.p;
+                    wp.qlen = p->dQlen.p;
+                    wp.readList = dPair.p;
+                    wp.kInit = dK.p;
+                    wp.winStart = dWs.p;
+                    wp.winLen = dLen.p;
+                    wp.trackFrom = dTf.p;
+                    wp.numReads = V;
+                    wp.ncodes = p->ncodes;
+                    wp.eqtab = p->hasEq ? p->dEqtab.p : nullptr;
+                    wp.recs = dRecs.p;
+                    be->launch_k1w(wp, nw);
+                    std::vector<Rec> rv(V);
+                    dRecs.download(rv.data(), V);
+                    stats.d2hBytes += (long long)V * (long long)sizeof(Rec);
+                    trace.mark("filter: window sweeps");
+                    for (int j = 0; j < V; ++j) {
+                        const Rec& r = rv[j];
+                        const int s = vSlot[j], t = vK[j] - 1, pair = vPair[j];
+                        if (r.cnt <= 0 || r.best > t) {  // the window minimum is above the threshold
+                            undecided(s, t);
+                            continue;
+                        }
+                        if (r.cnt > KPOS) {  // long end-location list: the plain sweep collects it
+                            direct.push_back(s);
+                            stats.filterFallback++;
+                            continue;
+                        }
+                        stats.filterDecided++;
+                        best[pair] = r.best;
+                        cnt[pair] = r.cnt;
+                        posStart[pair] = (long long)posPool.size();
+                        for (int q = 0; q < r.cnt; ++q) posPool.push_back(r.pos[q]);
+                        posLen[pair] = r.cnt;
                     }
-                    stats.filterDecided++;
-                    best[w.pair] = w.rec.best;
-                    cnt[w.pair] = w.rec.cnt;
-                    posStart[w.pair] = (long long)posPool.size();
-                    for (int q = 0; q < std::min(w.rec.cnt, KPOS); ++q) posPool.push_back(w.rec.pos[q] + w.tag);
-                    for (int e : w.extra) posPool.push_back(e + w.tag);
-                    posLen[w.pair] = (int)((long long)posPool.size() - posStart[w.pair]);
                 }
             }
         } else {

@@ -34,6 +34,7 @@ struct Backend {
     virtual void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int numPairs, int* out) = 0;
     virtual void launch_encode(const EncodeParams& p) = 0;
     virtual void launch_k1(const K1Params& p, int nw32) = 0;
+    virtual void launch_k1w(const K1WParams& p, int nw32) = 0;
     virtual void launch_peq(const PeqParams& p) = 0;
     virtual void launch_w(const WParams& p, int R) = 0;
     virtual void launch_traceback(const TbParams& p) = 0;

@@ -245,6 +245,20 @@ __global__ void k1_kernel(const K1Params p) {
     }
 }
 
+// K1W: same per-thread sweep, every thread over its own target window read through the generic
+// (global) pointer path; no tile staging, no barriers after the Peq build.
+template <int NW>
+__global__ void k1w_kernel(const K1WParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= p.numReads) return;
+    SmemPeqAcc<NW> acc;
+    acc.codeStride = (uint32_t)blockDim.x * (16u + 4u * SmemPeqAcc<NW>::NWB);
+    acc.a0 = smem_u32(smem) + 16u * threadIdx.x;
+    acc.b0 = smem_u32(smem) + 16u * blockDim.x + 4u * SmemPeqAcc<NW>::NWB * threadIdx.x;
+    k1w_thread<NW>(p, slot, acc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // W and the small kernels
 // ---------------------------------------------------------------------------------------------
@@ -320,11 +334,10 @@ struct CudaBackend : Backend {
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> pool;
     int launchCount = 0;
-    int shiftVariant = 0;  // EDLIB_B200_K1_SHIFT: kernel variant for A/B measurements (see k1_step)
+
 
     CudaBackend() {
-        const char* v = getenv("EDLIB_B200_K1_SHIFT");
-        if (v && *v) shiftVariant = atoi(v);
+
         int dev = 0;
         EB_CUDA(cudaGetDevice(&dev));
         cudaDeviceProp prop;
@@ -503,9 +516,7 @@ struct CudaBackend : Backend {
     }
     template <int NW, int MODE>
     void launch_k1_t(const K1Params& p) {
-        if (shiftVariant == 3) launch_k1_v<NW, MODE, 3>(p);
-        else if (shiftVariant == 1) launch_k1_v<NW, MODE, 1>(p);
-        else launch_k1_v<NW, MODE, 0>(p);
+        launch_k1_v<NW, MODE, 0>(p);
     }
     // candidate-filter sweep: 64-row prefixes (two words), HW, range recording
     void launch_k1_range(const K1Params& p) {
@@ -514,16 +525,8 @@ struct CudaBackend : Backend {
         k1_block(2, p.ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
-        if (shiftVariant == 3) {
-            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k1_kernel<2, MODE_HW, 3, true><<<grid, block, smem, stream>>>(p);
-        } else if (shiftVariant == 1) {
-            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k1_kernel<2, MODE_HW, 1, true><<<grid, block, smem, stream>>>(p);
-        } else {
-            EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k1_kernel<2, MODE_HW, 0, true><<<grid, block, smem, stream>>>(p);
-        }
+        EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_kernel<2, MODE_HW, 0, true><<<grid, block, smem, stream>>>(p);
         check_launch("k1 range");
     }
     template <int NW>
@@ -549,6 +552,29 @@ struct CudaBackend : Backend {
             case 7: launch_k1_m<7>(p); break;
             case 8: launch_k1_m<8>(p); break;
             default: throw std::runtime_error("bad K1 word class");
+        }
+    }
+    template <int NW>
+    void launch_k1w_t(const K1WParams& p) {
+        const int block = 128;
+        const size_t smem = (size_t)p.ncodes * block * (16 + 4 * (NW > 4 ? NW - 4 : 0));
+        if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1W: alphabet too large for shared memory");
+        EB_CUDA(cudaFuncSetAttribute(k1w_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1w_kernel<NW><<<(p.numReads + block - 1) / block, block, smem, stream>>>(p);
+        check_launch("k1w");
+    }
+    void launch_k1w(const K1WParams& p, int nw) override {
+        Scope s(this, "k1w");
+        switch (nw) {
+            case 1: launch_k1w_t<1>(p); break;
+            case 2: launch_k1w_t<2>(p); break;
+            case 3: launch_k1w_t<3>(p); break;
+            case 4: launch_k1w_t<4>(p); break;
+            case 5: launch_k1w_t<5>(p); break;
+            case 6: launch_k1w_t<6>(p); break;
+            case 7: launch_k1w_t<7>(p); break;
+            case 8: launch_k1w_t<8>(p); break;
+            default: throw std::runtime_error("bad K1W word class");
         }
     }
     void launch_peq(const PeqParams& p) override {

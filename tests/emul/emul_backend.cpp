@@ -52,6 +52,13 @@ void emul_k1(const K1Params& p) {
         for (int slot = 0; slot < p.numReads; ++slot) k1_thread<NW>(p, slot, chunk, acc);
 }
 
+template <int NW>
+void emul_k1w(const K1WParams& p) {
+    HostPeqAcc<NW> acc;
+    acc.w.assign((size_t)p.ncodes * NW, 0);
+    for (int slot = 0; slot < p.numReads; ++slot) k1w_thread<NW>(p, slot, acc);
+}
+
 struct EmulBackend : Backend {
     int launchesCount = 0;
     void* alloc(size_t bytes) override {
@@ -99,6 +106,20 @@ struct EmulBackend : Backend {
             case 7: emul_k1<7>(p); break;
             case 8: emul_k1<8>(p); break;
             default: throw std::runtime_error("bad K1 word class");
+        }
+    }
+    void launch_k1w(const K1WParams& p, int nw) override {
+        ++launchesCount;
+        switch (nw) {
+            case 1: emul_k1w<1>(p); break;
+            case 2: emul_k1w<2>(p); break;
+            case 3: emul_k1w<3>(p); break;
+            case 4: emul_k1w<4>(p); break;
+            case 5: emul_k1w<5>(p); break;
+            case 6: emul_k1w<6>(p); break;
+            case 7: emul_k1w<7>(p); break;
+            case 8: emul_k1w<8>(p); break;
+            default: throw std::runtime_error("bad K1W word class");
         }
     }
     void launch_peq(const PeqParams& p) override {
