@@ -20,6 +20,7 @@
 #include <chrono>
 #include <map>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
 
 namespace eb {
@@ -238,11 +239,21 @@ Prepared* Engine::prepare(const BatchInput& in) {
         total += 16;
         uint8_t* stage = static_cast<uint8_t*>(be->alloc_host(total));
         {
-            size_t pos = 0;
-            for (int i = 0; i < N; ++i) {
-                if (p->qlen[i]) memcpy(stage + pos, in.queries[i], (size_t)p->qlen[i]);
-                pos += (size_t)p->qlen[i];
+            // queries: copied by a few host threads when the batch is large (pure memcpy work)
+            const size_t qBytes = N ? (size_t)(p->qoff[N - 1] + (uint64_t)p->qlen[N - 1]) : 0;
+            const int nthr = qBytes > (32u << 20) ? (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+            auto copy_range = [&](int lo, int hi) {
+                for (int i = lo; i < hi; ++i)
+                    if (p->qlen[i]) memcpy(stage + p->qoff[i], in.queries[i], (size_t)p->qlen[i]);
+            };
+            if (nthr > 1) {
+                std::vector<std::thread> th;
+                for (int t = 0; t < nthr; ++t) th.emplace_back(copy_range, (int)((long long)N * t / nthr), (int)((long long)N * (t + 1) / nthr));
+                for (auto& x : th) x.join();
+            } else {
+                copy_range(0, N);
             }
+            size_t pos = qBytes;
             size_t end = p->tg.empty() ? total : p->tg[0].off;
             memset(stage + pos, 0, end - pos);
             for (int t = 0; t < T; ++t) {
@@ -572,7 +583,9 @@ void Engine::compute(Prepared* p) {
     // ---- K1 groups ----------------------------------------------------------------------
     for (auto& kv : groups) {
         std::vector<int>& list = kv.second;
-        if ((int)list.size() < tun.k1MinGroup) {
+        // Small groups go to the warp kernel, except HW over a long target: there the lane kernel
+        // can cut the target into chunks and spread even one alignment over many CTAs.
+        if ((int)list.size() < tun.k1MinGroup && !(mode == MODE_HW && p->tg[kv.first.first].len >= 8 * tun.k1MinChunk)) {
             wPairs.insert(wPairs.end(), list.begin(), list.end());
             continue;
         }

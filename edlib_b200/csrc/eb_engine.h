@@ -55,7 +55,7 @@ struct BatchInput {
 
 struct EngineTunables {
     int k1MinGroup = 32;          // pairs sharing one target before the lane-per-alignment kernel is used
-    int k1MinChunk = 8192;        // smallest target chunk (columns) when one HW sweep is split
+    int k1MinChunk = 1024;        // smallest target chunk (columns) when one HW sweep is split
     int ovfCap = 1 << 20;         // overflow entries per launch before the exact-size retry
     size_t sliceBytes = 1ull << 30;  // device memory budget of one slice of W jobs
     // Candidate filter for HW sweeps of reads over a shared target (0 disables): a 64-row prefix
