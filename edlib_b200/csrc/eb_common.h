@@ -69,7 +69,6 @@ struct K1Params {
     Ovf* ovf;
     int* ovfCount;
     int ovfCap;
-    uint32_t two;            // the constant 2, passed as data so ptxas keeps IMADs (eb_core.h: mad_lo)
     int prefixLen;           // > 0: sweep only the first prefixLen rows of every query (candidate filter)
     int rangeMode;           // 1: record {count, first, last} of the columns whose score is <= kInit
                              //    (Rec.cnt, Rec.pos[0], Rec.last) instead of the running minimum

@@ -154,35 +154,11 @@ EB_HD uint32_t init_pv_word(int wordIdx, int off) {
 // calculateBlock (cpp:421-444) but over ONE NW*32-bit integer: the add carry and the <<1 carry
 // cross word boundaries natively, so no per-block hin/hout is needed.  TOP_ONE selects the
 // horizontal delta entering above row 0: +1 for NW/SHW (cpp:779, 584), 0 for HW.
-// x*two + c and its high half, kept as integer multiply-adds (IMAD / IMAD.HI, FMA pipe).  `two`
-// is the constant 2 delivered through the kernel parameters so that ptxas cannot strength-reduce
-// the products back into shifts: the sweep is bound by the ALU pipe (LOP3/SHF/IADD3), the FMA
-// pipe is idle, so the <<1 of the horizontal delta words is moved over there.
-EB_HD uint32_t mad_lo(uint32_t x, uint32_t two, uint32_t c) {
-#if defined(__CUDA_ARCH__)
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(two), "r"(c));
-    return r;
-#else
-    return x * two + c;
-#endif
-}
-EB_HD uint32_t mul_hi(uint32_t x, uint32_t two) {
-#if defined(__CUDA_ARCH__)
-    uint32_t r;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(two));
-    return r;
-#else
-    return (uint32_t)(((uint64_t)x * two) >> 32);
-#endif
-}
-
-// SHV selects where the helper work around the LOP3 core runs (the sweep is bound by the ALU pipe,
-// profiles/r01_pipe_microbench.txt): 0 = funnel shifts + bit extraction on the ALU pipe;
-// 1 = the <<1 as integer multiply-adds on the FMA pipe (IMAD.HI is quarter-rate on B200, measured
-// slower); 3 = funnel shifts, but the last-row delta bits via IMAD.HI on the otherwise idle FMA pipe.
-template <int NW, bool TOP_ONE, int SHV = 0>
-EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score, uint32_t two = 2u) {
+// (Measured alternatives, dropped: doing the <<1 or the last-row bit extraction with IMAD/IMAD.HI on
+// the idle FMA pipe is slower because the high-half multiply is quarter-rate on B200, and an
+// add-with-carry chain needs as many ALU instructions as the funnel shifts; profiles/README.md.)
+template <int NW, bool TOP_ONE>
+EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score) {
     uint32_t T[NW], S[NW], Ph[NW], Mh[NW];
     EB_UNROLL
     for (int w = 0; w < NW; ++w) T[w] = Eq[w] & Pv[w];
@@ -193,31 +169,15 @@ EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[
         Ph[w] = Mv[w] | ~(Xh | Pv[w]);
         Mh[w] = Pv[w] & Xh;
     }
-    if (SHV == 1) {
-        uint32_t cP = TOP_ONE ? 1u : 0u, cM = 0u;
-        EB_UNROLL
-        for (int w = 0; w < NW; ++w) {
-            const uint32_t Phs = mad_lo(Ph[w], two, cP);
-            const uint32_t Mhs = mad_lo(Mh[w], two, cM);
-            cP = mul_hi(Ph[w], two);
-            cM = mul_hi(Mh[w], two);
-            const uint32_t Xv = Eq[w] | Mv[w];
-            Pv[w] = Mhs | ~(Xv | Phs);
-            Mv[w] = Phs & Xv;
-        }
-        score += (int)cP - (int)cM;  // bit 31 of the last word = delta of the last query row
-    } else {
-        // the last query row is bit 31 of the last word (top padding, see eb_common.h)
-        if (SHV == 3) score += (int)mul_hi(Ph[NW - 1], two) - (int)mul_hi(Mh[NW - 1], two);
-        else score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
-        EB_UNROLL
-        for (int w = NW - 1; w >= 0; --w) {
-            const uint32_t Phs = w ? funnel_l1(Ph[w - 1 < 0 ? 0 : w - 1], Ph[w]) : ((Ph[0] << 1) | (TOP_ONE ? 1u : 0u));
-            const uint32_t Mhs = w ? funnel_l1(Mh[w - 1 < 0 ? 0 : w - 1], Mh[w]) : (Mh[0] << 1);
-            const uint32_t Xv = Eq[w] | Mv[w];
-            Pv[w] = Mhs | ~(Xv | Phs);
-            Mv[w] = Phs & Xv;
-        }
+    // the last query row is bit 31 of the last word (top padding, see eb_common.h)
+    score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
+    EB_UNROLL
+    for (int w = NW - 1; w >= 0; --w) {
+        const uint32_t Phs = w ? funnel_l1(Ph[w - 1 < 0 ? 0 : w - 1], Ph[w]) : ((Ph[0] << 1) | (TOP_ONE ? 1u : 0u));
+        const uint32_t Mhs = w ? funnel_l1(Mh[w - 1 < 0 ? 0 : w - 1], Mh[w]) : (Mh[0] << 1);
+        const uint32_t Xv = Eq[w] | Mv[w];
+        Pv[w] = Mhs | ~(Xv | Phs);
+        Mv[w] = Phs & Xv;
     }
 }
 
@@ -228,7 +188,6 @@ struct K1State {
     int score;  // D[m-1][c] of the last column swept
     int best;   // running minimum (starts at the bound sentinel)
     int cnt;    // columns attaining best so far
-    uint32_t two;  // the constant 2, opaque to ptxas (see mad_lo)
 };
 
 template <int NW>
@@ -242,7 +201,6 @@ EB_HD void k1_init(K1State<NW>& st, int m, int kInit) {
     st.score = m;  // D[m-1][-1] = m  (ref cpp:576, 760)
     st.best = kInit;
     st.cnt = 0;
-    st.two = 2u;
 }
 
 // Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
@@ -286,14 +244,14 @@ struct PtrSyms {
 // running minimum and its columns are recorded; without it only the state advances (halo
 // columns of a chunk).  Columns go four at a time: the four last-row scores stay in registers
 // and are compared against the running minimum once per group (events are rare).
-template <int NW, bool TOP_ONE, bool TRACK, int SHV = 0, bool RANGE = false, class Acc, class Syms>
+template <int NW, bool TOP_ONE, bool TRACK, bool RANGE = false, class Acc, class Syms>
 EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int count, int cAbs,
                       Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     int i = 0;
     while (i < count && !syms.aligned4(i)) {  // head: until the symbols are 4-byte aligned
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
-        k1_step<NW, TOP_ONE, SHV>(st.Pv, st.Mv, Eq, st.score, st.two);
+        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
         if (TRACK && st.score <= st.best) k1_event<NW, RANGE>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
         ++i;
     }
@@ -303,7 +261,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
         for (int j = 0; j < 4; ++j) {
             uint32_t Eq[NW];
             acc.load(syms.read1(i + j), Eq);
-            k1_step<NW, TOP_ONE, SHV>(st.Pv, st.Mv, Eq, st.score, st.two);
+            k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
             sc[j] = st.score;
         }
         if (TRACK) {
@@ -320,7 +278,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
     for (; i < count; ++i) {  // tail
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
-        k1_step<NW, TOP_ONE, SHV>(st.Pv, st.Mv, Eq, st.score, st.two);
+        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
         if (TRACK && st.score <= st.best) k1_event<NW, RANGE>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
     }
 }
@@ -381,16 +339,15 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     k1_build_peq<NW>(acc, q, m, p.mode, p.ncodes, p.eqtab);
     K1State<NW> st;
     k1_init<NW>(st, m, p.kInit[slot]);
-    st.two = p.two;
     const K1Chunk g = k1_chunk(p, chunk);
     if (p.mode == MODE_HW && p.rangeMode) {
-        k1_columns<NW, false, false, 3, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_columns<NW, false, true, 3, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, false, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_HW) {
-        k1_columns<NW, false, false, 1>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_columns<NW, false, true, 1>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else if (p.mode == MODE_SHW) {
-        k1_columns<NW, true, true, 3>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else {
         k1_columns<NW, true, false>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
         st.best = st.score;  // NW: the bottom-right cell (ref cpp:916)

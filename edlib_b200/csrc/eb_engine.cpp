@@ -590,6 +590,14 @@ void Engine::compute(Prepared* p) {
             continue;
         }
         const int t = kv.first.first, nw = kv.first.second;
+        {
+            int bt = 0, rc = 0;
+            be->k1_shape(nw, p->ncodes, &bt, &rc);
+            if (rc <= 0) {  // alphabet too large for per-thread Peq rows in shared memory
+                wPairs.insert(wPairs.end(), list.begin(), list.end());
+                continue;
+            }
+        }
         const Target& tg = p->tg[t];
         const int G = (int)list.size();
         const int n = tg.len;
@@ -659,7 +667,6 @@ void Engine::compute(Prepared* p) {
             kp.ovf = dOvf.p;
             kp.ovfCount = dCount.p;
             kp.ovfCap = cap;
-            kp.two = 2u;
             kp.prefixLen = prefixLen;
             kp.rangeMode = rangeMode;
             be->launch_k1(kp, nwL);

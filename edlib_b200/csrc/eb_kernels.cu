@@ -162,7 +162,7 @@ EB_D void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
                  : "memory");
 }
 
-template <int NW, int MODE, int SHV, bool RANGE = false>
+template <int NW, int MODE, bool RANGE = false>
 __global__ void k1_kernel(const K1Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -209,7 +209,6 @@ __global__ void k1_kernel(const K1Params p) {
         const int m = p.prefixLen > 0 ? p.prefixLen : p.qlen[pair];
         k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE, p.ncodes, p.eqtab);
         k1_init<NW>(st, m, p.kInit[slot]);
-        st.two = p.two;
         recIdx = chunk * p.numReads + slot;
         rec = p.recs + recIdx;
     }
@@ -223,12 +222,12 @@ __global__ void k1_kernel(const K1Params p) {
             const uint32_t sa = tileAddr[i & 1];
             if (MODE == MODE_HW) {
                 const int mid = min(max(g.cs, a), b);               // columns before cs are halo
-                if (mid > a) k1_columns<NW, false, false, SHV, RANGE>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-                if (b > mid) k1_columns<NW, false, true, SHV, RANGE>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (mid > a) k1_columns<NW, false, false, RANGE>(st, acc, SmemSyms{sa}, mid - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                if (b > mid) k1_columns<NW, false, true, RANGE>(st, acc, SmemSyms{sa + (uint32_t)(mid - a)}, b - mid, mid, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             } else if (MODE == MODE_SHW) {
-                k1_columns<NW, true, true, SHV>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                k1_columns<NW, true, true>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             } else {
-                k1_columns<NW, true, false, SHV>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+                k1_columns<NW, true, false>(st, acc, SmemSyms{sa}, b - a, a, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
             }
         }
         __syncthreads();  // everyone is done with tile i before its buffer is refilled
@@ -469,22 +468,22 @@ struct CudaBackend : Backend {
         *block = b;
         *smem = fixed + perThread * b;
     }
-    template <int NW, int MODE, int SHV>
-    void launch_k1_v(const K1Params& p) {
+    template <int NW, int MODE>
+    void launch_k1_t(const K1Params& p) {
         int block;
         size_t smem;
         k1_block(NW, p.ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
-        EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE, SHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
-        k1_kernel<NW, MODE, SHV><<<grid, block, smem, stream>>>(p);
+        k1_kernel<NW, MODE><<<grid, block, smem, stream>>>(p);
         check_launch("k1");
     }
     template <int NW>
     int k1_occupancy(int block, size_t smem) {
         int perSm = 0;
-        cudaFuncSetAttribute(k1_kernel<NW, MODE_HW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_kernel<NW, MODE_HW, 0>, block, smem) != cudaSuccess) perSm = 1;
+        cudaFuncSetAttribute(k1_kernel<NW, MODE_HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k1_kernel<NW, MODE_HW>, block, smem) != cudaSuccess) perSm = 1;
         return perSm < 1 ? 1 : perSm;
     }
     std::vector<int> shapeCache;  // [nw*1024 + ncodes] -> block | resident << 12, 0 = unknown
@@ -499,6 +498,11 @@ struct CudaBackend : Backend {
         int block;
         size_t smem;
         k1_block(nw, ncodes, &block, &smem);
+        if (smem > (size_t)maxSmemOptin) {  // Peq rows of even a 32-thread CTA do not fit: not a K1 case
+            *blockThreads = block;
+            *residentCtas = 0;
+            return;
+        }
         int perSm = 1;
         switch (nw) {
             case 1: perSm = k1_occupancy<1>(block, smem); break;
@@ -514,10 +518,6 @@ struct CudaBackend : Backend {
         *residentCtas = perSm * sms;
         if (ncodes < 1023) shapeCache[key] = block | ((perSm * sms) << 12);
     }
-    template <int NW, int MODE>
-    void launch_k1_t(const K1Params& p) {
-        launch_k1_v<NW, MODE, 0>(p);
-    }
     // candidate-filter sweep: 64-row prefixes (two words), HW, range recording
     void launch_k1_range(const K1Params& p) {
         int block;
@@ -525,8 +525,8 @@ struct CudaBackend : Backend {
         k1_block(2, p.ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
-        EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1_kernel<2, MODE_HW, 0, true><<<grid, block, smem, stream>>>(p);
+        EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_kernel<2, MODE_HW, true><<<grid, block, smem, stream>>>(p);
         check_launch("k1 range");
     }
     template <int NW>
@@ -556,8 +556,10 @@ struct CudaBackend : Backend {
     }
     template <int NW>
     void launch_k1w_t(const K1WParams& p) {
-        const int block = 128;
-        const size_t smem = (size_t)p.ncodes * block * (16 + 4 * (NW > 4 ? NW - 4 : 0));
+        int block = 128;
+        const size_t perThread = (size_t)p.ncodes * (16 + 4 * (NW > 4 ? NW - 4 : 0));
+        while (block > 32 && perThread * block > 96 * 1024) block >>= 1;
+        const size_t smem = perThread * block;
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1W: alphabet too large for shared memory");
         EB_CUDA(cudaFuncSetAttribute(k1w_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k1w_kernel<NW><<<(p.numReads + block - 1) / block, block, smem, stream>>>(p);

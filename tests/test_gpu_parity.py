@@ -56,6 +56,78 @@ def test_candidate_filter_all_branches():
         assert int(out.stdout.strip().splitlines()[-1]) > 500
 
 
+def test_large_alphabets_and_equalities(lib):
+    """Protein-sized and full-byte alphabets over shared targets (per-thread Peq rows shrink the CTA or
+    push the group to the warp kernel), with and without extra equalities."""
+    import random
+    from helpers import mutate, rand_seq
+    chk = parity.checker()
+    rng = random.Random(31)
+    for asz in (20, 25, 64, 256):
+        alpha = bytes(rng.sample(range(256), asz))
+        t = rand_seq(rng, 4000, alpha)
+        qs = []
+        for _ in range(80):
+            a = rng.randrange(0, len(t) - 300)
+            qs.append(mutate(rng, t[a:a + rng.choice([40, 150, 250])], 0.08, alpha))
+        eqs = [(bytes([alpha[0]]), bytes([alpha[1]])), (bytes([alpha[2]]), bytes([alpha[3]]))]
+        for mode, task, e in ((2, 1, None), (1, 0, eqs), (0, 2, eqs), (2, 2, eqs)):
+            st, res = lib.align_batch(qs, [t] * len(qs), -1, mode, task, e)
+            assert st == 0
+            for i in range(0, len(qs), 5):
+                assert res[i] == chk.align(qs[i], t, -1, mode, task, e), (asz, mode, task, i)
+
+
+def test_concurrent_callers(lib):
+    """The ABI is re-entrant (called without the GIL by the reference binding): threads serialise safely."""
+    import random
+    from concurrent.futures import ThreadPoolExecutor
+    from helpers import mutate, rand_seq
+    chk = parity.checker()
+    rng = random.Random(5)
+    t = rand_seq(rng, 3000, b"ACGT")
+    qs = [mutate(rng, t[a:a + 120], 0.05, b"ACGT") for a in range(0, 2400, 40)]
+    exp = [chk.align(q, t, -1, 2, 1) for q in qs]
+    with ThreadPoolExecutor(8) as ex:
+        got = list(ex.map(lambda q: lib.align(q, t, -1, 2, 1), qs * 3))
+    assert got == exp * 3
+
+
+def test_results_do_not_depend_on_the_plan():
+    """Size-independent property on a config-2-shaped batch too large for the CPU checker: the same
+    200k reads give identical results with the candidate filter on/off and under different chunkings."""
+    import hashlib
+    import subprocess
+    from edlib_b200._ffi import REPO
+    code = (
+        "import sys, hashlib; sys.path.insert(0, %r)\n"
+        "import numpy as np, ctypes as C\n"
+        "import bench\n"
+        "from edlib_b200 import workloads\n"
+        "from edlib_b200._ffi import EdlibLib, AlignResult, make_config, product_path\n"
+        "lib = EdlibLib(product_path(), has_batch=True)\n"
+        "target, reads = workloads.reads_vs_target(200000, 150, 1000000, seed=11)\n"
+        "qptr, qlen, tptr, tlen = bench.pointer_arrays(reads, target)\n"
+        "cfg, _ = make_config(-1, 2, 1)\n"
+        "res = np.zeros(len(reads), dtype=bench.RESULT_DTYPE)\n"
+        "rc = lib.lib.edlibAlignBatch(bench.as_pp(qptr), bench.as_pi(qlen), bench.as_pp(tptr), bench.as_pi(tlen), len(reads), cfg,\n"
+        "                             C.cast(res.ctypes.data, C.POINTER(AlignResult)))\n"
+        "assert rc == 0\n"
+        "h = hashlib.sha1()\n"
+        "h.update(res['editDistance'].tobytes()); h.update(res['numLocations'].tobytes())\n"
+        "for i in range(0, len(reads), 1):\n"
+        "    n = int(res['numLocations'][i])\n"
+        "    h.update(C.string_at(int(res['endLocations'][i]), 4 * n)); h.update(C.string_at(int(res['startLocations'][i]), 4 * n))\n"
+        "print(h.hexdigest(), float(res['editDistance'].mean()))\n"
+    ) % REPO
+    digests = []
+    for extra in ({}, {"EDLIB_B200_FILTER_K0": "0"}, {"EDLIB_B200_FILTER_K0": "5", "EDLIB_B200_K1_MIN_CHUNK": "4096"},
+                  {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_K1_MIN_CHUNK": "200000"}):
+        out = subprocess.run(["python", "-c", code], env=dict(os.environ, **extra), check=True, capture_output=True, text=True)
+        digests.append(out.stdout.strip().split()[0])
+    assert len(set(digests)) == 1, digests
+
+
 def test_many_end_locations(lib):
     chk = parity.checker()
     for q, t, mode in [(b"A" * 64, b"B" * 70, 2), (b"A" * 10, b"A" * 300, 2), (b"AC" * 20, b"AC" * 200, 2),
