@@ -1,0 +1,66 @@
+"""The batched command-line aligner (apps/aligner/aligner.cpp over edlibAlignBatch) must print what the
+reference's edlib-aligner prints (reference apps/aligner/aligner.cpp, built unmodified into
+oracle/_ref/edlib-aligner_ref by `make -C oracle reftests`), for every option combination, except the
+progress counter and the timing line."""
+import os
+import random
+import subprocess
+
+import pytest
+
+from edlib_b200._ffi import REPO
+from helpers import mutate, rand_seq
+
+REFBIN = os.path.join(REPO, "oracle", "_ref")
+OPTION_SETS = [["-m", "HW"], ["-m", "NW", "-l"], ["-m", "SHW", "-l", "-k", "30"], ["-m", "HW", "-p", "-f", "CIG_EXT"],
+               ["-m", "HW", "-p"], ["-m", "NW", "-p", "-f", "CIG_STD"], ["-m", "HW", "-n", "5", "-l"],
+               ["-m", "HW", "-n", "3", "-k", "8", "-p", "-f", "CIG_EXT"], ["-m", "SHW", "-n", "2"]]
+
+
+def write_fasta(path, seqs):
+    with open(path, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(">seq%d some description\n" % i)
+            for a in range(0, len(s), 70):
+                f.write(s[a:a + 70].decode() + "\n")
+
+
+def make_inputs(tmp):
+    rng = random.Random(77)
+    t = rand_seq(rng, 20000, b"ACGT")
+    qs = []
+    for i in range(60):
+        a = rng.randrange(0, len(t) - 400)
+        qs.append(mutate(rng, t[a:a + rng.choice([60, 150, 300])], rng.choice([0.0, 0.03, 0.1]), b"ACGT"))
+    qs.append(rand_seq(rng, 120, b"ACGT"))
+    qf, tf = os.path.join(tmp, "q.fasta"), os.path.join(tmp, "t.fasta")
+    write_fasta(qf, qs)
+    write_fasta(tf, [t])
+    return qf, tf
+
+
+def normalised(exe, opts, qf, tf):
+    out = subprocess.run([exe] + opts + [qf, tf], capture_output=True, text=True, check=True).stdout
+    lines = out.replace("\r", "\n").split("\n")
+    return [l for l in lines if not l.startswith("Cpu time") and not (l and l.replace("/", "").isdigit())]
+
+
+def compare(mine, tmp_path):
+    ref = os.path.join(REFBIN, "edlib-aligner_ref")
+    if not (os.path.exists(ref) and os.path.exists(mine)):
+        pytest.skip("aligner binaries not built")
+    qf, tf = make_inputs(str(tmp_path))
+    for opts in OPTION_SETS:
+        assert normalised(mine, opts, qf, tf) == normalised(ref, opts, qf, tf), opts
+
+
+def test_aligner_matches_reference_on_emulated_kernels(tmp_path):
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-s", "-C", os.path.join(REPO, "tests", "emul")], check=True)
+        subprocess.run(["make", "-s", "-C", os.path.join(REPO, "oracle"), "reftests"], check=True)
+    compare(os.path.join(REFBIN, "edlib-aligner_emul"), tmp_path)
+
+
+@pytest.mark.gpu
+def test_aligner_matches_reference_on_gpu(tmp_path):
+    compare(os.path.join(REPO, "edlib_b200", "lib", "edlib-aligner"), tmp_path)
