@@ -239,26 +239,44 @@ Prepared* Engine::prepare(const BatchInput& in) {
         total += 16;
         uint8_t* stage = static_cast<uint8_t*>(be->alloc_host(total));
         {
-            // queries: copied by a few host threads when the batch is large (pure memcpy work)
+            // Pure memcpy work, split by bytes over a few host threads when the batch is large:
+            // items 0..N-1 are the queries, N..N+T-1 the distinct targets.
             const size_t qBytes = N ? (size_t)(p->qoff[N - 1] + (uint64_t)p->qlen[N - 1]) : 0;
-            const int nthr = qBytes > (32u << 20) ? (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
-            auto copy_range = [&](int lo, int hi) {
-                for (int i = lo; i < hi; ++i)
-                    if (p->qlen[i]) memcpy(stage + p->qoff[i], in.queries[i], (size_t)p->qlen[i]);
+            size_t allBytes = qBytes;
+            for (int t = 0; t < T; ++t) allBytes += (size_t)p->tg[t].len;
+            const int nthr = allBytes > (32u << 20) ? (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+            auto copy_item = [&](int it) {
+                if (it < N) {
+                    if (p->qlen[it]) memcpy(stage + p->qoff[it], in.queries[it], (size_t)p->qlen[it]);
+                } else {
+                    const Target& g = p->tg[it - N];
+                    if (g.len) memcpy(stage + g.off, g.ptr, (size_t)g.len);
+                }
             };
             if (nthr > 1) {
+                // contiguous item ranges of roughly equal byte counts
+                std::vector<int> cut(nthr + 1, N + T);
+                cut[0] = 0;
+                size_t acc = 0;
+                int next = 1;
+                for (int it = 0; it < N + T && next < nthr; ++it) {
+                    acc += it < N ? (size_t)p->qlen[it] : (size_t)p->tg[it - N].len;
+                    if (acc >= allBytes * next / nthr) cut[next++] = it + 1;
+                }
                 std::vector<std::thread> th;
-                for (int t = 0; t < nthr; ++t) th.emplace_back(copy_range, (int)((long long)N * t / nthr), (int)((long long)N * (t + 1) / nthr));
+                for (int t = 0; t < nthr; ++t)
+                    th.emplace_back([&, t]() {
+                        for (int it = cut[t]; it < cut[t + 1]; ++it) copy_item(it);
+                    });
                 for (auto& x : th) x.join();
             } else {
-                copy_range(0, N);
+                for (int it = 0; it < N + T; ++it) copy_item(it);
             }
             size_t pos = qBytes;
             size_t end = p->tg.empty() ? total : p->tg[0].off;
             memset(stage + pos, 0, end - pos);
             for (int t = 0; t < T; ++t) {
                 const Target& g = p->tg[t];
-                if (g.len) memcpy(stage + g.off, g.ptr, (size_t)g.len);
                 const size_t next = (t + 1 < T) ? p->tg[t + 1].off : total;
                 memset(stage + g.off + g.len, 0, next - g.off - (size_t)g.len);
             }
