@@ -53,15 +53,17 @@ def main():
 
     # ---- config 3: 10 kbp pairs, NW, k = 500, LOC -------------------------------------------------
     qs, ts = workloads.long_pairs(args.pairs3, 10_000, seed=43)
-    batch_call(lib, qs[:64], ts[:64], 500, 0, 1)  # warm-up (context, allocations)
-    res, dt, st = batch_call(lib, qs, ts, 500, 0, 1)
+    batch_call(lib, qs[:64], ts[:64], 500, 0, 1)  # warm-up (context)
+    res, dt_first, st = batch_call(lib, qs, ts, 500, 0, 1)  # first full-size call: pools and staging grow
+    L.edlibB200FreeResults(res, len(qs))
+    res, dt, st = batch_call(lib, qs, ts, 500, 0, 1)        # steady state
     cells = float(sum(len(q) * len(t) for q, t in zip(qs, ts)))
     bad = 0
     for i in range(0, len(qs), max(1, len(qs) // 200)):
         exp = ref.align(qs[i].tobytes(), ts[i].tobytes(), 500, 0, 1)
         bad += result_to_dict(res[i]) != exp
     eds = [res[i].editDistance for i in range(len(qs))]
-    out["config3"] = {"pairs": len(qs), "e2e_s": dt, "pairs_per_s": len(qs) / dt, "gcups_e2e": cells / dt / 1e9,
+    out["config3"] = {"pairs": len(qs), "e2e_first_call_s": dt_first, "e2e_s": dt, "pairs_per_s": len(qs) / dt, "gcups_e2e": cells / dt / 1e9,
                       "kernel_ms": st.kernelMs, "gcups_kernel": cells / (st.kernelMs / 1e3) / 1e9, "launches": st.launches,
                       "h2d": st.h2dBytes, "d2h": st.d2hBytes, "mean_ed": float(np.mean(eds)), "spot_mismatches": bad}
     L.edlibB200FreeResults(res, len(qs))
