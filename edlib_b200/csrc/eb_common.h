@@ -65,13 +65,13 @@ struct K1Params {
     int chunks;              // target chunks (HW only; 1 otherwise)
     int chunkLen;            // multiple of 16
     int halo;                // columns swept before a chunk without tracking (>= 2*max m)
-    Rec* recs;               // [chunks][numReads]
+    Rec* recs;               // [chunks][numReads]  (rangeMode: [numReads])
     Ovf* ovf;
     int* ovfCount;
     int ovfCap;
     int prefixLen;           // > 0: sweep only the first prefixLen rows of every query (candidate filter)
-    int rangeMode;           // 1: record {count, first, last} of the columns whose score is <= kInit
-                             //    (Rec.cnt, Rec.pos[0], Rec.last) instead of the running minimum
+    int rangeMode;           // 1: record {count, first, last} of the columns whose score is <= kInit,
+                             //    merged over chunks into recs[slot] (eb_core.h: k1_range_commit)
 };
 
 // K1W: lane-per-alignment HW sweep of each query over ITS OWN window of the shared target (the

@@ -43,6 +43,14 @@ EB_HD int atomic_add_int(int* p, int v) {
 #endif
 }
 
+EB_HD void atomic_max_int(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+
 EB_HD void atomic_or_u32(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
     atomicOr(p, v);
@@ -188,6 +196,7 @@ struct K1State {
     int score;  // D[m-1][c] of the last column swept
     int best;   // running minimum (starts at the bound sentinel)
     int cnt;    // columns attaining best so far
+    int first, last;  // RANGE mode: first / last column at or below the threshold
 };
 
 template <int NW>
@@ -201,14 +210,15 @@ EB_HD void k1_init(K1State<NW>& st, int m, int kInit) {
     st.score = m;  // D[m-1][-1] = m  (ref cpp:576, 760)
     st.best = kInit;
     st.cnt = 0;
+    st.first = st.last = 0;
 }
 
 // Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
 template <int NW, bool RANGE = false>
 EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     if (RANGE) {  // candidate filter: every column at or below the fixed threshold, as a range
-        if (st.cnt == 0) rec->pos[0] = column;
-        rec->last = column;
+        if (st.cnt == 0) st.first = column;
+        st.last = column;
         st.cnt++;
         return;
     }
@@ -308,6 +318,17 @@ EB_HD void k1_build_peq(Acc& acc, const uint8_t* q, int m, int mode, int ncodes,
     }
 }
 
+// RANGE mode result: the chunks of one read merge on the device into ONE record (zero-initialised by
+// the host): cnt = number of columns at or below the threshold, pos[0] = INT_MAX - first such column,
+// pos[1] = last such column + 1.
+template <int NW>
+EB_HD void k1_range_commit(const K1State<NW>& st, Rec* rec) {
+    if (st.cnt <= 0) return;
+    atomic_add_int(&rec->cnt, st.cnt);
+    atomic_max_int(&rec->pos[0], 0x7fffffff - st.first);
+    atomic_max_int(&rec->pos[1], st.last + 1);
+}
+
 // Chunk geometry of a K1 launch: chunk j owns columns [cs, ce) and starts sweeping at hs.
 struct K1Chunk {
     int hs, cs, ce;
@@ -334,7 +355,7 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     const int pair = p.readList[slot];
     const int m = p.prefixLen > 0 ? p.prefixLen : p.qlen[pair];
     const uint8_t* q = p.qcodes + p.qoff[pair];
-    const int recIdx = chunk * p.numReads + slot;
+    const int recIdx = p.rangeMode ? slot : chunk * p.numReads + slot;
     Rec* rec = p.recs + recIdx;
     k1_build_peq<NW>(acc, q, m, p.mode, p.ncodes, p.eqtab);
     K1State<NW> st;
@@ -343,6 +364,8 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     if (p.mode == MODE_HW && p.rangeMode) {
         k1_columns<NW, false, false, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
         k1_columns<NW, false, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
+        k1_range_commit<NW>(st, rec);
+        return;
     } else if (p.mode == MODE_HW) {
         k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
         k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);

@@ -660,8 +660,9 @@ void Engine::compute(Prepared* p) {
             DevBuf<int> dList(be, g), dK(be, g);
             dList.upload(rl.data(), g);
             dK.upload(subK.data(), g);
-            DevBuf<Rec> dRecs(be, (size_t)g * chunks);
-            be->zero(dRecs.p, (size_t)g * chunks * sizeof(Rec));
+            const size_t numRecs = rangeMode ? (size_t)g : (size_t)g * chunks;  // range records merge on the device
+            DevBuf<Rec> dRecs(be, numRecs);
+            be->zero(dRecs.p, numRecs * sizeof(Rec));
             DevBuf<Ovf> dOvf(be, (size_t)std::max(cap, 1));
             DevBuf<int> dCount(be, 1);
             be->zero(dCount.p, sizeof(int));
@@ -688,7 +689,7 @@ void Engine::compute(Prepared* p) {
             kp.prefixLen = prefixLen;
             kp.rangeMode = rangeMode;
             be->launch_k1(kp, nwL);
-            outRecs.resize((size_t)g * chunks);
+            outRecs.resize(numRecs);
             dRecs.download(outRecs.data(), outRecs.size());
             stats.d2hBytes += (long long)outRecs.size() * (long long)sizeof(Rec);
             outOvf.clear();
@@ -797,15 +798,9 @@ void Engine::compute(Prepared* p) {
                 for (int i = 0; i < g; ++i) {
                     const int s = cand[i];
                     const int pair = list[s], m = p->qlen[pair], t = thr[i];
-                    long long total = 0;
-                    int first = 0x7fffffff, last = -1;
-                    for (int c = 0; c < chunksA; ++c) {
-                        const Rec& r = ra[(size_t)c * g + i];
-                        if (r.cnt <= 0) continue;
-                        total += r.cnt;
-                        first = std::min(first, r.pos[0]);
-                        last = std::max(last, r.last);
-                    }
+                    const Rec& r = ra[(size_t)i];
+                    const long long total = r.cnt;
+                    const int first = 0x7fffffff - r.pos[0], last = r.pos[1] - 1;
                     // An alignment with distance d <= t ending at column e passes, after its first P rows,
                     // through a column c' with prefix score <= d and e in [c'+(m-P)-d, c'+(m-P)+d].
                     const long long lo = (long long)first + (m - P) - t;

@@ -209,7 +209,7 @@ __global__ void k1_kernel(const K1Params p) {
         const int m = p.prefixLen > 0 ? p.prefixLen : p.qlen[pair];
         k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE, p.ncodes, p.eqtab);
         k1_init<NW>(st, m, p.kInit[slot]);
-        recIdx = chunk * p.numReads + slot;
+        recIdx = RANGE ? slot : chunk * p.numReads + slot;
         rec = p.recs + recIdx;
     }
 
@@ -232,7 +232,9 @@ __global__ void k1_kernel(const K1Params p) {
         }
         __syncthreads();  // everyone is done with tile i before its buffer is refilled
     }
-    if (active) {
+    if (active && RANGE) {
+        k1_range_commit<NW>(st, rec);
+    } else if (active) {
         if (MODE == MODE_NW) {
             st.best = st.score;
             st.cnt = 1;

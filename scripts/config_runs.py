@@ -83,7 +83,9 @@ def main():
     # ---- config 4: reads vs 5 Mbp target, HW, PATH (+ CIGAR on a sample) ---------------------------
     target, reads = workloads.reads_vs_target(args.reads4, 150, 5_000_000, seed=42)
     rl = [reads[i] for i in range(args.reads4)]
-    res, dt, st = batch_call(lib, rl, [target] * args.reads4, -1, 2, 2)
+    res, dt_first, st = batch_call(lib, rl, [target] * args.reads4, -1, 2, 2)  # first call at this size
+    L.edlibB200FreeResults(res, args.reads4)
+    res, dt, st = batch_call(lib, rl, [target] * args.reads4, -1, 2, 2)        # steady state
     cells = float(args.reads4) * 150 * 5_000_000
     bad = 0
     tb = target.tobytes()
@@ -96,7 +98,7 @@ def main():
         p = lib._cigar(res[i].alignment, res[i].alignmentLength, 1)
         lib._libc.free(p)
     cig_dt = time.perf_counter() - t0
-    out["config4"] = {"reads": args.reads4, "e2e_s": dt, "aln_per_s": args.reads4 / dt, "gcups_e2e": cells / dt / 1e9,
+    out["config4"] = {"reads": args.reads4, "e2e_first_call_s": dt_first, "e2e_s": dt, "aln_per_s": args.reads4 / dt, "gcups_e2e": cells / dt / 1e9,
                       "kernel_ms": st.kernelMs, "k1_ms": st.k1Ms, "launches": st.launches, "mean_alignment_len": float(alen),
                       "cigar_us_each": 1e6 * cig_dt / ncig, "spot_mismatches": bad}
     L.edlibB200FreeResults(res, args.reads4)
