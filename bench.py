@@ -102,6 +102,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(n_reads):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (same batch size only)."""
+    path = os.path.join(REPO, "profiles", "k1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if int(t["reads"]) == int(n_reads):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -355,7 +368,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k1_kernel (all launches of a step: 64-row prefix sweep k1_kernel<2,HW,range> + full-width "
+                         "traffic": measured_traffic(n_reads), "peak_source": peak_src, "kernel": "k1_kernel (all launches of a step: 64-row prefix sweep k1_kernel<2,HW,range> + full-width "
                                    "k1_kernel<5,HW> over the undecided reads)", "kernel_ms": k1 * 1000.0,
                          "bytes_algorithmic": bytes_alg, "int_lane_ops_per_s": lane_ops / k1,
                          "note": "integer-issue bound (see DESIGN.md): HBM fraction is low by construction"},
