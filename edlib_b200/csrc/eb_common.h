@@ -92,6 +92,26 @@ struct K1WParams {
     Rec* recs;               // [numReads]; positions are absolute target columns
 };
 
+// L: lane-per-alignment sweep of a short query over its own target (any mode).
+struct LJob {
+    uint64_t qOff;     // into qcodes (read backwards from qOff+m-1 when the launch is reversed)
+    uint64_t tOff;     // into tcodes: first symbol read (reversed launches walk down from it)
+    uint64_t matOff;   // into mat (U2 entries, [column][NW]) for storing launches
+    int m, n;
+    int kInit;         // HW/SHW: initial best sentinel
+    int trackFrom;     // HW: first column whose score may be recorded
+};
+struct LParams {
+    const LJob* jobs;
+    int numJobs;
+    const uint8_t* qcodes;
+    const uint8_t* tcodes;
+    int ncodes;
+    const uint8_t* eqtab;
+    Rec* recs;         // [numJobs]
+    U2* mat;
+};
+
 // ---------------------------------------------------------------------------------------------
 // W: warp-per-alignment sweep (any query length, any alphabet, per-job target window).
 // ---------------------------------------------------------------------------------------------
@@ -148,7 +168,8 @@ struct PeqParams {
 // Traceback over a stored matrix (one thread per job).
 struct TbJob {
     uint64_t matOff;   // U2 entries, [column][nWp]
-    uint64_t peqOff;   // Peq of the (forward) query
+    uint64_t qOff;     // query codes (used when peqOff == ~0)
+    uint64_t peqOff;   // Peq of the (forward) query, or ~0: compare symbols directly
     uint64_t tOff;     // target window start in tcodes
     uint64_t outOff;   // into ops: m+n bytes reserved; ops are written back-to-front
     int m, n, nWp;
@@ -160,6 +181,9 @@ struct TbParams {
     const U2* mat;
     const uint32_t* peq;
     const uint8_t* tcodes;
+    const uint8_t* qcodes;
+    const uint8_t* eqtab;
+    int ncodes;
     uint8_t* ops;
     int* opsStart;     // [job] index of the first op inside the job's reserved area
     int* opsLen;       // [job]

@@ -166,7 +166,7 @@ EB_HD uint32_t init_pv_word(int wordIdx, int off) {
 // the idle FMA pipe is slower because the high-half multiply is quarter-rate on B200, and an
 // add-with-carry chain needs as many ALU instructions as the funnel shifts; profiles/README.md.)
 template <int NW, bool TOP_ONE>
-EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score) {
+EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score, uint32_t* phOut = nullptr) {
     uint32_t T[NW], S[NW], Ph[NW], Mh[NW];
     EB_UNROLL
     for (int w = 0; w < NW; ++w) T[w] = Eq[w] & Pv[w];
@@ -179,6 +179,10 @@ EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[
     }
     // the last query row is bit 31 of the last word (top padding, see eb_common.h)
     score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
+    if (phOut) {  // matrix-storing sweeps keep the unshifted horizontal +1 deltas for the traceback
+        EB_UNROLL
+        for (int w = 0; w < NW; ++w) phOut[w] = Ph[w];
+    }
     EB_UNROLL
     for (int w = NW - 1; w >= 0; --w) {
         const uint32_t Phs = w ? funnel_l1(Ph[w - 1 < 0 ? 0 : w - 1], Ph[w]) : ((Ph[0] << 1) | (TOP_ONE ? 1u : 0u));
@@ -244,9 +248,12 @@ EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx
 // target).  The device kernel substitutes a reader over its shared-memory tile.
 struct PtrSyms {
     const uint8_t* p;
-    EB_HD bool aligned4(int i) const { return (((uintptr_t)(p + i)) & 3u) == 0; }
     EB_HD uint32_t read1(int i) const { return p[i]; }
-    EB_HD uint32_t read4(int i) const { return *reinterpret_cast<const uint32_t*>(p + i); }
+};
+// The same, walking the target backwards from p (reversed sweeps of ref cpp:253-257).
+struct RevSyms {
+    const uint8_t* p;
+    EB_HD uint32_t read1(int i) const { return *(p - i); }
 };
 
 // Sweeps `count` consecutive target symbols starting at absolute column cAbs.  `Acc` hands out
@@ -258,13 +265,6 @@ template <int NW, bool TOP_ONE, bool TRACK, bool RANGE = false, class Acc, class
 EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int count, int cAbs,
                       Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     int i = 0;
-    while (i < count && !syms.aligned4(i)) {  // head: until the symbols are 4-byte aligned
-        uint32_t Eq[NW];
-        acc.load(syms.read1(i), Eq);
-        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
-        if (TRACK && st.score <= st.best) k1_event<NW, RANGE>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
-        ++i;
-    }
     for (; i + 4 <= count; i += 4) {  // body: groups of four columns (byte reads: LSU, not ALU, work)
         int sc[4];
         EB_UNROLL
@@ -296,7 +296,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
 // Query profile for one K1 thread (ref buildPeq cpp:358-384 with top padding instead of the
 // bottom wildcard rows).  `Acc::store(code, w, bits)` writes one Eq word.
 template <int NW, class Acc>
-EB_HD void k1_build_peq(Acc& acc, const uint8_t* q, int m, int mode, int ncodes, const uint8_t* eqtab) {
+EB_HD void k1_build_peq(Acc& acc, const uint8_t* q, int m, int mode, int ncodes, const uint8_t* eqtab, bool rev = false) {
     const int off = 32 * NW - m;
     const uint32_t padBit = (mode == MODE_HW) ? 1u : 0u;
     for (int code = 0; code < ncodes; ++code) {
@@ -308,7 +308,7 @@ EB_HD void k1_build_peq(Acc& acc, const uint8_t* q, int m, int mode, int ncodes,
                 if (g < off) {
                     bit = padBit;
                 } else {
-                    const int qc = q[g - off];
+                    const int qc = rev ? q[m - 1 - (g - off)] : q[g - off];
                     bit = eqtab ? (eqtab[qc * ncodes + code] ? 1u : 0u) : (qc == code ? 1u : 0u);
                 }
                 bits |= bit << b;
@@ -395,6 +395,58 @@ EB_HD void k1w_thread(const K1WParams& p, int slot, Acc& acc) {
     const int ws = p.winStart[slot], tf = p.trackFrom[slot], len = p.winLen[slot];
     k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + ws}, tf, ws, rec, slot, nullptr, nullptr, 0);
     k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
+    rec->best = st.best;
+    rec->cnt = st.cnt;
+}
+
+// =============================================================================================
+// L -- one alignment per thread with its OWN target (per-pair targets, start-location sweeps,
+// matrix-storing sweeps of short queries).  Same per-thread sweep as K1; symbols come straight from
+// global memory, forward or reversed.  One launch = one (word class, mode, direction, store) class.
+// =============================================================================================
+template <int NW, int MODE, bool REV, bool STORE, class Acc>
+EB_HD void lane_job(const LParams& p, int jobIdx, Acc& acc) {
+    const LJob J = p.jobs[jobIdx];
+    Rec* rec = p.recs + jobIdx;
+    k1_build_peq<NW>(acc, p.qcodes + J.qOff, J.m, MODE, p.ncodes, p.eqtab, REV);
+    K1State<NW> st;
+    k1_init<NW>(st, J.m, J.kInit);
+    const uint8_t* t = p.tcodes + J.tOff;
+    if (STORE) {
+        U2* mat = p.mat + J.matOff;
+        for (int c = 0; c < J.n; ++c) {
+            uint32_t Eq[NW], Ph[NW];
+            acc.load(t[c], Eq);
+            k1_step<NW, true>(st.Pv, st.Mv, Eq, st.score, Ph);
+            EB_UNROLL
+            for (int w = 0; w < NW; ++w) {
+                U2 e;
+                e.x = st.Pv[w];
+                e.y = Ph[w];
+                mat[(size_t)c * NW + w] = e;
+            }
+        }
+    } else if (REV) {
+        if (MODE == MODE_HW) {
+            k1_columns<NW, false, false>(st, acc, RevSyms{t}, J.trackFrom, 0, rec, jobIdx, nullptr, nullptr, 0);
+            k1_columns<NW, false, true>(st, acc, RevSyms{t - J.trackFrom}, J.n - J.trackFrom, J.trackFrom, rec, jobIdx, nullptr, nullptr, 0);
+        } else {
+            k1_columns<NW, true, MODE == MODE_SHW>(st, acc, RevSyms{t}, J.n, 0, rec, jobIdx, nullptr, nullptr, 0);
+        }
+    } else {
+        if (MODE == MODE_HW) {
+            k1_columns<NW, false, false>(st, acc, PtrSyms{t}, J.trackFrom, 0, rec, jobIdx, nullptr, nullptr, 0);
+            k1_columns<NW, false, true>(st, acc, PtrSyms{t + J.trackFrom}, J.n - J.trackFrom, J.trackFrom, rec, jobIdx, nullptr, nullptr, 0);
+        } else {
+            k1_columns<NW, true, MODE == MODE_SHW>(st, acc, PtrSyms{t}, J.n, 0, rec, jobIdx, nullptr, nullptr, 0);
+        }
+    }
+    if (MODE == MODE_NW) {  // the bottom-right cell (ref cpp:916)
+        st.best = st.score;
+        st.cnt = 1;
+        rec->last = J.n - 1;
+        rec->pos[0] = J.n - 1;
+    }
     rec->best = st.best;
     rec->cnt = st.cnt;
 }
@@ -667,7 +719,7 @@ EB_HD void peq_build_words(const PeqParams& p, int jobIdx, int firstWord, int wo
 EB_HD void traceback_job(const TbParams& p, int jobIdx) {
     const TbJob J = p.jobs[jobIdx];
     const U2* mat = p.mat + J.matOff;
-    const uint32_t* peq = p.peq + J.peqOff;
+    const uint32_t* peq = p.peq + (J.peqOff != ~0ull ? J.peqOff : 0);
     const uint8_t* t = p.tcodes + J.tOff;
     uint8_t* ops = p.ops + J.outOff;
     const int off = 32 * J.nWp - J.m;
@@ -690,7 +742,13 @@ EB_HD void traceback_job(const TbParams& p, int jobIdx) {
                 break;
             }
         } else {
-            const uint32_t eq = peq[(size_t)t[c] * J.nWp + (g >> 5)] & bit;
+            uint32_t eq;
+            if (J.peqOff != ~0ull) {
+                eq = peq[(size_t)t[c] * J.nWp + (g >> 5)] & bit;
+            } else {  // lane sweeps keep no Peq in global memory: compare the symbols directly
+                const int qc = p.qcodes[J.qOff + (uint64_t)r];
+                eq = p.eqtab ? p.eqtab[qc * p.ncodes + t[c]] : (uint32_t)(qc == t[c]);
+            }
             ops[--w] = eq ? 0 : 3;
             --r;
             --c;

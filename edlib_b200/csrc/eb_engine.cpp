@@ -388,9 +388,35 @@ struct WRunner {
         return b;
     }
 
+    // Tasks whose query fits 256 rows and whose shape one of the lane-kernel classes covers run one
+    // alignment per THREAD (lane_kernel); everything else one alignment per warp (w_kernel).
+    static int lane_class(const WTask& t) {  // -1: not a lane task
+        if (t.m > 256 || (t.flags & (WF_SLIDE | WF_STOPCOL))) return -1;
+        const bool qrev = (t.flags & WF_QREV) != 0, trev = (t.flags & WF_TREV) != 0;
+        if (t.flags & WF_STORE) return (t.mode == MODE_NW && !qrev && !trev) ? 4 : -1;
+        if (qrev != trev) return -1;
+        if (qrev) return t.mode == MODE_SHW ? 3 : -1;
+        return t.mode;  // 0 NW, 1 SHW, 2 HW, forward
+    }
+
     void run(std::vector<WTask>& tasks) {
-        std::vector<int> order(tasks.size());
-        for (size_t i = 0; i < tasks.size(); ++i) order[i] = (int)i;
+        std::vector<int> warp;
+        std::map<std::pair<int, int>, std::vector<int>> lanes;  // (word class, lane class) -> tasks
+        for (size_t i = 0; i < tasks.size(); ++i) {
+            const int lc = lane_class(tasks[i]);
+            if (lc < 0) warp.push_back((int)i);
+            else lanes[std::make_pair(ceil_div(tasks[i].m, 32), lc)].push_back((int)i);
+        }
+        for (auto& kv : lanes) {
+            int bt = 0, rc = 0;
+            be->k1_shape(kv.first.first, p->ncodes, &bt, &rc);
+            if (rc <= 0 || (int)kv.second.size() < 8) {  // alphabet too large for per-thread Peq rows / too few to bother
+                warp.insert(warp.end(), kv.second.begin(), kv.second.end());
+                continue;
+            }
+            run_lane(tasks, kv.second, kv.first.first, kv.first.second, warp);
+        }
+        std::vector<int>& order = warp;
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tasks[a].R < tasks[b].R; });
         size_t i = 0;
         while (i < order.size()) {
@@ -404,6 +430,99 @@ struct WRunner {
             }
             std::vector<int> slice(order.begin() + i, order.begin() + j);
             run_slice(tasks, slice, R, 0);
+            i = j;
+        }
+    }
+
+    // One class of lane tasks, in memory-bounded slices.  Tasks that need a longer end-location list
+    // than a record holds are handed to the warp kernel (`spill`), which owns the list machinery.
+    void run_lane(std::vector<WTask>& tasks, const std::vector<int>& idx, int nw, int lc, std::vector<int>& spill) {
+        const bool store = lc == 4, rev = lc == 3;
+        const int mode = store ? MODE_NW : rev ? MODE_SHW : lc;
+        size_t i = 0;
+        while (i < idx.size()) {
+            size_t bytes = 0, j = i;
+            while (j < idx.size()) {
+                const WTask& t = tasks[idx[j]];
+                const size_t tb = sizeof(LJob) + sizeof(Rec) + (store ? (size_t)t.n * nw * 8 + (size_t)t.m + t.n + 64 : 0);
+                if (j > i && bytes + tb > eng->tun.sliceBytes) break;
+                bytes += tb;
+                ++j;
+            }
+            const int J = (int)(j - i);
+            std::vector<LJob> jobs(J);
+            std::vector<TbJob> tb;
+            uint64_t matEntries = 0, opsBytes = 0;
+            for (int s = 0; s < J; ++s) {
+                const WTask& t = tasks[idx[i + s]];
+                LJob& lj = jobs[s];
+                memset(&lj, 0, sizeof(lj));
+                lj.qOff = t.qOff;
+                lj.tOff = t.tOff;
+                lj.m = t.m;
+                lj.n = t.n;
+                lj.kInit = t.kInit;
+                lj.trackFrom = t.trackFrom;
+                if (store) {
+                    lj.matOff = matEntries;
+                    TbJob b;
+                    memset(&b, 0, sizeof(b));
+                    b.matOff = matEntries;
+                    b.qOff = t.qOff;
+                    b.peqOff = ~0ull;
+                    b.tOff = t.tOff;
+                    b.outOff = opsBytes;
+                    b.m = t.m;
+                    b.n = t.n;
+                    b.nWp = nw;
+                    tb.push_back(b);
+                    matEntries += (uint64_t)t.n * nw;
+                    opsBytes += (uint64_t)t.m + t.n;
+                }
+            }
+            DevBuf<LJob> dJobs(be, J);
+            dJobs.upload(jobs.data(), J);
+            DevBuf<Rec> dRecs(be, J);
+            be->zero(dRecs.p, (size_t)J * sizeof(Rec));
+            DevBuf<U2> dMat(be, matEntries);
+            LParams lp{dJobs.p, J, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p};
+            be->launch_lane(lp, nw, mode, rev, store);
+            DevBuf<TbJob> dTb;
+            DevBuf<uint8_t> dOps;
+            DevBuf<int> dOpsStart, dOpsLen;
+            if (store) {
+                dTb.alloc(be, tb.size());
+                dTb.upload(tb.data(), tb.size());
+                dOps.alloc(be, opsBytes);
+                dOpsStart.alloc(be, tb.size());
+                dOpsLen.alloc(be, tb.size());
+                TbParams tp{dTb.p, (int)tb.size(), dMat.p, nullptr, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
+                            dOps.p, dOpsStart.p, dOpsLen.p};
+                be->launch_traceback(tp);
+            }
+            std::vector<Rec> recs(J);
+            dRecs.download(recs.data(), J);
+            eng->stats.d2hBytes += (long long)J * (long long)sizeof(Rec);
+            for (int s = 0; s < J; ++s) {
+                WTask& t = tasks[idx[i + s]];
+                t.rec = recs[s];
+                t.extra.clear();
+                if (t.wantPositions && t.rec.cnt > KPOS) spill.push_back(idx[i + s]);
+            }
+            if (store) {
+                std::vector<int> st(tb.size()), ln(tb.size());
+                dOpsStart.download(st.data(), tb.size());
+                dOpsLen.download(ln.data(), tb.size());
+                std::vector<uint8_t> ops(opsBytes);
+                dOps.download(ops.data(), opsBytes);
+                eng->stats.d2hBytes += (long long)opsBytes + 8LL * (long long)tb.size();
+                for (int s = 0; s < J; ++s) {
+                    WTask& t = tasks[idx[i + s]];
+                    t.opsOff = (long long)opsPool->size();
+                    t.opsLen = ln[s];
+                    opsPool->insert(opsPool->end(), ops.begin() + tb[s].outOff + st[s], ops.begin() + tb[s].outOff + st[s] + ln[s]);
+                }
+            }
             i = j;
         }
     }
@@ -439,6 +558,7 @@ struct WRunner {
                 TbJob b;
                 memset(&b, 0, sizeof(b));
                 b.matOff = matEntries;
+                b.qOff = t.qOff;
                 b.peqOff = j.peqOff;
                 b.tOff = t.tOff;
                 b.outOff = opsBytes;
@@ -487,7 +607,8 @@ struct WRunner {
             dOps.alloc(be, opsBytes);
             dOpsStart.alloc(be, tb.size());
             dOpsLen.alloc(be, tb.size());
-            TbParams tp{dTb.p, (int)tb.size(), dMat.p, dPeq.p, p->dSeq.p, dOps.p, dOpsStart.p, dOpsLen.p};
+            TbParams tp{dTb.p, (int)tb.size(), dMat.p, dPeq.p, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
+                        dOps.p, dOpsStart.p, dOpsLen.p};
             be->launch_traceback(tp);
         }
 

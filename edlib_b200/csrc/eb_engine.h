@@ -35,6 +35,8 @@ struct Backend {
     virtual void launch_encode(const EncodeParams& p) = 0;
     virtual void launch_k1(const K1Params& p, int nw32) = 0;
     virtual void launch_k1w(const K1WParams& p, int nw32) = 0;
+    // lane-per-alignment sweeps with per-job targets; one launch = one class (mode / reversed / storing)
+    virtual void launch_lane(const LParams& p, int nw32, int mode, bool reversed, bool store) = 0;
     virtual void launch_peq(const PeqParams& p) = 0;
     virtual void launch_w(const WParams& p, int R) = 0;
     virtual void launch_traceback(const TbParams& p) = 0;

@@ -122,15 +122,9 @@ struct SmemPeqAcc {
 // Target symbols of the current tile, read as warp-uniform (broadcast) shared loads.
 struct SmemSyms {
     uint32_t addr;  // shared address of the first symbol
-    EB_D bool aligned4(int i) const { return ((addr + (uint32_t)i) & 3u) == 0; }
     EB_D uint32_t read1(int i) const {
         uint32_t v;
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr + (uint32_t)i));
-        return v;
-    }
-    EB_D uint32_t read4(int i) const {
-        uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr + (uint32_t)i));
         return v;
     }
 };
@@ -258,6 +252,19 @@ __global__ void k1w_kernel(const K1WParams p) {
     acc.a0 = smem_u32(smem) + 16u * threadIdx.x;
     acc.b0 = smem_u32(smem) + 16u * blockDim.x + 4u * SmemPeqAcc<NW>::NWB * threadIdx.x;
     k1w_thread<NW>(p, slot, acc);
+}
+
+// L: one alignment per thread over its own target (eb_core.h: lane_job).
+template <int NW, int MODE, bool REV, bool STORE>
+__global__ void lane_kernel(const LParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int job = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= p.numJobs) return;
+    SmemPeqAcc<NW> acc;
+    acc.codeStride = (uint32_t)blockDim.x * (16u + 4u * SmemPeqAcc<NW>::NWB);
+    acc.a0 = smem_u32(smem) + 16u * threadIdx.x;
+    acc.b0 = smem_u32(smem) + 16u * blockDim.x + 4u * SmemPeqAcc<NW>::NWB * threadIdx.x;
+    lane_job<NW, MODE, REV, STORE>(p, job, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -579,6 +586,40 @@ struct CudaBackend : Backend {
             case 7: launch_k1w_t<7>(p); break;
             case 8: launch_k1w_t<8>(p); break;
             default: throw std::runtime_error("bad K1W word class");
+        }
+    }
+    template <int NW, int MODE, bool REV, bool STORE>
+    void launch_lane_c(const LParams& p) {
+        int block = 128;
+        const size_t perThread = (size_t)p.ncodes * (16 + 4 * (NW > 4 ? NW - 4 : 0));
+        while (block > 32 && perThread * block > 96 * 1024) block >>= 1;
+        const size_t smem = perThread * block;
+        if (smem > (size_t)maxSmemOptin) throw std::runtime_error("lane kernel: alphabet too large for shared memory");
+        EB_CUDA(cudaFuncSetAttribute(lane_kernel<NW, MODE, REV, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lane_kernel<NW, MODE, REV, STORE><<<(p.numJobs + block - 1) / block, block, smem, stream>>>(p);
+        check_launch("lane");
+    }
+    template <int NW>
+    void launch_lane_t(const LParams& p, int mode, bool rev, bool store) {
+        if (store) launch_lane_c<NW, MODE_NW, false, true>(p);
+        else if (rev && mode == MODE_SHW) launch_lane_c<NW, MODE_SHW, true, false>(p);
+        else if (!rev && mode == MODE_HW) launch_lane_c<NW, MODE_HW, false, false>(p);
+        else if (!rev && mode == MODE_SHW) launch_lane_c<NW, MODE_SHW, false, false>(p);
+        else if (!rev && mode == MODE_NW) launch_lane_c<NW, MODE_NW, false, false>(p);
+        else throw std::runtime_error("unsupported lane class");
+    }
+    void launch_lane(const LParams& p, int nw, int mode, bool rev, bool store) override {
+        Scope s(this, "lane");
+        switch (nw) {
+            case 1: launch_lane_t<1>(p, mode, rev, store); break;
+            case 2: launch_lane_t<2>(p, mode, rev, store); break;
+            case 3: launch_lane_t<3>(p, mode, rev, store); break;
+            case 4: launch_lane_t<4>(p, mode, rev, store); break;
+            case 5: launch_lane_t<5>(p, mode, rev, store); break;
+            case 6: launch_lane_t<6>(p, mode, rev, store); break;
+            case 7: launch_lane_t<7>(p, mode, rev, store); break;
+            case 8: launch_lane_t<8>(p, mode, rev, store); break;
+            default: throw std::runtime_error("bad lane word class");
         }
     }
     void launch_peq(const PeqParams& p) override {

@@ -138,6 +138,26 @@ def filter_cases(seed, count):
         yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 3, 10, 40]), mode=2, task=rng.randrange(3), eqs=None)
 
 
+def pairwise_cases(seed, count):
+    """Batches of short queries each with its OWN target (pairwise comparison shape): the lane-per-
+    alignment kernel with per-job targets, all modes and tasks, odd alphabets, equalities."""
+    rng = random.Random(seed)
+    for _ in range(count):
+        alpha = bytes(rng.sample(range(256), rng.choice([2, 4, 4, 20])))
+        qs, ts = [], []
+        for _ in range(rng.choice([10, 60, 150])):
+            t = rand_seq(rng, rng.randrange(1, 500), alpha)
+            if rng.random() < 0.6 and len(t) > 5:
+                a = rng.randrange(0, len(t) - 1)
+                q = mutate(rng, t[a:a + rng.randrange(1, 257)], rng.choice([0, 0.05, 0.3]), alpha)[:256]
+            else:
+                q = rand_seq(rng, rng.choice([0, 1, 33, 64, 100, 200, 256]), alpha)
+            qs.append(q)
+            ts.append(t)
+        eqs = [(bytes([alpha[0]]), bytes([alpha[1]]))] if rng.random() < 0.2 else None
+        yield dict(qs=qs, ts=ts, k=rng.choice([-1, -1, 2, 20]), mode=rng.randrange(3), task=rng.randrange(3), eqs=eqs)
+
+
 # Hand vectors with known answers from the reference's own tests (SURVEY.md section 8c):
 # bindings/python/test.py:6-73 and test/runTests.cpp:427-570, plus API probes measured on the
 # reference build.  (query, target, mode, task, k, equalities) -> expected fields.

@@ -59,6 +59,20 @@ void emul_k1w(const K1WParams& p) {
     for (int slot = 0; slot < p.numReads; ++slot) k1w_thread<NW>(p, slot, acc);
 }
 
+template <int NW>
+void emul_lane(const LParams& p, int mode, bool rev, bool store) {
+    HostPeqAcc<NW> acc;
+    acc.w.assign((size_t)p.ncodes * NW, 0);
+    for (int j = 0; j < p.numJobs; ++j) {
+        if (store) lane_job<NW, MODE_NW, false, true>(p, j, acc);
+        else if (rev && mode == MODE_SHW) lane_job<NW, MODE_SHW, true, false>(p, j, acc);
+        else if (!rev && mode == MODE_HW) lane_job<NW, MODE_HW, false, false>(p, j, acc);
+        else if (!rev && mode == MODE_SHW) lane_job<NW, MODE_SHW, false, false>(p, j, acc);
+        else if (!rev && mode == MODE_NW) lane_job<NW, MODE_NW, false, false>(p, j, acc);
+        else throw std::runtime_error("unsupported lane class");
+    }
+}
+
 struct EmulBackend : Backend {
     int launchesCount = 0;
     void* alloc(size_t bytes) override {
@@ -120,6 +134,20 @@ struct EmulBackend : Backend {
             case 7: emul_k1w<7>(p); break;
             case 8: emul_k1w<8>(p); break;
             default: throw std::runtime_error("bad K1W word class");
+        }
+    }
+    void launch_lane(const LParams& p, int nw, int mode, bool rev, bool store) override {
+        ++launchesCount;
+        switch (nw) {
+            case 1: emul_lane<1>(p, mode, rev, store); break;
+            case 2: emul_lane<2>(p, mode, rev, store); break;
+            case 3: emul_lane<3>(p, mode, rev, store); break;
+            case 4: emul_lane<4>(p, mode, rev, store); break;
+            case 5: emul_lane<5>(p, mode, rev, store); break;
+            case 6: emul_lane<6>(p, mode, rev, store); break;
+            case 7: emul_lane<7>(p, mode, rev, store); break;
+            case 8: emul_lane<8>(p, mode, rev, store); break;
+            default: throw std::runtime_error("bad lane word class");
         }
     }
     void launch_peq(const PeqParams& p) override {

@@ -36,6 +36,11 @@ def test_batches_shared_targets(emul):
     assert parity.run_batches(emul, 12, 30) > 1000
 
 
+def test_pairwise_batches_with_own_targets(emul):
+    import cases
+    assert parity.run_batches(emul, 17, 40, gen=cases.pairwise_cases) > 1500
+
+
 def test_long_queries(emul):
     import cases
     assert parity.run_single(emul, 13, 40, gen=cases.long_cases) == 40

@@ -31,6 +31,11 @@ def test_batches_shared_targets(lib):
     assert parity.run_batches(lib, 22, 40) > 1000
 
 
+def test_pairwise_batches_with_own_targets(lib):
+    import cases
+    assert parity.run_batches(lib, 17, 40, gen=cases.pairwise_cases) > 1500
+
+
 def test_long_queries(lib):
     assert parity.run_single(lib, 23, 40, gen=cases.long_cases) == 40
 
