@@ -472,7 +472,12 @@ struct InitSbFn {  // D at the bottom row of a chunk in column -1: rows above it
     }
 };
 
-template <class B, int R>
+// FEAT is a compile-time superset of what the job may need (WM_* bits): a feature whose bit is clear is
+// compiled out, so the per-column loop of the common job shapes carries no test for sliding, matrix
+// stores, stop columns, tracking or strip hand-over (w_dispatch picks the instantiation).
+enum WMask : int { WM_SLIDE = 1, WM_STORE = 2, WM_STOPCOL = 4, WM_TRACK = 8, WM_STRIPS = 16, WM_ALL = 31 };
+
+template <class B, int R, int FEAT = WM_ALL>
 EB_HD void w_sweep(const WParams& P, int jobIdx) {
     using U = typename B::U;
     using Pr = typename B::P;
@@ -480,11 +485,11 @@ EB_HD void w_sweep(const WParams& P, int jobIdx) {
     const int m = J.m, n = J.n, nWp = J.nWp;
     const int off = 32 * nWp - m;
     const int chunksTotal = nWp / R;
-    const bool slide = (J.flags & WF_SLIDE) != 0;
-    const bool store = (J.flags & WF_STORE) != 0;
-    const bool stopcol = (J.flags & WF_STOPCOL) != 0;
+    const bool slide = (FEAT & WM_SLIDE) && (J.flags & WF_SLIDE) != 0;
+    const bool store = (FEAT & WM_STORE) && (J.flags & WF_STORE) != 0;
+    const bool stopcol = (FEAT & WM_STOPCOL) && (J.flags & WF_STOPCOL) != 0;
     const bool trev = (J.flags & WF_TREV) != 0;
-    const int strips = slide ? 1 : (chunksTotal + 31) / 32;
+    const int strips = (slide || !(FEAT & WM_STRIPS)) ? 1 : (chunksTotal + 31) / 32;
     const uint8_t* tptr = P.tcodes + J.tOff;
     const uint32_t* peq = P.peq + J.peqOff;
     const U lane = B::lane();
@@ -498,7 +503,7 @@ EB_HD void w_sweep(const WParams& P, int jobIdx) {
     for (int strip = 0; strip < strips; ++strip) {
         int topChunk = strip * 32;
         const bool lastStrip = (strip == strips - 1);
-        const bool track = lastStrip && J.mode != MODE_NW && !stopcol;
+        const bool track = (FEAT & WM_TRACK) && lastStrip && J.mode != MODE_NW && !stopcol;
         const uint8_t* hin = nullptr;
         uint8_t* hout = nullptr;
         if (strips > 1) {
@@ -662,6 +667,24 @@ EB_HD void w_sweep(const WParams& P, int jobIdx) {
             }
         }
     }
+}
+
+// Picks the leanest instantiation that covers the job (all branches warp-uniform).
+template <class B, int R>
+EB_HD void w_dispatch(const WParams& P, int jobIdx) {
+    const int flags = P.jobs[jobIdx].flags, mode = P.jobs[jobIdx].mode;
+    const int nWp = P.jobs[jobIdx].nWp;
+    const bool slide = (flags & WF_SLIDE) != 0;
+    const bool strips = !slide && (nWp / R) > 32;
+    int need = (slide ? WM_SLIDE : 0) | ((flags & WF_STORE) ? WM_STORE : 0) | ((flags & WF_STOPCOL) ? WM_STOPCOL : 0) |
+               ((mode != MODE_NW && !(flags & WF_STOPCOL)) ? WM_TRACK : 0) | (strips ? WM_STRIPS : 0);
+    if (need == 0) w_sweep<B, R, 0>(P, jobIdx);                                         // NW, one fixed window
+    else if (need == WM_SLIDE) w_sweep<B, R, WM_SLIDE>(P, jobIdx);                      // banded NW
+    else if (need == WM_TRACK) w_sweep<B, R, WM_TRACK>(P, jobIdx);                      // HW / SHW, one window
+    else if (need == WM_STORE) w_sweep<B, R, WM_STORE>(P, jobIdx);                      // matrix-storing NW
+    else if (need == WM_STOPCOL) w_sweep<B, R, WM_STOPCOL>(P, jobIdx);                  // Hirschberg half, fixed
+    else if (need == (WM_STOPCOL | WM_SLIDE)) w_sweep<B, R, WM_STOPCOL | WM_SLIDE>(P, jobIdx);  // ... banded
+    else w_sweep<B, R, WM_ALL>(P, jobIdx);                                              // strips and mixtures
 }
 
 // Scalar helper used by both backends' dump_column: writes the scores of one lane's chunk.

@@ -276,7 +276,7 @@ template <int R>
 __global__ void __launch_bounds__(W_WARPS * 32) w_kernel(const WParams p) {
     const int job = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
     if (job >= p.numJobs) return;
-    w_sweep<DevWarp, R>(p, job);
+    w_dispatch<DevWarp, R>(p, job);
 }
 
 __global__ void peq_kernel(const PeqParams p) {

@@ -159,10 +159,10 @@ struct EmulBackend : Backend {
         ++launchesCount;
         for (int j = 0; j < p.numJobs; ++j) {
             switch (R) {
-                case 1: w_sweep<ebhost::HostWarp, 1>(p, j); break;
-                case 2: w_sweep<ebhost::HostWarp, 2>(p, j); break;
-                case 4: w_sweep<ebhost::HostWarp, 4>(p, j); break;
-                case 8: w_sweep<ebhost::HostWarp, 8>(p, j); break;
+                case 1: w_dispatch<ebhost::HostWarp, 1>(p, j); break;
+                case 2: w_dispatch<ebhost::HostWarp, 2>(p, j); break;
+                case 4: w_dispatch<ebhost::HostWarp, 4>(p, j); break;
+                case 8: w_dispatch<ebhost::HostWarp, 8>(p, j); break;
                 default: throw std::runtime_error("bad W chunk size");
             }
         }
