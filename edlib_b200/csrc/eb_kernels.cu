@@ -139,7 +139,9 @@ EB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 EB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
+    uint32_t spins = 0;
     do {
+        if (++spins > (1u << 22)) __trap();  // a copy that never lands must fail the launch, not hang the device
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
