@@ -677,66 +677,38 @@ struct WRunner {
 // ---------------------------------------------------------------------------------------------
 // compute
 // ---------------------------------------------------------------------------------------------
-void Engine::compute(Prepared* p) {
-    Backend* be = be_;
+// ---------------------------------------------------------------------------------------------
+// One compute() over a prepared batch: shared state + the phases of the reference driver
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Pass {
+    Engine& eng;
+    Backend* be;
+    Prepared* p;
+    EngineTunables& tun;
+    EngineStats& stats;
     Trace trace;
-    be->reset_timing();
-    const int N = p->N;
-    const int mode = p->mode;
-    const int k = p->cfg.k;
-    p->ed.assign(N, -1);
-    p->special.assign(N, 0);
-    p->endStart.assign(N, 0);
-    p->endCount.assign(N, 0);
-    p->endPool.clear();
-    p->startPool.clear();
-    p->alnStart.assign(N, -1);
-    p->alnLen.assign(N, 0);
-    p->alnPool.clear();
-    stats.k1Cells = stats.wCells = 0;
-    stats.filterDecided = stats.filterFallback = 0;
-
+    const int N, mode, k;
     // per-pair sweep outcome before the "-1" rule
-    std::vector<int> best(N, -1), cnt(N, 0);
-    std::vector<long long> posStart(N, -1);  // end columns of pair i: posPool[posStart[i] .. +posLen[i])
-    std::vector<int> posLen(N, 0);
-    std::vector<int> posPool;
-    posPool.reserve((size_t)N + 16);
+    std::vector<int> best, cnt;
+    std::vector<long long> posStart;  // end columns of pair i: posPool[posStart[i] .. +posLen[i])
+    std::vector<int> posLen, posPool;
+    std::vector<int> wPairs;          // pairs swept by the warp / lane-job kernels
+    std::vector<uint8_t> opsPool;
+    std::vector<int> colPool;
+    WRunner runner;
 
-    // ---- classification -----------------------------------------------------------------
-    std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, nw32) -> pairs
-    std::vector<int> wPairs;
-    for (int i = 0; i < N; ++i) {
-        const int m = p->qlen[i], n = p->tlen[i];
-        if (m == 0 || n == 0) {
-            p->special[i] = 1;
-            continue;
-        }
-        if (mode == MODE_NW && k >= 0 && k < abs(n - m)) continue;  // ref cpp:744
-        if (m <= 256)
-            groups[std::make_pair(p->tidx[i], ceil_div(m, 32))].push_back(i);
-        else
-            wPairs.push_back(i);
+    Pass(Engine& e, Backend* b, Prepared* pr)
+        : eng(e), be(b), p(pr), tun(e.tun), stats(e.stats), N(pr->N), mode(pr->mode), k(pr->cfg.k),
+          best(pr->N, -1), cnt(pr->N, 0), posStart(pr->N, -1), posLen(pr->N, 0),
+          runner{&e, b, pr, &opsPool, &colPool} {
+        posPool.reserve((size_t)N + 16);
     }
 
-    // ---- K1 groups ----------------------------------------------------------------------
-    for (auto& kv : groups) {
-        std::vector<int>& list = kv.second;
-        // Small groups go to the warp kernel, except HW over a long target: there the lane kernel
-        // can cut the target into chunks and spread even one alignment over many CTAs.
-        if ((int)list.size() < tun.k1MinGroup && !(mode == MODE_HW && p->tg[kv.first.first].len >= 8 * tun.k1MinChunk)) {
-            wPairs.insert(wPairs.end(), list.begin(), list.end());
-            continue;
-        }
-        const int t = kv.first.first, nw = kv.first.second;
-        {
-            int bt = 0, rc = 0;
-            be->k1_shape(nw, p->ncodes, &bt, &rc);
-            if (rc <= 0) {  // alphabet too large for per-thread Peq rows in shared memory
-                wPairs.insert(wPairs.end(), list.begin(), list.end());
-                continue;
-            }
-        }
+    // Distance pass of one group of pairs that share target `t` and word class `nw` (queries <= 256
+    // rows): candidate filter (HW), then the plain lane-per-alignment sweep of what is left.
+    void lane_group(int t, int nw, std::vector<int>& list) {
         const Target& tg = p->tg[t];
         const int G = (int)list.size();
         const int n = tg.len;
@@ -1032,293 +1004,364 @@ void Engine::compute(Prepared* p) {
         }
     }
 
-    trace.mark("compute: K1 groups done");
-    // ---- W distance pass ------------------------------------------------------------------
-    std::vector<uint8_t> opsPool;
-    std::vector<int> colPool;
-    WRunner runner{this, be, p, &opsPool, &colPool};
-    {
-        std::vector<int> pending = wPairs;
-        int kRound = 64;  // ref cpp:201: the doubling schedule only matters for speed
-        while (!pending.empty()) {
-            std::vector<WTask> tasks;
-            std::vector<int> later;
-            for (int pair : pending) {
-                const int m = p->qlen[pair], n = p->tlen[pair];
-                int bound = -1;
-                if (mode == MODE_NW) {
-                    if (k >= 0) {
-                        bound = k;
-                    } else if (ceil_div(m, 32) > 32) {
-                        bound = kRound;
-                        if (bound < abs(n - m)) {
-                            later.push_back(pair);
-                            continue;
+    // Distance pass of everything else: one alignment per warp (or per thread with its own target).
+    void warp_distance() {
+        // ---- W distance pass ------------------------------------------------------------------
+        {
+            std::vector<int> pending = wPairs;
+            int kRound = 64;  // ref cpp:201: the doubling schedule only matters for speed
+            while (!pending.empty()) {
+                std::vector<WTask> tasks;
+                std::vector<int> later;
+                for (int pair : pending) {
+                    const int m = p->qlen[pair], n = p->tlen[pair];
+                    int bound = -1;
+                    if (mode == MODE_NW) {
+                        if (k >= 0) {
+                            bound = k;
+                        } else if (ceil_div(m, 32) > 32) {
+                            bound = kRound;
+                            if (bound < abs(n - m)) {
+                                later.push_back(pair);
+                                continue;
+                            }
                         }
                     }
+                    WPlan pl = plan_w(m, n, mode, bound);
+                    WTask t;
+                    t.pair = pair;
+                    t.qOff = p->qoff[pair];
+                    t.tOff = p->tg[p->tidx[pair]].off;
+                    t.m = m;
+                    t.n = n;
+                    t.mode = mode;
+                    t.flags = pl.slide ? WF_SLIDE : 0;
+                    t.dhi = pl.dhi;
+                    t.R = pl.R;
+                    t.nWp = pl.nWp;
+                    t.kInit = ((k < 0 || k > m) ? m : k) + 1;
+                    t.tag = pl.slide ? bound : -1;  // a sliding result is only valid when <= bound
+                    t.wantPositions = (mode != MODE_NW);
+                    tasks.push_back(std::move(t));
                 }
-                WPlan pl = plan_w(m, n, mode, bound);
-                WTask t;
-                t.pair = pair;
-                t.qOff = p->qoff[pair];
-                t.tOff = p->tg[p->tidx[pair]].off;
-                t.m = m;
-                t.n = n;
-                t.mode = mode;
-                t.flags = pl.slide ? WF_SLIDE : 0;
-                t.dhi = pl.dhi;
-                t.R = pl.R;
-                t.nWp = pl.nWp;
-                t.kInit = ((k < 0 || k > m) ? m : k) + 1;
-                t.tag = pl.slide ? bound : -1;  // a sliding result is only valid when <= bound
-                t.wantPositions = (mode != MODE_NW);
-                tasks.push_back(std::move(t));
-            }
-            runner.run(tasks);
-            for (WTask& t : tasks) {
-                stats.wCells += (long long)t.m * t.n;
-                if (t.tag >= 0 && t.rec.best > t.tag) {  // outside the band of this round
-                    if (k < 0) later.push_back(t.pair);
-                    else best[t.pair] = 0x7fffffff;
-                    continue;
+                runner.run(tasks);
+                for (WTask& t : tasks) {
+                    stats.wCells += (long long)t.m * t.n;
+                    if (t.tag >= 0 && t.rec.best > t.tag) {  // outside the band of this round
+                        if (k < 0) later.push_back(t.pair);
+                        else best[t.pair] = 0x7fffffff;
+                        continue;
+                    }
+                    best[t.pair] = t.rec.cnt > 0 ? t.rec.best : 0x7fffffff;
+                    cnt[t.pair] = t.rec.cnt;
+                    posStart[t.pair] = (long long)posPool.size();
+                    for (int q = 0; q < std::min(t.rec.cnt, KPOS); ++q) posPool.push_back(t.rec.pos[q]);
+                    posPool.insert(posPool.end(), t.extra.begin(), t.extra.end());
+                    posLen[t.pair] = (int)((long long)posPool.size() - posStart[t.pair]);
                 }
-                best[t.pair] = t.rec.cnt > 0 ? t.rec.best : 0x7fffffff;
-                cnt[t.pair] = t.rec.cnt;
-                posStart[t.pair] = (long long)posPool.size();
-                for (int q = 0; q < std::min(t.rec.cnt, KPOS); ++q) posPool.push_back(t.rec.pos[q]);
-                posPool.insert(posPool.end(), t.extra.begin(), t.extra.end());
-                posLen[t.pair] = (int)((long long)posPool.size() - posStart[t.pair]);
+                pending.swap(later);
+                if (kRound < (1 << 29)) kRound *= 2;
             }
-            pending.swap(later);
-            if (kRound < (1 << 29)) kRound *= 2;
         }
     }
 
-    trace.mark("compute: W distance pass");
-    // ---- distances and end locations ------------------------------------------------------
-    for (int i = 0; i < N; ++i) {
-        if (p->special[i]) continue;
-        const int m = p->qlen[i], n = p->tlen[i];
-        p->endStart[i] = (long long)p->endPool.size();
-        if (best[i] < 0 || best[i] == 0x7fffffff) continue;  // rejected up front or nothing tracked
-        if (k >= 0 && best[i] > k) continue;
-        if (mode == MODE_NW) {
+    // editDistance and endLocations per pair from the sweep outcomes (ref cpp:219-225 and the -1 rule).
+    void collect_ends() {
+        // ---- distances and end locations ------------------------------------------------------
+        for (int i = 0; i < N; ++i) {
+            if (p->special[i]) continue;
+            const int m = p->qlen[i], n = p->tlen[i];
+            p->endStart[i] = (long long)p->endPool.size();
+            if (best[i] < 0 || best[i] == 0x7fffffff) continue;  // rejected up front or nothing tracked
+            if (k >= 0 && best[i] > k) continue;
+            if (mode == MODE_NW) {
+                p->ed[i] = best[i];
+                p->endPool.push_back(n - 1);  // ref cpp:221-225
+                p->endCount[i] = 1;
+                continue;
+            }
+            if (best[i] > m) continue;
             p->ed[i] = best[i];
-            p->endPool.push_back(n - 1);  // ref cpp:221-225
-            p->endCount[i] = 1;
-            continue;
+            // ref cpp:670, 681-693: the padded bottom cell of column W-1 shows up as end location -1
+            const int W64 = ceil_div(m, 64) * 64 - m;
+            if (best[i] == m && W64 > 0) p->endPool.push_back(-1);
+            if (posLen[i] != cnt[i]) throw std::runtime_error("internal: end-location count mismatch");
+            p->endPool.insert(p->endPool.end(), posPool.begin() + posStart[i], posPool.begin() + posStart[i] + posLen[i]);
+            p->endCount[i] = (int)(p->endPool.size() - (size_t)p->endStart[i]);
         }
-        if (best[i] > m) continue;
-        p->ed[i] = best[i];
-        // ref cpp:670, 681-693: the padded bottom cell of column W-1 shows up as end location -1
-        const int W64 = ceil_div(m, 64) * 64 - m;
-        if (best[i] == m && W64 > 0) p->endPool.push_back(-1);
-        if (posLen[i] != cnt[i]) throw std::runtime_error("internal: end-location count mismatch");
-        p->endPool.insert(p->endPool.end(), posPool.begin() + posStart[i], posPool.begin() + posStart[i] + posLen[i]);
-        p->endCount[i] = (int)(p->endPool.size() - (size_t)p->endStart[i]);
     }
 
-    trace.mark("compute: end locations");
-    // ---- start locations (ref cpp:228-272) ------------------------------------------------
-    const bool wantLoc = p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH;
-    if (wantLoc) {
-        p->startPool.assign(p->endPool.size(), 0);
-        if (mode == MODE_HW) {
-            std::vector<WTask> tasks;
-            std::vector<long long> slotOf;
+    void start_locations() {
+        // ---- start locations (ref cpp:228-272) ------------------------------------------------
+        const bool wantLoc = p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH;
+        if (wantLoc) {
+            p->startPool.assign(p->endPool.size(), 0);
+            if (mode == MODE_HW) {
+                std::vector<WTask> tasks;
+                std::vector<long long> slotOf;
+                for (int i = 0; i < N; ++i) {
+                    if (p->ed[i] < 0) continue;
+                    const int m = p->qlen[i];
+                    for (int q = 0; q < p->endCount[i]; ++q) {
+                        const long long slot = p->endStart[i] + q;
+                        const int e = p->endPool[(size_t)slot];
+                        if (e < 0) continue;  // ref cpp:237-249: start 0
+                        WTask t;
+                        t.pair = i;
+                        t.qOff = p->qoff[i];
+                        t.tOff = p->tg[p->tidx[i]].off + (uint64_t)e;  // first symbol read, walking backward
+                        t.m = m;
+                        t.n = (int)std::min<long long>((long long)e + 1, (long long)m + p->ed[i]);
+                        t.mode = MODE_SHW;
+                        t.flags = WF_QREV | WF_TREV;
+                        t.kInit = p->ed[i] + 1;
+                        WPlan pl = plan_w(t.m, t.n, MODE_SHW, -1);
+                        t.R = pl.R;
+                        t.nWp = pl.nWp;
+                        tasks.push_back(std::move(t));
+                        slotOf.push_back(slot);
+                    }
+                }
+                runner.run(tasks);
+                for (size_t j = 0; j < tasks.size(); ++j) {
+                    const WTask& t = tasks[j];
+                    if (t.rec.cnt <= 0 || t.rec.best != p->ed[t.pair]) throw std::runtime_error("internal: start-location sweep disagrees");
+                    const int e = p->endPool[(size_t)slotOf[j]];
+                    p->startPool[(size_t)slotOf[j]] = e - t.rec.last;  // ref cpp:260
+                }
+            }
+        }
+    }
+
+    void paths() {
+        // ---- alignment path (ref cpp:276-289, 1161-1213, 1231-1396) ---------------------------
+        // obtainAlignment as a level-synchronous tree: a node is an NW sub-problem (query slice,
+        // target slice, known score).  Inside the reference's 1 MiB rule (cpp:1188-1190) it is a
+        // leaf: matrix-storing sweep + traceback kernel.  Otherwise it is split like
+        // obtainAlignmentHirschberg: the score column left of the target's middle from a forward
+        // sweep and the one right of it from a reversed sweep (both on the device, cpp:1252-1260),
+        // the split row chosen by the reference's candidate order (cpp:1321-1353), both halves
+        // becoming nodes of the next level (cpp:1372-1380).  All nodes of a level run in one batch.
+        if (p->cfg.task == EDLIB_TASK_PATH) {
+            struct Node {
+                int pair;
+                uint64_t qOff, tOff;
+                int m, n, best;
+                int left = -1, right = -1;
+                long long opsOff = -1;  // into opsPool (leaf) ...
+                int opsLen = 0;
+                int fillOp = -1;        // ... or a run of one op (empty side, cpp:1168-1175)
+            };
+            std::vector<Node> nodes;
+            std::vector<int> rootOf(N, -1), frontier, leaves;
             for (int i = 0; i < N; ++i) {
                 if (p->ed[i] < 0) continue;
-                const int m = p->qlen[i];
-                for (int q = 0; q < p->endCount[i]; ++q) {
-                    const long long slot = p->endStart[i] + q;
-                    const int e = p->endPool[(size_t)slot];
-                    if (e < 0) continue;  // ref cpp:237-249: start 0
+                const int s0 = p->startPool[(size_t)p->endStart[i]], e0 = p->endPool[(size_t)p->endStart[i]];
+                Node nd;
+                nd.pair = i;
+                nd.qOff = p->qoff[i];
+                nd.tOff = p->tg[p->tidx[i]].off + (uint64_t)s0;
+                nd.m = p->qlen[i];
+                nd.n = e0 - s0 + 1;
+                nd.best = p->ed[i];
+                rootOf[i] = (int)nodes.size();
+                frontier.push_back((int)nodes.size());
+                nodes.push_back(nd);
+            }
+            while (!frontier.empty()) {
+                std::vector<int> split;
+                for (int id : frontier) {
+                    Node& nd = nodes[id];
+                    if (nd.m == 0 || nd.n <= 0) {
+                        nd.fillOp = (nd.m == 0) ? EDLIB_EDOP_DELETE : EDLIB_EDOP_INSERT;
+                        nd.opsLen = nd.m + std::max(nd.n, 0);
+                        continue;
+                    }
+                    const long long matrixBytes = 20LL * ceil_div(nd.m, 64) * nd.n + 8LL * nd.n;  // cpp:1188-1190
+                    if (matrixBytes < 1024 * 1024) leaves.push_back(id);
+                    else split.push_back(id);
+                }
+                frontier.clear();
+                if (split.empty()) break;
+                std::vector<WTask> tasks;
+                tasks.reserve(split.size() * 2);
+                for (int id : split) {
+                    const Node& nd = nodes[id];
+                    const int leftW = nd.n / 2, rightW = nd.n - leftW;  // cpp:1247-1248
+                    const WPlan pl = plan_w(nd.m, nd.n, MODE_NW, nd.best);  // band of the WHOLE node
+                    WTask f;
+                    f.pair = id;
+                    f.qOff = nd.qOff;
+                    f.tOff = nd.tOff;
+                    f.m = nd.m;
+                    f.n = leftW;
+                    f.mode = MODE_NW;
+                    f.flags = WF_STOPCOL | (pl.slide ? WF_SLIDE : 0);
+                    f.dhi = pl.dhi;
+                    f.stopCol = leftW - 1;
+                    f.R = pl.R;
+                    f.nWp = pl.nWp;
+                    WTask r = f;
+                    r.tOff = nd.tOff + (uint64_t)nd.n - 1;  // reversed: first symbol read is the last one
+                    r.n = rightW;
+                    r.flags |= WF_QREV | WF_TREV;
+                    r.stopCol = rightW - 1;
+                    tasks.push_back(std::move(f));
+                    tasks.push_back(std::move(r));
+                }
+                runner.run(tasks);
+                for (size_t s = 0; s < split.size(); ++s) {
+                    const int id = split[s];
+                    const Node nd = nodes[id];
+                    const int leftW = nd.n / 2, rightW = nd.n - leftW;
+                    const int* colF = colPool.data() + tasks[2 * s].colOff;      // D_fwd[r][leftW-1]
+                    const int* colR = colPool.data() + tasks[2 * s + 1].colOff;  // D_rev[r'][rightW-1]
+                    auto L = [&](int h) { return h == 0 ? leftW : colF[h - 1]; };       // q[0..h) vs left half
+                    auto Rr = [&](int sfx) { return sfx == 0 ? rightW : colR[sfx - 1]; };  // suffix of length sfx vs right half
+                    int h = -1;
+                    for (int cand = 1; cand <= nd.m - 1 && h < 0; ++cand)  // cpp:1327-1335
+                        if (L(cand) + Rr(nd.m - cand) == nd.best) h = cand;
+                    if (h < 0 && L(0) + Rr(nd.m) == nd.best) h = 0;       // cpp:1337-1344
+                    if (h < 0 && L(nd.m) + Rr(0) == nd.best) h = nd.m;    // cpp:1345-1353
+                    if (h < 0) throw std::runtime_error("internal: Hirschberg split not found");
+                    Node a, b;
+                    a.pair = b.pair = nd.pair;
+                    a.qOff = nd.qOff;
+                    a.tOff = nd.tOff;
+                    a.m = h;
+                    a.n = leftW;
+                    a.best = L(h);
+                    b.qOff = nd.qOff + (uint64_t)h;
+                    b.tOff = nd.tOff + (uint64_t)leftW;
+                    b.m = nd.m - h;
+                    b.n = rightW;
+                    b.best = Rr(nd.m - h);
+                    nodes[id].left = (int)nodes.size();
+                    frontier.push_back((int)nodes.size());
+                    nodes.push_back(a);
+                    nodes[id].right = (int)nodes.size();
+                    frontier.push_back((int)nodes.size());
+                    nodes.push_back(b);
+                }
+                colPool.clear();
+            }
+            {
+                std::vector<WTask> tasks;
+                tasks.reserve(leaves.size());
+                for (int id : leaves) {
+                    const Node& nd = nodes[id];
                     WTask t;
-                    t.pair = i;
-                    t.qOff = p->qoff[i];
-                    t.tOff = p->tg[p->tidx[i]].off + (uint64_t)e;  // first symbol read, walking backward
-                    t.m = m;
-                    t.n = (int)std::min<long long>((long long)e + 1, (long long)m + p->ed[i]);
-                    t.mode = MODE_SHW;
-                    t.flags = WF_QREV | WF_TREV;
-                    t.kInit = p->ed[i] + 1;
-                    WPlan pl = plan_w(t.m, t.n, MODE_SHW, -1);
+                    t.pair = id;
+                    t.qOff = nd.qOff;
+                    t.tOff = nd.tOff;
+                    t.m = nd.m;
+                    t.n = nd.n;
+                    t.mode = MODE_NW;
+                    t.flags = WF_STORE;
+                    const WPlan pl = plan_w(nd.m, nd.n, MODE_NW, -1);
                     t.R = pl.R;
                     t.nWp = pl.nWp;
                     tasks.push_back(std::move(t));
-                    slotOf.push_back(slot);
+                }
+                runner.run(tasks);
+                for (const WTask& t : tasks) {
+                    Node& nd = nodes[t.pair];
+                    if (t.rec.best != nd.best) throw std::runtime_error("internal: path sweep disagrees with the distance");
+                    nd.opsOff = t.opsOff;
+                    nd.opsLen = t.opsLen;
                 }
             }
-            runner.run(tasks);
-            for (size_t j = 0; j < tasks.size(); ++j) {
-                const WTask& t = tasks[j];
-                if (t.rec.cnt <= 0 || t.rec.best != p->ed[t.pair]) throw std::runtime_error("internal: start-location sweep disagrees");
-                const int e = p->endPool[(size_t)slotOf[j]];
-                p->startPool[(size_t)slotOf[j]] = e - t.rec.last;  // ref cpp:260
+            // in-order concatenation (cpp:1388-1391)
+            std::vector<int> stack;
+            for (int i = 0; i < N; ++i) {
+                if (rootOf[i] < 0) continue;
+                p->alnStart[i] = (long long)p->alnPool.size();
+                stack.assign(1, rootOf[i]);
+                while (!stack.empty()) {
+                    const int id = stack.back();
+                    stack.pop_back();
+                    const Node& nd = nodes[id];
+                    if (nd.left >= 0) {
+                        stack.push_back(nd.right);
+                        stack.push_back(nd.left);
+                    } else if (nd.fillOp >= 0) {
+                        p->alnPool.insert(p->alnPool.end(), (size_t)nd.opsLen, (uint8_t)nd.fillOp);
+                    } else {
+                        p->alnPool.insert(p->alnPool.end(), opsPool.begin() + nd.opsOff, opsPool.begin() + nd.opsOff + nd.opsLen);
+                    }
+                }
+                p->alnLen[i] = (int)(p->alnPool.size() - (size_t)p->alnStart[i]);
             }
         }
     }
+};
 
-    // ---- alignment path (ref cpp:276-289, 1161-1213, 1231-1396) ---------------------------
-    // obtainAlignment as a level-synchronous tree: a node is an NW sub-problem (query slice,
-    // target slice, known score).  Inside the reference's 1 MiB rule (cpp:1188-1190) it is a
-    // leaf: matrix-storing sweep + traceback kernel.  Otherwise it is split like
-    // obtainAlignmentHirschberg: the score column left of the target's middle from a forward
-    // sweep and the one right of it from a reversed sweep (both on the device, cpp:1252-1260),
-    // the split row chosen by the reference's candidate order (cpp:1321-1353), both halves
-    // becoming nodes of the next level (cpp:1372-1380).  All nodes of a level run in one batch.
-    if (p->cfg.task == EDLIB_TASK_PATH) {
-        struct Node {
-            int pair;
-            uint64_t qOff, tOff;
-            int m, n, best;
-            int left = -1, right = -1;
-            long long opsOff = -1;  // into opsPool (leaf) ...
-            int opsLen = 0;
-            int fillOp = -1;        // ... or a run of one op (empty side, cpp:1168-1175)
-        };
-        std::vector<Node> nodes;
-        std::vector<int> rootOf(N, -1), frontier, leaves;
-        for (int i = 0; i < N; ++i) {
-            if (p->ed[i] < 0) continue;
-            const int s0 = p->startPool[(size_t)p->endStart[i]], e0 = p->endPool[(size_t)p->endStart[i]];
-            Node nd;
-            nd.pair = i;
-            nd.qOff = p->qoff[i];
-            nd.tOff = p->tg[p->tidx[i]].off + (uint64_t)s0;
-            nd.m = p->qlen[i];
-            nd.n = e0 - s0 + 1;
-            nd.best = p->ed[i];
-            rootOf[i] = (int)nodes.size();
-            frontier.push_back((int)nodes.size());
-            nodes.push_back(nd);
+}  // namespace
+
+void Engine::compute(Prepared* p) {
+    Backend* be = be_;
+    be->reset_timing();
+    const int N = p->N;
+    const int mode = p->mode;
+    const int k = p->cfg.k;
+    p->ed.assign(N, -1);
+    p->special.assign(N, 0);
+    p->endStart.assign(N, 0);
+    p->endCount.assign(N, 0);
+    p->endPool.clear();
+    p->startPool.clear();
+    p->alnStart.assign(N, -1);
+    p->alnLen.assign(N, 0);
+    p->alnPool.clear();
+    stats.k1Cells = stats.wCells = 0;
+    stats.filterDecided = stats.filterFallback = 0;
+
+    Pass ps(*this, be, p);
+    std::vector<int>& wPairs = ps.wPairs;
+    Trace& trace = ps.trace;
+
+    // ---- classification -----------------------------------------------------------------
+    std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, nw32) -> pairs
+    for (int i = 0; i < N; ++i) {
+        const int m = p->qlen[i], n = p->tlen[i];
+        if (m == 0 || n == 0) {
+            p->special[i] = 1;
+            continue;
         }
-        while (!frontier.empty()) {
-            std::vector<int> split;
-            for (int id : frontier) {
-                Node& nd = nodes[id];
-                if (nd.m == 0 || nd.n <= 0) {
-                    nd.fillOp = (nd.m == 0) ? EDLIB_EDOP_DELETE : EDLIB_EDOP_INSERT;
-                    nd.opsLen = nd.m + std::max(nd.n, 0);
-                    continue;
-                }
-                const long long matrixBytes = 20LL * ceil_div(nd.m, 64) * nd.n + 8LL * nd.n;  // cpp:1188-1190
-                if (matrixBytes < 1024 * 1024) leaves.push_back(id);
-                else split.push_back(id);
-            }
-            frontier.clear();
-            if (split.empty()) break;
-            std::vector<WTask> tasks;
-            tasks.reserve(split.size() * 2);
-            for (int id : split) {
-                const Node& nd = nodes[id];
-                const int leftW = nd.n / 2, rightW = nd.n - leftW;  // cpp:1247-1248
-                const WPlan pl = plan_w(nd.m, nd.n, MODE_NW, nd.best);  // band of the WHOLE node
-                WTask f;
-                f.pair = id;
-                f.qOff = nd.qOff;
-                f.tOff = nd.tOff;
-                f.m = nd.m;
-                f.n = leftW;
-                f.mode = MODE_NW;
-                f.flags = WF_STOPCOL | (pl.slide ? WF_SLIDE : 0);
-                f.dhi = pl.dhi;
-                f.stopCol = leftW - 1;
-                f.R = pl.R;
-                f.nWp = pl.nWp;
-                WTask r = f;
-                r.tOff = nd.tOff + (uint64_t)nd.n - 1;  // reversed: first symbol read is the last one
-                r.n = rightW;
-                r.flags |= WF_QREV | WF_TREV;
-                r.stopCol = rightW - 1;
-                tasks.push_back(std::move(f));
-                tasks.push_back(std::move(r));
-            }
-            runner.run(tasks);
-            for (size_t s = 0; s < split.size(); ++s) {
-                const int id = split[s];
-                const Node nd = nodes[id];
-                const int leftW = nd.n / 2, rightW = nd.n - leftW;
-                const int* colF = colPool.data() + tasks[2 * s].colOff;      // D_fwd[r][leftW-1]
-                const int* colR = colPool.data() + tasks[2 * s + 1].colOff;  // D_rev[r'][rightW-1]
-                auto L = [&](int h) { return h == 0 ? leftW : colF[h - 1]; };       // q[0..h) vs left half
-                auto Rr = [&](int sfx) { return sfx == 0 ? rightW : colR[sfx - 1]; };  // suffix of length sfx vs right half
-                int h = -1;
-                for (int cand = 1; cand <= nd.m - 1 && h < 0; ++cand)  // cpp:1327-1335
-                    if (L(cand) + Rr(nd.m - cand) == nd.best) h = cand;
-                if (h < 0 && L(0) + Rr(nd.m) == nd.best) h = 0;       // cpp:1337-1344
-                if (h < 0 && L(nd.m) + Rr(0) == nd.best) h = nd.m;    // cpp:1345-1353
-                if (h < 0) throw std::runtime_error("internal: Hirschberg split not found");
-                Node a, b;
-                a.pair = b.pair = nd.pair;
-                a.qOff = nd.qOff;
-                a.tOff = nd.tOff;
-                a.m = h;
-                a.n = leftW;
-                a.best = L(h);
-                b.qOff = nd.qOff + (uint64_t)h;
-                b.tOff = nd.tOff + (uint64_t)leftW;
-                b.m = nd.m - h;
-                b.n = rightW;
-                b.best = Rr(nd.m - h);
-                nodes[id].left = (int)nodes.size();
-                frontier.push_back((int)nodes.size());
-                nodes.push_back(a);
-                nodes[id].right = (int)nodes.size();
-                frontier.push_back((int)nodes.size());
-                nodes.push_back(b);
-            }
-            colPool.clear();
+        if (mode == MODE_NW && k >= 0 && k < abs(n - m)) continue;  // ref cpp:744
+        if (m <= 256)
+            groups[std::make_pair(p->tidx[i], ceil_div(m, 32))].push_back(i);
+        else
+            wPairs.push_back(i);
+    }
+
+    // ---- K1 groups ----------------------------------------------------------------------
+    for (auto& kv : groups) {
+        std::vector<int>& list = kv.second;
+        // Small groups go to the warp kernel, except HW over a long target: there the lane kernel
+        // can cut the target into chunks and spread even one alignment over many CTAs.
+        if ((int)list.size() < tun.k1MinGroup && !(mode == MODE_HW && p->tg[kv.first.first].len >= 8 * tun.k1MinChunk)) {
+            wPairs.insert(wPairs.end(), list.begin(), list.end());
+            continue;
         }
+        const int t = kv.first.first, nw = kv.first.second;
         {
-            std::vector<WTask> tasks;
-            tasks.reserve(leaves.size());
-            for (int id : leaves) {
-                const Node& nd = nodes[id];
-                WTask t;
-                t.pair = id;
-                t.qOff = nd.qOff;
-                t.tOff = nd.tOff;
-                t.m = nd.m;
-                t.n = nd.n;
-                t.mode = MODE_NW;
-                t.flags = WF_STORE;
-                const WPlan pl = plan_w(nd.m, nd.n, MODE_NW, -1);
-                t.R = pl.R;
-                t.nWp = pl.nWp;
-                tasks.push_back(std::move(t));
-            }
-            runner.run(tasks);
-            for (const WTask& t : tasks) {
-                Node& nd = nodes[t.pair];
-                if (t.rec.best != nd.best) throw std::runtime_error("internal: path sweep disagrees with the distance");
-                nd.opsOff = t.opsOff;
-                nd.opsLen = t.opsLen;
+            int bt = 0, rc = 0;
+            be->k1_shape(nw, p->ncodes, &bt, &rc);
+            if (rc <= 0) {  // alphabet too large for per-thread Peq rows in shared memory
+                wPairs.insert(wPairs.end(), list.begin(), list.end());
+                continue;
             }
         }
-        // in-order concatenation (cpp:1388-1391)
-        std::vector<int> stack;
-        for (int i = 0; i < N; ++i) {
-            if (rootOf[i] < 0) continue;
-            p->alnStart[i] = (long long)p->alnPool.size();
-            stack.assign(1, rootOf[i]);
-            while (!stack.empty()) {
-                const int id = stack.back();
-                stack.pop_back();
-                const Node& nd = nodes[id];
-                if (nd.left >= 0) {
-                    stack.push_back(nd.right);
-                    stack.push_back(nd.left);
-                } else if (nd.fillOp >= 0) {
-                    p->alnPool.insert(p->alnPool.end(), (size_t)nd.opsLen, (uint8_t)nd.fillOp);
-                } else {
-                    p->alnPool.insert(p->alnPool.end(), opsPool.begin() + nd.opsOff, opsPool.begin() + nd.opsOff + nd.opsLen);
-                }
-            }
-            p->alnLen[i] = (int)(p->alnPool.size() - (size_t)p->alnStart[i]);
-        }
+        ps.lane_group(t, nw, list);
     }
-
+    trace.mark("compute: K1 groups done");
+    ps.warp_distance();
+    trace.mark("compute: W distance pass");
+    ps.collect_ends();
+    trace.mark("compute: end locations");
+    ps.start_locations();
+    ps.paths();
     trace.mark("compute: starts + paths");
     be->sync();
     stats.kernelMs = be->kernel_ms(nullptr);
