@@ -189,6 +189,24 @@ struct TbParams {
     int* opsLen;       // [job]
 };
 
+// Hirschberg split search (ref cpp:1321-1353) over the two stop columns of a node, on the device.
+struct SplitNode {
+    uint64_t colF;     // into cols: D_fwd[r][leftW-1], r = 0..m-1 (0x3f3f3f3f where outside the band)
+    uint64_t colR;     // into cols: D_rev[r'][rightW-1]
+    int m, leftW, rightW, best;
+};
+struct SplitOut {
+    int h;             // rows of the query that go with the left half (-1: no split found)
+    int left, right;   // scores of the two halves
+    int rsv;
+};
+struct SplitParams {
+    const SplitNode* nodes;
+    int numNodes;
+    const int* cols;
+    SplitOut* out;
+};
+
 // Presence / alphabet kernels.
 struct MaskItem {
     uint64_t off;            // into raw

@@ -789,6 +789,30 @@ EB_HD void traceback_job(const TbParams& p, int jobIdx) {
     p.opsLen[jobIdx] = J.m + J.n - w;
 }
 
+// Split row of one Hirschberg node.  With L[h] = distance(q[0..h), left half) and R[s] = distance(last s
+// query rows, right half): the first h in 1..m-1 with L[h] + R[m-h] == best (cpp:1327-1335), else the
+// top boundary h = 0 (cpp:1337-1344), else the bottom boundary h = m (cpp:1345-1353).
+EB_HD void split_node(const SplitParams& p, int nodeIdx) {
+    const SplitNode nd = p.nodes[nodeIdx];
+    const int* colF = p.cols + nd.colF;
+    const int* colR = p.cols + nd.colR;
+    int h = -1;
+    for (int cand = 1; cand <= nd.m - 1; ++cand) {
+        if (colF[cand - 1] + colR[nd.m - cand - 1] == nd.best) {
+            h = cand;
+            break;
+        }
+    }
+    if (h < 0 && nd.leftW + colR[nd.m - 1] == nd.best) h = 0;
+    if (h < 0 && colF[nd.m - 1] + nd.rightW == nd.best) h = nd.m;
+    SplitOut o;
+    o.h = h;
+    o.left = h < 0 ? 0 : (h == 0 ? nd.leftW : colF[h - 1]);
+    o.right = h < 0 ? 0 : (h == nd.m ? nd.rightW : colR[nd.m - h - 1]);
+    o.rsv = 0;
+    p.out[nodeIdx] = o;
+}
+
 // Presence set of one item (<= 64 KiB of raw bytes), OR-ed into its destination set.
 EB_HD void mask_item(const MaskParams& p, int itemIdx, int first, int stride) {
     const MaskItem it = p.items[itemIdx];

@@ -98,11 +98,13 @@ struct WTask {
     int R = 1, nWp = 0;
     int pair = -1, tag = 0;
     bool wantPositions = false;  // the caller needs every end position, not just best/cnt/last
+    int splitSide = -1;          // WF_STOPCOL pairs of a Hirschberg node: 0 forward half, 1 reversed half (adjacent tasks)
+    int splitBest = 0;           // ... the node's known score
+    SplitOut split{};            // ... the split found on the device (stored on the forward task)
     Rec rec{};
     std::vector<int> extra;  // positions past KPOS that attain rec.best, ascending
     long long opsOff = -1;   // into the ops pool (WF_STORE)
     int opsLen = 0;
-    long long colOff = -1;   // into the column pool (WF_STOPCOL)
 };
 
 struct WPlan {
@@ -378,7 +380,6 @@ struct WRunner {
     Backend* be;
     Prepared* p;
     std::vector<uint8_t>* opsPool = nullptr;
-    std::vector<int>* colPool = nullptr;
 
     size_t task_bytes(const WTask& t) const {
         size_t b = (size_t)p->ncodes * t.nWp * 4 + sizeof(WJob) + sizeof(Rec);
@@ -424,7 +425,7 @@ struct WRunner {
             size_t bytes = 0, j = i;
             while (j < order.size() && tasks[order[j]].R == R) {
                 const size_t tb = task_bytes(tasks[order[j]]);
-                if (j > i && bytes + tb > eng->tun.sliceBytes) break;
+                if (j > i && bytes + tb > eng->tun.sliceBytes && tasks[order[j]].splitSide != 1) break;
                 bytes += tb;
                 ++j;
             }
@@ -589,10 +590,7 @@ struct WRunner {
         DevBuf<Ovf> dOvf(be, (size_t)std::max(ovfCap, 1));
         DevBuf<int> dOvfCount(be, 1);
         be->zero(dOvfCount.p, sizeof(int));
-        if (colInts) {
-            std::vector<int> big(colInts, 0x3f3f3f3f);  // rows outside a sliding window: "far above any k"
-            dCol.upload(big.data(), colInts);
-        }
+        if (colInts) be->fill(dCol.p, 0x3f, (size_t)colInts * sizeof(int));  // rows outside a sliding window: far above any k
         PeqParams pp{dJobs.p, J, p->dSeq.p, dPeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr};
         be->launch_peq(pp);
         WParams wp{dJobs.p, J, p->dSeq.p, p->dSeq.p, dPeq.p, dH.p, dMat.p, dCol.p, dRecs.p, dOvf.p, dOvfCount.p, ovfCap};
@@ -644,16 +642,33 @@ struct WRunner {
             }
         }
         if (colInts) {
-            std::vector<int> cols(colInts);
-            dCol.download(cols.data(), colInts);
-            eng->stats.d2hBytes += (long long)colInts * 4;
-            for (int s = 0; s < J; ++s) {
-                WTask& t = tasks[slice[s]];
-                if (t.flags & WF_STOPCOL) {
-                    t.colOff = (long long)colPool->size();
-                    colPool->insert(colPool->end(), cols.begin() + jobs[s].auxOff, cols.begin() + jobs[s].auxOff + t.m);
-                }
+            // Hirschberg halves: the split row is searched on the device, only {h, left, right} come back.
+            std::vector<SplitNode> nodes;
+            std::vector<int> owner;
+            for (int s = 0; s + 1 < J; ++s) {
+                const WTask& f = tasks[slice[s]];
+                const WTask& r = tasks[slice[s + 1]];
+                if (f.splitSide != 0 || r.splitSide != 1) continue;
+                SplitNode nd;
+                nd.colF = jobs[s].auxOff;
+                nd.colR = jobs[s + 1].auxOff;
+                nd.m = f.m;
+                nd.leftW = f.n;
+                nd.rightW = r.n;
+                nd.best = f.splitBest;
+                nodes.push_back(nd);
+                owner.push_back(slice[s]);
             }
+            if (nodes.empty()) throw std::runtime_error("internal: stop-column tasks without a split pair");
+            DevBuf<SplitNode> dNodes(be, nodes.size());
+            dNodes.upload(nodes.data(), nodes.size());
+            DevBuf<SplitOut> dOut(be, nodes.size());
+            SplitParams sp{dNodes.p, (int)nodes.size(), dCol.p, dOut.p};
+            be->launch_split(sp);
+            std::vector<SplitOut> outs(nodes.size());
+            dOut.download(outs.data(), outs.size());
+            eng->stats.d2hBytes += (long long)outs.size() * (long long)sizeof(SplitOut);
+            for (size_t q = 0; q < outs.size(); ++q) tasks[owner[q]].split = outs[q];
         }
         if (ovfCap == 0) {
             std::vector<int> again;
@@ -696,13 +711,12 @@ struct Pass {
     std::vector<int> posLen, posPool;
     std::vector<int> wPairs;          // pairs swept by the warp / lane-job kernels
     std::vector<uint8_t> opsPool;
-    std::vector<int> colPool;
     WRunner runner;
 
     Pass(Engine& e, Backend* b, Prepared* pr)
         : eng(e), be(b), p(pr), tun(e.tun), stats(e.stats), N(pr->N), mode(pr->mode), k(pr->cfg.k),
           best(pr->N, -1), cnt(pr->N, 0), posStart(pr->N, -1), posLen(pr->N, 0),
-          runner{&e, b, pr, &opsPool, &colPool} {
+          runner{&e, b, pr, &opsPool} {
         posPool.reserve((size_t)N + 16);
     }
 
@@ -1201,11 +1215,14 @@ struct Pass {
                     f.stopCol = leftW - 1;
                     f.R = pl.R;
                     f.nWp = pl.nWp;
+                    f.splitSide = 0;
+                    f.splitBest = nd.best;
                     WTask r = f;
                     r.tOff = nd.tOff + (uint64_t)nd.n - 1;  // reversed: first symbol read is the last one
                     r.n = rightW;
                     r.flags |= WF_QREV | WF_TREV;
                     r.stopCol = rightW - 1;
+                    r.splitSide = 1;
                     tasks.push_back(std::move(f));
                     tasks.push_back(std::move(r));
                 }
@@ -1214,15 +1231,8 @@ struct Pass {
                     const int id = split[s];
                     const Node nd = nodes[id];
                     const int leftW = nd.n / 2, rightW = nd.n - leftW;
-                    const int* colF = colPool.data() + tasks[2 * s].colOff;      // D_fwd[r][leftW-1]
-                    const int* colR = colPool.data() + tasks[2 * s + 1].colOff;  // D_rev[r'][rightW-1]
-                    auto L = [&](int h) { return h == 0 ? leftW : colF[h - 1]; };       // q[0..h) vs left half
-                    auto Rr = [&](int sfx) { return sfx == 0 ? rightW : colR[sfx - 1]; };  // suffix of length sfx vs right half
-                    int h = -1;
-                    for (int cand = 1; cand <= nd.m - 1 && h < 0; ++cand)  // cpp:1327-1335
-                        if (L(cand) + Rr(nd.m - cand) == nd.best) h = cand;
-                    if (h < 0 && L(0) + Rr(nd.m) == nd.best) h = 0;       // cpp:1337-1344
-                    if (h < 0 && L(nd.m) + Rr(0) == nd.best) h = nd.m;    // cpp:1345-1353
+                    const SplitOut& so = tasks[2 * s].split;  // found on the device (split_kernel)
+                    const int h = so.h;
                     if (h < 0) throw std::runtime_error("internal: Hirschberg split not found");
                     Node a, b;
                     a.pair = b.pair = nd.pair;
@@ -1230,12 +1240,12 @@ struct Pass {
                     a.tOff = nd.tOff;
                     a.m = h;
                     a.n = leftW;
-                    a.best = L(h);
+                    a.best = so.left;
                     b.qOff = nd.qOff + (uint64_t)h;
                     b.tOff = nd.tOff + (uint64_t)leftW;
                     b.m = nd.m - h;
                     b.n = rightW;
-                    b.best = Rr(nd.m - h);
+                    b.best = so.right;
                     nodes[id].left = (int)nodes.size();
                     frontier.push_back((int)nodes.size());
                     nodes.push_back(a);
@@ -1243,7 +1253,6 @@ struct Pass {
                     frontier.push_back((int)nodes.size());
                     nodes.push_back(b);
                 }
-                colPool.clear();
             }
             {
                 std::vector<WTask> tasks;

@@ -25,6 +25,7 @@ struct Backend {
     virtual void h2d(void* dst, const void* src, size_t bytes) = 0;
     virtual void d2h(void* dst, const void* src, size_t bytes) = 0;  // synchronising
     virtual void zero(void* dst, size_t bytes) = 0;
+    virtual void fill(void* dst, int byteValue, size_t bytes) = 0;
     virtual void sync() = 0;
     virtual int sm_count() = 0;
     // Launch shape of the lane-per-alignment kernel for a word class / alphabet size: threads per
@@ -40,6 +41,7 @@ struct Backend {
     virtual void launch_peq(const PeqParams& p) = 0;
     virtual void launch_w(const WParams& p, int R) = 0;
     virtual void launch_traceback(const TbParams& p) = 0;
+    virtual void launch_split(const SplitParams& p) = 0;
     // timing of the launches issued since the last reset (device time, ms) and their count
     virtual void reset_timing() = 0;
     virtual double kernel_ms(const char* nameOrNull) = 0;

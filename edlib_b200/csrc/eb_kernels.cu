@@ -292,6 +292,11 @@ __global__ void traceback_kernel(const TbParams p) {
     if (job < p.numJobs) traceback_job(p, job);
 }
 
+__global__ void split_kernel(const SplitParams p) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node < p.numNodes) split_node(p, node);
+}
+
 __global__ void mask_kernel(const MaskParams p) {
     const int item = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
     if (item >= p.numItems) return;
@@ -416,6 +421,9 @@ struct CudaBackend : Backend {
     }
     void zero(void* d, size_t n) override {
         if (n) EB_CUDA(cudaMemsetAsync(d, 0, n, stream));
+    }
+    void fill(void* d, int v, size_t n) override {
+        if (n) EB_CUDA(cudaMemsetAsync(d, v, n, stream));
     }
     void sync() override { EB_CUDA(cudaStreamSynchronize(stream)); }
     int sm_count() override { return sms; }
@@ -640,6 +648,11 @@ struct CudaBackend : Backend {
             default: throw std::runtime_error("bad W chunk size");
         }
         check_launch("w");
+    }
+    void launch_split(const SplitParams& p) override {
+        Scope s(this, "split");
+        split_kernel<<<(p.numNodes + 63) / 64, 64, 0, stream>>>(p);
+        check_launch("split");
     }
     void launch_traceback(const TbParams& p) override {
         Scope s(this, "traceback");

@@ -87,6 +87,7 @@ struct EmulBackend : Backend {
     void h2d(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
     void d2h(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
     void zero(void* d, size_t n) override { memset(d, 0, n); }
+    void fill(void* d, int v, size_t n) override { memset(d, v, n); }
     void sync() override {}
     int sm_count() override {
         const char* s = getenv("EDLIB_EMUL_SMS");
@@ -166,6 +167,10 @@ struct EmulBackend : Backend {
                 default: throw std::runtime_error("bad W chunk size");
             }
         }
+    }
+    void launch_split(const SplitParams& p) override {
+        ++launchesCount;
+        for (int j = 0; j < p.numNodes; ++j) split_node(p, j);
     }
     void launch_traceback(const TbParams& p) override {
         ++launchesCount;
