@@ -712,12 +712,101 @@ struct Pass {
     std::vector<int> wPairs;          // pairs swept by the warp / lane-job kernels
     std::vector<uint8_t> opsPool;
     WRunner runner;
+    int laneOkCache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
 
     Pass(Engine& e, Backend* b, Prepared* pr)
         : eng(e), be(b), p(pr), tun(e.tun), stats(e.stats), N(pr->N), mode(pr->mode), k(pr->cfg.k),
           best(pr->N, -1), cnt(pr->N, 0), posStart(pr->N, -1), posLen(pr->N, 0),
           runner{&e, b, pr, &opsPool} {
         posPool.reserve((size_t)N + 16);
+    }
+
+    // ---- direct lane-kernel launches (no per-job host objects): the LOC / PATH phases of large read
+    // batches issue millions of tiny sweeps, so their jobs are built straight into LJob arrays. --------
+    bool lane_ok(int m) {
+        if (m <= 0 || m > 256) return false;
+        const int nw = ceil_div(m, 32);
+        if (laneOkCache[nw] < 0) {
+            int bt = 0, rc = 0;
+            be->k1_shape(nw, p->ncodes, &bt, &rc);
+            laneOkCache[nw] = rc > 0 ? 1 : 0;
+        }
+        return laneOkCache[nw] == 1;
+    }
+
+    void lane_launch(const std::vector<LJob>& jobs, int nw, int laneMode, bool rev, std::vector<Rec>& recs) {
+        const size_t J = jobs.size();
+        recs.resize(J);
+        const size_t step = 4u << 20;
+        for (size_t a = 0; a < J; a += step) {
+            const size_t n = std::min(step, J - a);
+            DevBuf<LJob> dJobs(be, n);
+            dJobs.upload(jobs.data() + a, n);
+            DevBuf<Rec> dRecs(be, n);
+            be->zero(dRecs.p, n * sizeof(Rec));
+            LParams lp{dJobs.p, (int)n, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, nullptr};
+            be->launch_lane(lp, nw, laneMode, rev, false);
+            dRecs.download(recs.data() + a, n);
+            stats.d2hBytes += (long long)n * (long long)sizeof(Rec);
+        }
+    }
+
+    // Matrix-storing NW sweeps + traceback of `jobs` (matOff is assigned here); `sink(jobIndex, ops, len,
+    // score)` receives every edit script.  Slices bound the stored matrices to the slice budget.
+    template <class Sink>
+    void lane_paths(std::vector<LJob>& jobs, int nw, Sink sink) {
+        size_t a = 0;
+        while (a < jobs.size()) {
+            size_t bytes = 0, b = a;
+            uint64_t matEntries = 0, opsBytes = 0;
+            std::vector<TbJob> tb;
+            while (b < jobs.size()) {
+                LJob& j = jobs[b];
+                const size_t need = (size_t)j.n * nw * 8 + (size_t)j.m + j.n + sizeof(LJob) + sizeof(TbJob) + 64;
+                if (b > a && bytes + need > tun.sliceBytes) break;
+                j.matOff = matEntries;
+                TbJob t;
+                memset(&t, 0, sizeof(t));
+                t.matOff = matEntries;
+                t.qOff = j.qOff;
+                t.peqOff = ~0ull;
+                t.tOff = j.tOff;
+                t.outOff = opsBytes;
+                t.m = j.m;
+                t.n = j.n;
+                t.nWp = nw;
+                tb.push_back(t);
+                matEntries += (uint64_t)j.n * nw;
+                opsBytes += (uint64_t)j.m + j.n;
+                bytes += need;
+                ++b;
+            }
+            const size_t n = b - a;
+            DevBuf<LJob> dJobs(be, n);
+            dJobs.upload(jobs.data() + a, n);
+            DevBuf<Rec> dRecs(be, n);
+            be->zero(dRecs.p, n * sizeof(Rec));
+            DevBuf<U2> dMat(be, matEntries);
+            LParams lp{dJobs.p, (int)n, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p};
+            be->launch_lane(lp, nw, MODE_NW, false, true);
+            DevBuf<TbJob> dTb(be, n);
+            dTb.upload(tb.data(), n);
+            DevBuf<uint8_t> dOps(be, opsBytes);
+            DevBuf<int> dStart(be, n), dLen(be, n);
+            TbParams tp{dTb.p, (int)n, dMat.p, nullptr, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
+                        dOps.p, dStart.p, dLen.p};
+            be->launch_traceback(tp);
+            std::vector<Rec> recs(n);
+            std::vector<int> st(n), ln(n);
+            std::vector<uint8_t> ops(opsBytes);
+            dRecs.download(recs.data(), n);
+            dStart.download(st.data(), n);
+            dLen.download(ln.data(), n);
+            dOps.download(ops.data(), opsBytes);
+            stats.d2hBytes += (long long)opsBytes + (long long)n * (long long)(sizeof(Rec) + 8);
+            for (size_t q = 0; q < n; ++q) sink(a + q, ops.data() + tb[q].outOff + st[q], ln[q], recs[q].best);
+            a = b;
+        }
     }
 
     // Distance pass of one group of pairs that share target `t` and word class `nw` (queries <= 256
@@ -1113,13 +1202,31 @@ struct Pass {
             if (mode == MODE_HW) {
                 std::vector<WTask> tasks;
                 std::vector<long long> slotOf;
+                std::vector<LJob> lj[9];          // short queries: straight to the lane kernel, per word class
+                std::vector<long long> lslot[9];
+                std::vector<int> lpair[9];
                 for (int i = 0; i < N; ++i) {
                     if (p->ed[i] < 0) continue;
                     const int m = p->qlen[i];
+                    const bool lane = lane_ok(m);
                     for (int q = 0; q < p->endCount[i]; ++q) {
                         const long long slot = p->endStart[i] + q;
                         const int e = p->endPool[(size_t)slot];
                         if (e < 0) continue;  // ref cpp:237-249: start 0
+                        if (lane) {
+                            const int nw = ceil_div(m, 32);
+                            LJob j;
+                            memset(&j, 0, sizeof(j));
+                            j.qOff = p->qoff[i];
+                            j.tOff = p->tg[p->tidx[i]].off + (uint64_t)e;  // first symbol read, walking backward
+                            j.m = m;
+                            j.n = (int)std::min<long long>((long long)e + 1, (long long)m + p->ed[i]);
+                            j.kInit = p->ed[i] + 1;
+                            lj[nw].push_back(j);
+                            lslot[nw].push_back(slot);
+                            lpair[nw].push_back(i);
+                            continue;
+                        }
                         WTask t;
                         t.pair = i;
                         t.qOff = p->qoff[i];
@@ -1134,6 +1241,17 @@ struct Pass {
                         t.nWp = pl.nWp;
                         tasks.push_back(std::move(t));
                         slotOf.push_back(slot);
+                    }
+                }
+                for (int nw = 1; nw <= 8; ++nw) {
+                    if (lj[nw].empty()) continue;
+                    std::vector<Rec> recs;
+                    lane_launch(lj[nw], nw, MODE_SHW, true, recs);
+                    for (size_t j = 0; j < recs.size(); ++j) {
+                        if (recs[j].cnt <= 0 || recs[j].best != p->ed[lpair[nw][j]])
+                            throw std::runtime_error("internal: start-location sweep disagrees");
+                        const int e = p->endPool[(size_t)lslot[nw][j]];
+                        p->startPool[(size_t)lslot[nw][j]] = e - recs[j].last;  // ref cpp:260
                     }
                 }
                 runner.run(tasks);
@@ -1256,9 +1374,22 @@ struct Pass {
             }
             {
                 std::vector<WTask> tasks;
-                tasks.reserve(leaves.size());
+                std::vector<LJob> lj[9];  // leaves with short queries: lane kernel, per word class
+                std::vector<int> lnode[9];
                 for (int id : leaves) {
                     const Node& nd = nodes[id];
+                    if (lane_ok(nd.m)) {
+                        const int nw = ceil_div(nd.m, 32);
+                        LJob j;
+                        memset(&j, 0, sizeof(j));
+                        j.qOff = nd.qOff;
+                        j.tOff = nd.tOff;
+                        j.m = nd.m;
+                        j.n = nd.n;
+                        lj[nw].push_back(j);
+                        lnode[nw].push_back(id);
+                        continue;
+                    }
                     WTask t;
                     t.pair = id;
                     t.qOff = nd.qOff;
@@ -1271,6 +1402,16 @@ struct Pass {
                     t.R = pl.R;
                     t.nWp = pl.nWp;
                     tasks.push_back(std::move(t));
+                }
+                for (int nw = 1; nw <= 8; ++nw) {
+                    if (lj[nw].empty()) continue;
+                    lane_paths(lj[nw], nw, [&](size_t j, const uint8_t* ops, int len, int score) {
+                        Node& nd = nodes[lnode[nw][j]];
+                        if (score != nd.best) throw std::runtime_error("internal: path sweep disagrees with the distance");
+                        nd.opsOff = (long long)opsPool.size();
+                        nd.opsLen = len;
+                        opsPool.insert(opsPool.end(), ops, ops + len);
+                    });
                 }
                 runner.run(tasks);
                 for (const WTask& t : tasks) {

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Long randomized parity run (not part of pytest): every case generator of tests/cases.py with many seeds
+through the product library, bit-exact against the reference build.  Usage: python scripts/stress.py [minutes]"""
+import os
+import sys
+import time
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+import cases  # noqa: E402
+import parity  # noqa: E402
+from helpers import product  # noqa: E402
+
+budget = float(sys.argv[1]) * 60 if len(sys.argv) > 1 else 120.0
+lib = product()
+t0 = time.time()
+total = 0
+seed = 1000
+plan = [("single", cases.single_pair_cases, 400, parity.run_single), ("batch", cases.batch_cases, 12, parity.run_batches),
+        ("pairwise", cases.pairwise_cases, 12, parity.run_batches), ("filter", cases.filter_cases, 10, parity.run_batches),
+        ("long", cases.long_cases, 12, parity.run_single), ("path", cases.path_cases, 20, parity.run_single)]
+counts = {}
+while time.time() - t0 < budget:
+    for name, gen, n, runner in plan:
+        seed += 1
+        got = runner(lib, seed, n, gen=gen)
+        counts[name] = counts.get(name, 0) + got
+        total += got
+print("stress ok:", total, "alignments bit-exact in %.0f s" % (time.time() - t0), counts)
