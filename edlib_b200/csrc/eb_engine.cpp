@@ -796,15 +796,21 @@ struct Pass {
             TbParams tp{dTb.p, (int)n, dMat.p, nullptr, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
                         dOps.p, dStart.p, dLen.p};
             be->launch_traceback(tp);
-            std::vector<Rec> recs(n);
-            std::vector<int> st(n), ln(n);
-            std::vector<uint8_t> ops(opsBytes);
-            dRecs.download(recs.data(), n);
-            dStart.download(st.data(), n);
-            dLen.download(ln.data(), n);
-            dOps.download(ops.data(), opsBytes);
+            // one pinned staging block for everything that comes back (fast D2H, no zero-fill of vectors)
+            const size_t offSt = round_up(n * sizeof(Rec), 64), offLn = offSt + round_up(n * sizeof(int), 64);
+            const size_t offOps = offLn + round_up(n * sizeof(int), 64);
+            uint8_t* host = static_cast<uint8_t*>(be->alloc_host(offOps + opsBytes));
+            const Rec* recs = reinterpret_cast<const Rec*>(host);
+            const int* st = reinterpret_cast<const int*>(host + offSt);
+            const int* ln = reinterpret_cast<const int*>(host + offLn);
+            const uint8_t* ops = host + offOps;
+            be->d2h(host, dRecs.p, n * sizeof(Rec));
+            be->d2h(host + offSt, dStart.p, n * sizeof(int));
+            be->d2h(host + offLn, dLen.p, n * sizeof(int));
+            be->d2h(host + offOps, dOps.p, opsBytes);
             stats.d2hBytes += (long long)opsBytes + (long long)n * (long long)(sizeof(Rec) + 8);
-            for (size_t q = 0; q < n; ++q) sink(a + q, ops.data() + tb[q].outOff + st[q], ln[q], recs[q].best);
+            for (size_t q = 0; q < n; ++q) sink(a + q, ops + tb[q].outOff + st[q], ln[q], recs[q].best);
+            be->free_host(host);
             a = b;
         }
     }
@@ -1243,6 +1249,7 @@ struct Pass {
                         slotOf.push_back(slot);
                     }
                 }
+                trace.mark("starts: jobs built");
                 for (int nw = 1; nw <= 8; ++nw) {
                     if (lj[nw].empty()) continue;
                     std::vector<Rec> recs;
@@ -1254,6 +1261,7 @@ struct Pass {
                         p->startPool[(size_t)lslot[nw][j]] = e - recs[j].last;  // ref cpp:260
                     }
                 }
+                trace.mark("starts: lane sweeps");
                 runner.run(tasks);
                 for (size_t j = 0; j < tasks.size(); ++j) {
                     const WTask& t = tasks[j];
@@ -1403,6 +1411,7 @@ struct Pass {
                     t.nWp = pl.nWp;
                     tasks.push_back(std::move(t));
                 }
+                trace.mark("paths: tree + leaf jobs built");
                 for (int nw = 1; nw <= 8; ++nw) {
                     if (lj[nw].empty()) continue;
                     lane_paths(lj[nw], nw, [&](size_t j, const uint8_t* ops, int len, int score) {
@@ -1421,6 +1430,7 @@ struct Pass {
                     nd.opsLen = t.opsLen;
                 }
             }
+            trace.mark("paths: leaf sweeps + tracebacks");
             // in-order concatenation (cpp:1388-1391)
             std::vector<int> stack;
             for (int i = 0; i < N; ++i) {
