@@ -234,6 +234,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: whatever NCCL_DEBUG level is set goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     lib = EdlibLib(product_path(), has_batch=True)
