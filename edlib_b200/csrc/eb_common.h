@@ -45,6 +45,11 @@ struct Ovf {
     int pos;
 };
 
+// Candidate-filter range list (K1 rangeMode, eb_core.h: k1_range_flush)
+#define K1_RANGE_GAP 256    // a candidate this far after the previous one opens a new range
+#define K1_RANGE_SPAN 1024  // ... or this far after the first one of the open range
+#define K1_RANGE_MAX 16     // ranges per (chunk, read) before the read is marked as saturated
+
 enum Mode : int { MODE_NW = 0, MODE_SHW = 1, MODE_HW = 2 };
 
 // ---------------------------------------------------------------------------------------------
@@ -65,13 +70,13 @@ struct K1Params {
     int chunks;              // target chunks (HW only; 1 otherwise)
     int chunkLen;            // multiple of 16
     int halo;                // columns swept before a chunk without tracking (>= 2*max m)
-    Rec* recs;               // [chunks][numReads]  (rangeMode: [numReads])
+    Rec* recs;               // [chunks][numReads]  (unused in rangeMode)
     Ovf* ovf;
     int* ovfCount;
     int ovfCap;
     int prefixLen;           // > 0: sweep only the first prefixLen rows of every query (candidate filter)
-    int rangeMode;           // 1: record {count, first, last} of the columns whose score is <= kInit,
-                             //    merged over chunks into recs[slot] (eb_core.h: k1_range_commit)
+    int rangeMode;           // 1: instead of the running minimum, append the ranges of columns whose prefix score
+                             //    is <= kInit to ovf[] as {rec = read slot, score = first, pos = last}
 };
 
 // K1W: lane-per-alignment HW sweep of each query over ITS OWN window of the shared target (the

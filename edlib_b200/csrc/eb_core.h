@@ -146,6 +146,78 @@ struct AddChain<8> {
 };
 #endif
 
+// S = X << 1 over NW words as the add X + X with the carry rippling upward; the bit shifted out of the
+// last word (the last query row, see eb_common.h) is added to `top`.  On the B200 the integer add issues
+// at twice the rate of the funnel shift (profiles/r01_pipe_microbench.txt: IADD 0.97 vs SHF 0.49
+// warp-instructions/clk/SMSP) and the carry-out replaces the separate extraction of the last-row bit.
+template <int NW>
+struct ShiftChain {
+    static EB_HD void run(uint32_t (&S)[NW], const uint32_t (&X)[NW], int& top) {
+        EB_UNROLL
+        for (int w = NW - 1; w > 0; --w) S[w] = (X[w] << 1) | (X[w - 1] >> 31);
+        S[0] = X[0] << 1;
+        top += (int)(X[NW - 1] >> 31);
+    }
+};
+#if defined(__CUDA_ARCH__)
+template <>
+struct ShiftChain<1> {
+    static EB_HD void run(uint32_t (&S)[1], const uint32_t (&X)[1], int& top) {
+        asm("add.cc.u32 %0, %2, %2;\n\taddc.u32 %1, %1, 0;"
+            : "=&r"(S[0]), "+r"(top) : "r"(X[0]));
+    }
+};
+template <>
+struct ShiftChain<2> {
+    static EB_HD void run(uint32_t (&S)[2], const uint32_t (&X)[2], int& top) {
+        asm("add.cc.u32 %0, %3, %3;\n\taddc.cc.u32 %1, %4, %4;\n\taddc.u32 %2, %2, 0;"
+            : "=&r"(S[0]), "=&r"(S[1]), "+r"(top) : "r"(X[0]), "r"(X[1]));
+    }
+};
+template <>
+struct ShiftChain<3> {
+    static EB_HD void run(uint32_t (&S)[3], const uint32_t (&X)[3], int& top) {
+        asm("add.cc.u32 %0, %4, %4;\n\taddc.cc.u32 %1, %5, %5;\n\taddc.cc.u32 %2, %6, %6;\n\taddc.u32 %3, %3, 0;"
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "+r"(top) : "r"(X[0]), "r"(X[1]), "r"(X[2]));
+    }
+};
+template <>
+struct ShiftChain<4> {
+    static EB_HD void run(uint32_t (&S)[4], const uint32_t (&X)[4], int& top) {
+        asm("add.cc.u32 %0, %5, %5;\n\taddc.cc.u32 %1, %6, %6;\n\taddc.cc.u32 %2, %7, %7;\n\taddc.cc.u32 %3, %8, %8;\n\taddc.u32 %4, %4, 0;"
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "+r"(top) : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]));
+    }
+};
+template <>
+struct ShiftChain<5> {
+    static EB_HD void run(uint32_t (&S)[5], const uint32_t (&X)[5], int& top) {
+        asm("add.cc.u32 %0, %6, %6;\n\taddc.cc.u32 %1, %7, %7;\n\taddc.cc.u32 %2, %8, %8;\n\taddc.cc.u32 %3, %9, %9;\n\taddc.cc.u32 %4, %10, %10;\n\taddc.u32 %5, %5, 0;"
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "+r"(top) : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]));
+    }
+};
+template <>
+struct ShiftChain<6> {
+    static EB_HD void run(uint32_t (&S)[6], const uint32_t (&X)[6], int& top) {
+        asm("add.cc.u32 %0, %7, %7;\n\taddc.cc.u32 %1, %8, %8;\n\taddc.cc.u32 %2, %9, %9;\n\taddc.cc.u32 %3, %10, %10;\n\taddc.cc.u32 %4, %11, %11;\n\taddc.cc.u32 %5, %12, %12;\n\taddc.u32 %6, %6, 0;"
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "+r"(top) : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]));
+    }
+};
+template <>
+struct ShiftChain<7> {
+    static EB_HD void run(uint32_t (&S)[7], const uint32_t (&X)[7], int& top) {
+        asm("add.cc.u32 %0, %8, %8;\n\taddc.cc.u32 %1, %9, %9;\n\taddc.cc.u32 %2, %10, %10;\n\taddc.cc.u32 %3, %11, %11;\n\taddc.cc.u32 %4, %12, %12;\n\taddc.cc.u32 %5, %13, %13;\n\taddc.cc.u32 %6, %14, %14;\n\taddc.u32 %7, %7, 0;"
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "=&r"(S[6]), "+r"(top) : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]));
+    }
+};
+template <>
+struct ShiftChain<8> {
+    static EB_HD void run(uint32_t (&S)[8], const uint32_t (&X)[8], int& top) {
+        asm("add.cc.u32 %0, %9, %9;\n\taddc.cc.u32 %1, %10, %10;\n\taddc.cc.u32 %2, %11, %11;\n\taddc.cc.u32 %3, %12, %12;\n\taddc.cc.u32 %4, %13, %13;\n\taddc.cc.u32 %5, %14, %14;\n\taddc.cc.u32 %6, %15, %15;\n\taddc.cc.u32 %7, %16, %16;\n\taddc.u32 %8, %8, 0;"
+            : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "=&r"(S[6]), "=&r"(S[7]), "+r"(top) : "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]));
+    }
+};
+#endif
+
 // Pv word for the column before the first one: ones on real rows, zeros on padding bits.
 EB_HD uint32_t init_pv_word(int wordIdx, int off) {
     const int lo = wordIdx * 32;
@@ -162,11 +234,12 @@ EB_HD uint32_t init_pv_word(int wordIdx, int off) {
 // calculateBlock (cpp:421-444) but over ONE NW*32-bit integer: the add carry and the <<1 carry
 // cross word boundaries natively, so no per-block hin/hout is needed.  TOP_ONE selects the
 // horizontal delta entering above row 0: +1 for NW/SHW (cpp:779, 584), 0 for HW.
-// (Measured alternatives, dropped: doing the <<1 or the last-row bit extraction with IMAD/IMAD.HI on
-// the idle FMA pipe is slower because the high-half multiply is quarter-rate on B200, and an
-// add-with-carry chain needs as many ALU instructions as the funnel shifts; profiles/README.md.)
+// The last-row score is kept as score = up - down: both <<1 shifts are add-with-carry chains whose carry-out
+// (the last-row bit of Ph / Mh) accumulates into `up` / `down`.
+// (Measured alternative, dropped: doing the <<1 with IMAD/IMAD.HI on the FMA pipe is slower because the
+// high-half multiply is quarter-rate on B200; profiles/README.md.)
 template <int NW, bool TOP_ONE>
-EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& score, uint32_t* phOut = nullptr) {
+EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[NW], int& up, int& down, uint32_t* phOut = nullptr) {
     uint32_t T[NW], S[NW], Ph[NW], Mh[NW];
     EB_UNROLL
     for (int w = 0; w < NW; ++w) T[w] = Eq[w] & Pv[w];
@@ -177,19 +250,19 @@ EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[
         Ph[w] = Mv[w] | ~(Xh | Pv[w]);
         Mh[w] = Pv[w] & Xh;
     }
-    // the last query row is bit 31 of the last word (top padding, see eb_common.h)
-    score += (int)(Ph[NW - 1] >> 31) - (int)(Mh[NW - 1] >> 31);
     if (phOut) {  // matrix-storing sweeps keep the unshifted horizontal +1 deltas for the traceback
         EB_UNROLL
         for (int w = 0; w < NW; ++w) phOut[w] = Ph[w];
     }
+    uint32_t Phs[NW], Mhs[NW];
+    ShiftChain<NW>::run(Phs, Ph, up);
+    ShiftChain<NW>::run(Mhs, Mh, down);
+    if (TOP_ONE) Phs[0] |= 1u;
     EB_UNROLL
-    for (int w = NW - 1; w >= 0; --w) {
-        const uint32_t Phs = w ? funnel_l1(Ph[w - 1 < 0 ? 0 : w - 1], Ph[w]) : ((Ph[0] << 1) | (TOP_ONE ? 1u : 0u));
-        const uint32_t Mhs = w ? funnel_l1(Mh[w - 1 < 0 ? 0 : w - 1], Mh[w]) : (Mh[0] << 1);
+    for (int w = 0; w < NW; ++w) {
         const uint32_t Xv = Eq[w] | Mv[w];
-        Pv[w] = Mhs | ~(Xv | Phs);
-        Mv[w] = Phs & Xv;
+        Pv[w] = Mhs[w] | ~(Xv | Phs[w]);
+        Mv[w] = Phs[w] & Xv;
     }
 }
 
@@ -197,10 +270,11 @@ EB_HD void k1_step(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[
 template <int NW>
 struct K1State {
     uint32_t Pv[NW], Mv[NW];
-    int score;  // D[m-1][c] of the last column swept
+    int up, down;  // D[m-1][c] of the last column swept = up - down
     int best;   // running minimum (starts at the bound sentinel)
     int cnt;    // columns attaining best so far
-    int first, last;  // RANGE mode: first / last column at or below the threshold
+    int first, last;  // RANGE mode: the open candidate range (cnt columns; 0 = none open)
+    int emitted;      // RANGE mode: ranges written to the list so far
 };
 
 template <int NW>
@@ -211,16 +285,49 @@ EB_HD void k1_init(K1State<NW>& st, int m, int kInit) {
         st.Pv[w] = init_pv_word(w, off);
         st.Mv[w] = 0;
     }
-    st.score = m;  // D[m-1][-1] = m  (ref cpp:576, 760)
+    st.up = m;  // D[m-1][-1] = m  (ref cpp:576, 760)
+    st.down = 0;
     st.best = kInit;
     st.cnt = 0;
     st.first = st.last = 0;
+    st.emitted = 0;
+}
+
+// RANGE mode (candidate filter): the columns whose prefix score is at or below the fixed threshold
+// st.best are reported as ranges {read slot, first, last} appended to a list (the Ovf array of the
+// launch: rec = slot, score = first, pos = last).  A range is closed when the next candidate lies more
+// than K1_RANGE_GAP columns after its last or K1_RANGE_SPAN after its first one.  A thread that has
+// written K1_RANGE_MAX ranges appends the marker {slot, -1, -1} and stops recording: the host hands
+// such a read to the next stage.
+template <int NW>
+EB_HD void k1_range_flush(K1State<NW>& st, int slot, Ovf* list, int* listCount, int listCap) {
+    if (st.cnt == 0) return;
+    int i = atomic_add_int(listCount, 1);
+    if (i < listCap) {
+        list[i].rec = slot;
+        list[i].score = st.first;
+        list[i].pos = st.last;
+    }
+    st.cnt = 0;
+    if (++st.emitted >= K1_RANGE_MAX) {
+        i = atomic_add_int(listCount, 1);
+        if (i < listCap) {
+            list[i].rec = slot;
+            list[i].score = -1;
+            list[i].pos = -1;
+        }
+        st.best = -1;  // scores are never negative: nothing is recorded any more
+    }
 }
 
 // Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
 template <int NW, bool RANGE = false>
 EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
-    if (RANGE) {  // candidate filter: every column at or below the fixed threshold, as a range
+    if (RANGE) {  // candidate filter: recIdx is the read slot, ovf the range list
+        if (st.cnt > 0 && (column - st.last > K1_RANGE_GAP || column - st.first > K1_RANGE_SPAN)) {
+            k1_range_flush<NW>(st, recIdx, ovf, ovfCount, ovfCap);
+            if (st.best < 0) return;
+        }
         if (st.cnt == 0) st.first = column;
         st.last = column;
         st.cnt++;
@@ -271,8 +378,8 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
         for (int j = 0; j < 4; ++j) {
             uint32_t Eq[NW];
             acc.load(syms.read1(i + j), Eq);
-            k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
-            sc[j] = st.score;
+            k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.up, st.down);
+            sc[j] = st.up - st.down;
         }
         if (TRACK) {
             int lo = sc[0] < sc[1] ? sc[0] : sc[1];
@@ -288,8 +395,8 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
     for (; i < count; ++i) {  // tail
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
-        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.score);
-        if (TRACK && st.score <= st.best) k1_event<NW, RANGE>(st, st.score, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+        k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.up, st.down);
+        if (TRACK && st.up - st.down <= st.best) k1_event<NW, RANGE>(st, st.up - st.down, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
     }
 }
 
@@ -318,17 +425,6 @@ EB_HD void k1_build_peq(Acc& acc, const uint8_t* q, int m, int mode, int ncodes,
     }
 }
 
-// RANGE mode result: the chunks of one read merge on the device into ONE record (zero-initialised by
-// the host): cnt = number of columns at or below the threshold, pos[0] = INT_MAX - first such column,
-// pos[1] = last such column + 1.
-template <int NW>
-EB_HD void k1_range_commit(const K1State<NW>& st, Rec* rec) {
-    if (st.cnt <= 0) return;
-    atomic_add_int(&rec->cnt, st.cnt);
-    atomic_max_int(&rec->pos[0], 0x7fffffff - st.first);
-    atomic_max_int(&rec->pos[1], st.last + 1);
-}
-
 // Chunk geometry of a K1 launch: chunk j owns columns [cs, ce) and starts sweeping at hs.
 struct K1Chunk {
     int hs, cs, ce;
@@ -355,16 +451,16 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     const int pair = p.readList[slot];
     const int m = p.prefixLen > 0 ? p.prefixLen : p.qlen[pair];
     const uint8_t* q = p.qcodes + p.qoff[pair];
-    const int recIdx = p.rangeMode ? slot : chunk * p.numReads + slot;
-    Rec* rec = p.recs + recIdx;
+    const int recIdx = chunk * p.numReads + slot;
+    Rec* rec = p.rangeMode ? nullptr : p.recs + recIdx;
     k1_build_peq<NW>(acc, q, m, p.mode, p.ncodes, p.eqtab);
     K1State<NW> st;
     k1_init<NW>(st, m, p.kInit[slot]);
     const K1Chunk g = k1_chunk(p, chunk);
     if (p.mode == MODE_HW && p.rangeMode) {
-        k1_columns<NW, false, false, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_columns<NW, false, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        k1_range_commit<NW>(st, rec);
+        k1_columns<NW, false, false, true>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, slot, p.ovf, p.ovfCount, p.ovfCap);
+        k1_columns<NW, false, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, slot, p.ovf, p.ovfCount, p.ovfCap);
+        k1_range_flush<NW>(st, slot, p.ovf, p.ovfCount, p.ovfCap);
         return;
     } else if (p.mode == MODE_HW) {
         k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + g.hs}, g.cs - g.hs, g.hs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
@@ -373,7 +469,7 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
         k1_columns<NW, true, true>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
     } else {
         k1_columns<NW, true, false>(st, acc, PtrSyms{p.tcodes + g.cs}, g.ce - g.cs, g.cs, rec, recIdx, p.ovf, p.ovfCount, p.ovfCap);
-        st.best = st.score;  // NW: the bottom-right cell (ref cpp:916)
+        st.best = st.up - st.down;  // NW: the bottom-right cell (ref cpp:916)
         st.cnt = 1;
         rec->last = p.n - 1;
         rec->pos[0] = p.n - 1;
@@ -417,7 +513,7 @@ EB_HD void lane_job(const LParams& p, int jobIdx, Acc& acc) {
         for (int c = 0; c < J.n; ++c) {
             uint32_t Eq[NW], Ph[NW];
             acc.load(t[c], Eq);
-            k1_step<NW, true>(st.Pv, st.Mv, Eq, st.score, Ph);
+            k1_step<NW, true>(st.Pv, st.Mv, Eq, st.up, st.down, Ph);
             EB_UNROLL
             for (int w = 0; w < NW; ++w) {
                 U2 e;
@@ -442,7 +538,7 @@ EB_HD void lane_job(const LParams& p, int jobIdx, Acc& acc) {
         }
     }
     if (MODE == MODE_NW) {  // the bottom-right cell (ref cpp:916)
-        st.best = st.score;
+        st.best = st.up - st.down;
         st.cnt = 1;
         rec->last = J.n - 1;
         rec->pos[0] = J.n - 1;

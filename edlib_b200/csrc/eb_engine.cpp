@@ -35,6 +35,8 @@ EngineTunables::EngineTunables() {
     k1MinChunk = env_int("EDLIB_B200_K1_MIN_CHUNK", k1MinChunk);
     ovfCap = env_int("EDLIB_B200_OVF_CAP", ovfCap);
     filterK0 = env_int("EDLIB_B200_FILTER_K0", filterK0);
+    filterK1 = env_int("EDLIB_B200_FILTER_K1", filterK1);
+    filterMaxWindows = env_int("EDLIB_B200_FILTER_MAX_WINDOWS", filterMaxWindows);
     filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
     filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
     filterMinTarget = env_int("EDLIB_B200_FILTER_MIN_TARGET", filterMinTarget);
@@ -862,12 +864,10 @@ struct Pass {
             DevBuf<int> dList(be, g), dK(be, g);
             dList.upload(rl.data(), g);
             dK.upload(subK.data(), g);
-            const size_t numRecs = rangeMode ? (size_t)g : (size_t)g * chunks;  // range records merge on the device
-            DevBuf<Rec> dRecs(be, numRecs);
-            be->zero(dRecs.p, numRecs * sizeof(Rec));
-            DevBuf<Ovf> dOvf(be, (size_t)std::max(cap, 1));
+            const size_t numRecs = rangeMode ? 0 : (size_t)g * chunks;  // range mode reports through the list only
+            DevBuf<Rec> dRecs(be, std::max<size_t>(numRecs, 1));
+            if (numRecs) be->zero(dRecs.p, numRecs * sizeof(Rec));
             DevBuf<int> dCount(be, 1);
-            be->zero(dCount.p, sizeof(int));
             K1Params kp;
             memset(&kp, 0, sizeof(kp));
             kp.tcodes = p->dSeq.p + tg.off;
@@ -885,24 +885,33 @@ struct Pass {
             kp.chunkLen = chunkLen;
             kp.halo = 64 * nwL;
             kp.recs = dRecs.p;
-            kp.ovf = dOvf.p;
             kp.ovfCount = dCount.p;
-            kp.ovfCap = cap;
             kp.prefixLen = prefixLen;
             kp.rangeMode = rangeMode;
-            be->launch_k1(kp, nwL);
-            outRecs.resize(numRecs);
-            dRecs.download(outRecs.data(), outRecs.size());
-            stats.d2hBytes += (long long)outRecs.size() * (long long)sizeof(Rec);
-            outOvf.clear();
-            if (cap > 0) {
+            for (;;) {
+                DevBuf<Ovf> dOvf(be, (size_t)std::max(cap, 1));
+                be->zero(dCount.p, sizeof(int));
+                kp.ovf = dOvf.p;
+                kp.ovfCap = cap;
+                be->launch_k1(kp, nwL);
+                outOvf.clear();
+                if (cap <= 0) break;
                 int count = 0;
                 dCount.download(&count, 1);
-                if (count > cap) throw std::runtime_error("internal: end-location list larger than counted");
+                stats.d2hBytes += 4;
+                if (count > cap) {
+                    if (!rangeMode) throw std::runtime_error("internal: end-location list larger than counted");
+                    cap = count;  // range list overflow: repeat with the exact size
+                    continue;
+                }
                 outOvf.resize(count);
                 if (count) dOvf.download(outOvf.data(), count);
-                stats.d2hBytes += (long long)count * (long long)sizeof(Ovf) + 4;
+                stats.d2hBytes += (long long)count * (long long)sizeof(Ovf);
+                break;
             }
+            outRecs.resize(numRecs);
+            if (numRecs) dRecs.download(outRecs.data(), outRecs.size());
+            stats.d2hBytes += (long long)outRecs.size() * (long long)sizeof(Rec);
         };
 
         // Merge the chunks of every read: the minimum wins; its columns are the inline positions
@@ -963,123 +972,201 @@ struct Pass {
             stats.k1Cells += (long long)m * n;
         }
 
-        // ---- candidate filter (HW): prefix sweep, then windows around the candidates ----------
+        // ---- candidate filter (HW): prefix sweeps, then windows around the candidates -----------
+        // One stage over the reads `in` (indices into `list`): a sweep of the first P rows of every read
+        // reports the target ranges where that prefix matches within t = min(K0, bound); the whole read
+        // is then swept over one window per range.  A read is decided when a window holds a distance
+        // <= t (or when t is the caller's bound and none does).  Undecided reads go to `next` (a longer
+        // prefix or the plain sweep), reads with long end-location lists to `direct`.
         std::vector<int> direct;  // reads that take the plain full sweep
         direct.reserve(G);
-        const int P = 64;
-        if (mode == MODE_HW && tun.filterK0 > 0 && n >= tun.filterMinTarget) {
+        auto filter_stage = [&](int P, int K0, const std::vector<int>& in, std::vector<int>& next) {
             std::vector<int> cand, thr;
-            for (int s = 0; s < G; ++s) {
-                if (p->qlen[list[s]] >= std::max(tun.filterMinLen, P + 1)) {
+            const int minLen = std::max(tun.filterMinLen * P / 64, P + 1);
+            for (int s : in) {
+                if (p->qlen[list[s]] >= minLen) {
                     cand.push_back(s);
-                    thr.push_back(std::min(tun.filterK0, bound[s]));
+                    thr.push_back(std::min(K0, bound[s]));
                 } else {
-                    direct.push_back(s);
+                    next.push_back(s);
                 }
             }
-            if (!cand.empty()) {
-                int chunksA = 1, chunkLenA = 0;
-                geometry((int)cand.size(), 2, chunksA, chunkLenA);
-                std::vector<Rec> ra;
-                std::vector<Ovf> none;
-                trace.mark("compute: classify");
-                launch(cand, thr, 2, chunksA, chunkLenA, 0, P, 1, ra, none);
-                trace.mark("filter: prefix sweep");
-                const int g = (int)cand.size();
-                std::vector<int> vSlot, vPair, vK, vWs, vLen, vTf;  // windows to verify
-                auto undecided = [&](int s, int t) {  // the filter cannot decide: bound above its threshold?
-                    if (t == bound[s]) {
-                        best[list[s]] = 0x7fffffff;   // nothing within the caller's k: final
-                        cnt[list[s]] = 0;
-                        stats.filterDecided++;
-                    } else {
-                        direct.push_back(s);
-                        stats.filterFallback++;
+            if (cand.empty()) return;
+            const int g = (int)cand.size();
+            int chunksA = 1, chunkLenA = 0;
+            geometry(g, P / 32, chunksA, chunkLenA);
+            std::vector<Rec> none;
+            std::vector<Ovf> ranges;
+            launch(cand, thr, P / 32, chunksA, chunkLenA, (int)std::min<long long>(16LL * g + 4096, 1LL << 28), P, 1, none, ranges);
+            trace.mark("filter: prefix sweep");
+            auto undecided = [&](int s, int t) {  // no distance <= t exists: final if t is the caller's bound
+                if (t == bound[s]) {
+                    best[list[s]] = 0x7fffffff;
+                    cnt[list[s]] = 0;
+                    stats.filterDecided++;
+                } else {
+                    next.push_back(s);
+                }
+            };
+            // ranges of every read, ascending (the list is in completion order)
+            std::vector<int> start(g + 1, 0);
+            std::vector<char> saturated(g, 0);
+            for (const Ovf& o : ranges) {
+                if (o.score < 0) saturated[o.rec] = 1;
+                else start[o.rec + 1]++;
+            }
+            for (int i = 0; i < g; ++i) start[i + 1] += start[i];
+            std::vector<std::pair<int, int>> rg(start[g]);
+            {
+                std::vector<int> fill(start.begin(), start.end() - 1);
+                for (const Ovf& o : ranges)
+                    if (o.score >= 0) rg[fill[o.rec]++] = std::make_pair(o.score, o.pos);
+            }
+            std::vector<int> vOwner, vPair, vK, vWs, vLen, vTf;  // windows to verify
+            std::vector<int> wFirst(g + 1, 0);
+            for (int i = 0; i < g; ++i) {
+                wFirst[i] = (int)vOwner.size();
+                const int s = cand[i];
+                const int pair = list[s], m = p->qlen[pair], t = thr[i];
+                if (saturated[i]) {
+                    next.push_back(s);
+                    continue;
+                }
+                if (start[i] == start[i + 1]) {
+                    undecided(s, t);
+                    continue;
+                }
+                std::sort(rg.begin() + start[i], rg.begin() + start[i + 1]);
+                // An alignment with distance d <= t ending at column e passes, after its first P rows,
+                // through a column c' with prefix score <= d and e in [c'+(m-P)-d, c'+(m-P)+d]: the end
+                // columns to examine are [first+(m-P)-t, last+(m-P)+t] of every range.  Ranges close to
+                // each other share one window; tracked columns of successive windows are kept disjoint.
+                long long prevHi = -1;
+                int windows = 0;
+                for (int a = start[i]; a < start[i + 1];) {
+                    const int first = rg[a].first;
+                    int last = rg[a].second;
+                    int b = a + 1;
+                    while (b < start[i + 1] && rg[b].first - last <= K1_RANGE_GAP && rg[b].second - first <= tun.filterSpread) {
+                        last = std::max(last, rg[b].second);
+                        ++b;
                     }
-                };
-                for (int i = 0; i < g; ++i) {
-                    const int s = cand[i];
-                    const int pair = list[s], m = p->qlen[pair], t = thr[i];
-                    const Rec& r = ra[(size_t)i];
-                    const long long total = r.cnt;
-                    const int first = 0x7fffffff - r.pos[0], last = r.pos[1] - 1;
-                    // An alignment with distance d <= t ending at column e passes, after its first P rows,
-                    // through a column c' with prefix score <= d and e in [c'+(m-P)-d, c'+(m-P)+d].
-                    const long long lo = (long long)first + (m - P) - t;
+                    a = b;
+                    long long lo = (long long)first + (m - P) - t;
                     long long hi = (long long)last + (m - P) + t;
+                    if (lo <= prevHi) lo = prevHi + 1;
                     if (hi > n - 1) hi = n - 1;
-                    if (total == 0 || lo > hi) {
-                        undecided(s, t);
-                        continue;
-                    }
-                    if (last - first > tun.filterSpread) {
-                        direct.push_back(s);
-                        stats.filterFallback++;
-                        continue;
-                    }
+                    if (lo > hi) continue;
+                    prevHi = hi;
                     const long long ws = std::max<long long>(0, lo - 2LL * m);  // HW restart: exact after 2m columns
-                    vSlot.push_back(s);
+                    vOwner.push_back(i);
                     vPair.push_back(pair);
                     vK.push_back(t + 1);
                     vWs.push_back((int)ws);
                     vLen.push_back((int)(hi - ws + 1));
                     vTf.push_back((int)(lo - ws));
+                    ++windows;
                 }
-                trace.mark("filter: windows planned");
-                const int V = (int)vSlot.size();
-                if (V > 0) {
-                    // Whole reads over their windows, one read per thread (k1w_kernel).
-                    DevBuf<int> dPair(be, V), dK(be, V), dWs(be, V), dLen(be, V), dTf(be, V);
-                    dPair.upload(vPair.data(), V);
-                    dK.upload(vK.data(), V);
-                    dWs.upload(vWs.data(), V);
-                    dLen.upload(vLen.data(), V);
-                    dTf.upload(vTf.data(), V);
-                    DevBuf<Rec> dRecs(be, V);
-                    be->zero(dRecs.p, (size_t)V * sizeof(Rec));
-                    K1WParams wp;
-                    memset(&wp, 0, sizeof(wp));
-                    wp.tcodes = p->dSeq.p + tg.off;
-                    wp.qcodes = p->dSeq.p;
-                    wp.qoff = p->dQoff.p;
-                    wp.qlen = p->dQlen.p;
-                    wp.readList = dPair.p;
-                    wp.kInit = dK.p;
-                    wp.winStart = dWs.p;
-                    wp.winLen = dLen.p;
-                    wp.trackFrom = dTf.p;
-                    wp.numReads = V;
-                    wp.ncodes = p->ncodes;
-                    wp.eqtab = p->hasEq ? p->dEqtab.p : nullptr;
-                    wp.recs = dRecs.p;
-                    be->launch_k1w(wp, nw);
-                    std::vector<Rec> rv(V);
-                    dRecs.download(rv.data(), V);
-                    stats.d2hBytes += (long long)V * (long long)sizeof(Rec);
-                    trace.mark("filter: window sweeps");
-                    for (int j = 0; j < V; ++j) {
-                        const Rec& r = rv[j];
-                        const int s = vSlot[j], t = vK[j] - 1, pair = vPair[j];
-                        if (r.cnt <= 0 || r.best > t) {  // the window minimum is above the threshold
-                            undecided(s, t);
-                            continue;
-                        }
-                        if (r.cnt > KPOS) {  // long end-location list: the plain sweep collects it
-                            direct.push_back(s);
-                            stats.filterFallback++;
-                            continue;
-                        }
-                        stats.filterDecided++;
-                        best[pair] = r.best;
-                        cnt[pair] = r.cnt;
-                        posStart[pair] = (long long)posPool.size();
-                        for (int q = 0; q < r.cnt; ++q) posPool.push_back(r.pos[q]);
-                        posLen[pair] = r.cnt;
-                    }
+                if (windows == 0) {
+                    undecided(s, t);
+                } else if (windows > tun.filterMaxWindows) {
+                    vOwner.resize(wFirst[i]);
+                    vPair.resize(wFirst[i]);
+                    vK.resize(wFirst[i]);
+                    vWs.resize(wFirst[i]);
+                    vLen.resize(wFirst[i]);
+                    vTf.resize(wFirst[i]);
+                    next.push_back(s);
                 }
             }
-        } else {
-            for (int s = 0; s < G; ++s) direct.push_back(s);
+            wFirst[g] = (int)vOwner.size();
+            trace.mark("filter: windows planned");
+            const int V = (int)vOwner.size();
+            if (trace.on) {
+                int sat = 0;
+                for (char c : saturated) sat += c;
+                fprintf(stderr, "[edlib_b200] filter stage P=%d: %d reads, %zu ranges, %d saturated, %d windows, %zu to the next stage\n",
+                        P, g, rg.size(), sat, V, next.size());
+            }
+            if (V == 0) return;
+            // Whole reads over their windows, one window per thread (k1w_kernel).
+            DevBuf<int> dPair(be, V), dK(be, V), dWs(be, V), dLen(be, V), dTf(be, V);
+            dPair.upload(vPair.data(), V);
+            dK.upload(vK.data(), V);
+            dWs.upload(vWs.data(), V);
+            dLen.upload(vLen.data(), V);
+            dTf.upload(vTf.data(), V);
+            DevBuf<Rec> dRecs(be, V);
+            be->zero(dRecs.p, (size_t)V * sizeof(Rec));
+            K1WParams wp;
+            memset(&wp, 0, sizeof(wp));
+            wp.tcodes = p->dSeq.p + tg.off;
+            wp.qcodes = p->dSeq.p;
+            wp.qoff = p->dQoff.p;
+            wp.qlen = p->dQlen.p;
+            wp.readList = dPair.p;
+            wp.kInit = dK.p;
+            wp.winStart = dWs.p;
+            wp.winLen = dLen.p;
+            wp.trackFrom = dTf.p;
+            wp.numReads = V;
+            wp.ncodes = p->ncodes;
+            wp.eqtab = p->hasEq ? p->dEqtab.p : nullptr;
+            wp.recs = dRecs.p;
+            be->launch_k1w(wp, nw);
+            std::vector<Rec> rv(V);
+            dRecs.download(rv.data(), V);
+            stats.d2hBytes += (long long)V * (long long)sizeof(Rec);
+            trace.mark("filter: window sweeps");
+            for (int i = 0; i < g; ++i) {
+                if (wFirst[i] == wFirst[i + 1]) continue;
+                const int s = cand[i], t = thr[i], pair = list[s];
+                int b = 0x7fffffff;
+                for (int j = wFirst[i]; j < wFirst[i + 1]; ++j)
+                    if (rv[j].cnt > 0 && rv[j].best < b) b = rv[j].best;
+                if (b > t) {  // every window minimum is above the threshold
+                    undecided(s, t);
+                    continue;
+                }
+                bool longList = false;
+                int total = 0;
+                for (int j = wFirst[i]; j < wFirst[i + 1]; ++j)
+                    if (rv[j].cnt > 0 && rv[j].best == b) {
+                        total += rv[j].cnt;
+                        if (rv[j].cnt > KPOS) longList = true;
+                    }
+                if (longList) {  // long end-location list: the plain sweep collects it
+                    direct.push_back(s);
+                    continue;
+                }
+                stats.filterDecided++;
+                best[pair] = b;
+                cnt[pair] = total;
+                posStart[pair] = (long long)posPool.size();
+                for (int j = wFirst[i]; j < wFirst[i + 1]; ++j)
+                    if (rv[j].cnt > 0 && rv[j].best == b)
+                        for (int q = 0; q < rv[j].cnt; ++q) posPool.push_back(rv[j].pos[q]);
+                posLen[pair] = total;
+            }
+        };
+
+        {
+            std::vector<int> cur(G);
+            for (int s = 0; s < G; ++s) cur[s] = s;
+            if (mode == MODE_HW && n >= tun.filterMinTarget) {
+                trace.mark("compute: classify");
+                const int stageP[2] = {32, 64};
+                const int stageK[2] = {tun.filterK1, tun.filterK0};
+                for (int st = 0; st < 2; ++st) {
+                    if (stageK[st] <= 0 || cur.empty()) continue;
+                    if (stageP[st] / 32 >= nw) continue;  // the prefix must be shorter than the read's word class
+                    std::vector<int> next;
+                    filter_stage(stageP[st], stageK[st], cur, next);
+                    cur.swap(next);
+                }
+            }
+            for (int s : cur) direct.push_back(s);
+            if (mode == MODE_HW && n >= tun.filterMinTarget) stats.filterFallback += (long long)direct.size();
         }
 
         trace.mark("filter: collect");

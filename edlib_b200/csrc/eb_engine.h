@@ -62,12 +62,15 @@ struct EngineTunables {
     int k1MinChunk = 1024;        // smallest target chunk (columns) when one HW sweep is split
     int ovfCap = 1 << 20;         // overflow entries per launch before the exact-size retry
     size_t sliceBytes = 1ull << 30;  // device memory budget of one slice of W jobs
-    // Candidate filter for HW sweeps of reads over a shared target (0 disables): a 64-row prefix
-    // sweep finds the columns where the prefix matches within filterK0; only windows around them
-    // are swept with the whole read; reads the filter cannot decide take the plain full sweep.
-    int filterK0 = 12;
-    int filterMinLen = 96;        // shortest query worth filtering
-    int filterSpread = 1024;      // widest candidate range verified as one window
+    // Candidate filter for HW sweeps of reads over a shared target, two stages (0 disables one): a
+    // 32-row prefix sweep finds the target ranges where the prefix matches within filterK1, a 64-row
+    // one (for the reads the first stage cannot decide) within filterK0; only windows around those
+    // ranges are swept with the whole read; reads no stage decides take the plain full sweep.
+    int filterK1 = 8;
+    int filterK0 = 16;
+    int filterMinLen = 96;        // shortest query worth the 64-row stage (scaled by P/64 for the other)
+    int filterSpread = 1024;      // widest group of candidate ranges verified as one window
+    int filterMaxWindows = 32;    // windows per read and stage before the next stage takes the read
     int filterMinTarget = 65536;  // shortest target worth filtering
     EngineTunables();             // reads EDLIB_B200_* environment overrides (used by tests)
 };

@@ -205,8 +205,8 @@ __global__ void k1_kernel(const K1Params p) {
         const int m = p.prefixLen > 0 ? p.prefixLen : p.qlen[pair];
         k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE, p.ncodes, p.eqtab);
         k1_init<NW>(st, m, p.kInit[slot]);
-        recIdx = RANGE ? slot : chunk * p.numReads + slot;
-        rec = p.recs + recIdx;
+        recIdx = RANGE ? slot : chunk * p.numReads + slot;  // RANGE: events carry the read slot
+        rec = RANGE ? nullptr : p.recs + recIdx;
     }
 
     for (int i = 0; i < numTiles; ++i) {
@@ -229,10 +229,10 @@ __global__ void k1_kernel(const K1Params p) {
         __syncthreads();  // everyone is done with tile i before its buffer is refilled
     }
     if (active && RANGE) {
-        k1_range_commit<NW>(st, rec);
+        k1_range_flush<NW>(st, slot, p.ovf, p.ovfCount, p.ovfCap);
     } else if (active) {
         if (MODE == MODE_NW) {
-            st.best = st.score;
+            st.best = st.up - st.down;
             st.cnt = 1;
             rec->last = p.n - 1;
             rec->pos[0] = p.n - 1;
@@ -537,15 +537,16 @@ struct CudaBackend : Backend {
         *residentCtas = perSm * sms;
         if (ncodes < 1023) shapeCache[key] = block | ((perSm * sms) << 12);
     }
-    // candidate-filter sweep: 64-row prefixes (two words), HW, range recording
-    void launch_k1_range(const K1Params& p) {
+    // candidate-filter sweeps: 32- or 64-row prefixes (one or two words), HW, range recording
+    template <int NW>
+    void launch_k1_range_t(const K1Params& p) {
         int block;
         size_t smem;
-        k1_block(2, p.ncodes, &block, &smem);
+        k1_block(NW, p.ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
-        EB_CUDA(cudaFuncSetAttribute(k1_kernel<2, MODE_HW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1_kernel<2, MODE_HW, true><<<grid, block, smem, stream>>>(p);
+        EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE_HW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_kernel<NW, MODE_HW, true><<<grid, block, smem, stream>>>(p);
         check_launch("k1 range");
     }
     template <int NW>
@@ -557,8 +558,9 @@ struct CudaBackend : Backend {
     void launch_k1(const K1Params& p, int nw) override {
         Scope s(this, "k1");
         if (p.rangeMode) {
-            if (nw != 2 || p.mode != MODE_HW) throw std::runtime_error("range mode needs the 2-word HW kernel");
-            launch_k1_range(p);
+            if ((nw != 1 && nw != 2) || p.mode != MODE_HW) throw std::runtime_error("range mode needs the 1- or 2-word HW kernel");
+            if (nw == 1) launch_k1_range_t<1>(p);
+            else launch_k1_range_t<2>(p);
             return;
         }
         switch (nw) {

@@ -111,18 +111,27 @@ def path_cases(seed, count):
 
 
 def filter_cases(seed, count):
-    """HW batches of reads (>= 96 bp) over one shared target: clean hits, hits above the filter
-    threshold, unrelated reads, exact copies inside a repeated target segment (several far-apart
-    candidate clusters), explicit and free k -- every branch of the candidate filter."""
+    """HW batches of reads (>= 48 bp) over one shared target: clean hits, hits above the filter
+    thresholds, unrelated reads, exact copies inside repeated target segments (several far-apart or
+    neighbouring candidate ranges, equal-score hits in different windows), tandem-repeat targets
+    (range lists that saturate), explicit and free k -- every branch of the two-stage candidate filter."""
     rng = random.Random(seed)
     alpha = b"ACGT"
     for _ in range(count):
-        t = rand_seq(rng, rng.choice([3000, 8000, 20000]), alpha)
-        if rng.random() < 0.3:
-            t = t[:1500] + t[100:700] + t[1500:]
+        shape = rng.random()
+        if shape < 0.12:  # tandem repeat with a few mutations: candidates everywhere
+            unit = rand_seq(rng, rng.choice([5, 13, 31, 50]), alpha)
+            t = mutate(rng, unit * (rng.choice([6000, 20000]) // len(unit)), 0.01, alpha)
+        else:
+            t = rand_seq(rng, rng.choice([3000, 8000, 20000]), alpha)
+            if shape < 0.45:  # a segment copied to several places (some close to each other)
+                seg = t[100:100 + rng.choice([200, 600])]
+                for _c in range(rng.choice([1, 2, 4])):
+                    at = rng.randrange(0, len(t))
+                    t = t[:at] + (mutate(rng, seg, 0.01, alpha) if rng.random() < 0.5 else seg) + t[at:]
         qs = []
         for _ in range(rng.choice([8, 40, 100])):
-            L = rng.choice([96, 100, 128, 150, 150, 200, 256])
+            L = rng.choice([48, 64, 80, 96, 100, 128, 150, 150, 200, 256])
             r = rng.random()
             if r < 0.7:
                 a = rng.randrange(0, len(t) - L - 10)
@@ -132,8 +141,8 @@ def filter_cases(seed, count):
             else:
                 a = rng.randrange(0, max(1, len(t) - L))
                 q = t[a:a + L]
-            if len(q) < 96:
-                q = q + rand_seq(rng, 96 - len(q), alpha)
+            if len(q) < L:
+                q = q + rand_seq(rng, L - len(q), alpha)
             qs.append(q)
         yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 3, 10, 40]), mode=2, task=rng.randrange(3), eqs=None)
 

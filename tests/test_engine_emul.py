@@ -76,8 +76,9 @@ def test_candidate_filter_all_branches():
         "lib = T.load_emul()\n"
         "print(parity.run_batches(lib, 16, 25, gen=cases.filter_cases))\n"
     ) % (REPO, os.path.join(REPO, "tests"))
-    for extra in ({}, {"EDLIB_B200_FILTER_K0": "4", "EDLIB_B200_FILTER_SPREAD": "64", "EDLIB_B200_K1_MIN_CHUNK": "64",
-                       "EDLIB_EMUL_SMS": "64"}):
+    for extra in ({}, {"EDLIB_B200_FILTER_K0": "4", "EDLIB_B200_FILTER_K1": "2", "EDLIB_B200_FILTER_SPREAD": "64",
+                       "EDLIB_B200_FILTER_MAX_WINDOWS": "2", "EDLIB_B200_K1_MIN_CHUNK": "64", "EDLIB_EMUL_SMS": "64"},
+                  {"EDLIB_B200_FILTER_K1": "0"}, {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "12"}):
         env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 500
