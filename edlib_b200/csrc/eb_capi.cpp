@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -239,6 +240,16 @@ EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {
     s->wCells = g_engine->stats.wCells;
     s->filterDecided = g_engine->stats.filterDecided;
     s->filterFallback = g_engine->stats.filterFallback;
+}
+
+EDLIB_API int edlibB200LastKernelReport(char* buf, int bufLen) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!buf || bufLen <= 0) return 0;
+    const std::string r = g_engine ? g_engine->stats.kernelReport : std::string();
+    const int n = (int)std::min<size_t>(r.size(), (size_t)bufLen - 1);
+    memcpy(buf, r.data(), (size_t)n);
+    buf[n] = 0;
+    return (int)r.size();
 }
 
 }  // extern "C"

@@ -36,6 +36,14 @@ struct Rec {
     int pos[KPOS];  // first KPOS such columns, ascending
 };
 
+// Record of one window sweep (K1W): same header as Rec, more inline positions -- windows are short and the
+// reads that tie on many end columns would otherwise need a whole-target sweep.
+constexpr int KPOSW = 12;
+struct WinRec {
+    int best, cnt, last, rsv;
+    int pos[KPOSW];
+};
+
 // Overflow entry for columns beyond KPOS.  The list is only armed (ovfCap > 0) in the second
 // pass over the few sweeps that have more than KPOS end positions; that pass starts from the
 // known minimum, so every entry is a final position and the capacity is known exactly.
@@ -94,7 +102,7 @@ struct K1WParams {
     int numReads;
     int ncodes;
     const uint8_t* eqtab;
-    Rec* recs;               // [numReads]; positions are absolute target columns
+    WinRec* recs;            // [numReads]; positions are absolute target columns
 };
 
 // L: lane-per-alignment sweep of a short query over its own target (any mode).
@@ -210,6 +218,63 @@ struct SplitParams {
     int numNodes;
     const int* cols;
     SplitOut* out;
+};
+
+// Seed index of a target (candidate filter, first stage): a CSR table from the hash bucket of every
+// L-symbol substring of the target to the positions where such substrings start.  Build: count
+// (seed_count_item), exclusive scan of the counts (Backend::launch_scan), fill (seed_fill_item).
+struct SeedIndexParams {
+    const uint8_t* tcodes;   // encoded target
+    int n;
+    int L;                   // seed length
+    int bits;                // 2^bits buckets
+    int* bucketStart;        // [2^bits + 1] counts, then their exclusive prefix sums (last = n - L + 1)
+    int* cursor;             // [2^bits] fill cursors, zeroed by the host
+    int* positions;          // [n - L + 1]
+};
+#define SEED_MAX_CAND 256    // candidate end columns per read before the read is passed on as saturated
+enum SeedState : int { SEED_NONE = 0, SEED_WINDOWS = 1, SEED_SATURATED = 2, SEED_LONG_LIST = 3 };
+struct SeedPlan {
+    int first, count;        // the read's windows in the job arrays
+    int state;               // SeedState
+};
+// Per read: t+1 disjoint seeds are looked up; every exact occurrence yields the expected end column
+// of the alignment it belongs to; neighbouring ones share a window (eb_core.h: seed_plan_read).
+struct SeedPlanParams {
+    const uint8_t* tcodes;
+    int n;
+    const uint8_t* qcodes;
+    const uint64_t* qoff;
+    const int* qlen;
+    const int* readList;     // [numReads] pair indices
+    const int* thr;          // [numReads] threshold t; (t + 1) * L <= query length (t < 0: read skipped)
+    int numReads;
+    int L, bits;
+    const int* bucketStart;
+    const int* positions;
+    int maxBucket;           // buckets longer than this saturate the read (repeats)
+    int spread;              // widest group of candidates verified as one window
+    // outputs: K1W jobs (K1WParams arrays) and the per-read plan
+    int* winPair;
+    int* winK;
+    int* winStart;
+    int* winLen;
+    int* winTf;
+    int winCap;
+    int* winCount;           // zeroed by the host; may exceed winCap (nothing is written beyond it)
+    SeedPlan* plan;          // [numReads]
+};
+// Per read: minimum over its windows -> out[slot] (rsv = SeedState: SEED_WINDOWS means decided with
+// best/cnt/pos filled, SEED_NONE that no distance <= t exists).
+struct WinReduceParams {
+    const SeedPlan* plan;
+    const int* thr;
+    const WinRec* winRecs;
+    int numReads;
+    Rec* out;                // cnt > KPOS: positions KPOS.. are extra[out.last ...]
+    int* extra;
+    int* extraCount;         // zeroed by the host
+    int extraCap;
 };
 
 // Presence / alphabet kernels.

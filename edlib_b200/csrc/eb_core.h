@@ -321,7 +321,8 @@ EB_HD void k1_range_flush(K1State<NW>& st, int slot, Ovf* list, int* listCount, 
 }
 
 // Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
-template <int NW, bool RANGE = false>
+// CAP inline positions: KPOS for Rec, KPOSW when `rec` is really the header of a WinRec.
+template <int NW, bool RANGE = false, int CAP = KPOS>
 EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     if (RANGE) {  // candidate filter: recIdx is the read slot, ovf the range list
         if (st.cnt > 0 && (column - st.last > K1_RANGE_GAP || column - st.first > K1_RANGE_SPAN)) {
@@ -337,8 +338,9 @@ EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx
         st.best = score;
         st.cnt = 0;
     }
-    if (st.cnt < KPOS) {
-        rec->pos[st.cnt] = column;
+    if (st.cnt < CAP) {
+        int* pos = rec->pos;
+        pos[st.cnt] = column;
     } else if (ovfCap > 0) {  // second pass only: the list then holds final positions exclusively
         const int slot = atomic_add_int(ovfCount, 1);
         if (slot < ovfCap) {
@@ -368,7 +370,7 @@ struct RevSyms {
 // running minimum and its columns are recorded; without it only the state advances (halo
 // columns of a chunk).  Columns go four at a time: the four last-row scores stay in registers
 // and are compared against the running minimum once per group (events are rare).
-template <int NW, bool TOP_ONE, bool TRACK, bool RANGE = false, class Acc, class Syms>
+template <int NW, bool TOP_ONE, bool TRACK, bool RANGE = false, int CAP = KPOS, class Acc, class Syms>
 EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int count, int cAbs,
                       Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     int i = 0;
@@ -388,7 +390,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
             if (lo <= st.best) {
                 EB_UNROLL
                 for (int j = 0; j < 4; ++j)
-                    if (sc[j] <= st.best) k1_event<NW, RANGE>(st, sc[j], cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
+                    if (sc[j] <= st.best) k1_event<NW, RANGE, CAP>(st, sc[j], cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
             }
         }
     }
@@ -396,7 +398,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
         k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.up, st.down);
-        if (TRACK && st.up - st.down <= st.best) k1_event<NW, RANGE>(st, st.up - st.down, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+        if (TRACK && st.up - st.down <= st.best) k1_event<NW, RANGE, CAP>(st, st.up - st.down, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
     }
 }
 
@@ -484,15 +486,189 @@ template <int NW, class Acc>
 EB_HD void k1w_thread(const K1WParams& p, int slot, Acc& acc) {
     const int pair = p.readList[slot];
     const int m = p.qlen[pair];
-    Rec* rec = p.recs + slot;
+    Rec* rec = reinterpret_cast<Rec*>(p.recs + slot);  // header of the WinRec; KPOSW positions follow
     k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE_HW, p.ncodes, p.eqtab);
     K1State<NW> st;
     k1_init<NW>(st, m, p.kInit[slot]);
     const int ws = p.winStart[slot], tf = p.trackFrom[slot], len = p.winLen[slot];
-    k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + ws}, tf, ws, rec, slot, nullptr, nullptr, 0);
-    k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
+    k1_columns<NW, false, false, false, KPOSW>(st, acc, PtrSyms{p.tcodes + ws}, tf, ws, rec, slot, nullptr, nullptr, 0);
+    k1_columns<NW, false, true, false, KPOSW>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
     rec->best = st.best;
     rec->cnt = st.cnt;
+}
+
+// =============================================================================================
+// Seed stage of the candidate filter (HW, plain symbol equality).  If a read aligns somewhere with
+// d <= t edits, then of any t+1 disjoint pieces of the read at least one is untouched by the edits
+// and occurs verbatim in the target: piece read[a, a+L) == target[p, p+L) puts the end column of that
+// alignment within d of E = p + (m - a) - 1.  So the columns [E-t, E+t] of all exact piece occurrences
+// cover every end column with a distance <= t; the whole read is swept over windows around them
+// (k1w_thread) and the minimum is final when it is <= t.
+// =============================================================================================
+EB_HD uint32_t seed_bucket(const uint8_t* s, int L, int bits) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int i = 0; i < L; ++i) {
+        h ^= s[i];
+        h *= 0x100000001b3ull;
+    }
+    h ^= h >> 29;
+    h *= 0xbf58476d1ce4e5b9ull;
+    h ^= h >> 32;
+    return (uint32_t)h & ((1u << bits) - 1u);
+}
+EB_HD void seed_count_item(const SeedIndexParams& p, int i) { atomic_add_int(p.bucketStart + seed_bucket(p.tcodes + i, p.L, p.bits), 1); }
+EB_HD void seed_fill_item(const SeedIndexParams& p, int i) {
+    const uint32_t b = seed_bucket(p.tcodes + i, p.L, p.bits);
+    p.positions[p.bucketStart[b] + atomic_add_int(p.cursor + b, 1)] = i;
+}
+
+// Windows of one read from its sorted candidate end columns E[0..c): emit == false only counts them.
+EB_HD int seed_windows(const SeedPlanParams& p, const int* E, int c, int m, int t, int pair, int base, bool emit) {
+    long long prevHi = -1;
+    int nW = 0;
+    for (int i = 0; i < c;) {
+        const int first = E[i];
+        int last = first;
+        ++i;
+        while (i < c && E[i] - last <= K1_RANGE_GAP && E[i] - first <= p.spread) last = E[i++];
+        long long lo = (long long)first - t, hi = (long long)last + t;
+        if (lo <= prevHi) lo = prevHi + 1;  // tracked columns of successive windows stay disjoint
+        if (lo < 0) lo = 0;
+        if (hi > p.n - 1) hi = p.n - 1;
+        if (lo > hi) continue;
+        prevHi = hi;
+        // HW restart: an alignment with <= t edits spans at most m + t target columns, so every score <= t
+        // of a tracked column is exact (larger ones may come out larger still, which changes nothing)
+        long long ws = lo - (long long)(m + t);
+        if (ws < 0) ws = 0;
+        if (emit) {
+            const int w = base + nW;
+            p.winPair[w] = pair;
+            p.winK[w] = t + 1;
+            p.winStart[w] = (int)ws;
+            p.winLen[w] = (int)(hi - ws + 1);
+            p.winTf[w] = (int)(lo - ws);
+        }
+        ++nW;
+    }
+    return nW;
+}
+
+EB_HD void seed_plan_read(const SeedPlanParams& p, int slot) {
+    const int pair = p.readList[slot];
+    const int m = p.qlen[pair], t = p.thr[slot];
+    const uint8_t* q = p.qcodes + p.qoff[pair];
+    SeedPlan pl;
+    pl.first = pl.count = 0;
+    pl.state = SEED_NONE;
+    if (t < 0) {  // the host left this read out of the stage
+        pl.state = SEED_SATURATED;
+        p.plan[slot] = pl;
+        return;
+    }
+    int E[SEED_MAX_CAND];
+    int c = 0;
+    const int stride = m / (t + 1);  // >= L: the t+1 pieces are disjoint
+    bool saturated = false;
+    for (int j = 0; j <= t && !saturated; ++j) {
+        const int a = j * stride;
+        const uint32_t b = seed_bucket(q + a, p.L, p.bits);
+        const int s0 = p.bucketStart[b], s1 = p.bucketStart[b + 1];
+        if (s1 - s0 > p.maxBucket) {
+            saturated = true;
+            break;
+        }
+        for (int i = s0; i < s1; ++i) {
+            const int pos = p.positions[i];
+            bool same = true;
+            for (int x = 0; x < p.L; ++x)
+                if (p.tcodes[pos + x] != q[a + x]) {
+                    same = false;
+                    break;
+                }
+            if (!same) continue;  // bucket collision
+            if (c == SEED_MAX_CAND) {
+                saturated = true;
+                break;
+            }
+            E[c++] = pos + (m - a) - 1;
+        }
+    }
+    if (saturated) {
+        pl.state = SEED_SATURATED;
+        p.plan[slot] = pl;
+        return;
+    }
+    for (int i = 1; i < c; ++i) {  // insertion sort: c is small
+        const int v = E[i];
+        int j = i - 1;
+        while (j >= 0 && E[j] > v) {
+            E[j + 1] = E[j];
+            --j;
+        }
+        E[j + 1] = v;
+    }
+    const int nW = seed_windows(p, E, c, m, t, pair, 0, false);
+    if (nW > 0) {
+        const int base = atomic_add_int(p.winCount, nW);
+        if (base + nW <= p.winCap) seed_windows(p, E, c, m, t, pair, base, true);
+        pl.first = base;
+        pl.count = nW;
+        pl.state = SEED_WINDOWS;
+    }
+    p.plan[slot] = pl;
+}
+
+EB_HD void win_reduce_read(const WinReduceParams& p, int slot) {
+    const SeedPlan pl = p.plan[slot];
+    Rec out;
+    out.best = 0x7fffffff;
+    out.cnt = 0;
+    out.last = 0;
+    out.rsv = pl.state;
+    for (int q = 0; q < KPOS; ++q) out.pos[q] = 0;
+    if (pl.state == SEED_WINDOWS) {
+        const int t = p.thr[slot];
+        int b = 0x7fffffff;
+        for (int w = 0; w < pl.count; ++w) {
+            const WinRec& r = p.winRecs[pl.first + w];
+            if (r.cnt > 0 && r.best < b) b = r.best;
+        }
+        if (b > t) {
+            out.rsv = SEED_NONE;  // every window minimum is above the threshold
+        } else {
+            int total = 0;
+            bool longList = false;
+            for (int w = 0; w < pl.count; ++w) {
+                const WinRec& r = p.winRecs[pl.first + w];
+                if (r.cnt <= 0 || r.best != b) continue;
+                if (r.cnt > KPOSW) longList = true;
+                total += r.cnt;
+            }
+            int base = 0;
+            if (!longList && total > KPOS) {
+                base = atomic_add_int(p.extraCount, total - KPOS);
+                if (base + total - KPOS > p.extraCap) longList = true;
+            }
+            if (longList) {
+                out.rsv = SEED_LONG_LIST;
+            } else {
+                int i = 0;
+                for (int w = 0; w < pl.count; ++w) {
+                    const WinRec& r = p.winRecs[pl.first + w];
+                    if (r.cnt <= 0 || r.best != b) continue;
+                    for (int q = 0; q < r.cnt; ++q, ++i) {
+                        if (i < KPOS) out.pos[i] = r.pos[q];
+                        else p.extra[base + i - KPOS] = r.pos[q];
+                    }
+                }
+                out.best = b;
+                out.cnt = total;
+                out.last = base;
+            }
+        }
+    }
+    p.out[slot] = out;
 }
 
 // =============================================================================================

@@ -17,6 +17,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
+#include <functional>
 #include <chrono>
 #include <map>
 #include <stdexcept>
@@ -36,6 +38,8 @@ EngineTunables::EngineTunables() {
     ovfCap = env_int("EDLIB_B200_OVF_CAP", ovfCap);
     filterK0 = env_int("EDLIB_B200_FILTER_K0", filterK0);
     filterK1 = env_int("EDLIB_B200_FILTER_K1", filterK1);
+    filterSeedK = env_int("EDLIB_B200_FILTER_SEED_K", filterSeedK);
+    filterSeedBucket = env_int("EDLIB_B200_FILTER_SEED_BUCKET", filterSeedBucket);
     filterMaxWindows = env_int("EDLIB_B200_FILTER_MAX_WINDOWS", filterMaxWindows);
     filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
     filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
@@ -59,8 +63,37 @@ struct Trace {
     }
 };
 
+// fn(begin, end) over [0, n) on up to 16 host threads (only when every thread gets >= grain items).
+template <class F>
+void parallel_ranges(size_t n, size_t grain, F fn) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthr = std::min<size_t>(std::min<size_t>(16, hw), n / std::max<size_t>(grain, 1));
+    if (nthr <= 1) {
+        fn((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nthr; ++t) th.emplace_back([=]() { fn(n * t / nthr, n * (t + 1) / nthr); });
+    for (auto& x : th) x.join();
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// Host staging memory from the backend (pinned and cached on CUDA): transfers run at full PCIe rate and
+// the host reads / writes it in place.
+template <class T>
+struct HostBuf {
+    Backend* be = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    HostBuf(Backend* b, size_t count) : be(b), p(static_cast<T*>(b->alloc_host(std::max<size_t>(count, 1) * sizeof(T)))), n(count) {}
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+    ~HostBuf() { be->free_host(p); }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
 
 template <class T>
 struct DevBuf {
@@ -248,7 +281,7 @@ Prepared* Engine::prepare(const BatchInput& in) {
             const size_t qBytes = N ? (size_t)(p->qoff[N - 1] + (uint64_t)p->qlen[N - 1]) : 0;
             size_t allBytes = qBytes;
             for (int t = 0; t < T; ++t) allBytes += (size_t)p->tg[t].len;
-            const int nthr = allBytes > (32u << 20) ? (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+            const int nthr = allBytes > (32u << 20) ? (int)std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
             auto copy_item = [&](int it) {
                 if (it < N) {
                     if (p->qlen[it]) memcpy(stage + p->qoff[it], in.queries[it], (size_t)p->qlen[it]);
@@ -294,29 +327,39 @@ Prepared* Engine::prepare(const BatchInput& in) {
         p->dQlen.alloc(be, N);
         p->dQlen.upload(p->qlen.data(), N);
 
-        // byte-presence sets: one per query, one per distinct target, one union for the batch
-        std::vector<MaskItem> items;
-        items.reserve((size_t)N + T);
-        auto add_items = [&](uint64_t off, int len, int dst) {
-            for (int s = 0; s < len; s += 65536) items.push_back(MaskItem{off + (uint64_t)s, std::min(65536, len - s), dst});
-        };
-        for (int i = 0; i < N; ++i) add_items(p->qoff[i], p->qlen[i], i);
-        for (int t = 0; t < T; ++t) add_items(p->tg[t].off, p->tg[t].len, N + t);
+        // byte-presence sets: one per query, one per distinct target, one union for the batch.  Work items
+        // cover at most 65536 bytes each; they are laid out (counts, offsets, fill) on a few host threads
+        // straight into staging memory.
+        auto pieces = [](int len) { return (len + 65535) / 65536; };
+        std::vector<size_t> itemAt((size_t)N + T + 1, 0);
+        parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) itemAt[i + 1] = (size_t)pieces(p->qlen[i]);
+        });
+        for (int t = 0; t < T; ++t) itemAt[(size_t)N + t + 1] = (size_t)pieces(p->tg[t].len);
+        for (size_t i = 0; i < (size_t)N + T; ++i) itemAt[i + 1] += itemAt[i];
+        const size_t numItems = itemAt[(size_t)N + T];
+        HostBuf<MaskItem> items(be, numItems);
+        HostBuf<int> tset(be, (size_t)N);
+        parallel_ranges((size_t)N + T, 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const uint64_t off = i < (size_t)N ? p->qoff[i] : p->tg[i - N].off;
+                const int len = i < (size_t)N ? p->qlen[i] : p->tg[i - N].len;
+                size_t at = itemAt[i];
+                for (int s0 = 0; s0 < len; s0 += 65536) items[at++] = MaskItem{off + (uint64_t)s0, std::min(65536, len - s0), (int)i};
+                if (i < (size_t)N) tset[i] = N + p->tidx[i];
+            }
+        });
         const int unionSet = N + T;
         DevBuf<uint32_t> dMasks(be, (size_t)(N + T + 1) * 8);
         be->zero(dMasks.p, (size_t)(N + T + 1) * 8 * sizeof(uint32_t));
-        DevBuf<MaskItem> dItems(be, items.size());
-        if (!items.empty()) {
-            dItems.upload(items.data(), items.size());
-            MaskParams mp{p->dSeq.p, dItems.p, (int)items.size(), dMasks.p, unionSet};
+        DevBuf<MaskItem> dItems(be, numItems);
+        if (numItems) {
+            dItems.upload(items.p, numItems);
+            MaskParams mp{p->dSeq.p, dItems.p, (int)numItems, dMasks.p, unionSet};
             be->launch_mask(mp);
         }
         DevBuf<int> dTset(be, N), dAlpha(be, N);
-        {
-            std::vector<int> tset(N);
-            for (int i = 0; i < N; ++i) tset[i] = N + p->tidx[i];
-            dTset.upload(tset.data(), N);
-        }
+        dTset.upload(tset.p, N);
         be->launch_alpha_len(dMasks.p, nullptr, dTset.p, N, dAlpha.p);
         p->alphaLen.resize(N);
         dAlpha.download(p->alphaLen.data(), N);
@@ -707,10 +750,10 @@ struct Pass {
     EngineStats& stats;
     Trace trace;
     const int N, mode, k;
-    // per-pair sweep outcome before the "-1" rule
-    std::vector<int> best, cnt;
-    std::vector<long long> posStart;  // end columns of pair i: posPool[posStart[i] .. +posLen[i])
-    std::vector<int> posLen, posPool;
+    // per-pair sweep outcome before the "-1" rule (storage reused from pass to pass: EngineScratch)
+    std::vector<int>&best, &cnt;
+    std::vector<long long>& posStart;  // end columns of pair i: posPool[posStart[i] .. +posLen[i])
+    std::vector<int>&posLen, &posPool;
     std::vector<int> wPairs;          // pairs swept by the warp / lane-job kernels
     std::vector<uint8_t> opsPool;
     WRunner runner;
@@ -718,8 +761,21 @@ struct Pass {
 
     Pass(Engine& e, Backend* b, Prepared* pr)
         : eng(e), be(b), p(pr), tun(e.tun), stats(e.stats), N(pr->N), mode(pr->mode), k(pr->cfg.k),
-          best(pr->N, -1), cnt(pr->N, 0), posStart(pr->N, -1), posLen(pr->N, 0),
-          runner{&e, b, pr, &opsPool} {
+          best(e.scratch.best), cnt(e.scratch.cnt), posStart(e.scratch.posStart), posLen(e.scratch.posLen),
+          posPool(e.scratch.posPool), runner{&e, b, pr, &opsPool} {
+        best.resize((size_t)N);
+        cnt.resize((size_t)N);
+        posStart.resize((size_t)N);
+        posLen.resize((size_t)N);
+        parallel_ranges((size_t)N, 65536, [this](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                best[i] = -1;
+                cnt[i] = 0;
+                posStart[i] = -1;
+                posLen[i] = 0;
+            }
+        });
+        posPool.clear();
         posPool.reserve((size_t)N + 16);
     }
 
@@ -817,6 +873,60 @@ struct Pass {
         }
     }
 
+    // Hash indexes of the seeds of one target (candidate filter, seed stages), one per seed length; kept for
+    // the last target used.  Level 0: the shortest L with sigma^L >= n (about one chance occurrence per seed);
+    // level 1: two symbols shorter (more seeds fit into a read, so a higher threshold, at the price of more
+    // chance occurrences) for the reads level 0 cannot decide.
+    struct SeedIndex {
+        int target = -1;
+        int L = 0, bits = 0;
+        DevBuf<int> bucketStart, positions;
+    } seed[2];
+    bool seed_index(int t, int level) {
+        SeedIndex& sx = seed[level];
+        const Target& tg = p->tg[t];
+        const int n = tg.len;
+        if (sx.target == t) return sx.L > 0;
+        sx.target = t;
+        sx.L = 0;
+        const double sigma = std::max(2, p->ncodes);
+        int L = 8;
+        double v = std::pow(sigma, 8);
+        while (v < (double)n && L < 32) {
+            v *= sigma;
+            ++L;
+        }
+        if (level == 1) {
+            if (L < 10) return false;  // seeds shorter than 8 symbols select nothing
+            L -= 2;
+        }
+        if (n < 4 * L) return false;
+        int bits = 12;
+        while (bits < 27 && (1LL << bits) < 2LL * n) ++bits;
+        const size_t B = (size_t)1 << bits;
+        sx.bucketStart.alloc(be, B + 1);
+        sx.positions.alloc(be, (size_t)(n - L + 1));
+        DevBuf<int> cursor(be, B);
+        be->zero(sx.bucketStart.p, (B + 1) * sizeof(int));
+        be->zero(cursor.p, B * sizeof(int));
+        SeedIndexParams ip;
+        memset(&ip, 0, sizeof(ip));
+        ip.tcodes = p->dSeq.p + tg.off;
+        ip.n = n;
+        ip.L = L;
+        ip.bits = bits;
+        ip.bucketStart = sx.bucketStart.p;
+        ip.cursor = cursor.p;
+        ip.positions = sx.positions.p;
+        be->launch_seed_count(ip);
+        be->launch_scan(sx.bucketStart.p, (int)B);
+        be->launch_seed_fill(ip);
+        sx.L = L;
+        sx.bits = bits;
+        trace.mark("filter: seed index");
+        return true;
+    }
+
     // Distance pass of one group of pairs that share target `t` and word class `nw` (queries <= 256
     // rows): candidate filter (HW), then the plain lane-per-alignment sweep of what is left.
     void lane_group(int t, int nw, std::vector<int>& list) {
@@ -827,21 +937,24 @@ struct Pass {
         // Chunk geometry: a HW sweep may be cut into target chunks (each re-started 2*m columns
         // early, exact because no HW path spans more than 2*m target symbols) so that a small
         // group still fills the machine.
-        auto geometry = [&](int g, int nwL, int& chunks, int& chunkLen) {
+        auto geometry = [&](int g, int nwL, int& chunks, int& chunkLen, bool perChunkRecs) {
             int blockThreads = 256, residentCtas = 1;
             be->k1_shape(nwL, p->ncodes, &blockThreads, &residentCtas);
             chunks = 1;
             chunkLen = (int)round_up((size_t)n, 16);
             if (mode != MODE_HW) return;
             const int minChunk = std::max(tun.k1MinChunk, 8 * 64 * nwL);
-            const long long maxChunks = std::max<long long>(1, n / minChunk);
+            long long maxChunks = std::max<long long>(1, n / minChunk);
+            // plain sweeps return one record per (chunk, read): keep that below ~64 MB
+            if (perChunkRecs) maxChunks = std::min<long long>(maxChunks, std::max<long long>(64, (2LL << 20) / std::max(g, 1)));
+            maxChunks = std::min<long long>(maxChunks, 4096);
             const long long tiles = ceil_div(g, blockThreads);
             // CTAs run in waves of `residentCtas`; all CTAs of a launch cost the same, so the launch
-            // takes ceil(waves) CTA-times.  Pick the cut (<= 64 chunks) with the best
-            // (fullness of the last wave) x (1 - halo overhead); more, shorter CTAs fill waves better.
+            // takes ceil(waves) CTA-times.  Pick the cut with the best (fullness of the last wave) x
+            // (1 - halo overhead); more, shorter CTAs fill waves better.
             long long best = 1;
             double bestScore = -1;
-            for (long long c = 1; c <= std::min<long long>(64, maxChunks); ++c) {
+            for (long long c = 1; c <= maxChunks; ++c) {
                 const double waves = (double)(tiles * c) / residentCtas;
                 const double eff = waves / (double)((tiles * c + residentCtas - 1) / residentCtas);
                 const double len = (double)n / (double)c;
@@ -980,11 +1093,218 @@ struct Pass {
         // prefix or the plain sweep), reads with long end-location lists to `direct`.
         std::vector<int> direct;  // reads that take the plain full sweep
         direct.reserve(G);
+        std::vector<int> excl(G, -1);  // per read: it is known that no distance <= excl[s] exists
+        auto no_distance_within = [&](int s, int t, std::vector<int>& next) {  // final if t is the caller's bound
+            if (t > excl[s]) excl[s] = t;
+            if (t == bound[s]) {
+                best[list[s]] = 0x7fffffff;
+                cnt[list[s]] = 0;
+                stats.filterDecided++;
+            } else {
+                next.push_back(s);
+            }
+        };
+        // Seed stage: exact seeds of every read looked up in the hash index of the target; windows around
+        // the expected end columns are planned, swept and reduced on the device (eb_core.h: seed_plan_read).
+        auto seed_stage = [&](int level, const std::vector<int>& in, std::vector<int>& next) {
+            if (!seed_index(t, level)) {
+                next = in;
+                return;
+            }
+            const SeedIndex& sx = seed[level];
+            const int L = sx.L;
+            // every read of `in` gets a slot; thr < 0 marks the ones this stage cannot help (the kernel skips them)
+            const std::vector<int>& cand = in;
+            const int g = (int)cand.size();
+            if (g == 0) return;
+            HostBuf<int> rl(be, g), hThr(be, g);
+            const int* thr = hThr.p;
+            parallel_ranges((size_t)g, 65536, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i) {
+                    const int s = cand[i];
+                    const int m = p->qlen[list[s]];
+                    const int tt = std::min(std::min(bound[s], tun.filterSeedK), m / L - 1);
+                    rl[i] = list[s];
+                    hThr[i] = (m >= 2 * L && tt > excl[s]) ? tt : -1;
+                }
+            });
+            DevBuf<int> dList(be, g), dThr(be, g), dCount(be, 1);
+            dList.upload(rl.p, g);
+            dThr.upload(hThr.p, g);
+            DevBuf<SeedPlan> dPlan(be, g);
+            DevBuf<int> wPair, wK, wStart, wLen, wTf;
+            int cap = 4 * g + 1024, V = 0;
+            for (;;) {
+                wPair.alloc(be, cap);
+                wK.alloc(be, cap);
+                wStart.alloc(be, cap);
+                wLen.alloc(be, cap);
+                wTf.alloc(be, cap);
+                be->zero(dCount.p, sizeof(int));
+                SeedPlanParams sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.tcodes = p->dSeq.p + tg.off;
+                sp.n = n;
+                sp.qcodes = p->dSeq.p;
+                sp.qoff = p->dQoff.p;
+                sp.qlen = p->dQlen.p;
+                sp.readList = dList.p;
+                sp.thr = dThr.p;
+                sp.numReads = g;
+                sp.L = L;
+                sp.bits = sx.bits;
+                sp.bucketStart = sx.bucketStart.p;
+                sp.positions = sx.positions.p;
+                sp.maxBucket = tun.filterSeedBucket << (4 * level);  // shorter seeds: longer buckets are normal
+                sp.spread = tun.filterSpread;
+                sp.winPair = wPair.p;
+                sp.winK = wK.p;
+                sp.winStart = wStart.p;
+                sp.winLen = wLen.p;
+                sp.winTf = wTf.p;
+                sp.winCap = cap;
+                sp.winCount = dCount.p;
+                sp.plan = dPlan.p;
+                be->launch_seed_plan(sp);
+                dCount.download(&V, 1);
+                stats.d2hBytes += 4;
+                if (V <= cap) break;
+                cap = V;  // window list overflow: repeat with the exact size
+            }
+            trace.mark("filter: seeds planned");
+            DevBuf<WinRec> dWinRecs(be, (size_t)std::max(V, 1));
+            if (V > 0) {
+                K1WParams wp;
+                memset(&wp, 0, sizeof(wp));
+                wp.tcodes = p->dSeq.p + tg.off;
+                wp.qcodes = p->dSeq.p;
+                wp.qoff = p->dQoff.p;
+                wp.qlen = p->dQlen.p;
+                wp.readList = wPair.p;
+                wp.kInit = wK.p;
+                wp.winStart = wStart.p;
+                wp.winLen = wLen.p;
+                wp.trackFrom = wTf.p;
+                wp.numReads = V;
+                wp.ncodes = p->ncodes;
+                wp.eqtab = nullptr;
+                wp.recs = dWinRecs.p;
+                be->launch_k1w(wp, nw);
+            }
+            DevBuf<Rec> dOut(be, g);
+            const int extraCap = g / 4 + 1024;
+            DevBuf<int> dExtra(be, (size_t)extraCap);
+            be->zero(dCount.p, sizeof(int));
+            WinReduceParams rp;
+            rp.plan = dPlan.p;
+            rp.thr = dThr.p;
+            rp.winRecs = dWinRecs.p;
+            rp.numReads = g;
+            rp.out = dOut.p;
+            rp.extra = dExtra.p;
+            rp.extraCount = dCount.p;
+            rp.extraCap = extraCap;
+            be->launch_win_reduce(rp);
+            HostBuf<Rec> out(be, g);
+            dOut.download(out.p, g);
+            int nExtra = 0;
+            dCount.download(&nExtra, 1);
+            nExtra = std::min(nExtra, extraCap);  // reads whose run did not fit were marked as long lists
+            std::vector<int> extra((size_t)nExtra);
+            if (nExtra) dExtra.download(extra.data(), (size_t)nExtra);
+            stats.d2hBytes += (long long)g * (long long)sizeof(Rec) + 4 + 4LL * nExtra;
+            trace.mark("filter: seed windows");
+            // Outcome per read, on a few host threads: records of decided reads go straight to best / cnt;
+            // their positions are appended to posPool in slot order (counts first, then the fill).
+            struct Part {
+                std::vector<int> next, direct;
+                long long decided = 0, positions = 0;
+                int nSat = 0, nLong = 0;
+            };
+            std::vector<Part> parts;
+            std::vector<size_t> partLo;
+            {
+                const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+                const size_t nparts = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, hw), (size_t)g / 65536));
+                parts.resize(nparts);
+                for (size_t t2 = 0; t2 <= nparts; ++t2) partLo.push_back((size_t)g * t2 / nparts);
+            }
+            auto for_parts = [&](const std::function<void(size_t)>& fn) {
+                if (parts.size() == 1) {
+                    fn(0);
+                    return;
+                }
+                std::vector<std::thread> th;
+                for (size_t t2 = 0; t2 < parts.size(); ++t2) th.emplace_back([&fn, t2]() { fn(t2); });
+                for (auto& x : th) x.join();
+            };
+            for_parts([&](size_t t2) {
+                Part& P = parts[t2];
+                for (size_t i = partLo[t2]; i < partLo[t2 + 1]; ++i) {
+                    const int s = cand[i], pair = list[s];
+                    const Rec& r = out[i];
+                    if (thr[i] < 0) {
+                        P.next.push_back(s);
+                    } else if (r.rsv == SEED_WINDOWS) {
+                        P.decided++;
+                        best[pair] = r.best;
+                        cnt[pair] = r.cnt;
+                        posLen[pair] = r.cnt;
+                        P.positions += r.cnt;
+                    } else if (r.rsv == SEED_NONE) {
+                        if (thr[i] > excl[s]) excl[s] = thr[i];
+                        if (thr[i] == bound[s]) {  // nothing within the caller's bound: final
+                            best[pair] = 0x7fffffff;
+                            cnt[pair] = 0;
+                            P.decided++;
+                        } else {
+                            P.next.push_back(s);
+                        }
+                    } else if (r.rsv == SEED_LONG_LIST) {
+                        P.direct.push_back(s);
+                        P.nLong++;
+                    } else {
+                        P.next.push_back(s);
+                        P.nSat++;
+                    }
+                }
+            });
+            int nSat = 0, nLong = 0;
+            std::vector<long long> partPos(parts.size());
+            {
+                long long at = (long long)posPool.size();
+                for (size_t t2 = 0; t2 < parts.size(); ++t2) {
+                    partPos[t2] = at;
+                    at += parts[t2].positions;
+                    stats.filterDecided += parts[t2].decided;
+                    nSat += parts[t2].nSat;
+                    nLong += parts[t2].nLong;
+                    next.insert(next.end(), parts[t2].next.begin(), parts[t2].next.end());
+                    direct.insert(direct.end(), parts[t2].direct.begin(), parts[t2].direct.end());
+                }
+                posPool.resize((size_t)at);
+            }
+            for_parts([&](size_t t2) {
+                long long at = partPos[t2];
+                for (size_t i = partLo[t2]; i < partLo[t2 + 1]; ++i) {
+                    const Rec& r = out[i];
+                    if (thr[i] < 0 || r.rsv != SEED_WINDOWS) continue;
+                    const int pair = list[cand[i]];
+                    posStart[pair] = at;
+                    for (int q = 0; q < std::min(r.cnt, KPOS); ++q) posPool[(size_t)at++] = r.pos[q];
+                    for (int q = KPOS; q < r.cnt; ++q) posPool[(size_t)at++] = extra[(size_t)r.last + q - KPOS];
+                }
+            });
+            if (trace.on)
+                fprintf(stderr, "[edlib_b200] filter seed stage %d, L=%d: %d reads, %d windows, %d saturated, %d long lists, %zu to the next stage\n",
+                        level, L, g, V, nSat, nLong, next.size());
+        };
         auto filter_stage = [&](int P, int K0, const std::vector<int>& in, std::vector<int>& next) {
             std::vector<int> cand, thr;
             const int minLen = std::max(tun.filterMinLen * P / 64, P + 1);
             for (int s : in) {
-                if (p->qlen[list[s]] >= minLen) {
+                // worth a sweep only if it can decide clearly more than what is already excluded
+                if (p->qlen[list[s]] >= minLen && std::min(K0, bound[s]) > excl[s] && (excl[s] < 0 || K0 >= excl[s] + 4)) {
                     cand.push_back(s);
                     thr.push_back(std::min(K0, bound[s]));
                 } else {
@@ -994,20 +1314,12 @@ struct Pass {
             if (cand.empty()) return;
             const int g = (int)cand.size();
             int chunksA = 1, chunkLenA = 0;
-            geometry(g, P / 32, chunksA, chunkLenA);
+            geometry(g, P / 32, chunksA, chunkLenA, false);
             std::vector<Rec> none;
             std::vector<Ovf> ranges;
             launch(cand, thr, P / 32, chunksA, chunkLenA, (int)std::min<long long>(16LL * g + 4096, 1LL << 28), P, 1, none, ranges);
             trace.mark("filter: prefix sweep");
-            auto undecided = [&](int s, int t) {  // no distance <= t exists: final if t is the caller's bound
-                if (t == bound[s]) {
-                    best[list[s]] = 0x7fffffff;
-                    cnt[list[s]] = 0;
-                    stats.filterDecided++;
-                } else {
-                    next.push_back(s);
-                }
-            };
+            auto undecided = [&](int s, int t) { no_distance_within(s, t, next); };
             // ranges of every read, ascending (the list is in completion order)
             std::vector<int> start(g + 1, 0);
             std::vector<char> saturated(g, 0);
@@ -1055,10 +1367,12 @@ struct Pass {
                     long long lo = (long long)first + (m - P) - t;
                     long long hi = (long long)last + (m - P) + t;
                     if (lo <= prevHi) lo = prevHi + 1;
+                    if (lo < 0) lo = 0;
                     if (hi > n - 1) hi = n - 1;
                     if (lo > hi) continue;
                     prevHi = hi;
-                    const long long ws = std::max<long long>(0, lo - 2LL * m);  // HW restart: exact after 2m columns
+                    // HW restart: alignments with <= t edits span at most m + t columns (scores <= t stay exact)
+                    const long long ws = std::max<long long>(0, lo - (long long)(m + t));
                     vOwner.push_back(i);
                     vPair.push_back(pair);
                     vK.push_back(t + 1);
@@ -1096,8 +1410,7 @@ struct Pass {
             dWs.upload(vWs.data(), V);
             dLen.upload(vLen.data(), V);
             dTf.upload(vTf.data(), V);
-            DevBuf<Rec> dRecs(be, V);
-            be->zero(dRecs.p, (size_t)V * sizeof(Rec));
+            DevBuf<WinRec> dRecs(be, V);
             K1WParams wp;
             memset(&wp, 0, sizeof(wp));
             wp.tcodes = p->dSeq.p + tg.off;
@@ -1114,9 +1427,9 @@ struct Pass {
             wp.eqtab = p->hasEq ? p->dEqtab.p : nullptr;
             wp.recs = dRecs.p;
             be->launch_k1w(wp, nw);
-            std::vector<Rec> rv(V);
+            std::vector<WinRec> rv(V);
             dRecs.download(rv.data(), V);
-            stats.d2hBytes += (long long)V * (long long)sizeof(Rec);
+            stats.d2hBytes += (long long)V * (long long)sizeof(WinRec);
             trace.mark("filter: window sweeps");
             for (int i = 0; i < g; ++i) {
                 if (wFirst[i] == wFirst[i + 1]) continue;
@@ -1133,7 +1446,7 @@ struct Pass {
                 for (int j = wFirst[i]; j < wFirst[i + 1]; ++j)
                     if (rv[j].cnt > 0 && rv[j].best == b) {
                         total += rv[j].cnt;
-                        if (rv[j].cnt > KPOS) longList = true;
+                        if (rv[j].cnt > KPOSW) longList = true;
                     }
                 if (longList) {  // long end-location list: the plain sweep collects it
                     direct.push_back(s);
@@ -1155,6 +1468,11 @@ struct Pass {
             for (int s = 0; s < G; ++s) cur[s] = s;
             if (mode == MODE_HW && n >= tun.filterMinTarget) {
                 trace.mark("compute: classify");
+                for (int level = 0; level < 2 && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
+                    std::vector<int> next;
+                    seed_stage(level, cur, next);
+                    cur.swap(next);
+                }
                 const int stageP[2] = {32, 64};
                 const int stageK[2] = {tun.filterK1, tun.filterK0};
                 for (int st = 0; st < 2; ++st) {
@@ -1173,7 +1491,7 @@ struct Pass {
         // ---- plain full sweep of the remaining reads ------------------------------------------
         if (!direct.empty()) {
             int chunks = 1, chunkLen = 0;
-            geometry((int)direct.size(), nw, chunks, chunkLen);
+            geometry((int)direct.size(), nw, chunks, chunkLen, true);
             std::vector<int> kInit(direct.size());
             for (size_t s = 0; s < direct.size(); ++s) kInit[s] = bound[direct[s]] + 1;
             std::vector<Rec> recs;
@@ -1189,7 +1507,7 @@ struct Pass {
                 std::vector<int> subK(incomplete.size());
                 for (size_t s = 0; s < incomplete.size(); ++s) subK[s] = best[list[incomplete[s]]];
                 int chunks2 = 1, chunkLen2 = 0;
-                geometry((int)incomplete.size(), nw, chunks2, chunkLen2);
+                geometry((int)incomplete.size(), nw, chunks2, chunkLen2, true);
                 std::vector<Rec> recs2;
                 std::vector<Ovf> ovf2;
                 std::vector<int> still;
@@ -1263,28 +1581,66 @@ struct Pass {
 
     // editDistance and endLocations per pair from the sweep outcomes (ref cpp:219-225 and the -1 rule).
     void collect_ends() {
-        // ---- distances and end locations ------------------------------------------------------
-        for (int i = 0; i < N; ++i) {
-            if (p->special[i]) continue;
-            const int m = p->qlen[i], n = p->tlen[i];
-            p->endStart[i] = (long long)p->endPool.size();
-            if (best[i] < 0 || best[i] == 0x7fffffff) continue;  // rejected up front or nothing tracked
-            if (k >= 0 && best[i] > k) continue;
-            if (mode == MODE_NW) {
-                p->ed[i] = best[i];
-                p->endPool.push_back(n - 1);  // ref cpp:221-225
-                p->endCount[i] = 1;
-                continue;
-            }
-            if (best[i] > m) continue;
-            p->ed[i] = best[i];
-            // ref cpp:670, 681-693: the padded bottom cell of column W-1 shows up as end location -1
+        // ---- distances and end locations: counts per pair, offsets, fill (on a few host threads) -------
+        // ref cpp:670, 681-693: the padded bottom cell of column W-1 shows up as end location -1
+        auto accepted = [&](int i) -> int {  // number of end locations of pair i, or -1 if it has no result
+            if (p->special[i]) return -1;
+            if (best[i] < 0 || best[i] == 0x7fffffff) return -1;  // rejected up front or nothing tracked
+            if (k >= 0 && best[i] > k) return -1;
+            if (mode == MODE_NW) return 1;
+            const int m = p->qlen[i];
+            if (best[i] > m) return -1;
             const int W64 = ceil_div(m, 64) * 64 - m;
-            if (best[i] == m && W64 > 0) p->endPool.push_back(-1);
-            if (posLen[i] != cnt[i]) throw std::runtime_error("internal: end-location count mismatch");
-            p->endPool.insert(p->endPool.end(), posPool.begin() + posStart[i], posPool.begin() + posStart[i] + posLen[i]);
-            p->endCount[i] = (int)(p->endPool.size() - (size_t)p->endStart[i]);
+            return posLen[i] + ((best[i] == m && W64 > 0) ? 1 : 0);
+        };
+        const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t nparts = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, hw), (size_t)N / 65536));
+        std::vector<long long> partCount(nparts + 1, 0);
+        std::vector<int> bad(nparts, 0);
+        auto run = [&](const std::function<void(size_t, size_t, size_t)>& fn) {
+            if (nparts == 1) {
+                fn(0, 0, (size_t)N);
+                return;
+            }
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < nparts; ++t) th.emplace_back([&fn, t, this, nparts]() { fn(t, (size_t)N * t / nparts, (size_t)N * (t + 1) / nparts); });
+            for (auto& x : th) x.join();
+        };
+        run([&](size_t t, size_t lo, size_t hi) {
+            long long c = 0;
+            for (size_t i = lo; i < hi; ++i) {
+                const int a = accepted((int)i);
+                if (a > 0) c += a;
+                if (a >= 0 && mode != MODE_NW && posLen[i] != cnt[i]) bad[t] = 1;
+            }
+            partCount[t + 1] = c;
+        });
+        for (size_t t = 0; t < nparts; ++t) {
+            if (bad[t]) throw std::runtime_error("internal: end-location count mismatch");
+            partCount[t + 1] += partCount[t];
         }
+        p->endPool.resize((size_t)partCount[nparts]);
+        run([&](size_t t, size_t lo, size_t hi) {
+            long long at = partCount[t];
+            for (size_t i = lo; i < hi; ++i) {
+                p->endStart[i] = at;
+                const int a = accepted((int)i);
+                if (a < 0) {
+                    p->ed[i] = -1;
+                    p->endCount[i] = 0;
+                    continue;
+                }
+                p->ed[i] = best[i];
+                p->endCount[i] = a;
+                if (mode == MODE_NW) {
+                    p->endPool[(size_t)at++] = p->tlen[i] - 1;  // ref cpp:221-225
+                    continue;
+                }
+                if (a > posLen[i]) p->endPool[(size_t)at++] = -1;
+                if (posLen[i]) memcpy(p->endPool.data() + at, posPool.data() + posStart[i], sizeof(int) * (size_t)posLen[i]);
+                at += posLen[i];
+            }
+        });
     }
 
     void start_locations() {
@@ -1551,14 +1907,20 @@ void Engine::compute(Prepared* p) {
     const int N = p->N;
     const int mode = p->mode;
     const int k = p->cfg.k;
-    p->ed.assign(N, -1);
-    p->special.assign(N, 0);
-    p->endStart.assign(N, 0);
-    p->endCount.assign(N, 0);
+    // ed / endStart / endCount are written for every pair by collect_ends, special by the classification
+    p->ed.resize(N);
+    p->special.resize(N);
+    p->endStart.resize(N);
+    p->endCount.resize(N);
     p->endPool.clear();
     p->startPool.clear();
-    p->alnStart.assign(N, -1);
-    p->alnLen.assign(N, 0);
+    if (p->cfg.task == EDLIB_TASK_PATH) {
+        p->alnStart.assign(N, -1);
+        p->alnLen.assign(N, 0);
+    } else {
+        p->alnStart.clear();
+        p->alnLen.clear();
+    }
     p->alnPool.clear();
     stats.k1Cells = stats.wCells = 0;
     stats.filterDecided = stats.filterFallback = 0;
@@ -1568,18 +1930,58 @@ void Engine::compute(Prepared* p) {
     Trace& trace = ps.trace;
 
     // ---- classification -----------------------------------------------------------------
-    std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, nw32) -> pairs
-    for (int i = 0; i < N; ++i) {
-        const int m = p->qlen[i], n = p->tlen[i];
-        if (m == 0 || n == 0) {
-            p->special[i] = 1;
-            continue;
+    std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, nw32) -> pairs, ascending
+    {
+        // contiguous ranges of pairs are classified on a few host threads and concatenated in order
+        const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t nparts = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, hw), (size_t)N / 65536));
+        struct Part {
+            std::map<std::pair<int, int>, std::vector<int>> groups;
+            std::vector<int> wPairs;
+        };
+        std::vector<Part> parts(nparts);
+        auto classify = [&](size_t t) {
+            Part& P = parts[t];
+            std::pair<int, int> lastKey(-1, -1);
+            std::vector<int>* lastList = nullptr;
+            const int lo = (int)((size_t)N * t / nparts), hi = (int)((size_t)N * (t + 1) / nparts);
+            for (int i = lo; i < hi; ++i) {
+                const int m = p->qlen[i], n = p->tlen[i];
+                p->special[i] = (m == 0 || n == 0) ? 1 : 0;
+                if (p->special[i]) continue;
+                if (mode == MODE_NW && k >= 0 && k < abs(n - m)) continue;  // ref cpp:744
+                if (m <= 256) {
+                    const std::pair<int, int> key(p->tidx[i], ceil_div(m, 32));
+                    if (key != lastKey) {  // neighbours usually share their group
+                        lastKey = key;
+                        lastList = &P.groups[key];
+                        if (lastList->empty()) lastList->reserve((size_t)(hi - i));
+                    }
+                    lastList->push_back(i);
+                } else {
+                    P.wPairs.push_back(i);
+                }
+            }
+        };
+        if (nparts == 1) {
+            classify(0);
+        } else {
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < nparts; ++t) th.emplace_back([&classify, t]() { classify(t); });
+            for (auto& x : th) x.join();
         }
-        if (mode == MODE_NW && k >= 0 && k < abs(n - m)) continue;  // ref cpp:744
-        if (m <= 256)
-            groups[std::make_pair(p->tidx[i], ceil_div(m, 32))].push_back(i);
-        else
-            wPairs.push_back(i);
+        if (nparts == 1) {
+            groups.swap(parts[0].groups);
+            wPairs.swap(parts[0].wPairs);
+        } else {
+            for (Part& P : parts) {
+                for (auto& kv : P.groups) {
+                    std::vector<int>& dst = groups[kv.first];
+                    dst.insert(dst.end(), kv.second.begin(), kv.second.end());
+                }
+                wPairs.insert(wPairs.end(), P.wPairs.begin(), P.wPairs.end());
+            }
+        }
     }
 
     // ---- K1 groups ----------------------------------------------------------------------
@@ -1612,7 +2014,8 @@ void Engine::compute(Prepared* p) {
     trace.mark("compute: starts + paths");
     be->sync();
     stats.kernelMs = be->kernel_ms(nullptr);
-    stats.k1Ms = be->kernel_ms("k1");
+    stats.k1Ms = be->kernel_ms("k1") + be->kernel_ms("k1_prefix");
+    stats.kernelReport = be->kernel_report();
     stats.launches = be->launches();
     p->computed = true;
 }
@@ -1623,7 +2026,8 @@ void Engine::compute(Prepared* p) {
 void Engine::materialize(Prepared* p, EdlibAlignResult* results) {
     Trace trace;
     const int N = p->N;
-    for (int i = 0; i < N; ++i) {
+    parallel_ranges((size_t)N, 65536, [=](size_t lo, size_t hi) {
+    for (int i = (int)lo; i < (int)hi; ++i) {
         EdlibAlignResult& r = results[i];
         memset(&r, 0, sizeof(r));
         r.status = EDLIB_STATUS_OK;
@@ -1652,12 +2056,13 @@ void Engine::materialize(Prepared* p, EdlibAlignResult* results) {
             r.startLocations = static_cast<int*>(malloc(sizeof(int) * (size_t)std::max(c, 1)));
             memcpy(r.startLocations, p->startPool.data() + p->endStart[i], sizeof(int) * (size_t)c);
         }
-        if (p->alnStart[i] >= 0) {
+        if (!p->alnStart.empty() && p->alnStart[i] >= 0) {
             r.alignmentLength = p->alnLen[i];
             r.alignment = static_cast<unsigned char*>(malloc((size_t)std::max(p->alnLen[i], 1)));
             memcpy(r.alignment, p->alnPool.data() + p->alnStart[i], (size_t)p->alnLen[i]);
         }
     }
+    });
     trace.mark("materialize");
 }
 

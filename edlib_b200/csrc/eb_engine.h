@@ -42,10 +42,17 @@ struct Backend {
     virtual void launch_w(const WParams& p, int R) = 0;
     virtual void launch_traceback(const TbParams& p) = 0;
     virtual void launch_split(const SplitParams& p) = 0;
+    // seed stage of the candidate filter: index build (count / scan / fill), per-read planning, window reduction
+    virtual void launch_seed_count(const SeedIndexParams& p) = 0;
+    virtual void launch_scan(int* data, int count) = 0;  // in place: exclusive prefix sums; data[count] = total
+    virtual void launch_seed_fill(const SeedIndexParams& p) = 0;
+    virtual void launch_seed_plan(const SeedPlanParams& p) = 0;
+    virtual void launch_win_reduce(const WinReduceParams& p) = 0;
     // timing of the launches issued since the last reset (device time, ms) and their count
     virtual void reset_timing() = 0;
     virtual double kernel_ms(const char* nameOrNull) = 0;
     virtual int launches() = 0;
+    virtual std::string kernel_report() = 0;  // "name:ms:launches;..." of the launches since the last reset
 };
 
 struct BatchInput {
@@ -62,10 +69,14 @@ struct EngineTunables {
     int k1MinChunk = 1024;        // smallest target chunk (columns) when one HW sweep is split
     int ovfCap = 1 << 20;         // overflow entries per launch before the exact-size retry
     size_t sliceBytes = 1ull << 30;  // device memory budget of one slice of W jobs
-    // Candidate filter for HW sweeps of reads over a shared target, two stages (0 disables one): a
+    // Candidate filter for HW sweeps of reads over a shared target, three stages (0 disables one):
+    // exact seeds looked up in a hash index of the target (pigeonhole: t+1 disjoint seeds for threshold
+    // t); then, for the reads still undecided, a
     // 32-row prefix sweep finds the target ranges where the prefix matches within filterK1, a 64-row
     // one (for the reads the first stage cannot decide) within filterK0; only windows around those
     // ranges are swept with the whole read; reads no stage decides take the plain full sweep.
+    int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
+    int filterSeedBucket = 32;    // seed stage: longest hash bucket looked at (longer: repeat, read passed on)
     int filterK1 = 8;
     int filterK0 = 16;
     int filterMinLen = 96;        // shortest query worth the 64-row stage (scaled by P/64 for the other)
@@ -83,6 +94,13 @@ struct EngineStats {
     long long k1Cells = 0;  // nominal cells (sum m*n) handled by K1
     long long wCells = 0;   // nominal cells of the distance pass handled by W
     long long filterDecided = 0, filterFallback = 0;
+    std::string kernelReport;  // per-kernel device time of the last compute(): "name:ms:launches;..."
+};
+
+// Host vectors of a compute pass, kept between passes so that their pages stay mapped.
+struct EngineScratch {
+    std::vector<int> best, cnt, posLen, posPool;
+    std::vector<long long> posStart;
 };
 
 class Prepared;  // a batch whose inputs are resident on the device
@@ -101,6 +119,7 @@ public:
 
     EngineTunables tun;
     EngineStats stats;
+    EngineScratch scratch;
     std::string lastError;
 
 private:

@@ -297,6 +297,96 @@ __global__ void split_kernel(const SplitParams p) {
     if (node < p.numNodes) split_node(p, node);
 }
 
+__global__ void seed_count_kernel(const SeedIndexParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= p.n - p.L) seed_count_item(p, i);
+}
+__global__ void seed_fill_kernel(const SeedIndexParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= p.n - p.L) seed_fill_item(p, i);
+}
+__global__ void seed_plan_kernel(const SeedPlanParams p) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < p.numReads) seed_plan_read(p, slot);
+}
+__global__ void win_reduce_kernel(const WinReduceParams p) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < p.numReads) win_reduce_read(p, slot);
+}
+
+// Exclusive prefix sums over ints, three launches: per-tile sums, scan of the tile sums (one CTA),
+// per-tile scan with the tile offset.  A tile is SCAN_THREADS * SCAN_PER consecutive elements.
+constexpr int SCAN_THREADS = 256, SCAN_PER = 16, SCAN_TILE = SCAN_THREADS * SCAN_PER;
+template <int THREADS>
+__device__ int block_exclusive_scan(int v, int* total) {
+    __shared__ int warpSums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warpSums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < THREADS / 32 ? warpSums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += o;
+        }
+        warpSums[lane] = s;
+    }
+    __syncthreads();
+    *total = warpSums[THREADS / 32 - 1];
+    return incl - v + (wid ? warpSums[wid - 1] : 0);
+}
+__global__ void scan_tile_sums_kernel(const int* data, int count, int* tileSums) {
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER; ++i)
+        if (base + i < count) s += data[base + i];
+    int total;
+    block_exclusive_scan<SCAN_THREADS>(s, &total);
+    if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+__global__ void scan_top_kernel(int* tileSums, int numTiles, int* totalOut) {
+    const int per = (numTiles + 1023) / 1024;
+    const int base = threadIdx.x * per;
+    int s = 0;
+    for (int i = 0; i < per; ++i)
+        if (base + i < numTiles) s += tileSums[base + i];
+    int total;
+    int run = block_exclusive_scan<1024>(s, &total);
+    for (int i = 0; i < per; ++i)
+        if (base + i < numTiles) {
+            const int v = tileSums[base + i];
+            tileSums[base + i] = run;
+            run += v;
+        }
+    if (threadIdx.x == 0) *totalOut = total;
+}
+__global__ void scan_apply_kernel(int* data, int count, const int* tileSums) {
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+    int v[SCAN_PER];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER; ++i) {
+        v[i] = base + i < count ? data[base + i] : 0;
+        s += v[i];
+    }
+    int total;
+    int run = block_exclusive_scan<SCAN_THREADS>(s, &total) + tileSums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_PER; ++i)
+        if (base + i < count) {
+            data[base + i] = run;
+            run += v[i];
+        }
+}
+
 __global__ void mask_kernel(const MaskParams p) {
     const int item = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
     if (item >= p.numItems) return;
@@ -391,12 +481,14 @@ struct CudaBackend : Backend {
     };
     std::vector<HostBlock> hostBlocks;
     void* alloc_host(size_t bytes) override {
+        HostBlock* fit = nullptr;  // best fit among the cached blocks
         for (auto& b : hostBlocks)
-            if (!b.used && b.bytes >= bytes) {
-                b.used = true;
-                return b.p;
-            }
-        for (size_t i = 0; i < hostBlocks.size(); ++i)  // drop an unused smaller block before growing
+            if (!b.used && b.bytes >= bytes && (!fit || b.bytes < fit->bytes)) fit = &b;
+        if (fit) {
+            fit->used = true;
+            return fit->p;
+        }
+        for (size_t i = 0; i < hostBlocks.size() && hostBlocks.size() >= 8; ++i)  // bound the cache: drop an unused block
             if (!hostBlocks[i].used) {
                 cudaFreeHost(hostBlocks[i].p);
                 hostBlocks.erase(hostBlocks.begin() + i);
@@ -556,7 +648,7 @@ struct CudaBackend : Backend {
         else launch_k1_t<NW, MODE_NW>(p);
     }
     void launch_k1(const K1Params& p, int nw) override {
-        Scope s(this, "k1");
+        Scope s(this, p.rangeMode ? "k1_prefix" : "k1");
         if (p.rangeMode) {
             if ((nw != 1 && nw != 2) || p.mode != MODE_HW) throw std::runtime_error("range mode needs the 1- or 2-word HW kernel");
             if (nw == 1) launch_k1_range_t<1>(p);
@@ -651,6 +743,46 @@ struct CudaBackend : Backend {
         }
         check_launch("w");
     }
+    void launch_seed_count(const SeedIndexParams& p) override {
+        Scope s(this, "seed_count");
+        seed_count_kernel<<<(p.n - p.L + 1 + 255) / 256, 256, 0, stream>>>(p);
+        check_launch("seed_count");
+    }
+    void launch_seed_fill(const SeedIndexParams& p) override {
+        Scope s(this, "seed_fill");
+        seed_fill_kernel<<<(p.n - p.L + 1 + 255) / 256, 256, 0, stream>>>(p);
+        check_launch("seed_fill");
+    }
+    void launch_scan(int* data, int count) override {
+        const int numTiles = (count + SCAN_TILE - 1) / SCAN_TILE;
+        int* tileSums = static_cast<int*>(alloc((size_t)numTiles * sizeof(int)));
+        {
+            Scope s(this, "scan");
+            scan_tile_sums_kernel<<<numTiles, SCAN_THREADS, 0, stream>>>(data, count, tileSums);
+            check_launch("scan tile sums");
+        }
+        {
+            Scope s(this, "scan");
+            scan_top_kernel<<<1, 1024, 0, stream>>>(tileSums, numTiles, data + count);
+            check_launch("scan top");
+        }
+        {
+            Scope s(this, "scan");
+            scan_apply_kernel<<<numTiles, SCAN_THREADS, 0, stream>>>(data, count, tileSums);
+            check_launch("scan apply");
+        }
+        free(tileSums);
+    }
+    void launch_seed_plan(const SeedPlanParams& p) override {
+        Scope s(this, "seed_plan");
+        seed_plan_kernel<<<(p.numReads + 127) / 128, 128, 0, stream>>>(p);
+        check_launch("seed_plan");
+    }
+    void launch_win_reduce(const WinReduceParams& p) override {
+        Scope s(this, "win_reduce");
+        win_reduce_kernel<<<(p.numReads + 127) / 128, 128, 0, stream>>>(p);
+        check_launch("win_reduce");
+    }
     void launch_split(const SplitParams& p) override {
         Scope s(this, "split");
         split_kernel<<<(p.numNodes + 63) / 64, 64, 0, stream>>>(p);
@@ -680,6 +812,31 @@ struct CudaBackend : Backend {
         return total;
     }
     int launches() override { return launchCount; }
+    std::string kernel_report() override {
+        cudaStreamSynchronize(stream);
+        std::vector<std::string> names;
+        std::vector<double> ms;
+        std::vector<int> count;
+        for (auto& t : timed) {
+            size_t i = 0;
+            while (i < names.size() && names[i] != t.name) ++i;
+            if (i == names.size()) {
+                names.push_back(t.name);
+                ms.push_back(0);
+                count.push_back(0);
+            }
+            float e = 0;
+            if (cudaEventElapsedTime(&e, t.a, t.b) == cudaSuccess) ms[i] += e;
+            count[i]++;
+        }
+        std::string out;
+        for (size_t i = 0; i < names.size(); ++i) {
+            char buf[96];
+            snprintf(buf, sizeof(buf), "%s%s:%.4f:%d", i ? ";" : "", names[i].c_str(), ms[i], count[i]);
+            out += buf;
+        }
+        return out;
+    }
 };
 
 int select_device(int device, std::string* err) {

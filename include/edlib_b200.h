@@ -62,6 +62,10 @@ EDLIB_API void edlibB200BatchFree(EdlibB200Batch* batch);
 /* Stats of the most recent edlibAlign / edlibAlignBatch / BatchCompute on this process. */
 EDLIB_API void edlibB200LastStats(EdlibB200Stats* statsOut);
 
+/* Device time per kernel of the most recent compute, as text "name:milliseconds:launches;..." written
+ * to buf (NUL-terminated, truncated to bufLen); returns the full length. */
+EDLIB_API int edlibB200LastKernelReport(char* buf, int bufLen);
+
 #ifdef __cplusplus
 }
 #endif

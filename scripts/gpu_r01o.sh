@@ -1,0 +1,10 @@
+#!/bin/bash
+# Seed stage of the candidate filter: parity, bench, A/B without it, trace.
+TAG=${1:-r01o}
+OUT=gpurun_out; mkdir -p $OUT
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+echo "== bench (default flags)"; timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "rc=$?"; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
+echo "== trace of one pass (1M reads)"
+EDLIB_B200_TRACE=1 timeout 600 python bench.py --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline > $OUT/trace_$TAG.txt 2>&1; tail -60 $OUT/trace_$TAG.txt | cut -c1-200
+echo "== A/B: seed stage off"
+EDLIB_B200_FILTER_SEED_K=0 timeout 600 python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline 2>/dev/null | tee $OUT/bench_${TAG}_noseed.json | cut -c1-300

@@ -116,8 +116,8 @@ def filter_cases(seed, count):
     neighbouring candidate ranges, equal-score hits in different windows), tandem-repeat targets
     (range lists that saturate), explicit and free k -- every branch of the two-stage candidate filter."""
     rng = random.Random(seed)
-    alpha = b"ACGT"
     for _ in range(count):
+        alpha = rng.choice([b"ACGT", b"ACGT", b"ACGT", b"ACGTN", b"ACDEFGHIKLMNPQRSTVWY", b"AC"])
         shape = rng.random()
         if shape < 0.12:  # tandem repeat with a few mutations: candidates everywhere
             unit = rand_seq(rng, rng.choice([5, 13, 31, 50]), alpha)
@@ -186,3 +186,28 @@ KNOWN = [
     (b"GCATATCAATAAGCGGAGGA", b"TAACAAGGTTTCCGTAGGTGAACCTGCGGAAGGATCATTATTGAATTATATCTT", "HW", "locations", -1,
      [(b"R", b"A"), (b"R", b"G"), (b"M", b"A"), (b"M", b"C"), (b"W", b"A"), (b"W", b"T")], dict()),
 ]
+
+
+def big_batch_case(seed, num=140_000, target_len=4000):
+    """One HW batch large enough for the multi-threaded host paths (classification, seed-stage
+    outcomes, end-location assembly): short reads of two word classes over one target, with empty
+    queries, unrelated reads and a few queries beyond the lane kernels mixed in."""
+    rng = random.Random(seed)
+    alpha = b"ACGT"
+    t = rand_seq(rng, target_len, alpha)
+    qs = []
+    for i in range(num):
+        r = rng.random()
+        L = rng.choice([40, 48, 60, 70])
+        if r < 0.001:
+            q = b""
+        elif r < 0.0015:
+            a = rng.randrange(0, target_len - 400)
+            q = mutate(rng, t[a:a + 300], 0.05, alpha)
+        elif r < 0.9:
+            a = rng.randrange(0, target_len - L - 8)
+            q = mutate(rng, t[a:a + L + 6], rng.choice([0, 0.03, 0.08]), alpha)[:L]
+        else:
+            q = rand_seq(rng, L, alpha)
+        qs.append(q)
+    return dict(qs=qs, ts=[t] * num, k=rng.choice([-1, 6]), mode=2, task=rng.choice([0, 1]), eqs=None)

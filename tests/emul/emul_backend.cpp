@@ -109,6 +109,32 @@ struct EmulBackend : Backend {
         ++launchesCount;
         for (uint64_t i = 0; i < p.numBytes; ++i) p.data[i] = p.map[p.data[i]];
     }
+    void launch_seed_count(const SeedIndexParams& p) override {
+        ++launchesCount;
+        for (int i = 0; i <= p.n - p.L; ++i) seed_count_item(p, i);
+    }
+    void launch_seed_fill(const SeedIndexParams& p) override {
+        ++launchesCount;
+        for (int i = p.n - p.L; i >= 0; --i) seed_fill_item(p, i);  // any order is valid; not the ascending one
+    }
+    void launch_scan(int* data, int count) override {
+        ++launchesCount;
+        int run = 0;
+        for (int i = 0; i < count; ++i) {
+            const int v = data[i];
+            data[i] = run;
+            run += v;
+        }
+        data[count] = run;
+    }
+    void launch_seed_plan(const SeedPlanParams& p) override {
+        ++launchesCount;
+        for (int i = p.numReads - 1; i >= 0; --i) seed_plan_read(p, i);
+    }
+    void launch_win_reduce(const WinReduceParams& p) override {
+        ++launchesCount;
+        for (int i = 0; i < p.numReads; ++i) win_reduce_read(p, i);
+    }
     void launch_k1(const K1Params& p, int nw) override {
         ++launchesCount;
         switch (nw) {
@@ -179,6 +205,7 @@ struct EmulBackend : Backend {
     void reset_timing() override { launchesCount = 0; }
     double kernel_ms(const char*) override { return 0.0; }
     int launches() override { return launchesCount; }
+    std::string kernel_report() override { return std::string(); }
 };
 
 }  // namespace

@@ -68,8 +68,9 @@ def test_paths_beyond_the_stored_matrix_rule(emul):
 
 
 def test_candidate_filter_all_branches():
-    """Prefix filter + window verification + fallbacks, forced on for small targets (separate
-    process: tunables are read once), in two settings incl. a tight threshold/spread."""
+    """Seed stage + prefix stages + window verification + fallbacks, forced on for small targets
+    (separate processes: tunables are read once), under settings that push reads through every branch
+    (tight thresholds / spread / window and bucket limits, single stages alone)."""
     code = (
         "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "import parity, cases, test_engine_emul as T\n"
@@ -78,10 +79,26 @@ def test_candidate_filter_all_branches():
     ) % (REPO, os.path.join(REPO, "tests"))
     for extra in ({}, {"EDLIB_B200_FILTER_K0": "4", "EDLIB_B200_FILTER_K1": "2", "EDLIB_B200_FILTER_SPREAD": "64",
                        "EDLIB_B200_FILTER_MAX_WINDOWS": "2", "EDLIB_B200_K1_MIN_CHUNK": "64", "EDLIB_EMUL_SMS": "64"},
-                  {"EDLIB_B200_FILTER_K1": "0"}, {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "12"}):
+                  {"EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "3", "EDLIB_B200_FILTER_SEED_BUCKET": "2"},
+                  {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "12", "EDLIB_B200_FILTER_SEED_K": "0"},
+                  {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "40"}):
         env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 500
+
+
+def test_large_batch_uses_the_threaded_host_paths():
+    """> 131072 pairs: classification, seed-stage outcomes and end-location assembly run on several host
+    threads; every result still equals the reference's."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 3, 1, gen=lambda seed, count: [cases.big_batch_case(seed)]))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128")
+    out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+    assert int(out.stdout.strip().splitlines()[-1]) == 140000
 
 
 def test_many_end_locations(emul):
