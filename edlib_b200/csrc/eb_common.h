@@ -285,8 +285,13 @@ struct MaskItem {
 };
 struct MaskParams {
     const uint8_t* raw;      // raw bytes as uploaded
-    const MaskItem* items;
+    const MaskItem* items;   // explicit items: targets, and the pieces of queries longer than 65536
     int numItems;
+    // implicit items 0..numQueries-1 (work item indices numItems..numItems+numQueries-1): query i at
+    // qoff[i], qlen[i] bytes, destination set i; queries longer than 65536 are skipped (explicit pieces)
+    const uint64_t* qoff;
+    const int* qlen;
+    int numQueries;
     uint32_t* masks;         // [numSets][8] 256-bit presence sets, zeroed by the host
     int unionSet;            // set that additionally receives every byte seen (or -1)
 };

@@ -491,8 +491,20 @@ EB_HD void k1w_thread(const K1WParams& p, int slot, Acc& acc) {
     K1State<NW> st;
     k1_init<NW>(st, m, p.kInit[slot]);
     const int ws = p.winStart[slot], tf = p.trackFrom[slot], len = p.winLen[slot];
-    k1_columns<NW, false, false, false, KPOSW>(st, acc, PtrSyms{p.tcodes + ws}, tf, ws, rec, slot, nullptr, nullptr, 0);
-    k1_columns<NW, false, true, false, KPOSW>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
+    // Lead-in columns in blocks of 32.  The last-row score falls by at most one per column, so once it
+    // exceeds the sentinel by more than the columns left in the window no tracked column can reach the
+    // threshold any more and the sweep stops (most windows come from chance seed hits and end here).
+    bool hopeless = false;
+    for (int j = 0; j < tf; j += 32) {
+        const int cntj = tf - j < 32 ? tf - j : 32;
+        k1_columns<NW, false, false, false, KPOSW>(st, acc, PtrSyms{p.tcodes + ws + j}, cntj, ws + j, rec, slot, nullptr, nullptr, 0);
+        if (st.up - st.down - (len - (j + cntj)) >= st.best) {
+            hopeless = true;
+            break;
+        }
+    }
+    if (!hopeless)
+        k1_columns<NW, false, true, false, KPOSW>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
     rec->best = st.best;
     rec->cnt = st.cnt;
 }
@@ -1087,7 +1099,15 @@ EB_HD void split_node(const SplitParams& p, int nodeIdx) {
 
 // Presence set of one item (<= 64 KiB of raw bytes), OR-ed into its destination set.
 EB_HD void mask_item(const MaskParams& p, int itemIdx, int first, int stride) {
-    const MaskItem it = p.items[itemIdx];
+    MaskItem it;
+    if (itemIdx < p.numItems) {
+        it = p.items[itemIdx];
+    } else {
+        const int q = itemIdx - p.numItems;
+        it.off = p.qoff[q];
+        it.len = p.qlen[q] <= 65536 ? p.qlen[q] : 0;
+        it.dst = q;
+    }
     uint32_t local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint8_t* s = p.raw + it.off;
     for (int i = first; i < it.len; i += stride) {

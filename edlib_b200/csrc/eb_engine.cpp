@@ -19,6 +19,9 @@
 #include <algorithm>
 #include <cmath>
 #include <functional>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <chrono>
 #include <map>
 #include <stdexcept>
@@ -38,6 +41,7 @@ EngineTunables::EngineTunables() {
     ovfCap = env_int("EDLIB_B200_OVF_CAP", ovfCap);
     filterK0 = env_int("EDLIB_B200_FILTER_K0", filterK0);
     filterK1 = env_int("EDLIB_B200_FILTER_K1", filterK1);
+    packParallelBytes = (size_t)env_int("EDLIB_B200_PACK_PARALLEL_KB", (int)(packParallelBytes >> 10)) << 10;
     filterSeedK = env_int("EDLIB_B200_FILTER_SEED_K", filterSeedK);
     filterSeedBucket = env_int("EDLIB_B200_FILTER_SEED_BUCKET", filterSeedBucket);
     filterMaxWindows = env_int("EDLIB_B200_FILTER_MAX_WINDOWS", filterMaxWindows);
@@ -63,18 +67,94 @@ struct Trace {
     }
 };
 
-// fn(begin, end) over [0, n) on up to 16 host threads (only when every thread gets >= grain items).
+// Persistent host worker threads (spawning threads per loop costs more than most of these loops): run(n, fn)
+// executes fn(0) .. fn(n-1), the caller taking part, and returns when all are done.  One client at a time
+// (the engine runs under the library's lock).  The workers live until the process ends.
+class HostPool {
+public:
+    static HostPool& get() {
+        static HostPool* pool = new HostPool();  // never destroyed: workers may still be parked at exit
+        return *pool;
+    }
+    size_t width() const { return workers_ + 1; }
+    void run(size_t n, const std::function<void(size_t)>& fn) {
+        if (n == 0) return;
+        if (n == 1 || workers_ == 0) {
+            for (size_t i = 0; i < n; ++i) fn(i);
+            return;
+        }
+        unsigned long long gen;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            fn_ = &fn;
+            total_ = n;
+            next_ = 0;
+            pending_ = n;
+            gen = ++generation_;
+        }
+        cv_.notify_all();
+        work(gen);
+        std::unique_lock<std::mutex> lock(mu_);
+        done_.wait(lock, [this]() { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    HostPool() {
+        const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+        workers_ = std::min<size_t>(16, hw) - 1;
+        for (size_t i = 0; i < workers_; ++i) std::thread([this]() { loop(); }).detach();
+    }
+    // Tasks are few and coarse, so they are claimed under the lock; a worker only ever claims tasks of
+    // the generation it woke up for.
+    void work(unsigned long long gen) {
+        for (;;) {
+            const std::function<void(size_t)>* fn;
+            size_t i;
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                if (generation_ != gen || next_ >= total_) return;
+                i = next_++;
+                fn = fn_;
+            }
+            (*fn)(i);
+            std::lock_guard<std::mutex> lock(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_.wait(lock, [&]() { return generation_ != seen; });
+                seen = generation_;
+            }
+            work(seen);
+        }
+    }
+    size_t workers_ = 0;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t total_ = 0, pending_ = 0, next_ = 0;
+    unsigned long long generation_ = 0;
+};
+
+// number of parts a loop over n items is cut into (every part gets >= grain items)
+inline size_t host_parts(size_t n, size_t grain) {
+    return std::max<size_t>(1, std::min<size_t>(HostPool::get().width(), n / std::max<size_t>(grain, 1)));
+}
+
+// fn(begin, end) over [0, n) on the host workers (only when every part gets >= grain items).
 template <class F>
 void parallel_ranges(size_t n, size_t grain, F fn) {
-    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nthr = std::min<size_t>(std::min<size_t>(16, hw), n / std::max<size_t>(grain, 1));
+    const size_t nthr = host_parts(n, grain);
     if (nthr <= 1) {
         fn((size_t)0, n);
         return;
     }
-    std::vector<std::thread> th;
-    for (size_t t = 0; t < nthr; ++t) th.emplace_back([=]() { fn(n * t / nthr, n * (t + 1) / nthr); });
-    for (auto& x : th) x.join();
+    HostPool::get().run(nthr, [&](size_t t) { fn(n * t / nthr, n * (t + 1) / nthr); });
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -227,19 +307,34 @@ public:
 Prepared* Engine::prepare(const BatchInput& in) {
     Backend* be = be_;
     Trace trace;
-    Prepared* p = new Prepared();
+    // the host vectors of the previous batch are reused (their pages stay mapped)
+    Prepared* p = spare_ ? spare_ : new Prepared();
+    spare_ = nullptr;
     try {
+        p->tg.clear();
+        p->hasEq = false;
+        p->ncodes = 0;
+        p->computed = false;
         p->be = be;
         p->N = in.numPairs;
         p->cfg = in.config;
         p->mode = (in.config.mode == EDLIB_MODE_SHW) ? MODE_SHW : (in.config.mode == EDLIB_MODE_HW) ? MODE_HW : MODE_NW;
         const int N = p->N;
-        p->qlen.assign(in.queryLengths, in.queryLengths + N);
-        p->tlen.assign(in.targetLengths, in.targetLengths + N);
+        p->qlen.resize(N);
+        p->tlen.resize(N);
         p->tidx.resize(N);
         p->qoff.resize(N);
-        for (int i = 0; i < N; ++i)
-            if (p->qlen[i] < 0 || p->tlen[i] < 0) throw std::runtime_error("negative sequence length");
+        {
+            std::vector<int> bad(1, 0);
+            parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i) {
+                    p->qlen[i] = in.queryLengths[i];
+                    p->tlen[i] = in.targetLengths[i];
+                    if (p->qlen[i] < 0 || p->tlen[i] < 0) bad[0] = 1;
+                }
+            });
+            if (bad[0]) throw std::runtime_error("negative sequence length");
+        }
 
         // identical (pointer, length) targets are uploaded and encoded once
         struct Key {
@@ -251,22 +346,49 @@ Prepared* Engine::prepare(const BatchInput& in) {
             size_t operator()(const Key& k) const { return std::hash<const void*>()(k.ptr) * 31 + (size_t)k.len; }
         };
         std::unordered_map<Key, int, KeyHash> seen;
-        for (int i = 0; i < N; ++i) {
+        Key lastKey{nullptr, -1};
+        int lastIdx = -1;
+        bool oneTarget = N > 0;  // the usual batch shape (reads over one shared target), checked in parallel
+        if (N >= 131072) {
+            std::vector<int> differs(1, 0);
+            const Key first{in.targets[0], in.targetLengths[0]};
+            parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i)
+                    if (in.targets[i] != first.ptr || in.targetLengths[i] != first.len) differs[0] = 1;
+            });
+            oneTarget = !differs[0];
+        } else {
+            oneTarget = false;
+        }
+        if (oneTarget) {
+            p->tg.push_back(Target{in.targets[0], in.targetLengths[0], 0});
+            parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i) p->tidx[i] = 0;
+            });
+        }
+        for (int i = 0; i < N && !oneTarget; ++i) {
             Key k{in.targets[i], in.targetLengths[i]};
-            auto it = seen.find(k);
-            if (it == seen.end()) {
-                it = seen.emplace(k, (int)p->tg.size()).first;
-                p->tg.push_back(Target{k.ptr, k.len, 0});
+            if (!(k == lastKey)) {  // neighbours usually share their target
+                auto it = seen.find(k);
+                if (it == seen.end()) {
+                    it = seen.emplace(k, (int)p->tg.size()).first;
+                    p->tg.push_back(Target{k.ptr, k.len, 0});
+                }
+                lastKey = k;
+                lastIdx = it->second;
             }
-            p->tidx[i] = it->second;
+            p->tidx[i] = lastIdx;
         }
         const int T = (int)p->tg.size();
+        trace.mark("prepare: lengths + distinct targets");
 
         // pack: queries back to back, then every target 16-aligned with >= 16 bytes of slack
         size_t total = 0;
+        std::vector<int> longQueries;  // beyond one presence-set work item
         for (int i = 0; i < N; ++i) {
             p->qoff[i] = total;
             total += (size_t)p->qlen[i];
+            if (p->qlen[i] > 65536) longQueries.push_back(i);
         }
         total = round_up(total, 16);
         for (int t = 0; t < T; ++t) {
@@ -275,13 +397,21 @@ Prepared* Engine::prepare(const BatchInput& in) {
         }
         total += 16;
         uint8_t* stage = static_cast<uint8_t*>(be->alloc_host(total));
+        p->dSeq.alloc(be, total);
+        // the small per-pair arrays go first: they would otherwise queue behind the sequences
+        p->dQoff.alloc(be, N);
+        p->dQoff.upload(p->qoff.data(), N);
+        p->dQlen.alloc(be, N);
+        p->dQlen.upload(p->qlen.data(), N);
+        trace.mark("prepare: offsets + buffers");
         {
-            // Pure memcpy work, split by bytes over a few host threads when the batch is large:
-            // items 0..N-1 are the queries, N..N+T-1 the distinct targets.
+            // Pure memcpy work, split by bytes over a few host threads when the batch is large: items
+            // 0..N-1 are the queries, N..N+T-1 the distinct targets.  Every thread uploads its own byte
+            // range as soon as it is packed, so the host->device copy overlaps the packing.
             const size_t qBytes = N ? (size_t)(p->qoff[N - 1] + (uint64_t)p->qlen[N - 1]) : 0;
             size_t allBytes = qBytes;
             for (int t = 0; t < T; ++t) allBytes += (size_t)p->tg[t].len;
-            const int nthr = allBytes > (32u << 20) ? (int)std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+            const int nthr = allBytes > tun.packParallelBytes ? (int)HostPool::get().width() : 1;
             auto copy_item = [&](int it) {
                 if (it < N) {
                     if (p->qlen[it]) memcpy(stage + p->qoff[it], in.queries[it], (size_t)p->qlen[it]);
@@ -290,82 +420,100 @@ Prepared* Engine::prepare(const BatchInput& in) {
                     if (g.len) memcpy(stage + g.off, g.ptr, (size_t)g.len);
                 }
             };
+            auto item_off = [&](int it) -> size_t {  // first staging byte of item `it` (N + T: the end)
+                if (it >= N + T) return total;
+                return it < N ? (size_t)p->qoff[it] : p->tg[it - N].off;
+            };
+            // padding first: it lies between the items and travels with the neighbouring byte ranges
+            {
+                size_t pos = qBytes;
+                size_t end = p->tg.empty() ? total : p->tg[0].off;
+                memset(stage + pos, 0, end - pos);
+                for (int t = 0; t < T; ++t) {
+                    const Target& g = p->tg[t];
+                    const size_t next = (t + 1 < T) ? p->tg[t + 1].off : total;
+                    memset(stage + g.off + g.len, 0, next - g.off - (size_t)g.len);
+                }
+            }
             if (nthr > 1) {
                 // contiguous item ranges of roughly equal byte counts
                 std::vector<int> cut(nthr + 1, N + T);
                 cut[0] = 0;
-                size_t acc = 0;
-                int next = 1;
-                for (int it = 0; it < N + T && next < nthr; ++it) {
-                    acc += it < N ? (size_t)p->qlen[it] : (size_t)p->tg[it - N].len;
-                    if (acc >= allBytes * next / nthr) cut[next++] = it + 1;
+                {
+                    size_t tAcc = qBytes;  // bytes before target `tt`
+                    int tt = 0;
+                    for (int c = 1; c < nthr; ++c) {
+                        const size_t want = allBytes * c / nthr;
+                        if (want < qBytes) {  // qoff is the running byte count of the queries
+                            cut[c] = (int)(std::upper_bound(p->qoff.begin(), p->qoff.end(), (uint64_t)want) - p->qoff.begin());
+                        } else {
+                            while (tt < T && tAcc + (size_t)p->tg[tt].len <= want) tAcc += (size_t)p->tg[tt++].len;
+                            cut[c] = N + tt;
+                        }
+                        if (cut[c] < cut[c - 1]) cut[c] = cut[c - 1];
+                    }
                 }
-                std::vector<std::thread> th;
-                for (int t = 0; t < nthr; ++t)
-                    th.emplace_back([&, t]() {
+                std::vector<std::string> errs(nthr);
+                HostPool::get().run((size_t)nthr, [&](size_t t) {
+                    try {
                         for (int it = cut[t]; it < cut[t + 1]; ++it) copy_item(it);
-                    });
-                for (auto& x : th) x.join();
+                        const size_t a = t == 0 ? 0 : item_off(cut[t]), b = item_off(cut[t + 1]);
+                        if (b > a) be->h2d(p->dSeq.p + a, stage + a, b - a);
+                    } catch (const std::exception& e) {
+                        errs[t] = e.what();
+                    }
+                });
+                for (auto& e : errs)
+                    if (!e.empty()) throw std::runtime_error(e);
             } else {
                 for (int it = 0; it < N + T; ++it) copy_item(it);
-            }
-            size_t pos = qBytes;
-            size_t end = p->tg.empty() ? total : p->tg[0].off;
-            memset(stage + pos, 0, end - pos);
-            for (int t = 0; t < T; ++t) {
-                const Target& g = p->tg[t];
-                const size_t next = (t + 1 < T) ? p->tg[t + 1].off : total;
-                memset(stage + g.off + g.len, 0, next - g.off - (size_t)g.len);
+                p->dSeq.upload(stage, total);
             }
         }
         trace.mark("prepare: pack");
-        p->dSeq.alloc(be, total);
-        p->dSeq.upload(stage, total);
         stats.h2dBytes += (long long)total;
-        p->dQoff.alloc(be, N);
-        p->dQoff.upload(p->qoff.data(), N);
-        p->dQlen.alloc(be, N);
-        p->dQlen.upload(p->qlen.data(), N);
 
-        // byte-presence sets: one per query, one per distinct target, one union for the batch.  Work items
-        // cover at most 65536 bytes each; they are laid out (counts, offsets, fill) on a few host threads
-        // straight into staging memory.
-        auto pieces = [](int len) { return (len + 65535) / 65536; };
-        std::vector<size_t> itemAt((size_t)N + T + 1, 0);
-        parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
-            for (size_t i = lo; i < hi; ++i) itemAt[i + 1] = (size_t)pieces(p->qlen[i]);
-        });
-        for (int t = 0; t < T; ++t) itemAt[(size_t)N + t + 1] = (size_t)pieces(p->tg[t].len);
-        for (size_t i = 0; i < (size_t)N + T; ++i) itemAt[i + 1] += itemAt[i];
-        const size_t numItems = itemAt[(size_t)N + T];
-        HostBuf<MaskItem> items(be, numItems);
+        // byte-presence sets: one per query, one per distinct target, one union for the batch.  Queries are
+        // implicit work items of the kernel; explicit ones (at most 65536 bytes each) are only needed for
+        // the targets and for the pieces of longer queries.
+        std::vector<MaskItem> items;
+        auto add_items = [&](uint64_t off, int len, int dst) {
+            for (int s0 = 0; s0 < len; s0 += 65536) items.push_back(MaskItem{off + (uint64_t)s0, std::min(65536, len - s0), dst});
+        };
+        for (int i : longQueries) add_items(p->qoff[i], p->qlen[i], i);
+        for (int t = 0; t < T; ++t) add_items(p->tg[t].off, p->tg[t].len, N + t);
         HostBuf<int> tset(be, (size_t)N);
-        parallel_ranges((size_t)N + T, 65536, [&](size_t lo, size_t hi) {
-            for (size_t i = lo; i < hi; ++i) {
-                const uint64_t off = i < (size_t)N ? p->qoff[i] : p->tg[i - N].off;
-                const int len = i < (size_t)N ? p->qlen[i] : p->tg[i - N].len;
-                size_t at = itemAt[i];
-                for (int s0 = 0; s0 < len; s0 += 65536) items[at++] = MaskItem{off + (uint64_t)s0, std::min(65536, len - s0), (int)i};
-                if (i < (size_t)N) tset[i] = N + p->tidx[i];
-            }
+        parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) tset[i] = N + p->tidx[i];
         });
         const int unionSet = N + T;
         DevBuf<uint32_t> dMasks(be, (size_t)(N + T + 1) * 8);
         be->zero(dMasks.p, (size_t)(N + T + 1) * 8 * sizeof(uint32_t));
-        DevBuf<MaskItem> dItems(be, numItems);
-        if (numItems) {
-            dItems.upload(items.p, numItems);
-            MaskParams mp{p->dSeq.p, dItems.p, (int)numItems, dMasks.p, unionSet};
-            be->launch_mask(mp);
+        DevBuf<MaskItem> dItems(be, items.size());
+        if (!items.empty()) dItems.upload(items.data(), items.size());
+        {
+            MaskParams mp;
+            memset(&mp, 0, sizeof(mp));
+            mp.raw = p->dSeq.p;
+            mp.items = dItems.p;
+            mp.numItems = (int)items.size();
+            mp.qoff = p->dQoff.p;
+            mp.qlen = p->dQlen.p;
+            mp.numQueries = N;
+            mp.masks = dMasks.p;
+            mp.unionSet = unionSet;
+            if (mp.numItems + mp.numQueries > 0) be->launch_mask(mp);
         }
         DevBuf<int> dTset(be, N), dAlpha(be, N);
         dTset.upload(tset.p, N);
+        trace.mark("prepare: mask items");
         be->launch_alpha_len(dMasks.p, nullptr, dTset.p, N, dAlpha.p);
         p->alphaLen.resize(N);
         dAlpha.download(p->alphaLen.data(), N);
         uint32_t uni[8];
         be->d2h(uni, dMasks.p + (size_t)unionSet * 8, sizeof(uni));
         stats.d2hBytes += (long long)N * 4 + 32;
+        trace.mark("prepare: alphabet lengths back");
 
         // dense codes in ascending byte order; absent bytes (padding) map to code 0
         uint8_t map[256];
@@ -1133,7 +1281,9 @@ struct Pass {
             dThr.upload(hThr.p, g);
             DevBuf<SeedPlan> dPlan(be, g);
             DevBuf<int> wPair, wK, wStart, wLen, wTf;
-            int cap = 4 * g + 1024, V = 0;
+            // room for the window jobs: sized from what the previous pass of this level needed per read
+            int& perRead = eng.scratch.seedWindowsPerRead[level];
+            int cap = (int)std::min<long long>((long long)g * std::max(perRead + 2, level ? 96 : 8) + 4096, 1LL << 28), V = 0;
             for (;;) {
                 wPair.alloc(be, cap);
                 wK.alloc(be, cap);
@@ -1171,6 +1321,7 @@ struct Pass {
                 if (V <= cap) break;
                 cap = V;  // window list overflow: repeat with the exact size
             }
+            perRead = (int)(((long long)V + g - 1) / g);
             trace.mark("filter: seeds planned");
             DevBuf<WinRec> dWinRecs(be, (size_t)std::max(V, 1));
             if (V > 0) {
@@ -1224,20 +1375,11 @@ struct Pass {
             std::vector<Part> parts;
             std::vector<size_t> partLo;
             {
-                const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-                const size_t nparts = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, hw), (size_t)g / 65536));
+                const size_t nparts = host_parts((size_t)g, 65536);
                 parts.resize(nparts);
                 for (size_t t2 = 0; t2 <= nparts; ++t2) partLo.push_back((size_t)g * t2 / nparts);
             }
-            auto for_parts = [&](const std::function<void(size_t)>& fn) {
-                if (parts.size() == 1) {
-                    fn(0);
-                    return;
-                }
-                std::vector<std::thread> th;
-                for (size_t t2 = 0; t2 < parts.size(); ++t2) th.emplace_back([&fn, t2]() { fn(t2); });
-                for (auto& x : th) x.join();
-            };
+            auto for_parts = [&](const std::function<void(size_t)>& fn) { HostPool::get().run(parts.size(), fn); };
             for_parts([&](size_t t2) {
                 Part& P = parts[t2];
                 for (size_t i = partLo[t2]; i < partLo[t2 + 1]; ++i) {
@@ -1593,18 +1735,11 @@ struct Pass {
             const int W64 = ceil_div(m, 64) * 64 - m;
             return posLen[i] + ((best[i] == m && W64 > 0) ? 1 : 0);
         };
-        const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-        const size_t nparts = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, hw), (size_t)N / 65536));
+        const size_t nparts = host_parts((size_t)N, 65536);
         std::vector<long long> partCount(nparts + 1, 0);
         std::vector<int> bad(nparts, 0);
         auto run = [&](const std::function<void(size_t, size_t, size_t)>& fn) {
-            if (nparts == 1) {
-                fn(0, 0, (size_t)N);
-                return;
-            }
-            std::vector<std::thread> th;
-            for (size_t t = 0; t < nparts; ++t) th.emplace_back([&fn, t, this, nparts]() { fn(t, (size_t)N * t / nparts, (size_t)N * (t + 1) / nparts); });
-            for (auto& x : th) x.join();
+            HostPool::get().run(nparts, [&](size_t t) { fn(t, (size_t)N * t / nparts, (size_t)N * (t + 1) / nparts); });
         };
         run([&](size_t t, size_t lo, size_t hi) {
             long long c = 0;
@@ -1930,18 +2065,21 @@ void Engine::compute(Prepared* p) {
     Trace& trace = ps.trace;
 
     // ---- classification -----------------------------------------------------------------
-    std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, nw32) -> pairs, ascending
+    // (target, nw32) -> pairs, ascending.  The lists live in the engine's scratch: a batch shaped like the
+    // previous one refills them without new allocations.
+    std::map<std::pair<int, int>, std::vector<int>>& groups = scratch.groups;
+    for (auto& kv : groups) kv.second.clear();
     {
         // contiguous ranges of pairs are classified on a few host threads and concatenated in order
-        const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-        const size_t nparts = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, hw), (size_t)N / 65536));
-        struct Part {
-            std::map<std::pair<int, int>, std::vector<int>> groups;
-            std::vector<int> wPairs;
-        };
-        std::vector<Part> parts(nparts);
+        const size_t nparts = host_parts((size_t)N, 65536);
+        std::vector<EngineScratch::Part>& parts = scratch.parts;
+        parts.resize(nparts);
+        for (auto& P : parts) {
+            for (auto& kv : P.groups) kv.second.clear();
+            P.wPairs.clear();
+        }
         auto classify = [&](size_t t) {
-            Part& P = parts[t];
+            EngineScratch::Part& P = parts[t];
             std::pair<int, int> lastKey(-1, -1);
             std::vector<int>* lastList = nullptr;
             const int lo = (int)((size_t)N * t / nparts), hi = (int)((size_t)N * (t + 1) / nparts);
@@ -1963,25 +2101,17 @@ void Engine::compute(Prepared* p) {
                 }
             }
         };
-        if (nparts == 1) {
-            classify(0);
-        } else {
-            std::vector<std::thread> th;
-            for (size_t t = 0; t < nparts; ++t) th.emplace_back([&classify, t]() { classify(t); });
-            for (auto& x : th) x.join();
-        }
-        if (nparts == 1) {
-            groups.swap(parts[0].groups);
-            wPairs.swap(parts[0].wPairs);
-        } else {
-            for (Part& P : parts) {
-                for (auto& kv : P.groups) {
-                    std::vector<int>& dst = groups[kv.first];
-                    dst.insert(dst.end(), kv.second.begin(), kv.second.end());
-                }
-                wPairs.insert(wPairs.end(), P.wPairs.begin(), P.wPairs.end());
+        HostPool::get().run(nparts, classify);
+        for (EngineScratch::Part& P : parts) {
+            for (auto& kv : P.groups) {
+                if (kv.second.empty()) continue;
+                std::vector<int>& dst = groups[kv.first];
+                dst.insert(dst.end(), kv.second.begin(), kv.second.end());
             }
+            wPairs.insert(wPairs.end(), P.wPairs.begin(), P.wPairs.end());
         }
+        // drop the keys this batch does not use (bounded memory across differently shaped batches)
+        for (auto it = groups.begin(); it != groups.end();) it = it->second.empty() ? groups.erase(it) : std::next(it);
     }
 
     // ---- K1 groups ----------------------------------------------------------------------
@@ -2066,7 +2196,21 @@ void Engine::materialize(Prepared* p, EdlibAlignResult* results) {
     trace.mark("materialize");
 }
 
-void Engine::release(Prepared* p) { delete p; }
+void Engine::release(Prepared* p) {
+    if (!p) return;
+    if (spare_) {
+        delete p;
+        return;
+    }
+    // keep the object for the next batch: device buffers go back to the pool now
+    p->dSeq.reset();
+    p->dQoff.reset();
+    p->dQlen.reset();
+    p->dEqtab.reset();
+    spare_ = p;
+}
+
+Engine::~Engine() { delete spare_; }
 
 int Engine::align_batch(const BatchInput& in, EdlibAlignResult* results) {
     Prepared* p = nullptr;

@@ -7,7 +7,9 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/edlib.h"
@@ -69,6 +71,7 @@ struct EngineTunables {
     int k1MinChunk = 1024;        // smallest target chunk (columns) when one HW sweep is split
     int ovfCap = 1 << 20;         // overflow entries per launch before the exact-size retry
     size_t sliceBytes = 1ull << 30;  // device memory budget of one slice of W jobs
+    size_t packParallelBytes = 32u << 20;  // batches above this are packed and uploaded by several host threads
     // Candidate filter for HW sweeps of reads over a shared target, three stages (0 disables one):
     // exact seeds looked up in a hash index of the target (pigeonhole: t+1 disjoint seeds for threshold
     // t); then, for the reads still undecided, a
@@ -101,6 +104,13 @@ struct EngineStats {
 struct EngineScratch {
     std::vector<int> best, cnt, posLen, posPool;
     std::vector<long long> posStart;
+    struct Part {
+        std::map<std::pair<int, int>, std::vector<int>> groups;
+        std::vector<int> wPairs;
+    };
+    std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, word class) -> pairs
+    std::vector<Part> parts;
+    int seedWindowsPerRead[2] = {0, 0};  // seed stage: windows per read the previous pass produced
 };
 
 class Prepared;  // a batch whose inputs are resident on the device
@@ -108,6 +118,7 @@ class Prepared;  // a batch whose inputs are resident on the device
 class Engine {
 public:
     explicit Engine(Backend* be) : be_(be) {}
+    ~Engine();
     // One-shot: prepare + compute + materialise.  Returns EDLIB_STATUS_OK / EDLIB_STATUS_ERROR.
     int align_batch(const BatchInput& in, EdlibAlignResult* results);
 
@@ -124,6 +135,7 @@ public:
 
 private:
     Backend* be_;
+    Prepared* spare_ = nullptr;  // released batch object whose host vectors the next prepare() reuses
 };
 
 }  // namespace eb

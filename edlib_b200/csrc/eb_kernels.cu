@@ -389,7 +389,7 @@ __global__ void scan_apply_kernel(int* data, int count, const int* tileSums) {
 
 __global__ void mask_kernel(const MaskParams p) {
     const int item = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
-    if (item >= p.numItems) return;
+    if (item >= p.numItems + p.numQueries) return;
     mask_item(p, item, threadIdx.x & 31, 32);
 }
 
@@ -552,7 +552,7 @@ struct CudaBackend : Backend {
 
     void launch_mask(const MaskParams& p) override {
         Scope s(this, "mask");
-        mask_kernel<<<(p.numItems + W_WARPS - 1) / W_WARPS, W_WARPS * 32, 0, stream>>>(p);
+        mask_kernel<<<(p.numItems + p.numQueries + W_WARPS - 1) / W_WARPS, W_WARPS * 32, 0, stream>>>(p);
         check_launch("mask");
     }
     void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int n, int* out) override {

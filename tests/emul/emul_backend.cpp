@@ -99,7 +99,7 @@ struct EmulBackend : Backend {
     }
     void launch_mask(const MaskParams& p) override {
         ++launchesCount;
-        for (int i = 0; i < p.numItems; ++i) mask_item(p, i, 0, 1);
+        for (int i = 0; i < p.numItems + p.numQueries; ++i) mask_item(p, i, 0, 1);
     }
     void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int n, int* out) override {
         ++launchesCount;

@@ -88,17 +88,34 @@ def test_candidate_filter_all_branches():
 
 
 def test_large_batch_uses_the_threaded_host_paths():
-    """> 131072 pairs: classification, seed-stage outcomes and end-location assembly run on several host
-    threads; every result still equals the reference's."""
+    """> 131072 pairs: packing + upload, classification, seed-stage outcomes and end-location assembly run
+    on several host threads; every result still equals the reference's."""
     code = (
         "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "import parity, cases, test_engine_emul as T\n"
         "lib = T.load_emul()\n"
         "print(parity.run_batches(lib, 3, 1, gen=lambda seed, count: [cases.big_batch_case(seed)]))\n"
     ) % (REPO, os.path.join(REPO, "tests"))
-    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128")
+    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_PACK_PARALLEL_KB="1024")
     out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
     assert int(out.stdout.strip().splitlines()[-1]) == 140000
+
+
+def test_sequences_longer_than_one_presence_item(emul):
+    """Queries and targets above 65536 bytes are split into several presence-set work items
+    (alphabetLength) and sweep as usual."""
+    import random
+    from helpers import mutate, rand_seq
+    chk = parity.checker()
+    rng = random.Random(9)
+    q = rand_seq(rng, 70000, b"ACGTN")
+    t = mutate(rng, q, 0.001, b"ACGT")
+    assert emul.align(q, t, -1, 0, 0) == chk.align(q, t, -1, 0, 0)
+    pairs = [(q, t), (b"ACGT" * 10, t), (q[:66000], b"AXY")]
+    st, res = emul.align_batch([a for a, _ in pairs], [b for _, b in pairs], -1, 2, 0)
+    assert st == 0
+    for (a, b), r in zip(pairs, res):
+        assert r == chk.align(a, b, -1, 2, 0)
 
 
 def test_many_end_locations(emul):
