@@ -55,7 +55,11 @@ def test_candidate_filter_all_branches():
         "from helpers import product\n"
         "print(parity.run_batches(product(), 26, 40, gen=cases.filter_cases))\n"
     ) % (REPO, os.path.join(REPO, "tests"))
-    for extra in ({}, {"EDLIB_B200_FILTER_K0": "4", "EDLIB_B200_FILTER_SPREAD": "64", "EDLIB_B200_K1_MIN_CHUNK": "64"}):
+    for extra in ({}, {"EDLIB_B200_FILTER_K0": "4", "EDLIB_B200_FILTER_K1": "2", "EDLIB_B200_FILTER_SPREAD": "64",
+                       "EDLIB_B200_FILTER_MAX_WINDOWS": "2", "EDLIB_B200_K1_MIN_CHUNK": "64"},
+                  {"EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "3", "EDLIB_B200_FILTER_SEED_BUCKET": "2"},
+                  {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "12", "EDLIB_B200_FILTER_SEED_K": "0"},
+                  {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "40"}):
         env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 500
@@ -100,7 +104,7 @@ def test_concurrent_callers(lib):
 
 def test_results_do_not_depend_on_the_plan():
     """Size-independent property on a config-2-shaped batch too large for the CPU checker: the same
-    200k reads give identical results with the candidate filter on/off and under different chunkings."""
+    200k reads give identical results with every subset of the filter stages and under different chunkings."""
     import hashlib
     import subprocess
     from edlib_b200._ffi import REPO
@@ -126,8 +130,14 @@ def test_results_do_not_depend_on_the_plan():
         "print(h.hexdigest(), float(res['editDistance'].mean()))\n"
     ) % REPO
     digests = []
-    for extra in ({}, {"EDLIB_B200_FILTER_K0": "0"}, {"EDLIB_B200_FILTER_K0": "5", "EDLIB_B200_K1_MIN_CHUNK": "4096"},
-                  {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_K1_MIN_CHUNK": "200000"}):
+    off = {"EDLIB_B200_FILTER_SEED_K": "0", "EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_K0": "0"}
+    for extra in ({}, {"EDLIB_B200_PACK_PARALLEL_KB": "1024"},                      # seed stages; threaded pack + upload
+                  off,                                                              # no filter: plain sweeps
+                  {"EDLIB_B200_FILTER_SEED_K": "0"},                                # prefix stages only
+                  {"EDLIB_B200_FILTER_SEED_K": "0", "EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_K0": "5",
+                   "EDLIB_B200_K1_MIN_CHUNK": "4096"},                              # tight 64-row stage, other chunking
+                  {"EDLIB_B200_FILTER_SEED_K": "6", "EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_K0": "0"},  # seeds only, low t
+                  dict(off, EDLIB_B200_K1_MIN_CHUNK="200000")):
         out = subprocess.run(["python", "-c", code], env=dict(os.environ, **extra), check=True, capture_output=True, text=True)
         digests.append(out.stdout.strip().split()[0])
     assert len(set(digests)) == 1, digests
