@@ -1097,8 +1097,8 @@ EB_HD void split_node(const SplitParams& p, int nodeIdx) {
     p.out[nodeIdx] = o;
 }
 
-// Presence set of one item (<= 64 KiB of raw bytes), OR-ed into its destination set.
-EB_HD void mask_item(const MaskParams& p, int itemIdx, int first, int stride) {
+// Presence set of one item (<= 64 KiB of raw bytes): the bytes at first, first+stride, ... into local[8].
+EB_HD MaskItem mask_item_scan(const MaskParams& p, int itemIdx, int first, int stride, uint32_t (&local)[8]) {
     MaskItem it;
     if (itemIdx < p.numItems) {
         it = p.items[itemIdx];
@@ -1108,17 +1108,29 @@ EB_HD void mask_item(const MaskParams& p, int itemIdx, int first, int stride) {
         it.len = p.qlen[q] <= 65536 ? p.qlen[q] : 0;
         it.dst = q;
     }
-    uint32_t local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 8; ++k) local[k] = 0;
     const uint8_t* s = p.raw + it.off;
     for (int i = first; i < it.len; i += stride) {
         const uint32_t b = s[i];
         local[b >> 5] |= 1u << (b & 31);
     }
-    for (int k = 0; k < 8; ++k)
-        if (local[k]) {
-            atomic_or_u32(&p.masks[(size_t)it.dst * 8 + k], local[k]);
-            if (p.unionSet >= 0) atomic_or_u32(&p.masks[(size_t)p.unionSet * 8 + k], local[k]);
-        }
+    return it;
+}
+// OR word k of an item's presence set into its destination set and into the union set.  The union is
+// read first: after the first few items it already holds every byte value, and the atomics disappear.
+EB_HD void mask_item_commit(const MaskParams& p, int dst, int k, uint32_t bits) {
+    if (!bits) return;
+    atomic_or_u32(&p.masks[(size_t)dst * 8 + k], bits);
+    if (p.unionSet >= 0) {
+        uint32_t* u = &p.masks[(size_t)p.unionSet * 8 + k];
+        if (bits & ~*u) atomic_or_u32(u, bits);
+    }
+}
+// Whole item by one caller (host emulation).
+EB_HD void mask_item(const MaskParams& p, int itemIdx, int first, int stride) {
+    uint32_t local[8];
+    const MaskItem it = mask_item_scan(p, itemIdx, first, stride, local);
+    for (int k = 0; k < 8; ++k) mask_item_commit(p, it.dst, k, local[k]);
 }
 
 // alphabetLength of one pair: distinct byte values in query and target together

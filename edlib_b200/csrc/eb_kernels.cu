@@ -390,7 +390,16 @@ __global__ void scan_apply_kernel(int* data, int count, const int* tileSums) {
 __global__ void mask_kernel(const MaskParams p) {
     const int item = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
     if (item >= p.numItems + p.numQueries) return;
-    mask_item(p, item, threadIdx.x & 31, 32);
+    // lanes stride over the bytes; the eight words are OR-reduced across the warp and lane k commits word k
+    uint32_t local[8];
+    const MaskItem it = mask_item_scan(p, item, threadIdx.x & 31, 32, local);
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t v = __reduce_or_sync(0xffffffffu, local[k]);
+        if ((int)(threadIdx.x & 31) == k) mine = v;
+    }
+    if ((threadIdx.x & 31) < 8) mask_item_commit(p, it.dst, (int)(threadIdx.x & 31), mine);
 }
 
 __global__ void alpha_len_kernel(const uint32_t* masks, const int* qset, const int* tset, int n, int* out) {
