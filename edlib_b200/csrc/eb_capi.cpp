@@ -6,8 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <mutex>
 #include <algorithm>
+#include <mutex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,15 @@ eb::Engine* engine_locked() {
         g_initTried = true;
         g_backend = eb::create_backend(&g_initError);
         if (g_backend) g_engine = new eb::Engine(g_backend);
+    }
+    // the caller may be any host thread: CUDA's current device is per thread
+    if (g_backend) {
+        try {
+            g_backend->bind_thread();
+        } catch (const std::exception& e) {
+            if (g_engine) g_engine->lastError = e.what();
+            return nullptr;
+        }
     }
     return g_engine;
 }
@@ -223,7 +233,7 @@ EDLIB_API int edlibB200BatchResults(EdlibB200Batch* batch, EdlibAlignResult* res
 
 EDLIB_API void edlibB200BatchFree(EdlibB200Batch* batch) {
     std::lock_guard<std::mutex> lock(g_mu);
-    if (g_engine && batch) g_engine->release(reinterpret_cast<eb::Prepared*>(batch));
+    if (batch && engine_locked()) g_engine->release(reinterpret_cast<eb::Prepared*>(batch));
 }
 
 EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {

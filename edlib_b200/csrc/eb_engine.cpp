@@ -458,6 +458,7 @@ Prepared* Engine::prepare(const BatchInput& in) {
                     try {
                         for (int it = cut[t]; it < cut[t + 1]; ++it) copy_item(it);
                         const size_t a = t == 0 ? 0 : item_off(cut[t]), b = item_off(cut[t + 1]);
+                        be->bind_thread();  // a pool worker: select the backend's device before the copy
                         if (b > a) be->h2d(p->dSeq.p + a, stage + a, b - a);
                     } catch (const std::exception& e) {
                         errs[t] = e.what();

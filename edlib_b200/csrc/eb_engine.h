@@ -29,6 +29,9 @@ struct Backend {
     virtual void zero(void* dst, size_t bytes) = 0;
     virtual void fill(void* dst, int byteValue, size_t bytes) = 0;
     virtual void sync() = 0;
+    // Makes the calling host thread use this backend's device (CUDA keeps the current device per thread):
+    // called on entry of every API call and by pool workers before they issue copies.
+    virtual void bind_thread() {}
     virtual int sm_count() = 0;
     // Launch shape of the lane-per-alignment kernel for a word class / alphabet size: threads per
     // CTA and how many CTAs are resident on the whole device at once (for wave-aware chunking).

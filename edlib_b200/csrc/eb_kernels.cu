@@ -450,10 +450,12 @@ struct CudaBackend : Backend {
     int launchCount = 0;
 
 
-    CudaBackend() {
+    int deviceId = 0;
 
+    CudaBackend() {
         int dev = 0;
         EB_CUDA(cudaGetDevice(&dev));
+        deviceId = dev;
         cudaDeviceProp prop;
         EB_CUDA(cudaGetDeviceProperties(&prop, dev));
         sms = prop.multiProcessorCount;
@@ -527,6 +529,7 @@ struct CudaBackend : Backend {
         if (n) EB_CUDA(cudaMemsetAsync(d, v, n, stream));
     }
     void sync() override { EB_CUDA(cudaStreamSynchronize(stream)); }
+    void bind_thread() override { EB_CUDA(cudaSetDevice(deviceId)); }
     int sm_count() override { return sms; }
 
     cudaEvent_t get_event() {
