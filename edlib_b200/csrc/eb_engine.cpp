@@ -289,6 +289,16 @@ public:
     int ncodes = 0;
     std::vector<int> alphaLen;
 
+    // classification (Engine::classify): pairs per (target, word class) for the lane kernels, the rest
+    struct Part {
+        std::map<std::pair<int, int>, std::vector<int>> groups;
+        std::vector<int> wPairs;
+    };
+    std::map<std::pair<int, int>, std::vector<int>> groups;
+    std::vector<Part> parts;        // per-thread pieces, kept for their storage
+    std::vector<int> wPairsBase;    // queries above 256 rows
+    bool classified = false;
+
     // results
     std::vector<int> ed;            // distance or -1
     std::vector<uint8_t> special;   // 1: an empty sequence (ref cpp:166-184)
@@ -315,6 +325,7 @@ Prepared* Engine::prepare(const BatchInput& in) {
         p->hasEq = false;
         p->ncodes = 0;
         p->computed = false;
+        p->classified = false;
         p->be = be;
         p->N = in.numPairs;
         p->cfg = in.config;
@@ -509,6 +520,8 @@ Prepared* Engine::prepare(const BatchInput& in) {
         dTset.upload(tset.p, N);
         trace.mark("prepare: mask items");
         be->launch_alpha_len(dMasks.p, nullptr, dTset.p, N, dAlpha.p);
+        classify(p);  // host work while the upload and the alphabet kernels run
+        trace.mark("prepare: classification");
         p->alphaLen.resize(N);
         dAlpha.download(p->alphaLen.data(), N);
         uint32_t uni[8];
@@ -1080,7 +1093,7 @@ struct Pass {
     // the distance pass.  Reads are addressed by their index `s` into `list`.
     struct LaneGroup {
         int t, nw;               // target index, 32-bit words per query
-        std::vector<int>& list;  // the pairs of the group
+        const std::vector<int>& list;  // the pairs of the group
         const Target& tg;
         int n;                   // target length
         std::vector<int> bound;  // per read: largest distance that still counts as found
@@ -1126,7 +1139,7 @@ struct Pass {
     // One launch over the reads `sub` (indices into `list`) with sentinels / thresholds subK.
     void lane_sweep(LaneGroup& c, const std::vector<int>& sub, const std::vector<int>& subK, int nwL, int chunks, int chunkLen,
                     int cap, int prefixLen, int rangeMode, std::vector<Rec>& outRecs, std::vector<Ovf>& outOvf) {
-        std::vector<int>& list = c.list;
+        const std::vector<int>& list = c.list;
         const Target& tg = c.tg;
         const int n = c.n;
         const int g = (int)sub.size();
@@ -1190,7 +1203,7 @@ struct Pass {
     // listed ones.  Returns the reads whose lists are incomplete (some chunk holds > KPOS).
     void lane_merge(LaneGroup& c, const std::vector<int>& sub, int chunks, const std::vector<Rec>& rr, const std::vector<Ovf>* oo,
                     std::vector<int>& incomplete, long long& missing) {
-        std::vector<int>& list = c.list;
+        const std::vector<int>& list = c.list;
         const int g = (int)sub.size();
         std::unordered_map<int, std::vector<int>> extra;  // rec index -> listed positions
         if (oo)
@@ -1253,7 +1266,7 @@ struct Pass {
     // Seed stage: exact seeds of every read looked up in the hash index of the target; windows around
     // the expected end columns are planned, swept and reduced on the device (eb_core.h: seed_plan_read).
     void seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::vector<int>& next) {
-        std::vector<int>& list = c.list;
+        const std::vector<int>& list = c.list;
         const Target& tg = c.tg;
         const int n = c.n;
         const int nw = c.nw;
@@ -1453,7 +1466,7 @@ struct Pass {
     // bound and none does).  Undecided reads go to `next` (a longer prefix or the plain sweep), reads with
     // long end-location lists to c.direct.
     void prefix_stage(LaneGroup& c, int P, int K0, const std::vector<int>& in, std::vector<int>& next) {
-        std::vector<int>& list = c.list;
+        const std::vector<int>& list = c.list;
         const Target& tg = c.tg;
         const int n = c.n;
         const int nw = c.nw;
@@ -1625,7 +1638,7 @@ struct Pass {
 
     // The plain lane-per-alignment sweep of the reads in c.direct over the whole target.
     void plain_sweep(LaneGroup& c) {
-        std::vector<int>& list = c.list;
+        const std::vector<int>& list = c.list;
         const std::vector<int>& direct = c.direct;
         if (direct.empty()) return;
         int chunks = 1, chunkLen = 0;
@@ -1657,7 +1670,7 @@ struct Pass {
     // Distance pass of one group of pairs that share target `t` and word class `nw` (queries <= 256
     // rows): the stages of the candidate filter (HW over a long target), each on the
     // reads the previous ones left undecided, then the plain lane-per-alignment sweep of what is left.
-    void lane_group(int t, int nw, std::vector<int>& list) {
+    void lane_group(int t, int nw, const std::vector<int>& list) {
         const Target& tg = p->tg[t];
         const int G = (int)list.size();
         LaneGroup c{t, nw, list, tg, tg.len, std::vector<int>(G), std::vector<int>(G, -1), std::vector<int>()};
@@ -2069,50 +2082,29 @@ struct Pass {
 
 }  // namespace
 
-void Engine::compute(Prepared* p) {
-    Backend* be = be_;
-    be->reset_timing();
+// Groups the pairs by (target, word class): a pure function of the lengths, the distinct targets and the
+// config, so prepare() runs it on the host workers while the sequences travel to the device; the lists stay
+// with the batch (and, through the spare batch object, keep their storage from call to call).
+void Engine::classify(Prepared* p) {
     const int N = p->N;
     const int mode = p->mode;
     const int k = p->cfg.k;
-    // ed / endStart / endCount are written for every pair by collect_ends, special by the classification
-    p->ed.resize(N);
     p->special.resize(N);
-    p->endStart.resize(N);
-    p->endCount.resize(N);
-    p->endPool.clear();
-    p->startPool.clear();
-    if (p->cfg.task == EDLIB_TASK_PATH) {
-        p->alnStart.assign(N, -1);
-        p->alnLen.assign(N, 0);
-    } else {
-        p->alnStart.clear();
-        p->alnLen.clear();
-    }
-    p->alnPool.clear();
-    stats.k1Cells = stats.wCells = 0;
-    stats.filterDecided = stats.filterFallback = 0;
-
-    Pass ps(*this, be, p);
-    std::vector<int>& wPairs = ps.wPairs;
-    Trace& trace = ps.trace;
-
-    // ---- classification -----------------------------------------------------------------
-    // (target, nw32) -> pairs, ascending.  The lists live in the engine's scratch: a batch shaped like the
-    // previous one refills them without new allocations.
-    std::map<std::pair<int, int>, std::vector<int>>& groups = scratch.groups;
+    std::map<std::pair<int, int>, std::vector<int>>& groups = p->groups;  // (target, nw32) -> pairs, ascending
+    std::vector<int>& wPairs = p->wPairsBase;
+    wPairs.clear();
     for (auto& kv : groups) kv.second.clear();
     {
         // contiguous ranges of pairs are classified on a few host threads and concatenated in order
         const size_t nparts = host_parts((size_t)N, 65536);
-        std::vector<EngineScratch::Part>& parts = scratch.parts;
+        std::vector<Prepared::Part>& parts = p->parts;
         parts.resize(nparts);
         for (auto& P : parts) {
             for (auto& kv : P.groups) kv.second.clear();
             P.wPairs.clear();
         }
         auto classify = [&](size_t t) {
-            EngineScratch::Part& P = parts[t];
+            Prepared::Part& P = parts[t];
             std::pair<int, int> lastKey(-1, -1);
             std::vector<int>* lastList = nullptr;
             const int lo = (int)((size_t)N * t / nparts), hi = (int)((size_t)N * (t + 1) / nparts);
@@ -2135,7 +2127,7 @@ void Engine::compute(Prepared* p) {
             }
         };
         HostPool::get().run(nparts, classify);
-        for (EngineScratch::Part& P : parts) {
+        for (Prepared::Part& P : parts) {
             for (auto& kv : P.groups) {
                 if (kv.second.empty()) continue;
                 std::vector<int>& dst = groups[kv.first];
@@ -2146,10 +2138,43 @@ void Engine::compute(Prepared* p) {
         // drop the keys this batch does not use (bounded memory across differently shaped batches)
         for (auto it = groups.begin(); it != groups.end();) it = it->second.empty() ? groups.erase(it) : std::next(it);
     }
+    p->classified = true;
+}
+
+void Engine::compute(Prepared* p) {
+    Backend* be = be_;
+    be->reset_timing();
+    const int N = p->N;
+    const int mode = p->mode;
+    // ed / endStart / endCount are written for every pair by collect_ends, special by the classification
+    p->ed.resize(N);
+    p->endStart.resize(N);
+    p->endCount.resize(N);
+    p->endPool.clear();
+    p->startPool.clear();
+    if (p->cfg.task == EDLIB_TASK_PATH) {
+        p->alnStart.assign(N, -1);
+        p->alnLen.assign(N, 0);
+    } else {
+        p->alnStart.clear();
+        p->alnLen.clear();
+    }
+    p->alnPool.clear();
+    stats.k1Cells = stats.wCells = 0;
+    stats.filterDecided = stats.filterFallback = 0;
+
+    Pass ps(*this, be, p);
+    std::vector<int>& wPairs = ps.wPairs;
+    Trace& trace = ps.trace;
+
+    // ---- classification (normally done by prepare() while the upload is in flight) --------
+    if (!p->classified) classify(p);
+    std::map<std::pair<int, int>, std::vector<int>>& groups = p->groups;
+    wPairs = p->wPairsBase;
 
     // ---- K1 groups ----------------------------------------------------------------------
     for (auto& kv : groups) {
-        std::vector<int>& list = kv.second;
+        const std::vector<int>& list = kv.second;
         // Small groups go to the warp kernel, except HW over a long target: there the lane kernel
         // can cut the target into chunks and spread even one alignment over many CTAs.
         if ((int)list.size() < tun.k1MinGroup && !(mode == MODE_HW && p->tg[kv.first.first].len >= 8 * tun.k1MinChunk)) {

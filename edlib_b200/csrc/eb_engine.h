@@ -107,12 +107,6 @@ struct EngineStats {
 struct EngineScratch {
     std::vector<int> best, cnt, posLen, posPool;
     std::vector<long long> posStart;
-    struct Part {
-        std::map<std::pair<int, int>, std::vector<int>> groups;
-        std::vector<int> wPairs;
-    };
-    std::map<std::pair<int, int>, std::vector<int>> groups;  // (target, word class) -> pairs
-    std::vector<Part> parts;
     int seedWindowsPerRead[2] = {0, 0};  // seed stage: windows per read the previous pass produced
 };
 
@@ -130,6 +124,7 @@ public:
     void compute(Prepared* p);                               // every kernel; records come back to the host
     void materialize(Prepared* p, EdlibAlignResult* results);  // malloc the per-pair arrays
     void release(Prepared* p);
+    void classify(Prepared* p);                              // pairs -> (target, word class) groups (host only)
 
     EngineTunables tun;
     EngineStats stats;

@@ -118,6 +118,54 @@ def test_sequences_longer_than_one_presence_item(emul):
         assert r == chk.align(a, b, -1, 2, 0)
 
 
+def test_staged_batches_are_independent(emul):
+    """edlibB200BatchPrepare / Compute / Results: two batches alive at once, computed out of order and twice;
+    each yields what the one-shot call yields."""
+    import ctypes as C
+    import random
+    from edlib_b200._ffi import AlignConfig, AlignResult, make_config, result_to_dict
+    from helpers import mutate, rand_seq
+    L = emul.lib
+    L.edlibB200BatchPrepare.restype = C.c_void_p
+    L.edlibB200BatchPrepare.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_int),
+                                        C.c_int, AlignConfig]
+    L.edlibB200BatchCompute.argtypes = [C.c_void_p, C.c_void_p]
+    L.edlibB200BatchResults.argtypes = [C.c_void_p, C.POINTER(AlignResult)]
+    L.edlibB200BatchFree.argtypes = [C.c_void_p]
+    rng = random.Random(77)
+
+    def make(nq, tlen, mode, task):
+        t = rand_seq(rng, tlen, b"ACGT")
+        qs = [mutate(rng, t[a:a + 60], 0.05, b"ACGT") for a in (rng.randrange(0, tlen - 60) for _ in range(nq))]
+        n = len(qs)
+        tb = C.create_string_buffer(t, len(t))
+        arrs = ((C.c_char_p * n)(*qs), (C.c_int * n)(*[len(q) for q in qs]),
+                (C.c_char_p * n)(*[C.cast(tb, C.c_char_p)] * n), (C.c_int * n)(*[len(t)] * n))
+        cfg, keep = make_config(-1, mode, task, None)
+        return dict(qs=qs, t=t, arrs=arrs, cfg=cfg, keep=(keep, tb), mode=mode, task=task, n=n)
+
+    def results(b, handle):
+        res = (AlignResult * b["n"])()
+        assert L.edlibB200BatchResults(handle, res) == 0
+        out = [result_to_dict(res[i]) for i in range(b["n"])]
+        for i in range(b["n"]):
+            emul.free(res[i])
+        return out
+
+    a, b = make(50, 900, 2, 1), make(70, 500, 0, 0)
+    ha = L.edlibB200BatchPrepare(*a["arrs"], a["n"], a["cfg"])
+    hb = L.edlibB200BatchPrepare(*b["arrs"], b["n"], b["cfg"])
+    assert ha and hb
+    assert L.edlibB200BatchCompute(hb, None) == 0
+    assert L.edlibB200BatchCompute(ha, None) == 0
+    assert L.edlibB200BatchCompute(hb, None) == 0
+    for batch, h in ((a, ha), (b, hb)):
+        st, exp = emul.align_batch(batch["qs"], [batch["t"]] * batch["n"], -1, batch["mode"], batch["task"])
+        assert st == 0 and results(batch, h) == exp
+    L.edlibB200BatchFree(ha)
+    L.edlibB200BatchFree(hb)
+
+
 def test_many_end_locations(emul):
     """Repeats: every column is an end location (ref runTests-style 'A*64 vs B*70' shapes)."""
     chk = parity.checker()
