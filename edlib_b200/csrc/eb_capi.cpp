@@ -214,6 +214,7 @@ EDLIB_API int edlibB200BatchCompute(EdlibB200Batch* batch, EdlibB200Stats* stats
         statsOut->wCells = e->stats.wCells;
         statsOut->filterDecided = e->stats.filterDecided;
         statsOut->filterFallback = e->stats.filterFallback;
+        statsOut->filterWindows = (int)std::min<long long>(e->stats.filterWindows, 0x7fffffff);
     }
     return EDLIB_STATUS_OK;
 }
@@ -250,6 +251,7 @@ EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {
     s->wCells = g_engine->stats.wCells;
     s->filterDecided = g_engine->stats.filterDecided;
     s->filterFallback = g_engine->stats.filterFallback;
+    s->filterWindows = (int)std::min<long long>(g_engine->stats.filterWindows, 0x7fffffff);
 }
 
 EDLIB_API int edlibB200LastKernelReport(char* buf, int bufLen) {

@@ -2161,7 +2161,7 @@ void Engine::compute(Prepared* p) {
     }
     p->alnPool.clear();
     stats.k1Cells = stats.wCells = 0;
-    stats.filterDecided = stats.filterFallback = 0;
+    stats.filterDecided = stats.filterFallback = stats.filterWindows = 0;
 
     Pass ps(*this, be, p);
     std::vector<int>& wPairs = ps.wPairs;

@@ -100,6 +100,7 @@ struct EngineStats {
     long long k1Cells = 0;  // nominal cells (sum m*n) handled by K1
     long long wCells = 0;   // nominal cells of the distance pass handled by W
     long long filterDecided = 0, filterFallback = 0;
+    long long filterWindows = 0;  // window sweeps planned by the candidate filter
     std::string kernelReport;  // per-kernel device time of the last compute(): "name:ms:launches;..."
 };
 

@@ -29,7 +29,7 @@ typedef struct {
     double kernelMs;      /* device time of all kernel launches of the last compute (CUDA events) */
     double k1Ms;          /* ... of the lane-per-alignment sweep kernel alone */
     int launches;         /* kernel launches of the last compute */
-    int reserved;
+    int filterWindows;     /* window sweeps planned by the candidate filter (all stages) */
     long long h2dBytes;   /* host->device bytes since the batch was prepared */
     long long d2hBytes;   /* device->host bytes */
     long long k1Cells;    /* nominal DP cells (sum queryLength*targetLength) swept by that kernel */
