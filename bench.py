@@ -420,9 +420,10 @@ def main():
         if dominant == "k1w":
             # unit = one window sweep: the read, its target window (lead-in m+t plus >= 2t+1 tracked columns;
             # merged windows are longer, so this is a lower bound), a 20-byte job, a 64-byte record
+            slack = int(os.environ.get("EDLIB_B200_FILTER_SEED_SLACK", "4"))
             seed_len = 8
-            while 4 ** seed_len < TARGET_LEN:
-                seed_len += 1  # eb_engine.cpp: seed_index (shortest L with sigma^L >= n)
+            while 4 ** seed_len < slack * TARGET_LEN:
+                seed_len += 1  # eb_engine.cpp: seed_index (shortest L with sigma^L >= slack * n)
             t_seed = min(16, READ_LEN // seed_len - 1)
             unit = READ_LEN + (READ_LEN + 3 * t_seed + 1) + 20 + 64
             dom_units, dom_what = float(filt[2]), "window sweeps x (read + target window + job + record)"

@@ -582,28 +582,44 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot) {
     int c = 0;
     const int stride = m / (t + 1);  // >= L: the t+1 pieces are disjoint
     bool saturated = false;
-    for (int j = 0; j <= t && !saturated; ++j) {
-        const int a = j * stride;
-        const uint32_t b = seed_bucket(q + a, p.L, p.bits);
-        const int s0 = p.bucketStart[b], s1 = p.bucketStart[b + 1];
-        if (s1 - s0 > p.maxBucket) {
-            saturated = true;
-            break;
-        }
-        for (int i = s0; i < s1; ++i) {
-            const int pos = p.positions[i];
-            bool same = true;
-            for (int x = 0; x < p.L; ++x)
-                if (p.tcodes[pos + x] != q[a + x]) {
-                    same = false;
+    // Pieces go eight at a time: first all their hashes, then all their bucket bounds (independent loads in
+    // flight together), then the occurrences -- the lookups of one read are otherwise one long latency chain.
+    for (int j0 = 0; j0 <= t && !saturated; j0 += 8) {
+        const int group = t + 1 - j0 < 8 ? t + 1 - j0 : 8;
+        uint32_t bucket[8];
+        int s0[8], s1[8];
+        EB_UNROLL
+        for (int u = 0; u < 8; ++u)
+            if (u < group) bucket[u] = seed_bucket(q + (j0 + u) * stride, p.L, p.bits);
+        EB_UNROLL
+        for (int u = 0; u < 8; ++u)
+            if (u < group) {
+                s0[u] = p.bucketStart[bucket[u]];
+                s1[u] = p.bucketStart[bucket[u] + 1];
+            }
+        EB_UNROLL
+        for (int u = 0; u < 8; ++u) {
+            if (u >= group || saturated) continue;
+            const int a = (j0 + u) * stride;
+            if (s1[u] - s0[u] > p.maxBucket) {
+                saturated = true;
+                continue;
+            }
+            for (int i = s0[u]; i < s1[u]; ++i) {
+                const int pos = p.positions[i];
+                bool same = true;
+                for (int x = 0; x < p.L; ++x)
+                    if (p.tcodes[pos + x] != q[a + x]) {
+                        same = false;
+                        break;
+                    }
+                if (!same) continue;  // bucket collision
+                if (c == SEED_MAX_CAND) {
+                    saturated = true;
                     break;
                 }
-            if (!same) continue;  // bucket collision
-            if (c == SEED_MAX_CAND) {
-                saturated = true;
-                break;
+                E[c++] = pos + (m - a) - 1;
             }
-            E[c++] = pos + (m - a) - 1;
         }
     }
     if (saturated) {

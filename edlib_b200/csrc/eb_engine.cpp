@@ -44,6 +44,7 @@ EngineTunables::EngineTunables() {
     packParallelBytes = (size_t)env_int("EDLIB_B200_PACK_PARALLEL_KB", (int)(packParallelBytes >> 10)) << 10;
     filterSeedK = env_int("EDLIB_B200_FILTER_SEED_K", filterSeedK);
     filterSeedBucket = env_int("EDLIB_B200_FILTER_SEED_BUCKET", filterSeedBucket);
+    filterSeedSlack = env_int("EDLIB_B200_FILTER_SEED_SLACK", filterSeedSlack);
     filterMaxWindows = env_int("EDLIB_B200_FILTER_MAX_WINDOWS", filterMaxWindows);
     filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
     filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
@@ -1036,7 +1037,8 @@ struct Pass {
     }
 
     // Hash indexes of the seeds of one target (candidate filter, seed stages), one per seed length; kept for
-    // the last target used.  Level 0: the shortest L with sigma^L >= n (about one chance occurrence per seed);
+    // the last target used.  Level 0: the shortest L with sigma^L >= filterSeedSlack * n (a fraction of a chance
+    // occurrence per seed: every occurrence costs a window sweep);
     // level 1: two symbols shorter (more seeds fit into a read, so a higher threshold, at the price of more
     // chance occurrences) for the reads level 0 cannot decide.
     struct SeedIndex {
@@ -1054,7 +1056,7 @@ struct Pass {
         const double sigma = std::max(2, p->ncodes);
         int L = 8;
         double v = std::pow(sigma, 8);
-        while (v < (double)n && L < 32) {
+        while (v < (double)tun.filterSeedSlack * (double)n && L < 32) {
             v *= sigma;
             ++L;
         }

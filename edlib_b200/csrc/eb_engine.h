@@ -83,6 +83,7 @@ struct EngineTunables {
     // ranges are swept with the whole read; reads no stage decides take the plain full sweep.
     int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 32;    // seed stage: longest hash bucket looked at (longer: repeat, read passed on)
+    int filterSeedSlack = 4;      // seed stage: seed length L is the shortest with sigma^L >= slack * target length
     int filterK1 = 8;
     int filterK0 = 16;
     int filterMinLen = 96;        // shortest query worth the 64-row stage (scaled by P/64 for the other)
