@@ -1342,6 +1342,7 @@ struct Pass {
             cap = V;  // window list overflow: repeat with the exact size
         }
         perRead = (int)(((long long)V + g - 1) / g);
+        stats.filterWindows += V;
         trace.mark("filter: seeds planned");
         DevBuf<WinRec> dWinRecs(be, (size_t)std::max(V, 1));
         if (V > 0) {
@@ -1571,6 +1572,7 @@ struct Pass {
         wFirst[g] = (int)vOwner.size();
         trace.mark("filter: windows planned");
         const int V = (int)vOwner.size();
+        stats.filterWindows += V;
         if (trace.on) {
             int sat = 0;
             for (char c : saturated) sat += c;
