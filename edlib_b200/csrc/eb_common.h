@@ -232,7 +232,12 @@ struct SeedIndexParams {
     int* cursor;             // [2^bits] fill cursors, zeroed by the host
     int* positions;          // [n - L + 1]
 };
-#define SEED_MAX_CAND 256    // candidate end columns per read before the read is passed on as saturated
+// candidate end columns per read before the read is passed on as saturated, per seed level (shorter seeds
+// have more chance occurrences); the planning kernel is instantiated per capacity
+#define SEED_LEVELS 3
+#define SEED_CAND_0 64
+#define SEED_CAND_1 256
+#define SEED_CAND_2 512
 enum SeedState : int { SEED_NONE = 0, SEED_WINDOWS = 1, SEED_SATURATED = 2, SEED_LONG_LIST = 3 };
 struct SeedPlan {
     int first, count;        // the read's windows in the job arrays
@@ -253,6 +258,7 @@ struct SeedPlanParams {
     const int* bucketStart;
     const int* positions;
     int maxBucket;           // buckets longer than this saturate the read (repeats)
+    int level;               // seed level (selects the candidate capacity)
     int spread;              // widest group of candidates verified as one window
     // outputs: K1W jobs (K1WParams arrays) and the per-read plan
     int* winPair;

@@ -566,6 +566,7 @@ EB_HD int seed_windows(const SeedPlanParams& p, const int* E, int c, int m, int 
     return nW;
 }
 
+template <int CAP>
 EB_HD void seed_plan_read(const SeedPlanParams& p, int slot) {
     const int pair = p.readList[slot];
     const int m = p.qlen[pair], t = p.thr[slot];
@@ -578,7 +579,7 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot) {
         p.plan[slot] = pl;
         return;
     }
-    int E[SEED_MAX_CAND];
+    int E[CAP];
     int c = 0;
     const int stride = m / (t + 1);  // >= L: the t+1 pieces are disjoint
     bool saturated = false;
@@ -614,7 +615,7 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot) {
                         break;
                     }
                 if (!same) continue;  // bucket collision
-                if (c == SEED_MAX_CAND) {
+                if (c == CAP) {
                     saturated = true;
                     break;
                 }

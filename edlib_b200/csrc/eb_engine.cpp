@@ -618,7 +618,7 @@ struct WRunner {
         }
         for (auto& kv : lanes) {
             int bt = 0, rc = 0;
-            be->k1_shape(kv.first.first, p->ncodes, &bt, &rc);
+            be->k1_shape(kv.first.first, p->ncodes, 0x7fffffff, &bt, &rc);
             if (rc <= 0 || (int)kv.second.size() < 8) {  // alphabet too large for per-thread Peq rows / too few to bother
                 warp.insert(warp.end(), kv.second.begin(), kv.second.end());
                 continue;
@@ -949,7 +949,7 @@ struct Pass {
         const int nw = ceil_div(m, 32);
         if (laneOkCache[nw] < 0) {
             int bt = 0, rc = 0;
-            be->k1_shape(nw, p->ncodes, &bt, &rc);
+            be->k1_shape(nw, p->ncodes, 0x7fffffff, &bt, &rc);
             laneOkCache[nw] = rc > 0 ? 1 : 0;
         }
         return laneOkCache[nw] == 1;
@@ -1039,13 +1039,13 @@ struct Pass {
     // Hash indexes of the seeds of one target (candidate filter, seed stages), one per seed length; kept for
     // the last target used.  Level 0: the shortest L with sigma^L >= filterSeedSlack * n (a fraction of a chance
     // occurrence per seed: every occurrence costs a window sweep);
-    // level 1: two symbols shorter (more seeds fit into a read, so a higher threshold, at the price of more
-    // chance occurrences) for the reads level 0 cannot decide.
+    // levels 1 and 2: two and four symbols shorter (more seeds fit into a read, so a higher threshold, at the
+    // price of more chance occurrences) for the reads the previous level cannot decide.
     struct SeedIndex {
         int target = -1;
         int L = 0, bits = 0;
         DevBuf<int> bucketStart, positions;
-    } seed[2];
+    } seed[SEED_LEVELS];
     bool seed_index(int t, int level) {
         SeedIndex& sx = seed[level];
         const Target& tg = p->tg[t];
@@ -1060,9 +1060,9 @@ struct Pass {
             v *= sigma;
             ++L;
         }
-        if (level == 1) {
-            if (L < 10) return false;  // seeds shorter than 8 symbols select nothing
-            L -= 2;
+        if (level > 0) {
+            if (L - 2 * level < 8) return false;  // seeds shorter than 8 symbols select nothing
+            L -= 2 * level;
         }
         if (n < 4 * L) return false;
         int bits = 12;
@@ -1109,11 +1109,13 @@ struct Pass {
     void lane_geometry(const LaneGroup& c, int g, int nwL, int& chunks, int& chunkLen, bool perChunkRecs) {
         const int n = c.n;
         int blockThreads = 256, residentCtas = 1;
-        be->k1_shape(nwL, p->ncodes, &blockThreads, &residentCtas);
+        be->k1_shape(nwL, p->ncodes, g, &blockThreads, &residentCtas);
         chunks = 1;
         chunkLen = (int)round_up((size_t)n, 16);
         if (mode != MODE_HW) return;
-        const int minChunk = std::max(tun.k1MinChunk, 8 * 64 * nwL);
+        // the restart lead-in (64 * nwL columns) stays below 1/8 of a chunk; a handful of reads is latency-bound
+        // per CTA and may be cut finer (lead-in up to 1/3)
+        const int minChunk = std::max(tun.k1MinChunk, (g <= 32 ? 2 : 8) * 64 * nwL);
         long long maxChunks = std::max<long long>(1, n / minChunk);
         // plain sweeps return one record per (chunk, read): keep that below ~64 MB
         if (perChunkRecs) maxChunks = std::min<long long>(maxChunks, std::max<long long>(64, (2LL << 20) / std::max(g, 1)));
@@ -1303,7 +1305,7 @@ struct Pass {
         DevBuf<int> wPair, wK, wStart, wLen, wTf;
         // room for the window jobs: sized from what the previous pass of this level needed per read
         int& perRead = eng.scratch.seedWindowsPerRead[level];
-        int cap = (int)std::min<long long>((long long)g * std::max(perRead + 2, level ? 96 : 8) + 4096, 1LL << 28), V = 0;
+        int cap = (int)std::min<long long>((long long)g * std::max(perRead + 2, level == 0 ? 8 : level == 1 ? 96 : 400) + 4096, 1LL << 28), V = 0;
         for (;;) {
             wPair.alloc(be, cap);
             wK.alloc(be, cap);
@@ -1326,6 +1328,7 @@ struct Pass {
             sp.bucketStart = sx.bucketStart.p;
             sp.positions = sx.positions.p;
             sp.maxBucket = tun.filterSeedBucket << (4 * level);  // shorter seeds: longer buckets are normal
+            sp.level = level;
             sp.spread = tun.filterSpread;
             sp.winPair = wPair.p;
             sp.winK = wK.p;
@@ -1689,7 +1692,7 @@ struct Pass {
         const bool filtered = mode == MODE_HW && c.n >= tun.filterMinTarget;
         if (filtered) {
             trace.mark("compute: classify");
-            for (int level = 0; level < 2 && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
+            for (int level = 0; level < SEED_LEVELS && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
                 std::vector<int> next;
                 seed_stage(c, level, cur, next);
                 cur.swap(next);
@@ -2188,7 +2191,7 @@ void Engine::compute(Prepared* p) {
         const int t = kv.first.first, nw = kv.first.second;
         {
             int bt = 0, rc = 0;
-            be->k1_shape(nw, p->ncodes, &bt, &rc);
+            be->k1_shape(nw, p->ncodes, (int)list.size(), &bt, &rc);
             if (rc <= 0) {  // alphabet too large for per-thread Peq rows in shared memory
                 wPairs.insert(wPairs.end(), list.begin(), list.end());
                 continue;

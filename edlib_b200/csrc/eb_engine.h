@@ -33,9 +33,10 @@ struct Backend {
     // called on entry of every API call and by pool workers before they issue copies.
     virtual void bind_thread() {}
     virtual int sm_count() = 0;
-    // Launch shape of the lane-per-alignment kernel for a word class / alphabet size: threads per
-    // CTA and how many CTAs are resident on the whole device at once (for wave-aware chunking).
-    virtual void k1_shape(int nw32, int ncodes, int* blockThreads, int* residentCtas) = 0;
+    // Launch shape of the lane-per-alignment kernel for a word class / alphabet size / number of reads
+    // (few reads get small CTAs): threads per CTA and how many CTAs are resident on the whole device at
+    // once (for wave-aware chunking).  residentCtas == 0: the alphabet is too large for this kernel.
+    virtual void k1_shape(int nw32, int ncodes, int numReads, int* blockThreads, int* residentCtas) = 0;
     virtual void launch_mask(const MaskParams& p) = 0;
     virtual void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int numPairs, int* out) = 0;
     virtual void launch_encode(const EncodeParams& p) = 0;
@@ -109,7 +110,7 @@ struct EngineStats {
 struct EngineScratch {
     std::vector<int> best, cnt, posLen, posPool;
     std::vector<long long> posStart;
-    int seedWindowsPerRead[2] = {0, 0};  // seed stage: windows per read the previous pass produced
+    int seedWindowsPerRead[SEED_LEVELS] = {0, 0, 0};  // seed stages: windows per read the previous pass produced
 };
 
 class Prepared;  // a batch whose inputs are resident on the device

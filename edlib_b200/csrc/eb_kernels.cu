@@ -305,9 +305,10 @@ __global__ void seed_fill_kernel(const SeedIndexParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= p.n - p.L) seed_fill_item(p, i);
 }
+template <int CAP>
 __global__ void seed_plan_kernel(const SeedPlanParams p) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < p.numReads) seed_plan_read(p, slot);
+    if (slot < p.numReads) seed_plan_read<CAP>(p, slot);
 }
 __global__ void win_reduce_kernel(const WinReduceParams p) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -582,12 +583,14 @@ struct CudaBackend : Backend {
     }
 
     // CTA size and dynamic shared memory of a K1 launch: four CTAs of 256 threads per SM when the
-    // alphabet is small; the CTA shrinks when the per-thread Peq rows would not fit.
-    static void k1_block(int nw, int ncodes, int* block, size_t* smem) {
+    // alphabet is small; the CTA shrinks when the per-thread Peq rows would not fit, and when there are
+    // only a few reads (more, smaller CTAs are resident: such launches are latency-bound per warp).
+    static void k1_block(int nw, int ncodes, int numReads, int* block, size_t* smem) {
         const size_t perThread = (size_t)ncodes * (16 + 4 * (nw > 4 ? nw - 4 : 0));
         const size_t fixed = 2 * K1_TILE + 64;
         int b = 256;
         while (b > 32 && fixed + perThread * b > 44 * 1024) b >>= 1;
+        while (b > 32 && b / 2 >= numReads) b >>= 1;
         *block = b;
         *smem = fixed + perThread * b;
     }
@@ -595,7 +598,7 @@ struct CudaBackend : Backend {
     void launch_k1_t(const K1Params& p) {
         int block;
         size_t smem;
-        k1_block(NW, p.ncodes, &block, &smem);
+        k1_block(NW, p.ncodes, p.numReads, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
         EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
@@ -610,17 +613,18 @@ struct CudaBackend : Backend {
         return perSm < 1 ? 1 : perSm;
     }
     std::vector<int> shapeCache;  // [nw*1024 + ncodes] -> block | resident << 12, 0 = unknown
-    void k1_shape(int nw, int ncodes, int* blockThreads, int* residentCtas) override {
-        if (shapeCache.empty()) shapeCache.assign(9 * 1024, 0);
-        const int key = nw * 1024 + (ncodes < 1024 ? ncodes : 1023);
+    void k1_shape(int nw, int ncodes, int numReads, int* blockThreads, int* residentCtas) override {
+        int block;
+        size_t smem;
+        k1_block(nw, ncodes, numReads, &block, &smem);
+        if (shapeCache.empty()) shapeCache.assign(4 * 9 * 1024, 0);
+        const int blockClass = block >= 256 ? 3 : block >= 128 ? 2 : block >= 64 ? 1 : 0;
+        const int key = (blockClass * 9 + nw) * 1024 + (ncodes < 1024 ? ncodes : 1023);
         if (ncodes < 1023 && shapeCache[key]) {
             *blockThreads = shapeCache[key] & 0xfff;
             *residentCtas = shapeCache[key] >> 12;
             return;
         }
-        int block;
-        size_t smem;
-        k1_block(nw, ncodes, &block, &smem);
         if (smem > (size_t)maxSmemOptin) {  // Peq rows of even a 32-thread CTA do not fit: not a K1 case
             *blockThreads = block;
             *residentCtas = 0;
@@ -646,7 +650,7 @@ struct CudaBackend : Backend {
     void launch_k1_range_t(const K1Params& p) {
         int block;
         size_t smem;
-        k1_block(NW, p.ncodes, &block, &smem);
+        k1_block(NW, p.ncodes, p.numReads, &block, &smem);
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1: alphabet too large for shared memory");
         dim3 grid((p.numReads + block - 1) / block, p.chunks);
         EB_CUDA(cudaFuncSetAttribute(k1_kernel<NW, MODE_HW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -787,7 +791,10 @@ struct CudaBackend : Backend {
     }
     void launch_seed_plan(const SeedPlanParams& p) override {
         Scope s(this, "seed_plan");
-        seed_plan_kernel<<<(p.numReads + 127) / 128, 128, 0, stream>>>(p);
+        const int grid = (p.numReads + 127) / 128;
+        if (p.level <= 0) seed_plan_kernel<SEED_CAND_0><<<grid, 128, 0, stream>>>(p);
+        else if (p.level == 1) seed_plan_kernel<SEED_CAND_1><<<grid, 128, 0, stream>>>(p);
+        else seed_plan_kernel<SEED_CAND_2><<<grid, 128, 0, stream>>>(p);
         check_launch("seed_plan");
     }
     void launch_win_reduce(const WinReduceParams& p) override {

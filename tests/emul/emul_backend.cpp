@@ -93,7 +93,7 @@ struct EmulBackend : Backend {
         const char* s = getenv("EDLIB_EMUL_SMS");
         return s ? atoi(s) : 2;
     }
-    void k1_shape(int, int, int* blockThreads, int* residentCtas) override {
+    void k1_shape(int, int, int, int* blockThreads, int* residentCtas) override {
         *blockThreads = 32;
         *residentCtas = sm_count() * 4;
     }
@@ -129,7 +129,11 @@ struct EmulBackend : Backend {
     }
     void launch_seed_plan(const SeedPlanParams& p) override {
         ++launchesCount;
-        for (int i = p.numReads - 1; i >= 0; --i) seed_plan_read(p, i);
+        for (int i = p.numReads - 1; i >= 0; --i) {
+            if (p.level <= 0) seed_plan_read<SEED_CAND_0>(p, i);
+            else if (p.level == 1) seed_plan_read<SEED_CAND_1>(p, i);
+            else seed_plan_read<SEED_CAND_2>(p, i);
+        }
     }
     void launch_win_reduce(const WinReduceParams& p) override {
         ++launchesCount;
