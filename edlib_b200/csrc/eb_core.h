@@ -628,14 +628,19 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot) {
         p.plan[slot] = pl;
         return;
     }
-    for (int i = 1; i < c; ++i) {  // insertion sort: c is small
-        const int v = E[i];
-        int j = i - 1;
-        while (j >= 0 && E[j] > v) {
-            E[j + 1] = E[j];
-            --j;
+    // Shell sort (Ciura gaps; plain insertion sort when c is small, the usual case)
+    const int gaps[7] = {301, 132, 57, 23, 10, 4, 1};
+    for (int gi = c > 32 ? 0 : 6; gi < 7; ++gi) {
+        const int gap = gaps[gi];
+        for (int i = gap; i < c; ++i) {
+            const int v = E[i];
+            int j = i - gap;
+            while (j >= 0 && E[j] > v) {
+                E[j + gap] = E[j];
+                j -= gap;
+            }
+            E[j + gap] = v;
         }
-        E[j + 1] = v;
     }
     const int nW = seed_windows(p, E, c, m, t, pair, 0, false);
     if (nW > 0) {

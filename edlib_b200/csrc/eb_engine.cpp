@@ -45,6 +45,7 @@ EngineTunables::EngineTunables() {
     filterSeedK = env_int("EDLIB_B200_FILTER_SEED_K", filterSeedK);
     filterSeedBucket = env_int("EDLIB_B200_FILTER_SEED_BUCKET", filterSeedBucket);
     filterSeedSlack = env_int("EDLIB_B200_FILTER_SEED_SLACK", filterSeedSlack);
+    filterSeedLevels = std::min(SEED_LEVELS, env_int("EDLIB_B200_FILTER_SEED_LEVELS", filterSeedLevels));
     filterMaxWindows = env_int("EDLIB_B200_FILTER_MAX_WINDOWS", filterMaxWindows);
     filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
     filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
@@ -1692,7 +1693,7 @@ struct Pass {
         const bool filtered = mode == MODE_HW && c.n >= tun.filterMinTarget;
         if (filtered) {
             trace.mark("compute: classify");
-            for (int level = 0; level < SEED_LEVELS && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
+            for (int level = 0; level < tun.filterSeedLevels && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
                 std::vector<int> next;
                 seed_stage(c, level, cur, next);
                 cur.swap(next);

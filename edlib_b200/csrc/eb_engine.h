@@ -84,6 +84,7 @@ struct EngineTunables {
     // ranges are swept with the whole read; reads no stage decides take the plain full sweep.
     int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 32;    // seed stage: longest hash bucket looked at (longer: repeat, read passed on)
+    int filterSeedLevels = 2;     // seed stage: levels tried (seed length L, L-2, L-4; at most SEED_LEVELS)
     int filterSeedSlack = 4;      // seed stage: seed length L is the shortest with sigma^L >= slack * target length
     int filterK1 = 8;
     int filterK0 = 16;
