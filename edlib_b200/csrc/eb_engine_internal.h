@@ -1,0 +1,461 @@
+// eb_engine_internal.h -- shared declarations of the host engine's translation units (eb_engine.cpp: batch
+// preparation and the compute driver; eb_wrunner.cpp: warp-per-alignment job runner; eb_pass_lane.cpp: the
+// lane-per-alignment distance pass with the candidate filter; eb_pass_results.cpp: end/start locations and
+// alignment paths).  Not part of the library's interface.
+#pragma once
+#include "eb_engine.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <chrono>
+#include <map>
+#include <stdexcept>
+#include <thread>
+#include <unordered_map>
+
+namespace eb {
+
+
+// EDLIB_B200_TRACE=1: wall-clock of the host phases to stderr (diagnostics only).
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("EDLIB_B200_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[edlib_b200] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+// Persistent host worker threads (spawning threads per loop costs more than most of these loops): run(n, fn)
+// executes fn(0) .. fn(n-1), the caller taking part, and returns when all are done.  One client at a time
+// (the engine runs under the library's lock).  The workers live until the process ends.
+class HostPool {
+public:
+    static HostPool& get() {
+        static HostPool* pool = new HostPool();  // never destroyed: workers may still be parked at exit
+        return *pool;
+    }
+    size_t width() const { return workers_ + 1; }
+    void run(size_t n, const std::function<void(size_t)>& fn) {
+        if (n == 0) return;
+        if (n == 1 || workers_ == 0) {
+            for (size_t i = 0; i < n; ++i) fn(i);
+            return;
+        }
+        unsigned long long gen;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            fn_ = &fn;
+            total_ = n;
+            next_ = 0;
+            pending_ = n;
+            gen = ++generation_;
+        }
+        cv_.notify_all();
+        work(gen);
+        std::unique_lock<std::mutex> lock(mu_);
+        done_.wait(lock, [this]() { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    HostPool() {
+        const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+        workers_ = std::min<size_t>(16, hw) - 1;
+        for (size_t i = 0; i < workers_; ++i) std::thread([this]() { loop(); }).detach();
+    }
+    // Tasks are few and coarse, so they are claimed under the lock; a worker only ever claims tasks of
+    // the generation it woke up for.
+    void work(unsigned long long gen) {
+        for (;;) {
+            const std::function<void(size_t)>* fn;
+            size_t i;
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                if (generation_ != gen || next_ >= total_) return;
+                i = next_++;
+                fn = fn_;
+            }
+            (*fn)(i);
+            std::lock_guard<std::mutex> lock(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_.wait(lock, [&]() { return generation_ != seen; });
+                seen = generation_;
+            }
+            work(seen);
+        }
+    }
+    size_t workers_ = 0;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t total_ = 0, pending_ = 0, next_ = 0;
+    unsigned long long generation_ = 0;
+};
+
+// number of parts a loop over n items is cut into (every part gets >= grain items)
+inline size_t host_parts(size_t n, size_t grain) {
+    return std::max<size_t>(1, std::min<size_t>(HostPool::get().width(), n / std::max<size_t>(grain, 1)));
+}
+
+// fn(begin, end) over [0, n) on the host workers (only when every part gets >= grain items).
+template <class F>
+void parallel_ranges(size_t n, size_t grain, F fn) {
+    const size_t nthr = host_parts(n, grain);
+    if (nthr <= 1) {
+        fn((size_t)0, n);
+        return;
+    }
+    HostPool::get().run(nthr, [&](size_t t) { fn(n * t / nthr, n * (t + 1) / nthr); });
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// Host staging memory from the backend (pinned and cached on CUDA): transfers run at full PCIe rate and
+// the host reads / writes it in place.
+template <class T>
+struct HostBuf {
+    Backend* be = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    HostBuf(Backend* b, size_t count) : be(b), p(static_cast<T*>(b->alloc_host(std::max<size_t>(count, 1) * sizeof(T)))), n(count) {}
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+    ~HostBuf() { be->free_host(p); }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
+template <class T>
+struct DevBuf {
+    Backend* be = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(Backend* b, size_t count) { alloc(b, count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { reset(); }
+    void alloc(Backend* b, size_t count) {
+        reset();
+        be = b;
+        n = count;
+        p = static_cast<T*>(be->alloc(std::max<size_t>(count, 1) * sizeof(T)));
+    }
+    void reset() {
+        if (p) be->free(p);
+        p = nullptr;
+        n = 0;
+    }
+    void upload(const T* src, size_t count) { be->h2d(p, src, count * sizeof(T)); }
+    void download(T* dst, size_t count) { be->d2h(dst, p, count * sizeof(T)); }
+};
+
+struct Target {
+    const char* ptr;
+    int len;
+    uint64_t off;  // into the packed sequence buffer
+};
+
+// One warp-per-alignment sweep as seen by the host.
+struct WTask {
+    uint64_t qOff = 0, tOff = 0;
+    int m = 0, n = 0, mode = 0, flags = 0, kInit = 0, dhi = 0, stopCol = -1, trackFrom = 0;
+    int R = 1, nWp = 0;
+    int pair = -1, tag = 0;
+    bool wantPositions = false;  // the caller needs every end position, not just best/cnt/last
+    int splitSide = -1;          // WF_STOPCOL pairs of a Hirschberg node: 0 forward half, 1 reversed half (adjacent tasks)
+    int splitBest = 0;           // ... the node's known score
+    SplitOut split{};            // ... the split found on the device (stored on the forward task)
+    Rec rec{};
+    std::vector<int> extra;  // positions past KPOS that attain rec.best, ascending
+    long long opsOff = -1;   // into the ops pool (WF_STORE)
+    int opsLen = 0;
+};
+
+struct WPlan {
+    int R, nWp;
+    bool slide;
+    int dhi;
+};
+
+WPlan plan_w(int m, int n, int mode, int kBound);
+
+// ---------------------------------------------------------------------------------------------
+// Prepared batch
+// ---------------------------------------------------------------------------------------------
+class Prepared {
+public:
+    Backend* be = nullptr;
+    int N = 0;
+    EdlibAlignConfig cfg{};
+    int mode = MODE_NW;  // normalised: anything that is not SHW/HW runs as NW (ref cpp:205-215)
+    std::vector<int> qlen, tlen, tidx;
+    std::vector<uint64_t> qoff;
+    std::vector<Target> tg;
+    DevBuf<uint8_t> dSeq;
+    DevBuf<uint64_t> dQoff;
+    DevBuf<int> dQlen;
+    DevBuf<uint8_t> dEqtab;
+    bool hasEq = false;
+    int ncodes = 0;
+    std::vector<int> alphaLen;
+
+    // classification (Engine::classify): pairs per (target, word class) for the lane kernels, the rest
+    struct Part {
+        std::map<std::pair<int, int>, std::vector<int>> groups;
+        std::vector<int> wPairs;
+    };
+    std::map<std::pair<int, int>, std::vector<int>> groups;
+    std::vector<Part> parts;        // per-thread pieces, kept for their storage
+    std::vector<int> wPairsBase;    // queries above 256 rows
+    bool classified = false;
+
+    // results
+    std::vector<int> ed;            // distance or -1
+    std::vector<uint8_t> special;   // 1: an empty sequence (ref cpp:166-184)
+    std::vector<long long> endStart;
+    std::vector<int> endCount;
+    std::vector<int> endPool, startPool;
+    std::vector<long long> alnStart;  // -1: none
+    std::vector<int> alnLen;
+    std::vector<uint8_t> alnPool;
+    bool computed = false;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Runner of warp-per-alignment (and per-job lane) sweeps in memory-bounded slices (eb_wrunner.cpp)
+// ---------------------------------------------------------------------------------------------
+struct WRunner {
+    Engine* eng;
+    Backend* be;
+    Prepared* p;
+    std::vector<uint8_t>* opsPool = nullptr;
+
+    size_t task_bytes(const WTask& t) const;
+
+    // Tasks whose query fits 256 rows and whose shape one of the lane-kernel classes covers run one
+    // alignment per THREAD (lane_kernel); everything else one alignment per warp (w_kernel).
+    static int lane_class(const WTask& t) {  // -1: not a lane task
+        if (t.m > 256 || (t.flags & (WF_SLIDE | WF_STOPCOL))) return -1;
+        const bool qrev = (t.flags & WF_QREV) != 0, trev = (t.flags & WF_TREV) != 0;
+        if (t.flags & WF_STORE) return (t.mode == MODE_NW && !qrev && !trev) ? 4 : -1;
+        if (qrev != trev) return -1;
+        if (qrev) return t.mode == MODE_SHW ? 3 : -1;
+        return t.mode;  // 0 NW, 1 SHW, 2 HW, forward
+    }
+
+    void run(std::vector<WTask>& tasks);
+
+    // One class of lane tasks, in memory-bounded slices.  Tasks that need a longer end-location list
+    // than a record holds are handed to the warp kernel (`spill`), which owns the list machinery.
+    void run_lane(std::vector<WTask>& tasks, const std::vector<int>& idx, int nw, int lc, std::vector<int>& spill);
+
+    // ovfCap == 0: first pass (no position list).  ovfCap > 0: second pass over the tasks whose
+    // end-location lists exceed KPOS, started from their known minimum with an exact-size list.
+    void run_slice(std::vector<WTask>& tasks, const std::vector<int>& slice, int R, int ovfCap);
+};
+
+// ---------------------------------------------------------------------------------------------
+// One compute() over a prepared batch: shared state + the phases of the reference driver
+// ---------------------------------------------------------------------------------------------
+struct Pass {
+    Engine& eng;
+    Backend* be;
+    Prepared* p;
+    EngineTunables& tun;
+    EngineStats& stats;
+    Trace trace;
+    const int N, mode, k;
+    // per-pair sweep outcome before the "-1" rule (storage reused from pass to pass: EngineScratch)
+    std::vector<int>&best, &cnt;
+    std::vector<long long>& posStart;  // end columns of pair i: posPool[posStart[i] .. +posLen[i])
+    std::vector<int>&posLen, &posPool;
+    std::vector<int> wPairs;          // pairs swept by the warp / lane-job kernels
+    std::vector<uint8_t> opsPool;
+    WRunner runner;
+    int laneOkCache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+
+    Pass(Engine& e, Backend* b, Prepared* pr)
+        : eng(e), be(b), p(pr), tun(e.tun), stats(e.stats), N(pr->N), mode(pr->mode), k(pr->cfg.k),
+          best(e.scratch.best), cnt(e.scratch.cnt), posStart(e.scratch.posStart), posLen(e.scratch.posLen),
+          posPool(e.scratch.posPool), runner{&e, b, pr, &opsPool} {
+        best.resize((size_t)N);
+        cnt.resize((size_t)N);
+        posStart.resize((size_t)N);
+        posLen.resize((size_t)N);
+        parallel_ranges((size_t)N, 65536, [this](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                best[i] = -1;
+                cnt[i] = 0;
+                posStart[i] = -1;
+                posLen[i] = 0;
+            }
+        });
+        posPool.clear();
+        posPool.reserve((size_t)N + 16);
+    }
+
+    // ---- direct lane-kernel launches (no per-job host objects): the LOC / PATH phases of large read
+    // batches issue millions of tiny sweeps, so their jobs are built straight into LJob arrays. --------
+    bool lane_ok(int m);
+
+    void lane_launch(const std::vector<LJob>& jobs, int nw, int laneMode, bool rev, std::vector<Rec>& recs);
+
+    // Matrix-storing NW sweeps + traceback of `jobs` (matOff is assigned here); `sink(jobIndex, ops, len,
+    // score)` receives every edit script.  Slices bound the stored matrices to the slice budget.
+    template <class Sink>
+    void lane_paths(std::vector<LJob>& jobs, int nw, Sink sink) {
+        size_t a = 0;
+        while (a < jobs.size()) {
+            size_t bytes = 0, b = a;
+            uint64_t matEntries = 0, opsBytes = 0;
+            std::vector<TbJob> tb;
+            while (b < jobs.size()) {
+                LJob& j = jobs[b];
+                const size_t need = (size_t)j.n * nw * 8 + (size_t)j.m + j.n + sizeof(LJob) + sizeof(TbJob) + 64;
+                if (b > a && bytes + need > tun.sliceBytes) break;
+                j.matOff = matEntries;
+                TbJob t;
+                memset(&t, 0, sizeof(t));
+                t.matOff = matEntries;
+                t.qOff = j.qOff;
+                t.peqOff = ~0ull;
+                t.tOff = j.tOff;
+                t.outOff = opsBytes;
+                t.m = j.m;
+                t.n = j.n;
+                t.nWp = nw;
+                tb.push_back(t);
+                matEntries += (uint64_t)j.n * nw;
+                opsBytes += (uint64_t)j.m + j.n;
+                bytes += need;
+                ++b;
+            }
+            const size_t n = b - a;
+            DevBuf<LJob> dJobs(be, n);
+            dJobs.upload(jobs.data() + a, n);
+            DevBuf<Rec> dRecs(be, n);
+            be->zero(dRecs.p, n * sizeof(Rec));
+            DevBuf<U2> dMat(be, matEntries);
+            LParams lp{dJobs.p, (int)n, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p};
+            be->launch_lane(lp, nw, MODE_NW, false, true);
+            DevBuf<TbJob> dTb(be, n);
+            dTb.upload(tb.data(), n);
+            DevBuf<uint8_t> dOps(be, opsBytes);
+            DevBuf<int> dStart(be, n), dLen(be, n);
+            TbParams tp{dTb.p, (int)n, dMat.p, nullptr, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
+                        dOps.p, dStart.p, dLen.p};
+            be->launch_traceback(tp);
+            // one pinned staging block for everything that comes back (fast D2H, no zero-fill of vectors)
+            const size_t offSt = round_up(n * sizeof(Rec), 64), offLn = offSt + round_up(n * sizeof(int), 64);
+            const size_t offOps = offLn + round_up(n * sizeof(int), 64);
+            uint8_t* host = static_cast<uint8_t*>(be->alloc_host(offOps + opsBytes));
+            const Rec* recs = reinterpret_cast<const Rec*>(host);
+            const int* st = reinterpret_cast<const int*>(host + offSt);
+            const int* ln = reinterpret_cast<const int*>(host + offLn);
+            const uint8_t* ops = host + offOps;
+            be->d2h(host, dRecs.p, n * sizeof(Rec));
+            be->d2h(host + offSt, dStart.p, n * sizeof(int));
+            be->d2h(host + offLn, dLen.p, n * sizeof(int));
+            be->d2h(host + offOps, dOps.p, opsBytes);
+            stats.d2hBytes += (long long)opsBytes + (long long)n * (long long)(sizeof(Rec) + 8);
+            for (size_t q = 0; q < n; ++q) sink(a + q, ops + tb[q].outOff + st[q], ln[q], recs[q].best);
+            be->free_host(host);
+            a = b;
+        }
+    }
+
+    // Hash indexes of the seeds of one target (candidate filter, seed stages), one per seed length; kept for
+    // the last target used.  Level 0: the shortest L with sigma^L >= filterSeedSlack * n (a fraction of a chance
+    // occurrence per seed: every occurrence costs a window sweep);
+    // levels 1 and 2: two and four symbols shorter (more seeds fit into a read, so a higher threshold, at the
+    // price of more chance occurrences) for the reads the previous level cannot decide.
+    struct SeedIndex {
+        int target = -1;
+        int L = 0, bits = 0;
+        DevBuf<int> bucketStart, positions;
+    } seed[SEED_LEVELS];
+    bool seed_index(int t, int level);
+
+    // One group of pairs that share a target and a word class (queries <= 256 rows), on its way through
+    // the distance pass.  Reads are addressed by their index `s` into `list`.
+    struct LaneGroup {
+        int t, nw;               // target index, 32-bit words per query
+        const std::vector<int>& list;  // the pairs of the group
+        const Target& tg;
+        int n;                   // target length
+        std::vector<int> bound;  // per read: largest distance that still counts as found
+        std::vector<int> excl;   // per read: it is known that no distance <= excl[s] exists
+        std::vector<int> direct; // reads that take the plain full sweep
+    };
+
+    // Chunk geometry: a HW sweep may be cut into target chunks (each re-started 2*m columns
+    // early, exact because no HW path spans more than 2*m target symbols) so that a small
+    // group still fills the machine.
+    void lane_geometry(const LaneGroup& c, int g, int nwL, int& chunks, int& chunkLen, bool perChunkRecs);
+
+    // One launch over the reads `sub` (indices into `list`) with sentinels / thresholds subK.
+    void lane_sweep(LaneGroup& c, const std::vector<int>& sub, const std::vector<int>& subK, int nwL, int chunks, int chunkLen,
+                    int cap, int prefixLen, int rangeMode, std::vector<Rec>& outRecs, std::vector<Ovf>& outOvf);
+
+    // Merge the chunks of every read: the minimum wins; its columns are the inline positions
+    // of the chunks attaining it (ascending by construction) plus, in a second pass, the
+    // listed ones.  Returns the reads whose lists are incomplete (some chunk holds > KPOS).
+    void lane_merge(LaneGroup& c, const std::vector<int>& sub, int chunks, const std::vector<Rec>& rr, const std::vector<Ovf>* oo,
+                    std::vector<int>& incomplete, long long& missing);
+
+    // It is now known that read s has no alignment within t: final if t is the caller's bound, else the
+    // read moves on to `next`.
+    void no_distance_within(LaneGroup& c, int s, int t, std::vector<int>& next);
+
+    // Seed stage: exact seeds of every read looked up in the hash index of the target; windows around
+    // the expected end columns are planned, swept and reduced on the device (eb_core.h: seed_plan_read).
+    void seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::vector<int>& next);
+
+    // Prefix stage over the reads `in` (indices into `list`): a sweep of the first P rows of every read reports
+    // the target ranges where that prefix matches within t = min(K0, bound); the whole read is then swept over
+    // one window per range.  A read is decided when a window holds a distance <= t (or when t is the caller's
+    // bound and none does).  Undecided reads go to `next` (a longer prefix or the plain sweep), reads with
+    // long end-location lists to c.direct.
+    void prefix_stage(LaneGroup& c, int P, int K0, const std::vector<int>& in, std::vector<int>& next);
+
+    // The plain lane-per-alignment sweep of the reads in c.direct over the whole target.
+    void plain_sweep(LaneGroup& c);
+
+    // Distance pass of one group of pairs that share target `t` and word class `nw` (queries <= 256
+    // rows): the stages of the candidate filter (HW over a long target), each on the
+    // reads the previous ones left undecided, then the plain lane-per-alignment sweep of what is left.
+    void lane_group(int t, int nw, const std::vector<int>& list);
+
+    // Distance pass of everything else: one alignment per warp (or per thread with its own target).
+    void warp_distance();
+
+    // editDistance and endLocations per pair from the sweep outcomes (ref cpp:219-225 and the -1 rule).
+    void collect_ends();
+
+    void start_locations();
+
+    void paths();
+};
+
+}  // namespace eb

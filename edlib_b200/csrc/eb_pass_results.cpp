@@ -1,0 +1,380 @@
+// eb_pass_results.cpp -- the remaining phases of a compute pass: warp-per-alignment distance sweeps,
+// assembly of distances and end locations (ref cpp:221-225, 658-693), start locations by reversed sweeps
+// (ref cpp:228-272), alignment paths (stored-matrix traceback and Hirschberg, ref cpp:276-289, 1161-1396).
+#include "eb_engine_internal.h"
+
+namespace eb {
+
+// Distance pass of everything else: one alignment per warp (or per thread with its own target).
+void Pass::warp_distance() {
+    // ---- W distance pass ------------------------------------------------------------------
+    {
+        std::vector<int> pending = wPairs;
+        int kRound = 64;  // ref cpp:201: the doubling schedule only matters for speed
+        while (!pending.empty()) {
+            std::vector<WTask> tasks;
+            std::vector<int> later;
+            for (int pair : pending) {
+                const int m = p->qlen[pair], n = p->tlen[pair];
+                int bound = -1;
+                if (mode == MODE_NW) {
+                    if (k >= 0) {
+                        bound = k;
+                    } else if (ceil_div(m, 32) > 32) {
+                        bound = kRound;
+                        if (bound < abs(n - m)) {
+                            later.push_back(pair);
+                            continue;
+                        }
+                    }
+                }
+                WPlan pl = plan_w(m, n, mode, bound);
+                WTask t;
+                t.pair = pair;
+                t.qOff = p->qoff[pair];
+                t.tOff = p->tg[p->tidx[pair]].off;
+                t.m = m;
+                t.n = n;
+                t.mode = mode;
+                t.flags = pl.slide ? WF_SLIDE : 0;
+                t.dhi = pl.dhi;
+                t.R = pl.R;
+                t.nWp = pl.nWp;
+                t.kInit = ((k < 0 || k > m) ? m : k) + 1;
+                t.tag = pl.slide ? bound : -1;  // a sliding result is only valid when <= bound
+                t.wantPositions = (mode != MODE_NW);
+                tasks.push_back(std::move(t));
+            }
+            runner.run(tasks);
+            for (WTask& t : tasks) {
+                stats.wCells += (long long)t.m * t.n;
+                if (t.tag >= 0 && t.rec.best > t.tag) {  // outside the band of this round
+                    if (k < 0) later.push_back(t.pair);
+                    else best[t.pair] = 0x7fffffff;
+                    continue;
+                }
+                best[t.pair] = t.rec.cnt > 0 ? t.rec.best : 0x7fffffff;
+                cnt[t.pair] = t.rec.cnt;
+                posStart[t.pair] = (long long)posPool.size();
+                for (int q = 0; q < std::min(t.rec.cnt, KPOS); ++q) posPool.push_back(t.rec.pos[q]);
+                posPool.insert(posPool.end(), t.extra.begin(), t.extra.end());
+                posLen[t.pair] = (int)((long long)posPool.size() - posStart[t.pair]);
+            }
+            pending.swap(later);
+            if (kRound < (1 << 29)) kRound *= 2;
+        }
+    }
+}
+
+// editDistance and endLocations per pair from the sweep outcomes (ref cpp:219-225 and the -1 rule).
+void Pass::collect_ends() {
+    // ---- distances and end locations: counts per pair, offsets, fill (on a few host threads) -------
+    // ref cpp:670, 681-693: the padded bottom cell of column W-1 shows up as end location -1
+    auto accepted = [&](int i) -> int {  // number of end locations of pair i, or -1 if it has no result
+        if (p->special[i]) return -1;
+        if (best[i] < 0 || best[i] == 0x7fffffff) return -1;  // rejected up front or nothing tracked
+        if (k >= 0 && best[i] > k) return -1;
+        if (mode == MODE_NW) return 1;
+        const int m = p->qlen[i];
+        if (best[i] > m) return -1;
+        const int W64 = ceil_div(m, 64) * 64 - m;
+        return posLen[i] + ((best[i] == m && W64 > 0) ? 1 : 0);
+    };
+    const size_t nparts = host_parts((size_t)N, 65536);
+    std::vector<long long> partCount(nparts + 1, 0);
+    std::vector<int> bad(nparts, 0);
+    auto run = [&](const std::function<void(size_t, size_t, size_t)>& fn) {
+        HostPool::get().run(nparts, [&](size_t t) { fn(t, (size_t)N * t / nparts, (size_t)N * (t + 1) / nparts); });
+    };
+    run([&](size_t t, size_t lo, size_t hi) {
+        long long c = 0;
+        for (size_t i = lo; i < hi; ++i) {
+            const int a = accepted((int)i);
+            if (a > 0) c += a;
+            if (a >= 0 && mode != MODE_NW && posLen[i] != cnt[i]) bad[t] = 1;
+        }
+        partCount[t + 1] = c;
+    });
+    for (size_t t = 0; t < nparts; ++t) {
+        if (bad[t]) throw std::runtime_error("internal: end-location count mismatch");
+        partCount[t + 1] += partCount[t];
+    }
+    p->endPool.resize((size_t)partCount[nparts]);
+    run([&](size_t t, size_t lo, size_t hi) {
+        long long at = partCount[t];
+        for (size_t i = lo; i < hi; ++i) {
+            p->endStart[i] = at;
+            const int a = accepted((int)i);
+            if (a < 0) {
+                p->ed[i] = -1;
+                p->endCount[i] = 0;
+                continue;
+            }
+            p->ed[i] = best[i];
+            p->endCount[i] = a;
+            if (mode == MODE_NW) {
+                p->endPool[(size_t)at++] = p->tlen[i] - 1;  // ref cpp:221-225
+                continue;
+            }
+            if (a > posLen[i]) p->endPool[(size_t)at++] = -1;
+            if (posLen[i]) memcpy(p->endPool.data() + at, posPool.data() + posStart[i], sizeof(int) * (size_t)posLen[i]);
+            at += posLen[i];
+        }
+    });
+}
+
+void Pass::start_locations() {
+    // ---- start locations (ref cpp:228-272) ------------------------------------------------
+    const bool wantLoc = p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH;
+    if (wantLoc) {
+        p->startPool.assign(p->endPool.size(), 0);
+        if (mode == MODE_HW) {
+            std::vector<WTask> tasks;
+            std::vector<long long> slotOf;
+            std::vector<LJob> lj[9];          // short queries: straight to the lane kernel, per word class
+            std::vector<long long> lslot[9];
+            std::vector<int> lpair[9];
+            for (int i = 0; i < N; ++i) {
+                if (p->ed[i] < 0) continue;
+                const int m = p->qlen[i];
+                const bool lane = lane_ok(m);
+                for (int q = 0; q < p->endCount[i]; ++q) {
+                    const long long slot = p->endStart[i] + q;
+                    const int e = p->endPool[(size_t)slot];
+                    if (e < 0) continue;  // ref cpp:237-249: start 0
+                    if (lane) {
+                        const int nw = ceil_div(m, 32);
+                        LJob j;
+                        memset(&j, 0, sizeof(j));
+                        j.qOff = p->qoff[i];
+                        j.tOff = p->tg[p->tidx[i]].off + (uint64_t)e;  // first symbol read, walking backward
+                        j.m = m;
+                        j.n = (int)std::min<long long>((long long)e + 1, (long long)m + p->ed[i]);
+                        j.kInit = p->ed[i] + 1;
+                        lj[nw].push_back(j);
+                        lslot[nw].push_back(slot);
+                        lpair[nw].push_back(i);
+                        continue;
+                    }
+                    WTask t;
+                    t.pair = i;
+                    t.qOff = p->qoff[i];
+                    t.tOff = p->tg[p->tidx[i]].off + (uint64_t)e;  // first symbol read, walking backward
+                    t.m = m;
+                    t.n = (int)std::min<long long>((long long)e + 1, (long long)m + p->ed[i]);
+                    t.mode = MODE_SHW;
+                    t.flags = WF_QREV | WF_TREV;
+                    t.kInit = p->ed[i] + 1;
+                    WPlan pl = plan_w(t.m, t.n, MODE_SHW, -1);
+                    t.R = pl.R;
+                    t.nWp = pl.nWp;
+                    tasks.push_back(std::move(t));
+                    slotOf.push_back(slot);
+                }
+            }
+            trace.mark("starts: jobs built");
+            for (int nw = 1; nw <= 8; ++nw) {
+                if (lj[nw].empty()) continue;
+                std::vector<Rec> recs;
+                lane_launch(lj[nw], nw, MODE_SHW, true, recs);
+                for (size_t j = 0; j < recs.size(); ++j) {
+                    if (recs[j].cnt <= 0 || recs[j].best != p->ed[lpair[nw][j]])
+                        throw std::runtime_error("internal: start-location sweep disagrees");
+                    const int e = p->endPool[(size_t)lslot[nw][j]];
+                    p->startPool[(size_t)lslot[nw][j]] = e - recs[j].last;  // ref cpp:260
+                }
+            }
+            trace.mark("starts: lane sweeps");
+            runner.run(tasks);
+            for (size_t j = 0; j < tasks.size(); ++j) {
+                const WTask& t = tasks[j];
+                if (t.rec.cnt <= 0 || t.rec.best != p->ed[t.pair]) throw std::runtime_error("internal: start-location sweep disagrees");
+                const int e = p->endPool[(size_t)slotOf[j]];
+                p->startPool[(size_t)slotOf[j]] = e - t.rec.last;  // ref cpp:260
+            }
+        }
+    }
+}
+
+void Pass::paths() {
+    // ---- alignment path (ref cpp:276-289, 1161-1213, 1231-1396) ---------------------------
+    // obtainAlignment as a level-synchronous tree: a node is an NW sub-problem (query slice,
+    // target slice, known score).  Inside the reference's 1 MiB rule (cpp:1188-1190) it is a
+    // leaf: matrix-storing sweep + traceback kernel.  Otherwise it is split like
+    // obtainAlignmentHirschberg: the score column left of the target's middle from a forward
+    // sweep and the one right of it from a reversed sweep (both on the device, cpp:1252-1260),
+    // the split row chosen by the reference's candidate order (cpp:1321-1353), both halves
+    // becoming nodes of the next level (cpp:1372-1380).  All nodes of a level run in one batch.
+    if (p->cfg.task == EDLIB_TASK_PATH) {
+        struct Node {
+            int pair;
+            uint64_t qOff, tOff;
+            int m, n, best;
+            int left = -1, right = -1;
+            long long opsOff = -1;  // into opsPool (leaf) ...
+            int opsLen = 0;
+            int fillOp = -1;        // ... or a run of one op (empty side, cpp:1168-1175)
+        };
+        std::vector<Node> nodes;
+        std::vector<int> rootOf(N, -1), frontier, leaves;
+        for (int i = 0; i < N; ++i) {
+            if (p->ed[i] < 0) continue;
+            const int s0 = p->startPool[(size_t)p->endStart[i]], e0 = p->endPool[(size_t)p->endStart[i]];
+            Node nd;
+            nd.pair = i;
+            nd.qOff = p->qoff[i];
+            nd.tOff = p->tg[p->tidx[i]].off + (uint64_t)s0;
+            nd.m = p->qlen[i];
+            nd.n = e0 - s0 + 1;
+            nd.best = p->ed[i];
+            rootOf[i] = (int)nodes.size();
+            frontier.push_back((int)nodes.size());
+            nodes.push_back(nd);
+        }
+        while (!frontier.empty()) {
+            std::vector<int> split;
+            for (int id : frontier) {
+                Node& nd = nodes[id];
+                if (nd.m == 0 || nd.n <= 0) {
+                    nd.fillOp = (nd.m == 0) ? EDLIB_EDOP_DELETE : EDLIB_EDOP_INSERT;
+                    nd.opsLen = nd.m + std::max(nd.n, 0);
+                    continue;
+                }
+                const long long matrixBytes = 20LL * ceil_div(nd.m, 64) * nd.n + 8LL * nd.n;  // cpp:1188-1190
+                if (matrixBytes < 1024 * 1024) leaves.push_back(id);
+                else split.push_back(id);
+            }
+            frontier.clear();
+            if (split.empty()) break;
+            std::vector<WTask> tasks;
+            tasks.reserve(split.size() * 2);
+            for (int id : split) {
+                const Node& nd = nodes[id];
+                const int leftW = nd.n / 2, rightW = nd.n - leftW;  // cpp:1247-1248
+                const WPlan pl = plan_w(nd.m, nd.n, MODE_NW, nd.best);  // band of the WHOLE node
+                WTask f;
+                f.pair = id;
+                f.qOff = nd.qOff;
+                f.tOff = nd.tOff;
+                f.m = nd.m;
+                f.n = leftW;
+                f.mode = MODE_NW;
+                f.flags = WF_STOPCOL | (pl.slide ? WF_SLIDE : 0);
+                f.dhi = pl.dhi;
+                f.stopCol = leftW - 1;
+                f.R = pl.R;
+                f.nWp = pl.nWp;
+                f.splitSide = 0;
+                f.splitBest = nd.best;
+                WTask r = f;
+                r.tOff = nd.tOff + (uint64_t)nd.n - 1;  // reversed: first symbol read is the last one
+                r.n = rightW;
+                r.flags |= WF_QREV | WF_TREV;
+                r.stopCol = rightW - 1;
+                r.splitSide = 1;
+                tasks.push_back(std::move(f));
+                tasks.push_back(std::move(r));
+            }
+            runner.run(tasks);
+            for (size_t s = 0; s < split.size(); ++s) {
+                const int id = split[s];
+                const Node nd = nodes[id];
+                const int leftW = nd.n / 2, rightW = nd.n - leftW;
+                const SplitOut& so = tasks[2 * s].split;  // found on the device (split_kernel)
+                const int h = so.h;
+                if (h < 0) throw std::runtime_error("internal: Hirschberg split not found");
+                Node a, b;
+                a.pair = b.pair = nd.pair;
+                a.qOff = nd.qOff;
+                a.tOff = nd.tOff;
+                a.m = h;
+                a.n = leftW;
+                a.best = so.left;
+                b.qOff = nd.qOff + (uint64_t)h;
+                b.tOff = nd.tOff + (uint64_t)leftW;
+                b.m = nd.m - h;
+                b.n = rightW;
+                b.best = so.right;
+                nodes[id].left = (int)nodes.size();
+                frontier.push_back((int)nodes.size());
+                nodes.push_back(a);
+                nodes[id].right = (int)nodes.size();
+                frontier.push_back((int)nodes.size());
+                nodes.push_back(b);
+            }
+        }
+        {
+            std::vector<WTask> tasks;
+            std::vector<LJob> lj[9];  // leaves with short queries: lane kernel, per word class
+            std::vector<int> lnode[9];
+            for (int id : leaves) {
+                const Node& nd = nodes[id];
+                if (lane_ok(nd.m)) {
+                    const int nw = ceil_div(nd.m, 32);
+                    LJob j;
+                    memset(&j, 0, sizeof(j));
+                    j.qOff = nd.qOff;
+                    j.tOff = nd.tOff;
+                    j.m = nd.m;
+                    j.n = nd.n;
+                    lj[nw].push_back(j);
+                    lnode[nw].push_back(id);
+                    continue;
+                }
+                WTask t;
+                t.pair = id;
+                t.qOff = nd.qOff;
+                t.tOff = nd.tOff;
+                t.m = nd.m;
+                t.n = nd.n;
+                t.mode = MODE_NW;
+                t.flags = WF_STORE;
+                const WPlan pl = plan_w(nd.m, nd.n, MODE_NW, -1);
+                t.R = pl.R;
+                t.nWp = pl.nWp;
+                tasks.push_back(std::move(t));
+            }
+            trace.mark("paths: tree + leaf jobs built");
+            for (int nw = 1; nw <= 8; ++nw) {
+                if (lj[nw].empty()) continue;
+                lane_paths(lj[nw], nw, [&](size_t j, const uint8_t* ops, int len, int score) {
+                    Node& nd = nodes[lnode[nw][j]];
+                    if (score != nd.best) throw std::runtime_error("internal: path sweep disagrees with the distance");
+                    nd.opsOff = (long long)opsPool.size();
+                    nd.opsLen = len;
+                    opsPool.insert(opsPool.end(), ops, ops + len);
+                });
+            }
+            runner.run(tasks);
+            for (const WTask& t : tasks) {
+                Node& nd = nodes[t.pair];
+                if (t.rec.best != nd.best) throw std::runtime_error("internal: path sweep disagrees with the distance");
+                nd.opsOff = t.opsOff;
+                nd.opsLen = t.opsLen;
+            }
+        }
+        trace.mark("paths: leaf sweeps + tracebacks");
+        // in-order concatenation (cpp:1388-1391)
+        std::vector<int> stack;
+        for (int i = 0; i < N; ++i) {
+            if (rootOf[i] < 0) continue;
+            p->alnStart[i] = (long long)p->alnPool.size();
+            stack.assign(1, rootOf[i]);
+            while (!stack.empty()) {
+                const int id = stack.back();
+                stack.pop_back();
+                const Node& nd = nodes[id];
+                if (nd.left >= 0) {
+                    stack.push_back(nd.right);
+                    stack.push_back(nd.left);
+                } else if (nd.fillOp >= 0) {
+                    p->alnPool.insert(p->alnPool.end(), (size_t)nd.opsLen, (uint8_t)nd.fillOp);
+                } else {
+                    p->alnPool.insert(p->alnPool.end(), opsPool.begin() + nd.opsOff, opsPool.begin() + nd.opsOff + nd.opsLen);
+                }
+            }
+            p->alnLen[i] = (int)(p->alnPool.size() - (size_t)p->alnStart[i]);
+        }
+    }
+}
+}  // namespace eb

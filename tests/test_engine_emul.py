@@ -1,4 +1,4 @@
-"""CPU tests of the host engine + kernel LOGIC: the real planner (eb_engine.cpp) drives the real
+"""CPU tests of the host engine + kernel LOGIC: the real planner (eb_engine.cpp and the eb_pass_*.cpp / eb_wrunner.cpp units) drives the real
 kernel bodies (eb_core.h) through the host SIMT emulation backend (tests/emul/), and every
 result field is compared with the reference build / oracle.  No GPU involved; the product
 library is not used here (its CUDA path is covered by the -m gpu tests)."""
