@@ -116,7 +116,8 @@ def filter_cases(seed, count):
     neighbouring candidate ranges, equal-score hits in different windows), tandem-repeat targets
     (range lists that saturate), explicit and free k -- every branch of the two-stage candidate filter."""
     rng = random.Random(seed)
-    for _ in range(count):
+    yield filter_edge_case(seed)
+    for _ in range(count - 1):
         alpha = rng.choice([b"ACGT", b"ACGT", b"ACGT", b"ACGTN", b"ACDEFGHIKLMNPQRSTVWY", b"AC"])
         shape = rng.random()
         if shape < 0.12:  # tandem repeat with a few mutations: candidates everywhere
@@ -145,6 +146,27 @@ def filter_cases(seed, count):
                 q = q + rand_seq(rng, L - len(q), alpha)
             qs.append(q)
         yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 3, 10, 40]), mode=2, task=rng.randrange(3), eqs=None)
+
+
+def filter_edge_case(seed):
+    """Deterministic corner cases of the window planning: reads taken from the very start and the very end
+    of the target (windows clipped at column 0 / n-1), reads hanging over either end, a read longer than what
+    is left of the target, exact duplicates far apart and back to back (equal-score hits in several windows,
+    long end-location lists), a read equal to a tandem stretch (saturation), one unrelated read."""
+    rng = random.Random(seed * 7919 + 1)
+    alpha = b"ACGT"
+    unit = rand_seq(rng, 11, alpha)
+    body = rand_seq(rng, 6000, alpha)
+    dup = body[2000:2150]
+    t = body[:4000] + dup + dup + body[4000:] + unit * 40 + rand_seq(rng, 500, alpha)
+    n = len(t)
+    qs = [t[:150], t[:90], t[n - 150:], t[n - 70:],                              # flush with either end
+          rand_seq(rng, 20, alpha) + t[:130], t[n - 130:] + rand_seq(rng, 20, alpha),  # hanging over the ends
+          t[n - 200:] + rand_seq(rng, 56, alpha),                                # longer than what is left
+          dup, mutate(rng, dup, 0.03, alpha), dup[10:140],                       # three copies of the same stretch
+          (unit * 40)[:150], (unit * 40)[5:125],                                 # tandem repeat
+          rand_seq(rng, 150, alpha), t[3000:3100], mutate(rng, t[1000:1256], 0.05, alpha)[:256]]
+    return dict(qs=qs, ts=[t] * len(qs), k=[-1, 12, 3][seed % 3], mode=2, task=seed % 3, eqs=None)
 
 
 def pairwise_cases(seed, count):
