@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <exception>
 #include <functional>
 #include <atomic>
 #include <condition_variable>
@@ -64,9 +65,15 @@ public:
         }
         cv_.notify_all();
         work(gen);
-        std::unique_lock<std::mutex> lock(mu_);
-        done_.wait(lock, [this]() { return pending_ == 0; });
-        fn_ = nullptr;
+        std::exception_ptr err;
+        {
+            std::unique_lock<std::mutex> lock(mu_);
+            done_.wait(lock, [this]() { return pending_ == 0; });
+            fn_ = nullptr;
+            err = error_;
+            error_ = nullptr;
+        }
+        if (err) std::rethrow_exception(err);  // the first exception a task threw, on the caller's thread
     }
 
 private:
@@ -87,8 +94,14 @@ private:
                 i = next_++;
                 fn = fn_;
             }
-            (*fn)(i);
+            std::exception_ptr err;
+            try {
+                (*fn)(i);
+            } catch (...) {
+                err = std::current_exception();
+            }
             std::lock_guard<std::mutex> lock(mu_);
+            if (err && !error_) error_ = err;
             if (--pending_ == 0) done_.notify_all();
         }
     }
@@ -107,6 +120,7 @@ private:
     std::mutex mu_;
     std::condition_variable cv_, done_;
     const std::function<void(size_t)>* fn_ = nullptr;
+    std::exception_ptr error_;
     size_t total_ = 0, pending_ = 0, next_ = 0;
     unsigned long long generation_ = 0;
 };

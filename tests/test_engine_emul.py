@@ -119,6 +119,32 @@ def test_sequences_longer_than_one_presence_item(emul):
         assert r == chk.align(a, b, -1, 2, 0)
 
 
+def test_bad_input_in_a_large_batch_is_an_error_not_a_crash(emul):
+    """A negative length is found by a worker thread of the host pool: the call returns EDLIB_STATUS_ERROR with
+    every result marked, and the engine keeps working afterwards."""
+    import ctypes as C
+    from edlib_b200._ffi import AlignResult, make_config
+    n = 140000
+    q = C.create_string_buffer(b"ACGTACGTAC", 10)
+    t = C.create_string_buffer(b"ACGTTCGTACGGA", 13)
+    qptr = (C.c_char_p * n)(*[C.cast(q, C.c_char_p)] * n)
+    tptr = (C.c_char_p * n)(*[C.cast(t, C.c_char_p)] * n)
+    qlen = (C.c_int * n)(*[10] * n)
+    tlen = (C.c_int * n)(*[13] * n)
+    qlen[n - 7] = -3
+    cfg, keep = make_config(-1, 2, 0, None)
+    res = (AlignResult * n)()
+    assert emul.lib.edlibAlignBatch(qptr, qlen, tptr, tlen, n, cfg, res) == 1
+    assert res[0].status == 1 and res[n - 1].status == 1
+    qlen[n - 7] = 10
+    assert emul.lib.edlibAlignBatch(qptr, qlen, tptr, tlen, n, cfg, res) == 0
+    exp = emul.align(b"ACGTACGTAC", b"ACGTTCGTACGGA", -1, 2, 0)
+    assert res[5].editDistance == exp["editDistance"] and res[n - 7].editDistance == exp["editDistance"]
+    for i in range(n):
+        emul.free(res[i])
+    del keep
+
+
 def test_staged_batches_are_independent(emul):
     """edlibB200BatchPrepare / Compute / Results: two batches alive at once, computed out of order and twice;
     each yields what the one-shot call yields."""
