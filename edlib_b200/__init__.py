@@ -12,7 +12,7 @@ import re as _re
 from ._ffi import (EDLIB_CIGAR_EXTENDED, EDLIB_CIGAR_STANDARD, EDLIB_STATUS_OK, MODES, TASKS, EdlibLib,
                    product_path)
 
-__all__ = ["align", "align_batch", "getNiceAlignment", "library"]
+__all__ = ["align", "align_batch", "align_many", "getNiceAlignment", "library"]
 
 _lib = None
 
@@ -92,6 +92,9 @@ def align_batch(queries, targets, mode="NW", task="distance", k=-1, additionalEq
     if st != EDLIB_STATUS_OK:
         raise Exception("There was an error. (" + library().lib.edlibB200LastError().decode() + ")")
     return [_result(d, True) for d in res]
+
+
+align_many = align_batch  # the name SURVEY.md 8f proposes for the batched binding entry
 
 
 def getNiceAlignment(alignResult, query, target, gapSymbol="-"):
