@@ -321,9 +321,10 @@ EB_HD void k1_range_flush(K1State<NW>& st, int slot, Ovf* list, int* listCount, 
 }
 
 // Restates the bookkeeping of ref cpp:658-673: a strictly better score restarts the list.
-// CAP inline positions: KPOS for Rec, KPOSW when `rec` is really the header of a WinRec.
-template <int NW, bool RANGE = false, int CAP = KPOS>
-EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
+// RecT is Rec (KPOS inline positions) or WinRec (KPOSW).
+template <int NW, bool RANGE = false, class RecT>
+EB_HD void k1_event(K1State<NW>& st, int score, int column, RecT* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
+    constexpr int CAP = (int)(sizeof(rec->pos) / sizeof(rec->pos[0]));
     if (RANGE) {  // candidate filter: recIdx is the read slot, ovf the range list
         if (st.cnt > 0 && (column - st.last > K1_RANGE_GAP || column - st.first > K1_RANGE_SPAN)) {
             k1_range_flush<NW>(st, recIdx, ovf, ovfCount, ovfCap);
@@ -339,8 +340,7 @@ EB_HD void k1_event(K1State<NW>& st, int score, int column, Rec* rec, int recIdx
         st.cnt = 0;
     }
     if (st.cnt < CAP) {
-        int* pos = rec->pos;
-        pos[st.cnt] = column;
+        rec->pos[st.cnt] = column;
     } else if (ovfCap > 0) {  // second pass only: the list then holds final positions exclusively
         const int slot = atomic_add_int(ovfCount, 1);
         if (slot < ovfCap) {
@@ -370,9 +370,9 @@ struct RevSyms {
 // running minimum and its columns are recorded; without it only the state advances (halo
 // columns of a chunk).  Columns go four at a time: the four last-row scores stay in registers
 // and are compared against the running minimum once per group (events are rare).
-template <int NW, bool TOP_ONE, bool TRACK, bool RANGE = false, int CAP = KPOS, class Acc, class Syms>
+template <int NW, bool TOP_ONE, bool TRACK, bool RANGE = false, class Acc, class Syms, class RecT>
 EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int count, int cAbs,
-                      Rec* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
+                      RecT* rec, int recIdx, Ovf* ovf, int* ovfCount, int ovfCap) {
     int i = 0;
     for (; i + 4 <= count; i += 4) {  // body: groups of four columns (byte reads: LSU, not ALU, work)
         int sc[4];
@@ -390,7 +390,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
             if (lo <= st.best) {
                 EB_UNROLL
                 for (int j = 0; j < 4; ++j)
-                    if (sc[j] <= st.best) k1_event<NW, RANGE, CAP>(st, sc[j], cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
+                    if (sc[j] <= st.best) k1_event<NW, RANGE>(st, sc[j], cAbs + i + j, rec, recIdx, ovf, ovfCount, ovfCap);
             }
         }
     }
@@ -398,7 +398,7 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
         uint32_t Eq[NW];
         acc.load(syms.read1(i), Eq);
         k1_step<NW, TOP_ONE>(st.Pv, st.Mv, Eq, st.up, st.down);
-        if (TRACK && st.up - st.down <= st.best) k1_event<NW, RANGE, CAP>(st, st.up - st.down, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
+        if (TRACK && st.up - st.down <= st.best) k1_event<NW, RANGE>(st, st.up - st.down, cAbs + i, rec, recIdx, ovf, ovfCount, ovfCap);
     }
 }
 
@@ -486,7 +486,7 @@ template <int NW, class Acc>
 EB_HD void k1w_thread(const K1WParams& p, int slot, Acc& acc) {
     const int pair = p.readList[slot];
     const int m = p.qlen[pair];
-    Rec* rec = reinterpret_cast<Rec*>(p.recs + slot);  // header of the WinRec; KPOSW positions follow
+    WinRec* rec = p.recs + slot;
     k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE_HW, p.ncodes, p.eqtab);
     K1State<NW> st;
     k1_init<NW>(st, m, p.kInit[slot]);
@@ -497,14 +497,14 @@ EB_HD void k1w_thread(const K1WParams& p, int slot, Acc& acc) {
     bool hopeless = false;
     for (int j = 0; j < tf; j += 32) {
         const int cntj = tf - j < 32 ? tf - j : 32;
-        k1_columns<NW, false, false, false, KPOSW>(st, acc, PtrSyms{p.tcodes + ws + j}, cntj, ws + j, rec, slot, nullptr, nullptr, 0);
+        k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + ws + j}, cntj, ws + j, rec, slot, nullptr, nullptr, 0);
         if (st.up - st.down - (len - (j + cntj)) >= st.best) {
             hopeless = true;
             break;
         }
     }
     if (!hopeless)
-        k1_columns<NW, false, true, false, KPOSW>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
+        k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
     rec->best = st.best;
     rec->cnt = st.cnt;
 }
