@@ -77,9 +77,38 @@ public:
     }
 
 private:
+    // Pool width: EDLIB_B200_HOST_THREADS if set; else min(16, CPUs this process may use / ranks on this node),
+    // where the CPUs are bounded by a cgroup quota when there is one (containers often expose every hardware
+    // thread but grant far fewer) and the ranks come from torchrun's LOCAL_WORLD_SIZE.
+    static size_t pool_width() {
+        if (const char* e = getenv("EDLIB_B200_HOST_THREADS")) {
+            const int v = atoi(e);
+            if (v > 0) return (size_t)std::min(v, 64);
+        }
+        double cpus = (double)std::max(1u, std::thread::hardware_concurrency());
+        if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2: "<quota|max> <period>"
+            char quota[32];
+            double period = 0;
+            if (fscanf(f, "%31s %lf", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0)
+                cpus = std::min(cpus, std::max(1.0, atof(quota) / period));
+            fclose(f);
+        } else if (FILE* q = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {  // cgroup v1
+            double quotaUs = -1, periodUs = 0;
+            if (fscanf(q, "%lf", &quotaUs) != 1) quotaUs = -1;
+            fclose(q);
+            if (FILE* pf = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+                if (fscanf(pf, "%lf", &periodUs) != 1) periodUs = 0;
+                fclose(pf);
+            }
+            if (quotaUs > 0 && periodUs > 0) cpus = std::min(cpus, std::max(1.0, quotaUs / periodUs));
+        }
+        int ranks = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        const size_t w = (size_t)(cpus / ranks + 0.5);
+        return std::max<size_t>(2, std::min<size_t>(16, w));
+    }
     HostPool() {
-        const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-        workers_ = std::min<size_t>(16, hw) - 1;
+        workers_ = pool_width() - 1;
         for (size_t i = 0; i < workers_; ++i) std::thread([this]() { loop(); }).detach();
     }
     // Tasks are few and coarse, so they are claimed under the lock; a worker only ever claims tasks of
