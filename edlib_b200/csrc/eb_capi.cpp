@@ -150,8 +150,9 @@ EDLIB_API char* edlibAlignmentToCigar(const unsigned char* alignment, int alignm
 // ---- include/edlib_b200.h ------------------------------------------------------------------
 
 EDLIB_API const char* edlibB200LastError(void) {
+    // every calling thread reads its own copy: a later call on another thread cannot change it under the reader
+    static thread_local std::string copy;
     std::lock_guard<std::mutex> lock(g_mu);
-    static std::string copy;
     copy = g_engine ? g_engine->lastError : g_initError;
     return copy.c_str();
 }
@@ -159,6 +160,7 @@ EDLIB_API const char* edlibB200LastError(void) {
 EDLIB_API int edlibB200SetDevice(int device) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (g_initTried) return EDLIB_STATUS_ERROR;
+    // remembered by the backend factory: the engine binds to THIS device whichever thread makes the first call
     return eb::select_device(device, &g_initError) == 0 ? EDLIB_STATUS_OK : EDLIB_STATUS_ERROR;
 }
 

@@ -100,6 +100,7 @@ struct K1WParams {
     const int* winLen;       // [numReads] columns swept
     const int* trackFrom;    // [numReads] first column (relative to winStart) whose score may be recorded
     int numReads;
+    const int* countPtr;     // device-planned jobs: the number of jobs is min(*countPtr, numReads); or nullptr
     int ncodes;
     const uint8_t* eqtab;
     WinRec* recs;            // [numReads]; positions are absolute target columns
@@ -220,29 +221,45 @@ struct SplitParams {
     SplitOut* out;
 };
 
-// Seed index of a target (candidate filter, first stage): a CSR table from the hash bucket of every
-// L-symbol substring of the target to the positions where such substrings start.  Build: count
-// (seed_count_item), exclusive scan of the counts (Backend::launch_scan), fill (seed_fill_item).
+// Seed index of a target (candidate filter, seed stages): ONE radix table serves every seed level.  The key of
+// target position i is the base-sigma number of the Lidx codes starting there (codes past the end count as 0),
+// so the table is a CSR from key to the positions holding that Lidx-mer, and all positions whose Lidx-mer
+// starts with a SHORTER word form one contiguous key range: a seed of length Ls <= Lidx is looked up as the
+// range [key(seed) * sigma^(Lidx-Ls), (key(seed)+1) * sigma^(Lidx-Ls)) with no verification at all, a longer
+// seed by its first Lidx codes plus a comparison of the remaining ones.  Build: count (seed_count_item),
+// exclusive scan of the counts (Backend::launch_scan), fill (seed_fill_item).
 struct SeedIndexParams {
     const uint8_t* tcodes;   // encoded target
     int n;
-    int L;                   // seed length
-    int bits;                // 2^bits buckets
-    int* bucketStart;        // [2^bits + 1] counts, then their exclusive prefix sums (last = n - L + 1)
-    int* cursor;             // [2^bits] fill cursors, zeroed by the host
-    int* positions;          // [n - L + 1]
+    int Lidx;                // symbols per key
+    int sigma;               // radix (>= 2, >= number of target codes)
+    int numPos;              // positions indexed: 0 .. numPos-1 (= n - Lmin + 1, Lmin the shortest seed used)
+    int numKeys;             // sigma^Lidx
+    int* bucketStart;        // [numKeys + 1] counts, then their exclusive prefix sums (last = numPos)
+    int* cursor;             // [numKeys] fill cursors, zeroed by the host
+    int* positions;          // [numPos]
 };
 // candidate end columns per read before the read is passed on as saturated, per seed level (shorter seeds
 // have more chance occurrences); the planning kernel is instantiated per capacity
 #define SEED_LEVELS 3
 #define SEED_CAND_0 64
 #define SEED_CAND_1 256
-#define SEED_CAND_2 512
+#define SEED_CAND_2 1024
 enum SeedState : int { SEED_NONE = 0, SEED_WINDOWS = 1, SEED_SATURATED = 2, SEED_LONG_LIST = 3 };
 struct SeedPlan {
     int first, count;        // the read's windows in the job arrays
     int state;               // SeedState
+    int thr;                 // threshold t the windows were planned for (-1: the read was left out of the stage)
 };
+// Threshold of a read of m rows at a seed level with seeds of Ls symbols: the largest t with t+1 disjoint
+// seeds inside the read, capped by the caller's bound and the stage's cap; -1 if the stage cannot help.
+EB_HD int seed_threshold(int m, int kBound, int Ls, int seedK, int excl) {
+    const int bound = (kBound < 0 || kBound > m) ? m : kBound;  // distances never exceed m in HW (ref cpp:566-568)
+    int t = m / Ls - 1;
+    if (t > seedK) t = seedK;
+    if (t > bound) t = bound;
+    return (m >= 2 * Ls && t > excl) ? t : -1;
+}
 // Per read: t+1 disjoint seeds are looked up; every exact occurrence yields the expected end column
 // of the alignment it belongs to; neighbouring ones share a window (eb_core.h: seed_plan_read).
 struct SeedPlanParams {
@@ -251,13 +268,16 @@ struct SeedPlanParams {
     const uint8_t* qcodes;
     const uint64_t* qoff;
     const int* qlen;
-    const int* readList;     // [numReads] pair indices
-    const int* thr;          // [numReads] threshold t; (t + 1) * L <= query length (t < 0: read skipped)
+    const int* readList;     // [numReads] pair indices, or nullptr: pair = firstPair + slot
+    int firstPair;
+    const int* thr;          // [numReads] threshold t per read (t < 0: read skipped), or nullptr: seed_threshold(m, kBound, Ls, seedK, -1)
+    int kBound, seedK;
     int numReads;
-    int L, bits;
+    int Ls;                  // seed length of this level
+    int Lidx, sigma, numKeys;
     const int* bucketStart;
     const int* positions;
-    int maxBucket;           // buckets longer than this saturate the read (repeats)
+    int maxBucket;           // a seed with more index entries than this saturates the read (repeats)
     int level;               // seed level (selects the candidate capacity)
     int spread;              // widest group of candidates verified as one window
     // outputs: K1W jobs (K1WParams arrays) and the per-read plan
@@ -267,20 +287,56 @@ struct SeedPlanParams {
     int* winLen;
     int* winTf;
     int winCap;
-    int* winCount;           // zeroed by the host; may exceed winCap (nothing is written beyond it)
+    int* winCount;           // zeroed by the host; may exceed winCap (reads whose windows do not fit are saturated)
     SeedPlan* plan;          // [numReads]
 };
-// Per read: minimum over its windows -> out[slot] (rsv = SeedState: SEED_WINDOWS means decided with
-// best/cnt/pos filled, SEED_NONE that no distance <= t exists).
+// Leftover entry of the device-driven first seed level: a read this level could not decide.
+struct Leftover {
+    int pair;
+    int excl;                // no distance <= excl exists (-1: nothing known); -2: long end-location list (plain sweep)
+};
+enum RecState : int { REC_DONE = 100, REC_PENDING = 101 };
+// Per read: minimum over its windows -> out[slot].
+//   host-driven stages (leftover == nullptr): rsv = SeedState (SEED_WINDOWS: decided with best/cnt/pos filled,
+//   SEED_NONE: no distance <= t exists); the host works out what happens to the read.
+//   device-driven first level (leftover != nullptr): rsv = REC_DONE (best/cnt/pos final; best = 0x7fffffff with
+//   cnt = 0 when no alignment within the caller's bound exists) or REC_PENDING, in which case the read is
+//   appended to the leftover list for the host-driven stages.
 struct WinReduceParams {
     const SeedPlan* plan;
-    const int* thr;
     const WinRec* winRecs;
     int numReads;
     Rec* out;                // cnt > KPOS: positions KPOS.. are extra[out.last ...]
     int* extra;
     int* extraCount;         // zeroed by the host
     int extraCap;
+    // device-driven mode
+    Leftover* leftover;
+    int* leftoverCount;
+    const int* readList;     // or nullptr: pair = firstPair + slot
+    int firstPair;
+    const int* qlen;
+    int kBound;
+};
+// Device-side assembly of editDistance / endLocations of a slice of reads decided on the device (the -1 rule of
+// ref cpp:670, 681-693 included): fin_count_item -> exclusive scan of cnt32 -> fin_fill_item.
+struct FinParams {
+    const Rec* recs;         // [numReads] by slot
+    const int* extra;
+    const int* readList;     // or nullptr: pair = firstPair + slot
+    int firstPair;
+    int numReads;
+    const int* qlen;
+    int kBound;
+    int* ed;                 // [pair]: distance, -1 (none within the bound) or -2 (pending: host-driven stages)
+    int* endCount;           // [pair]
+    long long* endStart;     // [pair] into the batch's end-location pool
+    int* cnt32;              // [numReads + 1] counts, then their exclusive prefix sums (last = total)
+    int* pool;               // the slice's region of the end-location pool
+    long long poolBase;      // offset of that region in the batch pool
+    int poolCap;
+    int* header;             // [4]: total end locations, reads pending, pool overflow flag, windows planned
+    const int* winCount;     // copied into header[3]
 };
 
 // Presence / alphabet kernels.
@@ -302,9 +358,20 @@ struct MaskParams {
     int unionSet;            // set that additionally receives every byte seen (or -1)
 };
 struct EncodeParams {
-    uint8_t* data;           // encoded in place
+    uint8_t* data;           // encoded in place (any alignment)
     uint64_t numBytes;
     const uint8_t* map;      // [256] byte -> code
+};
+// alphabetLength of a run of queries that all face ONE target (streamed batches): distinct byte values of the
+// query united with the target's presence set (ref transformSequences cpp:1437-1461), straight from the raw bytes.
+struct QAlphaParams {
+    const uint8_t* raw;      // raw bytes as uploaded
+    const uint64_t* qoff;    // [pair]
+    const int* qlen;         // [pair]
+    int firstPair;
+    int numQueries;
+    const uint32_t* tmask;   // [8] presence set of the target
+    int* alphaLen;           // [pair]
 };
 
 }  // namespace eb

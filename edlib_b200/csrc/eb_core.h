@@ -512,29 +512,29 @@ EB_HD void k1w_thread(const K1WParams& p, int slot, Acc& acc) {
 // =============================================================================================
 // Seed stage of the candidate filter (HW, plain symbol equality).  If a read aligns somewhere with
 // d <= t edits, then of any t+1 disjoint pieces of the read at least one is untouched by the edits
-// and occurs verbatim in the target: piece read[a, a+L) == target[p, p+L) puts the end column of that
+// and occurs verbatim in the target: piece read[a, a+Ls) == target[p, p+Ls) puts the end column of that
 // alignment within d of E = p + (m - a) - 1.  So the columns [E-t, E+t] of all exact piece occurrences
 // cover every end column with a distance <= t; the whole read is swept over windows around them
 // (k1w_thread) and the minimum is final when it is <= t.
 // =============================================================================================
-EB_HD uint32_t seed_bucket(const uint8_t* s, int L, int bits) {
-    uint64_t h = 0xcbf29ce484222325ull;
-    for (int i = 0; i < L; ++i) {
-        h ^= s[i];
-        h *= 0x100000001b3ull;
-    }
-    h ^= h >> 29;
-    h *= 0xbf58476d1ce4e5b9ull;
-    h ^= h >> 32;
-    return (uint32_t)h & ((1u << bits) - 1u);
+
+// Radix key of the Lidx codes at s (eb_common.h: SeedIndexParams); only `avail` codes exist, the rest count as 0.
+EB_HD uint32_t seed_key(const uint8_t* s, int avail, int Lidx, uint32_t sigma) {
+    uint32_t key = 0;
+    for (int x = 0; x < Lidx; ++x) key = key * sigma + (x < avail ? (uint32_t)s[x] : 0u);
+    return key;
 }
-EB_HD void seed_count_item(const SeedIndexParams& p, int i) { atomic_add_int(p.bucketStart + seed_bucket(p.tcodes + i, p.L, p.bits), 1); }
+EB_HD void seed_count_item(const SeedIndexParams& p, int i) {
+    atomic_add_int(p.bucketStart + seed_key(p.tcodes + i, p.n - i, p.Lidx, (uint32_t)p.sigma), 1);
+}
 EB_HD void seed_fill_item(const SeedIndexParams& p, int i) {
-    const uint32_t b = seed_bucket(p.tcodes + i, p.L, p.bits);
+    const uint32_t b = seed_key(p.tcodes + i, p.n - i, p.Lidx, (uint32_t)p.sigma);
     p.positions[p.bucketStart[b] + atomic_add_int(p.cursor + b, 1)] = i;
 }
 
 // Windows of one read from its sorted candidate end columns E[0..c): emit == false only counts them.
+// Windows start at multiples of 16 columns (vector loads of the target in k1w_thread; a longer lead-in is
+// still exact).
 EB_HD int seed_windows(const SeedPlanParams& p, const int* E, int c, int m, int t, int pair, int base, bool emit) {
     long long prevHi = -1;
     int nW = 0;
@@ -553,6 +553,7 @@ EB_HD int seed_windows(const SeedPlanParams& p, const int* E, int c, int m, int 
         // of a tracked column is exact (larger ones may come out larger still, which changes nothing)
         long long ws = lo - (long long)(m + t);
         if (ws < 0) ws = 0;
+        ws &= ~15LL;
         if (emit) {
             const int w = base + nW;
             p.winPair[w] = pair;
@@ -566,89 +567,110 @@ EB_HD int seed_windows(const SeedPlanParams& p, const int* E, int c, int m, int 
     return nW;
 }
 
-template <int CAP>
-EB_HD void seed_plan_read(const SeedPlanParams& p, int slot) {
-    const int pair = p.readList[slot];
-    const int m = p.qlen[pair], t = p.thr[slot];
+// Host spelling of the cooperative group that plans one read (one member); the device kernel passes a warp.
+struct CoopSerial {
+    static EB_HD int lane() { return 0; }
+    static EB_HD int width() { return 1; }
+    static EB_HD void sync() {}
+    static EB_HD bool any(bool v) { return v; }
+    static EB_HD int add_shared(int* p, int v) {
+        const int old = *p;
+        *p = old + v;
+        return old;
+    }
+};
+
+// One read, planned by a cooperative group C (a warp on the device: its members take the seeds of the read;
+// a single member on the host).  E[CAP] candidate end columns, ctl[2] = {candidates, saturated} and qs[256]
+// (the read's codes) are scratch shared by the group (shared memory on the device).
+template <int CAP, class C>
+EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl, uint8_t* qs) {
+    const int lane = C::lane(), W = C::width();
+    const int pair = p.readList ? p.readList[slot] : p.firstPair + slot;
+    const int m = p.qlen[pair];
+    const int t = p.thr ? p.thr[slot] : seed_threshold(m, p.kBound, p.Ls, p.seedK, -1);
     const uint8_t* q = p.qcodes + p.qoff[pair];
     SeedPlan pl;
     pl.first = pl.count = 0;
     pl.state = SEED_NONE;
-    if (t < 0) {  // the host left this read out of the stage
+    pl.thr = t;
+    if (t < 0 || m > 256) {  // left out of the stage (the host, or the threshold rule)
         pl.state = SEED_SATURATED;
-        p.plan[slot] = pl;
+        pl.thr = -1;
+        if (lane == 0) p.plan[slot] = pl;
         return;
     }
-    int E[CAP];
-    int c = 0;
-    const int stride = m / (t + 1);  // >= L: the t+1 pieces are disjoint
-    bool saturated = false;
-    // Pieces go eight at a time: first all their hashes, then all their bucket bounds (independent loads in
-    // flight together), then the occurrences -- the lookups of one read are otherwise one long latency chain.
-    for (int j0 = 0; j0 <= t && !saturated; j0 += 8) {
-        const int group = t + 1 - j0 < 8 ? t + 1 - j0 : 8;
-        uint32_t bucket[8];
-        int s0[8], s1[8];
-        EB_UNROLL
-        for (int u = 0; u < 8; ++u)
-            if (u < group) bucket[u] = seed_bucket(q + (j0 + u) * stride, p.L, p.bits);
-        EB_UNROLL
-        for (int u = 0; u < 8; ++u)
-            if (u < group) {
-                s0[u] = p.bucketStart[bucket[u]];
-                s1[u] = p.bucketStart[bucket[u] + 1];
-            }
-        EB_UNROLL
-        for (int u = 0; u < 8; ++u) {
-            if (u >= group || saturated) continue;
-            const int a = (j0 + u) * stride;
-            if (s1[u] - s0[u] > p.maxBucket) {
-                saturated = true;
-                continue;
-            }
-            for (int i = s0[u]; i < s1[u]; ++i) {
-                const int pos = p.positions[i];
-                bool same = true;
-                for (int x = 0; x < p.L; ++x)
-                    if (p.tcodes[pos + x] != q[a + x]) {
-                        same = false;
-                        break;
-                    }
-                if (!same) continue;  // bucket collision
-                if (c == CAP) {
-                    saturated = true;
-                    break;
+    for (int i = lane; i < m; i += W) qs[i] = q[i];
+    if (lane == 0) {
+        ctl[0] = 0;
+        ctl[1] = 0;
+    }
+    C::sync();
+    const int stride = m / (t + 1);  // >= Ls: the t+1 pieces are disjoint
+    const int Lk = p.Ls < p.Lidx ? p.Ls : p.Lidx;  // symbols of the seed that go into the key
+    uint32_t span = 1;                             // keys sharing that prefix
+    for (int x = Lk; x < p.Lidx; ++x) span *= (uint32_t)p.sigma;
+    for (int j0 = 0; j0 <= t; j0 += W) {
+        const int j = j0 + lane;
+        const int a = j * stride;
+        int i0 = 0, i1 = 0;
+        if (j <= t) {
+            // a code outside the target's alphabet (streamed batches give the reads' foreign bytes one) occurs nowhere
+            bool known = true;
+            for (int x = 0; x < p.Ls; ++x) known = known && qs[a + x] < p.sigma;
+            if (known) {
+                const uint32_t key = seed_key(qs + a, Lk, Lk, (uint32_t)p.sigma) * span;
+                i0 = p.bucketStart[key];
+                i1 = p.bucketStart[key + span];
+                if (i1 - i0 > p.maxBucket) {  // repeat: the read is passed on unseen
+                    ctl[1] = 1;
+                    i1 = i0;
                 }
-                E[c++] = pos + (m - a) - 1;
             }
         }
+        for (int i = i0; C::any(i < i1); ++i) {
+            if (i >= i1) continue;
+            const int pos = p.positions[i];
+            bool same = pos + p.Ls <= p.n;  // keys near the end of the target were padded with code 0
+            for (int x = Lk; same && x < p.Ls; ++x) same = p.tcodes[pos + x] == qs[a + x];
+            if (!same) continue;
+            const int at = C::add_shared(&ctl[0], 1);
+            if (at < CAP) E[at] = pos + (m - a) - 1;
+        }
     }
-    if (saturated) {
+    C::sync();
+    if (lane != 0) return;
+    const int c = ctl[0];
+    if (ctl[1] || c > CAP) {
         pl.state = SEED_SATURATED;
         p.plan[slot] = pl;
         return;
     }
     // Shell sort (Ciura gaps; plain insertion sort when c is small, the usual case)
-    const int gaps[7] = {301, 132, 57, 23, 10, 4, 1};
-    for (int gi = c > 32 ? 0 : 6; gi < 7; ++gi) {
+    const int gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
+    for (int gi = c > 32 ? 0 : 7; gi < 8; ++gi) {
         const int gap = gaps[gi];
         for (int i = gap; i < c; ++i) {
             const int v = E[i];
-            int j = i - gap;
-            while (j >= 0 && E[j] > v) {
-                E[j + gap] = E[j];
-                j -= gap;
+            int k = i - gap;
+            while (k >= 0 && E[k] > v) {
+                E[k + gap] = E[k];
+                k -= gap;
             }
-            E[j + gap] = v;
+            E[k + gap] = v;
         }
     }
     const int nW = seed_windows(p, E, c, m, t, pair, 0, false);
     if (nW > 0) {
         const int base = atomic_add_int(p.winCount, nW);
-        if (base + nW <= p.winCap) seed_windows(p, E, c, m, t, pair, base, true);
-        pl.first = base;
-        pl.count = nW;
-        pl.state = SEED_WINDOWS;
+        if (base + nW <= p.winCap) {
+            seed_windows(p, E, c, m, t, pair, base, true);
+            pl.first = base;
+            pl.count = nW;
+            pl.state = SEED_WINDOWS;
+        } else {
+            pl.state = SEED_SATURATED;  // the job arrays are full (host-driven stages repeat with the exact size)
+        }
     }
     p.plan[slot] = pl;
 }
@@ -662,7 +684,7 @@ EB_HD void win_reduce_read(const WinReduceParams& p, int slot) {
     out.rsv = pl.state;
     for (int q = 0; q < KPOS; ++q) out.pos[q] = 0;
     if (pl.state == SEED_WINDOWS) {
-        const int t = p.thr[slot];
+        const int t = pl.thr;
         int b = 0x7fffffff;
         for (int w = 0; w < pl.count; ++w) {
             const WinRec& r = p.winRecs[pl.first + w];
@@ -702,7 +724,76 @@ EB_HD void win_reduce_read(const WinReduceParams& p, int slot) {
             }
         }
     }
+    if (p.leftover) {  // device-driven first level: the outcome logic of Pass::seed_stage, per read
+        const int pair = p.readList ? p.readList[slot] : p.firstPair + slot;
+        const int m = p.qlen[pair];
+        const int bound = (p.kBound < 0 || p.kBound > m) ? m : p.kBound;
+        int excl = -3;  // -3: decided
+        if (out.rsv == SEED_WINDOWS) {
+            out.rsv = REC_DONE;
+        } else if (out.rsv == SEED_NONE && pl.thr >= 0 && pl.thr == bound) {
+            out.rsv = REC_DONE;  // nothing within the caller's bound: final (best stays at the sentinel)
+        } else {
+            excl = out.rsv == SEED_LONG_LIST ? -2 : (out.rsv == SEED_NONE ? pl.thr : -1);
+            out.rsv = REC_PENDING;
+        }
+        if (excl != -3) {
+            const int at = atomic_add_int(p.leftoverCount, 1);
+            p.leftover[at].pair = pair;
+            p.leftover[at].excl = excl;
+        }
+    }
     p.out[slot] = out;
+}
+
+// Number of end locations a finished sweep outcome yields (the -1 rule of ref cpp:670, 681-693: the padded
+// bottom cell of column W-1 shows up as end location -1 when editDistance == m), or -1 when there is no result.
+EB_HD int hw_accepted_count(int best, int cnt, int m, int kBound, bool* minusOne) {
+    *minusOne = false;
+    if (best < 0 || best == 0x7fffffff || cnt <= 0) return -1;
+    if (kBound >= 0 && best > kBound) return -1;
+    if (best > m) return -1;
+    const int W64 = (m + 63) / 64 * 64 - m;
+    *minusOne = (best == m && W64 > 0);
+    return cnt + (*minusOne ? 1 : 0);
+}
+EB_HD void fin_count_item(const FinParams& p, int slot) {
+    const Rec r = p.recs[slot];
+    const int pair = p.readList ? p.readList[slot] : p.firstPair + slot;
+    int count = 0, ed = -1;
+    if (r.rsv == REC_PENDING) {
+        ed = -2;
+        atomic_add_int(p.header + 1, 1);
+    } else {
+        bool minusOne;
+        const int a = hw_accepted_count(r.best, r.cnt, p.qlen[pair], p.kBound, &minusOne);
+        if (a >= 0) {
+            ed = r.best;
+            count = a;
+        }
+    }
+    p.ed[pair] = ed;
+    p.endCount[pair] = count;
+    p.cnt32[slot] = count;
+}
+EB_HD void fin_fill_item(const FinParams& p, int slot) {
+    const int pair = p.readList ? p.readList[slot] : p.firstPair + slot;
+    const int start = p.cnt32[slot];
+    const int count = p.cnt32[slot + 1] - start;
+    p.endStart[pair] = p.poolBase + start;
+    if (slot == 0) {
+        p.header[0] = p.cnt32[p.numReads];
+        p.header[3] = p.winCount ? *p.winCount : 0;
+    }
+    if (count <= 0) return;
+    if (start + count > p.poolCap) {
+        p.header[2] = 1;
+        return;
+    }
+    const Rec r = p.recs[slot];
+    int at = start;
+    if (count > r.cnt) p.pool[at++] = -1;
+    for (int q = 0; q < r.cnt; ++q) p.pool[at++] = q < KPOS ? r.pos[q] : p.extra[r.last + q - KPOS];
 }
 
 // =============================================================================================
@@ -1153,6 +1244,25 @@ EB_HD void mask_item(const MaskParams& p, int itemIdx, int first, int stride) {
     uint32_t local[8];
     const MaskItem it = mask_item_scan(p, itemIdx, first, stride, local);
     for (int k = 0; k < 8; ++k) mask_item_commit(p, it.dst, k, local[k]);
+}
+
+// Presence set of query `q` of a QAlphaParams run: the bytes at first, first+stride, ... into local[8].
+EB_HD void qalpha_scan(const QAlphaParams& p, int q, int first, int stride, uint32_t (&local)[8]) {
+    const int pair = p.firstPair + q;
+    const uint8_t* s = p.raw + p.qoff[pair];
+    const int len = p.qlen[pair];
+    for (int k = 0; k < 8; ++k) local[k] = 0;
+    for (int i = first; i < len; i += stride) {
+        const uint32_t b = s[i];
+        local[b >> 5] |= 1u << (b & 31);
+    }
+}
+EB_HD int popcount32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
 }
 
 // alphabetLength of one pair: distinct byte values in query and target together

@@ -10,6 +10,10 @@
 //             alignment path            (stored-matrix NW sweep + traceback kernel inside the
 //                                        reference's 1 MiB rule, ref cpp:276-289, 1161-1213)
 //   materialize : malloc'd arrays per result (ownership as ref edlib.h:177,186,205)
+//
+// edlibAlignBatch() on the usual large batch (reads, HW, one shared target) does not run these phases one
+// after the other: Engine::align_streamed cuts the reads into slices and overlaps packing + upload of slice
+// i+1 with the kernels of slice i and with the result structs of slice i-1 (second half of this file).
 #include "eb_engine_internal.h"
 
 namespace eb {
@@ -34,8 +38,23 @@ EngineTunables::EngineTunables() {
     filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
     filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
     filterMinTarget = env_int("EDLIB_B200_FILTER_MIN_TARGET", filterMinTarget);
+    deviceStage = env_int("EDLIB_B200_DEVICE_STAGE", deviceStage);
+    devSliceReads = std::max(64, env_int("EDLIB_B200_SLICE_READS", devSliceReads));
+    streamMinPairs = env_int("EDLIB_B200_STREAM_MIN_PAIRS", streamMinPairs);
     const int sliceMb = env_int("EDLIB_B200_SLICE_MB", 0);
     if (sliceMb > 0) sliceBytes = (size_t)sliceMb << 20;
+}
+
+// dense codes in ascending byte order for the bytes of `present`; every other byte maps to `other`
+static int code_map(const uint32_t (&present)[8], uint8_t (&map)[256], int other) {
+    int ncodes = 0;
+    for (int b = 0; b < 256; ++b) ncodes += (present[b >> 5] >> (b & 31)) & 1u;
+    int next = 0;
+    for (int b = 0; b < 256; ++b) {
+        if (present[b >> 5] >> (b & 31) & 1u) map[b] = (uint8_t)next++;
+        else map[b] = (uint8_t)(other < 0 ? 0 : std::min(other, 255));
+    }
+    return ncodes;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -48,12 +67,21 @@ Prepared* Engine::prepare(const BatchInput& in) {
     Prepared* p = spare_ ? spare_ : new Prepared();
     spare_ = nullptr;
     try {
+        p->bind(be);
         p->tg.clear();
         p->hasEq = false;
         p->ncodes = 0;
         p->computed = false;
         p->classified = false;
-        p->be = be;
+        // nothing of an earlier batch may survive in the result arrays (staged API: results before compute)
+        p->ed.clear();
+        p->endStart.clear();
+        p->endCount.clear();
+        p->endPool.clear();
+        p->startPool.clear();
+        p->alnStart.clear();
+        p->alnLen.clear();
+        p->alnPool.clear();
         p->N = in.numPairs;
         p->cfg = in.config;
         p->mode = (in.config.mode == EDLIB_MODE_SHW) ? MODE_SHW : (in.config.mode == EDLIB_MODE_HW) ? MODE_HW : MODE_NW;
@@ -63,15 +91,17 @@ Prepared* Engine::prepare(const BatchInput& in) {
         p->tidx.resize(N);
         p->qoff.resize(N);
         {
-            std::vector<int> bad(1, 0);
+            std::atomic<int> bad(0);
             parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+                bool b = false;
                 for (size_t i = lo; i < hi; ++i) {
                     p->qlen[i] = in.queryLengths[i];
                     p->tlen[i] = in.targetLengths[i];
-                    if (p->qlen[i] < 0 || p->tlen[i] < 0) bad[0] = 1;
+                    if (p->qlen[i] < 0 || p->tlen[i] < 0) b = true;
                 }
+                if (b) bad.store(1, std::memory_order_relaxed);
             });
-            if (bad[0]) throw std::runtime_error("negative sequence length");
+            if (bad.load()) throw std::runtime_error("negative sequence length");
         }
 
         // identical (pointer, length) targets are uploaded and encoded once
@@ -88,13 +118,15 @@ Prepared* Engine::prepare(const BatchInput& in) {
         int lastIdx = -1;
         bool oneTarget = N > 0;  // the usual batch shape (reads over one shared target), checked in parallel
         if (N >= 131072) {
-            std::vector<int> differs(1, 0);
+            std::atomic<int> differs(0);
             const Key first{in.targets[0], in.targetLengths[0]};
             parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+                bool d = false;
                 for (size_t i = lo; i < hi; ++i)
-                    if (in.targets[i] != first.ptr || in.targetLengths[i] != first.len) differs[0] = 1;
+                    if (in.targets[i] != first.ptr || in.targetLengths[i] != first.len) d = true;
+                if (d) differs.store(1, std::memory_order_relaxed);
             });
-            oneTarget = !differs[0];
+            oneTarget = !differs.load();
         } else {
             oneTarget = false;
         }
@@ -134,7 +166,8 @@ Prepared* Engine::prepare(const BatchInput& in) {
             total += round_up((size_t)p->tg[t].len, 16) + 16;
         }
         total += 16;
-        uint8_t* stage = static_cast<uint8_t*>(be->alloc_host(total));
+        HostBuf<uint8_t> stageBuf(be, total);  // released on every path out of this function
+        uint8_t* stage = stageBuf.p;
         p->dSeq.alloc(be, total);
         // the small per-pair arrays go first: they would otherwise queue behind the sequences
         p->dQoff.alloc(be, N);
@@ -191,19 +224,12 @@ Prepared* Engine::prepare(const BatchInput& in) {
                         if (cut[c] < cut[c - 1]) cut[c] = cut[c - 1];
                     }
                 }
-                std::vector<std::string> errs(nthr);
-                HostPool::get().run((size_t)nthr, [&](size_t t) {
-                    try {
-                        for (int it = cut[t]; it < cut[t + 1]; ++it) copy_item(it);
-                        const size_t a = t == 0 ? 0 : item_off(cut[t]), b = item_off(cut[t + 1]);
-                        be->bind_thread();  // a pool worker: select the backend's device before the copy
-                        if (b > a) be->h2d(p->dSeq.p + a, stage + a, b - a);
-                    } catch (const std::exception& e) {
-                        errs[t] = e.what();
-                    }
+                HostPool::get().run((size_t)nthr, [&](size_t t) {  // exceptions of a task are rethrown by run()
+                    for (int it = cut[t]; it < cut[t + 1]; ++it) copy_item(it);
+                    const size_t a = t == 0 ? 0 : item_off(cut[t]), b = item_off(cut[t + 1]);
+                    be->bind_thread();  // a pool worker: select the backend's device before the copy
+                    if (b > a) be->h2d(p->dSeq.p + a, stage + a, b - a);
                 });
-                for (auto& e : errs)
-                    if (!e.empty()) throw std::runtime_error(e);
             } else {
                 for (int it = 0; it < N + T; ++it) copy_item(it);
                 p->dSeq.upload(stage, total);
@@ -258,14 +284,7 @@ Prepared* Engine::prepare(const BatchInput& in) {
 
         // dense codes in ascending byte order; absent bytes (padding) map to code 0
         uint8_t map[256];
-        memset(map, 0, sizeof(map));
-        int byteOfCode[256];
-        p->ncodes = 0;
-        for (int b = 0; b < 256; ++b)
-            if (uni[b >> 5] >> (b & 31) & 1u) {
-                byteOfCode[p->ncodes] = b;
-                map[b] = (uint8_t)p->ncodes++;
-            }
+        p->ncodes = code_map(uni, map, -1);
         if (p->ncodes == 0) p->ncodes = 1;
         DevBuf<uint8_t> dMap(be, 256);
         dMap.upload(map, 256);
@@ -293,20 +312,18 @@ Prepared* Engine::prepare(const BatchInput& in) {
                 p->hasEq = true;
             }
         }
-        (void)byteOfCode;
         be->sync();
-        be->free_host(stage);
         trace.mark("prepare: upload+alphabet");
     } catch (...) {
+        try {
+            be->sync_all();  // nothing may still be reading the staging block when it goes back to the cache
+        } catch (...) {
+        }
         delete p;
         throw;
     }
     return p;
 }
-
-// ---------------------------------------------------------------------------------------------
-// W runner: executes a list of tasks in memory-bounded slices
-// ---------------------------------------------------------------------------------------------
 
 // Groups the pairs by (target, word class): a pure function of the lengths, the distinct targets and the
 // config, so prepare() runs it on the host workers while the sequences travel to the device; the lists stay
@@ -319,6 +336,7 @@ void Engine::classify(Prepared* p) {
     std::map<std::pair<int, int>, std::vector<int>>& groups = p->groups;  // (target, nw32) -> pairs, ascending
     std::vector<int>& wPairs = p->wPairsBase;
     wPairs.clear();
+    p->otherPairs.clear();
     for (auto& kv : groups) kv.second.clear();
     {
         // contiguous ranges of pairs are classified on a few host threads and concatenated in order
@@ -328,6 +346,7 @@ void Engine::classify(Prepared* p) {
         for (auto& P : parts) {
             for (auto& kv : P.groups) kv.second.clear();
             P.wPairs.clear();
+            P.other.clear();
         }
         auto classify = [&](size_t t) {
             Prepared::Part& P = parts[t];
@@ -337,8 +356,10 @@ void Engine::classify(Prepared* p) {
             for (int i = lo; i < hi; ++i) {
                 const int m = p->qlen[i], n = p->tlen[i];
                 p->special[i] = (m == 0 || n == 0) ? 1 : 0;
-                if (p->special[i]) continue;
-                if (mode == MODE_NW && k >= 0 && k < abs(n - m)) continue;  // ref cpp:744
+                if (p->special[i] || (mode == MODE_NW && k >= 0 && k < abs(n - m))) {  // ref cpp:166-184, 744
+                    P.other.push_back(i);
+                    continue;
+                }
                 if (m <= 256) {
                     const std::pair<int, int> key(p->tidx[i], ceil_div(m, 32));
                     if (key != lastKey) {  // neighbours usually share their group
@@ -360,6 +381,7 @@ void Engine::classify(Prepared* p) {
                 dst.insert(dst.end(), kv.second.begin(), kv.second.end());
             }
             wPairs.insert(wPairs.end(), P.wPairs.begin(), P.wPairs.end());
+            p->otherPairs.insert(p->otherPairs.end(), P.other.begin(), P.other.end());
         }
         // drop the keys this batch does not use (bounded memory across differently shaped batches)
         for (auto it = groups.begin(); it != groups.end();) it = it->second.empty() ? groups.erase(it) : std::next(it);
@@ -367,12 +389,9 @@ void Engine::classify(Prepared* p) {
     p->classified = true;
 }
 
-void Engine::compute(Prepared* p) {
-    Backend* be = be_;
-    be->reset_timing();
+static void reset_results(Prepared* p) {
     const int N = p->N;
-    const int mode = p->mode;
-    // ed / endStart / endCount are written for every pair by collect_ends, special by the classification
+    // ed / endStart / endCount are written for every pair by the distance pass, special by the classification
     p->ed.resize(N);
     p->endStart.resize(N);
     p->endCount.resize(N);
@@ -386,6 +405,15 @@ void Engine::compute(Prepared* p) {
         p->alnLen.clear();
     }
     p->alnPool.clear();
+}
+
+void Engine::compute(Prepared* p) {
+    Backend* be = be_;
+    p->computed = false;
+    be->reset_timing();
+    const int N = p->N;
+    const int mode = p->mode;
+    reset_results(p);
     stats.k1Cells = stats.wCells = 0;
     stats.filterDecided = stats.filterFallback = stats.filterWindows = 0;
 
@@ -398,7 +426,15 @@ void Engine::compute(Prepared* p) {
     std::map<std::pair<int, int>, std::vector<int>>& groups = p->groups;
     wPairs = p->wPairsBase;
 
-    // ---- K1 groups ----------------------------------------------------------------------
+    // ---- routes of the groups of short queries: warp kernel, device-driven first seed level, host-driven --------
+    struct Route {
+        int t, nw;
+        const std::vector<int>* list;
+        bool device;
+    };
+    std::vector<Route> routes;
+    long long devReads = 0, devListed = 0;
+    int devSlices = 0;
     for (auto& kv : groups) {
         const std::vector<int>& list = kv.second;
         // Small groups go to the warp kernel, except HW over a long target: there the lane kernel
@@ -416,17 +452,72 @@ void Engine::compute(Prepared* p) {
                 continue;
             }
         }
-        ps.lane_group(t, nw, list);
+        const bool dev = ps.dev_eligible(t, nw) && (int)list.size() >= tun.k1MinGroup;
+        routes.push_back(Route{t, nw, &list, dev});
+        if (dev) {
+            devReads += (long long)list.size();
+            devSlices += ceil_div((int)list.size(), tun.devSliceReads);
+            const bool consecutive = (long long)list.back() - list.front() + 1 == (long long)list.size();
+            if (!consecutive) devListed += (long long)list.size();
+        }
+    }
+    // ---- device-driven first seed level of every group that may take it: enqueued without waiting --------
+    if (devSlices > 0) {
+        ps.dev_begin(devSlices);
+        ps.dPool.alloc(be, (size_t)(4 * devReads + devReads / 4 + 1024LL * devSlices + 64));
+        ps.dLists.alloc(be, (size_t)devListed);
+        p->endPool.resize(ps.dPool.n);
+        for (Route& r : routes) {
+            if (!r.device) continue;
+            const std::vector<int>& list = *r.list;
+            if (!ps.seed_index(r.t) || ps.seedIdx->Ls[0] <= 0) {  // target too short for seeds
+                r.device = false;
+                continue;
+            }
+            const bool consecutive = (long long)list.back() - list.front() + 1 == (long long)list.size();
+            std::atomic<long long> rows(0);
+            parallel_ranges(list.size(), 65536, [&](size_t lo, size_t hi) {
+                long long s = 0;
+                for (size_t i = lo; i < hi; ++i) s += p->qlen[list[i]];
+                rows.fetch_add(s, std::memory_order_relaxed);
+            });
+            stats.k1Cells += rows.load() * (long long)p->tg[r.t].len;
+            for (int first = 0; first < (int)list.size(); first += tun.devSliceReads)
+                ps.dev_enqueue_slice(r.t, r.nw, consecutive ? list.front() : -1, list.data(), first,
+                                     std::min(tun.devSliceReads, (int)list.size() - first));
+        }
+        p->endPool.resize((size_t)ps.poolReserved);  // what the slices were actually handed
+        trace.mark("compute: device stage enqueued");
+    } else {
+        ps.host_touch_all();
+    }
+    // ---- host-driven groups ----------------------------------------------------------------
+    for (Route& r : routes) {
+        if (r.device) continue;
+        ps.lane_group(r.t, r.nw, *r.list);
+        if (ps.devMode) ps.hostPairs.insert(ps.hostPairs.end(), r.list->begin(), r.list->end());
     }
     trace.mark("compute: K1 groups done");
+    if (ps.devMode) {
+        ps.host_touch(wPairs.data(), wPairs.size());
+        ps.host_touch(p->otherPairs.data(), p->otherPairs.size());
+        ps.hostPairs.insert(ps.hostPairs.end(), wPairs.begin(), wPairs.end());
+        ps.hostPairs.insert(ps.hostPairs.end(), p->otherPairs.begin(), p->otherPairs.end());
+    }
     ps.warp_distance();
     trace.mark("compute: W distance pass");
-    ps.collect_ends();
+    if (ps.devMode) {
+        ps.dev_leftovers();
+        ps.collect_ends(&ps.hostPairs);
+    } else {
+        ps.collect_ends(nullptr);
+    }
     trace.mark("compute: end locations");
     ps.start_locations();
     ps.paths();
     trace.mark("compute: starts + paths");
-    be->sync();
+    be->sync_all();
+    be->release_marks();
     stats.kernelMs = be->kernel_ms(nullptr);
     stats.k1Ms = be->kernel_ms("k1") + be->kernel_ms("k1_prefix");
     stats.kernelReport = be->kernel_report();
@@ -437,61 +528,97 @@ void Engine::compute(Prepared* p) {
 // ---------------------------------------------------------------------------------------------
 // materialize / release / one-shot
 // ---------------------------------------------------------------------------------------------
+
+// The EdlibAlignResult of pair i (arrays malloc'd one by one: each is free()-able on its own, ref edlib.h:177,186,205).
+// Returns false when the allocator fails (the arrays of this result are released again).
+static bool materialize_one(const Prepared* p, int i, EdlibAlignResult& r) {
+    memset(&r, 0, sizeof(r));
+    r.status = EDLIB_STATUS_OK;
+    r.editDistance = -1;
+    r.alphabetLength = p->alphaLen[i];
+    const int m = p->qlen[i], n = p->tlen[i];
+    if (p->special[i]) {  // ref cpp:166-184
+        const int rawMode = (int)p->cfg.mode;
+        if (rawMode == EDLIB_MODE_NW || rawMode == EDLIB_MODE_SHW || rawMode == EDLIB_MODE_HW) {
+            r.endLocations = static_cast<int*>(malloc(sizeof(int)));
+            if (!r.endLocations) return false;
+            r.editDistance = rawMode == EDLIB_MODE_NW ? std::max(m, n) : m;
+            r.endLocations[0] = rawMode == EDLIB_MODE_NW ? n - 1 : -1;
+            r.numLocations = 1;
+        } else {
+            r.status = EDLIB_STATUS_ERROR;
+        }
+        return true;
+    }
+    if (p->ed[i] < 0) return true;
+    const int c = p->endCount[i];
+    r.endLocations = static_cast<int*>(malloc(sizeof(int) * (size_t)std::max(c, 1)));
+    if (!r.endLocations) return false;
+    memcpy(r.endLocations, p->endPool.data() + p->endStart[i], sizeof(int) * (size_t)c);
+    if (!p->startPool.empty() || p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH) {
+        r.startLocations = static_cast<int*>(malloc(sizeof(int) * (size_t)std::max(c, 1)));
+        if (!r.startLocations) {
+            free(r.endLocations);
+            r.endLocations = nullptr;
+            return false;
+        }
+        memcpy(r.startLocations, p->startPool.data() + p->endStart[i], sizeof(int) * (size_t)c);
+    }
+    if (!p->alnStart.empty() && p->alnStart[i] >= 0) {
+        r.alignment = static_cast<unsigned char*>(malloc((size_t)std::max(p->alnLen[i], 1)));
+        if (!r.alignment) {
+            free(r.endLocations);
+            free(r.startLocations);
+            r.endLocations = r.startLocations = nullptr;
+            return false;
+        }
+        r.alignmentLength = p->alnLen[i];
+        memcpy(r.alignment, p->alnPool.data() + p->alnStart[i], (size_t)p->alnLen[i]);
+    }
+    r.editDistance = p->ed[i];
+    r.numLocations = c;
+    return true;
+}
+
+static void free_result_arrays(EdlibAlignResult* results, int n) {
+    for (int i = 0; i < n; ++i) {
+        free(results[i].endLocations);
+        free(results[i].startLocations);
+        free(results[i].alignment);
+        results[i].endLocations = results[i].startLocations = nullptr;
+        results[i].alignment = nullptr;
+    }
+}
+
 void Engine::materialize(Prepared* p, EdlibAlignResult* results) {
+    if (!p->computed) throw std::runtime_error("results requested from a batch that was not (successfully) computed");
     Trace trace;
     const int N = p->N;
-    parallel_ranges((size_t)N, 65536, [=](size_t lo, size_t hi) {
-    for (int i = (int)lo; i < (int)hi; ++i) {
-        EdlibAlignResult& r = results[i];
-        memset(&r, 0, sizeof(r));
-        r.status = EDLIB_STATUS_OK;
-        r.editDistance = -1;
-        r.alphabetLength = p->alphaLen[i];
-        const int m = p->qlen[i], n = p->tlen[i];
-        if (p->special[i]) {  // ref cpp:166-184
-            const int rawMode = (int)p->cfg.mode;
-            if (rawMode == EDLIB_MODE_NW || rawMode == EDLIB_MODE_SHW || rawMode == EDLIB_MODE_HW) {
-                r.editDistance = rawMode == EDLIB_MODE_NW ? std::max(m, n) : m;
-                r.endLocations = static_cast<int*>(malloc(sizeof(int)));
-                r.endLocations[0] = rawMode == EDLIB_MODE_NW ? n - 1 : -1;
-                r.numLocations = 1;
-            } else {
-                r.status = EDLIB_STATUS_ERROR;
-            }
-            continue;
-        }
-        if (p->ed[i] < 0) continue;
-        r.editDistance = p->ed[i];
-        const int c = p->endCount[i];
-        r.numLocations = c;
-        r.endLocations = static_cast<int*>(malloc(sizeof(int) * (size_t)std::max(c, 1)));
-        memcpy(r.endLocations, p->endPool.data() + p->endStart[i], sizeof(int) * (size_t)c);
-        if (!p->startPool.empty() || p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH) {
-            r.startLocations = static_cast<int*>(malloc(sizeof(int) * (size_t)std::max(c, 1)));
-            memcpy(r.startLocations, p->startPool.data() + p->endStart[i], sizeof(int) * (size_t)c);
-        }
-        if (!p->alnStart.empty() && p->alnStart[i] >= 0) {
-            r.alignmentLength = p->alnLen[i];
-            r.alignment = static_cast<unsigned char*>(malloc((size_t)std::max(p->alnLen[i], 1)));
-            memcpy(r.alignment, p->alnPool.data() + p->alnStart[i], (size_t)p->alnLen[i]);
-        }
-    }
+    std::atomic<int> failed(0);
+    parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+        for (int i = (int)lo; i < (int)hi; ++i)
+            if (!materialize_one(p, i, results[i])) failed.store(1, std::memory_order_relaxed);
     });
+    if (failed.load()) {
+        free_result_arrays(results, N);
+        throw std::runtime_error("out of memory while building the results");
+    }
     trace.mark("materialize");
 }
 
 void Engine::release(Prepared* p) {
     if (!p) return;
-    if (spare_) {
-        delete p;
-        return;
-    }
-    // keep the object for the next batch: device buffers go back to the pool now
+    // device buffers go back to the pool now
     p->dSeq.reset();
     p->dQoff.reset();
     p->dQlen.reset();
     p->dEqtab.reset();
-    spare_ = p;
+    p->computed = false;
+    if (spare_) {
+        delete p;
+        return;
+    }
+    spare_ = p;  // keep the object (host vectors, pinned result arrays) for the next batch
 }
 
 Engine::~Engine() { delete spare_; }
@@ -499,21 +626,424 @@ Engine::~Engine() { delete spare_; }
 int Engine::align_batch(const BatchInput& in, EdlibAlignResult* results) {
     Prepared* p = nullptr;
     stats = EngineStats();
+    bool built = false;  // results[] holds malloc'd arrays
     try {
+        if (align_streamed(in, results)) return EDLIB_STATUS_OK;
         p = prepare(in);
         compute(p);
-        materialize(p, results);
+        built = true;
+        materialize(p, results);  // releases what it built when it fails
         release(p);
         return EDLIB_STATUS_OK;
     } catch (const std::exception& e) {
         lastError = e.what();
+        try {
+            be_->sync_all();
+            be_->release_marks();
+        } catch (...) {
+        }
         if (p) release(p);
+        (void)built;
         for (int i = 0; i < in.numPairs; ++i) {
             memset(&results[i], 0, sizeof(results[i]));
             results[i].status = EDLIB_STATUS_ERROR;
             results[i].editDistance = -1;
         }
         return EDLIB_STATUS_ERROR;
+    }
+}
+
+// =============================================================================================
+// Streamed one-shot path of edlibAlignBatch: many short reads, HW, ONE shared target, plain equality.
+//
+//   caller thread (orchestrator)                      pool workers
+//   ---------------------------------------------     --------------------------------------------------
+//   target: pack, upload, presence set, code map      pack slice 0 (all workers), upload on the copy stream,
+//           encode, seed index                         mark -> slice 1 -> ...
+//   per slice: wait for its upload mark; alphabet     then: result structs of the slices whose results the
+//           lengths, encode, device-driven seed        orchestrator has seen arrive (DISTANCE task)
+//           level, assembly, result copies on the
+//           results stream
+//   per slice: wait for its results, release it to the workers
+//   leftover reads through the host-driven stages; their result structs
+//
+// Codes: the dense codes of the TARGET's bytes; every other byte of a read becomes one extra code that matches
+// nothing (it selects no Peq row and no seed), which is all a byte absent from the target can do under plain
+// equality -- so no pass over the reads is needed before the first slice is encoded.
+// =============================================================================================
+namespace {
+struct StreamJob {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint64_t> uploadMark;  // per slice: mark on the copy stream (0: not yet)
+    std::vector<int> partsLeft;        // per slice: packing parts still running
+    std::vector<char> resultsReady;    // per slice: results on the host, result structs may be built
+    bool abort = false;
+    std::atomic<size_t> nextPack{0}, nextMat{0};
+    std::atomic<int> failed{0};
+    std::vector<char> matDone;         // per result-struct task: its range of results[] was written
+};
+}  // namespace
+
+bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
+    Backend* be = be_;
+    const int N = in.numPairs;
+    if (in.config.mode != EDLIB_MODE_HW || N < tun.streamMinPairs || !tun.deviceStage) return false;
+    if (in.config.additionalEqualities && in.config.additionalEqualitiesLength > 0) return false;
+    if (tun.filterSeedK <= 0 || tun.filterSeedLevels <= 0) return false;
+    const char* tptr = in.targets[0];
+    const int n = in.targetLengths[0];
+    if (n < tun.filterMinTarget || n < 64) return false;
+    // one pass over the pairs: same target everywhere, query lengths of at most two neighbouring word classes
+    struct Scan {
+        int minLen = 0x7fffffff, maxLen = 0;
+        long long bytes = 0;
+        bool differs = false;
+    };
+    const size_t nparts = host_parts((size_t)N, 32768);
+    std::vector<Scan> scans(nparts);
+    HostPool::get().run(nparts, [&](size_t t) {
+        Scan s;
+        for (size_t i = (size_t)N * t / nparts, hi = (size_t)N * (t + 1) / nparts; i < hi; ++i) {
+            if (in.targets[i] != tptr || in.targetLengths[i] != n) s.differs = true;
+            const int m = in.queryLengths[i];
+            s.minLen = std::min(s.minLen, m);
+            s.maxLen = std::max(s.maxLen, m);
+            s.bytes += m;
+        }
+        scans[t] = s;
+    });
+    Scan all;
+    for (const Scan& s : scans) {
+        all.differs |= s.differs;
+        all.minLen = std::min(all.minLen, s.minLen);
+        all.maxLen = std::max(all.maxLen, s.maxLen);
+        all.bytes += s.bytes;
+    }
+    if (all.differs || all.minLen < 1 || all.maxLen > 256) return false;
+    const int nw = ceil_div(all.maxLen, 32);
+    if (ceil_div(all.minLen, 32) * 2 < nw) return false;  // very uneven lengths: the grouped path sorts them by class
+    if (all.bytes + n > (1LL << 31) - (1 << 20)) return false;
+
+    Trace trace;
+    Prepared* p = spare_ ? spare_ : new Prepared();
+    spare_ = nullptr;
+    StreamJob job;
+    bool poolBusy = false;
+    std::function<void()> freeBuilt;
+    try {
+        p->bind(be);
+        p->tg.clear();
+        p->hasEq = false;
+        p->computed = false;
+        p->classified = false;
+        p->groups.clear();
+        p->wPairsBase.clear();
+        p->otherPairs.clear();
+        p->N = N;
+        p->cfg = in.config;
+        p->mode = MODE_HW;
+        p->qlen.resize(N);
+        p->tlen.resize(N);
+        p->tidx.resize(N);
+        p->qoff.resize(N);
+        p->special.resize(N);
+        p->alphaLen.resize(N);
+        reset_results(p);
+        // offsets of the packed queries: per-part byte sums from the scan, then a running sum inside every part
+        // (also into staging memory: the per-pair arrays are uploaded slice by slice with the sequences)
+        HostBuf<uint64_t> hQoff(be, (size_t)N);
+        HostBuf<int> hQlen(be, (size_t)N);
+        std::vector<long long> partOff(nparts + 1, 0);
+        for (size_t t = 0; t < nparts; ++t) partOff[t + 1] = partOff[t] + scans[t].bytes;
+        HostPool::get().run(nparts, [&](size_t t) {
+            uint64_t off = (uint64_t)partOff[t];
+            for (size_t i = (size_t)N * t / nparts, hi = (size_t)N * (t + 1) / nparts; i < hi; ++i) {
+                const int m = in.queryLengths[i];
+                p->qlen[i] = m;
+                p->tlen[i] = n;
+                p->tidx[i] = 0;
+                p->special[i] = 0;
+                p->qoff[i] = off;
+                hQoff[i] = off;
+                hQlen[i] = m;
+                off += (uint64_t)m;
+            }
+        });
+        const size_t qBytes = (size_t)all.bytes;
+        const size_t tOff = round_up(qBytes, 16);
+        const size_t total = tOff + round_up((size_t)n, 16) + 32;
+        p->tg.push_back(Target{tptr, n, (uint64_t)tOff});
+        HostBuf<uint8_t> stageBuf(be, total);
+        uint8_t* stage = stageBuf.p;
+        p->dSeq.alloc(be, total);
+        p->dQoff.alloc(be, N);
+        p->dQlen.alloc(be, N);
+        DevBuf<int> dAlpha(be, (size_t)N);
+        stats.h2dBytes += (long long)total + 12LL * N;
+        trace.mark("stream: lengths + offsets + buffers");
+
+        // slices of reads; every slice is packed by all workers together (parts), so that slice 0 is on its way first
+        const int sliceReads = std::min(tun.devSliceReads, std::max(4096, ceil_div(N, 4)));
+        const int numSlices = ceil_div(N, sliceReads);
+        const size_t W = HostPool::get().width();
+        const size_t workers = W > 1 ? W - 1 : 0;  // the caller orchestrates
+        const int partsPerSlice = (int)std::max<size_t>(1, workers);
+        job.uploadMark.assign((size_t)numSlices, 0);
+        job.partsLeft.assign((size_t)numSlices, partsPerSlice);
+        job.resultsReady.assign((size_t)numSlices, 0);
+        const bool matInJob = in.config.task == EDLIB_TASK_DISTANCE;
+        const int matPartsPerSlice = partsPerSlice;
+        const uint64_t allocated = be->mark(Backend::STREAM_COMPUTE);  // the copy stream may use the buffers after this
+        be->wait(Backend::STREAM_COPY, allocated);
+
+        auto slice_lo = [&](int s) { return (int)std::min<long long>((long long)s * sliceReads, N); };
+        auto pack_part = [&](size_t task) {
+            const int s = (int)(task / (size_t)partsPerSlice), part = (int)(task % (size_t)partsPerSlice);
+            const int lo = slice_lo(s), hi = slice_lo(s + 1);
+            const int a = lo + (int)((long long)(hi - lo) * part / partsPerSlice);
+            const int b = lo + (int)((long long)(hi - lo) * (part + 1) / partsPerSlice);
+            if (b > a) {
+                // runs of queries that are contiguous in the caller's memory are copied in one piece
+                int i = a;
+                while (i < b) {
+                    int j = i + 1;
+                    while (j < b && in.queries[j] == in.queries[j - 1] + p->qlen[j - 1]) ++j;
+                    const size_t bytes = (size_t)(p->qoff[j - 1] + (uint64_t)p->qlen[j - 1] - p->qoff[i]);
+                    memcpy(stage + p->qoff[i], in.queries[i], bytes);
+                    i = j;
+                }
+                const size_t off = (size_t)p->qoff[a];
+                const size_t bytes = (size_t)(p->qoff[b - 1] + (uint64_t)p->qlen[b - 1]) - off;
+                be->h2d_copy(p->dSeq.p + off, stage + off, bytes);
+                be->h2d_copy(p->dQoff.p + a, hQoff.p + a, (size_t)(b - a) * sizeof(uint64_t));
+                be->h2d_copy(p->dQlen.p + a, hQlen.p + a, (size_t)(b - a) * sizeof(int));
+            }
+            std::lock_guard<std::mutex> lock(job.mu);
+            if (--job.partsLeft[(size_t)s] == 0) {  // the last part of the slice: everything of it is on the copy stream
+                job.uploadMark[(size_t)s] = be->mark(Backend::STREAM_COPY);
+                job.cv.notify_all();
+            }
+        };
+        auto mat_part = [&](size_t task) {
+            const int s = (int)(task / (size_t)matPartsPerSlice), part = (int)(task % (size_t)matPartsPerSlice);
+            {
+                std::unique_lock<std::mutex> lock(job.mu);
+                job.cv.wait(lock, [&]() { return job.resultsReady[(size_t)s] || job.abort; });
+                if (job.abort) return;
+            }
+            const int lo = slice_lo(s), hi = slice_lo(s + 1);
+            const int a = lo + (int)((long long)(hi - lo) * part / matPartsPerSlice);
+            const int b = lo + (int)((long long)(hi - lo) * (part + 1) / matPartsPerSlice);
+            for (int i = a; i < b; ++i) {
+                if (p->ed[i] == -2) continue;  // pending: the host-driven stages will settle it
+                if (!materialize_one(p, i, results[i])) job.failed.store(1, std::memory_order_relaxed);
+            }
+            job.matDone[task] = 1;
+        };
+        const size_t packTasks = (size_t)numSlices * partsPerSlice;
+        const size_t matTasks = matInJob ? (size_t)numSlices * matPartsPerSlice : 0;
+        job.matDone.assign(matTasks, 0);
+        freeBuilt = [&, sliceReads, matPartsPerSlice]() {  // error path: the arrays of the result structs built so far
+            for (size_t task = 0; task < job.matDone.size(); ++task) {
+                if (!job.matDone[task]) continue;
+                const int s = (int)(task / (size_t)matPartsPerSlice), part = (int)(task % (size_t)matPartsPerSlice);
+                const int lo = (int)std::min<long long>((long long)s * sliceReads, N);
+                const int hi = (int)std::min<long long>((long long)(s + 1) * sliceReads, N);
+                const int a = lo + (int)((long long)(hi - lo) * part / matPartsPerSlice);
+                const int b = lo + (int)((long long)(hi - lo) * (part + 1) / matPartsPerSlice);
+                for (int i = a; i < b; ++i)
+                    if (p->ed[i] != -2) free_result_arrays(results + i, 1);
+            }
+        };
+        const std::function<void(size_t)> workerFn = [&](size_t) {
+            try {
+                be->bind_thread();
+                for (;;) {
+                    const size_t t = job.nextPack.fetch_add(1);
+                    if (t >= packTasks) break;
+                    pack_part(t);
+                }
+                for (;;) {
+                    const size_t t = job.nextMat.fetch_add(1);
+                    if (t >= matTasks) break;
+                    mat_part(t);
+                }
+            } catch (...) {
+                std::lock_guard<std::mutex> lock(job.mu);
+                job.abort = true;
+                job.cv.notify_all();
+                throw;
+            }
+        };
+        if (workers > 0) {
+            HostPool::get().begin(workers, workerFn);
+            poolBusy = true;
+        }
+
+        // ---- target: upload, presence set, codes, encoding, seed index (while the workers pack slice 0) ----
+        memcpy(stage + tOff, tptr, (size_t)n);
+        memset(stage + tOff + n, 0, total - tOff - (size_t)n);
+        if (tOff > qBytes) memset(stage + qBytes, 0, tOff - qBytes);
+        be->h2d(p->dSeq.p + qBytes, stage + qBytes, total - qBytes);
+        std::vector<MaskItem> items;
+        for (int s0 = 0; s0 < n; s0 += 65536) items.push_back(MaskItem{(uint64_t)tOff + (uint64_t)s0, std::min(65536, n - s0), 0});
+        DevBuf<MaskItem> dItems(be, items.size());
+        dItems.upload(items.data(), items.size());
+        DevBuf<uint32_t> dMask(be, 8);
+        be->zero(dMask.p, 8 * sizeof(uint32_t));
+        {
+            MaskParams mp;
+            memset(&mp, 0, sizeof(mp));
+            mp.raw = p->dSeq.p;
+            mp.items = dItems.p;
+            mp.numItems = (int)items.size();
+            mp.masks = dMask.p;
+            mp.unionSet = -1;
+            be->launch_mask(mp);
+        }
+        uint32_t tmask[8];
+        be->d2h(tmask, dMask.p, sizeof(tmask));
+        uint8_t map[256];
+        int ncodes = 0;
+        for (int b = 0; b < 256; ++b) ncodes += (tmask[b >> 5] >> (b & 31)) & 1u;
+        code_map(tmask, map, ncodes);  // bytes the target does not hold: the extra code `ncodes`
+        p->ncodes = std::max(1, std::min(ncodes, 255));
+        if (ncodes >= 256) {  // no spare code: every byte value occurs in the target, so no read byte is foreign
+            p->ncodes = 256;
+        }
+        DevBuf<uint8_t> dMap(be, 256);
+        dMap.upload(map, 256);
+        {
+            EncodeParams ep{p->dSeq.p + tOff, (uint64_t)round_up((size_t)n, 16), dMap.p};
+            be->launch_encode(ep);
+        }
+        stats = EngineStats();
+        stats.h2dBytes = (long long)total + 12LL * N;
+        be->reset_timing();
+        Pass ps(*this, be, p);
+        int bt = 0, rc = 0;
+        be->k1_shape(nw, p->ncodes, N, &bt, &rc);
+        if (rc <= 0 || !ps.dev_eligible(0, nw) || !ps.seed_index(0) || ps.seedIdx->Ls[0] <= 0) {
+            // cannot happen for the batches admitted above except with an exotic alphabet: back to the grouped path
+            if (poolBusy) {
+                {
+                    std::lock_guard<std::mutex> lock(job.mu);
+                    job.abort = true;
+                    job.cv.notify_all();
+                }
+                HostPool::get().end(true);
+                poolBusy = false;
+            }
+            be->sync_all();
+            be->release_marks();
+            release(p);
+            return false;
+        }
+        stats.k1Cells = all.bytes * (long long)n;
+        ps.dev_begin(numSlices);
+        ps.dPool.alloc(be, (size_t)(4LL * N + N / 4 + 1024LL * numSlices + 64));
+        p->endPool.resize(ps.dPool.n);
+        trace.mark("stream: target + index");
+
+        // ---- slices: enqueue as their uploads are issued ----
+        for (int s = 0; s < numSlices; ++s) {
+            if (workers == 0) {  // no pool: the caller packs the slice itself
+                for (int part = 0; part < partsPerSlice; ++part) pack_part((size_t)s * partsPerSlice + part);
+            }
+            uint64_t up = 0;
+            {
+                std::unique_lock<std::mutex> lock(job.mu);
+                job.cv.wait(lock, [&]() { return job.uploadMark[(size_t)s] != 0 || job.abort; });
+                if (job.abort) throw std::runtime_error("a worker failed while packing the batch");
+                up = job.uploadMark[(size_t)s];
+            }
+            be->wait(Backend::STREAM_COMPUTE, up);
+            const int lo = slice_lo(s), hi = slice_lo(s + 1);
+            QAlphaParams qa;
+            memset(&qa, 0, sizeof(qa));
+            qa.raw = p->dSeq.p;
+            qa.qoff = p->dQoff.p;
+            qa.qlen = p->dQlen.p;
+            qa.firstPair = lo;
+            qa.numQueries = hi - lo;
+            qa.tmask = dMask.p;
+            qa.alphaLen = dAlpha.p;
+            be->launch_qalpha(qa);
+            const uint64_t b0 = p->qoff[lo], b1 = p->qoff[hi - 1] + (uint64_t)p->qlen[hi - 1];
+            EncodeParams ep{p->dSeq.p + b0, b1 - b0, dMap.p};
+            be->launch_encode(ep);
+            ps.extraCopyDst = p->alphaLen.data() + lo;
+            ps.extraCopySrc = dAlpha.p + lo;
+            ps.extraCopyBytes = (size_t)(hi - lo) * sizeof(int);
+            ps.dev_enqueue_slice(0, nw, 0, nullptr, lo, hi - lo);
+            ps.extraCopyBytes = 0;
+        }
+        p->endPool.resize((size_t)ps.poolReserved);
+        trace.mark("stream: slices enqueued");
+        // ---- results of the slices as they arrive: released to the workers ----
+        for (int s = 0; s < numSlices; ++s) {
+            ps.dev_finish_slice(s);
+            std::lock_guard<std::mutex> lock(job.mu);
+            job.resultsReady[(size_t)s] = 1;
+            job.cv.notify_all();
+        }
+        if (poolBusy) {
+            poolBusy = false;
+            HostPool::get().end(true);  // the caller helps with the result structs that are left
+        } else if (matInJob) {
+            for (size_t t = 0; t < matTasks; ++t) mat_part(t);
+        }
+        if (job.failed.load()) throw std::runtime_error("out of memory while building the results");
+        trace.mark("stream: slices done");
+        // ---- the reads the first level could not decide; start locations / paths; their result structs ----
+        ps.dev_leftovers();
+        ps.collect_ends(&ps.hostPairs);
+        ps.start_locations();
+        ps.paths();
+        be->sync_all();
+        be->release_marks();
+        stats.kernelMs = be->kernel_ms(nullptr);
+        stats.k1Ms = be->kernel_ms("k1") + be->kernel_ms("k1_prefix");
+        stats.kernelReport = be->kernel_report();
+        stats.launches = be->launches();
+        p->computed = true;
+        if (matInJob) {
+            std::atomic<int> failed(0);
+            const std::vector<int>& hp = ps.hostPairs;
+            parallel_ranges(hp.size(), 4096, [&](size_t lo, size_t hi) {
+                for (size_t j = lo; j < hi; ++j)
+                    if (!materialize_one(p, hp[j], results[hp[j]])) failed.store(1, std::memory_order_relaxed);
+            });
+            if (failed.load()) throw std::runtime_error("out of memory while building the results");
+        } else {
+            materialize(p, results);
+        }
+        trace.mark("stream: leftovers + results");
+        release(p);
+        return true;
+    } catch (...) {
+        if (poolBusy) {
+            {
+                std::lock_guard<std::mutex> lock(job.mu);
+                job.abort = true;
+                job.cv.notify_all();
+            }
+            try {
+                HostPool::get().end(true);
+            } catch (...) {
+            }
+        }
+        try {
+            be->sync_all();
+            be->release_marks();
+        } catch (...) {
+        }
+        // result structs built so far own malloc'd arrays: give them back before the caller's array is reset
+        // (entries never written are untouched caller memory: only finished result-struct tasks count)
+        if (freeBuilt) freeBuilt();
+        release(p);
+        throw;
     }
 }
 

@@ -29,6 +29,17 @@ struct Backend {
     virtual void zero(void* dst, size_t bytes) = 0;
     virtual void fill(void* dst, int byteValue, size_t bytes) = 0;
     virtual void sync() = 0;
+    // Streamed batches use two more streams beside the compute stream: uploads and result downloads.  A mark is
+    // an event recorded on a stream (callable from any host thread); another stream or the host can wait for it.
+    // The defaults describe a backend where everything is synchronous.
+    enum { STREAM_COMPUTE = 0, STREAM_COPY = 1, STREAM_RESULTS = 2 };
+    virtual void h2d_copy(void* dst, const void* src, size_t bytes) { h2d(dst, src, bytes); }  // on the copy stream
+    virtual void d2h_async(int /*stream*/, void* dst, const void* src, size_t bytes) { d2h(dst, src, bytes); }
+    virtual uint64_t mark(int /*stream*/) { return 1; }
+    virtual void wait(int /*stream*/, uint64_t /*mark*/) {}
+    virtual void host_wait(uint64_t /*mark*/) {}
+    virtual void release_marks() {}
+    virtual void sync_all() { sync(); }
     // Makes the calling host thread use this backend's device (CUDA keeps the current device per thread):
     // called on entry of every API call and by pool workers before they issue copies.
     virtual void bind_thread() {}
@@ -54,6 +65,10 @@ struct Backend {
     virtual void launch_seed_fill(const SeedIndexParams& p) = 0;
     virtual void launch_seed_plan(const SeedPlanParams& p) = 0;
     virtual void launch_win_reduce(const WinReduceParams& p) = 0;
+    // device-side assembly of distances / end locations of a slice (count -> launch_scan of cnt32 -> fill)
+    virtual void launch_fin_count(const FinParams& p) = 0;
+    virtual void launch_fin_fill(const FinParams& p) = 0;
+    virtual void launch_qalpha(const QAlphaParams& p) = 0;
     // timing of the launches issued since the last reset (device time, ms) and their count
     virtual void reset_timing() = 0;
     virtual double kernel_ms(const char* nameOrNull) = 0;
@@ -82,9 +97,12 @@ struct EngineTunables {
     // 32-row prefix sweep finds the target ranges where the prefix matches within filterK1, a 64-row
     // one (for the reads the first stage cannot decide) within filterK0; only windows around those
     // ranges are swept with the whole read; reads no stage decides take the plain full sweep.
+    int deviceStage = 1;          // first seed level driven by the device (0: every stage host-driven)
+    int devSliceReads = 262144;   // reads per slice of the device-driven level
+    int streamMinPairs = 32768;   // smallest one-target HW batch that edlibAlignBatch streams (upload under compute)
     int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 32;    // seed stage: longest hash bucket looked at (longer: repeat, read passed on)
-    int filterSeedLevels = 2;     // seed stage: levels tried (seed length L, L-2, L-4; at most SEED_LEVELS)
+    int filterSeedLevels = 3;     // seed stage: levels tried (seed length L, L-2, L-4 for DNA; at most SEED_LEVELS)
     int filterSeedSlack = 4;      // seed stage: seed length L is the shortest with sigma^L >= slack * target length
     int filterK1 = 8;
     int filterK0 = 16;
@@ -129,6 +147,9 @@ public:
     void materialize(Prepared* p, EdlibAlignResult* results);  // malloc the per-pair arrays
     void release(Prepared* p);
     void classify(Prepared* p);                              // pairs -> (target, word class) groups (host only)
+    // One-shot streamed path for large HW batches of short reads over one shared target (eb_engine.cpp): returns
+    // false when the batch is not of that shape (nothing done), throws on failure.
+    bool align_streamed(const BatchInput& in, EdlibAlignResult* results);
 
     EngineTunables tun;
     EngineStats stats;

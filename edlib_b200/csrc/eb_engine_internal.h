@@ -54,17 +54,25 @@ public:
             for (size_t i = 0; i < n; ++i) fn(i);
             return;
         }
-        unsigned long long gen;
+        begin(n, fn);
+        end(true);
+    }
+    // Split form of run(): begin() hands fn(0) .. fn(n-1) to the workers and returns at once (fn must stay alive
+    // until end()); end() waits for them, the caller taking part in what is still unclaimed if `participate`.
+    // Between the two the caller must not use the pool.  With no workers the tasks run inside end().
+    void begin(size_t n, const std::function<void(size_t)>& fn) {
         {
             std::lock_guard<std::mutex> lock(mu_);
             fn_ = &fn;
             total_ = n;
             next_ = 0;
             pending_ = n;
-            gen = ++generation_;
+            activeGen_ = ++generation_;
         }
         cv_.notify_all();
-        work(gen);
+    }
+    void end(bool participate) {
+        if (participate || workers_ == 0) work(activeGen_);
         std::exception_ptr err;
         {
             std::unique_lock<std::mutex> lock(mu_);
@@ -151,7 +159,7 @@ private:
     const std::function<void(size_t)>* fn_ = nullptr;
     std::exception_ptr error_;
     size_t total_ = 0, pending_ = 0, next_ = 0;
-    unsigned long long generation_ = 0;
+    unsigned long long generation_ = 0, activeGen_ = 0;
 };
 
 // number of parts a loop over n items is cut into (every part gets >= grain items)
@@ -213,6 +221,49 @@ struct DevBuf {
     void download(T* dst, size_t count) { be->d2h(dst, p, count * sizeof(T)); }
 };
 
+// Growable array in staging memory of the backend (pinned on CUDA): result arrays the device writes with
+// asynchronous copies at full PCIe rate and the host then reads in place.  The storage stays with the batch object.
+template <class T>
+struct PinnedVec {
+    Backend* be = nullptr;
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+    PinnedVec() {}
+    PinnedVec(const PinnedVec&) = delete;
+    PinnedVec& operator=(const PinnedVec&) = delete;
+    ~PinnedVec() { release(); }
+    void bind(Backend* b) {
+        if (be != b) release();
+        be = b;
+    }
+    void release() {
+        if (p) be->free_host(p);
+        p = nullptr;
+        n = cap = 0;
+    }
+    void reserve(size_t c) {
+        if (c <= cap) return;
+        T* q = static_cast<T*>(be->alloc_host(std::max<size_t>(c, 1) * sizeof(T)));
+        if (p) {
+            if (n) memcpy(q, p, n * sizeof(T));
+            be->free_host(p);
+        }
+        p = q;
+        cap = c;
+    }
+    void resize(size_t c) {  // new elements are NOT initialised
+        if (c > cap) reserve(std::max(c, cap + cap / 2));
+        n = c;
+    }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct Target {
     const char* ptr;
     int len;
@@ -261,28 +312,38 @@ public:
     DevBuf<uint8_t> dEqtab;
     bool hasEq = false;
     int ncodes = 0;
-    std::vector<int> alphaLen;
+    PinnedVec<int> alphaLen;
 
     // classification (Engine::classify): pairs per (target, word class) for the lane kernels, the rest
     struct Part {
         std::map<std::pair<int, int>, std::vector<int>> groups;
-        std::vector<int> wPairs;
+        std::vector<int> wPairs, other;
     };
     std::map<std::pair<int, int>, std::vector<int>> groups;
     std::vector<Part> parts;        // per-thread pieces, kept for their storage
     std::vector<int> wPairsBase;    // queries above 256 rows
+    std::vector<int> otherPairs;    // pairs without a sweep: an empty sequence, or rejected up front (ref cpp:744)
     bool classified = false;
 
-    // results
-    std::vector<int> ed;            // distance or -1
+    // results (the distance pass may fill the first four straight from the device)
+    PinnedVec<int> ed;              // distance or -1
     std::vector<uint8_t> special;   // 1: an empty sequence (ref cpp:166-184)
-    std::vector<long long> endStart;
-    std::vector<int> endCount;
-    std::vector<int> endPool, startPool;
+    PinnedVec<long long> endStart;  // end locations of pair i: endPool[endStart[i] .. + endCount[i])
+    PinnedVec<int> endCount;
+    PinnedVec<int> endPool;         // not compact: regions filled by the device, then the host-assembled tail
+    std::vector<int> startPool;
     std::vector<long long> alnStart;  // -1: none
     std::vector<int> alnLen;
     std::vector<uint8_t> alnPool;
     bool computed = false;
+    void bind(Backend* b) {
+        be = b;
+        alphaLen.bind(b);
+        ed.bind(b);
+        endStart.bind(b);
+        endCount.bind(b);
+        endPool.bind(b);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -321,6 +382,31 @@ struct WRunner {
 // ---------------------------------------------------------------------------------------------
 // One compute() over a prepared batch: shared state + the phases of the reference driver
 // ---------------------------------------------------------------------------------------------
+
+// Seed index of one target (eb_common.h: SeedIndexParams) and the seed lengths of the levels it serves.
+struct SeedIndex {
+    int target = -1;
+    bool ok = false;
+    int Lidx = 0, sigma = 0, numKeys = 0, n = 0;
+    int Ls[SEED_LEVELS] = {0, 0, 0};  // seed length per level (0: level not available)
+    DevBuf<int> bucketStart, positions;
+};
+
+// One slice of a device-driven group: reads [first, first+count) of the group's list (pair = list[first+slot], or
+// firstPair + slot when the group is a run of consecutive pairs), its region of the end-location pool and its
+// header {end locations, reads pending, pool overflow, windows}.
+struct DevSlice {
+    int t = 0, nw = 0;
+    int firstPair = -1;      // >= 0: consecutive pairs (no read list on the device)
+    size_t listOff = 0;      // into the uploaded read lists otherwise
+    int count = 0;
+    long long poolBase = 0;
+    int poolCap = 0;
+    int poolFetched = 0;     // ints of the region the first (asynchronous) copy brings to the host
+    uint64_t done = 0;       // mark on the results stream: the slice's results are on the host
+    bool finished = false;
+};
+
 struct Pass {
     Engine& eng;
     Backend* be;
@@ -329,7 +415,9 @@ struct Pass {
     EngineStats& stats;
     Trace trace;
     const int N, mode, k;
-    // per-pair sweep outcome before the "-1" rule (storage reused from pass to pass: EngineScratch)
+    // per-pair sweep outcome before the "-1" rule (storage reused from pass to pass: EngineScratch).  Only the
+    // pairs the host-driven stages handle use these (host_touch): reads decided by the device-driven first seed
+    // level never appear here.
     std::vector<int>&best, &cnt;
     std::vector<long long>& posStart;  // end columns of pair i: posPool[posStart[i] .. +posLen[i])
     std::vector<int>&posLen, &posPool;
@@ -338,15 +426,48 @@ struct Pass {
     WRunner runner;
     int laneOkCache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
 
+    // ---- device-driven first seed level (eb_pass_lane.cpp) ----
+    bool devMode = false;             // some group of this pass runs it: results are assembled per slice on the device
+    std::vector<int> hostPairs;       // devMode: the pairs whose outcome lives in the host vectors above
+    std::vector<DevSlice> slices;
+    DevBuf<int> dEd, dEndCount, dHeaders, dPool, dLeftCount, dLists;
+    DevBuf<long long> dEndStart;
+    DevBuf<Leftover> dLeft;
+    PinnedVec<int> hHeaders;
+    long long poolReserved = 0;       // end-location pool handed out to slices so far
+    size_t listsUsed = 0;
+    bool wholeArrays = false;
+    long long windowsSeen = 0, readsSeen = 0;
+    // one more device->host copy to ride with the results of the next slice enqueued (streamed batches: alphabet lengths)
+    void* extraCopyDst = nullptr;
+    const void* extraCopySrc = nullptr;
+    size_t extraCopyBytes = 0;
+
     Pass(Engine& e, Backend* b, Prepared* pr)
         : eng(e), be(b), p(pr), tun(e.tun), stats(e.stats), N(pr->N), mode(pr->mode), k(pr->cfg.k),
           best(e.scratch.best), cnt(e.scratch.cnt), posStart(e.scratch.posStart), posLen(e.scratch.posLen),
           posPool(e.scratch.posPool), runner{&e, b, pr, &opsPool} {
+        hHeaders.bind(b);
         best.resize((size_t)N);
         cnt.resize((size_t)N);
         posStart.resize((size_t)N);
         posLen.resize((size_t)N);
-        parallel_ranges((size_t)N, 65536, [this](size_t lo, size_t hi) {
+        posPool.clear();
+    }
+    // Resets the host-side outcome of the pairs list[0..n) (every pair the host-driven stages are about to handle).
+    void host_touch(const int* list, size_t n) {
+        parallel_ranges(n, 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const int pair = list[i];
+                best[pair] = -1;
+                cnt[pair] = 0;
+                posStart[pair] = -1;
+                posLen[pair] = 0;
+            }
+        });
+    }
+    void host_touch_all() {
+        parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
             for (size_t i = lo; i < hi; ++i) {
                 best[i] = -1;
                 cnt[i] = 0;
@@ -354,8 +475,6 @@ struct Pass {
                 posLen[i] = 0;
             }
         });
-        posPool.clear();
-        posPool.reserve((size_t)N + 16);
     }
 
     // ---- direct lane-kernel launches (no per-job host objects): the LOC / PATH phases of large read
@@ -412,7 +531,8 @@ struct Pass {
             // one pinned staging block for everything that comes back (fast D2H, no zero-fill of vectors)
             const size_t offSt = round_up(n * sizeof(Rec), 64), offLn = offSt + round_up(n * sizeof(int), 64);
             const size_t offOps = offLn + round_up(n * sizeof(int), 64);
-            uint8_t* host = static_cast<uint8_t*>(be->alloc_host(offOps + opsBytes));
+            HostBuf<uint8_t> hostBuf(be, offOps + opsBytes);  // released on every path out, exceptions included
+            uint8_t* host = hostBuf.p;
             const Rec* recs = reinterpret_cast<const Rec*>(host);
             const int* st = reinterpret_cast<const int*>(host + offSt);
             const int* ln = reinterpret_cast<const int*>(host + offLn);
@@ -423,25 +543,18 @@ struct Pass {
             be->d2h(host + offOps, dOps.p, opsBytes);
             stats.d2hBytes += (long long)opsBytes + (long long)n * (long long)(sizeof(Rec) + 8);
             for (size_t q = 0; q < n; ++q) sink(a + q, ops + tb[q].outOff + st[q], ln[q], recs[q].best);
-            be->free_host(host);
             a = b;
         }
     }
 
-    // Hash indexes of the seeds of one target (candidate filter, seed stages), one per seed length; kept for
-    // the last target used.  Level 0: the shortest L with sigma^L >= filterSeedSlack * n (a fraction of a chance
-    // occurrence per seed: every occurrence costs a window sweep);
-    // levels 1 and 2: two and four symbols shorter (more seeds fit into a read, so a higher threshold, at the
-    // price of more chance occurrences) for the reads the previous level cannot decide.
-    struct SeedIndex {
-        int target = -1;
-        int L = 0, bits = 0;
-        DevBuf<int> bucketStart, positions;
-    } seed[SEED_LEVELS];
-    bool seed_index(int t, int level);
+    // The radix seed index of the target the seed stages last worked on (one table for every level); kept in the
+    // engine across passes when the caller registered the target (EngineScratch::keptIndex), else rebuilt per pass.
+    SeedIndex* seedIdx = nullptr;
+    SeedIndex ownIdx;
+    bool seed_index(int t);
 
     // One group of pairs that share a target and a word class (queries <= 256 rows), on its way through
-    // the distance pass.  Reads are addressed by their index `s` into `list`.
+    // the host-driven stages of the distance pass.  Reads are addressed by their index `s` into `list`.
     struct LaneGroup {
         int t, nw;               // target index, 32-bit words per query
         const std::vector<int>& list;  // the pairs of the group
@@ -471,8 +584,9 @@ struct Pass {
     // read moves on to `next`.
     void no_distance_within(LaneGroup& c, int s, int t, std::vector<int>& next);
 
-    // Seed stage: exact seeds of every read looked up in the hash index of the target; windows around
-    // the expected end columns are planned, swept and reduced on the device (eb_core.h: seed_plan_read).
+    // Seed stage, host-driven: exact seeds of every read looked up in the index of the target; windows around
+    // the expected end columns are planned, swept and reduced on the device (eb_core.h: seed_plan_read), the
+    // outcome per read is worked out on the host.
     void seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::vector<int>& next);
 
     // Prefix stage over the reads `in` (indices into `list`): a sweep of the first P rows of every read reports
@@ -486,15 +600,33 @@ struct Pass {
     void plain_sweep(LaneGroup& c);
 
     // Distance pass of one group of pairs that share target `t` and word class `nw` (queries <= 256
-    // rows): the stages of the candidate filter (HW over a long target), each on the
-    // reads the previous ones left undecided, then the plain lane-per-alignment sweep of what is left.
-    void lane_group(int t, int nw, const std::vector<int>& list);
+    // rows), host-driven: the stages of the candidate filter (HW over a long target), each on
+    // the reads the previous ones left undecided, then the plain lane-per-alignment sweep of what is left.
+    // `excl` (or nullptr) carries what the device-driven first level found out about the reads (-2: plain sweep),
+    // `firstSeedLevel` the first seed level still to try.
+    void lane_group(int t, int nw, const std::vector<int>& list, const std::vector<int>* excl = nullptr, int firstSeedLevel = 0);
+
+    // ---- device-driven first seed level ----------------------------------------------------------------
+    // May group (t, nw) take it?  (HW over a long target, plain equality, seed stage enabled, index available.)
+    bool dev_eligible(int t, int nw);
+    // Device arrays of the pass (per-pair results, leftover list, headers); `maxSlices` bounds the slices to come.
+    // (dPool / dLists and the host result arrays are sized by the caller, who knows the reads to come.)
+    void dev_begin(int maxSlices);
+    // Enqueues, without any host synchronisation, the whole first level for reads [first, first+count) of a group:
+    // seed planning, window sweeps, reduction, assembly of distances and end locations into the slice's pool region.
+    // Returns the slice index.
+    int dev_enqueue_slice(int t, int nw, int firstPair, const int* listHost, int first, int count);
+    // Waits for the results of slice si (their copies were enqueued with the slice).
+    void dev_finish_slice(int si);
+    // After the last slice: the reads the device could not decide, grouped and run through the host-driven stages.
+    void dev_leftovers();
 
     // Distance pass of everything else: one alignment per warp (or per thread with its own target).
     void warp_distance();
 
-    // editDistance and endLocations per pair from the sweep outcomes (ref cpp:219-225 and the -1 rule).
-    void collect_ends();
+    // editDistance and endLocations from the sweep outcomes (ref cpp:219-225 and the -1 rule), appended to the
+    // batch's end-location pool: of every pair (pairs == nullptr) or of the listed ones.
+    void collect_ends(const std::vector<int>* pairs);
 
     void start_locations();
 

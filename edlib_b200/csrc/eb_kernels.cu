@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -140,8 +141,16 @@ EB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 EB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     do {
-        if (++spins > (1u << 22)) __trap();  // a copy that never lands must fail the launch, not hang the device
+        // A copy that never lands must fail the launch, not hang the device -- but only after 20 s of wall
+        // time (globaltimer), so that a time-sliced / preempted context is never mistaken for a lost copy.
+        if ((++spins & 0xffffu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -248,7 +257,9 @@ template <int NW>
 __global__ void k1w_kernel(const K1WParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= p.numReads) return;
+    int numJobs = p.numReads;
+    if (p.countPtr) numJobs = min(numJobs, *p.countPtr);  // jobs planned on the device (seed_plan_kernel)
+    if (slot >= numJobs) return;
     SmemPeqAcc<NW> acc;
     acc.codeStride = (uint32_t)blockDim.x * (16u + 4u * SmemPeqAcc<NW>::NWB);
     acc.a0 = smem_u32(smem) + 16u * threadIdx.x;
@@ -299,20 +310,54 @@ __global__ void split_kernel(const SplitParams p) {
 
 __global__ void seed_count_kernel(const SeedIndexParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= p.n - p.L) seed_count_item(p, i);
+    if (i < p.numPos) seed_count_item(p, i);
 }
 __global__ void seed_fill_kernel(const SeedIndexParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= p.n - p.L) seed_fill_item(p, i);
+    if (i < p.numPos) seed_fill_item(p, i);
 }
+// One read per WARP: the lanes take the seeds of the read, so their index lookups (key -> bucket bounds ->
+// positions -> target symbols, a chain of dependent random reads) are in flight together; candidates meet in
+// shared memory, lane 0 sorts them and emits the windows.
+struct CoopWarp {
+    static EB_D int lane() { return (int)(threadIdx.x & 31u); }
+    static EB_D int width() { return 32; }
+    static EB_D void sync() { __syncwarp(); }
+    static EB_D bool any(bool v) { return __any_sync(0xffffffffu, v) != 0; }
+    static EB_D int add_shared(int* p, int v) { return atomicAdd(p, v); }
+};
+constexpr int SEED_PLAN_WARPS = 4;
 template <int CAP>
-__global__ void seed_plan_kernel(const SeedPlanParams p) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < p.numReads) seed_plan_read<CAP>(p, slot);
+__global__ void __launch_bounds__(SEED_PLAN_WARPS * 32) seed_plan_kernel(const SeedPlanParams p) {
+    __shared__ int E[SEED_PLAN_WARPS][CAP];
+    __shared__ int ctl[SEED_PLAN_WARPS][2];
+    __shared__ __align__(16) uint8_t qs[SEED_PLAN_WARPS][256];
+    const int w = threadIdx.x >> 5;
+    const int slot = blockIdx.x * SEED_PLAN_WARPS + w;
+    if (slot < p.numReads) seed_plan_read<CAP, CoopWarp>(p, slot, E[w], ctl[w], qs[w]);
 }
 __global__ void win_reduce_kernel(const WinReduceParams p) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot < p.numReads) win_reduce_read(p, slot);
+}
+__global__ void fin_count_kernel(const FinParams p) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < p.numReads) fin_count_item(p, slot);
+}
+__global__ void fin_fill_kernel(const FinParams p) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < p.numReads) fin_fill_item(p, slot);
+}
+// alphabetLength of queries facing one target: one query per warp, lanes stride over its bytes.
+__global__ void qalpha_kernel(const QAlphaParams p) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= p.numQueries) return;
+    uint32_t local[8];
+    qalpha_scan(p, q, threadIdx.x & 31, 32, local);
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) total += __popc(__reduce_or_sync(0xffffffffu, local[k]) | p.tmask[k]);
+    if ((threadIdx.x & 31) == 0) p.alphaLen[p.firstPair + q] = total;
 }
 
 // Exclusive prefix sums over ints, three launches: per-tile sums, scan of the tile sums (one CTA),
@@ -412,8 +457,12 @@ __global__ void encode_kernel(const EncodeParams p) {
     __shared__ uint8_t map[256];
     if (threadIdx.x < 256) map[threadIdx.x] = p.map[threadIdx.x];
     __syncthreads();
-    const uint64_t nvec = p.numBytes / 16;
-    uint4* v = reinterpret_cast<uint4*>(p.data);
+    // bytes before the first 16-byte boundary and after the last one go one by one (slices of a batch are
+    // encoded separately and must not touch their neighbours' bytes)
+    uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p.data) & 15)) & 15;
+    if (head > p.numBytes) head = p.numBytes;
+    const uint64_t nvec = (p.numBytes - head) / 16;
+    uint4* v = reinterpret_cast<uint4*>(p.data + head);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
         uint4 x = v[i];
         uint32_t* w = reinterpret_cast<uint32_t*>(&x);
@@ -425,8 +474,10 @@ __global__ void encode_kernel(const EncodeParams p) {
         }
         v[i] = x;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (uint64_t i = nvec * 16; i < p.numBytes; ++i) p.data[i] = map[p.data[i]];
+    if (blockIdx.x == 0) {
+        for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) p.data[i] = map[p.data[i]];
+        for (uint64_t i = head + nvec * 16 + threadIdx.x; i < p.numBytes; i += blockDim.x) p.data[i] = map[p.data[i]];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,7 +490,11 @@ __global__ void encode_kernel(const EncodeParams p) {
     } while (0)
 
 struct CudaBackend : Backend {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // compute stream: every kernel, the stream-ordered allocations
+    cudaStream_t copyStream = nullptr;  // uploads of streamed batches (overlap the kernels of earlier slices)
+    cudaStream_t resStream = nullptr;   // result downloads of streamed batches
+    std::mutex markMu;                  // marks are recorded by pool workers as well
+    std::vector<cudaEvent_t> marks, markPool;
     int sms = 0;
     int maxSmemOptin = 0;
     struct Timed {
@@ -462,6 +517,8 @@ struct CudaBackend : Backend {
         sms = prop.multiProcessorCount;
         maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
         EB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        EB_CUDA(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+        EB_CUDA(cudaStreamCreateWithFlags(&resStream, cudaStreamNonBlocking));
         cudaMemPool_t mp;
         EB_CUDA(cudaDeviceGetDefaultMemPool(&mp, dev));
         uint64_t keep = UINT64_MAX;
@@ -474,7 +531,49 @@ struct CudaBackend : Backend {
         }
         for (auto e : pool) cudaEventDestroy(e);
         for (auto& b : hostBlocks) cudaFreeHost(b.p);
+        for (auto e : marks) cudaEventDestroy(e);
+        for (auto e : markPool) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (copyStream) cudaStreamDestroy(copyStream);
+        if (resStream) cudaStreamDestroy(resStream);
+    }
+    // ---- second and third stream: ordering marks (events) between them, the compute stream and the host ----
+    cudaStream_t stream_of(int which) { return which == STREAM_COPY ? copyStream : which == STREAM_RESULTS ? resStream : stream; }
+    uint64_t mark(int which) override {
+        std::lock_guard<std::mutex> lock(markMu);
+        cudaEvent_t e;
+        if (!markPool.empty()) {
+            e = markPool.back();
+            markPool.pop_back();
+        } else {
+            EB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        EB_CUDA(cudaEventRecord(e, stream_of(which)));
+        marks.push_back(e);
+        return (uint64_t)marks.size();
+    }
+    cudaEvent_t mark_event(uint64_t token) {
+        std::lock_guard<std::mutex> lock(markMu);
+        if (token == 0 || token > marks.size()) throw std::runtime_error("internal: unknown stream mark");
+        return marks[(size_t)token - 1];
+    }
+    void wait(int which, uint64_t token) override { EB_CUDA(cudaStreamWaitEvent(stream_of(which), mark_event(token), 0)); }
+    void host_wait(uint64_t token) override { EB_CUDA(cudaEventSynchronize(mark_event(token))); }
+    void release_marks() override {
+        std::lock_guard<std::mutex> lock(markMu);
+        markPool.insert(markPool.end(), marks.begin(), marks.end());
+        marks.clear();
+    }
+    void h2d_copy(void* d, const void* s, size_t n) override {
+        if (n) EB_CUDA(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, copyStream));
+    }
+    void d2h_async(int which, void* d, const void* s, size_t n) override {
+        if (n) EB_CUDA(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream_of(which)));
+    }
+    void sync_all() override {
+        EB_CUDA(cudaStreamSynchronize(copyStream));
+        EB_CUDA(cudaStreamSynchronize(stream));
+        EB_CUDA(cudaStreamSynchronize(resStream));
     }
     // Device memory comes from the stream-ordered pool (cudaMallocAsync) with an unlimited release
     // threshold: after the first batch every alloc/free is a pool hit, ordered on the one stream all
@@ -500,7 +599,7 @@ struct CudaBackend : Backend {
             fit->used = true;
             return fit->p;
         }
-        for (size_t i = 0; i < hostBlocks.size() && hostBlocks.size() >= 8; ++i)  // bound the cache: drop an unused block
+        for (size_t i = 0; i < hostBlocks.size() && hostBlocks.size() >= 32; ++i)  // bound the cache: drop an unused block
             if (!hostBlocks[i].used) {
                 cudaFreeHost(hostBlocks[i].p);
                 hostBlocks.erase(hostBlocks.begin() + i);
@@ -575,7 +674,7 @@ struct CudaBackend : Backend {
     }
     void launch_encode(const EncodeParams& p) override {
         Scope s(this, "encode");
-        const uint64_t nvec = p.numBytes / 16;
+        const uint64_t nvec = p.numBytes / 16 + 1;
         int blocks = (int)std::min<uint64_t>((nvec + 255) / 256, (uint64_t)sms * 8);
         if (blocks < 1) blocks = 1;
         encode_kernel<<<blocks, 256, 0, stream>>>(p);
@@ -761,12 +860,12 @@ struct CudaBackend : Backend {
     }
     void launch_seed_count(const SeedIndexParams& p) override {
         Scope s(this, "seed_count");
-        seed_count_kernel<<<(p.n - p.L + 1 + 255) / 256, 256, 0, stream>>>(p);
+        seed_count_kernel<<<(p.numPos + 255) / 256, 256, 0, stream>>>(p);
         check_launch("seed_count");
     }
     void launch_seed_fill(const SeedIndexParams& p) override {
         Scope s(this, "seed_fill");
-        seed_fill_kernel<<<(p.n - p.L + 1 + 255) / 256, 256, 0, stream>>>(p);
+        seed_fill_kernel<<<(p.numPos + 255) / 256, 256, 0, stream>>>(p);
         check_launch("seed_fill");
     }
     void launch_scan(int* data, int count) override {
@@ -791,11 +890,26 @@ struct CudaBackend : Backend {
     }
     void launch_seed_plan(const SeedPlanParams& p) override {
         Scope s(this, "seed_plan");
-        const int grid = (p.numReads + 127) / 128;
-        if (p.level <= 0) seed_plan_kernel<SEED_CAND_0><<<grid, 128, 0, stream>>>(p);
-        else if (p.level == 1) seed_plan_kernel<SEED_CAND_1><<<grid, 128, 0, stream>>>(p);
-        else seed_plan_kernel<SEED_CAND_2><<<grid, 128, 0, stream>>>(p);
+        const int grid = (p.numReads + SEED_PLAN_WARPS - 1) / SEED_PLAN_WARPS;
+        if (p.level <= 0) seed_plan_kernel<SEED_CAND_0><<<grid, SEED_PLAN_WARPS * 32, 0, stream>>>(p);
+        else if (p.level == 1) seed_plan_kernel<SEED_CAND_1><<<grid, SEED_PLAN_WARPS * 32, 0, stream>>>(p);
+        else seed_plan_kernel<SEED_CAND_2><<<grid, SEED_PLAN_WARPS * 32, 0, stream>>>(p);
         check_launch("seed_plan");
+    }
+    void launch_fin_count(const FinParams& p) override {
+        Scope s(this, "fin_count");
+        fin_count_kernel<<<(p.numReads + 255) / 256, 256, 0, stream>>>(p);
+        check_launch("fin_count");
+    }
+    void launch_fin_fill(const FinParams& p) override {
+        Scope s(this, "fin_fill");
+        fin_fill_kernel<<<(p.numReads + 255) / 256, 256, 0, stream>>>(p);
+        check_launch("fin_fill");
+    }
+    void launch_qalpha(const QAlphaParams& p) override {
+        Scope s(this, "qalpha");
+        qalpha_kernel<<<(p.numQueries + 7) / 8, 256, 0, stream>>>(p);
+        check_launch("qalpha");
     }
     void launch_win_reduce(const WinReduceParams& p) override {
         Scope s(this, "win_reduce");
@@ -858,12 +972,16 @@ struct CudaBackend : Backend {
     }
 };
 
+// Device chosen through edlibB200SetDevice (-1: none, the backend takes the creating thread's current device).
+static int g_selectedDevice = -1;
+
 int select_device(int device, std::string* err) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
         if (err) *err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
         return 1;
     }
+    g_selectedDevice = device;  // under the library lock (eb_capi.cpp)
     return 0;
 }
 
@@ -873,6 +991,11 @@ Backend* create_backend(std::string* err) {
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0) {
             if (err) *err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+            return nullptr;
+        }
+        // the backend may be created by another host thread than the one that selected the device
+        if (g_selectedDevice >= 0 && (e = cudaSetDevice(g_selectedDevice)) != cudaSuccess) {
+            if (err) *err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
             return nullptr;
         }
         return new CudaBackend();

@@ -35,49 +35,88 @@ void Pass::lane_launch(const std::vector<LJob>& jobs, int nw, int laneMode, bool
     }
 }
 
-bool Pass::seed_index(int t, int level) {
-    SeedIndex& sx = seed[level];
+// Seed lengths and the radix index of target t (eb_common.h: SeedIndexParams).  Level 0 uses the shortest seeds
+// with sigma^L >= filterSeedSlack * n (a fraction of a chance occurrence per seed: every occurrence costs a window
+// sweep); the later levels shorter ones (more seeds fit into a read, so a higher threshold, at the price of more
+// chance occurrences) for the reads the previous level could not decide.  One table with keys of Lidx symbols
+// (sigma^Lidx <= 2n buckets) serves all of them.
+bool Pass::seed_index(int t) {
+    if (!seedIdx) seedIdx = &ownIdx;
+    SeedIndex& sx = *seedIdx;
     const Target& tg = p->tg[t];
     const int n = tg.len;
-    if (sx.target == t) return sx.L > 0;
+    if (sx.target == t && sx.n == n) return sx.ok;
     sx.target = t;
-    sx.L = 0;
-    const double sigma = std::max(2, p->ncodes);
-    int L = 8;
-    double v = std::pow(sigma, 8);
-    while (v < (double)tun.filterSeedSlack * (double)n && L < 32) {
+    sx.n = n;
+    sx.ok = false;
+    const int sigma = std::max(2, p->ncodes);
+    int L0 = 4;
+    double v = std::pow((double)sigma, 4);
+    while (v < (double)tun.filterSeedSlack * (double)n && L0 < 32) {
         v *= sigma;
-        ++L;
+        ++L0;
     }
-    if (level > 0) {
-        if (L - 2 * level < 8) return false;  // seeds shorter than 8 symbols select nothing
-        L -= 2 * level;
+    if (n < 4 * L0) return false;
+    const int step = (sigma * sigma <= 32) ? 2 : 1;
+    for (int level = 0; level < SEED_LEVELS; ++level) {
+        const int L = L0 - step * level;
+        // shorter than 4 symbols, or more than ~128 chance occurrences per seed: the level selects nothing
+        const bool useful = L >= 4 && (level == 0 || (double)n / std::pow((double)sigma, L) <= 128.0);
+        sx.Ls[level] = useful ? L : 0;
     }
-    if (n < 4 * L) return false;
-    int bits = 12;
-    while (bits < 27 && (1LL << bits) < 2LL * n) ++bits;
-    const size_t B = (size_t)1 << bits;
-    sx.bucketStart.alloc(be, B + 1);
-    sx.positions.alloc(be, (size_t)(n - L + 1));
-    DevBuf<int> cursor(be, B);
-    be->zero(sx.bucketStart.p, (B + 1) * sizeof(int));
-    be->zero(cursor.p, B * sizeof(int));
+    int Lidx = 1;
+    long long keys = sigma;
+    const long long maxKeys = std::min<long long>(std::max<long long>(2LL * n, 4096), 1LL << 28);
+    while (Lidx < 16 && keys * sigma <= maxKeys) {
+        keys *= sigma;
+        ++Lidx;
+    }
+    sx.Lidx = Lidx;
+    sx.sigma = sigma;
+    sx.numKeys = (int)keys;
+    sx.bucketStart.alloc(be, (size_t)keys + 1);
+    sx.positions.alloc(be, (size_t)n);
+    DevBuf<int> cursor(be, (size_t)keys);
+    be->zero(sx.bucketStart.p, ((size_t)keys + 1) * sizeof(int));
+    be->zero(cursor.p, (size_t)keys * sizeof(int));
     SeedIndexParams ip;
     memset(&ip, 0, sizeof(ip));
     ip.tcodes = p->dSeq.p + tg.off;
     ip.n = n;
-    ip.L = L;
-    ip.bits = bits;
+    ip.Lidx = Lidx;
+    ip.sigma = sigma;
+    ip.numPos = n;  // every position: keys near the end are padded with code 0 (hits are checked against n)
+    ip.numKeys = (int)keys;
     ip.bucketStart = sx.bucketStart.p;
     ip.cursor = cursor.p;
     ip.positions = sx.positions.p;
     be->launch_seed_count(ip);
-    be->launch_scan(sx.bucketStart.p, (int)B);
+    be->launch_scan(sx.bucketStart.p, (int)keys);
     be->launch_seed_fill(ip);
-    sx.L = L;
-    sx.bits = bits;
+    sx.ok = true;
     trace.mark("filter: seed index");
     return true;
+}
+
+static void fill_seed_plan(SeedPlanParams& sp, const Prepared* p, const Target& tg, const SeedIndex& sx, int level,
+                           const EngineTunables& tun) {
+    memset(&sp, 0, sizeof(sp));
+    sp.tcodes = p->dSeq.p + tg.off;
+    sp.n = tg.len;
+    sp.qcodes = p->dSeq.p;
+    sp.qoff = p->dQoff.p;
+    sp.qlen = p->dQlen.p;
+    sp.kBound = p->cfg.k;
+    sp.seedK = tun.filterSeedK;
+    sp.Ls = sx.Ls[level];
+    sp.Lidx = sx.Lidx;
+    sp.sigma = sx.sigma;
+    sp.numKeys = sx.numKeys;
+    sp.bucketStart = sx.bucketStart.p;
+    sp.positions = sx.positions.p;
+    sp.maxBucket = tun.filterSeedBucket << (1 + 3 * level);  // shorter seeds: longer index ranges are normal
+    sp.level = level;
+    sp.spread = tun.filterSpread;
 }
 
 // Chunk geometry: a HW sweep may be cut into target chunks (each re-started 2*m columns
@@ -244,22 +283,21 @@ void Pass::no_distance_within(LaneGroup& c, int s, int t, std::vector<int>& next
     }
 }
 
-// Seed stage: exact seeds of every read looked up in the hash index of the target; windows around
+// Seed stage, host-driven: exact seeds of every read looked up in the index of the target; windows around
 // the expected end columns are planned, swept and reduced on the device (eb_core.h: seed_plan_read).
 void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::vector<int>& next) {
     const std::vector<int>& list = c.list;
     const Target& tg = c.tg;
-    const int n = c.n;
     const int nw = c.nw;
     const std::vector<int>& bound = c.bound;
     std::vector<int>& excl = c.excl;
     std::vector<int>& direct = c.direct;
-    if (!seed_index(c.t, level)) {
+    if (!seed_index(c.t) || seedIdx->Ls[level] <= 0) {
         next = in;
         return;
     }
-    const SeedIndex& sx = seed[level];
-    const int L = sx.L;
+    const SeedIndex& sx = *seedIdx;
+    const int L = sx.Ls[level];
     // every read of `in` gets a slot; thr < 0 marks the ones this stage cannot help (the kernel skips them)
     const std::vector<int>& cand = in;
     const int g = (int)cand.size();
@@ -269,10 +307,8 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
     parallel_ranges((size_t)g, 65536, [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) {
             const int s = cand[i];
-            const int m = p->qlen[list[s]];
-            const int tt = std::min(std::min(bound[s], tun.filterSeedK), m / L - 1);
             rl[i] = list[s];
-            hThr[i] = (m >= 2 * L && tt > excl[s]) ? tt : -1;
+            hThr[i] = seed_threshold(p->qlen[list[s]], k, L, tun.filterSeedK, excl[s]);
         }
     });
     DevBuf<int> dList(be, g), dThr(be, g), dCount(be, 1);
@@ -291,22 +327,10 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
         wTf.alloc(be, cap);
         be->zero(dCount.p, sizeof(int));
         SeedPlanParams sp;
-        memset(&sp, 0, sizeof(sp));
-        sp.tcodes = p->dSeq.p + tg.off;
-        sp.n = n;
-        sp.qcodes = p->dSeq.p;
-        sp.qoff = p->dQoff.p;
-        sp.qlen = p->dQlen.p;
+        fill_seed_plan(sp, p, tg, sx, level, tun);
         sp.readList = dList.p;
         sp.thr = dThr.p;
         sp.numReads = g;
-        sp.L = L;
-        sp.bits = sx.bits;
-        sp.bucketStart = sx.bucketStart.p;
-        sp.positions = sx.positions.p;
-        sp.maxBucket = tun.filterSeedBucket << (4 * level);  // shorter seeds: longer buckets are normal
-        sp.level = level;
-        sp.spread = tun.filterSpread;
         sp.winPair = wPair.p;
         sp.winK = wK.p;
         sp.winStart = wStart.p;
@@ -348,8 +372,8 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
     DevBuf<int> dExtra(be, (size_t)extraCap);
     be->zero(dCount.p, sizeof(int));
     WinReduceParams rp;
+    memset(&rp, 0, sizeof(rp));
     rp.plan = dPlan.p;
-    rp.thr = dThr.p;
     rp.winRecs = dWinRecs.p;
     rp.numReads = g;
     rp.out = dOut.p;
@@ -528,7 +552,7 @@ void Pass::prefix_stage(LaneGroup& c, int P, int K0, const std::vector<int>& in,
             if (lo > hi) continue;
             prevHi = hi;
             // HW restart: alignments with <= t edits span at most m + t columns (scores <= t stay exact)
-            const long long ws = std::max<long long>(0, lo - (long long)(m + t));
+            const long long ws = std::max<long long>(0, lo - (long long)(m + t)) & ~15LL;  // windows start at multiples of 16
             vOwner.push_back(i);
             vPair.push_back(pair);
             vK.push_back(t + 1);
@@ -652,24 +676,35 @@ void Pass::plain_sweep(LaneGroup& c) {
 }
 
 // Distance pass of one group of pairs that share target `t` and word class `nw` (queries <= 256
-// rows): the stages of the candidate filter (HW over a long target), each on the
+// rows), host-driven: the stages of the candidate filter (HW over a long target), each on the
 // reads the previous ones left undecided, then the plain lane-per-alignment sweep of what is left.
-void Pass::lane_group(int t, int nw, const std::vector<int>& list) {
+void Pass::lane_group(int t, int nw, const std::vector<int>& list, const std::vector<int>* exclInit, int firstSeedLevel) {
     const Target& tg = p->tg[t];
     const int G = (int)list.size();
     LaneGroup c{t, nw, list, tg, tg.len, std::vector<int>(G), std::vector<int>(G, -1), std::vector<int>()};
+    host_touch(list.data(), list.size());
+    long long rows = 0;
     for (int s = 0; s < G; ++s) {
         const int m = p->qlen[list[s]];
         c.bound[s] = (k < 0 || k > m) ? m : k;  // distances never exceed m in HW/SHW (ref cpp:566-568)
-        stats.k1Cells += (long long)m * c.n;
+        rows += m;
     }
+    if (!exclInit) stats.k1Cells += rows * (long long)c.n;  // (device-driven groups were counted when enqueued)
     c.direct.reserve(G);
-    std::vector<int> cur(G);
-    for (int s = 0; s < G; ++s) cur[s] = s;
+    std::vector<int> cur;
+    cur.reserve(G);
+    for (int s = 0; s < G; ++s) {
+        if (exclInit && (*exclInit)[s] == -2) {
+            c.direct.push_back(s);  // long end-location list: the plain sweep collects it
+        } else {
+            if (exclInit) c.excl[s] = (*exclInit)[s];
+            cur.push_back(s);
+        }
+    }
     const bool filtered = mode == MODE_HW && c.n >= tun.filterMinTarget;
     if (filtered) {
         trace.mark("compute: classify");
-        for (int level = 0; level < tun.filterSeedLevels && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
+        for (int level = firstSeedLevel; level < tun.filterSeedLevels && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
             std::vector<int> next;
             seed_stage(c, level, cur, next);
             cur.swap(next);
@@ -688,5 +723,211 @@ void Pass::lane_group(int t, int nw, const std::vector<int>& list) {
     if (filtered) stats.filterFallback += (long long)c.direct.size();
     trace.mark("filter: collect");
     plain_sweep(c);
+}
+
+// =============================================================================================
+// Device-driven first seed level.  For the usual batch (a million reads over one genome) the first seed level
+// decides 99.8 % of the reads, so it runs without the host in the loop: thresholds are derived in the kernels,
+// the window jobs never leave the device (the sweep kernel reads their number from device memory), the
+// reduction either finishes a read or appends it to a leftover list, and distances / end locations are
+// assembled per slice on the device (-1 rule included) into arrays that travel to the host in four copies.
+// Only the leftover reads (a few thousand) see the host-driven stages above.
+// =============================================================================================
+bool Pass::dev_eligible(int t, int nw) {
+    (void)nw;
+    if (mode != MODE_HW || p->hasEq || !tun.deviceStage) return false;
+    if (tun.filterSeedK <= 0 || tun.filterSeedLevels <= 0) return false;
+    if (p->tg[t].len < tun.filterMinTarget) return false;
+    return true;
+}
+
+void Pass::dev_begin(int maxSlices) {
+    devMode = true;
+    dEd.alloc(be, (size_t)N);
+    dEndCount.alloc(be, (size_t)N);
+    dEndStart.alloc(be, (size_t)N);
+    dLeft.alloc(be, (size_t)N);
+    dLeftCount.alloc(be, 1);
+    be->zero(dLeftCount.p, sizeof(int));
+    dHeaders.alloc(be, (size_t)4 * maxSlices);
+    be->zero(dHeaders.p, (size_t)4 * maxSlices * sizeof(int));
+    hHeaders.resize((size_t)4 * maxSlices);
+    slices.clear();
+    slices.reserve((size_t)maxSlices);
+    poolReserved = 0;
+}
+
+int Pass::dev_enqueue_slice(int t, int nw, int firstPair, const int* listHost, int first, int count) {
+    const Target& tg = p->tg[t];
+    if (!seed_index(t) || seedIdx->Ls[0] <= 0) throw std::runtime_error("internal: device stage without a seed index");
+    const SeedIndex& sx = *seedIdx;
+    const int si = (int)slices.size();
+    DevSlice sl;
+    sl.t = t;
+    sl.nw = nw;
+    sl.firstPair = firstPair >= 0 ? firstPair + first : -1;
+    sl.count = count;
+    sl.poolBase = poolReserved;
+    sl.poolCap = 4 * count + count / 4 + 1024;  // <= KPOS inline positions per read + the slice's extra list
+    poolReserved += sl.poolCap;
+    if (poolReserved > (long long)dPool.n) throw std::runtime_error("internal: end-location pool of the device stage too small");
+    const int* dList = nullptr;
+    if (firstPair < 0) {  // an arbitrary subset of the batch: its pair indices go to the device
+        if (listsUsed + (size_t)count > dLists.n) throw std::runtime_error("internal: read lists of the device stage too small");
+        be->h2d(dLists.p + listsUsed, listHost + first, (size_t)count * sizeof(int));
+        dList = dLists.p + listsUsed;
+        listsUsed += (size_t)count;
+    }
+    int& perRead = eng.scratch.seedWindowsPerRead[0];
+    const int cap = (int)std::min<long long>((long long)count * std::max(perRead + 2, 6) + 4096, 1LL << 28);
+    const int extraCap = count / 4 + 1024;
+    DevBuf<SeedPlan> dPlan(be, count);
+    DevBuf<int> wPair(be, cap), wK(be, cap), wStart(be, cap), wLen(be, cap), wTf(be, cap);
+    DevBuf<WinRec> dWinRecs(be, cap);
+    DevBuf<Rec> dOut(be, count);
+    DevBuf<int> dExtra(be, extraCap), dCnt32(be, (size_t)count + 1), dCtr(be, 2);
+    be->zero(dCtr.p, 2 * sizeof(int));
+    SeedPlanParams sp;
+    fill_seed_plan(sp, p, tg, sx, 0, tun);
+    sp.readList = dList;
+    sp.firstPair = sl.firstPair;
+    sp.thr = nullptr;
+    sp.numReads = count;
+    sp.winPair = wPair.p;
+    sp.winK = wK.p;
+    sp.winStart = wStart.p;
+    sp.winLen = wLen.p;
+    sp.winTf = wTf.p;
+    sp.winCap = cap;
+    sp.winCount = dCtr.p;
+    sp.plan = dPlan.p;
+    be->launch_seed_plan(sp);
+    K1WParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.tcodes = p->dSeq.p + tg.off;
+    wp.qcodes = p->dSeq.p;
+    wp.qoff = p->dQoff.p;
+    wp.qlen = p->dQlen.p;
+    wp.readList = wPair.p;
+    wp.kInit = wK.p;
+    wp.winStart = wStart.p;
+    wp.winLen = wLen.p;
+    wp.trackFrom = wTf.p;
+    wp.numReads = cap;
+    wp.countPtr = dCtr.p;
+    wp.ncodes = p->ncodes;
+    wp.eqtab = nullptr;
+    wp.recs = dWinRecs.p;
+    be->launch_k1w(wp, nw);
+    WinReduceParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.plan = dPlan.p;
+    rp.winRecs = dWinRecs.p;
+    rp.numReads = count;
+    rp.out = dOut.p;
+    rp.extra = dExtra.p;
+    rp.extraCount = dCtr.p + 1;
+    rp.extraCap = extraCap;
+    rp.leftover = dLeft.p;
+    rp.leftoverCount = dLeftCount.p;
+    rp.readList = dList;
+    rp.firstPair = sl.firstPair;
+    rp.qlen = p->dQlen.p;
+    rp.kBound = k;
+    be->launch_win_reduce(rp);
+    FinParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.recs = dOut.p;
+    fp.extra = dExtra.p;
+    fp.readList = dList;
+    fp.firstPair = sl.firstPair;
+    fp.numReads = count;
+    fp.qlen = p->dQlen.p;
+    fp.kBound = k;
+    fp.ed = dEd.p;
+    fp.endCount = dEndCount.p;
+    fp.endStart = dEndStart.p;
+    fp.cnt32 = dCnt32.p;
+    fp.pool = dPool.p + sl.poolBase;
+    fp.poolBase = sl.poolBase;
+    fp.poolCap = sl.poolCap;
+    fp.header = dHeaders.p + 4 * si;
+    fp.winCount = dCtr.p;
+    be->launch_fin_count(fp);
+    be->launch_scan(dCnt32.p, count);
+    be->launch_fin_fill(fp);
+    // the slice's results travel on the results stream while the compute stream goes on with the next slice
+    const uint64_t done = be->mark(Backend::STREAM_COMPUTE);
+    be->wait(Backend::STREAM_RESULTS, done);
+    be->d2h_async(Backend::STREAM_RESULTS, hHeaders.data() + 4 * si, dHeaders.p + 4 * si, 4 * sizeof(int));
+    sl.poolFetched = std::min(sl.poolCap, count + count / 4 + 1024);
+    be->d2h_async(Backend::STREAM_RESULTS, p->endPool.data() + sl.poolBase, dPool.p + sl.poolBase, (size_t)sl.poolFetched * sizeof(int));
+    if (sl.firstPair >= 0) {
+        be->d2h_async(Backend::STREAM_RESULTS, p->ed.data() + sl.firstPair, dEd.p + sl.firstPair, (size_t)count * sizeof(int));
+        be->d2h_async(Backend::STREAM_RESULTS, p->endCount.data() + sl.firstPair, dEndCount.p + sl.firstPair, (size_t)count * sizeof(int));
+        be->d2h_async(Backend::STREAM_RESULTS, p->endStart.data() + sl.firstPair, dEndStart.p + sl.firstPair, (size_t)count * sizeof(long long));
+        stats.d2hBytes += 16LL * count;
+    } else {
+        wholeArrays = true;  // scattered pairs: the per-pair arrays come back in one piece after the last slice
+    }
+    if (extraCopyBytes) {
+        be->d2h_async(Backend::STREAM_RESULTS, extraCopyDst, extraCopySrc, extraCopyBytes);
+        stats.d2hBytes += (long long)extraCopyBytes;
+    }
+    stats.d2hBytes += 16 + 4LL * sl.poolFetched;
+    sl.done = be->mark(Backend::STREAM_RESULTS);
+    slices.push_back(sl);
+    return si;
+}
+
+// Waits for the results of slice si; afterwards its reads' ed / endCount / endStart / end locations are valid on
+// the host (pending reads carry ed == -2 until the host-driven stages have dealt with them).
+void Pass::dev_finish_slice(int si) {
+    DevSlice& sl = slices[(size_t)si];
+    if (sl.finished) return;
+    sl.finished = true;
+    be->host_wait(sl.done);
+    const int* h = hHeaders.data() + 4 * si;
+    if (h[2]) throw std::runtime_error("internal: end-location pool region of a slice overflowed");
+    if (h[0] > sl.poolFetched) {  // more end locations than the first copy brought: fetch the rest
+        be->d2h(p->endPool.data() + sl.poolBase + sl.poolFetched, dPool.p + sl.poolBase + sl.poolFetched,
+                (size_t)(h[0] - sl.poolFetched) * sizeof(int));
+        stats.d2hBytes += 4LL * (h[0] - sl.poolFetched);
+    }
+    stats.filterWindows += h[3];
+    stats.filterDecided += sl.count - h[1];
+    windowsSeen += h[3];
+    readsSeen += sl.count;
+}
+
+// After the last slice: per-pair arrays of scattered groups, then the reads the device could not decide, grouped by
+// (target, word class) and run through the host-driven stages (their outcome lands in the host vectors; hostPairs).
+void Pass::dev_leftovers() {
+    for (size_t si = 0; si < slices.size(); ++si) dev_finish_slice((int)si);
+    if (readsSeen > 0) eng.scratch.seedWindowsPerRead[0] = (int)((windowsSeen + readsSeen - 1) / readsSeen);
+    int L = 0;
+    dLeftCount.download(&L, 1);
+    if (wholeArrays) {
+        be->d2h_async(Backend::STREAM_COMPUTE, p->ed.data(), dEd.p, (size_t)N * sizeof(int));
+        be->d2h_async(Backend::STREAM_COMPUTE, p->endCount.data(), dEndCount.p, (size_t)N * sizeof(int));
+        be->d2h_async(Backend::STREAM_COMPUTE, p->endStart.data(), dEndStart.p, (size_t)N * sizeof(long long));
+        stats.d2hBytes += 16LL * N;
+    }
+    HostBuf<Leftover> left(be, (size_t)std::max(L, 1));
+    if (L) be->d2h(left.p, dLeft.p, (size_t)L * sizeof(Leftover));
+    else be->sync();
+    stats.d2hBytes += 4 + 8LL * L;
+    trace.mark("device stage: results on the host");
+    if (L == 0) return;
+    std::sort(left.p, left.p + L, [](const Leftover& a, const Leftover& b) { return a.pair < b.pair; });
+    std::map<std::pair<int, int>, std::pair<std::vector<int>, std::vector<int>>> groups;  // (t, nw) -> pairs, excl
+    for (int i = 0; i < L; ++i) {
+        const int pair = left[i].pair;
+        auto& g = groups[std::make_pair(p->tidx[pair], ceil_div(p->qlen[pair], 32))];
+        g.first.push_back(pair);
+        g.second.push_back(left[i].excl);
+        hostPairs.push_back(pair);
+    }
+    for (auto& kv : groups) lane_group(kv.first.first, kv.first.second, kv.second.first, &kv.second.second, 1);
 }
 }  // namespace eb

@@ -66,9 +66,11 @@ void Pass::warp_distance() {
     }
 }
 
-// editDistance and endLocations per pair from the sweep outcomes (ref cpp:219-225 and the -1 rule).
-void Pass::collect_ends() {
-    // ---- distances and end locations: counts per pair, offsets, fill (on a few host threads) -------
+// editDistance and endLocations from the sweep outcomes held in the host vectors (ref cpp:219-225 and the -1
+// rule), appended to the batch's end-location pool: of every pair (pairs == nullptr) or of the listed ones (the
+// rest was assembled on the device).
+void Pass::collect_ends(const std::vector<int>* pairs) {
+    // ---- counts per pair, offsets, fill (on a few host threads) -------
     // ref cpp:670, 681-693: the padded bottom cell of column W-1 shows up as end location -1
     auto accepted = [&](int i) -> int {  // number of end locations of pair i, or -1 if it has no result
         if (p->special[i]) return -1;
@@ -80,21 +82,26 @@ void Pass::collect_ends() {
         const int W64 = ceil_div(m, 64) * 64 - m;
         return posLen[i] + ((best[i] == m && W64 > 0) ? 1 : 0);
     };
-    const size_t nparts = host_parts((size_t)N, 65536);
+    const size_t M = pairs ? pairs->size() : (size_t)N;
+    auto pair_of = [&](size_t j) -> int { return pairs ? (*pairs)[j] : (int)j; };
+    const size_t nparts = host_parts(M, 65536);
     std::vector<long long> partCount(nparts + 1, 0);
     std::vector<int> bad(nparts, 0);
     auto run = [&](const std::function<void(size_t, size_t, size_t)>& fn) {
-        HostPool::get().run(nparts, [&](size_t t) { fn(t, (size_t)N * t / nparts, (size_t)N * (t + 1) / nparts); });
+        HostPool::get().run(nparts, [&](size_t t) { fn(t, M * t / nparts, M * (t + 1) / nparts); });
     };
     run([&](size_t t, size_t lo, size_t hi) {
         long long c = 0;
-        for (size_t i = lo; i < hi; ++i) {
-            const int a = accepted((int)i);
+        for (size_t j = lo; j < hi; ++j) {
+            const int i = pair_of(j);
+            const int a = accepted(i);
             if (a > 0) c += a;
             if (a >= 0 && mode != MODE_NW && posLen[i] != cnt[i]) bad[t] = 1;
         }
         partCount[t + 1] = c;
     });
+    const long long base = (long long)p->endPool.size();  // behind the regions the device filled
+    partCount[0] = base;
     for (size_t t = 0; t < nparts; ++t) {
         if (bad[t]) throw std::runtime_error("internal: end-location count mismatch");
         partCount[t + 1] += partCount[t];
@@ -102,9 +109,10 @@ void Pass::collect_ends() {
     p->endPool.resize((size_t)partCount[nparts]);
     run([&](size_t t, size_t lo, size_t hi) {
         long long at = partCount[t];
-        for (size_t i = lo; i < hi; ++i) {
+        for (size_t j = lo; j < hi; ++j) {
+            const int i = pair_of(j);
             p->endStart[i] = at;
-            const int a = accepted((int)i);
+            const int a = accepted(i);
             if (a < 0) {
                 p->ed[i] = -1;
                 p->endCount[i] = 0;

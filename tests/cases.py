@@ -169,6 +169,48 @@ def filter_edge_case(seed):
     return dict(qs=qs, ts=[t] * len(qs), k=[-1, 12, 3][seed % 3], mode=2, task=seed % 3, eqs=None)
 
 
+def stream_cases(seed, count):
+    """HW batches shaped like read sets (lengths within two neighbouring word classes, one shared target): what
+    edlibAlignBatch streams in slices when the batch is large (the tests lower the size limits).  Includes bytes
+    that do not occur in the target (they get the one extra code of a streamed batch), reads too short for any
+    seed, unrelated reads, reads hanging over the ends of the target, repeats, bounded and free k, all tasks."""
+    rng = random.Random(seed)
+    for it in range(count):
+        alpha = rng.choice([b"ACGT", b"ACGT", b"ACGT", b"ACGTN", b"ACDEFGHIKLMNPQRSTVWY", b"AC"])
+        foreign = bytes(b for b in b"NXZ#" if b not in alpha)
+        n = rng.choice([3000, 8000, 20000])
+        t = rand_seq(rng, n, alpha)
+        if rng.random() < 0.4:  # a segment copied to several places
+            seg = t[100:100 + rng.choice([200, 600])]
+            for _c in range(rng.choice([1, 2, 4])):
+                at = rng.randrange(0, len(t))
+                t = t[:at] + (mutate(rng, seg, 0.01, alpha) if rng.random() < 0.5 else seg) + t[at:]
+        lo, hi = rng.choice([(100, 150), (129, 160), (40, 64), (150, 150), (225, 256), (20, 32)])
+        qs = []
+        for _ in range(rng.choice([70, 200, 500])):
+            L = rng.randrange(lo, hi + 1)
+            r = rng.random()
+            if r < 0.7:
+                a = rng.randrange(0, len(t) - L - 10)
+                q = mutate(rng, t[a:a + L + 8], rng.choice([0, 0.02, 0.05, 0.12, 0.3]), alpha)[:L]
+            elif r < 0.8:
+                q = rand_seq(rng, L, alpha)
+            elif r < 0.9:  # hanging over either end of the target
+                q = (rand_seq(rng, 10, alpha) + t[:L])[:L] if rng.random() < 0.5 else (t[len(t) - L + 10:] + rand_seq(rng, 10, alpha))[:L]
+            else:
+                a = rng.randrange(0, max(1, len(t) - L))
+                q = t[a:a + L]
+            if len(q) < L:
+                q = q + rand_seq(rng, L - len(q), alpha)
+            if rng.random() < 0.15:  # bytes the target does not hold
+                q = bytearray(q)
+                for _x in range(rng.choice([1, 2, 5])):
+                    q[rng.randrange(len(q))] = rng.choice(foreign)
+                q = bytes(q)
+            qs.append(q)
+        yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 3, 10, 40]), mode=2, task=(it + seed) % 3, eqs=None)
+
+
 def pairwise_cases(seed, count):
     """Batches of short queries each with its OWN target (pairwise comparison shape): the lane-per-
     alignment kernel with per-job targets, all modes and tasks, odd alphabets, equalities."""

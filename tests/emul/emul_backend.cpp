@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -56,7 +57,8 @@ template <int NW>
 void emul_k1w(const K1WParams& p) {
     HostPeqAcc<NW> acc;
     acc.w.assign((size_t)p.ncodes * NW, 0);
-    for (int slot = 0; slot < p.numReads; ++slot) k1w_thread<NW>(p, slot, acc);
+    const int numJobs = p.countPtr ? std::min(p.numReads, *p.countPtr) : p.numReads;
+    for (int slot = 0; slot < numJobs; ++slot) k1w_thread<NW>(p, slot, acc);
 }
 
 template <int NW>
@@ -111,11 +113,11 @@ struct EmulBackend : Backend {
     }
     void launch_seed_count(const SeedIndexParams& p) override {
         ++launchesCount;
-        for (int i = 0; i <= p.n - p.L; ++i) seed_count_item(p, i);
+        for (int i = 0; i < p.numPos; ++i) seed_count_item(p, i);
     }
     void launch_seed_fill(const SeedIndexParams& p) override {
         ++launchesCount;
-        for (int i = p.n - p.L; i >= 0; --i) seed_fill_item(p, i);  // any order is valid; not the ascending one
+        for (int i = p.numPos - 1; i >= 0; --i) seed_fill_item(p, i);  // any order is valid; not the ascending one
     }
     void launch_scan(int* data, int count) override {
         ++launchesCount;
@@ -129,10 +131,31 @@ struct EmulBackend : Backend {
     }
     void launch_seed_plan(const SeedPlanParams& p) override {
         ++launchesCount;
+        std::vector<int> E(SEED_CAND_2);
+        int ctl[2];
+        uint8_t qs[256];
         for (int i = p.numReads - 1; i >= 0; --i) {
-            if (p.level <= 0) seed_plan_read<SEED_CAND_0>(p, i);
-            else if (p.level == 1) seed_plan_read<SEED_CAND_1>(p, i);
-            else seed_plan_read<SEED_CAND_2>(p, i);
+            if (p.level <= 0) seed_plan_read<SEED_CAND_0, CoopSerial>(p, i, E.data(), ctl, qs);
+            else if (p.level == 1) seed_plan_read<SEED_CAND_1, CoopSerial>(p, i, E.data(), ctl, qs);
+            else seed_plan_read<SEED_CAND_2, CoopSerial>(p, i, E.data(), ctl, qs);
+        }
+    }
+    void launch_fin_count(const FinParams& p) override {
+        ++launchesCount;
+        for (int i = 0; i < p.numReads; ++i) fin_count_item(p, i);
+    }
+    void launch_fin_fill(const FinParams& p) override {
+        ++launchesCount;
+        for (int i = p.numReads - 1; i >= 0; --i) fin_fill_item(p, i);
+    }
+    void launch_qalpha(const QAlphaParams& p) override {
+        ++launchesCount;
+        for (int q = 0; q < p.numQueries; ++q) {
+            uint32_t local[8];
+            qalpha_scan(p, q, 0, 1, local);
+            int total = 0;
+            for (int k = 0; k < 8; ++k) total += popcount32(local[k] | p.tmask[k]);
+            p.alphaLen[p.firstPair + q] = total;
         }
     }
     void launch_win_reduce(const WinReduceParams& p) override {

@@ -82,10 +82,31 @@ def test_candidate_filter_all_branches():
                   {"EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "3", "EDLIB_B200_FILTER_SEED_BUCKET": "2"},
                   {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "12", "EDLIB_B200_FILTER_SEED_K": "0"},
                   {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "40",
-                   "EDLIB_B200_FILTER_SEED_LEVELS": "3", "EDLIB_B200_FILTER_SEED_SLACK": "100000"}):
+                   "EDLIB_B200_FILTER_SEED_LEVELS": "3", "EDLIB_B200_FILTER_SEED_SLACK": "100000"},
+                  {"EDLIB_B200_DEVICE_STAGE": "0"},                                   # every stage host-driven
+                  {"EDLIB_B200_SLICE_READS": "64", "EDLIB_B200_FILTER_SEED_LEVELS": "1"}):  # many slices, one seed level
         env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 500
+
+
+def test_streamed_batches():
+    """edlibAlignBatch on read-set-shaped HW batches goes through the streamed path (slices packed and uploaded
+    under the kernels of earlier slices, results assembled on the device, result structs built per slice): the
+    size limits are lowered so that small batches take it, with one host thread, several, and slices of 64 reads."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 31, 18, gen=cases.stream_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra in ({"EDLIB_B200_HOST_THREADS": "1"}, {"EDLIB_B200_HOST_THREADS": "5", "EDLIB_B200_SLICE_READS": "64"},
+                  {"EDLIB_B200_HOST_THREADS": "3", "EDLIB_B200_SLICE_READS": "100", "EDLIB_B200_FILTER_SEED_BUCKET": "2",
+                   "EDLIB_B200_FILTER_SEED_K": "5"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_TRACE="1", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 2000
+        assert "stream: slices enqueued" in out.stderr  # the streamed path really ran
 
 
 def test_large_batch_uses_the_threaded_host_paths():
@@ -191,6 +212,42 @@ def test_staged_batches_are_independent(emul):
         assert st == 0 and results(batch, h) == exp
     L.edlibB200BatchFree(ha)
     L.edlibB200BatchFree(hb)
+
+
+def test_staged_api_misuse_is_an_error_not_a_crash(emul):
+    """Results requested from a batch that was never computed (after another batch went through the engine, so that
+    recycled storage is in play) return EDLIB_STATUS_ERROR; the batch still computes fine afterwards."""
+    import ctypes as C
+    from edlib_b200._ffi import AlignConfig, AlignResult, make_config, result_to_dict
+    L = emul.lib
+    L.edlibB200BatchPrepare.restype = C.c_void_p
+    L.edlibB200BatchPrepare.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_int),
+                                        C.c_int, AlignConfig]
+    L.edlibB200BatchCompute.argtypes = [C.c_void_p, C.c_void_p]
+    L.edlibB200BatchResults.argtypes = [C.c_void_p, C.POINTER(AlignResult)]
+    L.edlibB200BatchFree.argtypes = [C.c_void_p]
+    L.edlibB200LastError.restype = C.c_char_p
+    st, _ = emul.align_batch([b"ACGTACGT"] * 5, [b"ACGTTTACGT"] * 5, -1, 2, 1)
+    assert st == 0
+    qs = [b"ACGTAC", b"TTTT", b"ACGGGT"] * 7
+    n = len(qs)
+    t = C.create_string_buffer(b"ACGTACGGGTTTACG", 15)
+    arrs = ((C.c_char_p * n)(*qs), (C.c_int * n)(*[len(q) for q in qs]), (C.c_char_p * n)(*[C.cast(t, C.c_char_p)] * n),
+            (C.c_int * n)(*[15] * n))
+    cfg, keep = make_config(-1, 2, 1, None)
+    h = L.edlibB200BatchPrepare(*arrs, n, cfg)
+    assert h
+    res = (AlignResult * n)()
+    assert L.edlibB200BatchResults(h, res) == 1
+    assert b"not" in L.edlibB200LastError()
+    assert L.edlibB200BatchCompute(h, None) == 0
+    assert L.edlibB200BatchResults(h, res) == 0
+    got = [result_to_dict(res[i]) for i in range(n)]
+    for i in range(n):
+        emul.free(res[i])
+    assert got == [emul.align(q, t.raw, -1, 2, 1) for q in qs]
+    L.edlibB200BatchFree(h)
+    del keep
 
 
 def test_many_end_locations(emul):
