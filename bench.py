@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep-sample", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (other configs, sensitivity)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -33,6 +33,14 @@ EB_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi) {
 #endif
 }
 
+EB_HD int popcount32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
 EB_HD int atomic_add_int(int* p, int v) {
 #if defined(__CUDA_ARCH__)
     return atomicAdd(p, v);
@@ -403,11 +411,27 @@ EB_HD void k1_columns(K1State<NW>& st, const Acc& acc, const Syms& syms, int cou
 }
 
 // Query profile for one K1 thread (ref buildPeq cpp:358-384 with top padding instead of the
-// bottom wildcard rows).  `Acc::store(code, w, bits)` writes one Eq word.
+// bottom wildcard rows).  `Acc::store(code, w, bits)` writes one Eq word, `Acc::or_word(code, w, bits)` ORs into it.
+// Plain equality: every row starts as its padding bits and ONE pass over the m characters sets the bit of each
+// character in the row of its code (m read-modify-writes instead of ncodes * NW * 32 bit tests); a character
+// whose code is not a row (the foreign-byte code of streamed batches) matches nothing.  With an equality table
+// every (code, bit) is tested as before.
 template <int NW, class Acc>
 EB_HD void k1_build_peq(Acc& acc, const uint8_t* q, int m, int mode, int ncodes, const uint8_t* eqtab, bool rev = false) {
     const int off = 32 * NW - m;
     const uint32_t padBit = (mode == MODE_HW) ? 1u : 0u;
+    if (!eqtab) {
+        for (int code = 0; code < ncodes; ++code) {
+            EB_UNROLL
+            for (int w = 0; w < NW; ++w) acc.store(code, w, padBit ? ~init_pv_word(w, off) : 0u);
+        }
+        for (int r = 0; r < m; ++r) {
+            const int qc = rev ? q[m - 1 - r] : q[r];
+            const int g = r + off;
+            if (qc < ncodes) acc.or_word(qc, g >> 5, 1u << (g & 31));
+        }
+        return;
+    }
     for (int code = 0; code < ncodes; ++code) {
         for (int w = 0; w < NW; ++w) {
             uint32_t bits = 0;
@@ -418,7 +442,7 @@ EB_HD void k1_build_peq(Acc& acc, const uint8_t* q, int m, int mode, int ncodes,
                     bit = padBit;
                 } else {
                     const int qc = rev ? q[m - 1 - (g - off)] : q[g - off];
-                    bit = eqtab ? (eqtab[qc * ncodes + code] ? 1u : 0u) : (qc == code ? 1u : 0u);
+                    bit = eqtab[qc * ncodes + code] ? 1u : 0u;
                 }
                 bits |= bit << b;
             }
@@ -480,31 +504,145 @@ EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     rec->cnt = st.cnt;
 }
 
-// One K1W work item: the whole query over its own target window, symbols read straight from
-// global memory (each lane walks its own window; the target is L2-resident).
-template <int NW, class Acc>
-EB_HD void k1w_thread(const K1WParams& p, int slot, Acc& acc) {
+// (lo:hi) >> sh, low word; sh in 0..31.
+EB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+// View of a word-addressable profile (rows of NW + 4 words, see k1w_thread) as the NW-word K1 profile.
+template <int NW, class WAcc>
+struct K1View {
+    WAcc& a;
+    EB_HD void store(int code, int w, uint32_t bits) { a.store_word(code, w + 2, bits); }
+    EB_HD void or_word(int code, int w, uint32_t bits) { a.or_word(code, w + 2, bits); }
+    EB_HD void load(uint32_t code, uint32_t (&Eq)[NW]) const {
+        EB_UNROLL
+        for (int w = 0; w < NW; ++w) Eq[w] = a.load_word(code, w + 2);
+    }
+};
+
+// Banded window sweep (one K1W work item whose end columns of interest span few diagonals).
+//
+// Only scores <= t at the tracked columns [lo, hi] matter (t = kInit - 1), and an alignment with <= t edits that
+// ends at (m-1, e) stays within t diagonals of its last cell, so every cell that can matter lies on the
+// diagonals c - r in [lo-(m-1)-t, hi-(m-1)+t]: H = (hi-lo) + 2t + 1 of them.  With H <= 64 a 64-row window
+// that moves down one row per column covers them: bit k of the state of column j is row top(j) + k,
+// top(j) = j - dhi.  In that frame the Myers recurrences lose their shifts of the horizontal deltas (they
+// cancel against the moving window) and gain one shift of the diagonal vector (Hyyro's banded form):
+//     D0 = (((Eq & VP) + VP) ^ VP) | Eq | VN        diagonal zero-delta of the cells of column j
+//     HP = VN | ~(D0 | VP),  HN = VP & D0           horizontal deltas
+//     X  = D0 >> 1
+//     VN' = X & HP,  VP' = HN | ~(X | HP)           vertical deltas of column j, window of column j+1
+// Cells outside the window never enter: the top cell gets no contribution from above, the new bottom cell
+// none from its left (X brings in a 0), so every value is an upper bound of the true one and exact wherever
+// the optimal path stays inside -- which is the case for all scores <= t at tracked columns.  Rows above the
+// query (window rows < 0) are the wildcard rows of HW mode: Eq = 1, deltas 0 (two words of ones in front of the
+// profile); rows below it carry Eq = 0 and influence nothing above them.  The score of the window's bottom
+// cell is carried along (S += 1 - HN[63]); the last-row score at a tracked column is S minus the vertical
+// deltas between the last row and the bottom (two popcounts).
+template <class WAcc, class RecT>
+EB_HD void k1b_sweep(const WAcc& acc, const uint8_t* tsyms, int ws, int m, int off, int c0, int lo, int hi, int t,
+                     int& bestIo, int& cntIo, RecT* rec) {
+    constexpr int CAP = (int)(sizeof(rec->pos) / sizeof(rec->pos[0]));
+    const int dhi = hi - (m - 1) + t;
+    const int g0 = off + 64 - dhi;           // global profile bit of the window's top row at column 0 (>= 0 from c0 on)
+    // state before column c0: D[r][c0-1] = r + 1 on the rows of the query, 0 above it
+    const int gt0 = c0 + g0;                 // profile bit of the top row
+    const int firstReal = off + 64 - gt0;    // window bit of query row 0 (may be <= 0 or >= 64)
+    uint64_t vp64 = firstReal <= 0 ? ~0ull : (firstReal >= 64 ? 0ull : (~0ull << firstReal));
+    uint32_t VP0 = (uint32_t)vp64, VP1 = (uint32_t)(vp64 >> 32), VN0 = 0, VN1 = 0;
+    const int bottomRow = c0 - dhi + 63;
+    int S = bottomRow >= 0 ? bottomRow + 1 : 0;
+    int best = bestIo, cnt = cntIo;
+    for (int j = c0; j <= hi; ++j) {
+        const uint32_t sym = tsyms[j];
+        const int gt = j + g0;
+        const int wi = gt >> 5, sh = gt & 31;
+        const uint32_t w0 = acc.load_word(sym, wi), w1 = acc.load_word(sym, wi + 1), w2 = acc.load_word(sym, wi + 2);
+        const uint32_t Eq0 = funnel_r(w0, w1, sh), Eq1 = funnel_r(w1, w2, sh);
+        const uint32_t T0 = Eq0 & VP0, T1 = Eq1 & VP1;
+        const uint32_t S0 = T0 + VP0;
+        const uint32_t S1 = T1 + VP1 + (S0 < T0 ? 1u : 0u);
+        const uint32_t D00 = ((S0 ^ VP0) | Eq0) | VN0, D01 = ((S1 ^ VP1) | Eq1) | VN1;
+        const uint32_t HP0 = VN0 | ~(D00 | VP0), HP1 = VN1 | ~(D01 | VP1);
+        const uint32_t HN0 = VP0 & D00, HN1 = VP1 & D01;
+        const uint32_t X0 = (D00 >> 1) | (D01 << 31), X1 = D01 >> 1;
+        VN0 = X0 & HP0;
+        VN1 = X1 & HP1;
+        VP0 = HN0 | ~(X0 | HP0);
+        VP1 = HN1 | ~(X1 | HP1);
+        S += 1 - (int)(HN1 >> 31);
+        if (j >= lo) {
+            const int kb = m - 2 - j + dhi;  // window bit (frame of column j+1) of the last query row: 0..63
+            const uint64_t M = kb >= 63 ? 0ull : (~0ull << (kb + 1));
+            const int score = S - popcount32(VP0 & (uint32_t)M) - popcount32(VP1 & (uint32_t)(M >> 32)) +
+                              popcount32(VN0 & (uint32_t)M) + popcount32(VN1 & (uint32_t)(M >> 32));
+            if (score <= best) {  // same bookkeeping as k1_event (ref cpp:658-673)
+                if (score < best) {
+                    best = score;
+                    cnt = 0;
+                }
+                if (cnt < CAP) rec->pos[cnt] = ws + j;
+                rec->last = ws + j;
+                cnt++;
+            }
+        }
+    }
+    bestIo = best;
+    cntIo = cnt;
+}
+
+// One K1W work item: the whole query over its own target window (each lane walks its own window; the target is
+// L2-resident).  The profile rows have NW + 4 words: two words of ones (wildcard rows above the query, used by
+// the banded sweep), the NW-word K1 profile, two words of zeros.  Windows whose end columns of interest span at
+// most 64 diagonals take the banded sweep (k1b_sweep: 2 words per column instead of NW), the others the full one.
+template <int NW, class WAcc>
+EB_HD void k1w_thread(const K1WParams& p, int slot, WAcc& acc) {
     const int pair = p.readList[slot];
     const int m = p.qlen[pair];
     WinRec* rec = p.recs + slot;
-    k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], m, MODE_HW, p.ncodes, p.eqtab);
-    K1State<NW> st;
-    k1_init<NW>(st, m, p.kInit[slot]);
+    for (int code = 0; code < p.ncodes; ++code) {
+        acc.store_word(code, 0, ~0u);
+        acc.store_word(code, 1, ~0u);
+        acc.store_word(code, NW + 2, 0u);
+        acc.store_word(code, NW + 3, 0u);
+    }
+    K1View<NW, WAcc> k1acc{acc};
+    k1_build_peq<NW>(k1acc, p.qcodes + p.qoff[pair], m, MODE_HW, p.ncodes, p.eqtab);
     const int ws = p.winStart[slot], tf = p.trackFrom[slot], len = p.winLen[slot];
+    const int kInit = p.kInit[slot];
+    const int t = kInit - 1;
+    const int hi = len - 1;
+    if (t >= 0 && (hi - tf) + 2 * t + 1 <= 64) {
+        // lead-in: exactly m + t columns before the first tracked one (the window may start a little earlier,
+        // at a multiple of 16), or the start of the target
+        const int c0 = tf - (m + t) > 0 ? tf - (m + t) : 0;
+        int best = kInit, cnt = 0;
+        k1b_sweep(acc, p.tcodes + ws, ws, m, 32 * NW - m, c0, tf, hi, t, best, cnt, rec);
+        rec->best = best;
+        rec->cnt = cnt;
+        return;
+    }
+    K1State<NW> st;
+    k1_init<NW>(st, m, kInit);
     // Lead-in columns in blocks of 32.  The last-row score falls by at most one per column, so once it
     // exceeds the sentinel by more than the columns left in the window no tracked column can reach the
     // threshold any more and the sweep stops (most windows come from chance seed hits and end here).
     bool hopeless = false;
     for (int j = 0; j < tf; j += 32) {
         const int cntj = tf - j < 32 ? tf - j : 32;
-        k1_columns<NW, false, false>(st, acc, PtrSyms{p.tcodes + ws + j}, cntj, ws + j, rec, slot, nullptr, nullptr, 0);
+        k1_columns<NW, false, false>(st, k1acc, PtrSyms{p.tcodes + ws + j}, cntj, ws + j, rec, slot, nullptr, nullptr, 0);
         if (st.up - st.down - (len - (j + cntj)) >= st.best) {
             hopeless = true;
             break;
         }
     }
     if (!hopeless)
-        k1_columns<NW, false, true>(st, acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
+        k1_columns<NW, false, true>(st, k1acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
     rec->best = st.best;
     rec->cnt = st.cnt;
 }
@@ -533,17 +671,23 @@ EB_HD void seed_fill_item(const SeedIndexParams& p, int i) {
 }
 
 // Windows of one read from its sorted candidate end columns E[0..c): emit == false only counts them.
-// Windows start at multiples of 16 columns (vector loads of the target in k1w_thread; a longer lead-in is
-// still exact).
+// Windows start at multiples of 16 columns (a longer lead-in is still exact).  Candidates are verified together
+// as long as the window stays narrow enough for the banded sweep (k1b_sweep: tracked columns + 2t + 1 <= 64
+// diagonals); when t is too large for any banded window, as long as they are neighbours (gap / spread rule).
 EB_HD int seed_windows(const SeedPlanParams& p, const int* E, int c, int m, int t, int pair, int base, bool emit) {
-    long long prevHi = -1;
+    const int bandSlack = 63 - 4 * t;  // E[last] - E[first] may be this large in a banded window
+    int prevHi = -1;
     int nW = 0;
     for (int i = 0; i < c;) {
         const int first = E[i];
         int last = first;
         ++i;
-        while (i < c && E[i] - last <= K1_RANGE_GAP && E[i] - first <= p.spread) last = E[i++];
-        long long lo = (long long)first - t, hi = (long long)last + t;
+        if (bandSlack >= 0) {
+            while (i < c && E[i] - first <= bandSlack) last = E[i++];
+        } else {
+            while (i < c && E[i] - last <= K1_RANGE_GAP && E[i] - first <= p.spread) last = E[i++];
+        }
+        int lo = first - t, hi = last + t;
         if (lo <= prevHi) lo = prevHi + 1;  // tracked columns of successive windows stay disjoint
         if (lo < 0) lo = 0;
         if (hi > p.n - 1) hi = p.n - 1;
@@ -551,23 +695,24 @@ EB_HD int seed_windows(const SeedPlanParams& p, const int* E, int c, int m, int 
         prevHi = hi;
         // HW restart: an alignment with <= t edits spans at most m + t target columns, so every score <= t
         // of a tracked column is exact (larger ones may come out larger still, which changes nothing)
-        long long ws = lo - (long long)(m + t);
+        int ws = lo - (m + t);
         if (ws < 0) ws = 0;
-        ws &= ~15LL;
+        ws &= ~15;
         if (emit) {
             const int w = base + nW;
             p.winPair[w] = pair;
             p.winK[w] = t + 1;
-            p.winStart[w] = (int)ws;
-            p.winLen[w] = (int)(hi - ws + 1);
-            p.winTf[w] = (int)(lo - ws);
+            p.winStart[w] = ws;
+            p.winLen[w] = hi - ws + 1;
+            p.winTf[w] = lo - ws;
         }
         ++nW;
     }
     return nW;
 }
 
-// Host spelling of the cooperative group that plans one read (one member); the device kernel passes a warp.
+// Host spelling of the cooperative group that plans one read (one member); the device kernel passes a group of
+// eight lanes (four reads per warp).
 struct CoopSerial {
     static EB_HD int lane() { return 0; }
     static EB_HD int width() { return 1; }
@@ -580,11 +725,11 @@ struct CoopSerial {
     }
 };
 
-// One read, planned by a cooperative group C (a warp on the device: its members take the seeds of the read;
-// a single member on the host).  E[CAP] candidate end columns, ctl[2] = {candidates, saturated} and qs[256]
-// (the read's codes) are scratch shared by the group (shared memory on the device).
+// One read, planned by a cooperative group C (its members take the seeds of the read; a single member on the
+// host).  E[CAP] candidate end columns and ctl[2] = {candidates, saturated} are scratch shared by the group
+// (shared memory on the device).
 template <int CAP, class C>
-EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl, uint8_t* qs) {
+EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl) {
     const int lane = C::lane(), W = C::width();
     const int pair = p.readList ? p.readList[slot] : p.firstPair + slot;
     const int m = p.qlen[pair];
@@ -594,13 +739,12 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl, u
     pl.first = pl.count = 0;
     pl.state = SEED_NONE;
     pl.thr = t;
-    if (t < 0 || m > 256) {  // left out of the stage (the host, or the threshold rule)
+    if (t < 0) {  // left out of the stage (the host, or the threshold rule)
         pl.state = SEED_SATURATED;
         pl.thr = -1;
         if (lane == 0) p.plan[slot] = pl;
         return;
     }
-    for (int i = lane; i < m; i += W) qs[i] = q[i];
     if (lane == 0) {
         ctl[0] = 0;
         ctl[1] = 0;
@@ -616,10 +760,15 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl, u
         int i0 = 0, i1 = 0;
         if (j <= t) {
             // a code outside the target's alphabet (streamed batches give the reads' foreign bytes one) occurs nowhere
+            uint32_t key = 0;
             bool known = true;
-            for (int x = 0; x < p.Ls; ++x) known = known && qs[a + x] < p.sigma;
+            for (int x = 0; x < p.Ls; ++x) {
+                const uint32_t code = q[a + x];
+                known = known && code < (uint32_t)p.sigma;
+                if (x < Lk) key = key * (uint32_t)p.sigma + code;
+            }
             if (known) {
-                const uint32_t key = seed_key(qs + a, Lk, Lk, (uint32_t)p.sigma) * span;
+                key *= span;
                 i0 = p.bucketStart[key];
                 i1 = p.bucketStart[key + span];
                 if (i1 - i0 > p.maxBucket) {  // repeat: the read is passed on unseen
@@ -632,7 +781,7 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl, u
             if (i >= i1) continue;
             const int pos = p.positions[i];
             bool same = pos + p.Ls <= p.n;  // keys near the end of the target were padded with code 0
-            for (int x = Lk; same && x < p.Ls; ++x) same = p.tcodes[pos + x] == qs[a + x];
+            for (int x = Lk; same && x < p.Ls; ++x) same = p.tcodes[pos + x] == q[a + x];
             if (!same) continue;
             const int at = C::add_shared(&ctl[0], 1);
             if (at < CAP) E[at] = pos + (m - a) - 1;
@@ -1257,14 +1406,6 @@ EB_HD void qalpha_scan(const QAlphaParams& p, int q, int first, int stride, uint
         local[b >> 5] |= 1u << (b & 31);
     }
 }
-EB_HD int popcount32(uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    return __popc(v);
-#else
-    return __builtin_popcount(v);
-#endif
-}
-
 // alphabetLength of one pair: distinct byte values in query and target together
 // (ref transformSequences cpp:1437-1461 counts them while recoding).
 EB_HD int alpha_len_pair(const uint32_t* masks, int qset, int tset) {

@@ -16,11 +16,60 @@
 // i+1 with the kernels of slice i and with the result structs of slice i-1 (second half of this file).
 #include "eb_engine_internal.h"
 
+#include <sched.h>
+
 namespace eb {
 
 static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
+}
+
+// "0-3,8,10-11" -> cpu numbers
+static std::vector<int> parse_cpulist(const char* path) {
+    std::vector<int> cpus;
+    FILE* f = fopen(path, "r");
+    if (!f) return cpus;
+    char buf[4096];
+    if (fgets(buf, sizeof(buf), f)) {
+        for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            const int got = sscanf(tok, "%d-%d", &a, &b);
+            if (got == 1) b = a;
+            if (got >= 1)
+                for (int c = a; c <= b && c < 4096; ++c) cpus.push_back(c);
+        }
+    }
+    fclose(f);
+    return cpus;
+}
+
+void HostPool::bind_worker() {
+    const std::vector<int>& cpus = worker_cpus();
+    if (cpus.empty()) return;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&allowed);
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return;
+    int n = 0;
+    for (int c : cpus)
+        if (c < CPU_SETSIZE && CPU_ISSET(c, &allowed)) {
+            CPU_SET(c, &want);
+            ++n;
+        }
+    if (n > 0) sched_setaffinity(0, sizeof(want), &want);  // best effort
+}
+
+// The host workers of the engine run next to the GPU (EDLIB_B200_NUMA=0 leaves them where the caller runs); the
+// calling thread itself is never moved.
+Engine::Engine(Backend* be) : be_(be) {
+    if (env_int("EDLIB_B200_NUMA", 1) == 0) return;
+    const int node = be->numa_node();
+    if (node < 0) return;
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    std::vector<int> cpus = parse_cpulist(path);
+    if (!cpus.empty() && HostPool::worker_cpus().empty()) HostPool::worker_cpus() = cpus;
 }
 
 EngineTunables::EngineTunables() {
@@ -680,6 +729,7 @@ struct StreamJob {
     std::vector<char> resultsReady;    // per slice: results on the host, result structs may be built
     bool abort = false;
     std::atomic<size_t> nextPack{0}, nextMat{0};
+    std::atomic<int> targetIssued{0};  // the target's upload heads the copy stream: the slices queue behind it
     std::atomic<int> failed{0};
     std::vector<char> matDone;         // per result-struct task: its range of results[] was written
 };
@@ -815,6 +865,11 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
                 }
                 const size_t off = (size_t)p->qoff[a];
                 const size_t bytes = (size_t)(p->qoff[b - 1] + (uint64_t)p->qlen[b - 1]) - off;
+                while (!job.targetIssued.load(std::memory_order_acquire)) {  // (packing went on meanwhile)
+                    std::this_thread::yield();
+                    std::lock_guard<std::mutex> lock(job.mu);
+                    if (job.abort) return;
+                }
                 be->h2d_copy(p->dSeq.p + off, stage + off, bytes);
                 be->h2d_copy(p->dQoff.p + a, hQoff.p + a, (size_t)(b - a) * sizeof(uint64_t));
                 be->h2d_copy(p->dQlen.p + a, hQlen.p + a, (size_t)(b - a) * sizeof(int));
@@ -885,7 +940,10 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
         memcpy(stage + tOff, tptr, (size_t)n);
         memset(stage + tOff + n, 0, total - tOff - (size_t)n);
         if (tOff > qBytes) memset(stage + qBytes, 0, tOff - qBytes);
-        be->h2d(p->dSeq.p + qBytes, stage + qBytes, total - qBytes);
+        be->h2d_copy(p->dSeq.p + qBytes, stage + qBytes, total - qBytes);
+        const uint64_t targetUp = be->mark(Backend::STREAM_COPY);
+        job.targetIssued.store(1, std::memory_order_release);
+        be->wait(Backend::STREAM_COMPUTE, targetUp);
         std::vector<MaskItem> items;
         for (int s0 = 0; s0 < n; s0 += 65536) items.push_back(MaskItem{(uint64_t)tOff + (uint64_t)s0, std::min(65536, n - s0), 0});
         DevBuf<MaskItem> dItems(be, items.size());

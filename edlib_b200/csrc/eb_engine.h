@@ -43,6 +43,8 @@ struct Backend {
     // Makes the calling host thread use this backend's device (CUDA keeps the current device per thread):
     // called on entry of every API call and by pool workers before they issue copies.
     virtual void bind_thread() {}
+    // NUMA node the device hangs off (-1: unknown / not applicable)
+    virtual int numa_node() { return -1; }
     virtual int sm_count() = 0;
     // Launch shape of the lane-per-alignment kernel for a word class / alphabet size / number of reads
     // (few reads get small CTAs): threads per CTA and how many CTAs are resident on the whole device at
@@ -98,7 +100,7 @@ struct EngineTunables {
     // one (for the reads the first stage cannot decide) within filterK0; only windows around those
     // ranges are swept with the whole read; reads no stage decides take the plain full sweep.
     int deviceStage = 1;          // first seed level driven by the device (0: every stage host-driven)
-    int devSliceReads = 262144;   // reads per slice of the device-driven level
+    int devSliceReads = 1 << 20;  // reads per slice of the device-driven level (streamed batches: at least four slices)
     int streamMinPairs = 32768;   // smallest one-target HW batch that edlibAlignBatch streams (upload under compute)
     int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 32;    // seed stage: longest hash bucket looked at (longer: repeat, read passed on)
@@ -136,7 +138,7 @@ class Prepared;  // a batch whose inputs are resident on the device
 
 class Engine {
 public:
-    explicit Engine(Backend* be) : be_(be) {}
+    explicit Engine(Backend* be);
     ~Engine();
     // One-shot: prepare + compute + materialise.  Returns EDLIB_STATUS_OK / EDLIB_STATUS_ERROR.
     int align_batch(const BatchInput& in, EdlibAlignResult* results);

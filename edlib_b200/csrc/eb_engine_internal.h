@@ -43,6 +43,13 @@ struct Trace {
 // (the engine runs under the library's lock).  The workers live until the process ends.
 class HostPool {
 public:
+    // CPUs the workers should run on (the NUMA node of the GPU: packing writes pinned memory that the GPU then
+    // reads over PCIe, and a remote node halves that).  Set once, before the pool exists (Engine construction);
+    // empty: the workers inherit the creating thread's affinity.
+    static std::vector<int>& worker_cpus() {
+        static std::vector<int> cpus;
+        return cpus;
+    }
     static HostPool& get() {
         static HostPool* pool = new HostPool();  // never destroyed: workers may still be parked at exit
         return *pool;
@@ -143,6 +150,7 @@ private:
         }
     }
     void loop() {
+        bind_worker();
         unsigned long long seen = 0;
         for (;;) {
             {
@@ -153,6 +161,7 @@ private:
             work(seen);
         }
     }
+    static void bind_worker();  // eb_engine.cpp (sched_setaffinity to worker_cpus(), ignored when not permitted)
     size_t workers_ = 0;
     std::mutex mu_;
     std::condition_variable cv_, done_;

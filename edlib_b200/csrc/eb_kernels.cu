@@ -10,7 +10,10 @@
 //
 // The bodies live in eb_core.h (shared with the host emulation used by the CPU tests).
 #include <cuda_runtime.h>
+#include <ctype.h>
 #include <stdio.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -95,6 +98,12 @@ struct SmemPeqAcc {
     EB_D void store(int code, int w, uint32_t bits) {
         const uint32_t addr = (w < 4 ? a0 + 4u * w : b0 + 4u * (w - 4)) + (uint32_t)code * codeStride;
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+    }
+    EB_D void or_word(int code, int w, uint32_t bits) {  // the rows are private to the thread: no atomics
+        const uint32_t addr = (w < 4 ? a0 + 4u * w : b0 + 4u * (w - 4)) + (uint32_t)code * codeStride;
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v | bits) : "memory");
     }
     EB_D void load(uint32_t code, uint32_t (&Eq)[NW]) const {
         const uint32_t off = code * codeStride;
@@ -251,8 +260,30 @@ __global__ void k1_kernel(const K1Params p) {
     }
 }
 
-// K1W: same per-thread sweep, every thread over its own target window read through the generic
-// (global) pointer path; no tile staging, no barriers after the Peq build.
+// Word-addressable per-thread profile rows for K1W: word w of code c of thread t at base + (c * words + w) *
+// 4 * nthreads + 4 * t -- consecutive threads in consecutive banks whatever word each of them reads.
+struct SmemWordAcc {
+    uint32_t base;        // shared address of this thread's word 0 of code 0
+    uint32_t wordStride;  // bytes between consecutive words of a row (4 * nthreads)
+    uint32_t codeStride;  // bytes between rows
+    EB_D void store_word(int code, int w, uint32_t bits) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + (uint32_t)code * codeStride + (uint32_t)w * wordStride), "r"(bits) : "memory");
+    }
+    EB_D void or_word(int code, int w, uint32_t bits) {
+        const uint32_t addr = base + (uint32_t)code * codeStride + (uint32_t)w * wordStride;
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v | bits) : "memory");
+    }
+    EB_D uint32_t load_word(uint32_t code, int w) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + code * codeStride + (uint32_t)w * wordStride));
+        return v;
+    }
+};
+
+// K1W: every thread over its own target window read through the generic (global) pointer path; no tile
+// staging, no barriers.  Banded sweep for windows that span few diagonals, full sweep otherwise (eb_core.h).
 template <int NW>
 __global__ void k1w_kernel(const K1WParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -260,10 +291,10 @@ __global__ void k1w_kernel(const K1WParams p) {
     int numJobs = p.numReads;
     if (p.countPtr) numJobs = min(numJobs, *p.countPtr);  // jobs planned on the device (seed_plan_kernel)
     if (slot >= numJobs) return;
-    SmemPeqAcc<NW> acc;
-    acc.codeStride = (uint32_t)blockDim.x * (16u + 4u * SmemPeqAcc<NW>::NWB);
-    acc.a0 = smem_u32(smem) + 16u * threadIdx.x;
-    acc.b0 = smem_u32(smem) + 16u * blockDim.x + 4u * SmemPeqAcc<NW>::NWB * threadIdx.x;
+    SmemWordAcc acc;
+    acc.wordStride = 4u * blockDim.x;
+    acc.codeStride = (uint32_t)(NW + 4) * acc.wordStride;
+    acc.base = smem_u32(smem) + 4u * threadIdx.x;
     k1w_thread<NW>(p, slot, acc);
 }
 
@@ -316,25 +347,26 @@ __global__ void seed_fill_kernel(const SeedIndexParams p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < p.numPos) seed_fill_item(p, i);
 }
-// One read per WARP: the lanes take the seeds of the read, so their index lookups (key -> bucket bounds ->
-// positions -> target symbols, a chain of dependent random reads) are in flight together; candidates meet in
-// shared memory, lane 0 sorts them and emits the windows.
-struct CoopWarp {
-    static EB_D int lane() { return (int)(threadIdx.x & 31u); }
-    static EB_D int width() { return 32; }
-    static EB_D void sync() { __syncwarp(); }
-    static EB_D bool any(bool v) { return __any_sync(0xffffffffu, v) != 0; }
+// One read per group of EIGHT lanes (four reads per warp): the lanes take the seeds of the read, so their index
+// lookups (key -> bucket bounds -> positions -> target symbols, a chain of dependent random reads) are in flight
+// together; candidates meet in shared memory, lane 0 of the group sorts them and emits the windows.
+struct CoopGroup8 {
+    static EB_D int lane() { return (int)(threadIdx.x & 7u); }
+    static EB_D int width() { return 8; }
+    static EB_D unsigned mask() { return 0xffu << (threadIdx.x & 24u); }
+    static EB_D void sync() { __syncwarp(mask()); }
+    static EB_D bool any(bool v) { return __ballot_sync(mask(), v) != 0u; }
     static EB_D int add_shared(int* p, int v) { return atomicAdd(p, v); }
 };
-constexpr int SEED_PLAN_WARPS = 4;
+constexpr int SEED_PLAN_THREADS = 128, SEED_PLAN_GROUPS = SEED_PLAN_THREADS / 8;
 template <int CAP>
-__global__ void __launch_bounds__(SEED_PLAN_WARPS * 32) seed_plan_kernel(const SeedPlanParams p) {
-    __shared__ int E[SEED_PLAN_WARPS][CAP];
-    __shared__ int ctl[SEED_PLAN_WARPS][2];
-    __shared__ __align__(16) uint8_t qs[SEED_PLAN_WARPS][256];
-    const int w = threadIdx.x >> 5;
-    const int slot = blockIdx.x * SEED_PLAN_WARPS + w;
-    if (slot < p.numReads) seed_plan_read<CAP, CoopWarp>(p, slot, E[w], ctl[w], qs[w]);
+__global__ void __launch_bounds__(SEED_PLAN_THREADS) seed_plan_kernel(const SeedPlanParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    int* E = reinterpret_cast<int*>(smemRaw);              // [groups][CAP]
+    int* ctl = E + SEED_PLAN_GROUPS * CAP;                  // [groups][2]
+    const int g = threadIdx.x >> 3;
+    const int slot = blockIdx.x * SEED_PLAN_GROUPS + g;
+    if (slot < p.numReads) seed_plan_read<CAP, CoopGroup8>(p, slot, E + g * CAP, ctl + g * 2);
 }
 __global__ void win_reduce_kernel(const WinReduceParams p) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -507,11 +539,28 @@ struct CudaBackend : Backend {
 
 
     int deviceId = 0;
+    int numaNode = -1;   // NUMA node of the device's PCIe root (pinned staging memory is placed there)
+
+    int numa_node() override { return numaNode; }
 
     CudaBackend() {
         int dev = 0;
         EB_CUDA(cudaGetDevice(&dev));
         deviceId = dev;
+        {
+            char bus[32] = {0};
+            if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) == cudaSuccess) {
+                for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+                const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+                if (FILE* f = fopen(path.c_str(), "r")) {
+                    int node = -1;
+                    if (fscanf(f, "%d", &node) == 1) numaNode = node;
+                    fclose(f);
+                }
+            }
+            const char* e = getenv("EDLIB_B200_NUMA");
+            if (e && atoi(e) == 0) numaNode = -1;
+        }
         cudaDeviceProp prop;
         EB_CUDA(cudaGetDeviceProperties(&prop, dev));
         sms = prop.multiProcessorCount;
@@ -591,7 +640,9 @@ struct CudaBackend : Backend {
         bool used;
     };
     std::vector<HostBlock> hostBlocks;
+    std::mutex hostMu;
     void* alloc_host(size_t bytes) override {
+        std::lock_guard<std::mutex> lock(hostMu);
         HostBlock* fit = nullptr;  // best fit among the cached blocks
         for (auto& b : hostBlocks)
             if (!b.used && b.bytes >= bytes && (!fit || b.bytes < fit->bytes)) fit = &b;
@@ -607,11 +658,21 @@ struct CudaBackend : Backend {
             }
         void* p = nullptr;
         const size_t want = bytes + bytes / 4 + 4096;
-        EB_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        // the pages are faulted in by this thread inside cudaHostAlloc: prefer the GPU's NUMA node for them
+        // (set_mempolicy MPOL_PREFERRED for the duration of the call; best effort)
+        bool policy = false;
+        if (numaNode >= 0 && numaNode < 64) {
+            unsigned long mask = 1ul << numaNode;
+            policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
+        }
+        const cudaError_t err = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+        EB_CUDA(err);
         hostBlocks.push_back(HostBlock{p, want, true});
         return p;
     }
     void free_host(void* p) override {
+        std::lock_guard<std::mutex> lock(hostMu);
         for (auto& b : hostBlocks)
             if (b.p == p) b.used = false;
     }
@@ -724,7 +785,8 @@ struct CudaBackend : Backend {
             *residentCtas = shapeCache[key] >> 12;
             return;
         }
-        if (smem > (size_t)maxSmemOptin) {  // Peq rows of even a 32-thread CTA do not fit: not a K1 case
+        // (the window kernel keeps NW + 4 words per row: it must fit too, with 32-thread CTAs at least)
+        if (smem > (size_t)maxSmemOptin || (size_t)ncodes * 4 * (nw + 4) * 32 > (size_t)maxSmemOptin) {  // not a K1 case
             *blockThreads = block;
             *residentCtas = 0;
             return;
@@ -785,7 +847,7 @@ struct CudaBackend : Backend {
     template <int NW>
     void launch_k1w_t(const K1WParams& p) {
         int block = 128;
-        const size_t perThread = (size_t)p.ncodes * (16 + 4 * (NW > 4 ? NW - 4 : 0));
+        const size_t perThread = (size_t)p.ncodes * 4 * (NW + 4);
         while (block > 32 && perThread * block > 96 * 1024) block >>= 1;
         const size_t smem = perThread * block;
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1W: alphabet too large for shared memory");
@@ -890,10 +952,16 @@ struct CudaBackend : Backend {
     }
     void launch_seed_plan(const SeedPlanParams& p) override {
         Scope s(this, "seed_plan");
-        const int grid = (p.numReads + SEED_PLAN_WARPS - 1) / SEED_PLAN_WARPS;
-        if (p.level <= 0) seed_plan_kernel<SEED_CAND_0><<<grid, SEED_PLAN_WARPS * 32, 0, stream>>>(p);
-        else if (p.level == 1) seed_plan_kernel<SEED_CAND_1><<<grid, SEED_PLAN_WARPS * 32, 0, stream>>>(p);
-        else seed_plan_kernel<SEED_CAND_2><<<grid, SEED_PLAN_WARPS * 32, 0, stream>>>(p);
+        const int grid = (p.numReads + SEED_PLAN_GROUPS - 1) / SEED_PLAN_GROUPS;
+        auto smem_of = [](int cap) { return (size_t)SEED_PLAN_GROUPS * ((size_t)cap + 2) * sizeof(int); };
+        if (p.level <= 0) {
+            seed_plan_kernel<SEED_CAND_0><<<grid, SEED_PLAN_THREADS, smem_of(SEED_CAND_0), stream>>>(p);
+        } else if (p.level == 1) {
+            seed_plan_kernel<SEED_CAND_1><<<grid, SEED_PLAN_THREADS, smem_of(SEED_CAND_1), stream>>>(p);
+        } else {
+            EB_CUDA(cudaFuncSetAttribute(seed_plan_kernel<SEED_CAND_2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(SEED_CAND_2)));
+            seed_plan_kernel<SEED_CAND_2><<<grid, SEED_PLAN_THREADS, smem_of(SEED_CAND_2), stream>>>(p);
+        }
         check_launch("seed_plan");
     }
     void launch_fin_count(const FinParams& p) override {

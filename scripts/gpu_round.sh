@@ -1,0 +1,34 @@
+#!/bin/bash
+# One evidence run on a B200 (gpurun -- 'bash scripts/gpu_round.sh <tag> [stages]'); stages: smoke tests bench trace launches ncu ref stress
+TAG=${1:-r02a}
+STAGES=${2:-"smoke tests bench trace launches ncu"}
+OUT=gpurun_out; mkdir -p $OUT
+has() { [[ " $STAGES " == *" $1 "* ]]; }
+if has smoke; then echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2; fi
+if has tests; then echo "== pytest gpu"; timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -6; fi
+if has bench; then
+  echo "== bench (default flags)"; timeout 1200 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "rc=$?"; cut -c1-3000 $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
+fi
+if has trace; then
+  echo "== host-phase trace"
+  EDLIB_B200_TRACE=1 timeout 600 python bench.py --steps 1 --warmup 2 --e2e-steps 2 --no-cpu-baseline --no-sweep-sample --no-extras > $OUT/trace_$TAG.txt 2>&1; grep -v "^{" $OUT/trace_$TAG.txt | tail -60 | cut -c1-160
+fi
+if has launches; then
+  echo "== ncu launch list of the bench command (1 step, 1 warm-up)"
+  timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$TAG.csv \
+      python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --no-sweep-sample --no-extras > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu rc=$?"
+  python scripts/step_traffic.py $OUT/launches_$TAG.csv 1000000 $OUT/step_traffic_$TAG.json
+fi
+if has ncu; then
+  for K in ${NCU_KERNELS:-k1w_kernel seed_plan_kernel}; do
+    echo "== ncu --set full: $K"
+    timeout 900 ncu --set full --import-source on --clock-control none -k regex:$K -s ${NCU_SKIP:-4} -c 1 -f -o $OUT/ncu_${TAG}_$K \
+        python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --no-sweep-sample --no-extras > $OUT/ncu_${TAG}_$K.log 2>&1; echo "rc=$?"
+    ncu -i $OUT/ncu_${TAG}_$K.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_${K}_raw.csv 2>/dev/null
+  done
+fi
+if has ref; then echo "== bench --impl reference"; timeout 900 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; cut -c1-400 $OUT/bench_ref_$TAG.json; fi
+if has stress; then
+  echo "== stress (filter forced on for small targets)"
+  EDLIB_B200_FILTER_MIN_TARGET=128 EDLIB_B200_K1_MIN_GROUP=4 EDLIB_B200_STREAM_MIN_PAIRS=64 timeout 900 python scripts/stress.py ${STRESS_MIN:-3} 2>&1 | tail -2 | tee $OUT/stress_$TAG.txt
+fi

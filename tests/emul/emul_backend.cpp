@@ -40,6 +40,7 @@ template <int NW>
 struct HostPeqAcc {
     std::vector<uint32_t> w;
     void store(int code, int word, uint32_t bits) { w[(size_t)code * NW + word] = bits; }
+    void or_word(int code, int word, uint32_t bits) { w[(size_t)code * NW + word] |= bits; }
     void load(uint32_t code, uint32_t (&Eq)[NW]) const {
         for (int i = 0; i < NW; ++i) Eq[i] = w[(size_t)code * NW + i];
     }
@@ -53,10 +54,20 @@ void emul_k1(const K1Params& p) {
         for (int slot = 0; slot < p.numReads; ++slot) k1_thread<NW>(p, slot, chunk, acc);
 }
 
+// Word-addressable rows of NW + 4 words (K1W: banded and full sweeps share one profile).
+struct HostWordAcc {
+    std::vector<uint32_t> w;
+    int words;
+    void store_word(int code, int word, uint32_t bits) { w[(size_t)code * words + word] = bits; }
+    void or_word(int code, int word, uint32_t bits) { w[(size_t)code * words + word] |= bits; }
+    uint32_t load_word(uint32_t code, int word) const { return w[(size_t)code * words + word]; }
+};
+
 template <int NW>
 void emul_k1w(const K1WParams& p) {
-    HostPeqAcc<NW> acc;
-    acc.w.assign((size_t)p.ncodes * NW, 0);
+    HostWordAcc acc;
+    acc.words = NW + 4;
+    acc.w.assign((size_t)p.ncodes * (NW + 4), 0xdeadbeefu);
     const int numJobs = p.countPtr ? std::min(p.numReads, *p.countPtr) : p.numReads;
     for (int slot = 0; slot < numJobs; ++slot) k1w_thread<NW>(p, slot, acc);
 }
@@ -133,11 +144,10 @@ struct EmulBackend : Backend {
         ++launchesCount;
         std::vector<int> E(SEED_CAND_2);
         int ctl[2];
-        uint8_t qs[256];
         for (int i = p.numReads - 1; i >= 0; --i) {
-            if (p.level <= 0) seed_plan_read<SEED_CAND_0, CoopSerial>(p, i, E.data(), ctl, qs);
-            else if (p.level == 1) seed_plan_read<SEED_CAND_1, CoopSerial>(p, i, E.data(), ctl, qs);
-            else seed_plan_read<SEED_CAND_2, CoopSerial>(p, i, E.data(), ctl, qs);
+            if (p.level <= 0) seed_plan_read<SEED_CAND_0, CoopSerial>(p, i, E.data(), ctl);
+            else if (p.level == 1) seed_plan_read<SEED_CAND_1, CoopSerial>(p, i, E.data(), ctl);
+            else seed_plan_read<SEED_CAND_2, CoopSerial>(p, i, E.data(), ctl);
         }
     }
     void launch_fin_count(const FinParams& p) override {
