@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -17,6 +19,7 @@
 #include "eb_engine.h"
 
 namespace eb {
+void host_parallel_ranges(size_t n, size_t grain, const std::function<void(size_t, size_t)>& fn);  // eb_engine.cpp
 Backend* create_backend(std::string* err);  // provided by the backend object linked into this library
 int select_device(int device, std::string* err);  // 0 on success
 }
@@ -237,6 +240,27 @@ EDLIB_API int edlibB200BatchResults(EdlibB200Batch* batch, EdlibAlignResult* res
 EDLIB_API void edlibB200BatchFree(EdlibB200Batch* batch) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (batch && engine_locked()) g_engine->release(reinterpret_cast<eb::Prepared*>(batch));
+}
+
+EDLIB_API int edlibB200AlignmentsToCigar(const EdlibAlignResult* results, int n, EdlibCigarFormat cigarFormat, char** cigars) {
+    if (n < 0 || (n > 0 && (!results || !cigars))) return EDLIB_STATUS_ERROR;
+    if (cigarFormat != EDLIB_CIGAR_EXTENDED && cigarFormat != EDLIB_CIGAR_STANDARD) return EDLIB_STATUS_ERROR;
+    std::lock_guard<std::mutex> lock(g_mu);  // the host pool serves one client at a time
+    std::atomic<int> bad(0);
+    eb::host_parallel_ranges((size_t)n, 4096, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            cigars[i] = NULL;
+            if (!results[i].alignment || results[i].alignmentLength <= 0) continue;
+            cigars[i] = edlibAlignmentToCigar(results[i].alignment, results[i].alignmentLength, cigarFormat);
+            if (!cigars[i]) bad.store(1, std::memory_order_relaxed);
+        }
+    });
+    if (!bad.load()) return EDLIB_STATUS_OK;
+    for (int i = 0; i < n; ++i) {
+        free(cigars[i]);
+        cigars[i] = NULL;
+    }
+    return EDLIB_STATUS_ERROR;
 }
 
 EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {

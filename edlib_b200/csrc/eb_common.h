@@ -101,6 +101,7 @@ struct K1WParams {
     const int* trackFrom;    // [numReads] first column (relative to winStart) whose score may be recorded
     int numReads;
     const int* countPtr;     // device-planned jobs: the number of jobs is min(*countPtr, numReads); or nullptr
+    int checkAfter;          // banded sweeps: columns past the last possible start after which a hopeless window is left (-1: never)
     int ncodes;
     const uint8_t* eqtab;
     WinRec* recs;            // [numReads]; positions are absolute target columns

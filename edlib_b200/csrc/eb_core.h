@@ -544,40 +544,74 @@ struct K1View {
 // profile); rows below it carry Eq = 0 and influence nothing above them.  The score of the window's bottom
 // cell is carried along (S += 1 - HN[63]); the last-row score at a tracked column is S minus the vertical
 // deltas between the last row and the bottom (two popcounts).
+// 16 target symbols at once (the device reads them as one 128-bit load; windows start at multiples of 16 symbols
+// of a 16-byte aligned target with >= 16 bytes of slack behind it).
+struct Sym16 {
+    uint32_t w[4];
+};
+EB_HD Sym16 load_sym16(const uint8_t* p) {
+    Sym16 v;
+#if defined(__CUDA_ARCH__)
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
+    v.w[0] = x.x;
+    v.w[1] = x.y;
+    v.w[2] = x.z;
+    v.w[3] = x.w;
+#else
+    for (int k = 0; k < 4; ++k)
+        v.w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
+#endif
+    return v;
+}
+
+// State of one banded sweep (see k1b_sweep) and its column step.
 template <class WAcc, class RecT>
-EB_HD void k1b_sweep(const WAcc& acc, const uint8_t* tsyms, int ws, int m, int off, int c0, int lo, int hi, int t,
-                     int& bestIo, int& cntIo, RecT* rec) {
-    constexpr int CAP = (int)(sizeof(rec->pos) / sizeof(rec->pos[0]));
-    const int dhi = hi - (m - 1) + t;
-    const int g0 = off + 64 - dhi;           // global profile bit of the window's top row at column 0 (>= 0 from c0 on)
-    // state before column c0: D[r][c0-1] = r + 1 on the rows of the query, 0 above it
-    const int gt0 = c0 + g0;                 // profile bit of the top row
-    const int firstReal = off + 64 - gt0;    // window bit of query row 0 (may be <= 0 or >= 64)
-    uint64_t vp64 = firstReal <= 0 ? ~0ull : (firstReal >= 64 ? 0ull : (~0ull << firstReal));
-    uint32_t VP0 = (uint32_t)vp64, VP1 = (uint32_t)(vp64 >> 32), VN0 = 0, VN1 = 0;
-    const int bottomRow = c0 - dhi + 63;
-    int S = bottomRow >= 0 ? bottomRow + 1 : 0;
-    int best = bestIo, cnt = cntIo;
-    for (int j = c0; j <= hi; ++j) {
-        const uint32_t sym = tsyms[j];
+struct K1Band {
+    const WAcc& acc;
+    RecT* rec;
+    uint32_t VP0, VP1, VN0, VN1;
+    int S;          // score of the window's bottom cell
+    int best, cnt;
+    int g0;         // profile bit of the window's top row at column 0
+    int lo;         // first tracked column
+    int kb0;        // window bit of the last query row at column 0 (frame of the following column): kb = kb0 - j
+    int ws;         // absolute column of window column 0
+
+    // Smallest value among the cells of the column just swept that lie in the current frame (the window of the
+    // next column): D of the bottom cell is S, the vertical deltas lead upwards from there.
+    EB_HD int window_min() const {
+        int cur = S, mn = S;
+        for (int k = 31; k >= 0; --k) {
+            cur += (int)((VN1 >> k) & 1u) - (int)((VP1 >> k) & 1u);
+            mn = cur < mn ? cur : mn;
+        }
+        for (int k = 31; k >= 1; --k) {
+            cur += (int)((VN0 >> k) & 1u) - (int)((VP0 >> k) & 1u);
+            mn = cur < mn ? cur : mn;
+        }
+        return mn;
+    }
+
+    template <bool TRACK>
+    EB_HD void column(int j, uint32_t sym) {
         const int gt = j + g0;
         const int wi = gt >> 5, sh = gt & 31;
         const uint32_t w0 = acc.load_word(sym, wi), w1 = acc.load_word(sym, wi + 1), w2 = acc.load_word(sym, wi + 2);
         const uint32_t Eq0 = funnel_r(w0, w1, sh), Eq1 = funnel_r(w1, w2, sh);
-        const uint32_t T0 = Eq0 & VP0, T1 = Eq1 & VP1;
-        const uint32_t S0 = T0 + VP0;
-        const uint32_t S1 = T1 + VP1 + (S0 < T0 ? 1u : 0u);
-        const uint32_t D00 = ((S0 ^ VP0) | Eq0) | VN0, D01 = ((S1 ^ VP1) | Eq1) | VN1;
+        uint32_t T[2] = {Eq0 & VP0, Eq1 & VP1}, P[2] = {VP0, VP1}, Sm[2];
+        AddChain<2>::run(Sm, T, P);
+        const uint32_t D00 = ((Sm[0] ^ VP0) | Eq0) | VN0, D01 = ((Sm[1] ^ VP1) | Eq1) | VN1;
         const uint32_t HP0 = VN0 | ~(D00 | VP0), HP1 = VN1 | ~(D01 | VP1);
         const uint32_t HN0 = VP0 & D00, HN1 = VP1 & D01;
-        const uint32_t X0 = (D00 >> 1) | (D01 << 31), X1 = D01 >> 1;
+        const uint32_t X0 = funnel_r(D00, D01, 1), X1 = D01 >> 1;
         VN0 = X0 & HP0;
         VN1 = X1 & HP1;
         VP0 = HN0 | ~(X0 | HP0);
         VP1 = HN1 | ~(X1 | HP1);
         S += 1 - (int)(HN1 >> 31);
-        if (j >= lo) {
-            const int kb = m - 2 - j + dhi;  // window bit (frame of column j+1) of the last query row: 0..63
+        if (TRACK && j >= lo) {
+            constexpr int CAP = (int)(sizeof(rec->pos) / sizeof(rec->pos[0]));
+            const int kb = kb0 - j;  // 0..63
             const uint64_t M = kb >= 63 ? 0ull : (~0ull << (kb + 1));
             const int score = S - popcount32(VP0 & (uint32_t)M) - popcount32(VP1 & (uint32_t)(M >> 32)) +
                               popcount32(VN0 & (uint32_t)M) + popcount32(VN1 & (uint32_t)(M >> 32));
@@ -592,8 +626,50 @@ EB_HD void k1b_sweep(const WAcc& acc, const uint8_t* tsyms, int ws, int m, int o
             }
         }
     }
-    bestIo = best;
-    cntIo = cnt;
+};
+
+// Hopeless windows (most windows come from chance seed hits) are left early: from column dhi on every alignment
+// with <= t edits that ends at a tracked column has begun and crosses each column inside the window, at a cost
+// that is at least the banded value of the cell it crosses (the banded values are the cheapest in-band paths); so
+// once every cell of a column is above t no tracked column can score <= t.  Checked once, `checkAfter` columns
+// past dhi (by then the rows in the window are deep enough for an unrelated read to have left t behind).
+template <class WAcc, class RecT>
+EB_HD void k1b_sweep(const WAcc& acc, const uint8_t* tsyms, int ws, int m, int off, int c0, int lo, int hi, int t,
+                     int checkAfter, int& bestIo, int& cntIo, RecT* rec) {
+    const int dhi = hi - (m - 1) + t;
+    K1Band<WAcc, RecT> b{acc, rec, 0, 0, 0, 0, 0, bestIo, cntIo, off + 64 - dhi, lo, m - 2 + dhi, ws};
+    // state before column c0: D[r][c0-1] = r + 1 on the rows of the query, 0 above it
+    const int firstReal = off + 64 - (c0 + b.g0);  // window bit of query row 0 (may be <= 0 or >= 64)
+    const uint64_t vp64 = firstReal <= 0 ? ~0ull : (firstReal >= 64 ? 0ull : (~0ull << firstReal));
+    b.VP0 = (uint32_t)vp64;
+    b.VP1 = (uint32_t)(vp64 >> 32);
+    const int bottomRow = c0 - dhi + 63;
+    b.S = bottomRow >= 0 ? bottomRow + 1 : 0;
+    int j = c0;
+    for (; j <= hi && (j & 15); ++j) b.template column<true>(j, tsyms[j]);  // up to the next multiple of 16
+    if (j + 15 <= hi) {
+        Sym16 v = load_sym16(tsyms + j);
+        bool checked = checkAfter < 0;
+        for (; j + 15 < lo; j += 16) {  // lead-in groups: no column of them is tracked
+            if (!checked && j >= dhi + checkAfter) {
+                checked = true;
+                if (b.window_min() > t) return;  // nothing recorded: the window holds no score <= t
+            }
+            const Sym16 cur = v;
+            if (j + 31 <= hi) v = load_sym16(tsyms + j + 16);  // in flight while the 16 columns below are computed
+            EB_UNROLL
+            for (int q = 0; q < 16; ++q) b.template column<false>(j + q, (cur.w[q >> 2] >> (8 * (q & 3))) & 255u);
+        }
+        for (; j + 15 <= hi; j += 16) {
+            const Sym16 cur = v;
+            if (j + 31 <= hi) v = load_sym16(tsyms + j + 16);
+            EB_UNROLL
+            for (int q = 0; q < 16; ++q) b.template column<true>(j + q, (cur.w[q >> 2] >> (8 * (q & 3))) & 255u);
+        }
+    }
+    for (; j <= hi; ++j) b.template column<true>(j, tsyms[j]);
+    bestIo = b.best;
+    cntIo = b.cnt;
 }
 
 // One K1W work item: the whole query over its own target window (each lane walks its own window; the target is
@@ -622,7 +698,7 @@ EB_HD void k1w_thread(const K1WParams& p, int slot, WAcc& acc) {
         // at a multiple of 16), or the start of the target
         const int c0 = tf - (m + t) > 0 ? tf - (m + t) : 0;
         int best = kInit, cnt = 0;
-        k1b_sweep(acc, p.tcodes + ws, ws, m, 32 * NW - m, c0, tf, hi, t, best, cnt, rec);
+        k1b_sweep(acc, p.tcodes + ws, ws, m, 32 * NW - m, c0, tf, hi, t, p.checkAfter, best, cnt, rec);
         rec->best = best;
         rec->cnt = cnt;
         return;

@@ -60,6 +60,11 @@ void HostPool::bind_worker() {
     if (n > 0) sched_setaffinity(0, sizeof(want), &want);  // best effort
 }
 
+// parallel_ranges for the translation units that do not see the pool (eb_capi.cpp)
+void host_parallel_ranges(size_t n, size_t grain, const std::function<void(size_t, size_t)>& fn) {
+    parallel_ranges(n, grain, [&](size_t lo, size_t hi) { fn(lo, hi); });
+}
+
 // The host workers of the engine run next to the GPU (EDLIB_B200_NUMA=0 leaves them where the caller runs); the
 // calling thread itself is never moved.
 Engine::Engine(Backend* be) : be_(be) {
@@ -88,6 +93,7 @@ EngineTunables::EngineTunables() {
     filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
     filterMinTarget = env_int("EDLIB_B200_FILTER_MIN_TARGET", filterMinTarget);
     deviceStage = env_int("EDLIB_B200_DEVICE_STAGE", deviceStage);
+    windowCheckAfter = env_int("EDLIB_B200_WINDOW_CHECK", windowCheckAfter);
     devSliceReads = std::max(64, env_int("EDLIB_B200_SLICE_READS", devSliceReads));
     streamMinPairs = env_int("EDLIB_B200_STREAM_MIN_PAIRS", streamMinPairs);
     const int sliceMb = env_int("EDLIB_B200_SLICE_MB", 0);

@@ -102,6 +102,7 @@ struct EngineTunables {
     int deviceStage = 1;          // first seed level driven by the device (0: every stage host-driven)
     int devSliceReads = 1 << 20;  // reads per slice of the device-driven level (streamed batches: at least four slices)
     int streamMinPairs = 32768;   // smallest one-target HW batch that edlibAlignBatch streams (upload under compute)
+    int windowCheckAfter = 48;    // banded window sweeps: see K1WParams::checkAfter (-1 disables the early exit)
     int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 32;    // seed stage: longest hash bucket looked at (longer: repeat, read passed on)
     int filterSeedLevels = 3;     // seed stage: levels tried (seed length L, L-2, L-4 for DNA; at most SEED_LEVELS)

@@ -260,12 +260,13 @@ __global__ void k1_kernel(const K1Params p) {
     }
 }
 
-// Word-addressable per-thread profile rows for K1W: word w of code c of thread t at base + (c * words + w) *
-// 4 * nthreads + 4 * t -- consecutive threads in consecutive banks whatever word each of them reads.
+// Word-addressable per-thread profile rows for K1W: word w of code c of thread t at base + (c * WORDS + w) *
+// 4 * THREADS + 4 * t -- consecutive threads in consecutive banks whatever word each of them reads, and (CTA size
+// and row length being compile-time constants) every offset an immediate of the shared-memory instruction.
+template <int THREADS, int WORDS>
 struct SmemWordAcc {
-    uint32_t base;        // shared address of this thread's word 0 of code 0
-    uint32_t wordStride;  // bytes between consecutive words of a row (4 * nthreads)
-    uint32_t codeStride;  // bytes between rows
+    uint32_t base;  // shared address of this thread's word 0 of code 0
+    static constexpr uint32_t wordStride = 4u * THREADS, codeStride = wordStride * WORDS;
     EB_D void store_word(int code, int w, uint32_t bits) {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + (uint32_t)code * codeStride + (uint32_t)w * wordStride), "r"(bits) : "memory");
     }
@@ -284,16 +285,14 @@ struct SmemWordAcc {
 
 // K1W: every thread over its own target window read through the generic (global) pointer path; no tile
 // staging, no barriers.  Banded sweep for windows that span few diagonals, full sweep otherwise (eb_core.h).
-template <int NW>
-__global__ void k1w_kernel(const K1WParams p) {
+template <int NW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k1w_kernel(const K1WParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = blockIdx.x * THREADS + threadIdx.x;
     int numJobs = p.numReads;
     if (p.countPtr) numJobs = min(numJobs, *p.countPtr);  // jobs planned on the device (seed_plan_kernel)
     if (slot >= numJobs) return;
-    SmemWordAcc acc;
-    acc.wordStride = 4u * blockDim.x;
-    acc.codeStride = (uint32_t)(NW + 4) * acc.wordStride;
+    SmemWordAcc<THREADS, NW + 4> acc;
     acc.base = smem_u32(smem) + 4u * threadIdx.x;
     k1w_thread<NW>(p, slot, acc);
 }
@@ -844,6 +843,11 @@ struct CudaBackend : Backend {
             default: throw std::runtime_error("bad K1 word class");
         }
     }
+    template <int NW, int THREADS>
+    void launch_k1w_b(const K1WParams& p, size_t smem) {
+        EB_CUDA(cudaFuncSetAttribute(k1w_kernel<NW, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1w_kernel<NW, THREADS><<<(p.numReads + THREADS - 1) / THREADS, THREADS, smem, stream>>>(p);
+    }
     template <int NW>
     void launch_k1w_t(const K1WParams& p) {
         int block = 128;
@@ -851,8 +855,9 @@ struct CudaBackend : Backend {
         while (block > 32 && perThread * block > 96 * 1024) block >>= 1;
         const size_t smem = perThread * block;
         if (smem > (size_t)maxSmemOptin) throw std::runtime_error("K1W: alphabet too large for shared memory");
-        EB_CUDA(cudaFuncSetAttribute(k1w_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1w_kernel<NW><<<(p.numReads + block - 1) / block, block, smem, stream>>>(p);
+        if (block == 128) launch_k1w_b<NW, 128>(p, smem);
+        else if (block == 64) launch_k1w_b<NW, 64>(p, smem);
+        else launch_k1w_b<NW, 32>(p, smem);
         check_launch("k1w");
     }
     void launch_k1w(const K1WParams& p, int nw) override {

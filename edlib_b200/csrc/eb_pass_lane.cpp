@@ -362,6 +362,7 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
         wp.winLen = wLen.p;
         wp.trackFrom = wTf.p;
         wp.numReads = V;
+        wp.checkAfter = tun.windowCheckAfter;
         wp.ncodes = p->ncodes;
         wp.eqtab = nullptr;
         wp.recs = dWinRecs.p;
@@ -604,6 +605,7 @@ void Pass::prefix_stage(LaneGroup& c, int P, int K0, const std::vector<int>& in,
     wp.winLen = dLen.p;
     wp.trackFrom = dTf.p;
     wp.numReads = V;
+    wp.checkAfter = tun.windowCheckAfter;
     wp.ncodes = p->ncodes;
     wp.eqtab = p->hasEq ? p->dEqtab.p : nullptr;
     wp.recs = dRecs.p;
@@ -815,6 +817,7 @@ int Pass::dev_enqueue_slice(int t, int nw, int firstPair, const int* listHost, i
     wp.trackFrom = wTf.p;
     wp.numReads = cap;
     wp.countPtr = dCtr.p;
+    wp.checkAfter = tun.windowCheckAfter;
     wp.ncodes = p->ncodes;
     wp.eqtab = nullptr;
     wp.recs = dWinRecs.p;

@@ -24,17 +24,27 @@ void synth_dna(unsigned char* out, int64_t n, uint64_t seed) {
     }
 }
 
-/* out: nreads x readLen bytes.  Returns nothing; every read is exactly readLen long. */
+/* Reads [first, last) of the batch keyed by `seed` (read i only depends on (seed, i)): out holds (last - first) x
+ * readLen bytes; every read is exactly readLen long. */
+void synth_reads_range(const unsigned char* target, int64_t tlen, unsigned char* out, int64_t first, int64_t last, int readLen,
+                       double rate, uint64_t seed);
+
+/* out: nreads x readLen bytes: reads [0, nreads) of the batch. */
 void synth_reads(const unsigned char* target, int64_t tlen, unsigned char* out, int64_t nreads, int readLen,
                  double rate, uint64_t seed) {
+    synth_reads_range(target, tlen, out, 0, nreads, readLen, rate, seed);
+}
+
+void synth_reads_range(const unsigned char* target, int64_t tlen, unsigned char* out, int64_t first, int64_t last, int readLen,
+                       double rate, uint64_t seed) {
     const uint64_t thresh = (uint64_t)(rate * 18446744073709551615.0);
-    for (int64_t i = 0; i < nreads; ++i) {
+    for (int64_t i = first; i < last; ++i) {
         uint64_t s = (seed + 1) * 0x9E3779B97F4A7C15ull ^ ((uint64_t)i * 0xC2B2AE3D27D4EB4Full);
         s = splitmix(&s) ^ (uint64_t)i;          /* decorrelate neighbouring streams */
         int64_t span = tlen - readLen - 16;
         if (span < 1) span = 1;
         int64_t pos = (int64_t)(splitmix(&s) % (uint64_t)span);
-        unsigned char* o = out + i * readLen;
+        unsigned char* o = out + (i - first) * readLen;
         int len = 0;
         while (len < readLen) {
             unsigned char c = target[pos < tlen ? pos : tlen - 1];
@@ -75,4 +85,21 @@ int64_t synth_mutate(const unsigned char* src, int64_t n, unsigned char* out, do
         }
     }
     return len;
+}
+
+/* config 3 shape, pairs [i0, i1): query i = the `len` symbols of the genome at a seeded start, written to
+ * qbuf + i*len; target i = its mutated copy (same per-base events as the reads), written to tbuf + i*tstride with
+ * its length in tlens[i] (tstride >= 2*len). */
+void synth_pairs(const unsigned char* genome, int64_t glen, int64_t i0, int64_t i1, int len, double rate, uint64_t seed,
+                 unsigned char* qbuf, unsigned char* tbuf, int64_t tstride, int* tlens) {
+    for (int64_t i = i0; i < i1; ++i) {
+        uint64_t s = (seed + 3) * 0x9E3779B97F4A7C15ull ^ ((uint64_t)i * 0xC2B2AE3D27D4EB4Full);
+        s = splitmix(&s) ^ (uint64_t)i;
+        int64_t span = glen - len - 64;
+        if (span < 1) span = 1;
+        const int64_t start = (int64_t)(splitmix(&s) % (uint64_t)span);
+        unsigned char* q = qbuf + i * (int64_t)len;
+        for (int k = 0; k < len; ++k) q[k] = genome[start + k < glen ? start + k : glen - 1];
+        tlens[i] = (int)synth_mutate(q, len, tbuf + i * tstride, rate, seed * 1000003ull + (uint64_t)i);
+    }
 }

@@ -59,6 +59,11 @@ EDLIB_API int edlibB200BatchCompute(EdlibB200Batch* batch, EdlibB200Stats* stats
 EDLIB_API int edlibB200BatchResults(EdlibB200Batch* batch, EdlibAlignResult* results);
 EDLIB_API void edlibB200BatchFree(EdlibB200Batch* batch);
 
+/* edlibAlignmentToCigar (edlib.h) for n results at once, on the engine's host threads: cigars[i] receives a
+ * malloc'd C string (caller frees each with free()), or NULL where results[i] holds no alignment.  Returns
+ * EDLIB_STATUS_OK, or EDLIB_STATUS_ERROR on a bad format / operation code (then every cigars[i] is NULL). */
+EDLIB_API int edlibB200AlignmentsToCigar(const EdlibAlignResult* results, int n, EdlibCigarFormat cigarFormat, char** cigars);
+
 /* Stats of the most recent edlibAlign / edlibAlignBatch / BatchCompute on this process. */
 EDLIB_API void edlibB200LastStats(EdlibB200Stats* statsOut);
 
