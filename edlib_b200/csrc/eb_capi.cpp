@@ -210,6 +210,7 @@ EDLIB_API int edlibB200BatchCompute(EdlibB200Batch* batch, EdlibB200Stats* stats
         return EDLIB_STATUS_ERROR;
     }
     if (statsOut) {
+        e->finish_stats();
         statsOut->kernelMs = e->stats.kernelMs;
         statsOut->k1Ms = e->stats.k1Ms;
         statsOut->launches = e->stats.launches;
@@ -267,7 +268,8 @@ EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!s) return;
     memset(s, 0, sizeof(*s));
-    if (!g_engine) return;
+    if (!g_engine || !engine_locked()) return;
+    g_engine->finish_stats();
     s->kernelMs = g_engine->stats.kernelMs;
     s->k1Ms = g_engine->stats.k1Ms;
     s->launches = g_engine->stats.launches;
@@ -283,6 +285,7 @@ EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {
 EDLIB_API int edlibB200LastKernelReport(char* buf, int bufLen) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!buf || bufLen <= 0) return 0;
+    if (g_engine && engine_locked()) g_engine->finish_stats();
     const std::string r = g_engine ? g_engine->stats.kernelReport : std::string();
     const int n = (int)std::min<size_t>(r.size(), (size_t)bufLen - 1);
     memcpy(buf, r.data(), (size_t)n);

@@ -573,11 +573,19 @@ void Engine::compute(Prepared* p) {
     trace.mark("compute: starts + paths");
     be->sync_all();
     be->release_marks();
-    stats.kernelMs = be->kernel_ms(nullptr);
-    stats.k1Ms = be->kernel_ms("k1") + be->kernel_ms("k1_prefix");
-    stats.kernelReport = be->kernel_report();
     stats.launches = be->launches();
+    statsPending_ = true;  // the per-kernel device times are read from their events when somebody asks (finish_stats)
     p->computed = true;
+}
+
+// Device times of the last pass from the CUDA events around its launches: a few hundred event queries, so they are
+// only made when the caller asks for statistics, not inside every call.
+void Engine::finish_stats() {
+    if (!statsPending_) return;
+    statsPending_ = false;
+    stats.kernelMs = be_->kernel_ms(nullptr);
+    stats.k1Ms = be_->kernel_ms("k1") + be_->kernel_ms("k1_prefix");
+    stats.kernelReport = be_->kernel_report();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -681,6 +689,7 @@ Engine::~Engine() { delete spare_; }
 int Engine::align_batch(const BatchInput& in, EdlibAlignResult* results) {
     Prepared* p = nullptr;
     stats = EngineStats();
+    statsPending_ = false;
     bool built = false;  // results[] holds malloc'd arrays
     try {
         if (align_streamed(in, results)) return EDLIB_STATUS_OK;
@@ -1067,10 +1076,8 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
         ps.paths();
         be->sync_all();
         be->release_marks();
-        stats.kernelMs = be->kernel_ms(nullptr);
-        stats.k1Ms = be->kernel_ms("k1") + be->kernel_ms("k1_prefix");
-        stats.kernelReport = be->kernel_report();
         stats.launches = be->launches();
+        statsPending_ = true;
         p->computed = true;
         if (matInJob) {
             std::atomic<int> failed(0);

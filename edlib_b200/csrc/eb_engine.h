@@ -154,6 +154,8 @@ public:
     // false when the batch is not of that shape (nothing done), throws on failure.
     bool align_streamed(const BatchInput& in, EdlibAlignResult* results);
 
+    void finish_stats();  // fills the device-time fields of `stats` for the last pass (on demand)
+
     EngineTunables tun;
     EngineStats stats;
     EngineScratch scratch;
@@ -162,6 +164,7 @@ public:
 private:
     Backend* be_;
     Prepared* spare_ = nullptr;  // released batch object whose host vectors the next prepare() reuses
+    bool statsPending_ = false;
 };
 
 }  // namespace eb

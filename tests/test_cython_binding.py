@@ -32,3 +32,14 @@ def test_reference_cython_binding_over_this_library(tmp_path):
     subprocess.run([sys.executable, "setup.py", "-q", "build_ext", "--inplace"], cwd=tmp_path, check=True, capture_output=True)
     out = subprocess.run([sys.executable, "test.py"], cwd=tmp_path, check=True, capture_output=True, text=True)
     assert "All tests passed!" in out.stdout, out.stdout[-400:]
+
+
+@pytest.mark.gpu
+def test_reference_cython_binding_over_the_cuda_library():
+    """The same binding built over the PRODUCT library (`make -C oracle pybinding`, prebuilt into the git-ignored
+    oracle/_ref/pybinding, which travels to the GPU box): the reference's own bindings/python/test.py on the GPU."""
+    d = os.path.join(REPO, "oracle", "_ref", "pybinding")
+    if not os.path.exists(os.path.join(d, "test.py")):
+        pytest.skip("reference binding was not built (no /root/reference where the snapshot was taken)")
+    out = subprocess.run([sys.executable, "test.py"], cwd=d, capture_output=True, text=True)
+    assert out.returncode == 0 and "All tests passed!" in out.stdout, (out.stdout[-400:], out.stderr[-400:])

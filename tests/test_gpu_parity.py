@@ -173,3 +173,59 @@ def test_config2_shape_sample(lib):
         assert res[i] == chk.align(qs[i], t, -1, 2, 0), i
     eds = np.array([r["editDistance"] for r in res])
     assert 2.0 < eds.mean() < 8.0
+
+
+def test_config3_shape_every_field(lib):
+    """BASELINE configs[2] shape: 10 kbp queries vs their 3 %-mutated copies, NW, k = 500, EDLIB_TASK_LOC -- 2,000 pairs,
+    every result field of every pair against the reference build."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from edlib_b200 import workloads
+    genome = workloads.random_dna(2_000_000, 9)
+    qbuf, tbuf, tlens = workloads.long_pairs_packed(genome, 2000, 10_000, seed=43)
+    qs = [qbuf[i].tobytes() for i in range(2000)]
+    ts = [tbuf[i, :tlens[i]].tobytes() for i in range(2000)]
+    st, res = lib.align_batch(qs, ts, 500, 0, 1)
+    assert st == 0
+    chk = parity.checker()
+    with ThreadPoolExecutor(16) as ex:
+        exp = list(ex.map(lambda i: chk.align(qs[i], ts[i], 500, 0, 1), range(2000)))
+    assert res == exp
+    eds = np.array([r["editDistance"] for r in res])
+    assert (eds >= 0).mean() > 0.99 and 200 < eds[eds >= 0].mean() < 400
+
+
+def test_config4_shape_every_field(lib):
+    """BASELINE configs[3] shape: 150 bp reads (3 % sub/ins/del) vs one shared target, HW, EDLIB_TASK_PATH -- 50,000 reads
+    through the streamed path, every field (alignment bytes included) of every 10th read against the reference build,
+    plus the batched CIGAR helper against edlibAlignmentToCigar of the reference."""
+    import ctypes as C
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    import bench
+    from edlib_b200 import workloads
+    from edlib_b200._ffi import AlignResult, make_config
+    target, reads = workloads.reads_vs_target(num_reads=50_000, read_len=150, target_len=200_000, seed=8)
+    qptr, qlen, tptr, tlen = bench.pointer_arrays(reads, target)
+    cfg, _ = make_config(-1, 2, 2)
+    res = np.zeros(len(reads), dtype=bench.RESULT_DTYPE)
+    assert lib.lib.edlibAlignBatch(bench.as_pp(qptr), bench.as_pi(qlen), bench.as_pp(tptr), bench.as_pi(tlen), len(reads), cfg,
+                                   C.cast(res.ctypes.data, C.POINTER(AlignResult))) == 0
+    cg = (C.c_void_p * len(reads))()
+    lib.lib.edlibB200AlignmentsToCigar.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    assert lib.lib.edlibB200AlignmentsToCigar(res.ctypes.data, len(reads), 1, cg) == 0
+    chk = parity.checker()
+    t = target.tobytes()
+    idx = list(range(0, len(reads), 10))
+    with ThreadPoolExecutor(16) as ex:
+        exp = list(ex.map(lambda i: chk.align(reads[i].tobytes(), t, -1, 2, 2), idx))
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    for i, e in zip(idx, exp):
+        assert bench.gpu_result_dict(res, i) == e, i
+        assert C.string_at(cg[i]).decode() == chk.cigar(e["alignment"]), i
+    for p in cg:
+        if p:
+            libc.free(p)
+    lib.lib.edlibB200FreeResults.argtypes = [C.c_void_p, C.c_int]
+    lib.lib.edlibB200FreeResults(res.ctypes.data, len(reads))
