@@ -94,6 +94,8 @@ EngineTunables::EngineTunables() {
     filterMinTarget = env_int("EDLIB_B200_FILTER_MIN_TARGET", filterMinTarget);
     deviceStage = env_int("EDLIB_B200_DEVICE_STAGE", deviceStage);
     windowCheckAfter = env_int("EDLIB_B200_WINDOW_CHECK", windowCheckAfter);
+    longHwMinTarget = env_int("EDLIB_B200_LONG_HW_MIN_TARGET", longHwMinTarget);
+    longSeedMaxK = env_int("EDLIB_B200_LONG_SEED_MAX_K", longSeedMaxK);
     devSliceReads = std::max(64, env_int("EDLIB_B200_SLICE_READS", devSliceReads));
     streamMinPairs = env_int("EDLIB_B200_STREAM_MIN_PAIRS", streamMinPairs);
     const int sliceMb = env_int("EDLIB_B200_SLICE_MB", 0);

@@ -102,6 +102,8 @@ struct EngineTunables {
     int deviceStage = 1;          // first seed level driven by the device (0: every stage host-driven)
     int devSliceReads = 1 << 20;  // reads per slice of the device-driven level (streamed batches: at least four slices)
     int streamMinPairs = 32768;   // smallest one-target HW batch that edlibAlignBatch streams (upload under compute)
+    int longHwMinTarget = 65536;  // HW, query > 256 rows: shortest target worth seeds / chunking (and >= 8 query lengths)
+    int longSeedMaxK = 512;       // ... largest seed threshold tried (thresholds double from 64)
     int windowCheckAfter = 48;    // banded window sweeps: see K1WParams::checkAfter (-1 disables the early exit)
     int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 32;    // seed stage: longest hash bucket looked at (longer: repeat, read passed on)

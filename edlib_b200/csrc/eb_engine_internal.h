@@ -302,6 +302,7 @@ struct WPlan {
 };
 
 WPlan plan_w(int m, int n, int mode, int kBound);
+WPlan plan_w_band(int m, long long height, int dhi);
 
 // ---------------------------------------------------------------------------------------------
 // Prepared batch
@@ -632,6 +633,9 @@ struct Pass {
 
     // Distance pass of everything else: one alignment per warp (or per thread with its own target).
     void warp_distance();
+    // HW sweeps of long queries (> 256 rows) over a long target: seed levels with doubling thresholds (windows swept
+    // by the warp kernel along their diagonals), then the target cut into chunks restarted 2m columns early.
+    void long_hw_distance(const std::vector<int>& pairs);
 
     // editDistance and endLocations from the sweep outcomes (ref cpp:219-225 and the -1 rule), appended to the
     // batch's end-location pool: of every pair (pairs == nullptr) or of the listed ones.

@@ -5,8 +5,255 @@
 
 namespace eb {
 
+// HW sweeps of long queries over a long target.  The reference keeps these cheap with its band (ref cpp:601-642:
+// only the blocks within k of the best diagonal are computed, k doubling from 64, cpp:199-217); here the same
+// doubling drives exact seed levels: with threshold t, t+1 disjoint seeds of the query are looked up in the index
+// of the target, and the whole query is swept over windows around the end columns their occurrences imply -- by
+// the warp kernel, its 1024*R-row window sliding down the <= (4t+1 + spread) diagonals that matter.  A query is
+// decided when a window holds a distance <= t.  What no level decides (distances above the largest threshold,
+// repeats) is swept over the whole target cut into chunks that restart 2m columns early (no HW path spans more
+// than 2m target symbols), so that even one query fills the machine.
+void Pass::long_hw_distance(const std::vector<int>& pairs) {
+    std::map<int, std::vector<int>> byTarget;
+    for (int pair : pairs) byTarget[p->tidx[pair]].push_back(pair);
+    for (auto& kv : byTarget) {
+        const int t = kv.first;
+        const Target& tg = p->tg[t];
+        const int n = tg.len;
+        const std::vector<int>& list = kv.second;
+        const int G = (int)list.size();
+        std::vector<int> bound(G), excl(G, -1), cur(G);
+        for (int s = 0; s < G; ++s) {
+            const int m = p->qlen[list[s]];
+            bound[s] = (k < 0 || k > m) ? m : k;
+            cur[s] = s;
+            stats.wCells += (long long)m * n;
+        }
+        auto decide = [&](int s, int b, int c, const std::vector<int>& positions) {
+            const int pair = list[s];
+            best[pair] = c > 0 ? b : 0x7fffffff;
+            cnt[pair] = c;
+            posStart[pair] = (long long)posPool.size();
+            posPool.insert(posPool.end(), positions.begin(), positions.end());
+            posLen[pair] = (int)positions.size();
+        };
+        // ---- seed levels with doubling thresholds ----
+        const bool seeds = !p->hasEq && tun.filterSeedK > 0 && tun.longSeedMaxK > 0 && n >= tun.filterMinTarget && seed_index(t) &&
+                           seedIdx->Ls[0] > 0;
+        std::vector<int> rest;  // reads for the chunked sweep
+        if (!seeds) {
+            rest.swap(cur);
+        }
+        for (int thrCap = 64; !cur.empty(); thrCap *= 2) {
+            const SeedIndex& sx = *seedIdx;
+            const int L = sx.Ls[0];
+            std::vector<int> in, rl, thr, top;
+            for (int s : cur) {
+                const int m = p->qlen[list[s]];
+                const int tp = std::min(std::min(bound[s], m / L - 1), tun.longSeedMaxK);
+                const int tt = std::min(tp, thrCap);
+                if (m >= 2 * L && tt > excl[s]) {
+                    in.push_back(s);
+                    rl.push_back(list[s]);
+                    thr.push_back(tt);
+                    top.push_back(tp);
+                } else {
+                    rest.push_back(s);  // no (higher) threshold this query can be given
+                }
+            }
+            cur.clear();
+            if (in.empty()) break;
+            const int g = (int)in.size();
+            DevBuf<int> dList(be, g), dThr(be, g), dCount(be, 1);
+            dList.upload(rl.data(), g);
+            dThr.upload(thr.data(), g);
+            DevBuf<SeedPlan> dPlan(be, g);
+            DevBuf<int> wPair, wK, wStart, wLen, wTf;
+            int cap = g * 64 + 1024, V = 0;
+            for (;;) {
+                wPair.alloc(be, cap);
+                wK.alloc(be, cap);
+                wStart.alloc(be, cap);
+                wLen.alloc(be, cap);
+                wTf.alloc(be, cap);
+                be->zero(dCount.p, sizeof(int));
+                SeedPlanParams sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.tcodes = p->dSeq.p + tg.off;
+                sp.n = n;
+                sp.qcodes = p->dSeq.p;
+                sp.qoff = p->dQoff.p;
+                sp.qlen = p->dQlen.p;
+                sp.readList = dList.p;
+                sp.thr = dThr.p;
+                sp.kBound = k;
+                sp.seedK = tun.longSeedMaxK;
+                sp.numReads = g;
+                sp.Ls = L;
+                sp.Lidx = sx.Lidx;
+                sp.sigma = sx.sigma;
+                sp.numKeys = sx.numKeys;
+                sp.bucketStart = sx.bucketStart.p;
+                sp.positions = sx.positions.p;
+                sp.maxBucket = tun.filterSeedBucket * 8;
+                sp.level = SEED_LEVELS - 1;  // the largest candidate capacity
+                sp.spread = tun.filterSpread;
+                sp.winPair = wPair.p;
+                sp.winK = wK.p;
+                sp.winStart = wStart.p;
+                sp.winLen = wLen.p;
+                sp.winTf = wTf.p;
+                sp.winCap = cap;
+                sp.winCount = dCount.p;
+                sp.plan = dPlan.p;
+                be->launch_seed_plan(sp);
+                dCount.download(&V, 1);
+                if (V <= cap) break;
+                cap = V;
+            }
+            std::vector<SeedPlan> plan(g);
+            dPlan.download(plan.data(), g);
+            std::vector<int> hStart(V), hLen(V), hTf(V);
+            if (V) {
+                wStart.download(hStart.data(), V);
+                wLen.download(hLen.data(), V);
+                wTf.download(hTf.data(), V);
+            }
+            stats.filterWindows += V;
+            stats.d2hBytes += 4 + 16LL * g + 12LL * V;
+            std::vector<WTask> tasks;
+            std::vector<int> taskFirst(g + 1, 0);
+            for (int i = 0; i < g; ++i) {
+                taskFirst[i] = (int)tasks.size();
+                if (plan[i].state != SEED_WINDOWS) continue;
+                const int pair = list[in[i]], m = p->qlen[pair], tt = thr[i];
+                for (int w = plan[i].first; w < plan[i].first + plan[i].count; ++w) {
+                    const int hi = hLen[w] - 1, lo = hTf[w];
+                    const int dhi = hi - (m - 1) + tt;
+                    const WPlan pl = plan_w_band(m, (long long)(hi - lo) + 2LL * tt + 1, dhi);
+                    WTask tk;
+                    tk.pair = pair;
+                    tk.qOff = p->qoff[pair];
+                    tk.tOff = tg.off + (uint64_t)hStart[w];
+                    tk.m = m;
+                    tk.n = hLen[w];
+                    tk.mode = MODE_HW;
+                    tk.flags = pl.slide ? WF_SLIDE : 0;
+                    tk.dhi = pl.dhi;
+                    tk.R = pl.R;
+                    tk.nWp = pl.nWp;
+                    tk.kInit = tt + 1;
+                    tk.trackFrom = lo;
+                    tk.tag = hStart[w];  // columns of the task are relative to the window
+                    tk.wantPositions = true;
+                    tasks.push_back(std::move(tk));
+                }
+            }
+            taskFirst[g] = (int)tasks.size();
+            runner.run(tasks);
+            if (trace.on)
+                fprintf(stderr, "[edlib_b200] long HW queries, seed threshold <= %d: %d queries, %d windows (%zu sliding)\n", thrCap, g, V,
+                        (size_t)std::count_if(tasks.begin(), tasks.end(), [](const WTask& x) { return (x.flags & WF_SLIDE) != 0; }));
+            for (int i = 0; i < g; ++i) {
+                const int s = in[i], tt = thr[i];
+                if (plan[i].state == SEED_SATURATED) {  // repeats / too many candidates: the chunked sweep takes it
+                    rest.push_back(s);
+                    continue;
+                }
+                int b = 0x7fffffff;
+                for (int q = taskFirst[i]; q < taskFirst[i + 1]; ++q)
+                    if (tasks[q].rec.cnt > 0 && tasks[q].rec.best < b) b = tasks[q].rec.best;
+                if (b <= tt) {
+                    std::vector<int> positions;
+                    for (int q = taskFirst[i]; q < taskFirst[i + 1]; ++q) {
+                        const WTask& tk = tasks[q];
+                        if (tk.rec.cnt <= 0 || tk.rec.best != b) continue;
+                        for (int x = 0; x < std::min(tk.rec.cnt, KPOS); ++x) positions.push_back(tk.tag + tk.rec.pos[x]);
+                        for (int x : tk.extra) positions.push_back(tk.tag + x);
+                    }
+                    decide(s, b, (int)positions.size(), positions);
+                    stats.filterDecided++;
+                    continue;
+                }
+                excl[s] = tt;  // no alignment within tt
+                if (tt == bound[s]) {
+                    decide(s, 0, 0, std::vector<int>());  // ... which is the caller's bound: final
+                    stats.filterDecided++;
+                } else if (top[i] > tt) {
+                    cur.push_back(s);  // next level: twice the threshold
+                } else {
+                    rest.push_back(s);
+                }
+            }
+        }
+        cur.swap(rest);
+        std::sort(cur.begin(), cur.end());
+        if (cur.empty()) continue;
+        // ---- chunked sweeps of the whole target ----
+        stats.filterFallback += (long long)cur.size();
+        std::vector<WTask> tasks;
+        std::vector<int> taskFirst(cur.size() + 1, 0);
+        const long long wantTasks = 4LL * be->sm_count() * 4;  // a few warps per SM sub-partition
+        for (size_t i = 0; i < cur.size(); ++i) {
+            taskFirst[i] = (int)tasks.size();
+            const int s = cur[i], pair = list[s], m = p->qlen[pair];
+            long long chunks = std::max<long long>(1, std::min<long long>(n / (6LL * m), (wantTasks + (long long)cur.size() - 1) / (long long)cur.size()));
+            const int chunkLen = (int)round_up((size_t)((n + chunks - 1) / chunks), 16);
+            for (long long cs = 0; cs < n; cs += chunkLen) {
+                const long long ce = std::min<long long>(cs + chunkLen, n);
+                const long long hs = std::max<long long>(0, cs - 2LL * m);
+                const WPlan pl = plan_w(m, (int)(ce - hs), MODE_HW, -1);
+                WTask tk;
+                tk.pair = pair;
+                tk.qOff = p->qoff[pair];
+                tk.tOff = tg.off + (uint64_t)hs;
+                tk.m = m;
+                tk.n = (int)(ce - hs);
+                tk.mode = MODE_HW;
+                tk.flags = 0;
+                tk.R = pl.R;
+                tk.nWp = pl.nWp;
+                tk.kInit = bound[s] + 1;
+                tk.trackFrom = (int)(cs - hs);
+                tk.tag = (int)hs;
+                tk.wantPositions = true;
+                tasks.push_back(std::move(tk));
+            }
+        }
+        taskFirst[cur.size()] = (int)tasks.size();
+        runner.run(tasks);
+        if (trace.on) fprintf(stderr, "[edlib_b200] long HW queries, chunked sweeps: %zu queries, %zu chunks\n", cur.size(), tasks.size());
+        for (size_t i = 0; i < cur.size(); ++i) {
+            int b = 0x7fffffff;
+            for (int q = taskFirst[i]; q < taskFirst[i + 1]; ++q)
+                if (tasks[q].rec.cnt > 0 && tasks[q].rec.best < b) b = tasks[q].rec.best;
+            std::vector<int> positions;
+            for (int q = taskFirst[i]; q < taskFirst[i + 1]; ++q) {
+                const WTask& tk = tasks[q];
+                if (tk.rec.cnt <= 0 || tk.rec.best != b) continue;
+                for (int x = 0; x < std::min(tk.rec.cnt, KPOS); ++x) positions.push_back(tk.tag + tk.rec.pos[x]);
+                for (int x : tk.extra) positions.push_back(tk.tag + x);
+            }
+            decide(cur[i], b, (int)positions.size(), positions);
+        }
+    }
+}
+
 // Distance pass of everything else: one alignment per warp (or per thread with its own target).
 void Pass::warp_distance() {
+    // ---- HW, long queries over long targets: seeds + chunks (long_hw_distance) ----
+    if (mode == MODE_HW) {
+        std::vector<int> longHw, rest;
+        for (int pair : wPairs) {
+            const int m = p->qlen[pair], n = p->tlen[pair];
+            if (m > 256 && n >= tun.longHwMinTarget && (long long)n >= 8LL * m) longHw.push_back(pair);
+            else rest.push_back(pair);
+        }
+        if (!longHw.empty()) {
+            long_hw_distance(longHw);
+            wPairs.swap(rest);
+        }
+    }
     // ---- W distance pass ------------------------------------------------------------------
     {
         std::vector<int> pending = wPairs;
@@ -28,13 +275,15 @@ void Pass::warp_distance() {
                         }
                     }
                 }
-                WPlan pl = plan_w(m, n, mode, bound);
+                // SHW: D[m-1][e] >= e + 1 - m, so columns beyond m + (largest accepted distance) hold no end location
+                const int nEff = mode == MODE_SHW ? (int)std::min<long long>(n, (long long)m + ((k < 0 || k > m) ? m : k)) : n;
+                WPlan pl = plan_w(m, nEff, mode, bound);
                 WTask t;
                 t.pair = pair;
                 t.qOff = p->qoff[pair];
                 t.tOff = p->tg[p->tidx[pair]].off;
                 t.m = m;
-                t.n = n;
+                t.n = nEff;
                 t.mode = mode;
                 t.flags = pl.slide ? WF_SLIDE : 0;
                 t.dhi = pl.dhi;

@@ -43,6 +43,23 @@ WPlan plan_w(int m, int n, int mode, int kBound) {
     return pl;
 }
 
+// Window shape of a W job whose cells of interest lie on `height` diagonals (an HW window sweep of a long query
+// around seed hits): one window sliding down those diagonals when it covers them, strips otherwise.
+WPlan plan_w_band(int m, long long height, int dhi) {
+    WPlan pl = plan_w(m, 0, MODE_HW, -1);
+    const int nW = ceil_div(m, 32);
+    if (nW <= 32) return pl;  // one fixed window holds every row
+    for (int R = 1; R <= 8; R *= 2) {
+        if (height + 32LL * R <= 1024LL * R && 64 * R <= nW) {
+            pl.R = R;
+            pl.slide = true;
+            pl.dhi = dhi;
+            return pl;
+        }
+    }
+    return pl;
+}
+
 size_t WRunner::task_bytes(const WTask& t) const {
     size_t b = (size_t)p->ncodes * t.nWp * 4 + sizeof(WJob) + sizeof(Rec);
     if (t.flags & WF_STORE) b += (size_t)t.n * t.nWp * 8 + (size_t)t.m + t.n + 64;

@@ -211,6 +211,45 @@ def stream_cases(seed, count):
         yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 3, 10, 40]), mode=2, task=(it + seed) % 3, eqs=None)
 
 
+def long_hw_cases(seed, count):
+    """HW batches of LONG queries (300 .. 2600 rows) over one long-ish target: the seed levels with doubling thresholds
+    (distances below and above 64 / 128), sliding warp windows, unrelated and heavily mutated queries (chunked sweeps
+    with 2m halos), repeats (saturated seeds, many end locations), queries hanging over the ends, bounded k; all
+    tasks.  The tests lower the target-length limits so that these small targets take the long-query path."""
+    rng = random.Random(seed)
+    for it in range(count):
+        alpha = rng.choice([b"ACGT", b"ACGT", b"ACGTN", b"ACDEFGHIKLMNPQRSTVWY"])
+        n = rng.choice([12000, 20000, 30000, 45000])
+        t = rand_seq(rng, n, alpha)
+        if rng.random() < 0.5:  # a long segment copied elsewhere (equal-score hits far apart), or a tandem stretch
+            if rng.random() < 0.6:
+                seg = t[500:500 + rng.choice([600, 1500])]
+                at = rng.randrange(3000, len(t))
+                t = t[:at] + seg + t[at:]
+            else:
+                unit = rand_seq(rng, rng.choice([7, 40]), alpha)
+                at = rng.randrange(0, len(t))
+                t = t[:at] + unit * (1200 // len(unit)) + t[at:]
+        qs = []
+        for _ in range(rng.choice([3, 6])):
+            L = rng.choice([300, 700, 1100, 1500, 2600, 3400])
+            r = rng.random()
+            if r < 0.65:
+                a = rng.randrange(0, len(t) - L - 50)
+                q = mutate(rng, t[a:a + L + 40], rng.choice([0, 0.01, 0.04, 0.08, 0.15]), alpha)[:L]
+            elif r < 0.75:
+                q = rand_seq(rng, L, alpha)
+            elif r < 0.85:
+                q = (rand_seq(rng, 30, alpha) + t[:L])[:L] if rng.random() < 0.5 else (t[len(t) - L + 30:] + rand_seq(rng, 30, alpha))[:L]
+            else:
+                a = rng.randrange(0, max(1, len(t) - L))
+                q = t[a:a + L]
+            if len(q) < L:
+                q = q + rand_seq(rng, L - len(q), alpha)
+            qs.append(q)
+        yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 30, 100, 400]), mode=2, task=(it + seed) % 3, eqs=None)
+
+
 def pairwise_cases(seed, count):
     """Batches of short queries each with its OWN target (pairwise comparison shape): the lane-per-
     alignment kernel with per-job targets, all modes and tasks, odd alphabets, equalities."""

@@ -110,6 +110,22 @@ def test_streamed_batches():
         assert "stream: slices enqueued" in out.stderr  # the streamed path really ran
 
 
+def test_long_queries_hw_over_long_targets():
+    """HW, queries above 256 rows over a long target: seed levels with doubling thresholds + sliding warp windows, then
+    chunked sweeps with 2m halos (eb_pass_results.cpp: long_hw_distance); limits lowered so that small targets take it.
+    Also with seeds off (chunks only) and with a tiny seed-threshold cap."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 41, 9, gen=cases.long_hw_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra in ({}, {"EDLIB_B200_LONG_SEED_MAX_K": "0"}, {"EDLIB_B200_LONG_SEED_MAX_K": "70", "EDLIB_B200_FILTER_SEED_BUCKET": "1"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_LONG_HW_MIN_TARGET="2000", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) >= 27
+
+
 def test_large_batch_uses_the_threaded_host_paths():
     """> 131072 pairs: packing + upload, classification, seed-stage outcomes and end-location assembly run
     on several host threads; every result still equals the reference's."""
