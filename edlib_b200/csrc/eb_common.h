@@ -105,6 +105,11 @@ struct K1WParams {
     int ncodes;
     const uint8_t* eqtab;
     WinRec* recs;            // [numReads]; positions are absolute target columns
+    // end columns beyond the KPOSW inline ones: appended (window slot, score, column) in sweep order; entries whose
+    // score is not the window's final minimum are stale.  ovfCap == 0: not collected.
+    Ovf* ovf;
+    int* ovfCount;           // zeroed by the host; may run past ovfCap (then the list is incomplete)
+    int ovfCap;
 };
 
 // L: lane-per-alignment sweep of a short query over its own target (any mode).
@@ -311,6 +316,10 @@ struct WinReduceParams {
     int* extra;
     int* extraCount;         // zeroed by the host
     int extraCap;
+    // overflow list of the window sweeps (K1WParams::ovf): windows with more than KPOSW end columns
+    const Ovf* ovf;
+    const int* ovfCount;
+    int ovfCap;
     // device-driven mode
     Leftover* leftover;
     int* leftoverCount;

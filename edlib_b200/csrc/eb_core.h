@@ -576,6 +576,8 @@ struct K1Band {
     int lo;         // first tracked column
     int kb0;        // window bit of the last query row at column 0 (frame of the following column): kb = kb0 - j
     int ws;         // absolute column of window column 0
+    const K1WParams& prm;  // overflow list of end columns beyond the inline ones
+    int slot;
 
     // Smallest value among the cells of the column just swept that lie in the current frame (the window of the
     // next column): D of the bottom cell is S, the vertical deltas lead upwards from there.
@@ -620,7 +622,16 @@ struct K1Band {
                     best = score;
                     cnt = 0;
                 }
-                if (cnt < CAP) rec->pos[cnt] = ws + j;
+                if (cnt < CAP) {
+                    rec->pos[cnt] = ws + j;
+                } else if (prm.ovfCap > 0) {
+                    const int at = atomic_add_int(prm.ovfCount, 1);
+                    if (at < prm.ovfCap) {
+                        prm.ovf[at].rec = slot;
+                        prm.ovf[at].score = score;
+                        prm.ovf[at].pos = ws + j;
+                    }
+                }
                 rec->last = ws + j;
                 cnt++;
             }
@@ -635,9 +646,9 @@ struct K1Band {
 // past dhi (by then the rows in the window are deep enough for an unrelated read to have left t behind).
 template <class WAcc, class RecT>
 EB_HD void k1b_sweep(const WAcc& acc, const uint8_t* tsyms, int ws, int m, int off, int c0, int lo, int hi, int t,
-                     int checkAfter, int& bestIo, int& cntIo, RecT* rec) {
+                     int checkAfter, int& bestIo, int& cntIo, RecT* rec, const K1WParams& prm, int slot) {
     const int dhi = hi - (m - 1) + t;
-    K1Band<WAcc, RecT> b{acc, rec, 0, 0, 0, 0, 0, bestIo, cntIo, off + 64 - dhi, lo, m - 2 + dhi, ws};
+    K1Band<WAcc, RecT> b{acc, rec, 0, 0, 0, 0, 0, bestIo, cntIo, off + 64 - dhi, lo, m - 2 + dhi, ws, prm, slot};
     // state before column c0: D[r][c0-1] = r + 1 on the rows of the query, 0 above it
     const int firstReal = off + 64 - (c0 + b.g0);  // window bit of query row 0 (may be <= 0 or >= 64)
     const uint64_t vp64 = firstReal <= 0 ? ~0ull : (firstReal >= 64 ? 0ull : (~0ull << firstReal));
@@ -698,7 +709,7 @@ EB_HD void k1w_thread(const K1WParams& p, int slot, WAcc& acc) {
         // at a multiple of 16), or the start of the target
         const int c0 = tf - (m + t) > 0 ? tf - (m + t) : 0;
         int best = kInit, cnt = 0;
-        k1b_sweep(acc, p.tcodes + ws, ws, m, 32 * NW - m, c0, tf, hi, t, p.checkAfter, best, cnt, rec);
+        k1b_sweep(acc, p.tcodes + ws, ws, m, 32 * NW - m, c0, tf, hi, t, p.checkAfter, best, cnt, rec, p, slot);
         rec->best = best;
         rec->cnt = cnt;
         return;
@@ -718,7 +729,7 @@ EB_HD void k1w_thread(const K1WParams& p, int slot, WAcc& acc) {
         }
     }
     if (!hopeless)
-        k1_columns<NW, false, true>(st, k1acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, nullptr, nullptr, 0);
+        k1_columns<NW, false, true>(st, k1acc, PtrSyms{p.tcodes + ws + tf}, len - tf, ws + tf, rec, slot, p.ovf, p.ovfCount, p.ovfCap);
     rec->best = st.best;
     rec->cnt = st.cnt;
 }
@@ -919,12 +930,17 @@ EB_HD void win_reduce_read(const WinReduceParams& p, int slot) {
             out.rsv = SEED_NONE;  // every window minimum is above the threshold
         } else {
             int total = 0;
-            bool longList = false;
+            bool longList = false, listed = false;
             for (int w = 0; w < pl.count; ++w) {
                 const WinRec& r = p.winRecs[pl.first + w];
                 if (r.cnt <= 0 || r.best != b) continue;
-                if (r.cnt > KPOSW) longList = true;
+                if (r.cnt > KPOSW) listed = true;  // the columns beyond the inline ones are in the overflow list
                 total += r.cnt;
+            }
+            int listLen = 0;
+            if (listed) {
+                listLen = p.ovfCap > 0 ? *p.ovfCount : 0x7fffffff;
+                if (listLen > p.ovfCap) longList = true;  // no list, or it ran over: the plain sweep collects the columns
             }
             int base = 0;
             if (!longList && total > KPOS) {
@@ -938,14 +954,28 @@ EB_HD void win_reduce_read(const WinReduceParams& p, int slot) {
                 for (int w = 0; w < pl.count; ++w) {
                     const WinRec& r = p.winRecs[pl.first + w];
                     if (r.cnt <= 0 || r.best != b) continue;
-                    for (int q = 0; q < r.cnt; ++q, ++i) {
+                    for (int q = 0; q < r.cnt && q < KPOSW; ++q, ++i) {
                         if (i < KPOS) out.pos[i] = r.pos[q];
                         else p.extra[base + i - KPOS] = r.pos[q];
                     }
+                    if (r.cnt > KPOSW) {  // rare: the window's entries of the list, which is in sweep order per window
+                        int found = 0;
+                        for (int e = 0; e < listLen; ++e) {
+                            const Ovf o = p.ovf[e];
+                            if (o.rec != pl.first + w || o.score != b) continue;
+                            if (found < r.cnt - KPOSW) p.extra[base + i++ - KPOS] = o.pos;  // (i >= KPOSW > KPOS here)
+                            ++found;
+                        }
+                        if (found != r.cnt - KPOSW) longList = true;  // cannot happen; the plain sweep would settle it
+                    }
                 }
-                out.best = b;
-                out.cnt = total;
-                out.last = base;
+                if (longList) {
+                    out.rsv = SEED_LONG_LIST;
+                } else {
+                    out.best = b;
+                    out.cnt = total;
+                    out.last = base;
+                }
             }
         }
     }

@@ -92,6 +92,7 @@ EngineTunables::EngineTunables() {
     filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
     filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
     filterMinTarget = env_int("EDLIB_B200_FILTER_MIN_TARGET", filterMinTarget);
+    filterSkipRepeats = env_int("EDLIB_B200_FILTER_SKIP_REPEATS", filterSkipRepeats);
     deviceStage = env_int("EDLIB_B200_DEVICE_STAGE", deviceStage);
     windowCheckAfter = env_int("EDLIB_B200_WINDOW_CHECK", windowCheckAfter);
     longHwMinTarget = env_int("EDLIB_B200_LONG_HW_MIN_TARGET", longHwMinTarget);
@@ -521,7 +522,7 @@ void Engine::compute(Prepared* p) {
     // ---- device-driven first seed level of every group that may take it: enqueued without waiting --------
     if (devSlices > 0) {
         ps.dev_begin(devSlices);
-        ps.dPool.alloc(be, (size_t)(4 * devReads + devReads / 4 + 1024LL * devSlices + 64));
+        ps.dPool.alloc(be, (size_t)(4 * devReads + devReads / 4 + (long long)DEV_EXTRA_SLACK * devSlices + 64));
         ps.dLists.alloc(be, (size_t)devListed);
         p->endPool.resize(ps.dPool.n);
         for (Route& r : routes) {
@@ -1017,7 +1018,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
         }
         stats.k1Cells = all.bytes * (long long)n;
         ps.dev_begin(numSlices);
-        ps.dPool.alloc(be, (size_t)(4LL * N + N / 4 + 1024LL * numSlices + 64));
+        ps.dPool.alloc(be, (size_t)(4LL * N + N / 4 + (long long)DEV_EXTRA_SLACK * numSlices + 64));
         p->endPool.resize(ps.dPool.n);
         trace.mark("stream: target + index");
 

@@ -115,6 +115,7 @@ struct EngineTunables {
     int filterSpread = 1024;      // widest group of candidate ranges verified as one window
     int filterMaxWindows = 32;    // windows per read and stage before the next stage takes the read
     int filterMinTarget = 65536;  // shortest target worth filtering
+    int filterSkipRepeats = 1;    // reads the last seed level found too repetitive skip the prefix stages (plain sweep)
     EngineTunables();             // reads EDLIB_B200_* environment overrides (used by tests)
 };
 

@@ -405,6 +405,8 @@ struct SeedIndex {
 // One slice of a device-driven group: reads [first, first+count) of the group's list (pair = list[first+slot], or
 // firstPair + slot when the group is a run of consecutive pairs), its region of the end-location pool and its
 // header {end locations, reads pending, pool overflow, windows}.
+// Room of a slice's extra list (end columns beyond the KPOS inline ones of a read) beyond a quarter of its reads.
+constexpr int DEV_EXTRA_SLACK = 16384;
 struct DevSlice {
     int t = 0, nw = 0;
     int firstPair = -1;      // >= 0: consecutive pairs (no read list on the device)
@@ -573,6 +575,7 @@ struct Pass {
         std::vector<int> bound;  // per read: largest distance that still counts as found
         std::vector<int> excl;   // per read: it is known that no distance <= excl[s] exists
         std::vector<int> direct; // reads that take the plain full sweep
+        std::vector<uint8_t> repeat;  // per read: the last seed level tried found too many occurrences of its seeds
     };
 
     // Chunk geometry: a HW sweep may be cut into target chunks (each re-started 2*m columns

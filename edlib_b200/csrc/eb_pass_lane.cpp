@@ -349,6 +349,11 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
     stats.filterWindows += V;
     trace.mark("filter: seeds planned");
     DevBuf<WinRec> dWinRecs(be, (size_t)std::max(V, 1));
+    // end columns beyond the inline ones of a window (reads that tie on many end columns)
+    const int ovfCap = (int)std::min<long long>((long long)V / 8 + 65536, 1 << 24);
+    DevBuf<Ovf> dOvf(be, (size_t)ovfCap);
+    DevBuf<int> dOvfCount(be, 1);
+    be->zero(dOvfCount.p, sizeof(int));
     if (V > 0) {
         K1WParams wp;
         memset(&wp, 0, sizeof(wp));
@@ -366,27 +371,37 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
         wp.ncodes = p->ncodes;
         wp.eqtab = nullptr;
         wp.recs = dWinRecs.p;
+        wp.ovf = dOvf.p;
+        wp.ovfCount = dOvfCount.p;
+        wp.ovfCap = ovfCap;
         be->launch_k1w(wp, nw);
     }
     DevBuf<Rec> dOut(be, g);
-    const int extraCap = g / 4 + 1024;
-    DevBuf<int> dExtra(be, (size_t)extraCap);
-    be->zero(dCount.p, sizeof(int));
-    WinReduceParams rp;
-    memset(&rp, 0, sizeof(rp));
-    rp.plan = dPlan.p;
-    rp.winRecs = dWinRecs.p;
-    rp.numReads = g;
-    rp.out = dOut.p;
-    rp.extra = dExtra.p;
-    rp.extraCount = dCount.p;
-    rp.extraCap = extraCap;
-    be->launch_win_reduce(rp);
+    int extraCap = g / 4 + 16384;
+    DevBuf<int> dExtra;
+    int nExtra = 0;
+    for (;;) {
+        dExtra.alloc(be, (size_t)extraCap);
+        be->zero(dCount.p, sizeof(int));
+        WinReduceParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.plan = dPlan.p;
+        rp.winRecs = dWinRecs.p;
+        rp.numReads = g;
+        rp.out = dOut.p;
+        rp.extra = dExtra.p;
+        rp.extraCount = dCount.p;
+        rp.extraCap = extraCap;
+        rp.ovf = dOvf.p;
+        rp.ovfCount = dOvfCount.p;
+        rp.ovfCap = ovfCap;
+        be->launch_win_reduce(rp);
+        dCount.download(&nExtra, 1);
+        if (nExtra <= extraCap) break;
+        extraCap = nExtra;  // the extra list ran over (repeat-rich reads): reduce again with the exact size
+    }
     HostBuf<Rec> out(be, g);
     dOut.download(out.p, g);
-    int nExtra = 0;
-    dCount.download(&nExtra, 1);
-    nExtra = std::min(nExtra, extraCap);  // reads whose run did not fit were marked as long lists
     std::vector<int> extra((size_t)nExtra);
     if (nExtra) dExtra.download(extra.data(), (size_t)nExtra);
     stats.d2hBytes += (long long)g * (long long)sizeof(Rec) + 4 + 4LL * nExtra;
@@ -420,6 +435,7 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
                 posLen[pair] = r.cnt;
                 P.positions += r.cnt;
             } else if (r.rsv == SEED_NONE) {
+                c.repeat[s] = 0;
                 if (thr[i] > excl[s]) excl[s] = thr[i];
                 if (thr[i] == bound[s]) {  // nothing within the caller's bound: final
                     best[pair] = 0x7fffffff;
@@ -434,6 +450,7 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
             } else {
                 P.next.push_back(s);
                 P.nSat++;
+                c.repeat[s] = 1;  // too many seed occurrences for this level
             }
         }
     });
@@ -463,9 +480,12 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
             for (int q = KPOS; q < r.cnt; ++q) posPool[(size_t)at++] = extra[(size_t)r.last + q - KPOS];
         }
     });
-    if (trace.on)
-        fprintf(stderr, "[edlib_b200] filter seed stage %d, L=%d: %d reads, %d windows, %d saturated, %d long lists, %zu to the next stage\n",
-                level, L, g, V, nSat, nLong, next.size());
+    if (trace.on) {
+        int nOvf = 0;
+        dOvfCount.download(&nOvf, 1);
+        fprintf(stderr, "[edlib_b200] filter seed stage %d, L=%d: %d reads, %d windows (%d listed end columns), %d saturated, %d long lists, %zu to the next stage\n",
+                level, L, g, V, nOvf, nSat, nLong, next.size());
+    }
 }
 
 // Prefix stage over the reads `in` (indices into `list`): a sweep of the first P rows of every read reports
@@ -593,6 +613,10 @@ void Pass::prefix_stage(LaneGroup& c, int P, int K0, const std::vector<int>& in,
     dLen.upload(vLen.data(), V);
     dTf.upload(vTf.data(), V);
     DevBuf<WinRec> dRecs(be, V);
+    const int ovfCap = (int)std::min<long long>((long long)V / 8 + 65536, 1 << 24);
+    DevBuf<Ovf> dOvf(be, (size_t)ovfCap);
+    DevBuf<int> dOvfCount(be, 1);
+    be->zero(dOvfCount.p, sizeof(int));
     K1WParams wp;
     memset(&wp, 0, sizeof(wp));
     wp.tcodes = p->dSeq.p + tg.off;
@@ -609,11 +633,23 @@ void Pass::prefix_stage(LaneGroup& c, int P, int K0, const std::vector<int>& in,
     wp.ncodes = p->ncodes;
     wp.eqtab = p->hasEq ? p->dEqtab.p : nullptr;
     wp.recs = dRecs.p;
+    wp.ovf = dOvf.p;
+    wp.ovfCount = dOvfCount.p;
+    wp.ovfCap = ovfCap;
     be->launch_k1w(wp, nw);
     std::vector<WinRec> rv(V);
     dRecs.download(rv.data(), V);
-    stats.d2hBytes += (long long)V * (long long)sizeof(WinRec);
+    int nOvf = 0;
+    dOvfCount.download(&nOvf, 1);
+    const bool ovfComplete = nOvf <= ovfCap;
+    std::vector<Ovf> ovf((size_t)std::min(nOvf, ovfCap));
+    if (!ovf.empty()) dOvf.download(ovf.data(), ovf.size());
+    stats.d2hBytes += (long long)V * (long long)sizeof(WinRec) + 4 + (long long)ovf.size() * (long long)sizeof(Ovf);
     trace.mark("filter: window sweeps");
+    // end columns beyond the inline ones, per window, in sweep order (entries of another score are stale)
+    std::unordered_map<int, std::vector<int>> listed;
+    for (const Ovf& o : ovf)
+        if (o.rec >= 0 && o.rec < V && o.score == rv[o.rec].best) listed[o.rec].push_back(o.pos);
     for (int i = 0; i < g; ++i) {
         if (wFirst[i] == wFirst[i + 1]) continue;
         const int s = cand[i], t = thr[i], pair = list[s];
@@ -629,9 +665,12 @@ void Pass::prefix_stage(LaneGroup& c, int P, int K0, const std::vector<int>& in,
         for (int j = wFirst[i]; j < wFirst[i + 1]; ++j)
             if (rv[j].cnt > 0 && rv[j].best == b) {
                 total += rv[j].cnt;
-                if (rv[j].cnt > KPOSW) longList = true;
+                if (rv[j].cnt > KPOSW) {
+                    auto it = listed.find(j);
+                    if (!ovfComplete || it == listed.end() || (int)it->second.size() != rv[j].cnt - KPOSW) longList = true;
+                }
             }
-        if (longList) {  // long end-location list: the plain sweep collects it
+        if (longList) {  // the list ran over: the plain sweep collects the columns
             direct.push_back(s);
             continue;
         }
@@ -640,8 +679,13 @@ void Pass::prefix_stage(LaneGroup& c, int P, int K0, const std::vector<int>& in,
         cnt[pair] = total;
         posStart[pair] = (long long)posPool.size();
         for (int j = wFirst[i]; j < wFirst[i + 1]; ++j)
-            if (rv[j].cnt > 0 && rv[j].best == b)
-                for (int q = 0; q < rv[j].cnt; ++q) posPool.push_back(rv[j].pos[q]);
+            if (rv[j].cnt > 0 && rv[j].best == b) {
+                for (int q = 0; q < std::min(rv[j].cnt, KPOSW); ++q) posPool.push_back(rv[j].pos[q]);
+                if (rv[j].cnt > KPOSW) {
+                    const std::vector<int>& ex = listed[j];
+                    posPool.insert(posPool.end(), ex.begin(), ex.end());
+                }
+            }
         posLen[pair] = total;
     }
 }
@@ -683,7 +727,7 @@ void Pass::plain_sweep(LaneGroup& c) {
 void Pass::lane_group(int t, int nw, const std::vector<int>& list, const std::vector<int>* exclInit, int firstSeedLevel) {
     const Target& tg = p->tg[t];
     const int G = (int)list.size();
-    LaneGroup c{t, nw, list, tg, tg.len, std::vector<int>(G), std::vector<int>(G, -1), std::vector<int>()};
+    LaneGroup c{t, nw, list, tg, tg.len, std::vector<int>(G), std::vector<int>(G, -1), std::vector<int>(), std::vector<uint8_t>(G, 0)};
     host_touch(list.data(), list.size());
     long long rows = 0;
     for (int s = 0; s < G; ++s) {
@@ -711,6 +755,13 @@ void Pass::lane_group(int t, int nw, const std::vector<int>& list, const std::ve
             seed_stage(c, level, cur, next);
             cur.swap(next);
         }
+        // Reads that drowned in seed occurrences at the last level tried are repeats: their prefixes match all over
+        // the target as well, so the prefix stages would cost two more sweeps and decide few of them.
+        if (tun.filterSkipRepeats) {
+            std::vector<int> keep;
+            for (int s : cur) (c.repeat[s] ? c.direct : keep).push_back(s);
+            cur.swap(keep);
+        }
         const int stageP[2] = {32, 64};
         const int stageK[2] = {tun.filterK1, tun.filterK0};
         for (int st = 0; st < 2; ++st) {
@@ -721,6 +772,8 @@ void Pass::lane_group(int t, int nw, const std::vector<int>& list, const std::ve
             cur.swap(next);
         }
     }
+    if (trace.on)
+        fprintf(stderr, "[edlib_b200] plain sweep: %zu reads sent directly (long end-location lists, repeats), %zu undecided\n", c.direct.size(), cur.size());
     c.direct.insert(c.direct.end(), cur.begin(), cur.end());
     if (filtered) stats.filterFallback += (long long)c.direct.size();
     trace.mark("filter: collect");
@@ -770,7 +823,7 @@ int Pass::dev_enqueue_slice(int t, int nw, int firstPair, const int* listHost, i
     sl.firstPair = firstPair >= 0 ? firstPair + first : -1;
     sl.count = count;
     sl.poolBase = poolReserved;
-    sl.poolCap = 4 * count + count / 4 + 1024;  // <= KPOS inline positions per read + the slice's extra list
+    sl.poolCap = 4 * count + count / 4 + DEV_EXTRA_SLACK;  // <= KPOS inline positions per read + the slice's extra list
     poolReserved += sl.poolCap;
     if (poolReserved > (long long)dPool.n) throw std::runtime_error("internal: end-location pool of the device stage too small");
     const int* dList = nullptr;
@@ -782,13 +835,15 @@ int Pass::dev_enqueue_slice(int t, int nw, int firstPair, const int* listHost, i
     }
     int& perRead = eng.scratch.seedWindowsPerRead[0];
     const int cap = (int)std::min<long long>((long long)count * std::max(perRead + 2, 6) + 4096, 1LL << 28);
-    const int extraCap = count / 4 + 1024;
+    const int extraCap = count / 4 + DEV_EXTRA_SLACK;
+    const int ovfCap = cap / 8 + 65536;
+    DevBuf<Ovf> dOvf(be, (size_t)ovfCap);
     DevBuf<SeedPlan> dPlan(be, count);
     DevBuf<int> wPair(be, cap), wK(be, cap), wStart(be, cap), wLen(be, cap), wTf(be, cap);
     DevBuf<WinRec> dWinRecs(be, cap);
     DevBuf<Rec> dOut(be, count);
-    DevBuf<int> dExtra(be, extraCap), dCnt32(be, (size_t)count + 1), dCtr(be, 2);
-    be->zero(dCtr.p, 2 * sizeof(int));
+    DevBuf<int> dExtra(be, extraCap), dCnt32(be, (size_t)count + 1), dCtr(be, 3);
+    be->zero(dCtr.p, 3 * sizeof(int));
     SeedPlanParams sp;
     fill_seed_plan(sp, p, tg, sx, 0, tun);
     sp.readList = dList;
@@ -821,6 +876,9 @@ int Pass::dev_enqueue_slice(int t, int nw, int firstPair, const int* listHost, i
     wp.ncodes = p->ncodes;
     wp.eqtab = nullptr;
     wp.recs = dWinRecs.p;
+    wp.ovf = dOvf.p;
+    wp.ovfCount = dCtr.p + 2;
+    wp.ovfCap = ovfCap;
     be->launch_k1w(wp, nw);
     WinReduceParams rp;
     memset(&rp, 0, sizeof(rp));
@@ -831,6 +889,9 @@ int Pass::dev_enqueue_slice(int t, int nw, int firstPair, const int* listHost, i
     rp.extra = dExtra.p;
     rp.extraCount = dCtr.p + 1;
     rp.extraCap = extraCap;
+    rp.ovf = dOvf.p;
+    rp.ovfCount = dCtr.p + 2;
+    rp.ovfCap = ovfCap;
     rp.leftover = dLeft.p;
     rp.leftoverCount = dLeftCount.p;
     rp.readList = dList;

@@ -314,3 +314,42 @@ def big_batch_case(seed, num=140_000, target_len=4000):
             q = rand_seq(rng, L, alpha)
         qs.append(q)
     return dict(qs=qs, ts=[t] * num, k=rng.choice([-1, 6]), mode=2, task=rng.choice([0, 1]), eqs=None)
+
+
+def tied_ends_cases(seed, count):
+    """HW read sets whose reads tie on MANY neighbouring end columns (homopolymer and short-period tandem stretches
+    inside a random target): one window of the candidate filter then holds more than its inline end columns, so the
+    overflow list of the window sweeps and its assembly (device reduction, host-driven stages) are exercised; reads
+    across the borders of the stretches and plain reads ride along."""
+    from helpers import mutate, rand_seq
+    rng = random.Random(seed)
+    for it in range(count):
+        parts, marks = [], []
+        at = 0
+        for _ in range(rng.randrange(2, 5)):
+            u = rand_seq(rng, rng.randrange(1500, 4000), b"ACGT")
+            parts.append(u)
+            at += len(u)
+            unit = rng.choice([b"A", b"T", b"AC", b"GGC", b"ACGTTGCA"])
+            rep = unit * (rng.randrange(60, 420) // len(unit))
+            marks.append((at, len(rep)))
+            parts.append(rep)
+            at += len(rep)
+        parts.append(rand_seq(rng, 2000, b"ACGT"))
+        t = b"".join(parts)
+        qs = []
+        for _ in range(rng.randrange(40, 90)):
+            m = rng.choice([24, 32, 40, 40, 64, 100, 150, 200, 256])
+            kind = rng.randrange(4)
+            if kind == 0:      # inside a stretch
+                a, ln = rng.choice(marks)
+                s = a + rng.randrange(0, max(1, ln - m))
+            elif kind == 1:    # across a border of a stretch
+                a, ln = rng.choice(marks)
+                s = max(0, (a if rng.random() < 0.5 else a + ln) - rng.randrange(1, m))
+            else:
+                s = rng.randrange(0, len(t) - m)
+            q = mutate(rng, t[s:s + m], rng.choice([0.0, 0.0, 0.02, 0.05]), b"ACGT")
+            if q:
+                qs.append(q)
+        yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 2, 5, 20]), mode=2, task=(it + seed) % 3, eqs=None)

@@ -79,7 +79,8 @@ def test_candidate_filter_all_branches():
     ) % (REPO, os.path.join(REPO, "tests"))
     for extra in ({}, {"EDLIB_B200_FILTER_K0": "4", "EDLIB_B200_FILTER_K1": "2", "EDLIB_B200_FILTER_SPREAD": "64",
                        "EDLIB_B200_FILTER_MAX_WINDOWS": "2", "EDLIB_B200_K1_MIN_CHUNK": "64", "EDLIB_EMUL_SMS": "64"},
-                  {"EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "3", "EDLIB_B200_FILTER_SEED_BUCKET": "2"},
+                  {"EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "3", "EDLIB_B200_FILTER_SEED_BUCKET": "2",
+                   "EDLIB_B200_FILTER_SKIP_REPEATS": "0"},
                   {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "12", "EDLIB_B200_FILTER_SEED_K": "0"},
                   {"EDLIB_B200_WINDOW_CHECK": "0"}, {"EDLIB_B200_WINDOW_CHECK": "-1", "EDLIB_B200_FILTER_SEED_LEVELS": "2"},
                   {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "40",
@@ -89,6 +90,24 @@ def test_candidate_filter_all_branches():
         env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 500
+
+
+def test_reads_that_tie_on_many_end_columns():
+    """Homopolymer / tandem stretches: windows with more end columns than a record holds inline (overflow list of the
+    window sweeps), through the device-driven first seed level (streamed and staged), the host-driven seed levels and
+    the prefix stages alone."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 51, 8, gen=cases.tied_ends_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra in ({"EDLIB_B200_STREAM_MIN_PAIRS": "8"}, {"EDLIB_B200_DEVICE_STAGE": "0"},
+                  {"EDLIB_B200_FILTER_SEED_K": "0", "EDLIB_B200_FILTER_K1": "12"},
+                  {"EDLIB_B200_STREAM_MIN_PAIRS": "8", "EDLIB_B200_SLICE_READS": "64", "EDLIB_B200_FILTER_SEED_BUCKET": "4096"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 300
 
 
 def test_streamed_batches():
