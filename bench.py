@@ -676,6 +676,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep-sample", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (other configs, sensitivity, strong scaling)")
+    ap.add_argument("--extras", default="strong,other_target,sensitivity,config4,config3,sweep_kernel",
+                    help="comma-separated sub-records to run (default: all)")
     ap.add_argument("--config3-pairs", type=int, default=100_000)
     ap.add_argument("--strong-reads", type=int, default=10_000_000)
     args = ap.parse_args()
@@ -768,7 +770,8 @@ def main():
             "kernel_share_of_step": rs["kernel_ms"] / (1000.0 * elapsed / args.steps),
         }
     # ---- strong scaling (configs[4]) on every N; the other sub-records on one GPU only ----
-    if not args.no_extras:
+    wanted = set() if args.no_extras else set(x for x in args.extras.split(",") if x)
+    if "strong" in wanted:
         try:
             genome = target if args.target == "ecoli" else (workloads.ecoli_genome() if rank == 0 else None)
             if world > 1 and args.target != "ecoli":
@@ -779,11 +782,13 @@ def main():
         except Exception as e:  # a sub-record never takes the headline down
             if line is not None:
                 line["strong"] = {"error": repr(e)[:300]}
-    if rank == 0 and world == 1 and not args.no_extras:
+    if rank == 0 and world == 1 and wanted:
         peak, peak_src = measured_peaks()
         extras = {}
 
         def guarded(name, fn):
+            if name not in wanted:
+                return
             t0 = time.time()
             try:
                 extras[name] = fn()

@@ -22,10 +22,17 @@ fi
 if has ncu; then
   for K in ${NCU_KERNELS:-k1w_kernel seed_plan_kernel}; do
     echo "== ncu --set full: $K"
-    timeout 900 ncu --set full --import-source on --clock-control none -k regex:$K -s ${NCU_SKIP:-4} -c 1 -f -o $OUT/ncu_${TAG}_$K \
+    timeout 900 ncu --set full --import-source on --clock-control none -k regex:$K -s ${NCU_SKIP:-3} -c ${NCU_COUNT:-1} -f -o $OUT/ncu_${TAG}_$K \
         python bench.py --steps 1 --warmup 1 --e2e-steps 0 --no-cpu-baseline --no-sweep-sample --no-extras > $OUT/ncu_${TAG}_$K.log 2>&1; echo "rc=$?"
     ncu -i $OUT/ncu_${TAG}_$K.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_${K}_raw.csv 2>/dev/null
+    # gpurun brings back at most 64 MiB: a report that would break that is dropped (its CSV stays)
+    if [ $(du -sm $OUT | cut -f1) -gt 48 ]; then ncu -i $OUT/ncu_${TAG}_$K.ncu-rep --page source --csv > $OUT/ncu_${TAG}_${K}_source.csv 2>/dev/null; rm -f $OUT/ncu_${TAG}_$K.ncu-rep; fi
   done
+fi
+if has cfgtrace; then
+  echo "== host-phase trace of configs 3 and 4 (end to end)"
+  EDLIB_B200_TRACE=1 timeout 900 python bench.py --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline --no-sweep-sample --extras config4,config3 > $OUT/cfgtrace_$TAG.txt 2>&1
+  grep -v "^{" $OUT/cfgtrace_$TAG.txt | tail -150 | cut -c1-170
 fi
 if has ref; then echo "== bench --impl reference"; timeout 900 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; cut -c1-400 $OUT/bench_ref_$TAG.json; fi
 if has stress; then
