@@ -1104,6 +1104,167 @@ EB_HD void lane_job(const LParams& p, int jobIdx, Acc& acc) {
 }
 
 // =============================================================================================
+// B -- k-banded NW sweep of a LONG query, one alignment per THREAD (ref myersCalcEditDistanceNW cpp:730-928 with
+// its Ukkonen band, cpp:755, 799-830).  The thread holds a window of NW = 4*NB words (32*NW rows) of the column in
+// registers; the window slides down the band one WORD at a time, at columns that are multiples of 32 for every
+// thread of the launch (the window top is 32*floor(c/32) + A, A a multiple of 32 chosen per job so that the top
+// stays at or above the band's top diagonal dhi), so control flow stays uniform.  Rows above the window are outside
+// the band: the horizontal delta entering its top row is the pessimistic +1 (ref cpp:779; for the true first row
+// it is the NW boundary), rows entering at the bottom start from vertical deltas +1.  Every cell whose optimal
+// path stays inside the band is exact, everything else an upper bound: the result is valid iff it is <= the bound
+// the band was planned for (the host checks that, as for the warp kernel's sliding window).  The profile (peq_kernel:
+// [code][nWp] words in global memory) is far too large for per-thread shared memory, so the thread keeps only the
+// window's words of every code there (`acc`: NW + BAND_SLACK word slots per code; the origin moves up one slot per
+// slide and the slots are moved back every BAND_SLACK slides) and fetches ncodes new words per slide.
+// Needs: nWp >= NW, 32*NW >= band height + 31 + ((off - dhi) - A) (WRunner::run_band sizes NB that way).
+// =============================================================================================
+constexpr int BAND_SLACK = 4;
+
+// S = A + B + cin over four words; returns the carry out.
+EB_HD uint32_t chain4(uint32_t (&S)[4], const uint32_t (&A)[4], const uint32_t (&B)[4], uint32_t cin) {
+#if defined(__CUDA_ARCH__)
+    uint32_t cout;
+    asm("{\n\t.reg .u32 t;\n\t"
+        "add.cc.u32 t, %13, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.cc.u32 %3, %8, %12;\n\t"
+        "addc.u32 %4, 0, 0;\n\t}"
+        : "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(cout)
+        : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(cin));
+    return cout;
+#else
+    uint32_t carry = cin;
+    for (int w = 0; w < 4; ++w) {
+        const uint64_t s = (uint64_t)A[w] + B[w] + carry;
+        S[w] = (uint32_t)s;
+        carry = (uint32_t)(s >> 32);
+    }
+    return carry;
+#endif
+}
+
+struct BandCarry {
+    uint32_t add, ph, mh;  // carries into the next block of four words: of the add, of Ph << 1, of Mh << 1
+};
+
+// Column step of words [4*B, 4*B+4) of the window (k1_step with the carries between blocks spelled out).
+template <int NW, int B>
+EB_HD void band_block(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&Eq)[4], BandCarry& cy) {
+    uint32_t P[4], M[4], T[4], S[4], Ph[4], Mh[4], Phs[4], Mhs[4];
+    EB_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        P[i] = Pv[4 * B + i];
+        M[i] = Mv[4 * B + i];
+        T[i] = Eq[i] & P[i];
+    }
+    cy.add = chain4(S, T, P, cy.add);
+    EB_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t Xh = (S[i] ^ P[i]) | Eq[i];
+        Ph[i] = M[i] | ~(Xh | P[i]);
+        Mh[i] = P[i] & Xh;
+    }
+    cy.ph = chain4(Phs, Ph, Ph, cy.ph);
+    cy.mh = chain4(Mhs, Mh, Mh, cy.mh);
+    EB_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t Xv = Eq[i] | M[i];
+        Pv[4 * B + i] = Mhs[i] | ~(Xv | Phs[i]);
+        Mv[4 * B + i] = Phs[i] & Xv;
+    }
+}
+
+template <int NW, int B, int NB, class BAcc>
+struct BandBlocks {
+    static EB_HD void run(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const BAcc& acc, uint32_t codeOff, BandCarry& cy) {
+        uint32_t Eq[4];
+        EB_UNROLL
+        for (int i = 0; i < 4; ++i) Eq[i] = acc.load(codeOff, 4 * B + i);
+        band_block<NW, B>(Pv, Mv, Eq, cy);
+        BandBlocks<NW, B + 1, NB, BAcc>::run(Pv, Mv, acc, codeOff, cy);
+    }
+};
+template <int NW, int NB, class BAcc>
+struct BandBlocks<NW, NB, NB, BAcc> {
+    static EB_HD void run(uint32_t (&)[NW], uint32_t (&)[NW], const BAcc&, uint32_t, BandCarry&) {}
+};
+
+// BAcc: the thread's window of the profile.  set(code, slot, bits) writes a slot (absolute slot index), get(code, slot)
+// reads one; origin(slot) makes `slot` the window's first word for the column loop's load(code_off(sym), w), w a
+// compile-time word of the window.
+template <int NB, class BAcc>
+EB_HD void band_job(const WParams& P, int jobIdx, BAcc& acc, int ncodes) {
+    constexpr int NW = 4 * NB;
+    const WJob J = P.jobs[jobIdx];
+    const int n = J.n, nWp = J.nWp;
+    const int off = 32 * nWp - J.m;
+    const uint32_t* peq = P.peq + J.peqOff;
+    const uint8_t* t = P.tcodes + J.tOff;
+    Rec* rec = P.recs + J.rec;
+    int A = off - J.dhi;  // window top of column c: 32*floor(c/32) + A rounded down to a multiple of 32, at most 0
+    A = (A >= 0) ? 0 : -(((-A) + 31) / 32) * 32;
+    const int topMax = nWp - NW;
+    int top = 0, org = 0;
+    for (int code = 0; code < ncodes; ++code)
+        for (int w = 0; w < NW; ++w) acc.set(code, w, peq[(size_t)code * nWp + w]);
+    acc.origin(0);
+    uint32_t Pv[NW], Mv[NW];
+    EB_UNROLL
+    for (int w = 0; w < NW; ++w) {
+        Pv[w] = init_pv_word(w, off);
+        Mv[w] = 0;
+    }
+    int score = 32 * NW - off;  // D of the window's bottom row in column -1
+    Sym16 syms;
+    syms.w[0] = syms.w[1] = syms.w[2] = syms.w[3] = 0;
+    for (int c = 0; c < n; ++c) {
+        if ((c & 15) == 0) {
+            syms = load_sym16(t + c);
+        } else if ((c & 3) == 0) {  // next four symbols into word 0 (static indices: the words stay in registers)
+            syms.w[0] = syms.w[1];
+            syms.w[1] = syms.w[2];
+            syms.w[2] = syms.w[3];
+        }
+        if ((c & 31) == 0 && ((c + A) >> 5) > top && top < topMax) {
+            // slide: drop the top word, open a fresh one at the bottom (vertical deltas +1: ref cpp:799-809 grows the
+            // band the same way), fetch its profile words
+            EB_UNROLL
+            for (int w = 0; w + 1 < NW; ++w) {
+                Pv[w] = Pv[w + 1];
+                Mv[w] = Mv[w + 1];
+            }
+            Pv[NW - 1] = ~0u;
+            Mv[NW - 1] = 0u;
+            score += 32;
+            ++top;
+            ++org;
+            if (org == BAND_SLACK) {  // move the slots back to the front
+                for (int code = 0; code < ncodes; ++code)
+                    for (int w = 0; w + 1 < NW; ++w) acc.set(code, w, acc.get(code, w + BAND_SLACK));
+                org = 0;
+            }
+            for (int code = 0; code < ncodes; ++code) acc.set(code, org + NW - 1, peq[(size_t)code * nWp + top + NW - 1]);
+            acc.origin(org);
+        }
+        const uint32_t sym = (syms.w[0] >> (8 * (c & 3))) & 255u;
+        BandCarry cy;
+        cy.add = 0;
+        cy.ph = 1;  // +1 enters above the window's top row
+        cy.mh = 0;
+        BandBlocks<NW, 0, NB, BAcc>::run(Pv, Mv, acc, acc.code_off(sym), cy);
+        score += (int)cy.ph - (int)cy.mh;  // horizontal delta of the window's bottom row
+    }
+    // the window ends on the query's last row (top == topMax by the band's geometry); a window that did not get
+    // there cannot hold the bottom-right cell: report a score above every bound
+    rec->best = (top == topMax) ? score : 0x3fffffff;  // ref cpp:916
+    rec->cnt = 1;
+    rec->last = n - 1;
+    rec->pos[0] = n - 1;
+}
+
+// =============================================================================================
 // W -- one alignment per warp.  Lane l holds R consecutive words (a "chunk"); the 32 chunks of
 // a warp form a window of 1024*R rows.  A query taller than the window is swept in strips
 // (fixed windows stacked vertically, the horizontal deltas of a strip's bottom row feeding the

@@ -93,6 +93,7 @@ EngineTunables::EngineTunables() {
     filterSpread = env_int("EDLIB_B200_FILTER_SPREAD", filterSpread);
     filterMinTarget = env_int("EDLIB_B200_FILTER_MIN_TARGET", filterMinTarget);
     filterSkipRepeats = env_int("EDLIB_B200_FILTER_SKIP_REPEATS", filterSkipRepeats);
+    bandKernel = env_int("EDLIB_B200_BAND_KERNEL", bandKernel);
     deviceStage = env_int("EDLIB_B200_DEVICE_STAGE", deviceStage);
     windowCheckAfter = env_int("EDLIB_B200_WINDOW_CHECK", windowCheckAfter);
     longHwMinTarget = env_int("EDLIB_B200_LONG_HW_MIN_TARGET", longHwMinTarget);

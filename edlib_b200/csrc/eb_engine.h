@@ -59,6 +59,10 @@ struct Backend {
     virtual void launch_lane(const LParams& p, int nw32, int mode, bool reversed, bool store) = 0;
     virtual void launch_peq(const PeqParams& p) = 0;
     virtual void launch_w(const WParams& p, int R) = 0;
+    // k-banded NW sweeps of long queries, one alignment per thread over a sliding window of 4*NB words
+    // (eb_core.h: band_job).  band_max_blocks: the largest NB the backend runs for this alphabet size (0: none).
+    virtual int band_max_blocks(int ncodes) = 0;
+    virtual void launch_band(const WParams& p, int NB, int ncodes) = 0;
     virtual void launch_traceback(const TbParams& p) = 0;
     virtual void launch_split(const SplitParams& p) = 0;
     // seed stage of the candidate filter: index build (count / scan / fill), per-read planning, window reduction
@@ -115,6 +119,7 @@ struct EngineTunables {
     int filterSpread = 1024;      // widest group of candidate ranges verified as one window
     int filterMaxWindows = 32;    // windows per read and stage before the next stage takes the read
     int filterMinTarget = 65536;  // shortest target worth filtering
+    int bandKernel = 1;           // k-banded NW sweeps of long queries on the thread-per-alignment band kernel (0: warp kernel)
     int filterSkipRepeats = 1;    // reads the last seed level found too repetitive skip the prefix stages (plain sweep)
     EngineTunables();             // reads EDLIB_B200_* environment overrides (used by tests)
 };

@@ -284,6 +284,7 @@ struct WTask {
     uint64_t qOff = 0, tOff = 0;
     int m = 0, n = 0, mode = 0, flags = 0, kInit = 0, dhi = 0, stopCol = -1, trackFrom = 0;
     int R = 1, nWp = 0;
+    int bandH = 0;               // WF_SLIDE: diagonals of the band the window slides down (plan_w)
     int pair = -1, tag = 0;
     bool wantPositions = false;  // the caller needs every end position, not just best/cnt/last
     int splitSide = -1;          // WF_STOPCOL pairs of a Hirschberg node: 0 forward half, 1 reversed half (adjacent tasks)
@@ -299,6 +300,7 @@ struct WPlan {
     int R, nWp;
     bool slide;
     int dhi;
+    int height;  // slide: diagonals of the band
 };
 
 WPlan plan_w(int m, int n, int mode, int kBound);
@@ -379,6 +381,12 @@ struct WRunner {
     }
 
     void run(std::vector<WTask>& tasks);
+
+    // Window blocks (of four words) the thread-per-alignment band kernel needs for task t, or 0 when the task is not
+    // of its kind (plain k-banded NW distance sweep of a query taller than the window).
+    int band_blocks(const WTask& t) const;
+    // One window size of band tasks, in memory-bounded slices (eb_core.h: band_job).
+    void run_band(std::vector<WTask>& tasks, const std::vector<int>& idx, int NB);
 
     // One class of lane tasks, in memory-bounded slices.  Tasks that need a longer end-location list
     // than a record holds are handed to the warp kernel (`spill`), which owns the list machinery.

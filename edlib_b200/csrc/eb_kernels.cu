@@ -322,6 +322,42 @@ __global__ void __launch_bounds__(W_WARPS * 32) w_kernel(const WParams p) {
     w_dispatch<DevWarp, R>(p, job);
 }
 
+// B: k-banded NW sweep of a long query, one alignment per thread (eb_core.h: band_job).  The window's words of
+// every code live in shared memory, word-interleaved over the threads of the CTA (slot s of code c of thread t at
+// base + ((c * SLOTS + s) * THREADS + t) * 4): conflict-free whatever slot each thread reads, and with the origin
+// folded into `cur` every offset of the column loop is an immediate.
+template <int THREADS, int SLOTS>
+struct SmemBandAcc {
+    uint32_t base, cur;
+    static constexpr uint32_t wordStride = 4u * THREADS, codeStride = wordStride * SLOTS;
+    EB_D void set(int code, int slot, uint32_t bits) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + (uint32_t)code * codeStride + (uint32_t)slot * wordStride), "r"(bits) : "memory");
+    }
+    EB_D uint32_t get(int code, int slot) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)code * codeStride + (uint32_t)slot * wordStride) : "memory");
+        return v;
+    }
+    EB_D void origin(int slot) { cur = base + (uint32_t)slot * wordStride; }
+    EB_D uint32_t code_off(uint32_t sym) const { return sym * codeStride; }
+    EB_D uint32_t load(uint32_t codeOff, int w) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(cur + codeOff + (uint32_t)w * wordStride) : "memory");
+        return v;
+    }
+};
+constexpr int BAND_THREADS = 128;
+template <int NB>
+__global__ void __launch_bounds__(BAND_THREADS) band_kernel(const WParams p, int ncodes) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int job = blockIdx.x * BAND_THREADS + threadIdx.x;
+    if (job >= p.numJobs) return;
+    SmemBandAcc<BAND_THREADS, 4 * NB + BAND_SLACK> acc;
+    acc.base = smem_u32(smem) + 4u * threadIdx.x;
+    acc.cur = acc.base;
+    band_job<NB>(p, job, acc, ncodes);
+}
+
 __global__ void peq_kernel(const PeqParams p) {
     const int job = blockIdx.x * W_WARPS + (threadIdx.x >> 5);
     if (job >= p.numJobs) return;
@@ -924,6 +960,33 @@ struct CudaBackend : Backend {
             default: throw std::runtime_error("bad W chunk size");
         }
         check_launch("w");
+    }
+    static size_t band_smem(int NB, int ncodes) { return (size_t)ncodes * (4 * NB + BAND_SLACK) * 4 * BAND_THREADS; }
+    int band_max_blocks(int ncodes) override {
+        int nb = 0;
+        while (nb < 8 && band_smem(nb + 1, ncodes) <= (size_t)110 * 1024) ++nb;  // two CTAs per SM at least
+        return nb;
+    }
+    template <int NB>
+    void launch_band_t(const WParams& p, int ncodes) {
+        const size_t smem = band_smem(NB, ncodes);
+        EB_CUDA(cudaFuncSetAttribute(band_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        band_kernel<NB><<<(p.numJobs + BAND_THREADS - 1) / BAND_THREADS, BAND_THREADS, smem, stream>>>(p, ncodes);
+    }
+    void launch_band(const WParams& p, int NB, int ncodes) override {
+        Scope s(this, "band");
+        switch (NB) {
+            case 1: launch_band_t<1>(p, ncodes); break;
+            case 2: launch_band_t<2>(p, ncodes); break;
+            case 3: launch_band_t<3>(p, ncodes); break;
+            case 4: launch_band_t<4>(p, ncodes); break;
+            case 5: launch_band_t<5>(p, ncodes); break;
+            case 6: launch_band_t<6>(p, ncodes); break;
+            case 7: launch_band_t<7>(p, ncodes); break;
+            case 8: launch_band_t<8>(p, ncodes); break;
+            default: throw std::runtime_error("bad band window size");
+        }
+        check_launch("band");
     }
     void launch_seed_count(const SeedIndexParams& p) override {
         Scope s(this, "seed_count");

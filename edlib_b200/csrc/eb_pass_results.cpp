@@ -287,6 +287,7 @@ void Pass::warp_distance() {
                 t.mode = mode;
                 t.flags = pl.slide ? WF_SLIDE : 0;
                 t.dhi = pl.dhi;
+                t.bandH = pl.height;
                 t.R = pl.R;
                 t.nWp = pl.nWp;
                 t.kInit = ((k < 0 || k > m) ? m : k) + 1;

@@ -13,6 +13,7 @@ WPlan plan_w(int m, int n, int mode, int kBound) {
     const int nW = ceil_div(m, 32);
     pl.slide = false;
     pl.dhi = 0;
+    pl.height = 0;
     if (nW <= 32) {
         pl.R = 1;
         pl.nWp = nW;
@@ -30,6 +31,7 @@ WPlan plan_w(int m, int n, int mode, int kBound) {
                 pl.R = R;
                 pl.slide = true;
                 pl.dhi = (int)dhi;
+                pl.height = (int)height;
                 return pl;
             }
         }
@@ -54,6 +56,7 @@ WPlan plan_w_band(int m, long long height, int dhi) {
             pl.R = R;
             pl.slide = true;
             pl.dhi = dhi;
+            pl.height = (int)height;
             return pl;
         }
     }
@@ -68,14 +71,87 @@ size_t WRunner::task_bytes(const WTask& t) const {
     return b;
 }
 
+// The band kernel's window must hold the band (bandH diagonals), the 31 rows the window lags behind while it waits
+// for the next multiple of 32 columns, and the rows by which its top lies above the band's top diagonal (see band_job).
+int WRunner::band_blocks(const WTask& t) const {
+    if (!eng->tun.bandKernel || t.flags != WF_SLIDE || t.mode != MODE_NW || t.bandH <= 0 || (t.tOff & 15u)) return 0;
+    const int nW = ceil_div(t.m, 32);
+    const int off = 32 * nW - t.m;
+    int A = off - t.dhi;
+    A = (A >= 0) ? 0 : -(((-A) + 31) / 32) * 32;
+    const long long rows = (long long)t.bandH + 31 + ((off - t.dhi) - A);
+    const long long NB = (rows + 127) / 128;
+    if (NB > be->band_max_blocks(p->ncodes) || 4 * NB > nW) return 0;
+    return (int)NB;
+}
+
+void WRunner::run_band(std::vector<WTask>& tasks, const std::vector<int>& idx, int NB) {
+    size_t i = 0;
+    while (i < idx.size()) {
+        size_t bytes = 0, j = i;
+        while (j < idx.size()) {
+            const WTask& t = tasks[idx[j]];
+            const size_t tb = (size_t)p->ncodes * ceil_div(t.m, 32) * 4 + sizeof(WJob) + sizeof(Rec);
+            if (j > i && bytes + tb > eng->tun.sliceBytes) break;
+            bytes += tb;
+            ++j;
+        }
+        const int J = (int)(j - i);
+        HostBuf<WJob> jobs(be, (size_t)J);
+        uint64_t peqWords = 0;
+        for (int s = 0; s < J; ++s) {
+            const WTask& t = tasks[idx[i + s]];
+            WJob& wj = jobs[s];
+            memset(&wj, 0, sizeof(wj));
+            wj.qOff = t.qOff;
+            wj.tOff = t.tOff;
+            wj.m = t.m;
+            wj.n = t.n;
+            wj.nWp = ceil_div(t.m, 32);  // no padding words beyond the last one: the window ends on the last row
+            wj.mode = t.mode;
+            wj.flags = t.flags;
+            wj.kInit = t.kInit;
+            wj.dhi = t.dhi;
+            wj.rec = s;
+            wj.peqOff = peqWords;
+            peqWords += (uint64_t)p->ncodes * wj.nWp;
+        }
+        DevBuf<WJob> dJobs(be, (size_t)J);
+        dJobs.upload(jobs.p, (size_t)J);
+        DevBuf<uint32_t> dPeq(be, peqWords);
+        DevBuf<Rec> dRecs(be, (size_t)J);
+        PeqParams pp{dJobs.p, J, p->dSeq.p, dPeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr};
+        be->launch_peq(pp);
+        WParams wp{dJobs.p, J, p->dSeq.p, p->dSeq.p, dPeq.p, nullptr, nullptr, nullptr, dRecs.p, nullptr, nullptr, 0};
+        be->launch_band(wp, NB, p->ncodes);
+        if (getenv("EDLIB_B200_TRACE")) fprintf(stderr, "[edlib_b200] band kernel: %d sweeps, window of %d words\n", J, 4 * NB);
+        HostBuf<Rec> recs(be, (size_t)J);
+        dRecs.download(recs.p, (size_t)J);
+        eng->stats.d2hBytes += (long long)J * (long long)sizeof(Rec);
+        for (int s = 0; s < J; ++s) {
+            WTask& t = tasks[idx[i + s]];
+            t.rec = recs[s];
+            t.extra.clear();
+        }
+        i = j;
+    }
+}
+
 void WRunner::run(std::vector<WTask>& tasks) {
     std::vector<int> warp;
     std::map<std::pair<int, int>, std::vector<int>> lanes;  // (word class, lane class) -> tasks
+    std::map<int, std::vector<int>> bands;                  // window blocks -> tasks of the band kernel
     for (size_t i = 0; i < tasks.size(); ++i) {
         const int lc = lane_class(tasks[i]);
-        if (lc < 0) warp.push_back((int)i);
-        else lanes[std::make_pair(ceil_div(tasks[i].m, 32), lc)].push_back((int)i);
+        if (lc < 0) {
+            const int nb = band_blocks(tasks[i]);
+            if (nb > 0) bands[nb].push_back((int)i);
+            else warp.push_back((int)i);
+        } else {
+            lanes[std::make_pair(ceil_div(tasks[i].m, 32), lc)].push_back((int)i);
+        }
     }
+    for (auto& kv : bands) run_band(tasks, kv.second, kv.first);
     for (auto& kv : lanes) {
         int bt = 0, rc = 0;
         be->k1_shape(kv.first.first, p->ncodes, 0x7fffffff, &bt, &rc);

@@ -353,3 +353,30 @@ def tied_ends_cases(seed, count):
             if q:
                 qs.append(q)
         yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 2, 5, 20]), mode=2, task=(it + seed) % 3, eqs=None)
+
+
+def band_cases(seed, count):
+    """Pairwise NW batches of long queries (2,100 .. 12,000 rows) with a bound k or with k = -1 (doubling): the k-banded
+    sweeps run on the thread-per-alignment band kernel (eb_core.h: band_job) at several window sizes; targets are
+    mutated copies (some beyond the bound), some with a long insertion or deletion so that the band sits off the
+    main diagonal, protein-sized alphabets included."""
+    from helpers import mutate, rand_seq
+    rng = random.Random(seed)
+    for it in range(count):
+        alpha = rng.choice([b"ACGT", b"ACGT", b"ACGTN", b"ACDEFGHIKLMNPQRSTVWY"])
+        k = rng.choice([-1, 40, 90, 200, 500, 900])
+        qs, ts = [], []
+        for _ in range(rng.randrange(3, 9)):
+            m = rng.choice([2100, 3000, 4097, 6000, 10000, 12000])
+            q = rand_seq(rng, m, alpha)
+            t = mutate(rng, q, rng.choice([0.0, 0.005, 0.02, 0.03, 0.06]), alpha)
+            shift = rng.choice([0, 0, 0, 17, 150, 400])
+            if shift and rng.random() < 0.5:
+                at = rng.randrange(0, len(t))
+                t = t[:at] + rand_seq(rng, shift, alpha) + t[at:]
+            elif shift:
+                at = rng.randrange(0, max(1, len(t) - shift))
+                t = t[:at] + t[at + shift:]
+            qs.append(q)
+            ts.append(t)
+        yield dict(qs=qs, ts=ts, k=k, mode=0, task=rng.choice([0, 1]), eqs=None)

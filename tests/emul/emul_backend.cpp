@@ -86,6 +86,26 @@ void emul_lane(const LParams& p, int mode, bool rev, bool store) {
     }
 }
 
+// Window of the profile of one emulated band thread: plain array [code][slot].
+struct HostBandAcc {
+    std::vector<uint32_t> w;
+    int slots = 0, org = 0;
+    void set(int code, int slot, uint32_t bits) { w[(size_t)code * slots + slot] = bits; }
+    uint32_t get(int code, int slot) const { return w[(size_t)code * slots + slot]; }
+    void origin(int slot) { org = slot; }
+    uint32_t code_off(uint32_t sym) const { return sym * (uint32_t)slots; }
+    uint32_t load(uint32_t codeOff, int word) const { return w[(size_t)codeOff + org + word]; }
+};
+template <int NB>
+void emul_band(const WParams& p, int ncodes) {
+    HostBandAcc acc;
+    acc.slots = 4 * NB + BAND_SLACK;
+    for (int j = 0; j < p.numJobs; ++j) {
+        acc.w.assign((size_t)ncodes * acc.slots, 0xdeadbeefu);  // slots never written must never be read
+        band_job<NB>(p, j, acc, ncodes);
+    }
+}
+
 struct EmulBackend : Backend {
     int launchesCount = 0;
     void* alloc(size_t bytes) override {
@@ -229,6 +249,21 @@ struct EmulBackend : Backend {
                 case 8: w_dispatch<ebhost::HostWarp, 8>(p, j); break;
                 default: throw std::runtime_error("bad W chunk size");
             }
+        }
+    }
+    int band_max_blocks(int ncodes) override { return ncodes <= 64 ? 8 : 0; }
+    void launch_band(const WParams& p, int NB, int ncodes) override {
+        ++launchesCount;
+        switch (NB) {
+            case 1: emul_band<1>(p, ncodes); break;
+            case 2: emul_band<2>(p, ncodes); break;
+            case 3: emul_band<3>(p, ncodes); break;
+            case 4: emul_band<4>(p, ncodes); break;
+            case 5: emul_band<5>(p, ncodes); break;
+            case 6: emul_band<6>(p, ncodes); break;
+            case 7: emul_band<7>(p, ncodes); break;
+            case 8: emul_band<8>(p, ncodes); break;
+            default: throw std::runtime_error("bad band window size");
         }
     }
     void launch_split(const SplitParams& p) override {

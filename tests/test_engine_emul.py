@@ -46,6 +46,22 @@ def test_long_queries(emul):
     assert parity.run_single(emul, 13, 40, gen=cases.long_cases) == 40
 
 
+def test_banded_nw_of_long_queries_on_the_band_kernel():
+    """k-banded NW sweeps of long queries: thread-per-alignment band kernel (several window sizes in one batch), and the
+    same batches on the warp kernel's sliding window (EDLIB_B200_BAND_KERNEL=0)."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 61, 10, gen=cases.band_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra, want in (({}, True), ({"EDLIB_B200_BAND_KERNEL": "0"}, False)):
+        env = dict(os.environ, EDLIB_B200_TRACE="1", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) >= 30
+        assert ("band kernel:" in out.stderr) == want
+
+
 def test_chunked_sweeps_and_overflow_retry():
     """Same batches with tiny chunk / overflow limits so that target chunking with halo, the
     overflow list and its exact-size second pass are all exercised (separate process: the
