@@ -349,6 +349,57 @@ struct FinParams {
     const int* winCount;     // copied into header[3]
 };
 
+// ---------------------------------------------------------------------------------------------
+// Start locations and alignment paths of short queries (<= 256 rows) WITHOUT the host in the loop: the jobs of the
+// lane kernel (reversed SHW sweeps of ref cpp:253-257; matrix-storing NW sweeps + traceback of ref cpp:276-289,
+// 1161-1213) are derived on the device from the per-pair results, and their outcome is written straight into the
+// batch's start-location pool / a dense pool of edit scripts.  `stage` selects the per-item function of res_kernel.
+// ---------------------------------------------------------------------------------------------
+enum ResStage : int {
+    RS_LOC_COUNT = 0,    // cnt[pair] = end locations of the pair if it belongs to word class nw (else 0)        -> scan
+    RS_LOC_JOBS = 1,     // item = slot job j: LJob of the reversed sweep from end location j of its pair
+    RS_LOC_APPLY = 2,    // item = slot job j: startPool[slot] = end - last best column of the sweep (ref cpp:260)
+    RS_PATH_FLAG = 3,    // cnt[pair] = 1 if the pair gets a path from this launch (class nw, found, in [firstPair, lastPair)) -> scan
+    RS_PATH_JOBS = 4,    // item = pair: LJob (storing) + TbJob of its first (start, end)
+    RS_PATH_LEN = 5,     // item = job: len[j] = ops of its edit script                                          -> scan
+    RS_PATH_COPY = 6,    // item = job: edit script into the dense pool; alnStart / alnLen of the pair
+};
+struct ResParams {
+    int stage;
+    int nw;                  // word class handled by this launch
+    int numPairs;            // N
+    int numItems;            // items of this stage (pairs, or jobs)
+    int firstPair, lastPair; // RS_PATH_*: the pair range of this slice
+    // per-pair inputs
+    const int* ed;           // [N] distance or < 0
+    const int* endCount;     // [N]
+    const long long* endStart;  // [N] into endPool / startPool
+    const int* endPool;
+    const int* qlen;         // [N]
+    const uint64_t* qoff;    // [N]
+    const uint64_t* tOffPair;  // [N] offset of the pair's target in the packed buffer, or nullptr: tOff0 for every pair
+    uint64_t tOff0;
+    // scan arrays / job arrays
+    int* cnt;                // [numPairs + 1] or [numJobs + 1]: counts, then exclusive prefix sums
+    LJob* jobs;
+    int* jobPair;            // [job] pair of the job
+    long long* jobSlot;      // [job] RS_LOC_*: slot of the job's end location
+    const Rec* recs;         // [job] outcome of the lane sweeps
+    int* startPool;          // out (RS_LOC_APPLY); in (RS_PATH_JOBS)
+    TbJob* tb;
+    int maxPathN;            // RS_PATH_*: longest target slice (columns) a path job of this launch may have
+    uint64_t matStride;      // U2 entries reserved per path job
+    uint64_t opsStride;      // bytes reserved per path job
+    const uint8_t* ops;      // traceback output (opsStride per job), opsStart / opsLen per job
+    const int* opsStart;
+    const int* opsLen;
+    uint8_t* alnPool;        // dense pool of this slice
+    long long alnBase;       // offset of that pool in the batch's alignment pool
+    long long* alnStart;     // [N]
+    int* alnLen;             // [N]
+    int* err;                // set to 1 when a sweep disagrees with the distance it was started from
+};
+
 // Presence / alphabet kernels.
 struct MaskItem {
     uint64_t off;            // into raw

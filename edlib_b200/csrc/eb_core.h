@@ -1060,6 +1060,11 @@ template <int NW, int MODE, bool REV, bool STORE, class Acc>
 EB_HD void lane_job(const LParams& p, int jobIdx, Acc& acc) {
     const LJob J = p.jobs[jobIdx];
     Rec* rec = p.recs + jobIdx;
+    if (J.m <= 0) {  // placeholder job of a device-built list (eb_common.h: ResParams)
+        rec->best = 0x7fffffff;
+        rec->cnt = 0;
+        return;
+    }
     k1_build_peq<NW>(acc, p.qcodes + J.qOff, J.m, MODE, p.ncodes, p.eqtab, REV);
     K1State<NW> st;
     k1_init<NW>(st, J.m, J.kInit);
@@ -1101,6 +1106,133 @@ EB_HD void lane_job(const LParams& p, int jobIdx, Acc& acc) {
     }
     rec->best = st.best;
     rec->cnt = st.cnt;
+}
+
+// =============================================================================================
+// Start locations / paths of short queries driven from the device (eb_common.h: ResParams): per-item functions of
+// the stages around the lane and traceback kernels.
+// =============================================================================================
+EB_HD bool res_in_class(const ResParams& p, int pair) {
+    const int m = p.qlen[pair];
+    return p.ed[pair] >= 0 && m > 0 && (m + 31) / 32 == p.nw;
+}
+EB_HD uint64_t res_target_off(const ResParams& p, int pair) { return p.tOffPair ? p.tOffPair[pair] : p.tOff0; }
+
+// largest i in [0, n) with a[i] <= v (a ascending, a[0] <= v)
+EB_HD int res_owner(const int* a, int n, int v) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a[mid] <= v) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+EB_HD void res_item(const ResParams& p, int i) {
+    switch (p.stage) {
+        case RS_LOC_COUNT: {
+            p.cnt[i] = res_in_class(p, i) ? p.endCount[i] : 0;
+            break;
+        }
+        case RS_LOC_JOBS: {  // job i = end location (i - cnt[pair]) of its pair (ref cpp:230-262)
+            const int pair = res_owner(p.cnt, p.numPairs, i);
+            const long long slot = p.endStart[pair] + (i - p.cnt[pair]);
+            const int e = p.endPool[slot], m = p.qlen[pair], d = p.ed[pair];
+            LJob J;
+            J.qOff = p.qoff[pair];
+            J.tOff = res_target_off(p, pair) + (uint64_t)(e < 0 ? 0 : e);  // first symbol read, walking backwards
+            J.matOff = 0;
+            J.m = e < 0 ? 0 : m;  // end location -1 (ref cpp:237-249): start 0, no sweep (m == 0 jobs are skipped)
+            const long long span = (long long)m + d;
+            J.n = (int)((long long)e + 1 < span ? (long long)e + 1 : span);
+            J.kInit = d + 1;
+            J.trackFrom = 0;
+            p.jobs[i] = J;
+            p.jobPair[i] = pair;
+            p.jobSlot[i] = slot;
+            break;
+        }
+        case RS_LOC_APPLY: {
+            const int pair = p.jobPair[i];
+            const long long slot = p.jobSlot[i];
+            const int e = p.endPool[slot];
+            if (e < 0) {
+                p.startPool[slot] = 0;
+            } else {
+                const Rec r = p.recs[i];
+                if (r.cnt <= 0 || r.best != p.ed[pair]) *p.err = 1;
+                p.startPool[slot] = e - r.last;  // ref cpp:260
+            }
+            break;
+        }
+        case RS_PATH_FLAG: {  // pairs whose target slice is longer than the launch provides for stay with the host tree
+            const int pair = p.firstPair + i;
+            int take = 0;
+            if (pair < p.lastPair && res_in_class(p, pair)) {
+                const long long slot = p.endStart[pair];
+                take = (p.endPool[slot] - p.startPool[slot] + 1 <= p.maxPathN) ? 1 : 0;
+            }
+            p.cnt[i] = take;
+            break;
+        }
+        case RS_PATH_JOBS: {  // item = pair offset inside the slice
+            const int pair = p.firstPair + i;
+            if (p.cnt[i + 1] == p.cnt[i]) break;
+            const int j = p.cnt[i];
+            const long long slot = p.endStart[pair];
+            const int s0 = p.startPool[slot], e0 = p.endPool[slot];
+            LJob J;
+            J.qOff = p.qoff[pair];
+            J.tOff = res_target_off(p, pair) + (uint64_t)s0;
+            J.matOff = (uint64_t)j * p.matStride;
+            J.m = p.qlen[pair];
+            J.n = e0 - s0 + 1;  // <= 0: empty target slice, the script is m inserts (ref cpp:1168-1175)
+            if (J.n < 0) J.n = 0;
+            J.kInit = 0;
+            J.trackFrom = 0;
+            if ((uint64_t)J.n * (uint64_t)p.nw > p.matStride) {  // cannot happen: the stride covers m + ed columns
+                *p.err = 1;
+                J.n = 0;
+            }
+            p.jobs[j] = J;
+            TbJob T;
+            T.matOff = J.matOff;
+            T.qOff = J.qOff;
+            T.peqOff = ~0ull;
+            T.tOff = J.tOff;
+            T.outOff = (uint64_t)j * p.opsStride;
+            T.m = J.m;
+            T.n = J.n;
+            T.nWp = p.nw;
+            T.rsv = 0;
+            p.tb[j] = T;
+            p.jobPair[j] = pair;
+            break;
+        }
+        case RS_PATH_LEN: {
+            const LJob J = p.jobs[i];
+            if (J.n > 0 && p.recs[i].best != p.ed[p.jobPair[i]]) *p.err = 1;
+            p.cnt[i] = J.n > 0 ? p.opsLen[i] : J.m;
+            break;
+        }
+        case RS_PATH_COPY: {
+            const LJob J = p.jobs[i];
+            const int pair = p.jobPair[i];
+            const int len = p.cnt[i + 1] - p.cnt[i];
+            uint8_t* dst = p.alnPool + p.cnt[i];
+            if (J.n > 0) {
+                const uint8_t* src = p.ops + (uint64_t)i * p.opsStride + (uint64_t)p.opsStart[i];
+                for (int x = 0; x < len; ++x) dst[x] = src[x];
+            } else {
+                for (int x = 0; x < len; ++x) dst[x] = 1;  // EDLIB_EDOP_INSERT
+            }
+            p.alnStart[pair] = p.alnBase + p.cnt[i];
+            p.alnLen[pair] = len;
+            break;
+        }
+        default: break;
+    }
 }
 
 // =============================================================================================
@@ -1554,6 +1686,11 @@ EB_HD void peq_build_words(const PeqParams& p, int jobIdx, int firstWord, int wo
 // cpp:1025-1029, 1059-1065, 1090-1103.  Ops are written back-to-front, so no final reverse.
 EB_HD void traceback_job(const TbParams& p, int jobIdx) {
     const TbJob J = p.jobs[jobIdx];
+    if (J.n <= 0 || J.m <= 0) {  // empty side: the caller fills the script (ref cpp:1168-1175)
+        p.opsStart[jobIdx] = 0;
+        p.opsLen[jobIdx] = 0;
+        return;
+    }
     const U2* mat = p.mat + J.matOff;
     const uint32_t* peq = p.peq + (J.peqOff != ~0ull ? J.peqOff : 0);
     const uint8_t* t = p.tcodes + J.tOff;

@@ -64,6 +64,8 @@ struct Backend {
     virtual int band_max_blocks(int ncodes) = 0;
     virtual void launch_band(const WParams& p, int NB, int ncodes) = 0;
     virtual void launch_traceback(const TbParams& p) = 0;
+    // one stage of the device-driven start-location / path pipeline of short queries (eb_common.h: ResParams)
+    virtual void launch_res(const ResParams& p) = 0;
     virtual void launch_split(const SplitParams& p) = 0;
     // seed stage of the candidate filter: index build (count / scan / fill), per-read planning, window reduction
     virtual void launch_seed_count(const SeedIndexParams& p) = 0;
@@ -96,6 +98,8 @@ struct EngineTunables {
     int k1MinChunk = 1024;        // smallest target chunk (columns) when one HW sweep is split
     int ovfCap = 1 << 20;         // overflow entries per launch before the exact-size retry
     size_t sliceBytes = 1ull << 30;  // device memory budget of one slice of W jobs
+    size_t pathSliceBytes = 8ull << 30;  // ... of one slice of device-driven paths of short queries (stored matrices)
+    int deviceResults = 1;        // start locations / paths of short queries driven from the device (0: per-job host objects)
     size_t packParallelBytes = 32u << 20;  // batches above this are packed and uploaded by several host threads
     // Candidate filter for HW sweeps of reads over a shared target, three stages (0 disables one):
     // exact seeds looked up in a hash index of the target (pigeonhole: t+1 disjoint seeds for threshold

@@ -265,6 +265,20 @@ struct PinnedVec {
         n = c;
     }
     void clear() { n = 0; }
+    void assign(size_t c, const T& v) {
+        resize(c);
+        for (size_t i = 0; i < c; ++i) p[i] = v;
+    }
+    void append(const T* src, size_t c) {
+        const size_t at = n;
+        resize(n + c);
+        if (c) memcpy(p + at, src, c * sizeof(T));
+    }
+    void append_fill(size_t c, const T& v) {
+        const size_t at = n;
+        resize(n + c);
+        for (size_t i = 0; i < c; ++i) p[at + i] = v;
+    }
     size_t size() const { return n; }
     bool empty() const { return n == 0; }
     T* data() { return p; }
@@ -343,10 +357,10 @@ public:
     PinnedVec<long long> endStart;  // end locations of pair i: endPool[endStart[i] .. + endCount[i])
     PinnedVec<int> endCount;
     PinnedVec<int> endPool;         // not compact: regions filled by the device, then the host-assembled tail
-    std::vector<int> startPool;
-    std::vector<long long> alnStart;  // -1: none
-    std::vector<int> alnLen;
-    std::vector<uint8_t> alnPool;
+    PinnedVec<int> startPool;
+    PinnedVec<long long> alnStart;  // -1: none
+    PinnedVec<int> alnLen;
+    PinnedVec<uint8_t> alnPool;
     bool computed = false;
     void bind(Backend* b) {
         be = b;
@@ -355,6 +369,10 @@ public:
         endStart.bind(b);
         endCount.bind(b);
         endPool.bind(b);
+        startPool.bind(b);
+        alnStart.bind(b);
+        alnLen.bind(b);
+        alnPool.bind(b);
     }
 };
 
@@ -655,6 +673,24 @@ struct Pass {
     void start_locations();
 
     void paths();
+
+    // ---- start locations / paths of short queries (<= 256 rows) driven from the device (eb_pass_results.cpp) ----
+    // Word classes (bit nw) that hold found pairs the lane kernel can sweep, bit 0: some found pair is of no such class.
+    unsigned resClasses = 0;
+    bool resUploaded = false;
+    DevBuf<int> rEd, rEndCount, rEndPool, rStartPool, rErr;
+    DevBuf<long long> rEndStart;
+    DevBuf<uint64_t> rTOffPair;
+    void res_begin();                    // classes + per-pair results on the device
+    void res_fill(ResParams& rp, int nw);
+    void res_check();
+    int resMaxEd = 0;
+    // Longest target slice a device-driven path of word class nw may have (longer ones, rare, take the host tree;
+    // always inside the reference's 1 MiB rule, ref cpp:1188-1190, for queries of <= 256 rows).
+    int res_max_path_n(int nw) const { return std::min(64 * nw, 32 * nw + resMaxEd); }
+    bool res_class(int m) const { return m > 0 && m <= 256 && ((resClasses >> ((m + 31) / 32)) & 1u); }
+    void start_locations_device();
+    void paths_device();
 };
 
 }  // namespace eb

@@ -369,6 +369,11 @@ __global__ void traceback_kernel(const TbParams p) {
     if (job < p.numJobs) traceback_job(p, job);
 }
 
+__global__ void res_kernel(const ResParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.numItems) res_item(p, i);
+}
+
 __global__ void split_kernel(const SplitParams p) {
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
     if (node < p.numNodes) split_node(p, node);
@@ -943,6 +948,12 @@ struct CudaBackend : Backend {
             case 8: launch_lane_t<8>(p, mode, rev, store); break;
             default: throw std::runtime_error("bad lane word class");
         }
+    }
+    void launch_res(const ResParams& p) override {
+        if (p.numItems <= 0) return;
+        Scope s(this, "res");
+        res_kernel<<<(p.numItems + 255) / 256, 256, 0, stream>>>(p);
+        check_launch("res");
     }
     void launch_peq(const PeqParams& p) override {
         Scope s(this, "peq");

@@ -381,12 +381,232 @@ void Pass::collect_ends(const std::vector<int>* pairs) {
     });
 }
 
+// =============================================================================================
+// Start locations and paths of short queries (<= 256 rows) driven from the device.  A read set needs one reversed
+// sweep per end location and one matrix-storing sweep + traceback per read: millions of tiny jobs.  Their
+// descriptors are derived on the device from the per-pair results (eb_core.h: res_item), the lane / traceback
+// kernels run on those lists, and the outcome lands in the batch's start-location pool and in a dense pool of edit
+// scripts that comes back in one copy per slice -- the host neither builds nor walks per-job objects.
+// =============================================================================================
+void Pass::res_begin() {
+    if (resUploaded) return;
+    resUploaded = true;
+    // word classes that hold found pairs; bit 0: found pairs the lane kernel cannot take (long queries, big alphabets)
+    const size_t nparts = host_parts((size_t)N, 65536);
+    std::vector<unsigned> part(nparts, 0u);
+    HostPool::get().run(nparts, [&](size_t t) {
+        unsigned bits = 0;
+        for (size_t i = (size_t)N * t / nparts, hi = (size_t)N * (t + 1) / nparts; i < hi; ++i) {
+            if (p->ed[i] < 0 || p->special[i]) continue;
+            const int m = p->qlen[i];
+            bits |= (m > 0 && m <= 256) ? (1u << ((m + 31) / 32)) : 1u;
+        }
+        part[t] = bits;
+    });
+    resClasses = 0;
+    for (unsigned b : part) resClasses |= b;
+    for (int nw = 1; nw <= 8; ++nw)
+        if (((resClasses >> nw) & 1u) && !lane_ok(32 * nw)) resClasses = (resClasses & ~(1u << nw)) | 1u;
+    if (!tun.deviceResults) resClasses = (resClasses & ~0x1feu) | ((resClasses & 0x1feu) ? 1u : 0u);
+    if (!(resClasses & 0x1feu)) return;
+    rEd.alloc(be, (size_t)N);
+    rEndCount.alloc(be, (size_t)N);
+    rEndStart.alloc(be, (size_t)N);
+    rEndPool.alloc(be, p->endPool.size());
+    rEd.upload(p->ed.data(), (size_t)N);
+    rEndCount.upload(p->endCount.data(), (size_t)N);
+    rEndStart.upload(p->endStart.data(), (size_t)N);
+    rEndPool.upload(p->endPool.data(), p->endPool.size());
+    stats.h2dBytes += 16LL * N + 4LL * (long long)p->endPool.size();
+    if (p->tg.size() > 1) {
+        HostBuf<uint64_t> offs(be, (size_t)N);
+        parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) offs[i] = p->tg[p->tidx[i]].off;
+        });
+        rTOffPair.alloc(be, (size_t)N);
+        rTOffPair.upload(offs.p, (size_t)N);
+        be->sync();  // the staging block goes back to the cache
+        stats.h2dBytes += 8LL * N;
+    }
+    rErr.alloc(be, 1);
+    be->zero(rErr.p, sizeof(int));
+}
+
+void Pass::res_fill(ResParams& rp, int nw) {
+    memset(&rp, 0, sizeof(rp));
+    rp.nw = nw;
+    rp.numPairs = N;
+    rp.ed = rEd.p;
+    rp.endCount = rEndCount.p;
+    rp.endStart = rEndStart.p;
+    rp.endPool = rEndPool.p;
+    rp.qlen = p->dQlen.p;
+    rp.qoff = p->dQoff.p;
+    rp.tOffPair = p->tg.size() > 1 ? rTOffPair.p : nullptr;
+    rp.tOff0 = p->tg.empty() ? 0 : p->tg[0].off;
+    rp.startPool = rStartPool.p;
+    rp.err = rErr.p;
+}
+
+void Pass::res_check() {
+    int err = 0;
+    rErr.download(&err, 1);
+    if (err) throw std::runtime_error("internal: a start-location / path sweep disagrees with the distance");
+}
+
+// HW start locations (ref cpp:228-272) of every found pair of the lane kernel's word classes.
+void Pass::start_locations_device() {
+    res_begin();
+    if (!(resClasses & 0x1feu)) return;
+    rStartPool.alloc(be, p->endPool.size());
+    be->zero(rStartPool.p, p->endPool.size() * sizeof(int));
+    DevBuf<int> dCnt(be, (size_t)N + 1);
+    for (int nw = 1; nw <= 8; ++nw) {
+        if (!((resClasses >> nw) & 1u)) continue;
+        ResParams rp;
+        res_fill(rp, nw);
+        rp.cnt = dCnt.p;
+        rp.stage = RS_LOC_COUNT;
+        rp.numItems = N;
+        be->launch_res(rp);
+        be->launch_scan(dCnt.p, N);
+        int T = 0;
+        be->d2h(&T, dCnt.p + N, sizeof(int));
+        if (T <= 0) continue;
+        DevBuf<LJob> dJobs(be, (size_t)T);
+        DevBuf<int> dJobPair(be, (size_t)T);
+        DevBuf<long long> dJobSlot(be, (size_t)T);
+        DevBuf<Rec> dRecs(be, (size_t)T);
+        rp.jobs = dJobs.p;
+        rp.jobPair = dJobPair.p;
+        rp.jobSlot = dJobSlot.p;
+        rp.recs = dRecs.p;
+        rp.stage = RS_LOC_JOBS;
+        rp.numItems = T;
+        be->launch_res(rp);
+        LParams lp{dJobs.p, T, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, nullptr};
+        be->launch_lane(lp, nw, MODE_SHW, true, false);
+        rp.stage = RS_LOC_APPLY;
+        be->launch_res(rp);
+    }
+    be->d2h(p->startPool.data(), rStartPool.p, p->endPool.size() * sizeof(int));
+    stats.d2hBytes += 4LL * (long long)p->endPool.size();
+    res_check();
+    trace.mark("starts: device-driven lane sweeps");
+}
+
+// Paths (ref cpp:276-289, 1161-1213: inside the 1 MiB rule for every query of <= 256 rows) of the first (start, end)
+// of every found pair of the lane kernel's word classes: matrix-storing sweep + traceback per pair, in slices of pairs
+// whose stored matrices fit the slice budget; the scripts are compacted on the device and copied into alnPool.
+void Pass::paths_device() {
+    res_begin();
+    if (!(resClasses & 0x1feu)) return;
+    if (!rStartPool.p) {  // (start locations were not computed through the device path: cannot happen for PATH)
+        rStartPool.alloc(be, p->startPool.size());
+        rStartPool.upload(p->startPool.data(), p->startPool.size());
+    }
+    int maxEd = 0;
+    {
+        const size_t nparts = host_parts((size_t)N, 65536);
+        std::vector<int> part(nparts, 0);
+        HostPool::get().run(nparts, [&](size_t t) {
+            int mx = 0;
+            for (size_t i = (size_t)N * t / nparts, hi = (size_t)N * (t + 1) / nparts; i < hi; ++i) mx = std::max(mx, p->ed[i]);
+            part[t] = mx;
+        });
+        for (int v : part) maxEd = std::max(maxEd, v);
+    }
+    resMaxEd = maxEd;
+    DevBuf<long long> dAlnStart(be, (size_t)N);
+    DevBuf<int> dAlnLen(be, (size_t)N);
+    be->fill(dAlnStart.p, 0xff, (size_t)N * sizeof(long long));  // -1: no path
+    be->zero(dAlnLen.p, (size_t)N * sizeof(int));
+    long long poolAt = (long long)p->alnPool.size();
+    for (int nw = 1; nw <= 8; ++nw) {
+        if (!((resClasses >> nw) & 1u)) continue;
+        const uint64_t maxN = (uint64_t)res_max_path_n(nw);  // target slice of a path: at most m + distance symbols
+        const uint64_t matStride = maxN * (uint64_t)nw, opsStride = (uint64_t)32 * nw + maxN;
+        const size_t perJob = (size_t)matStride * sizeof(U2) + (size_t)opsStride + sizeof(LJob) + sizeof(TbJob) + sizeof(Rec) + 64;
+        const int S = (int)std::max<size_t>(64, std::min<size_t>((size_t)N, tun.pathSliceBytes / perJob));
+        DevBuf<int> dCnt(be, (size_t)S + 1), dLen(be, (size_t)S + 1);
+        for (int first = 0; first < N; first += S) {
+            const int last = std::min(N, first + S), span = last - first;
+            ResParams rp;
+            res_fill(rp, nw);
+            rp.firstPair = first;
+            rp.lastPair = last;
+            rp.maxPathN = (int)maxN;
+            rp.cnt = dCnt.p;
+            rp.stage = RS_PATH_FLAG;
+            rp.numItems = span;
+            be->launch_res(rp);
+            be->launch_scan(dCnt.p, span);
+            int J = 0;
+            be->d2h(&J, dCnt.p + span, sizeof(int));
+            if (J <= 0) continue;
+            DevBuf<LJob> dJobs(be, (size_t)J);
+            DevBuf<TbJob> dTb(be, (size_t)J);
+            DevBuf<int> dJobPair(be, (size_t)J), dOpsStart(be, (size_t)J), dOpsLen(be, (size_t)J);
+            DevBuf<Rec> dRecs(be, (size_t)J);
+            DevBuf<U2> dMat(be, (size_t)J * matStride);
+            DevBuf<uint8_t> dOps(be, (size_t)J * opsStride);
+            rp.jobs = dJobs.p;
+            rp.tb = dTb.p;
+            rp.jobPair = dJobPair.p;
+            rp.recs = dRecs.p;
+            rp.matStride = matStride;
+            rp.opsStride = opsStride;
+            rp.stage = RS_PATH_JOBS;
+            be->launch_res(rp);
+            LParams lp{dJobs.p, J, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p};
+            be->launch_lane(lp, nw, MODE_NW, false, true);
+            TbParams tp{dTb.p, J, dMat.p, nullptr, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
+                        dOps.p, dOpsStart.p, dOpsLen.p};
+            be->launch_traceback(tp);
+            rp.cnt = dLen.p;
+            rp.ops = dOps.p;
+            rp.opsStart = dOpsStart.p;
+            rp.opsLen = dOpsLen.p;
+            rp.stage = RS_PATH_LEN;
+            rp.numItems = J;
+            be->launch_res(rp);
+            be->launch_scan(dLen.p, J);
+            int bytes = 0;
+            be->d2h(&bytes, dLen.p + J, sizeof(int));
+            DevBuf<uint8_t> dAln(be, (size_t)std::max(bytes, 1));
+            rp.alnPool = dAln.p;
+            rp.alnBase = poolAt;
+            rp.alnStart = dAlnStart.p;
+            rp.alnLen = dAlnLen.p;
+            rp.stage = RS_PATH_COPY;
+            be->launch_res(rp);
+            p->alnPool.resize((size_t)(poolAt + bytes));
+            if (bytes) be->d2h(p->alnPool.data() + poolAt, dAln.p, (size_t)bytes);
+            poolAt += bytes;
+            stats.d2hBytes += (long long)bytes + 8;
+        }
+    }
+    // per-pair script positions: the device wrote the pairs it handled, the others stay at -1 / 0
+    be->d2h(p->alnStart.data(), dAlnStart.p, (size_t)N * sizeof(long long));
+    be->d2h(p->alnLen.data(), dAlnLen.p, (size_t)N * sizeof(int));
+    stats.d2hBytes += 12LL * N;
+    res_check();
+    trace.mark("paths: device-driven leaf sweeps + tracebacks");
+}
+
 void Pass::start_locations() {
     // ---- start locations (ref cpp:228-272) ------------------------------------------------
     const bool wantLoc = p->cfg.task == EDLIB_TASK_LOC || p->cfg.task == EDLIB_TASK_PATH;
     if (wantLoc) {
-        p->startPool.assign(p->endPool.size(), 0);
-        if (mode == MODE_HW) {
+        p->startPool.resize(p->endPool.size());
+        if (mode != MODE_HW) {
+            parallel_ranges(p->startPool.size(), 1 << 20, [&](size_t lo, size_t hi) { memset(p->startPool.data() + lo, 0, (hi - lo) * sizeof(int)); });
+        } else {
+            start_locations_device();  // every found pair of the lane kernel's word classes (or nothing)
+            if (!(resClasses & 0x1feu))
+                parallel_ranges(p->startPool.size(), 1 << 20, [&](size_t lo, size_t hi) { memset(p->startPool.data() + lo, 0, (hi - lo) * sizeof(int)); });
+        }
+        if (mode == MODE_HW && (resClasses & 1u)) {  // found pairs outside those classes: per-job objects on the host
             std::vector<WTask> tasks;
             std::vector<long long> slotOf;
             std::vector<LJob> lj[9];          // short queries: straight to the lane kernel, per word class
@@ -395,8 +615,10 @@ void Pass::start_locations() {
             for (int i = 0; i < N; ++i) {
                 if (p->ed[i] < 0) continue;
                 const int m = p->qlen[i];
+                if (res_class(m)) continue;  // done on the device
                 const bool lane = lane_ok(m);
                 for (int q = 0; q < p->endCount[i]; ++q) {
+                    p->startPool[(size_t)(p->endStart[i] + q)] = 0;
                     const long long slot = p->endStart[i] + q;
                     const int e = p->endPool[(size_t)slot];
                     if (e < 0) continue;  // ref cpp:237-249: start 0
@@ -474,9 +696,20 @@ void Pass::paths() {
             int fillOp = -1;        // ... or a run of one op (empty side, cpp:1168-1175)
         };
         std::vector<Node> nodes;
-        std::vector<int> rootOf(N, -1), frontier, leaves;
+        std::vector<int> rootOf, frontier, leaves;
+        paths_device();  // every found pair of the lane kernel's word classes (or nothing)
+        {
+            std::atomic<int> open(0);  // found pairs the device did not handle (long queries, long target slices)
+            parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+                bool any = false;
+                for (size_t i = lo; i < hi && !any; ++i) any = p->ed[i] >= 0 && p->alnStart[i] < 0;
+                if (any) open.store(1, std::memory_order_relaxed);
+            });
+            if (!open.load()) return;
+        }
+        rootOf.assign(N, -1);
         for (int i = 0; i < N; ++i) {
-            if (p->ed[i] < 0) continue;
+            if (p->ed[i] < 0 || p->alnStart[i] >= 0) continue;  // no result / done on the device
             const int s0 = p->startPool[(size_t)p->endStart[i]], e0 = p->endPool[(size_t)p->endStart[i]];
             Node nd;
             nd.pair = i;
@@ -626,9 +859,9 @@ void Pass::paths() {
                     stack.push_back(nd.right);
                     stack.push_back(nd.left);
                 } else if (nd.fillOp >= 0) {
-                    p->alnPool.insert(p->alnPool.end(), (size_t)nd.opsLen, (uint8_t)nd.fillOp);
+                    p->alnPool.append_fill((size_t)nd.opsLen, (uint8_t)nd.fillOp);
                 } else {
-                    p->alnPool.insert(p->alnPool.end(), opsPool.begin() + nd.opsOff, opsPool.begin() + nd.opsOff + nd.opsLen);
+                    p->alnPool.append(opsPool.data() + nd.opsOff, (size_t)nd.opsLen);
                 }
             }
             p->alnLen[i] = (int)(p->alnPool.size() - (size_t)p->alnStart[i]);

@@ -251,6 +251,10 @@ struct EmulBackend : Backend {
             }
         }
     }
+    void launch_res(const ResParams& p) override {
+        ++launchesCount;
+        for (int i = 0; i < p.numItems; ++i) res_item(p, i);
+    }
     int band_max_blocks(int ncodes) override { return ncodes <= 64 ? 8 : 0; }
     void launch_band(const WParams& p, int NB, int ncodes) override {
         ++launchesCount;

@@ -126,6 +126,26 @@ def test_reads_that_tie_on_many_end_columns():
         assert int(out.stdout.strip().splitlines()[-1]) > 300
 
 
+def test_start_locations_and_paths_driven_from_the_device():
+    """LOC / PATH of short queries: jobs derived on the device from the per-pair results (shared and per-pair targets,
+    several word classes per batch, slices of a few pairs), and the per-job host objects of the legacy path."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "a = parity.run_batches(lib, 71, 25)\n"
+        "b = parity.run_batches(lib, 72, 25, gen=cases.pairwise_cases)\n"
+        "c = parity.run_batches(lib, 73, 12, gen=cases.stream_cases)\n"
+        "print(a + b + c)\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra, want in (({}, True), ({"EDLIB_B200_SLICE_MB": "1", "EDLIB_B200_K1_MIN_GROUP": "4"}, True),
+                        ({"EDLIB_B200_DEVICE_RESULTS": "0"}, False)):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_TRACE="1", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 2500
+        assert ("device-driven lane sweeps" in out.stderr) == want and ("device-driven leaf sweeps" in out.stderr) == want
+
+
 def test_streamed_batches():
     """edlibAlignBatch on read-set-shaped HW batches goes through the streamed path (slices packed and uploaded
     under the kernels of earlier slices, results assembled on the device, result structs built per slice): the
