@@ -250,7 +250,7 @@ struct SeedIndexParams {
 #define SEED_LEVELS 3
 #define SEED_CAND_0 64
 #define SEED_CAND_1 256
-#define SEED_CAND_2 1024
+#define SEED_CAND_2 4096
 enum SeedState : int { SEED_NONE = 0, SEED_WINDOWS = 1, SEED_SATURATED = 2, SEED_LONG_LIST = 3 };
 struct SeedPlan {
     int first, count;        // the read's windows in the job arrays

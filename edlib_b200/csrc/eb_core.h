@@ -812,9 +812,26 @@ struct CoopSerial {
     }
 };
 
-// One read, planned by a cooperative group C (its members take the seeds of the read; a single member on the
-// host).  E[CAP] candidate end columns and ctl[2] = {candidates, saturated} are scratch shared by the group
-// (shared memory on the device).
+// Scratch of one planning group: E[CAP] candidate end columns, then SEED_CTL ints of control words:
+// ctl[0] candidates, ctl[1] saturated, ctl[2] long index ranges listed, ctl[3 + 3k ..] = {first, end, a} of range k.
+constexpr int SEED_LONG_RANGES = 16;
+constexpr int SEED_CTL = 3 + 3 * SEED_LONG_RANGES;
+
+// One occurrence list entry of seed read[a, a+Ls): verified against the target, its expected end column recorded.
+template <int CAP, class C>
+EB_HD void seed_try(const SeedPlanParams& p, const uint8_t* q, int m, int a, int Lk, int pos, int* E, int* ctl) {
+    bool same = pos + p.Ls <= p.n;  // keys near the end of the target were padded with code 0
+    for (int x = Lk; same && x < p.Ls; ++x) same = p.tcodes[pos + x] == q[a + x];
+    if (!same) return;
+    const int at = C::add_shared(&ctl[0], 1);
+    if (at < CAP) E[at] = pos + (m - a) - 1;
+}
+
+// One read, planned by a cooperative group C (a single member on the host, eight lanes on the device).  The members
+// take the seeds of the read, so that the chains of dependent random reads (key -> index range -> positions -> target
+// symbols) of different seeds are in flight together; index ranges longer than a few entries per member (repeats,
+// short seeds) are set aside and then walked by the whole group together, a member's loads two at a time.  The
+// candidates meet in E; small sets are sorted by one member, larger ones by a bitonic network over the group.
 template <int CAP, class C>
 EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl) {
     const int lane = C::lane(), W = C::width();
@@ -835,12 +852,14 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl) {
     if (lane == 0) {
         ctl[0] = 0;
         ctl[1] = 0;
+        ctl[2] = 0;
     }
     C::sync();
     const int stride = m / (t + 1);  // >= Ls: the t+1 pieces are disjoint
     const int Lk = p.Ls < p.Lidx ? p.Ls : p.Lidx;  // symbols of the seed that go into the key
     uint32_t span = 1;                             // keys sharing that prefix
     for (int x = Lk; x < p.Lidx; ++x) span *= (uint32_t)p.sigma;
+    const int longFrom = 4;  // entries a member walks alone
     for (int j0 = 0; j0 <= t; j0 += W) {
         const int j = j0 + lane;
         const int a = j * stride;
@@ -861,39 +880,74 @@ EB_HD void seed_plan_read(const SeedPlanParams& p, int slot, int* E, int* ctl) {
                 if (i1 - i0 > p.maxBucket) {  // repeat: the read is passed on unseen
                     ctl[1] = 1;
                     i1 = i0;
+                } else if (i1 - i0 > longFrom) {
+                    const int k = C::add_shared(&ctl[2], 1);
+                    if (k < SEED_LONG_RANGES) {
+                        ctl[3 + 3 * k] = i0;
+                        ctl[4 + 3 * k] = i1;
+                        ctl[5 + 3 * k] = a;
+                        i1 = i0;  // walked by the whole group below
+                    }
                 }
             }
         }
-        for (int i = i0; C::any(i < i1); ++i) {
-            if (i >= i1) continue;
-            const int pos = p.positions[i];
-            bool same = pos + p.Ls <= p.n;  // keys near the end of the target were padded with code 0
-            for (int x = Lk; same && x < p.Ls; ++x) same = p.tcodes[pos + x] == q[a + x];
-            if (!same) continue;
-            const int at = C::add_shared(&ctl[0], 1);
-            if (at < CAP) E[at] = pos + (m - a) - 1;
+        for (int i = i0; i < i1; ++i) seed_try<CAP, C>(p, q, m, a, Lk, p.positions[i], E, ctl);
+    }
+    C::sync();
+    {
+        const int nLong = ctl[2] < SEED_LONG_RANGES ? ctl[2] : SEED_LONG_RANGES;
+        for (int k = 0; k < nLong; ++k) {
+            const int i1 = ctl[4 + 3 * k], a = ctl[5 + 3 * k];
+            int i = ctl[3 + 3 * k] + lane;
+            for (; i + W < i1; i += 2 * W) {  // two independent loads per round
+                const int pos0 = p.positions[i], pos1 = p.positions[i + W];
+                seed_try<CAP, C>(p, q, m, a, Lk, pos0, E, ctl);
+                seed_try<CAP, C>(p, q, m, a, Lk, pos1, E, ctl);
+            }
+            if (i < i1) seed_try<CAP, C>(p, q, m, a, Lk, p.positions[i], E, ctl);
         }
     }
     C::sync();
-    if (lane != 0) return;
     const int c = ctl[0];
     if (ctl[1] || c > CAP) {
-        pl.state = SEED_SATURATED;
-        p.plan[slot] = pl;
+        if (lane == 0) {
+            pl.state = SEED_SATURATED;
+            p.plan[slot] = pl;
+        }
         return;
     }
-    // Shell sort (Ciura gaps; plain insertion sort when c is small, the usual case)
-    const int gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
-    for (int gi = c > 32 ? 0 : 7; gi < 8; ++gi) {
-        const int gap = gaps[gi];
-        for (int i = gap; i < c; ++i) {
-            const int v = E[i];
-            int k = i - gap;
-            while (k >= 0 && E[k] > v) {
-                E[k + gap] = E[k];
-                k -= gap;
+    if (c > 32 && CAP >= 64) {
+        // bitonic network over the candidates padded to a power of two, compare-exchanges dealt to the members
+        int P2 = 64;
+        while (P2 < c) P2 *= 2;  // <= CAP (a power of two)
+        for (int i = c + lane; i < P2; i += W) E[i] = 0x7fffffff;
+        C::sync();
+        for (int k = 2; k <= P2; k *= 2) {
+            for (int jj = k / 2; jj > 0; jj /= 2) {
+                for (int x = lane; x < P2 / 2; x += W) {
+                    const int lo = 2 * x - (x & (jj - 1));  // index with bit jj clear
+                    const int hi = lo + jj;
+                    const bool up = (lo & k) == 0;
+                    const int u = E[lo], v = E[hi];
+                    if ((u > v) == up) {
+                        E[lo] = v;
+                        E[hi] = u;
+                    }
+                }
+                C::sync();
             }
-            E[k + gap] = v;
+        }
+    }
+    if (lane != 0) return;
+    if (!(c > 32 && CAP >= 64)) {  // insertion sort (the usual case: a handful of candidates)
+        for (int i = 1; i < c; ++i) {
+            const int v = E[i];
+            int k = i - 1;
+            while (k >= 0 && E[k] > v) {
+                E[k + 1] = E[k];
+                --k;
+            }
+            E[k + 1] = v;
         }
     }
     const int nW = seed_windows(p, E, c, m, t, pair, 0, false);

@@ -398,15 +398,16 @@ struct CoopGroup8 {
     static EB_D bool any(bool v) { return __ballot_sync(mask(), v) != 0u; }
     static EB_D int add_shared(int* p, int v) { return atomicAdd(p, v); }
 };
-constexpr int SEED_PLAN_THREADS = 128, SEED_PLAN_GROUPS = SEED_PLAN_THREADS / 8;
-template <int CAP>
-__global__ void __launch_bounds__(SEED_PLAN_THREADS) seed_plan_kernel(const SeedPlanParams p) {
+// (CTAs of THREADS / 8 groups: the largest candidate capacity gets small CTAs so that its scratch fits shared memory)
+template <int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS) seed_plan_kernel(const SeedPlanParams p) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
+    constexpr int GROUPS = THREADS / 8;
     int* E = reinterpret_cast<int*>(smemRaw);              // [groups][CAP]
-    int* ctl = E + SEED_PLAN_GROUPS * CAP;                  // [groups][2]
+    int* ctl = E + GROUPS * CAP;                            // [groups][SEED_CTL]
     const int g = threadIdx.x >> 3;
-    const int slot = blockIdx.x * SEED_PLAN_GROUPS + g;
-    if (slot < p.numReads) seed_plan_read<CAP, CoopGroup8>(p, slot, E + g * CAP, ctl + g * 2);
+    const int slot = blockIdx.x * GROUPS + g;
+    if (slot < p.numReads) seed_plan_read<CAP, CoopGroup8>(p, slot, E + g * CAP, ctl + g * SEED_CTL);
 }
 __global__ void win_reduce_kernel(const WinReduceParams p) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1029,18 +1030,19 @@ struct CudaBackend : Backend {
         }
         free(tileSums);
     }
+    template <int CAP, int THREADS>
+    void launch_seed_plan_t(const SeedPlanParams& p) {
+        constexpr int GROUPS = THREADS / 8;
+        const size_t smem = (size_t)GROUPS * ((size_t)CAP + SEED_CTL) * sizeof(int);
+        if (smem > 48 * 1024)
+            EB_CUDA(cudaFuncSetAttribute(seed_plan_kernel<CAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        seed_plan_kernel<CAP, THREADS><<<(p.numReads + GROUPS - 1) / GROUPS, THREADS, smem, stream>>>(p);
+    }
     void launch_seed_plan(const SeedPlanParams& p) override {
         Scope s(this, "seed_plan");
-        const int grid = (p.numReads + SEED_PLAN_GROUPS - 1) / SEED_PLAN_GROUPS;
-        auto smem_of = [](int cap) { return (size_t)SEED_PLAN_GROUPS * ((size_t)cap + 2) * sizeof(int); };
-        if (p.level <= 0) {
-            seed_plan_kernel<SEED_CAND_0><<<grid, SEED_PLAN_THREADS, smem_of(SEED_CAND_0), stream>>>(p);
-        } else if (p.level == 1) {
-            seed_plan_kernel<SEED_CAND_1><<<grid, SEED_PLAN_THREADS, smem_of(SEED_CAND_1), stream>>>(p);
-        } else {
-            EB_CUDA(cudaFuncSetAttribute(seed_plan_kernel<SEED_CAND_2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(SEED_CAND_2)));
-            seed_plan_kernel<SEED_CAND_2><<<grid, SEED_PLAN_THREADS, smem_of(SEED_CAND_2), stream>>>(p);
-        }
+        if (p.level <= 0) launch_seed_plan_t<SEED_CAND_0, 128>(p);
+        else if (p.level == 1) launch_seed_plan_t<SEED_CAND_1, 128>(p);
+        else launch_seed_plan_t<SEED_CAND_2, 32>(p);
         check_launch("seed_plan");
     }
     void launch_fin_count(const FinParams& p) override {

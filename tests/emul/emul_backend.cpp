@@ -163,7 +163,7 @@ struct EmulBackend : Backend {
     void launch_seed_plan(const SeedPlanParams& p) override {
         ++launchesCount;
         std::vector<int> E(SEED_CAND_2);
-        int ctl[2];
+        int ctl[SEED_CTL];
         for (int i = p.numReads - 1; i >= 0; --i) {
             if (p.level <= 0) seed_plan_read<SEED_CAND_0, CoopSerial>(p, i, E.data(), ctl);
             else if (p.level == 1) seed_plan_read<SEED_CAND_1, CoopSerial>(p, i, E.data(), ctl);
