@@ -243,6 +243,23 @@ EDLIB_API void edlibB200BatchFree(EdlibB200Batch* batch) {
     if (batch && engine_locked()) g_engine->release(reinterpret_cast<eb::Prepared*>(batch));
 }
 
+EDLIB_API EdlibB200Target* edlibB200TargetPrepare(const char* target, int targetLength) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    eb::Engine* e = engine_locked();
+    if (!e) return NULL;
+    try {
+        return reinterpret_cast<EdlibB200Target*>(e->target_prepare(target, targetLength));
+    } catch (const std::exception& ex) {
+        e->lastError = ex.what();
+        return NULL;
+    }
+}
+
+EDLIB_API void edlibB200TargetFree(EdlibB200Target* target) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (target && engine_locked()) g_engine->target_free(reinterpret_cast<eb::TargetHandle*>(target));
+}
+
 EDLIB_API int edlibB200AlignmentsToCigar(const EdlibAlignResult* results, int n, EdlibCigarFormat cigarFormat, char** cigars) {
     if (n < 0 || (n > 0 && (!results || !cigars))) return EDLIB_STATUS_ERROR;
     if (cigarFormat != EDLIB_CIGAR_EXTENDED && cigarFormat != EDLIB_CIGAR_STANDARD) return EDLIB_STATUS_ERROR;

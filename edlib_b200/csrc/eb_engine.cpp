@@ -690,7 +690,82 @@ void Engine::release(Prepared* p) {
     spare_ = p;  // keep the object (host vectors, pinned result arrays) for the next batch
 }
 
-Engine::~Engine() { delete spare_; }
+Engine::~Engine() {
+    delete spare_;
+    for (TargetHandle* h : targets_) delete h;
+}
+
+TargetHandle* Engine::find_target(const char* ptr, int n) const {
+    for (TargetHandle* h : targets_)
+        if (h->ptr == ptr && h->n == n) return h;
+    return nullptr;
+}
+
+// Uploads, encodes and indexes a target once (the steps Engine::align_streamed otherwise repeats per batch).
+TargetHandle* Engine::target_prepare(const char* target, int n) {
+    Backend* be = be_;
+    if (!target || n < 64) throw std::runtime_error("target handle: target too short");
+    TargetHandle* h = new TargetHandle();
+    try {
+        h->ptr = target;
+        h->n = n;
+        h->bytes = round_up((size_t)n, 16) + 32;
+        h->codes.alloc(be, h->bytes);
+        {
+            HostBuf<uint8_t> stage(be, h->bytes);
+            memcpy(stage.p, target, (size_t)n);
+            memset(stage.p + n, 0, h->bytes - (size_t)n);
+            h->codes.upload(stage.p, h->bytes);
+            be->sync();
+        }
+        std::vector<MaskItem> items;
+        for (int s0 = 0; s0 < n; s0 += 65536) items.push_back(MaskItem{(uint64_t)s0, std::min(65536, n - s0), 0});
+        DevBuf<MaskItem> dItems(be, items.size());
+        dItems.upload(items.data(), items.size());
+        h->dMask.alloc(be, 8);
+        be->zero(h->dMask.p, 8 * sizeof(uint32_t));
+        MaskParams mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.raw = h->codes.p;
+        mp.items = dItems.p;
+        mp.numItems = (int)items.size();
+        mp.masks = h->dMask.p;
+        mp.unionSet = -1;
+        be->launch_mask(mp);
+        be->d2h(h->tmask, h->dMask.p, sizeof(h->tmask));
+        int ncodes = 0;
+        for (int b = 0; b < 256; ++b) ncodes += (h->tmask[b >> 5] >> (b & 31)) & 1u;
+        code_map(h->tmask, h->map, ncodes);
+        h->ncodesRaw = ncodes;
+        h->dMap.alloc(be, 256);
+        h->dMap.upload(h->map, 256);
+        EncodeParams ep{h->codes.p, (uint64_t)round_up((size_t)n, 16), h->dMap.p};
+        be->launch_encode(ep);
+        const int codes = ncodes >= 256 ? 256 : std::max(1, std::min(ncodes, 255));
+        build_seed_index(be, tun, h->idx, h->codes.p, n, codes);
+        be->sync();
+        targets_.push_back(h);
+        return h;
+    } catch (...) {
+        try {
+            be->sync_all();
+        } catch (...) {
+        }
+        delete h;
+        throw;
+    }
+}
+
+void Engine::target_free(TargetHandle* h) {
+    if (!h) return;
+    for (size_t i = 0; i < targets_.size(); ++i)
+        if (targets_[i] == h) {
+            be_->sync_all();
+            targets_.erase(targets_.begin() + (long)i);
+            delete h;
+            return;
+        }
+}
 
 int Engine::align_batch(const BatchInput& in, EdlibAlignResult* results) {
     Prepared* p = nullptr;
@@ -957,50 +1032,71 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             poolBusy = true;
         }
 
-        // ---- target: upload, presence set, codes, encoding, seed index (while the workers pack slice 0) ----
-        memcpy(stage + tOff, tptr, (size_t)n);
-        memset(stage + tOff + n, 0, total - tOff - (size_t)n);
-        if (tOff > qBytes) memset(stage + qBytes, 0, tOff - qBytes);
-        be->h2d_copy(p->dSeq.p + qBytes, stage + qBytes, total - qBytes);
-        const uint64_t targetUp = be->mark(Backend::STREAM_COPY);
-        job.targetIssued.store(1, std::memory_order_release);
-        be->wait(Backend::STREAM_COMPUTE, targetUp);
-        std::vector<MaskItem> items;
-        for (int s0 = 0; s0 < n; s0 += 65536) items.push_back(MaskItem{(uint64_t)tOff + (uint64_t)s0, std::min(65536, n - s0), 0});
-        DevBuf<MaskItem> dItems(be, items.size());
-        dItems.upload(items.data(), items.size());
-        DevBuf<uint32_t> dMask(be, 8);
-        be->zero(dMask.p, 8 * sizeof(uint32_t));
-        {
-            MaskParams mp;
-            memset(&mp, 0, sizeof(mp));
-            mp.raw = p->dSeq.p;
-            mp.items = dItems.p;
-            mp.numItems = (int)items.size();
-            mp.masks = dMask.p;
-            mp.unionSet = -1;
-            be->launch_mask(mp);
-        }
-        uint32_t tmask[8];
-        be->d2h(tmask, dMask.p, sizeof(tmask));
+        // ---- target: upload, presence set, codes, encoding, seed index (while the workers pack slice 0); a target the
+        // caller keeps resident (edlibB200TargetPrepare) brings all of that along ----
+        TargetHandle* const kept = find_target(tptr, n);
+        DevBuf<MaskItem> dItems;
+        DevBuf<uint32_t> dMaskOwn;
+        DevBuf<uint8_t> dMapOwn;
+        const uint32_t* dMaskP = nullptr;
+        const uint8_t* dMapP = nullptr;
         uint8_t map[256];
         int ncodes = 0;
-        for (int b = 0; b < 256; ++b) ncodes += (tmask[b >> 5] >> (b & 31)) & 1u;
-        code_map(tmask, map, ncodes);  // bytes the target does not hold: the extra code `ncodes`
+        if (kept) {
+            if (tOff > qBytes) be->zero(p->dSeq.p + qBytes, tOff - qBytes);
+            be->d2d(p->dSeq.p + tOff, kept->codes.p, kept->bytes);  // (bytes == total - tOff)
+            job.targetIssued.store(1, std::memory_order_release);
+            dMaskP = kept->dMask.p;
+            dMapP = kept->dMap.p;
+            memcpy(map, kept->map, sizeof(map));
+            ncodes = kept->ncodesRaw;
+        } else {
+            memcpy(stage + tOff, tptr, (size_t)n);
+            memset(stage + tOff + n, 0, total - tOff - (size_t)n);
+            if (tOff > qBytes) memset(stage + qBytes, 0, tOff - qBytes);
+            be->h2d_copy(p->dSeq.p + qBytes, stage + qBytes, total - qBytes);
+            const uint64_t targetUp = be->mark(Backend::STREAM_COPY);
+            job.targetIssued.store(1, std::memory_order_release);
+            be->wait(Backend::STREAM_COMPUTE, targetUp);
+            std::vector<MaskItem> items;
+            for (int s0 = 0; s0 < n; s0 += 65536) items.push_back(MaskItem{(uint64_t)tOff + (uint64_t)s0, std::min(65536, n - s0), 0});
+            dItems.alloc(be, items.size());
+            dItems.upload(items.data(), items.size());
+            dMaskOwn.alloc(be, 8);
+            be->zero(dMaskOwn.p, 8 * sizeof(uint32_t));
+            {
+                MaskParams mp;
+                memset(&mp, 0, sizeof(mp));
+                mp.raw = p->dSeq.p;
+                mp.items = dItems.p;
+                mp.numItems = (int)items.size();
+                mp.masks = dMaskOwn.p;
+                mp.unionSet = -1;
+                be->launch_mask(mp);
+            }
+            uint32_t tmask[8];
+            be->d2h(tmask, dMaskOwn.p, sizeof(tmask));
+            for (int b = 0; b < 256; ++b) ncodes += (tmask[b >> 5] >> (b & 31)) & 1u;
+            code_map(tmask, map, ncodes);  // bytes the target does not hold: the extra code `ncodes`
+            dMapOwn.alloc(be, 256);
+            dMapOwn.upload(map, 256);
+            EncodeParams ep{p->dSeq.p + tOff, (uint64_t)round_up((size_t)n, 16), dMapOwn.p};
+            be->launch_encode(ep);
+            dMaskP = dMaskOwn.p;
+            dMapP = dMapOwn.p;
+        }
         p->ncodes = std::max(1, std::min(ncodes, 255));
         if (ncodes >= 256) {  // no spare code: every byte value occurs in the target, so no read byte is foreign
             p->ncodes = 256;
         }
-        DevBuf<uint8_t> dMap(be, 256);
-        dMap.upload(map, 256);
-        {
-            EncodeParams ep{p->dSeq.p + tOff, (uint64_t)round_up((size_t)n, 16), dMap.p};
-            be->launch_encode(ep);
-        }
         stats = EngineStats();
-        stats.h2dBytes = (long long)total + 12LL * N;
+        stats.h2dBytes = (long long)(kept ? qBytes : total) + 12LL * N;
         be->reset_timing();
         Pass ps(*this, be, p);
+        if (kept) {
+            kept->idx.target = 0;
+            ps.seedIdx = &kept->idx;
+        }
         int bt = 0, rc = 0;
         be->k1_shape(nw, p->ncodes, N, &bt, &rc);
         if (rc <= 0 || !ps.dev_eligible(0, nw) || !ps.seed_index(0) || ps.seedIdx->Ls[0] <= 0) {
@@ -1046,11 +1142,11 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             qa.qlen = p->dQlen.p;
             qa.firstPair = lo;
             qa.numQueries = hi - lo;
-            qa.tmask = dMask.p;
+            qa.tmask = dMaskP;
             qa.alphaLen = dAlpha.p;
             be->launch_qalpha(qa);
             const uint64_t b0 = p->qoff[lo], b1 = p->qoff[hi - 1] + (uint64_t)p->qlen[hi - 1];
-            EncodeParams ep{p->dSeq.p + b0, b1 - b0, dMap.p};
+            EncodeParams ep{p->dSeq.p + b0, b1 - b0, dMapP};
             be->launch_encode(ep);
             ps.extraCopyDst = p->alphaLen.data() + lo;
             ps.extraCopySrc = dAlpha.p + lo;

@@ -27,6 +27,7 @@ struct Backend {
     virtual void h2d(void* dst, const void* src, size_t bytes) = 0;
     virtual void d2h(void* dst, const void* src, size_t bytes) = 0;  // synchronising
     virtual void zero(void* dst, size_t bytes) = 0;
+    virtual void d2d(void* dst, const void* src, size_t bytes) = 0;  // device to device, on the compute stream
     virtual void fill(void* dst, int byteValue, size_t bytes) = 0;
     virtual void sync() = 0;
     // Streamed batches use two more streams beside the compute stream: uploads and result downloads.  A mark is
@@ -148,6 +149,7 @@ struct EngineScratch {
 };
 
 class Prepared;  // a batch whose inputs are resident on the device
+struct TargetHandle;  // a target kept resident: encoded bytes, presence set, code map, seed index (eb_engine_internal.h)
 
 class Engine {
 public:
@@ -168,6 +170,10 @@ public:
 
     void finish_stats();  // fills the device-time fields of `stats` for the last pass (on demand)
 
+    // Targets kept resident for the streamed read-set path (include/edlib_b200.h: edlibB200TargetPrepare).
+    TargetHandle* target_prepare(const char* target, int n);
+    void target_free(TargetHandle* h);
+
     EngineTunables tun;
     EngineStats stats;
     EngineScratch scratch;
@@ -176,6 +182,8 @@ public:
 private:
     Backend* be_;
     Prepared* spare_ = nullptr;  // released batch object whose host vectors the next prepare() reuses
+    std::vector<TargetHandle*> targets_;
+    TargetHandle* find_target(const char* ptr, int n) const;
     bool statsPending_ = false;
 };
 

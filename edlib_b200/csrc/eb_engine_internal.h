@@ -428,6 +428,24 @@ struct SeedIndex {
     DevBuf<int> bucketStart, positions;
 };
 
+// Builds the radix seed index of an encoded target (seed lengths per level, bucket table, positions).
+bool build_seed_index(Backend* be, const EngineTunables& tun, SeedIndex& sx, const uint8_t* tcodes, int n, int ncodes);
+
+// A target kept resident on the device (streamed read-set path): its encoded bytes with the padding the kernels rely on,
+// the presence set / code map the encoding came from, and its seed index.
+struct TargetHandle {
+    const char* ptr = nullptr;
+    int n = 0;
+    size_t bytes = 0;          // round_up(n, 16) + 32 encoded bytes (zero padding)
+    DevBuf<uint8_t> codes;
+    DevBuf<uint32_t> dMask;    // [8] presence set
+    DevBuf<uint8_t> dMap;      // [256] byte -> code
+    uint32_t tmask[8];
+    uint8_t map[256];
+    int ncodesRaw = 0;         // distinct bytes of the target
+    SeedIndex idx;
+};
+
 // One slice of a device-driven group: reads [first, first+count) of the group's list (pair = list[first+slot], or
 // firstPair + slot when the group is a run of consecutive pairs), its region of the end-location pool and its
 // header {end locations, reads pending, pool overflow, windows}.

@@ -727,6 +727,9 @@ struct CudaBackend : Backend {
     void zero(void* d, size_t n) override {
         if (n) EB_CUDA(cudaMemsetAsync(d, 0, n, stream));
     }
+    void d2d(void* d, const void* s, size_t n) override {
+        if (n) EB_CUDA(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream));
+    }
     void fill(void* d, int v, size_t n) override {
         if (n) EB_CUDA(cudaMemsetAsync(d, v, n, stream));
     }

@@ -40,16 +40,10 @@ void Pass::lane_launch(const std::vector<LJob>& jobs, int nw, int laneMode, bool
 // sweep); the later levels shorter ones (more seeds fit into a read, so a higher threshold, at the price of more
 // chance occurrences) for the reads the previous level could not decide.  One table with keys of Lidx symbols
 // (sigma^Lidx <= 2n buckets) serves all of them.
-bool Pass::seed_index(int t) {
-    if (!seedIdx) seedIdx = &ownIdx;
-    SeedIndex& sx = *seedIdx;
-    const Target& tg = p->tg[t];
-    const int n = tg.len;
-    if (sx.target == t && sx.n == n) return sx.ok;
-    sx.target = t;
+bool build_seed_index(Backend* be, const EngineTunables& tun, SeedIndex& sx, const uint8_t* tcodes, int n, int ncodes) {
     sx.n = n;
     sx.ok = false;
-    const int sigma = std::max(2, p->ncodes);
+    const int sigma = std::max(2, ncodes);
     int L0 = 4;
     double v = std::pow((double)sigma, 4);
     while (v < (double)tun.filterSeedSlack * (double)n && L0 < 32) {
@@ -81,7 +75,7 @@ bool Pass::seed_index(int t) {
     be->zero(cursor.p, (size_t)keys * sizeof(int));
     SeedIndexParams ip;
     memset(&ip, 0, sizeof(ip));
-    ip.tcodes = p->dSeq.p + tg.off;
+    ip.tcodes = tcodes;
     ip.n = n;
     ip.Lidx = Lidx;
     ip.sigma = sigma;
@@ -94,8 +88,19 @@ bool Pass::seed_index(int t) {
     be->launch_scan(sx.bucketStart.p, (int)keys);
     be->launch_seed_fill(ip);
     sx.ok = true;
-    trace.mark("filter: seed index");
     return true;
+}
+
+bool Pass::seed_index(int t) {
+    if (!seedIdx) seedIdx = &ownIdx;
+    SeedIndex& sx = *seedIdx;
+    const Target& tg = p->tg[t];
+    const int n = tg.len;
+    if (sx.target == t && sx.n == n) return sx.ok;
+    sx.target = t;
+    const bool ok = build_seed_index(be, tun, sx, p->dSeq.p + tg.off, n, p->ncodes);
+    trace.mark("filter: seed index");
+    return ok;
 }
 
 static void fill_seed_plan(SeedPlanParams& sp, const Prepared* p, const Target& tg, const SeedIndex& sx, int level,

@@ -59,6 +59,14 @@ EDLIB_API int edlibB200BatchCompute(EdlibB200Batch* batch, EdlibB200Stats* stats
 EDLIB_API int edlibB200BatchResults(EdlibB200Batch* batch, EdlibAlignResult* results);
 EDLIB_API void edlibB200BatchFree(EdlibB200Batch* batch);
 
+/* A target kept resident on the device.  edlibAlignBatch calls of read sets (HW, short queries, plain equality) whose
+ * targets[i] all equal (target, targetLength) of a live handle skip the target's upload, its encoding and the build of
+ * its seed index: a caller that aligns many batches to one genome pays them once.  The bytes at `target` must not
+ * change while the handle lives; results are identical with and without a handle.  Returns NULL on failure. */
+typedef struct EdlibB200Target EdlibB200Target;
+EDLIB_API EdlibB200Target* edlibB200TargetPrepare(const char* target, int targetLength);
+EDLIB_API void edlibB200TargetFree(EdlibB200Target* target);
+
 /* edlibAlignmentToCigar (edlib.h) for n results at once, on the engine's host threads: cigars[i] receives a
  * malloc'd C string (caller frees each with free()), or NULL where results[i] holds no alignment.  Returns
  * EDLIB_STATUS_OK, or EDLIB_STATUS_ERROR on a bad format / operation code (then every cigars[i] is NULL). */

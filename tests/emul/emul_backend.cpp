@@ -120,6 +120,7 @@ struct EmulBackend : Backend {
     void h2d(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
     void d2h(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
     void zero(void* d, size_t n) override { memset(d, 0, n); }
+    void d2d(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
     void fill(void* d, int v, size_t n) override { memset(d, v, n); }
     void sync() override {}
     int sm_count() override {

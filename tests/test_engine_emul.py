@@ -146,6 +146,54 @@ def test_start_locations_and_paths_driven_from_the_device():
         assert ("device-driven lane sweeps" in out.stderr) == want and ("device-driven leaf sweeps" in out.stderr) == want
 
 
+TARGET_HANDLE_CODE = """
+import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)
+import ctypes as C, random
+import parity, cases
+from edlib_b200._ffi import AlignResult, make_config, result_to_dict
+lib = LOAD
+L = lib.lib
+L.edlibB200TargetPrepare.restype = C.c_void_p
+L.edlibB200TargetPrepare.argtypes = [C.c_char_p, C.c_int]
+L.edlibB200TargetFree.argtypes = [C.c_void_p]
+chk = parity.checker()
+total = 0
+for c in cases.stream_cases(81, 6):
+    t = c["ts"][0]
+    tb = C.create_string_buffer(t, len(t))
+    n = len(c["qs"])
+    qptr = (C.c_char_p * n)(*c["qs"]); qlen = (C.c_int * n)(*[len(q) for q in c["qs"]])
+    tptr = (C.c_char_p * n)(*[C.cast(tb, C.c_char_p)] * n); tlen = (C.c_int * n)(*[len(t)] * n)
+    cfg, keep = make_config(c["k"], c["mode"], c["task"], None)
+    outs = []
+    for use_handle in (False, True, True):
+        h = L.edlibB200TargetPrepare(C.cast(tb, C.c_char_p), len(t)) if use_handle else None
+        assert (h is not None and h != 0) == use_handle
+        res = (AlignResult * n)()
+        assert L.edlibAlignBatch(qptr, qlen, tptr, tlen, n, cfg, res) == 0
+        outs.append([result_to_dict(res[i]) for i in range(n)])
+        for i in range(n):
+            lib.free(res[i])
+        if h:
+            L.edlibB200TargetFree(h)
+    assert outs[0] == outs[1] == outs[2]
+    for i in range(0, n, 7):
+        assert outs[1][i] == chk.align(c["qs"][i], t, c["k"], c["mode"], c["task"], None)
+    total += n
+print(total)
+"""
+
+
+def test_target_handle():
+    """edlibB200TargetPrepare: batches against a target kept resident (encoded bytes + seed index reused) give what
+    the same call gives without a handle, handle after handle."""
+    code = (TARGET_HANDLE_CODE % (REPO, os.path.join(REPO, "tests"))).replace("LOAD", "__import__('test_engine_emul').load_emul()")
+    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_TRACE="1")
+    out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+    assert int(out.stdout.strip().splitlines()[-1]) > 500
+    assert "stream: slices enqueued" in out.stderr
+
+
 def test_streamed_batches():
     """edlibAlignBatch on read-set-shaped HW batches goes through the streamed path (slices packed and uploaded
     under the kernels of earlier slices, results assembled on the device, result structs built per slice): the

@@ -90,6 +90,17 @@ def test_reads_that_tie_on_many_end_columns():
         assert int(out.stdout.strip().splitlines()[-1]) > 600
 
 
+def test_target_handle():
+    """edlibB200TargetPrepare on the GPU: same results with and without a resident target."""
+    import subprocess
+    from edlib_b200._ffi import REPO
+    from test_engine_emul import TARGET_HANDLE_CODE
+    code = (TARGET_HANDLE_CODE % (REPO, os.path.join(REPO, "tests"))).replace("LOAD", "__import__('helpers').product()")
+    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8")
+    out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+    assert int(out.stdout.strip().splitlines()[-1]) > 500
+
+
 def test_large_alphabets_and_equalities(lib):
     """Protein-sized and full-byte alphabets over shared targets (per-thread Peq rows shrink the CTA or
     push the group to the warp kernel), with and without extra equalities."""
