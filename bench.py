@@ -589,6 +589,43 @@ def config4(E, target, reads, steps, cores, cpu_seconds, barrier):
             "mean_alignment_length": mean_aln}
 
 
+def long_hw(E, genome, cores):
+    """Long queries (> 256 bp, up to 10 kbp; 60 % .. 100 % identity) of the reference's E. coli test data, HW, EDLIB_TASK_LOC,
+    over the 4.63 Mbp genome: each read as ONE edlibAlign call (latency), all of them as one edlibAlignBatch, and the
+    reference build on the same reads (one core per read)."""
+    with open(os.path.join(REPO, "tests", "golden", "ecoli_reads.json")) as f:
+        fx = json.load(f)["reads"]
+    names = sorted(n for n in fx if len(fx[n]["seq"]) > 256)
+    seqs = [fx[n]["seq"].encode("ascii") for n in names]
+    gb = genome.tobytes()
+    lib, kind = ref_lib()
+    cfg, _ = make_config(-1, MODE_HW, TASK_LOC)
+    from edlib_b200._ffi import result_to_dict
+    per = {}
+    E.lib.align(seqs[0], gb, -1, MODE_HW, TASK_LOC)  # warm-up of the call path
+    for n, q in zip(names, seqs):
+        t0 = time.perf_counter()
+        got = E.lib.align(q, gb, -1, MODE_HW, TASK_LOC)
+        t1 = time.perf_counter()
+        r = lib.align_raw(q, gb, cfg)
+        t2 = time.perf_counter()
+        exp = result_to_dict(r)
+        lib.free(r)
+        assert got == exp, "long HW read %s differs from the reference" % n
+        per[n] = {"bp": len(q), "editDistance": got["editDistance"], "gpu_ms": 1000 * (t1 - t0), "cpu_1core_ms": 1000 * (t2 - t1),
+                  "speedup_vs_1core": (t2 - t1) / (t1 - t0)}
+    t0 = time.perf_counter()
+    st, res = E.lib.align_batch(seqs, [gb] * len(seqs), -1, MODE_HW, TASK_LOC)
+    tb = time.perf_counter() - t0
+    assert st == 0
+    cpu_total = sum(v["cpu_1core_ms"] for v in per.values())
+    return {"workload": "%d reads of 257..10,000 bp (tests/golden/ecoli_reads.json: mason reads and their 60..99 %% mutated copies), "
+                        "HW, EDLIB_TASK_LOC, vs the 4,630,707 bp genome" % len(seqs),
+            "single_calls": per, "batch_ms": 1000 * tb, "sum_gpu_single_ms": sum(v["gpu_ms"] for v in per.values()),
+            "sum_cpu_1core_ms": cpu_total, "cpu_kind": kind, "batch_speedup_vs_1core": cpu_total / (1000 * tb),
+            "batch_speedup_vs_%d_cores_ideal" % cores: cpu_total / cores / (1000 * tb)}
+
+
 def strong_scaling(E, genome, total_reads, steps, rank, world, dev, barrier):
     """BASELINE configs[4]: ONE batch of `total_reads` reads (seed 44) sharded over the ranks (sharding.shard_range).
     Inside every timed step: NCCL broadcast of the target from rank 0, edlibAlignBatch on the rank's shard (host
@@ -679,7 +716,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep-sample", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (other configs, sensitivity, strong scaling)")
-    ap.add_argument("--extras", default="strong,target_handle,other_target,sensitivity,config4,config3,sweep_kernel",
+    ap.add_argument("--extras", default="strong,target_handle,other_target,sensitivity,long_hw,config4,config3,sweep_kernel",
                     help="comma-separated sub-records to run (default: all)")
     ap.add_argument("--config3-pairs", type=int, default=100_000)
     ap.add_argument("--strong-reads", type=int, default=10_000_000)
@@ -832,6 +869,7 @@ def main():
         guarded("target_handle", target_handle)
         guarded("other_target", synthetic)
         guarded("sensitivity", lambda: sensitivity(E, target, reads, flush_l2, barrier))
+        guarded("long_hw", lambda: long_hw(E, target if args.target == "ecoli" else workloads.ecoli_genome(), cores))
         guarded("config4", lambda: config4(E, target, reads, 2, cores, 10.0, barrier))
         del reads
         genome = target if args.target == "ecoli" else workloads.ecoli_genome()

@@ -94,6 +94,7 @@ EngineTunables::EngineTunables() {
     filterMinTarget = env_int("EDLIB_B200_FILTER_MIN_TARGET", filterMinTarget);
     filterSkipRepeats = env_int("EDLIB_B200_FILTER_SKIP_REPEATS", filterSkipRepeats);
     bandKernel = env_int("EDLIB_B200_BAND_KERNEL", bandKernel);
+    collapseEqualities = env_int("EDLIB_B200_COLLAPSE_EQUALITIES", collapseEqualities);
     deviceStage = env_int("EDLIB_B200_DEVICE_STAGE", deviceStage);
     windowCheckAfter = env_int("EDLIB_B200_WINDOW_CHECK", windowCheckAfter);
     longHwMinTarget = env_int("EDLIB_B200_LONG_HW_MIN_TARGET", longHwMinTarget);
@@ -165,18 +166,13 @@ Prepared* Engine::prepare(const BatchInput& in) {
             if (bad.load()) throw std::runtime_error("negative sequence length");
         }
 
-        // identical (pointer, length) targets are uploaded and encoded once
+        // identical (pointer, length) targets are uploaded and encoded once: open-addressing table over the pairs
+        // (no node allocations: a batch of 100,000 pairs with their own targets spends ~1 ms here)
         struct Key {
             const char* ptr;
             int len;
             bool operator==(const Key& o) const { return ptr == o.ptr && len == o.len; }
         };
-        struct KeyHash {
-            size_t operator()(const Key& k) const { return std::hash<const void*>()(k.ptr) * 31 + (size_t)k.len; }
-        };
-        std::unordered_map<Key, int, KeyHash> seen;
-        Key lastKey{nullptr, -1};
-        int lastIdx = -1;
         bool oneTarget = N > 0;  // the usual batch shape (reads over one shared target), checked in parallel
         if (N >= 131072) {
             std::atomic<int> differs(0);
@@ -196,19 +192,37 @@ Prepared* Engine::prepare(const BatchInput& in) {
             parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
                 for (size_t i = lo; i < hi; ++i) p->tidx[i] = 0;
             });
-        }
-        for (int i = 0; i < N && !oneTarget; ++i) {
-            Key k{in.targets[i], in.targetLengths[i]};
-            if (!(k == lastKey)) {  // neighbours usually share their target
-                auto it = seen.find(k);
-                if (it == seen.end()) {
-                    it = seen.emplace(k, (int)p->tg.size()).first;
-                    p->tg.push_back(Target{k.ptr, k.len, 0});
+        } else {
+            size_t cap = 64;
+            while (cap < 2 * (size_t)N) cap *= 2;
+            std::vector<int>& table = scratch.targetTable;  // slot -> index into p->tg, -1: free
+            table.assign(cap, -1);
+            Key lastKey{nullptr, -1};
+            int lastIdx = -1;
+            for (int i = 0; i < N; ++i) {
+                const Key k{in.targets[i], in.targetLengths[i]};
+                if (!(k == lastKey)) {  // neighbours usually share their target
+                    uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull + (uint64_t)(uint32_t)k.len * 0xC2B2AE3D27D4EB4Full;
+                    h ^= h >> 29;
+                    size_t slot = (size_t)h & (cap - 1);
+                    for (;;) {
+                        const int t = table[slot];
+                        if (t < 0) {
+                            table[slot] = (int)p->tg.size();
+                            lastIdx = (int)p->tg.size();
+                            p->tg.push_back(Target{k.ptr, k.len, 0});
+                            break;
+                        }
+                        if (p->tg[(size_t)t].ptr == k.ptr && p->tg[(size_t)t].len == k.len) {
+                            lastIdx = t;
+                            break;
+                        }
+                        slot = (slot + 1) & (cap - 1);
+                    }
+                    lastKey = k;
                 }
-                lastKey = k;
-                lastIdx = it->second;
+                p->tidx[i] = lastIdx;
             }
-            p->tidx[i] = lastIdx;
         }
         const int T = (int)p->tg.size();
         trace.mark("prepare: lengths + distinct targets");
@@ -347,31 +361,70 @@ Prepared* Engine::prepare(const BatchInput& in) {
         uint8_t map[256];
         p->ncodes = code_map(uni, map, -1);
         if (p->ncodes == 0) p->ncodes = 1;
-        DevBuf<uint8_t> dMap(be, 256);
-        dMap.upload(map, 256);
-        EncodeParams ep{p->dSeq.p, (uint64_t)total, dMap.p};
-        be->launch_encode(ep);
-
-        // equality table over codes (ref cpp:63-94); a pair naming an absent byte changes nothing
+        // Additional equalities (ref cpp:63-94) over the codes; a pair naming an absent byte changes nothing.  When the
+        // relation they induce on the bytes present is TRANSITIVE (every group of connected bytes is pairwise equal:
+        // upper/lower case, synonyms), the bytes of a group get ONE code and the batch runs as a plain-equality batch --
+        // the DP only ever asks whether two symbols are equal -- so every fast path (seed filter, lane kernels without
+        // the table look-ups) applies.  Otherwise (e.g. a wildcard that equals several mutually different bytes) the
+        // kernels test pairs of codes through the table.
+        std::vector<uint8_t> eq;
+        bool anyEq = false;
         if (in.config.additionalEqualities && in.config.additionalEqualitiesLength > 0) {
-            const int s = p->ncodes;
-            std::vector<uint8_t> eq((size_t)s * s, 0);
-            for (int i = 0; i < s; ++i) eq[(size_t)i * s + i] = 1;
-            bool any = false;
+            const int s0 = p->ncodes;
+            eq.assign((size_t)s0 * s0, 0);
+            for (int i = 0; i < s0; ++i) eq[(size_t)i * s0 + i] = 1;
             for (int i = 0; i < in.config.additionalEqualitiesLength; ++i) {
                 const int a = (unsigned char)in.config.additionalEqualities[i].first;
                 const int b = (unsigned char)in.config.additionalEqualities[i].second;
                 const bool ha = uni[a >> 5] >> (a & 31) & 1u, hb = uni[b >> 5] >> (b & 31) & 1u;
-                if (ha && hb) {
-                    eq[(size_t)map[a] * s + map[b]] = eq[(size_t)map[b] * s + map[a]] = 1;
-                    any = true;
+                if (ha && hb && a != b) {
+                    eq[(size_t)map[a] * s0 + map[b]] = eq[(size_t)map[b] * s0 + map[a]] = 1;
+                    anyEq = true;
                 }
             }
-            if (any) {
-                p->dEqtab.alloc(be, eq.size());
-                p->dEqtab.upload(eq.data(), eq.size());
-                p->hasEq = true;
+        }
+        if (anyEq && tun.collapseEqualities) {
+            const int s0 = p->ncodes;
+            std::vector<int> comp(s0, -1);  // connected components of the equality graph, numbered by their smallest code
+            int ncomp = 0;
+            std::vector<int> stack;
+            for (int c = 0; c < s0; ++c) {
+                if (comp[c] >= 0) continue;
+                comp[c] = ncomp;
+                stack.assign(1, c);
+                while (!stack.empty()) {
+                    const int u = stack.back();
+                    stack.pop_back();
+                    for (int v = 0; v < s0; ++v)
+                        if (eq[(size_t)u * s0 + v] && comp[v] < 0) {
+                            comp[v] = ncomp;
+                            stack.push_back(v);
+                        }
+                }
+                ++ncomp;
             }
+            bool transitive = true;
+            for (int u = 0; u < s0 && transitive; ++u)
+                for (int v = 0; v < s0; ++v)
+                    if ((comp[u] == comp[v]) != (eq[(size_t)u * s0 + v] != 0)) {
+                        transitive = false;
+                        break;
+                    }
+            if (transitive) {
+                for (int b = 0; b < 256; ++b)
+                    if (uni[b >> 5] >> (b & 31) & 1u) map[b] = (uint8_t)comp[map[b]];
+                p->ncodes = ncomp;
+                anyEq = false;  // nothing left for the table
+            }
+        }
+        DevBuf<uint8_t> dMap(be, 256);
+        dMap.upload(map, 256);
+        EncodeParams ep{p->dSeq.p, (uint64_t)total, dMap.p};
+        be->launch_encode(ep);
+        if (anyEq) {
+            p->dEqtab.alloc(be, eq.size());
+            p->dEqtab.upload(eq.data(), eq.size());
+            p->hasEq = true;
         }
         be->sync();
         trace.mark("prepare: upload+alphabet");

@@ -124,6 +124,7 @@ struct EngineTunables {
     int filterSpread = 1024;      // widest group of candidate ranges verified as one window
     int filterMaxWindows = 32;    // windows per read and stage before the next stage takes the read
     int filterMinTarget = 65536;  // shortest target worth filtering
+    int collapseEqualities = 1;   // transitive additional equalities: one code per group of equal bytes, no equality table
     int bandKernel = 1;           // k-banded NW sweeps of long queries on the thread-per-alignment band kernel (0: warp kernel)
     int filterSkipRepeats = 1;    // reads the last seed level found too repetitive skip the prefix stages (plain sweep)
     EngineTunables();             // reads EDLIB_B200_* environment overrides (used by tests)
@@ -146,6 +147,7 @@ struct EngineScratch {
     std::vector<int> best, cnt, posLen, posPool;
     std::vector<long long> posStart;
     int seedWindowsPerRead[SEED_LEVELS] = {0, 0, 0};  // seed stages: windows per read the previous pass produced
+    std::vector<int> targetTable;  // prepare(): open-addressing table of the distinct targets
 };
 
 class Prepared;  // a batch whose inputs are resident on the device

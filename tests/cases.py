@@ -380,3 +380,29 @@ def band_cases(seed, count):
             qs.append(q)
             ts.append(t)
         yield dict(qs=qs, ts=ts, k=k, mode=0, task=rng.choice([0, 1]), eqs=None)
+
+
+def equality_read_cases(seed, count):
+    """HW read sets with additional equalities: case folding (a TRANSITIVE relation: the engine gives equal bytes one
+    code and runs its plain-equality fast paths, seed filter included) and, every third batch, a wildcard on top of it
+    (N equals A and C, which differ: the table path)."""
+    from helpers import mutate, rand_seq
+    rng = random.Random(seed)
+    for it in range(count):
+        t = rand_seq(rng, rng.randrange(3000, 9000), b"ACGT")
+        qs = []
+        for _ in range(rng.randrange(40, 120)):
+            m = rng.choice([33, 64, 100, 150, 200])
+            s = rng.randrange(0, len(t) - m)
+            q = bytearray(mutate(rng, t[s:s + m], rng.choice([0.0, 0.02, 0.05]), b"ACGT"))
+            for i in range(len(q)):
+                if rng.random() < 0.3:
+                    q[i] = q[i] + 32  # lower case
+                elif it % 3 == 2 and rng.random() < 0.03:
+                    q[i] = ord("N")
+            if q:
+                qs.append(bytes(q))
+        eqs = [(b"A", b"a"), (b"C", b"c"), (b"g", b"G"), (b"T", b"t")]
+        if it % 3 == 2:
+            eqs += [(b"N", b"A"), (b"N", b"C"), (b"N", b"a"), (b"N", b"c")]
+        yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 6, 20]), mode=2, task=(it + seed) % 3, eqs=eqs)

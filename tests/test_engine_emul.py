@@ -146,6 +146,22 @@ def test_start_locations_and_paths_driven_from_the_device():
         assert ("device-driven lane sweeps" in out.stderr) == want and ("device-driven leaf sweeps" in out.stderr) == want
 
 
+def test_read_sets_with_additional_equalities():
+    """Case-folding equalities collapse to one code per group (seed filter and lane kernels without the table), a
+    wildcard keeps the table; also with the collapse switched off."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 91, 9, gen=cases.equality_read_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra, seeds in (({}, True), ({"EDLIB_B200_COLLAPSE_EQUALITIES": "0"}, False)):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", EDLIB_B200_TRACE="1", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 300
+        assert ("filter seed stage" in out.stderr or "device stage" in out.stderr) == seeds
+
+
 TARGET_HANDLE_CODE = """
 import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)
 import ctypes as C, random

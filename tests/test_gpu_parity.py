@@ -90,6 +90,11 @@ def test_reads_that_tie_on_many_end_columns():
         assert int(out.stdout.strip().splitlines()[-1]) > 600
 
 
+def test_read_sets_with_additional_equalities(lib):
+    """Case-folding equalities (collapsed to one code per group: seed filter) and a wildcard on top (table path)."""
+    assert parity.run_batches(lib, 91, 12, gen=cases.equality_read_cases) > 400
+
+
 def test_target_handle():
     """edlibB200TargetPrepare on the GPU: same results with and without a resident target."""
     import subprocess
