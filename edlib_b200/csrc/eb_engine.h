@@ -115,7 +115,7 @@ struct EngineTunables {
     int longSeedMaxK = 512;       // ... largest seed threshold tried (thresholds double from 64)
     int windowCheckAfter = 48;    // banded window sweeps: see K1WParams::checkAfter (-1 disables the early exit)
     int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
-    int filterSeedBucket = 32;    // seed stage: longest hash bucket looked at (longer: repeat, read passed on)
+    int filterSeedBucket = 128;   // seed stage: longest index range looked at, level 0: twice this; x8 per level (longer: repeat, read passed on)
     int filterSeedLevels = 3;     // seed stage: levels tried (seed length L, L-2, L-4 for DNA; at most SEED_LEVELS)
     int filterSeedSlack = 4;      // seed stage: seed length L is the shortest with sigma^L >= slack * target length
     int filterK1 = 8;

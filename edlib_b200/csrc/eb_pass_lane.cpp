@@ -119,7 +119,7 @@ static void fill_seed_plan(SeedPlanParams& sp, const Prepared* p, const Target& 
     sp.numKeys = sx.numKeys;
     sp.bucketStart = sx.bucketStart.p;
     sp.positions = sx.positions.p;
-    sp.maxBucket = tun.filterSeedBucket << (1 + 3 * level);  // shorter seeds: longer index ranges are normal
+    sp.maxBucket = std::min(tun.filterSeedBucket << (1 + 3 * level), 8192);  // shorter seeds: longer index ranges are normal
     sp.level = level;
     sp.spread = tun.filterSpread;
 }
