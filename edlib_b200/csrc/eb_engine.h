@@ -112,7 +112,7 @@ struct EngineTunables {
     int devSliceReads = 1 << 20;  // reads per slice of the device-driven level (streamed batches: at least four slices)
     int streamMinPairs = 32768;   // smallest one-target HW batch that edlibAlignBatch streams (upload under compute)
     int longHwMinTarget = 65536;  // HW, query > 256 rows: shortest target worth seeds / chunking (and >= 8 query lengths)
-    int longSeedMaxK = 512;       // ... largest seed threshold tried (thresholds double from 64)
+    int longSeedMaxK = 1024;      // ... largest seed threshold tried (thresholds double from 64, capped by the seeds that fit the query)
     int windowCheckAfter = 48;    // banded window sweeps: see K1WParams::checkAfter (-1 disables the early exit)
     int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 128;   // seed stage: longest index range looked at, level 0: twice this; x8 per level (longer: repeat, read passed on)

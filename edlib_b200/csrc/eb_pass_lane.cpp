@@ -754,7 +754,7 @@ void Pass::lane_group(int t, int nw, const std::vector<int>& list, const std::ve
     }
     const bool filtered = mode == MODE_HW && c.n >= tun.filterMinTarget;
     if (filtered) {
-        trace.mark("compute: classify");
+        trace.mark("lane group: bounds");
         for (int level = firstSeedLevel; level < tun.filterSeedLevels && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
             std::vector<int> next;
             seed_stage(c, level, cur, next);
@@ -989,6 +989,7 @@ void Pass::dev_leftovers() {
     trace.mark("device stage: results on the host");
     if (L == 0) return;
     std::sort(left.p, left.p + L, [](const Leftover& a, const Leftover& b) { return a.pair < b.pair; });
+    trace.mark("device stage: leftovers sorted");
     std::map<std::pair<int, int>, std::pair<std::vector<int>, std::vector<int>>> groups;  // (t, nw) -> pairs, excl
     for (int i = 0; i < L; ++i) {
         const int pair = left[i].pair;
@@ -997,6 +998,7 @@ void Pass::dev_leftovers() {
         g.second.push_back(left[i].excl);
         hostPairs.push_back(pair);
     }
+    trace.mark("device stage: leftovers grouped");
     for (auto& kv : groups) lane_group(kv.first.first, kv.first.second, kv.second.first, &kv.second.second, 1);
 }
 }  // namespace eb

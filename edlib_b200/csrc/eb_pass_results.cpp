@@ -197,7 +197,10 @@ void Pass::long_hw_distance(const std::vector<int>& pairs) {
         for (size_t i = 0; i < cur.size(); ++i) {
             taskFirst[i] = (int)tasks.size();
             const int s = cur[i], pair = list[s], m = p->qlen[pair];
-            long long chunks = std::max<long long>(1, std::min<long long>(n / (6LL * m), (wantTasks + (long long)cur.size() - 1) / (long long)cur.size()));
+            // chunks of >= 2m columns (each re-sweeps a 2m halo): a handful of queries is latency-bound per warp, so more,
+            // shorter chunks finish sooner even though the halos double the work; many queries get chunks of >= 6m
+            const long long minChunk = ((long long)cur.size() * 8 <= wantTasks ? 2LL : 6LL) * m;
+            long long chunks = std::max<long long>(1, std::min<long long>(n / minChunk, (wantTasks + (long long)cur.size() - 1) / (long long)cur.size()));
             const int chunkLen = (int)round_up((size_t)((n + chunks - 1) / chunks), 16);
             for (long long cs = 0; cs < n; cs += chunkLen) {
                 const long long ce = std::min<long long>(cs + chunkLen, n);

@@ -34,6 +34,23 @@ if has cfgtrace; then
   EDLIB_B200_TRACE=1 timeout 900 python bench.py --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline --no-sweep-sample --extras config4,config3 > $OUT/cfgtrace_$TAG.txt 2>&1
   grep -v "^{" $OUT/cfgtrace_$TAG.txt | tail -150 | cut -c1-170
 fi
+if has ncu2; then
+  for KW in "band_kernel band" "lane_kernel path" "traceback_kernel path" "res_kernel path" "w_kernel long"; do
+    set -- $KW; K=$1; W=$2
+    echo "== ncu --set full: $K ($W)"
+    timeout 900 ncu --set full --import-source on --clock-control none -k regex:$K -s ${NCU2_SKIP:-1} -c 1 -f -o $OUT/ncu_${TAG}_$K \
+        python scripts/ncu_targets.py $W > $OUT/ncu_${TAG}_$K.log 2>&1; echo "rc=$?"
+    ncu -i $OUT/ncu_${TAG}_$K.ncu-rep --page raw --csv > $OUT/ncu_${TAG}_${K}_raw.csv 2>/dev/null
+    rm -f $OUT/ncu_${TAG}_$K.ncu-rep
+  done
+fi
+if has longtrace; then
+  echo "== host-phase trace of single long HW calls"
+  EDLIB_B200_TRACE=1 timeout 600 python scripts/ncu_targets.py long1 2>&1 | tail -120 | cut -c1-170
+  echo "== every long read, one call each"
+  timeout 600 python scripts/ncu_targets.py long 2>&1 | tail -45
+fi
+if has h2d; then echo "== h2d microbenchmark"; ./scripts/microbench/h2d 2048 2>&1 | tail -12; fi
 if has ref; then echo "== bench --impl reference"; timeout 900 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; cut -c1-400 $OUT/bench_ref_$TAG.json; fi
 if has stress; then
   echo "== stress (filter forced on for small targets)"
