@@ -95,6 +95,8 @@ EngineTunables::EngineTunables() {
     filterSkipRepeats = env_int("EDLIB_B200_FILTER_SKIP_REPEATS", filterSkipRepeats);
     bandKernel = env_int("EDLIB_B200_BAND_KERNEL", bandKernel);
     collapseEqualities = env_int("EDLIB_B200_COLLAPSE_EQUALITIES", collapseEqualities);
+    directUpload = env_int("EDLIB_B200_DIRECT_UPLOAD", directUpload);
+    directMinBytes = (size_t)env_int("EDLIB_B200_DIRECT_MIN_KB", (int)(directMinBytes >> 10)) << 10;
     deviceStage = env_int("EDLIB_B200_DEVICE_STAGE", deviceStage);
     windowCheckAfter = env_int("EDLIB_B200_WINDOW_CHECK", windowCheckAfter);
     longHwMinTarget = env_int("EDLIB_B200_LONG_HW_MIN_TARGET", longHwMinTarget);
@@ -255,7 +257,22 @@ Prepared* Engine::prepare(const BatchInput& in) {
             // 0..N-1 are the queries, N..N+T-1 the distinct targets.  Every thread uploads its own byte
             // range as soon as it is packed, so the host->device copy overlaps the packing.
             const size_t qBytes = N ? (size_t)(p->qoff[N - 1] + (uint64_t)p->qlen[N - 1]) : 0;
-            size_t allBytes = qBytes;
+            // Queries that lie back to back in PINNED caller memory (a read array the caller allocated page-locked) go
+            // to the device straight from there: no staging copy, no host memory traffic besides the DMA itself.
+            bool direct = false;
+            if (tun.directUpload && N > 0 && qBytes >= tun.directMinBytes) {
+                std::atomic<int> gaps(0);
+                parallel_ranges((size_t)N, 65536, [&](size_t lo, size_t hi) {
+                    bool g = false;
+                    for (size_t i = std::max<size_t>(lo, 1); i < hi; ++i)
+                        if (in.queries[i] != in.queries[i - 1] + p->qlen[i - 1]) g = true;
+                    if (g) gaps.store(1, std::memory_order_relaxed);
+                });
+                direct = !gaps.load() && be->host_pinned(in.queries[0], qBytes);
+            }
+            if (direct) be->h2d(p->dSeq.p, in.queries[0], qBytes);
+            const int firstItem = direct ? N : 0;
+            size_t allBytes = direct ? 0 : qBytes;
             for (int t = 0; t < T; ++t) allBytes += (size_t)p->tg[t].len;
             const int nthr = allBytes > tun.packParallelBytes ? (int)HostPool::get().width() : 1;
             auto copy_item = [&](int it) {
@@ -281,16 +298,17 @@ Prepared* Engine::prepare(const BatchInput& in) {
                     memset(stage + g.off + g.len, 0, next - g.off - (size_t)g.len);
                 }
             }
+            const size_t firstByte = direct ? qBytes : 0;  // the staging bytes before this travelled directly
             if (nthr > 1) {
                 // contiguous item ranges of roughly equal byte counts
                 std::vector<int> cut(nthr + 1, N + T);
-                cut[0] = 0;
+                cut[0] = firstItem;
                 {
-                    size_t tAcc = qBytes;  // bytes before target `tt`
+                    size_t tAcc = direct ? 0 : qBytes;  // bytes before target `tt`
                     int tt = 0;
                     for (int c = 1; c < nthr; ++c) {
                         const size_t want = allBytes * c / nthr;
-                        if (want < qBytes) {  // qoff is the running byte count of the queries
+                        if (!direct && want < qBytes) {  // qoff is the running byte count of the queries
                             cut[c] = (int)(std::upper_bound(p->qoff.begin(), p->qoff.end(), (uint64_t)want) - p->qoff.begin());
                         } else {
                             while (tt < T && tAcc + (size_t)p->tg[tt].len <= want) tAcc += (size_t)p->tg[tt++].len;
@@ -301,13 +319,13 @@ Prepared* Engine::prepare(const BatchInput& in) {
                 }
                 HostPool::get().run((size_t)nthr, [&](size_t t) {  // exceptions of a task are rethrown by run()
                     for (int it = cut[t]; it < cut[t + 1]; ++it) copy_item(it);
-                    const size_t a = t == 0 ? 0 : item_off(cut[t]), b = item_off(cut[t + 1]);
+                    const size_t a = t == 0 ? firstByte : item_off(cut[t]), b = item_off(cut[t + 1]);
                     be->bind_thread();  // a pool worker: select the backend's device before the copy
                     if (b > a) be->h2d(p->dSeq.p + a, stage + a, b - a);
                 });
             } else {
-                for (int it = 0; it < N + T; ++it) copy_item(it);
-                p->dSeq.upload(stage, total);
+                for (int it = firstItem; it < N + T; ++it) copy_item(it);
+                be->h2d(p->dSeq.p + firstByte, stage + firstByte, total - firstByte);
             }
         }
         trace.mark("prepare: pack");
@@ -898,6 +916,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
         int minLen = 0x7fffffff, maxLen = 0;
         long long bytes = 0;
         bool differs = false;
+        bool gaps = false;  // some query does not start where its predecessor ends (in the caller's memory)
     };
     const size_t nparts = host_parts((size_t)N, 32768);
     std::vector<Scan> scans(nparts);
@@ -905,6 +924,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
         Scan s;
         for (size_t i = (size_t)N * t / nparts, hi = (size_t)N * (t + 1) / nparts; i < hi; ++i) {
             if (in.targets[i] != tptr || in.targetLengths[i] != n) s.differs = true;
+            if (i > 0 && in.queries[i] != in.queries[i - 1] + in.queryLengths[i - 1]) s.gaps = true;
             const int m = in.queryLengths[i];
             s.minLen = std::min(s.minLen, m);
             s.maxLen = std::max(s.maxLen, m);
@@ -915,6 +935,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
     Scan all;
     for (const Scan& s : scans) {
         all.differs |= s.differs;
+        all.gaps |= s.gaps;
         all.minLen = std::min(all.minLen, s.minLen);
         all.maxLen = std::max(all.maxLen, s.maxLen);
         all.bytes += s.bytes;
@@ -970,6 +991,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             }
         });
         const size_t qBytes = (size_t)all.bytes;
+        const bool direct = tun.directUpload && !all.gaps && be->host_pinned(in.queries[0], qBytes);
         const size_t tOff = round_up(qBytes, 16);
         const size_t total = tOff + round_up((size_t)n, 16) + 32;
         p->tg.push_back(Target{tptr, n, (uint64_t)tOff});
@@ -1003,23 +1025,29 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             const int a = lo + (int)((long long)(hi - lo) * part / partsPerSlice);
             const int b = lo + (int)((long long)(hi - lo) * (part + 1) / partsPerSlice);
             if (b > a) {
-                // runs of queries that are contiguous in the caller's memory are copied in one piece
-                int i = a;
-                while (i < b) {
-                    int j = i + 1;
-                    while (j < b && in.queries[j] == in.queries[j - 1] + p->qlen[j - 1]) ++j;
-                    const size_t bytes = (size_t)(p->qoff[j - 1] + (uint64_t)p->qlen[j - 1] - p->qoff[i]);
-                    memcpy(stage + p->qoff[i], in.queries[i], bytes);
-                    i = j;
-                }
                 const size_t off = (size_t)p->qoff[a];
                 const size_t bytes = (size_t)(p->qoff[b - 1] + (uint64_t)p->qlen[b - 1]) - off;
+                const uint8_t* src = stage + off;
+                if (direct) {
+                    // the reads lie back to back in pinned caller memory: the device reads them from there
+                    src = reinterpret_cast<const uint8_t*>(in.queries[0]) + off;
+                } else {
+                    // runs of queries that are contiguous in the caller's memory are copied in one piece
+                    int i = a;
+                    while (i < b) {
+                        int j = i + 1;
+                        while (j < b && in.queries[j] == in.queries[j - 1] + p->qlen[j - 1]) ++j;
+                        const size_t run = (size_t)(p->qoff[j - 1] + (uint64_t)p->qlen[j - 1] - p->qoff[i]);
+                        memcpy(stage + p->qoff[i], in.queries[i], run);
+                        i = j;
+                    }
+                }
                 while (!job.targetIssued.load(std::memory_order_acquire)) {  // (packing went on meanwhile)
                     std::this_thread::yield();
                     std::lock_guard<std::mutex> lock(job.mu);
                     if (job.abort) return;
                 }
-                be->h2d_copy(p->dSeq.p + off, stage + off, bytes);
+                be->h2d_copy(p->dSeq.p + off, src, bytes);
                 be->h2d_copy(p->dQoff.p + a, hQoff.p + a, (size_t)(b - a) * sizeof(uint64_t));
                 be->h2d_copy(p->dQlen.p + a, hQlen.p + a, (size_t)(b - a) * sizeof(int));
             }

@@ -24,6 +24,9 @@ struct Backend {
     virtual void free(void* p) = 0;
     virtual void* alloc_host(size_t bytes) = 0;  // staging memory (pinned on CUDA)
     virtual void free_host(void* p) = 0;
+    // Is [p, p + bytes) page-locked host memory the device can read directly (the caller allocated it pinned)?  Then
+    // uploads go straight from the caller's buffer, without the staging copy.
+    virtual bool host_pinned(const void* /*p*/, size_t /*bytes*/) { return false; }
     virtual void h2d(void* dst, const void* src, size_t bytes) = 0;
     virtual void d2h(void* dst, const void* src, size_t bytes) = 0;  // synchronising
     virtual void zero(void* dst, size_t bytes) = 0;
@@ -124,6 +127,8 @@ struct EngineTunables {
     int filterSpread = 1024;      // widest group of candidate ranges verified as one window
     int filterMaxWindows = 32;    // windows per read and stage before the next stage takes the read
     int filterMinTarget = 65536;  // shortest target worth filtering
+    size_t directMinBytes = 1u << 20;  // ... grouped batches: from this many query bytes on
+    int directUpload = 1;         // queries that are contiguous in PINNED caller memory are uploaded from there (no staging copy)
     int collapseEqualities = 1;   // transitive additional equalities: one code per group of equal bytes, no equality table
     int bandKernel = 1;           // k-banded NW sweeps of long queries on the thread-per-alignment band kernel (0: warp kernel)
     int filterSkipRepeats = 1;    // reads the last seed level found too repetitive skip the prefix stages (plain sweep)

@@ -712,6 +712,15 @@ struct CudaBackend : Backend {
         hostBlocks.push_back(HostBlock{p, want, true});
         return p;
     }
+    bool host_pinned(const void* p, size_t bytes) override {
+        if (!p || bytes == 0) return false;
+        cudaPointerAttributes a0, a1;
+        if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, static_cast<const char*>(p) + bytes - 1) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+    }
     void free_host(void* p) override {
         std::lock_guard<std::mutex> lock(hostMu);
         for (auto& b : hostBlocks)

@@ -648,9 +648,16 @@ void Pass::start_locations() {
                     t.mode = MODE_SHW;
                     t.flags = WF_QREV | WF_TREV;
                     t.kInit = p->ed[i] + 1;
-                    WPlan pl = plan_w(t.m, t.n, MODE_SHW, -1);
+                    // the reversed alignment has distance ed: it stays within ed diagonals of the main one, so the
+                    // window only has to slide down that band (every last-row score <= ed is exact, larger ones can
+                    // only come out larger; ref cpp:253-257 sweeps the same columns with k = ed)
+                    WPlan pl = plan_w_band(t.m, 2LL * p->ed[i] + 1, p->ed[i]);
                     t.R = pl.R;
                     t.nWp = pl.nWp;
+                    if (pl.slide) {
+                        t.flags |= WF_SLIDE;
+                        t.dhi = pl.dhi;
+                    }
                     tasks.push_back(std::move(t));
                     slotOf.push_back(slot);
                 }

@@ -117,6 +117,7 @@ struct EmulBackend : Backend {
     void free(void* p) override { ::free(p); }
     void* alloc_host(size_t bytes) override { return malloc(bytes ? bytes : 1); }
     void free_host(void* p) override { ::free(p); }
+    bool host_pinned(const void*, size_t) override { return getenv("EDLIB_EMUL_PINNED") != nullptr; }  // (tests: take the direct-upload path)
     void h2d(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
     void d2h(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
     void zero(void* d, size_t n) override { memset(d, 0, n); }

@@ -162,6 +162,56 @@ def test_read_sets_with_additional_equalities():
         assert ("filter seed stage" in out.stderr or "device stage" in out.stderr) == seeds
 
 
+DIRECT_UPLOAD_CODE = """
+import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)
+import ctypes as C, random
+import numpy as np
+import parity
+from edlib_b200._ffi import AlignResult, make_config, result_to_dict
+from helpers import mutate, rand_seq
+lib = LOAD
+chk = parity.checker()
+rng = random.Random(5)
+total = 0
+for mode, task, shared in ((2, 1, True), (2, 0, True), (0, 0, False), (2, 2, False)):
+    n, m = 300, 150
+    t = rand_seq(rng, 6000, b"ACGT")
+    reads = ALLOC((n, m))          # ONE block: query i starts where query i-1 ends
+    for i in range(n):
+        a = rng.randrange(0, len(t) - m - 20)
+        q = (mutate(rng, t[a:a + m + 10], 0.03, b"ACGT") + b"A" * m)[:m]
+        reads[i] = np.frombuffer(q, dtype=np.uint8)
+    tb = [C.create_string_buffer(t, len(t))] if shared else [C.create_string_buffer(t[i %% 50:], len(t) - i %% 50) for i in range(n)]
+    tl = [len(t)] * n if shared else [len(t) - i %% 50 for i in range(n)]
+    qptr = (C.c_char_p * n)(*[C.cast(reads.ctypes.data + i * m, C.c_char_p) for i in range(n)])
+    qlen = (C.c_int * n)(*[m] * n)
+    tptr = (C.c_char_p * n)(*[C.cast(tb[0 if shared else i], C.c_char_p) for i in range(n)])
+    tlen = (C.c_int * n)(*tl)
+    cfg, keep = make_config(-1, mode, task, None)
+    res = (AlignResult * n)()
+    assert lib.lib.edlibAlignBatch(qptr, qlen, tptr, tlen, n, cfg, res) == 0
+    for i in range(n):
+        got = result_to_dict(res[i])
+        lib.free(res[i])
+        tt = t if shared else t[i %% 50:]
+        assert got == chk.align(reads[i].tobytes(), tt, -1, mode, task, None), (mode, task, i)
+    total += n
+print(total)
+"""
+
+
+def test_queries_in_one_pinned_block_are_uploaded_directly():
+    """Queries that lie back to back in page-locked caller memory skip the staging copy (streamed read sets and grouped
+    batches); the emulation backend is told to treat every host buffer as pinned."""
+    code = (DIRECT_UPLOAD_CODE % (REPO, os.path.join(REPO, "tests"))).replace("LOAD", "__import__('test_engine_emul').load_emul()") \
+        .replace("ALLOC", "(lambda shape: np.zeros(shape, dtype=np.uint8))")
+    for extra in ({"EDLIB_EMUL_PINNED": "1"}, {"EDLIB_EMUL_PINNED": "1", "EDLIB_B200_PACK_PARALLEL_KB": "16", "EDLIB_B200_HOST_THREADS": "4"},
+                  {"EDLIB_EMUL_PINNED": "1", "EDLIB_B200_DIRECT_UPLOAD": "0"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_DIRECT_MIN_KB="1", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) == 1200
+
+
 TARGET_HANDLE_CODE = """
 import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)
 import ctypes as C, random

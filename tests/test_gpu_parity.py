@@ -95,6 +95,20 @@ def test_read_sets_with_additional_equalities(lib):
     assert parity.run_batches(lib, 91, 12, gen=cases.equality_read_cases) > 400
 
 
+def test_queries_in_one_pinned_block_are_uploaded_directly():
+    """Reads in ONE page-locked block (torch pin_memory): the device reads them from the caller's buffer, no staging
+    copy -- streamed read sets and grouped batches; same results as ever."""
+    import subprocess
+    from edlib_b200._ffi import REPO
+    from test_engine_emul import DIRECT_UPLOAD_CODE
+    code = (DIRECT_UPLOAD_CODE % (REPO, os.path.join(REPO, "tests"))).replace("LOAD", "__import__('helpers').product()") \
+        .replace("ALLOC", "(lambda shape: __import__('torch').zeros(shape, dtype=__import__('torch').uint8, pin_memory=True).numpy())")
+    for extra in ({}, {"EDLIB_B200_DIRECT_UPLOAD": "0"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_DIRECT_MIN_KB="1", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) == 1200
+
+
 def test_target_handle():
     """edlibB200TargetPrepare on the GPU: same results with and without a resident target."""
     import subprocess
