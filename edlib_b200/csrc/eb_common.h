@@ -130,6 +130,9 @@ struct LParams {
     const uint8_t* eqtab;
     Rec* recs;         // [numJobs]
     U2* mat;
+    int matStep;       // storing launches: entries between consecutive (column, word) cells of one job; 0 / 1: the job's
+                       // matrix is contiguous, 32: the matrices of 32 consecutive jobs are interleaved entry by entry, so
+                       // that a warp's stores of one (column, word) form one 256-byte run
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -207,6 +210,7 @@ struct TbParams {
     uint8_t* ops;
     int* opsStart;     // [job] index of the first op inside the job's reserved area
     int* opsLen;       // [job]
+    int matStep;       // as LParams::matStep
 };
 
 // Hirschberg split search (ref cpp:1321-1353) over the two stop columns of a node, on the device.

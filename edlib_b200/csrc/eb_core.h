@@ -1125,6 +1125,7 @@ EB_HD void lane_job(const LParams& p, int jobIdx, Acc& acc) {
     const uint8_t* t = p.tcodes + J.tOff;
     if (STORE) {
         U2* mat = p.mat + J.matOff;
+        const size_t step = p.matStep > 1 ? (size_t)p.matStep : 1;
         for (int c = 0; c < J.n; ++c) {
             uint32_t Eq[NW], Ph[NW];
             acc.load(t[c], Eq);
@@ -1134,7 +1135,7 @@ EB_HD void lane_job(const LParams& p, int jobIdx, Acc& acc) {
                 U2 e;
                 e.x = st.Pv[w];
                 e.y = Ph[w];
-                mat[(size_t)c * NW + w] = e;
+                mat[((size_t)c * NW + w) * step] = e;
             }
         }
     } else if (REV) {
@@ -1239,7 +1240,7 @@ EB_HD void res_item(const ResParams& p, int i) {
             LJob J;
             J.qOff = p.qoff[pair];
             J.tOff = res_target_off(p, pair) + (uint64_t)s0;
-            J.matOff = (uint64_t)j * p.matStride;
+            J.matOff = (uint64_t)(j / 32) * 32u * p.matStride + (uint64_t)(j % 32);  // interleaved by 32 jobs (LParams::matStep)
             J.m = p.qlen[pair];
             J.n = e0 - s0 + 1;  // <= 0: empty target slice, the script is m inserts (ref cpp:1168-1175)
             if (J.n < 0) J.n = 0;
@@ -1746,6 +1747,7 @@ EB_HD void traceback_job(const TbParams& p, int jobIdx) {
         return;
     }
     const U2* mat = p.mat + J.matOff;
+    const size_t step = p.matStep > 1 ? (size_t)p.matStep : 1;
     const uint32_t* peq = p.peq + (J.peqOff != ~0ull ? J.peqOff : 0);
     const uint8_t* t = p.tcodes + J.tOff;
     uint8_t* ops = p.ops + J.outOff;
@@ -1754,7 +1756,7 @@ EB_HD void traceback_job(const TbParams& p, int jobIdx) {
     int r = J.m - 1, c = J.n - 1;
     for (;;) {
         const int g = r + off;
-        const U2 e = mat[(size_t)c * J.nWp + (g >> 5)];
+        const U2 e = mat[((size_t)c * J.nWp + (g >> 5)) * step];
         const uint32_t bit = 1u << (g & 31);
         if (e.x & bit) {  // up
             ops[--w] = 1;

@@ -575,14 +575,14 @@ struct Pass {
             DevBuf<Rec> dRecs(be, n);
             be->zero(dRecs.p, n * sizeof(Rec));
             DevBuf<U2> dMat(be, matEntries);
-            LParams lp{dJobs.p, (int)n, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p};
+            LParams lp{dJobs.p, (int)n, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p, 1};
             be->launch_lane(lp, nw, MODE_NW, false, true);
             DevBuf<TbJob> dTb(be, n);
             dTb.upload(tb.data(), n);
             DevBuf<uint8_t> dOps(be, opsBytes);
             DevBuf<int> dStart(be, n), dLen(be, n);
             TbParams tp{dTb.p, (int)n, dMat.p, nullptr, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
-                        dOps.p, dStart.p, dLen.p};
+                        dOps.p, dStart.p, dLen.p, 1};
             be->launch_traceback(tp);
             // one pinned staging block for everything that comes back (fast D2H, no zero-fill of vectors)
             const size_t offSt = round_up(n * sizeof(Rec), 64), offLn = offSt + round_up(n * sizeof(int), 64);

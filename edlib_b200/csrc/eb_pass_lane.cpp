@@ -28,7 +28,7 @@ void Pass::lane_launch(const std::vector<LJob>& jobs, int nw, int laneMode, bool
         dJobs.upload(jobs.data() + a, n);
         DevBuf<Rec> dRecs(be, n);
         be->zero(dRecs.p, n * sizeof(Rec));
-        LParams lp{dJobs.p, (int)n, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, nullptr};
+        LParams lp{dJobs.p, (int)n, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, nullptr, 1};
         be->launch_lane(lp, nw, laneMode, rev, false);
         dRecs.download(recs.data() + a, n);
         stats.d2hBytes += (long long)n * (long long)sizeof(Rec);

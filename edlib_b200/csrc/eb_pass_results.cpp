@@ -487,7 +487,7 @@ void Pass::start_locations_device() {
         rp.stage = RS_LOC_JOBS;
         rp.numItems = T;
         be->launch_res(rp);
-        LParams lp{dJobs.p, T, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, nullptr};
+        LParams lp{dJobs.p, T, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, nullptr, 1};
         be->launch_lane(lp, nw, MODE_SHW, true, false);
         rp.stage = RS_LOC_APPLY;
         be->launch_res(rp);
@@ -551,7 +551,7 @@ void Pass::paths_device() {
             DevBuf<TbJob> dTb(be, (size_t)J);
             DevBuf<int> dJobPair(be, (size_t)J), dOpsStart(be, (size_t)J), dOpsLen(be, (size_t)J);
             DevBuf<Rec> dRecs(be, (size_t)J);
-            DevBuf<U2> dMat(be, (size_t)J * matStride);
+            DevBuf<U2> dMat(be, (size_t)ceil_div(J, 32) * 32 * matStride);
             DevBuf<uint8_t> dOps(be, (size_t)J * opsStride);
             rp.jobs = dJobs.p;
             rp.tb = dTb.p;
@@ -561,10 +561,10 @@ void Pass::paths_device() {
             rp.opsStride = opsStride;
             rp.stage = RS_PATH_JOBS;
             be->launch_res(rp);
-            LParams lp{dJobs.p, J, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p};
+            LParams lp{dJobs.p, J, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p, 32};
             be->launch_lane(lp, nw, MODE_NW, false, true);
             TbParams tp{dTb.p, J, dMat.p, nullptr, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
-                        dOps.p, dOpsStart.p, dOpsLen.p};
+                        dOps.p, dOpsStart.p, dOpsLen.p, 32};
             be->launch_traceback(tp);
             rp.cnt = dLen.p;
             rp.ops = dOps.p;

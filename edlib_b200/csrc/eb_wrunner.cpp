@@ -230,7 +230,7 @@ void WRunner::run_lane(std::vector<WTask>& tasks, const std::vector<int>& idx, i
         DevBuf<Rec> dRecs(be, J);
         be->zero(dRecs.p, (size_t)J * sizeof(Rec));
         DevBuf<U2> dMat(be, matEntries);
-        LParams lp{dJobs.p, J, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p};
+        LParams lp{dJobs.p, J, p->dSeq.p, p->dSeq.p, p->ncodes, p->hasEq ? p->dEqtab.p : nullptr, dRecs.p, dMat.p, 1};
         be->launch_lane(lp, nw, mode, rev, store);
         DevBuf<TbJob> dTb;
         DevBuf<uint8_t> dOps;
@@ -242,7 +242,7 @@ void WRunner::run_lane(std::vector<WTask>& tasks, const std::vector<int>& idx, i
             dOpsStart.alloc(be, tb.size());
             dOpsLen.alloc(be, tb.size());
             TbParams tp{dTb.p, (int)tb.size(), dMat.p, nullptr, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
-                        dOps.p, dOpsStart.p, dOpsLen.p};
+                        dOps.p, dOpsStart.p, dOpsLen.p, 1};
             be->launch_traceback(tp);
         }
         std::vector<Rec> recs(J);
@@ -350,7 +350,7 @@ void WRunner::run_slice(std::vector<WTask>& tasks, const std::vector<int>& slice
         dOpsStart.alloc(be, tb.size());
         dOpsLen.alloc(be, tb.size());
         TbParams tp{dTb.p, (int)tb.size(), dMat.p, dPeq.p, p->dSeq.p, p->dSeq.p, p->hasEq ? p->dEqtab.p : nullptr, p->ncodes,
-                    dOps.p, dOpsStart.p, dOpsLen.p};
+                    dOps.p, dOpsStart.p, dOpsLen.p, 1};
         be->launch_traceback(tp);
     }
 
