@@ -266,6 +266,7 @@ class Engine:
         L.edlibB200TargetPrepare.restype = C.c_void_p
         L.edlibB200TargetPrepare.argtypes = [C.c_void_p, C.c_int]
         L.edlibB200TargetFree.argtypes = [C.c_void_p]
+        self.numa_node = int(L.edlibB200DeviceNumaNode())
         self.libc = C.CDLL(None)
         self.libc.free.argtypes = [C.c_void_p]
 
@@ -505,7 +506,7 @@ def sensitivity(E, genome, base_reads, flush, barrier):
 def config3(E, genome, pairs, steps, cores, cpu_seconds, peak, peak_src, barrier):
     """BASELINE configs[2]: `pairs` x 10 kbp queries vs their 3 %-mutated copies, NW, k = 500, EDLIB_TASK_LOC."""
     t0 = time.time()
-    qbuf, tbuf, tlens = workloads.long_pairs_packed(genome, pairs, 10_000, seed=43, pinned=True)
+    qbuf, tbuf, tlens = workloads.long_pairs_packed(genome, pairs, 10_000, seed=43, pinned=True, numa_node=E.numa_node)
     gen_s = time.time() - t0
     n = pairs
     qptr = (qbuf.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(qbuf.shape[1])).astype(np.uint64)
@@ -636,7 +637,7 @@ def strong_scaling(E, genome, total_reads, steps, rank, world, dev, barrier):
     n_t = len(genome)
     lo, hi = sharding.shard_range(total_reads, rank, world)
     # every rank derives its shard of the seeded batch: read i only depends on (seed, i)
-    reads = workloads.pinned_empty((hi - lo, READ_LEN))
+    reads = workloads.pinned_empty((hi - lo, READ_LEN), numa_node=E.numa_node)
     workloads._synth().synth_reads_range(genome.ctypes.data, n_t, reads.ctypes.data, lo, hi, READ_LEN, 0.03, 44)
     cfg, _ = make_config(-1, MODE_HW, TASK_DISTANCE)
     times = []
@@ -762,7 +763,7 @@ def main():
     t_len = 4_630_707 if args.target == "ecoli" else SYNTH_TARGET_LEN
     if world > 1:
         target = sharding.broadcast_target(target, t_len, dev)
-    reads = workloads.reads_of(target, n_reads, READ_LEN, seed=42 + rank, pinned=True)
+    reads = workloads.reads_of(target, n_reads, READ_LEN, seed=42 + rank, pinned=True, numa_node=E.numa_node)
     cells_rank = float(n_reads) * READ_LEN * t_len
     cores = effective_cores()
 
@@ -797,8 +798,9 @@ def main():
                                    "target (%s), per GPU" % (n_reads, READ_LEN, t_len,
                                                              "E. coli DH1 genome of the reference's test data" if args.target == "ecoli"
                                                              else "uniform-random DNA, seed 1"),
-                       "inputs": "the read array lives in pinned host memory (torch pin_memory); end-to-end calls upload it from "
-                                 "there (no staging copy); results are malloc'd arrays per read as in the reference",
+                       "inputs": "the read array lives in pinned host memory (torch pin_memory) on the GPU's NUMA node (node %d); "
+                                 "end-to-end calls upload it from there (no staging copy); results are malloc'd arrays per read "
+                                 "as in the reference" % E.numa_node,
                        "l2": "256 MiB write between steps (reads 150 MB > L2; the target is meant to stay L2-resident)",
                        "parallelism": "reads sharded over %d rank(s); target broadcast once" % world,
                        "index": "the seed index of the target is rebuilt inside every timed step (no target handle)"},
@@ -844,7 +846,7 @@ def main():
 
         def synthetic():
             other = workloads.random_dna(SYNTH_TARGET_LEN, 1) if args.target == "ecoli" else workloads.ecoli_genome()
-            rd = workloads.reads_of(other, n_reads, READ_LEN, seed=42, pinned=True)
+            rd = workloads.reads_of(other, n_reads, READ_LEN, seed=42, pinned=True, numa_node=E.numa_node)
             r2, e2, ed2, nl2, _ = run_reads_workload(E, other, rd, 5, 2, 3, flush_l2, barrier)
             c = float(n_reads) * READ_LEN * len(other)
             return {"target": "uniform-random 5,000,000 bp (seed 1)" if args.target == "ecoli" else "E. coli DH1 (4,630,707 bp)",

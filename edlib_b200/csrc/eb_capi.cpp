@@ -167,6 +167,11 @@ EDLIB_API int edlibB200SetDevice(int device) {
     return eb::select_device(device, &g_initError) == 0 ? EDLIB_STATUS_OK : EDLIB_STATUS_ERROR;
 }
 
+EDLIB_API int edlibB200DeviceNumaNode(void) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    return engine_locked() ? g_backend->numa_node() : -1;
+}
+
 EDLIB_API void edlibB200FreeResults(EdlibAlignResult* results, int n) {
     if (!results) return;
     for (int i = 0; i < n; ++i) {

@@ -43,6 +43,10 @@ typedef struct {
  * already initialised on another device or the device does not exist. */
 EDLIB_API int edlibB200SetDevice(int device);
 
+/* NUMA node the selected device hangs off (-1: unknown).  Host buffers a caller hands to edlibAlignBatch travel fastest
+ * when they live on that node (page-locked buffers are read by the device directly). */
+EDLIB_API int edlibB200DeviceNumaNode(void);
+
 /* free() the arrays of `n` results at once (same effect as n edlibFreeAlignResult calls). */
 EDLIB_API void edlibB200FreeResults(EdlibAlignResult* results, int n);
 
