@@ -1073,7 +1073,9 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             }
             job.matDone[task] = 1;
         };
-        const size_t packTasks = (size_t)numSlices * partsPerSlice;
+        // direct uploads need no packing: the orchestrator issues the copies of every slice itself, slice by slice, so
+        // that they reach the copy stream in the order the slices are computed in
+        const size_t packTasks = direct ? 0 : (size_t)numSlices * partsPerSlice;
         const size_t matTasks = matInJob ? (size_t)numSlices * matPartsPerSlice : 0;
         job.matDone.assign(matTasks, 0);
         freeBuilt = [&, sliceReads, matPartsPerSlice]() {  // error path: the arrays of the result structs built so far
@@ -1115,6 +1117,21 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
 
         // ---- target: upload, presence set, codes, encoding, seed index (while the workers pack slice 0); a target the
         // caller keeps resident (edlibB200TargetPrepare) brings all of that along ----
+        // Reads in pinned caller memory: their copies go onto the copy stream right behind the target's, slice by slice (in
+        // the order the slices are computed in), and run while the target is prepared below.
+        auto issue_direct_uploads = [&]() {
+            if (!direct) return;
+            for (int s = 0; s < numSlices; ++s) {
+                const int lo = slice_lo(s), hi = slice_lo(s + 1);
+                const size_t off = (size_t)p->qoff[lo];
+                const size_t bytes = (size_t)(p->qoff[hi - 1] + (uint64_t)p->qlen[hi - 1]) - off;
+                be->h2d_copy(p->dSeq.p + off, reinterpret_cast<const uint8_t*>(in.queries[0]) + off, bytes);
+                be->h2d_copy(p->dQoff.p + lo, hQoff.p + lo, (size_t)(hi - lo) * sizeof(uint64_t));
+                be->h2d_copy(p->dQlen.p + lo, hQlen.p + lo, (size_t)(hi - lo) * sizeof(int));
+                std::lock_guard<std::mutex> lock(job.mu);
+                job.uploadMark[(size_t)s] = be->mark(Backend::STREAM_COPY);
+            }
+        };
         TargetHandle* const kept = find_target(tptr, n);
         DevBuf<MaskItem> dItems;
         DevBuf<uint32_t> dMaskOwn;
@@ -1127,6 +1144,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             if (tOff > qBytes) be->zero(p->dSeq.p + qBytes, tOff - qBytes);
             be->d2d(p->dSeq.p + tOff, kept->codes.p, kept->bytes);  // (bytes == total - tOff)
             job.targetIssued.store(1, std::memory_order_release);
+            issue_direct_uploads();
             dMaskP = kept->dMask.p;
             dMapP = kept->dMap.p;
             memcpy(map, kept->map, sizeof(map));
@@ -1138,6 +1156,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             be->h2d_copy(p->dSeq.p + qBytes, stage + qBytes, total - qBytes);
             const uint64_t targetUp = be->mark(Backend::STREAM_COPY);
             job.targetIssued.store(1, std::memory_order_release);
+            issue_direct_uploads();
             be->wait(Backend::STREAM_COMPUTE, targetUp);
             std::vector<MaskItem> items;
             for (int s0 = 0; s0 < n; s0 += 65536) items.push_back(MaskItem{(uint64_t)tOff + (uint64_t)s0, std::min(65536, n - s0), 0});
@@ -1170,6 +1189,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
         if (ncodes >= 256) {  // no spare code: every byte value occurs in the target, so no read byte is foreign
             p->ncodes = 256;
         }
+        trace.mark("stream: target uploaded + encoded");
         stats = EngineStats();
         stats.h2dBytes = (long long)(kept ? qBytes : total) + 12LL * N;
         be->reset_timing();
@@ -1197,6 +1217,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             return false;
         }
         stats.k1Cells = all.bytes * (long long)n;
+        trace.mark("stream: pass + index");
         ps.dev_begin(numSlices);
         ps.dPool.alloc(be, (size_t)(4LL * N + N / 4 + (long long)DEV_EXTRA_SLACK * numSlices + 64));
         p->endPool.resize(ps.dPool.n);
@@ -1204,7 +1225,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
 
         // ---- slices: enqueue as their uploads are issued ----
         for (int s = 0; s < numSlices; ++s) {
-            if (workers == 0) {  // no pool: the caller packs the slice itself
+            if (!direct && workers == 0) {  // no pool: the caller packs the slice itself
                 for (int part = 0; part < partsPerSlice; ++part) pack_part((size_t)s * partsPerSlice + part);
             }
             uint64_t up = 0;

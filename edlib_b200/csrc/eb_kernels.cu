@@ -391,6 +391,7 @@ __global__ void seed_fill_kernel(const SeedIndexParams p) {
 // lookups (key -> bucket bounds -> positions -> target symbols, a chain of dependent random reads) are in flight
 // together; candidates meet in shared memory, lane 0 of the group sorts them and emits the windows.
 struct CoopGroup8 {
+    static constexpr int W = 8;
     static EB_D int lane() { return (int)(threadIdx.x & 7u); }
     static EB_D int width() { return 8; }
     static EB_D unsigned mask() { return 0xffu << (threadIdx.x & 24u); }
@@ -398,16 +399,26 @@ struct CoopGroup8 {
     static EB_D bool any(bool v) { return __ballot_sync(mask(), v) != 0u; }
     static EB_D int add_shared(int* p, int v) { return atomicAdd(p, v); }
 };
+// A whole warp per read: the last seed level sees few reads with long index ranges and thousands of candidates.
+struct CoopGroup32 {
+    static constexpr int W = 32;
+    static EB_D int lane() { return (int)(threadIdx.x & 31u); }
+    static EB_D int width() { return 32; }
+    static EB_D void sync() { __syncwarp(); }
+    static EB_D bool any(bool v) { return __any_sync(0xffffffffu, v) != 0; }
+    static EB_D int add_shared(int* p, int v) { return atomicAdd(p, v); }
+};
 // (CTAs of THREADS / 8 groups: the largest candidate capacity gets small CTAs so that its scratch fits shared memory)
-template <int CAP, int THREADS>
+template <int CAP, int THREADS, class Group>
 __global__ void __launch_bounds__(THREADS) seed_plan_kernel(const SeedPlanParams p) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    constexpr int GROUPS = THREADS / 8;
+    constexpr int GW = Group::W;
+    constexpr int GROUPS = THREADS / GW;
     int* E = reinterpret_cast<int*>(smemRaw);              // [groups][CAP]
     int* ctl = E + GROUPS * CAP;                            // [groups][SEED_CTL]
-    const int g = threadIdx.x >> 3;
+    const int g = threadIdx.x / GW;
     const int slot = blockIdx.x * GROUPS + g;
-    if (slot < p.numReads) seed_plan_read<CAP, CoopGroup8>(p, slot, E + g * CAP, ctl + g * SEED_CTL);
+    if (slot < p.numReads) seed_plan_read<CAP, Group>(p, slot, E + g * CAP, ctl + g * SEED_CTL);
 }
 __global__ void win_reduce_kernel(const WinReduceParams p) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1042,19 +1053,19 @@ struct CudaBackend : Backend {
         }
         free(tileSums);
     }
-    template <int CAP, int THREADS>
+    template <int CAP, int THREADS, class Group, int GW>
     void launch_seed_plan_t(const SeedPlanParams& p) {
-        constexpr int GROUPS = THREADS / 8;
+        constexpr int GROUPS = THREADS / GW;
         const size_t smem = (size_t)GROUPS * ((size_t)CAP + SEED_CTL) * sizeof(int);
         if (smem > 48 * 1024)
-            EB_CUDA(cudaFuncSetAttribute(seed_plan_kernel<CAP, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        seed_plan_kernel<CAP, THREADS><<<(p.numReads + GROUPS - 1) / GROUPS, THREADS, smem, stream>>>(p);
+            EB_CUDA(cudaFuncSetAttribute(seed_plan_kernel<CAP, THREADS, Group>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        seed_plan_kernel<CAP, THREADS, Group><<<(p.numReads + GROUPS - 1) / GROUPS, THREADS, smem, stream>>>(p);
     }
     void launch_seed_plan(const SeedPlanParams& p) override {
         Scope s(this, "seed_plan");
-        if (p.level <= 0) launch_seed_plan_t<SEED_CAND_0, 128>(p);
-        else if (p.level == 1) launch_seed_plan_t<SEED_CAND_1, 128>(p);
-        else launch_seed_plan_t<SEED_CAND_2, 32>(p);
+        if (p.level <= 0) launch_seed_plan_t<SEED_CAND_0, 128, CoopGroup8, 8>(p);
+        else if (p.level == 1) launch_seed_plan_t<SEED_CAND_1, 128, CoopGroup8, 8>(p);
+        else launch_seed_plan_t<SEED_CAND_2, 64, CoopGroup32, 32>(p);  // a warp per read, two reads per CTA
         check_launch("seed_plan");
     }
     void launch_fin_count(const FinParams& p) override {
