@@ -763,6 +763,10 @@ def main():
     t_len = 4_630_707 if args.target == "ecoli" else SYNTH_TARGET_LEN
     if world > 1:
         target = sharding.broadcast_target(target, t_len, dev)
+    E_numa = E.numa_node
+    pinned_target = workloads.pinned_empty((t_len,), numa_node=E_numa)  # the genome too sits in pinned host memory
+    pinned_target[:] = target
+    target = pinned_target
     reads = workloads.reads_of(target, n_reads, READ_LEN, seed=42 + rank, pinned=True, numa_node=E.numa_node)
     cells_rank = float(n_reads) * READ_LEN * t_len
     cores = effective_cores()

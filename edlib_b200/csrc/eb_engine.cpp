@@ -1005,7 +1005,8 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
         trace.mark("stream: lengths + offsets + buffers");
 
         // slices of reads; every slice is packed by all workers together (parts), so that slice 0 is on its way first
-        const int sliceReads = std::min(tun.devSliceReads, std::max(4096, ceil_div(N, 4)));
+        // at least eight slices for big batches: the result structs of the last slice are the tail of the call
+        const int sliceReads = std::min(tun.devSliceReads, std::max(4096, ceil_div(N, N >= 262144 ? 8 : 4)));
         const int numSlices = ceil_div(N, sliceReads);
         const size_t W = HostPool::get().width();
         const size_t workers = W > 1 ? W - 1 : 0;  // the caller orchestrates
@@ -1150,10 +1151,16 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
             memcpy(map, kept->map, sizeof(map));
             ncodes = kept->ncodesRaw;
         } else {
-            memcpy(stage + tOff, tptr, (size_t)n);
-            memset(stage + tOff + n, 0, total - tOff - (size_t)n);
-            if (tOff > qBytes) memset(stage + qBytes, 0, tOff - qBytes);
-            be->h2d_copy(p->dSeq.p + qBytes, stage + qBytes, total - qBytes);
+            if (tun.directUpload && be->host_pinned(tptr, (size_t)n)) {  // pinned caller memory: no staging copy
+                be->h2d_copy(p->dSeq.p + tOff, tptr, (size_t)n);
+                if (tOff > qBytes) be->zero(p->dSeq.p + qBytes, tOff - qBytes);  // (compute stream; the encode kernel follows there)
+                be->zero(p->dSeq.p + tOff + n, total - tOff - (size_t)n);
+            } else {
+                memcpy(stage + tOff, tptr, (size_t)n);
+                memset(stage + tOff + n, 0, total - tOff - (size_t)n);
+                if (tOff > qBytes) memset(stage + qBytes, 0, tOff - qBytes);
+                be->h2d_copy(p->dSeq.p + qBytes, stage + qBytes, total - qBytes);
+            }
             const uint64_t targetUp = be->mark(Backend::STREAM_COPY);
             job.targetIssued.store(1, std::memory_order_release);
             issue_direct_uploads();
