@@ -642,15 +642,24 @@ def strong_scaling(E, genome, total_reads, steps, rank, world, dev, barrier):
     cfg, _ = make_config(-1, MODE_HW, TASK_DISTANCE)
     times = []
     mean_ed = None
+    # buffers that live across the steps: the rank's copy of the target (pinned: one address, so the pointer arrays are
+    # built once), the gathered distances on rank 0
+    tbuf = workloads.pinned_empty((n_t,), numa_node=E.numa_node)
+    if world == 1:
+        tbuf[:] = genome
+    ptrs = pointer_arrays(reads, tbuf)
+    counts = [sharding.shard_range(total_reads, r, world)[1] - sharding.shard_range(total_reads, r, world)[0] for r in range(world)]
+    all_out = workloads.pinned_empty((total_reads,), dtype=np.int32, numa_node=E.numa_node) if (rank == 0 and world > 1) else None
     for it in range(1 + steps):
         res = np.empty(hi - lo, dtype=RESULT_DTYPE)
         res.view(np.uint8).fill(0)
         barrier()
         t0 = time.perf_counter()
-        target = sharding.broadcast_target(genome if rank == 0 else None, n_t, dev) if world > 1 else genome
-        E.align_batch(pointer_arrays(reads, target), hi - lo, cfg, res)
-        eds = res["editDistance"].copy()
-        all_eds = sharding.gather_int32(eds, dev) if world > 1 else eds
+        if world > 1:
+            sharding.broadcast_target_into(genome if rank == 0 else None, tbuf, dev)
+        E.align_batch(ptrs, hi - lo, cfg, res)
+        eds = np.ascontiguousarray(res["editDistance"])
+        all_eds = sharding.gather_int32_known(eds, counts, dev, out=all_out) if world > 1 else eds
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         E.free(res)

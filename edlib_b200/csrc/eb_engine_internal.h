@@ -33,7 +33,9 @@ struct Trace {
     void mark(const char* what) {
         if (!on) return;
         const auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[edlib_b200] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        const char* rank = getenv("RANK");
+        fprintf(stderr, "[edlib_b200%s%s] %-28s %8.2f ms\n", rank ? " r" : "", rank ? rank : "", what,
+                std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
     }
 };

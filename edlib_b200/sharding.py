@@ -40,3 +40,33 @@ def gather_int32(values, device, dst=0):
     if rank != dst:
         return None
     return np.concatenate([b[:int(s.item())].cpu().numpy() for b, s in zip(bufs, sizes)])
+
+
+def broadcast_target_into(target, out, device, src=0):
+    """As broadcast_target, but every rank receives the bytes in its own host buffer `out` (uint8 numpy, e.g. pinned):
+    the target keeps ONE address per rank from step to step, so pointer arrays built on it stay valid."""
+    rank = dist.get_rank()
+    buf = torch.from_numpy(target).to(device) if rank == src else torch.empty(len(out), dtype=torch.uint8, device=device)
+    dist.broadcast(buf, src=src)
+    torch.from_numpy(out).copy_(buf)
+    return out
+
+
+def gather_int32_known(values, counts, device, out=None, dst=0):
+    """gather_int32 when every rank's count is known up front (shard_range): one gather, no size exchange; `out`
+    (int32 numpy of sum(counts), e.g. pinned) receives the concatenation on `dst`."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cap = max(counts)
+    padded = torch.zeros(cap, dtype=torch.int32, device=device)
+    padded[:len(values)] = torch.from_numpy(np.ascontiguousarray(values, dtype=np.int32)).to(device, non_blocking=True)
+    bufs = [torch.empty(cap, dtype=torch.int32, device=device) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst)
+    if rank != dst:
+        return None
+    if out is None:
+        out = np.empty(sum(counts), dtype=np.int32)
+    at = 0
+    for b, c in zip(bufs, counts):
+        torch.from_numpy(out[at:at + c]).copy_(b[:c])
+        at += c
+    return out

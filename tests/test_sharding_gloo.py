@@ -25,8 +25,16 @@ lo, hi = sharding.shard_range(N, rank, world)
 t = target.tobytes()
 st, res = lib.align_batch([reads[i].tobytes() for i in range(lo, hi)], [t] * (hi - lo), -1, 2, 0)
 assert st == 0
-got = sharding.gather_int32(np.array([r["editDistance"] for r in res], dtype=np.int32), torch.device("cpu"))
+eds = np.array([r["editDistance"] for r in res], dtype=np.int32)
+got = sharding.gather_int32(eds, torch.device("cpu"))
+# the variants bench.py's strong-scaling step uses: target into a caller buffer, gather with known counts
+tbuf = np.zeros(TL, dtype=np.uint8)
+sharding.broadcast_target_into(target if rank == 0 else None, tbuf, torch.device("cpu"))
+assert (tbuf == target).all()
+counts = [sharding.shard_range(N, r, world)[1] - sharding.shard_range(N, r, world)[0] for r in range(world)]
+got2 = sharding.gather_int32_known(eds, counts, torch.device("cpu"))
 if rank == 0:
+    assert got2.tolist() == got.tolist()
     st, full = lib.align_batch([reads[i].tobytes() for i in range(N)], [t] * N, -1, 2, 0)
     assert got.tolist() == [r["editDistance"] for r in full]
     print("GLOO_OK", len(got))
