@@ -794,6 +794,14 @@ def main():
         all_eds = sharding.gather_int32(eds, dev)  # (the gather of results on rank 0; timed in `strong`)
         if rank == 0:
             assert len(all_eds) == world * n_reads
+    per_rank = None
+    if world > 1:  # what every rank saw (the slowest one sets the value): step time, device time of its kernels, e2e step
+        mine = torch.tensor([1000.0 * sum(rs["step_s"]) / max(args.steps, 1), rs["kernel_ms"],
+                             1000.0 * sum(ee["times"]) / max(args.e2e_steps, 1)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"rank": r, "ms_per_step": float(t[0]), "kernel_ms_per_step": float(t[1]), "e2e_ms_per_step": float(t[2])}
+                    for r, t in enumerate(allr)]
     elapsed = float(elapsed.item())
     e2e_value = (world * cells_rank * args.e2e_steps / float(e2e_t.item()) / 1e9) if args.e2e_steps > 0 else None
 
@@ -826,6 +834,7 @@ def main():
             "mean_edit_distance": float(eds.mean()), "mean_num_locations": float(nloc.mean()),
             "filter": rs["filter"], "kernel_ms_per_step": rs["kernel_ms"],
             "kernel_share_of_step": rs["kernel_ms"] / (1000.0 * elapsed / args.steps),
+            "per_rank": per_rank,
         }
     # ---- strong scaling (configs[4]) on every N; the other sub-records on one GPU only ----
     wanted = set() if args.no_extras else set(x for x in args.extras.split(",") if x)
