@@ -70,17 +70,18 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: ONE nvidia-smi process (rank 0) watches
+    the GPUs of all local ranks (a poller per rank would only add driver traffic)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_indices):
+        self.rows, self.proc, self.idx = [], None, list(gpu_indices)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
@@ -93,27 +94,31 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        """{gpu index: {"sm_mhz": median under load, "sm_max_mhz", "reasons", "samples"}}"""
         if not self.proc:
-            return None
+            return {}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {}
+        for gpu in self.idx:
+            sm, mx, reasons = [], [], set()
+            for r in self.rows:
+                try:
+                    if int(r[0]) != gpu:
+                        continue
+                    sm.append(float(r[1]))
+                    mx.append(float(r[2]))
+                except Exception:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out[gpu] = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
 
 
 def effective_cores():
@@ -267,6 +272,7 @@ class Engine:
         L.edlibB200TargetPrepare.argtypes = [C.c_void_p, C.c_int]
         L.edlibB200TargetFree.argtypes = [C.c_void_p]
         self.numa_node = int(L.edlibB200DeviceNumaNode())
+        self.allocator_tuned = L.edlibB200TuneHostAllocator() == 0  # keep freed result arrays in the allocator (edlib_b200.h)
         self.libc = C.CDLL(None)
         self.libc.free.argtypes = [C.c_void_p]
 
@@ -780,12 +786,15 @@ def main():
     cells_rank = float(n_reads) * READ_LEN * t_len
     cores = effective_cores()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    sampler = ClockSampler(range(local_world)) if rank == 0 else None
+    if sampler:
+        sampler.start()
     rs, ee, eds, nloc, cpu = run_reads_workload(E, target, reads, args.steps, args.warmup, args.e2e_steps, flush_l2, barrier,
                                                 want_cpu=(cores if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None),
                                                 cpu_seconds=args.cpu_seconds)
-    clocks = sampler.stop()
+    all_clocks = sampler.stop() if sampler else {}
+    clocks = all_clocks.get(local_rank)
     elapsed = torch.tensor([sum(rs["step_s"])], dtype=torch.float64, device=dev)
     e2e_t = torch.tensor([sum(ee["times"])], dtype=torch.float64, device=dev)
     if world > 1:
@@ -800,8 +809,8 @@ def main():
                              1000.0 * sum(ee["times"]) / max(args.e2e_steps, 1)], dtype=torch.float64, device=dev)
         allr = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = [{"rank": r, "ms_per_step": float(t[0]), "kernel_ms_per_step": float(t[1]), "e2e_ms_per_step": float(t[2])}
-                    for r, t in enumerate(allr)]
+        per_rank = [{"rank": r, "ms_per_step": float(t[0]), "kernel_ms_per_step": float(t[1]), "e2e_ms_per_step": float(t[2]),
+                     "clocks": all_clocks.get(r)} for r, t in enumerate(allr)]
     elapsed = float(elapsed.item())
     e2e_value = (world * cells_rank * args.e2e_steps / float(e2e_t.item()) / 1e9) if args.e2e_steps > 0 else None
 
@@ -822,6 +831,8 @@ def main():
                        "inputs": "the read array lives in pinned host memory (torch pin_memory) on the GPU's NUMA node (node %d); "
                                  "end-to-end calls upload it from there (no staging copy); results are malloc'd arrays per read "
                                  "as in the reference" % E.numa_node,
+                       "host_allocator": "glibc told to keep freed memory (edlibB200TuneHostAllocator: mallopt M_TRIM_THRESHOLD / "
+                                         "M_TOP_PAD): %s" % E.allocator_tuned,
                        "l2": "256 MiB write between steps (reads 150 MB > L2; the target is meant to stay L2-resident)",
                        "parallelism": "reads sharded over %d rank(s); target broadcast once" % world,
                        "index": "the seed index of the target is rebuilt inside every timed step (no target handle)"},

@@ -3,6 +3,7 @@
 // re-entrant and is called with the GIL released, ref bindings/python/edlib.pyx:128-129), and
 // the two pure-host helpers that carry no DP work (config constructors, CIGAR run-length
 // encoding, free).
+#include <malloc.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -32,6 +33,22 @@ eb::Engine* g_engine = nullptr;
 std::string g_initError;
 bool g_initTried = false;
 
+// Small calls (single edlibAlign calls, batches of a few pairs) do not queue behind each other or behind a large batch:
+// beside the main engine (large batches, the staged API, target handles; under g_mu) a few more engines, each with
+// its own streams, scratch and lock, take them round robin -- concurrent callers (the reference's Python binding
+// releases the GIL around edlibAlign, bindings/python/edlib.pyx:128-129) overlap their launches and copies.
+struct SideEngine {
+    std::mutex mu;
+    eb::Backend* be = nullptr;
+    eb::Engine* eng = nullptr;
+};
+constexpr int kMaxSide = 8;
+SideEngine g_side[kMaxSide];
+int g_numSide = -1;  // -1: not decided yet
+std::atomic<unsigned> g_nextSide{0};
+constexpr int kSmallBatch = 256;  // pairs; larger batches fill the device on their own and use the main engine
+thread_local eb::Engine* t_lastEngine = nullptr;  // engine the calling thread used last (LastError / LastStats)
+
 eb::Engine* engine_locked() {
     if (!g_initTried) {
         g_initTried = true;
@@ -48,6 +65,37 @@ eb::Engine* engine_locked() {
         }
     }
     return g_engine;
+}
+
+// A side engine for a small call, locked (nullptr: none configured / the device is unusable: use the main engine).
+SideEngine* side_engine_acquire() {
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (!engine_locked()) return nullptr;
+        if (g_numSide < 0) {
+            const char* e = getenv("EDLIB_B200_ENGINES");
+            g_numSide = std::max(0, std::min(kMaxSide, e && *e ? atoi(e) - 1 : 3));
+        }
+    }
+    if (g_numSide <= 0) return nullptr;
+    SideEngine* s = &g_side[g_nextSide.fetch_add(1, std::memory_order_relaxed) % (unsigned)g_numSide];
+    s->mu.lock();
+    if (!s->eng) {
+        std::string err;
+        s->be = eb::create_backend(&err);
+        if (s->be) s->eng = new eb::Engine(s->be);
+        if (!s->eng) {
+            s->mu.unlock();
+            return nullptr;
+        }
+    }
+    try {
+        s->be->bind_thread();
+    } catch (...) {
+        s->mu.unlock();
+        return nullptr;
+    }
+    return s;
 }
 
 void fail_results(EdlibAlignResult* results, int n) {
@@ -93,13 +141,22 @@ EDLIB_API int edlibAlignBatch(const char* const* queries, const int* queryLength
     if (numPairs < 0 || (numPairs > 0 && (!queries || !queryLengths || !targets || !targetLengths || !results)))
         return EDLIB_STATUS_ERROR;
     if (numPairs == 0) return EDLIB_STATUS_OK;
+    eb::BatchInput in{queries, queryLengths, targets, targetLengths, numPairs, config};
+    if (numPairs <= kSmallBatch) {
+        if (SideEngine* s = side_engine_acquire()) {
+            t_lastEngine = s->eng;
+            const int rc = s->eng->align_batch(in, results);
+            s->mu.unlock();
+            return rc;
+        }
+    }
     std::lock_guard<std::mutex> lock(g_mu);
     eb::Engine* e = engine_locked();
     if (!e) {  // no usable device: fail loudly, there is no CPU path
         fail_results(results, numPairs);
         return EDLIB_STATUS_ERROR;
     }
-    eb::BatchInput in{queries, queryLengths, targets, targetLengths, numPairs, config};
+    t_lastEngine = e;
     return e->align_batch(in, results);
 }
 
@@ -156,7 +213,8 @@ EDLIB_API const char* edlibB200LastError(void) {
     // every calling thread reads its own copy: a later call on another thread cannot change it under the reader
     static thread_local std::string copy;
     std::lock_guard<std::mutex> lock(g_mu);
-    copy = g_engine ? g_engine->lastError : g_initError;
+    eb::Engine* e = t_lastEngine ? t_lastEngine : g_engine;  // (a side engine is only written by calls of its own users)
+    copy = e ? e->lastError : g_initError;
     return copy.c_str();
 }
 
@@ -172,15 +230,36 @@ EDLIB_API int edlibB200DeviceNumaNode(void) {
     return engine_locked() ? g_backend->numa_node() : -1;
 }
 
+EDLIB_API int edlibB200TuneHostAllocator(void) {
+#if defined(__GLIBC__)
+    const int a = mallopt(M_TRIM_THRESHOLD, 1 << 30);  // freed heap memory stays with the allocator
+    const int b = mallopt(M_TOP_PAD, 64 << 20);        // heaps grow in large steps
+    return (a && b) ? EDLIB_STATUS_OK : EDLIB_STATUS_ERROR;
+#else
+    return EDLIB_STATUS_ERROR;
+#endif
+}
+
+// Large result sets are freed on the host pool, the way they were built: glibc re-serves chunks that ONE thread freed
+// (cold in every other core's cache, threaded through its bins one by one) several times slower than chunks the worker
+// threads freed themselves -- measured 17 ns vs 4 ns per malloc with eight threads (profiles/README.md).
 EDLIB_API void edlibB200FreeResults(EdlibAlignResult* results, int n) {
-    if (!results) return;
-    for (int i = 0; i < n; ++i) {
-        free(results[i].endLocations);
-        free(results[i].startLocations);
-        free(results[i].alignment);
-        results[i].endLocations = results[i].startLocations = NULL;
-        results[i].alignment = NULL;
+    if (!results || n <= 0) return;
+    auto free_range = [results](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            free(results[i].endLocations);
+            free(results[i].startLocations);
+            free(results[i].alignment);
+            results[i].endLocations = results[i].startLocations = NULL;
+            results[i].alignment = NULL;
+        }
+    };
+    if (n < 65536) {
+        free_range(0, (size_t)n);
+        return;
     }
+    std::lock_guard<std::mutex> lock(g_mu);  // the host pool serves one client at a time
+    eb::host_parallel_ranges((size_t)n, 16384, free_range);
 }
 
 EDLIB_API int edlibB200Available(void) {

@@ -70,6 +70,7 @@ public:
     // until end()); end() waits for them, the caller taking part in what is still unclaimed if `participate`.
     // Between the two the caller must not use the pool.  With no workers the tasks run inside end().
     void begin(size_t n, const std::function<void(size_t)>& fn) {
+        client_.lock();  // one client at a time (several engines share the pool); released by end()
         {
             std::lock_guard<std::mutex> lock(mu_);
             fn_ = &fn;
@@ -90,6 +91,7 @@ public:
             err = error_;
             error_ = nullptr;
         }
+        client_.unlock();
         if (err) std::rethrow_exception(err);  // the first exception a task threw, on the caller's thread
     }
 
@@ -165,6 +167,7 @@ private:
     }
     static void bind_worker();  // eb_engine.cpp (sched_setaffinity to worker_cpus(), ignored when not permitted)
     size_t workers_ = 0;
+    std::mutex client_;
     std::mutex mu_;
     std::condition_variable cv_, done_;
     const std::function<void(size_t)>* fn_ = nullptr;

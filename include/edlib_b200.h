@@ -47,6 +47,13 @@ EDLIB_API int edlibB200SetDevice(int device);
  * when they live on that node (page-locked buffers are read by the device directly). */
 EDLIB_API int edlibB200DeviceNumaNode(void);
 
+/* Optional, for callers that receive millions of results per call: every result owns malloc'd arrays (the reference's
+ * ownership rule), and glibc by default hands freed heap memory back to the kernel, so each batch pays the page faults
+ * of tens of megabytes of fresh heap again -- serialised across the threads that build the results.  This call tells the
+ * allocator to keep freed memory (mallopt M_TRIM_THRESHOLD / M_TOP_PAD); it changes nothing but the process's resident
+ * set.  Returns EDLIB_STATUS_OK when the allocator took the settings. */
+EDLIB_API int edlibB200TuneHostAllocator(void);
+
 /* free() the arrays of `n` results at once (same effect as n edlibFreeAlignResult calls). */
 EDLIB_API void edlibB200FreeResults(EdlibAlignResult* results, int n);
 
