@@ -273,6 +273,7 @@ EDLIB_API EdlibB200Batch* edlibB200BatchPrepare(const char* const* queries, cons
     std::lock_guard<std::mutex> lock(g_mu);
     eb::Engine* e = engine_locked();
     if (!e || numPairs <= 0) return NULL;
+    t_lastEngine = e;
     try {
         eb::BatchInput in{queries, queryLengths, targets, targetLengths, numPairs, config};
         return reinterpret_cast<EdlibB200Batch*>(e->prepare(in));
@@ -286,6 +287,7 @@ EDLIB_API int edlibB200BatchCompute(EdlibB200Batch* batch, EdlibB200Stats* stats
     std::lock_guard<std::mutex> lock(g_mu);
     eb::Engine* e = engine_locked();
     if (!e || !batch) return EDLIB_STATUS_ERROR;
+    t_lastEngine = e;
     try {
         e->stats = eb::EngineStats();
         e->compute(reinterpret_cast<eb::Prepared*>(batch));
@@ -313,6 +315,7 @@ EDLIB_API int edlibB200BatchResults(EdlibB200Batch* batch, EdlibAlignResult* res
     std::lock_guard<std::mutex> lock(g_mu);
     eb::Engine* e = engine_locked();
     if (!e || !batch || !results) return EDLIB_STATUS_ERROR;
+    t_lastEngine = e;
     try {
         e->materialize(reinterpret_cast<eb::Prepared*>(batch), results);
     } catch (const std::exception& ex) {
@@ -331,6 +334,7 @@ EDLIB_API EdlibB200Target* edlibB200TargetPrepare(const char* target, int target
     std::lock_guard<std::mutex> lock(g_mu);
     eb::Engine* e = engine_locked();
     if (!e) return NULL;
+    t_lastEngine = e;
     try {
         return reinterpret_cast<EdlibB200Target*>(e->target_prepare(target, targetLength));
     } catch (const std::exception& ex) {
@@ -370,24 +374,26 @@ EDLIB_API void edlibB200LastStats(EdlibB200Stats* s) {
     if (!s) return;
     memset(s, 0, sizeof(*s));
     if (!g_engine || !engine_locked()) return;
-    g_engine->finish_stats();
-    s->kernelMs = g_engine->stats.kernelMs;
-    s->k1Ms = g_engine->stats.k1Ms;
-    s->launches = g_engine->stats.launches;
-    s->h2dBytes = g_engine->stats.h2dBytes;
-    s->d2hBytes = g_engine->stats.d2hBytes;
-    s->k1Cells = g_engine->stats.k1Cells;
-    s->wCells = g_engine->stats.wCells;
-    s->filterDecided = g_engine->stats.filterDecided;
-    s->filterFallback = g_engine->stats.filterFallback;
-    s->filterWindows = (int)std::min<long long>(g_engine->stats.filterWindows, 0x7fffffff);
+    eb::Engine* e = t_lastEngine ? t_lastEngine : g_engine;  // the engine this thread's last call ran on
+    e->finish_stats();
+    s->kernelMs = e->stats.kernelMs;
+    s->k1Ms = e->stats.k1Ms;
+    s->launches = e->stats.launches;
+    s->h2dBytes = e->stats.h2dBytes;
+    s->d2hBytes = e->stats.d2hBytes;
+    s->k1Cells = e->stats.k1Cells;
+    s->wCells = e->stats.wCells;
+    s->filterDecided = e->stats.filterDecided;
+    s->filterFallback = e->stats.filterFallback;
+    s->filterWindows = (int)std::min<long long>(e->stats.filterWindows, 0x7fffffff);
 }
 
 EDLIB_API int edlibB200LastKernelReport(char* buf, int bufLen) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!buf || bufLen <= 0) return 0;
-    if (g_engine && engine_locked()) g_engine->finish_stats();
-    const std::string r = g_engine ? g_engine->stats.kernelReport : std::string();
+    eb::Engine* e = t_lastEngine ? t_lastEngine : g_engine;
+    if (e && engine_locked()) e->finish_stats();
+    const std::string r = e ? e->stats.kernelReport : std::string();
     const int n = (int)std::min<size_t>(r.size(), (size_t)bufLen - 1);
     memcpy(buf, r.data(), (size_t)n);
     buf[n] = 0;

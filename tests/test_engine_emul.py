@@ -436,6 +436,25 @@ def test_staged_api_misuse_is_an_error_not_a_crash(emul):
     del keep
 
 
+def test_concurrent_small_calls_and_a_large_batch(emul):
+    """Single calls from several threads go to the side engines (round robin, each behind its own lock) while a large
+    batch runs on the main engine; every result still equals the reference's."""
+    import random
+    from concurrent.futures import ThreadPoolExecutor
+    from helpers import mutate, rand_seq
+    chk = parity.checker()
+    rng = random.Random(6)
+    t = rand_seq(rng, 2500, b"ACGT")
+    qs = [mutate(rng, t[a:a + 100], 0.05, b"ACGT") for a in range(0, 2000, 50)]
+    big_q = [mutate(rng, t[a % 2300:a % 2300 + 150], 0.03, b"ACGT") for a in range(0, 9000, 7)]
+    with ThreadPoolExecutor(7) as ex:
+        fb = ex.submit(lambda: emul.align_batch(big_q, [t] * len(big_q), -1, 2, 1))
+        got = list(ex.map(lambda q: emul.align(q, t, -1, 2, 2), qs * 3))
+        st, res = fb.result()
+    assert st == 0 and res[::31] == [chk.align(q, t, -1, 2, 1) for q in big_q[::31]]
+    assert got == [chk.align(q, t, -1, 2, 2) for q in qs] * 3
+
+
 def test_many_end_locations(emul):
     """Repeats: every column is an end location (ref runTests-style 'A*64 vs B*70' shapes)."""
     chk = parity.checker()

@@ -155,6 +155,14 @@ def test_concurrent_callers(lib):
     with ThreadPoolExecutor(8) as ex:
         got = list(ex.map(lambda q: lib.align(q, t, -1, 2, 1), qs * 3))
     assert got == exp * 3
+    # small calls run on side engines (own streams and locks) while a large batch holds the main engine
+    big_q = [mutate(rng, t[a % 2800:a % 2800 + 150], 0.03, b"ACGT") for a in range(0, 40000, 7)]
+    with ThreadPoolExecutor(9) as ex:
+        fb = ex.submit(lambda: lib.align_batch(big_q, [t] * len(big_q), -1, 2, 0))
+        got = list(ex.map(lambda q: lib.align(q, t, -1, 2, 2), qs * 4))
+        st, res = fb.result()
+    assert st == 0 and res[::97] == [chk.align(q, t, -1, 2, 0) for q in big_q[::97]]
+    assert got == [chk.align(q, t, -1, 2, 2) for q in qs] * 4
 
 
 def test_results_do_not_depend_on_the_plan():
