@@ -838,7 +838,7 @@ def main():
                        "index": "the seed index of the target is rebuilt inside every timed step (no target handle)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": ee["h2d"], "d2h_bytes_per_step": ee["d2h"],
-                    "ms_per_step": 1000.0 * float(e2e_t.item()) / max(args.e2e_steps, 1)},
+                    "ms_per_step": 1000.0 * float(e2e_t.item()) / max(args.e2e_steps, 1), "kernel_ms_last_step": ee["kernel_ms"]},
             "gpu_launches": int(rs["launches"]),
             "roofline": reads_roofline(rs, n_reads, t_len, float(nloc.sum()), sm_mhz, peak, peak_src),
             "cpu_baseline": cpu,
