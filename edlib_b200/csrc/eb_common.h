@@ -251,7 +251,7 @@ struct SeedIndexParams {
 };
 // candidate end columns per read before the read is passed on as saturated, per seed level (shorter seeds
 // have more chance occurrences); the planning kernel is instantiated per capacity
-#define SEED_LEVELS 3
+#define SEED_LEVELS 4
 #define SEED_CAND_0 256
 #define SEED_CAND_1 256
 #define SEED_CAND_2 4096

@@ -117,9 +117,9 @@ struct EngineTunables {
     int longHwMinTarget = 65536;  // HW, query > 256 rows: shortest target worth seeds / chunking (and >= 8 query lengths)
     int longSeedMaxK = 1024;      // ... largest seed threshold tried (thresholds double from 64, capped by the seeds that fit the query)
     int windowCheckAfter = 48;    // banded window sweeps: see K1WParams::checkAfter (-1 disables the early exit)
-    int filterSeedK = 16;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
+    int filterSeedK = 20;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 128;   // seed stage: longest index range looked at, level 0: twice this; x8 per level (longer: repeat, read passed on)
-    int filterSeedLevels = 3;     // seed stage: levels tried (seed length L, L-2, L-4 for DNA; at most SEED_LEVELS)
+    int filterSeedLevels = 4;     // seed stage: levels tried (seed length L, L-2, L-4, L-5 for DNA; at most SEED_LEVELS)
     int filterSeedSlack = 4;      // seed stage: seed length L is the shortest with sigma^L >= slack * target length
     int filterK1 = 8;
     int filterK0 = 16;
@@ -151,7 +151,7 @@ struct EngineStats {
 struct EngineScratch {
     std::vector<int> best, cnt, posLen, posPool;
     std::vector<long long> posStart;
-    int seedWindowsPerRead[SEED_LEVELS] = {0, 0, 0};  // seed stages: windows per read the previous pass produced
+    int seedWindowsPerRead[SEED_LEVELS] = {0, 0, 0, 0};  // seed stages: windows per read the previous pass produced
     std::vector<int> targetTable;  // prepare(): open-addressing table of the distinct targets
 };
 

@@ -429,7 +429,7 @@ struct SeedIndex {
     int target = -1;
     bool ok = false;
     int Lidx = 0, sigma = 0, numKeys = 0, n = 0;
-    int Ls[SEED_LEVELS] = {0, 0, 0};  // seed length per level (0: level not available)
+    int Ls[SEED_LEVELS] = {0, 0, 0, 0};  // seed length per level (0: level not available)
     DevBuf<int> bucketStart, positions;
 };
 

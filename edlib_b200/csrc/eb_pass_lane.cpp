@@ -51,9 +51,11 @@ bool build_seed_index(Backend* be, const EngineTunables& tun, SeedIndex& sx, con
         ++L0;
     }
     if (n < 4 * L0) return false;
+    // seed lengths of the levels: small alphabets step by two symbols, then by one (every symbol less multiplies the
+    // chance occurrences by sigma: the last level of a DNA target sees ~70 per seed)
     const int step = (sigma * sigma <= 32) ? 2 : 1;
     for (int level = 0; level < SEED_LEVELS; ++level) {
-        const int L = L0 - step * level;
+        const int L = level < 3 ? L0 - step * level : L0 - step * 2 - (level - 2);
         // shorter than 4 symbols, or more than ~128 chance occurrences per seed: the level selects nothing
         const bool useful = L >= 4 && (level == 0 || (double)n / std::pow((double)sigma, L) <= 128.0);
         sx.Ls[level] = useful ? L : 0;
@@ -323,7 +325,7 @@ void Pass::seed_stage(LaneGroup& c, int level, const std::vector<int>& in, std::
     DevBuf<int> wPair, wK, wStart, wLen, wTf;
     // room for the window jobs: sized from what the previous pass of this level needed per read
     int& perRead = eng.scratch.seedWindowsPerRead[level];
-    int cap = (int)std::min<long long>((long long)g * std::max(perRead + 2, level == 0 ? 8 : level == 1 ? 96 : 400) + 4096, 1LL << 28), V = 0;
+    int cap = (int)std::min<long long>((long long)g * std::max(perRead + 2, level == 0 ? 8 : level == 1 ? 96 : level == 2 ? 400 : 1500) + 4096, 1LL << 28), V = 0;
     for (;;) {
         wPair.alloc(be, cap);
         wK.alloc(be, cap);
