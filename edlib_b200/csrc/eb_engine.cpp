@@ -87,6 +87,7 @@ EngineTunables::EngineTunables() {
     filterSeedK = env_int("EDLIB_B200_FILTER_SEED_K", filterSeedK);
     filterSeedBucket = env_int("EDLIB_B200_FILTER_SEED_BUCKET", filterSeedBucket);
     filterSeedSlack = env_int("EDLIB_B200_FILTER_SEED_SLACK", filterSeedSlack);
+    filterMinLevelReads = env_int("EDLIB_B200_FILTER_MIN_LEVEL_READS", filterMinLevelReads);
     filterSeedLevels = std::min(SEED_LEVELS, env_int("EDLIB_B200_FILTER_SEED_LEVELS", filterSeedLevels));
     filterMaxWindows = env_int("EDLIB_B200_FILTER_MAX_WINDOWS", filterMaxWindows);
     filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
@@ -96,6 +97,7 @@ EngineTunables::EngineTunables() {
     bandKernel = env_int("EDLIB_B200_BAND_KERNEL", bandKernel);
     collapseEqualities = env_int("EDLIB_B200_COLLAPSE_EQUALITIES", collapseEqualities);
     directUpload = env_int("EDLIB_B200_DIRECT_UPLOAD", directUpload);
+    streamSlices = std::max(1, env_int("EDLIB_B200_STREAM_SLICES", streamSlices));
     directMinBytes = (size_t)env_int("EDLIB_B200_DIRECT_MIN_KB", (int)(directMinBytes >> 10)) << 10;
     deviceStage = env_int("EDLIB_B200_DEVICE_STAGE", deviceStage);
     windowCheckAfter = env_int("EDLIB_B200_WINDOW_CHECK", windowCheckAfter);
@@ -1006,7 +1008,7 @@ bool Engine::align_streamed(const BatchInput& in, EdlibAlignResult* results) {
 
         // slices of reads; every slice is packed by all workers together (parts), so that slice 0 is on its way first
         // at least eight slices for big batches: the result structs of the last slice are the tail of the call
-        const int sliceReads = std::min(tun.devSliceReads, std::max(4096, ceil_div(N, N >= 262144 ? 8 : 4)));
+        const int sliceReads = std::min(tun.devSliceReads, std::max(4096, ceil_div(N, N >= 262144 ? tun.streamSlices : 4)));
         const int numSlices = ceil_div(N, sliceReads);
         const size_t W = HostPool::get().width();
         const size_t workers = W > 1 ? W - 1 : 0;  // the caller orchestrates

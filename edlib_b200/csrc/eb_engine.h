@@ -113,6 +113,7 @@ struct EngineTunables {
     // ranges are swept with the whole read; reads no stage decides take the plain full sweep.
     int deviceStage = 1;          // first seed level driven by the device (0: every stage host-driven)
     int devSliceReads = 1 << 20;  // reads per slice of the device-driven level (streamed batches: at least four slices)
+    int streamSlices = 8;         // slices of a big streamed batch (the result structs of the last slice are the tail of the call)
     int streamMinPairs = 32768;   // smallest one-target HW batch that edlibAlignBatch streams (upload under compute)
     int longHwMinTarget = 65536;  // HW, query > 256 rows: shortest target worth seeds / chunking (and >= 8 query lengths)
     int longSeedMaxK = 1024;      // ... largest seed threshold tried (thresholds double from 64, capped by the seeds that fit the query)
@@ -120,6 +121,7 @@ struct EngineTunables {
     int filterSeedK = 20;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 128;   // seed stage: longest index range looked at, level 0: twice this; x8 per level (longer: repeat, read passed on)
     int filterSeedLevels = 4;     // seed stage: levels tried (seed length L, L-2, L-4, L-5 for DNA; at most SEED_LEVELS)
+    int filterMinLevelReads = 64; // seed levels 2 and later: fewest undecided reads worth the level (else: plain sweep)
     int filterSeedSlack = 4;      // seed stage: seed length L is the shortest with sigma^L >= slack * target length
     int filterK1 = 8;
     int filterK0 = 16;

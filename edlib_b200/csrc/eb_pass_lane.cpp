@@ -758,6 +758,9 @@ void Pass::lane_group(int t, int nw, const std::vector<int>& list, const std::ve
     if (filtered) {
         trace.mark("lane group: bounds");
         for (int level = firstSeedLevel; level < tun.filterSeedLevels && tun.filterSeedK > 0 && !p->hasEq && !cur.empty(); ++level) {
+            // a late level costs about a millisecond whatever it is given (a few reads with thousands of candidates
+            // each: one planning group, one reduction thread per read); the plain sweep of a read costs ~15 us
+            if (level >= 2 && (int)cur.size() < tun.filterMinLevelReads) break;
             std::vector<int> next;
             seed_stage(c, level, cur, next);
             cur.swap(next);

@@ -103,7 +103,7 @@ def test_candidate_filter_all_branches():
                    "EDLIB_B200_FILTER_SEED_LEVELS": "3", "EDLIB_B200_FILTER_SEED_SLACK": "100000"},
                   {"EDLIB_B200_DEVICE_STAGE": "0"},                                   # every stage host-driven
                   {"EDLIB_B200_SLICE_READS": "64", "EDLIB_B200_FILTER_SEED_LEVELS": "1"}):  # many slices, one seed level
-        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 500
 
@@ -121,7 +121,7 @@ def test_reads_that_tie_on_many_end_columns():
     for extra in ({"EDLIB_B200_STREAM_MIN_PAIRS": "8"}, {"EDLIB_B200_DEVICE_STAGE": "0"},
                   {"EDLIB_B200_FILTER_SEED_K": "0", "EDLIB_B200_FILTER_K1": "12"},
                   {"EDLIB_B200_STREAM_MIN_PAIRS": "8", "EDLIB_B200_SLICE_READS": "64", "EDLIB_B200_FILTER_SEED_BUCKET": "4096"}):
-        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", **extra)
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 300
 
@@ -140,7 +140,7 @@ def test_start_locations_and_paths_driven_from_the_device():
     ) % (REPO, os.path.join(REPO, "tests"))
     for extra, want in (({}, True), ({"EDLIB_B200_SLICE_MB": "1", "EDLIB_B200_K1_MIN_GROUP": "4"}, True),
                         ({"EDLIB_B200_DEVICE_RESULTS": "0"}, False)):
-        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_TRACE="1", **extra)
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_TRACE="1", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 2500
         assert ("device-driven lane sweeps" in out.stderr) == want and ("device-driven leaf sweeps" in out.stderr) == want
@@ -156,7 +156,7 @@ def test_read_sets_with_additional_equalities():
         "print(parity.run_batches(lib, 91, 9, gen=cases.equality_read_cases))\n"
     ) % (REPO, os.path.join(REPO, "tests"))
     for extra, seeds in (({}, True), ({"EDLIB_B200_COLLAPSE_EQUALITIES": "0"}, False)):
-        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_K1_MIN_GROUP="4", EDLIB_B200_TRACE="1", **extra)
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_K1_MIN_GROUP="4", EDLIB_B200_TRACE="1", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 300
         assert ("filter seed stage" in out.stderr or "device stage" in out.stderr) == seeds
@@ -207,7 +207,7 @@ def test_queries_in_one_pinned_block_are_uploaded_directly():
         .replace("ALLOC", "(lambda shape: np.zeros(shape, dtype=np.uint8))")
     for extra in ({"EDLIB_EMUL_PINNED": "1"}, {"EDLIB_EMUL_PINNED": "1", "EDLIB_B200_PACK_PARALLEL_KB": "16", "EDLIB_B200_HOST_THREADS": "4"},
                   {"EDLIB_EMUL_PINNED": "1", "EDLIB_B200_DIRECT_UPLOAD": "0"}):
-        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_DIRECT_MIN_KB="1", **extra)
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_DIRECT_MIN_KB="1", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) == 1200
 
@@ -254,7 +254,7 @@ def test_target_handle():
     """edlibB200TargetPrepare: batches against a target kept resident (encoded bytes + seed index reused) give what
     the same call gives without a handle, handle after handle."""
     code = (TARGET_HANDLE_CODE % (REPO, os.path.join(REPO, "tests"))).replace("LOAD", "__import__('test_engine_emul').load_emul()")
-    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_TRACE="1")
+    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_STREAM_MIN_PAIRS="8", EDLIB_B200_TRACE="1")
     out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
     assert int(out.stdout.strip().splitlines()[-1]) > 500
     assert "stream: slices enqueued" in out.stderr
@@ -290,7 +290,7 @@ def test_long_queries_hw_over_long_targets():
         "print(parity.run_batches(lib, 41, 9, gen=cases.long_hw_cases))\n"
     ) % (REPO, os.path.join(REPO, "tests"))
     for extra in ({}, {"EDLIB_B200_LONG_SEED_MAX_K": "0"}, {"EDLIB_B200_LONG_SEED_MAX_K": "70", "EDLIB_B200_FILTER_SEED_BUCKET": "1"}):
-        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_LONG_HW_MIN_TARGET="2000", **extra)
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_LONG_HW_MIN_TARGET="2000", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) >= 27
 
@@ -304,7 +304,7 @@ def test_large_batch_uses_the_threaded_host_paths():
         "lib = T.load_emul()\n"
         "print(parity.run_batches(lib, 3, 1, gen=lambda seed, count: [cases.big_batch_case(seed)]))\n"
     ) % (REPO, os.path.join(REPO, "tests"))
-    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_PACK_PARALLEL_KB="1024")
+    env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_PACK_PARALLEL_KB="1024")
     out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
     assert int(out.stdout.strip().splitlines()[-1]) == 140000
 
