@@ -549,7 +549,7 @@ def config3(E, genome, pairs, steps, cores, cpu_seconds, peak, peak_src, barrier
             "fraction_within_k": within, "mean_edit_distance": mean_ed}
 
 
-def config4(E, target, reads, steps, cores, cpu_seconds, barrier):
+def config4(E, target, reads, steps, cores, cpu_seconds, barrier, peak=None, peak_src=None):
     """BASELINE configs[3]: the headline batch with EDLIB_TASK_PATH, plus the extended CIGAR of every alignment."""
     n = reads.shape[0]
     ptrs = pointer_arrays(reads, target)
@@ -583,6 +583,8 @@ def config4(E, target, reads, steps, cores, cpu_seconds, barrier):
     cig = [C.string_at(cg[i]).decode("ascii") if cg[i] else None for i in range(len(cs["results"]))]
     checked = check_sample(res, cs["results"], "config 4", cigars=cig)
     mean_aln = float(res["alignmentLength"].mean())
+    nloc_sum = float(res["numLocations"].sum())
+    aln_sum = float(res["alignmentLength"].sum())
     E.free_cigars(cg)
     E.free(res)
     t = float(np.mean(times))
@@ -592,9 +594,28 @@ def config4(E, target, reads, steps, cores, cpu_seconds, barrier):
             "e2e": {"gcups": cells / t / 1e9, "alignments_per_s": n / t, "ms_per_batch": 1000 * t,
                     "cigar_ms": 1000 * float(np.mean(cigar_times)), "h2d_bytes": int(st.h2dBytes), "d2h_bytes": int(st.d2hBytes)},
             "kernel_ms": float(st.kernelMs), "kernels_ms": kernels_ms,
+            "roofline": config4_roofline(kernels_ms, n, len(target), nloc_sum, aln_sum, float(st.kernelMs), peak, peak_src),
             "cpu_baseline": {"alignments_per_s": cs["alignments_per_s"], "gcups": cs["gcups"], "cores": cores, "kind": cs["kind"],
                              "sample": "first %d reads, %.1f s wall; every result field and the CIGAR bit-exact vs the GPU" % (checked, cs["wall"])},
             "mean_alignment_length": mean_aln}
+
+
+def config4_roofline(kernels_ms, n, target_len, nloc_sum, aln_sum, kernel_ms, peak, peak_src):
+    """Dominant kernel of the PATH batch against the HBM peak: SURVEY.md 8d's algorithmic bytes (query + whole target +
+    distance / counts + 8 B per location + the edit script, per alignment) over its device time, beside the bytes the
+    PATH phase must really move (stored matrices of the banded slices: written once, read once by the traceback)."""
+    if not kernels_ms or not peak:
+        return None
+    dom = next(iter(kernels_ms))
+    dom_s = kernels_ms[dom] / 1e3
+    bytes_alg = float(n) * (READ_LEN + target_len + 8) + 8.0 * nloc_sum + aln_sum
+    stored = float(n) * (READ_LEN + 10) * 5 * 8  # {Pv, Ph} per column and word of a ~160-column slice, 5 words
+    return {"bound": "hbm", "kernel": dom, "kernel_ms": kernels_ms[dom], "bytes_algorithmic": bytes_alg,
+            "achieved": bytes_alg / dom_s / 1e9 if dom_s > 0 else None, "peak": peak, "unit": "GB/s",
+            "frac": bytes_alg / dom_s / 1e9 / peak if dom_s > 0 else None, "peak_source": peak_src,
+            "stored_matrix_bytes": stored, "all_kernels_ms": kernel_ms,
+            "note": "nominal accounting as in the headline (every alignment 'consumes' its whole target); the PATH phase itself "
+                    "writes and re-reads ~%.1f GB of stored matrices, which bounds its lane / traceback kernels" % (stored / 1e9)}
 
 
 def long_hw(E, genome, cores):
@@ -908,7 +929,7 @@ def main():
         guarded("other_target", synthetic)
         guarded("sensitivity", lambda: sensitivity(E, target, reads, flush_l2, barrier))
         guarded("long_hw", lambda: long_hw(E, target if args.target == "ecoli" else workloads.ecoli_genome(), cores))
-        guarded("config4", lambda: config4(E, target, reads, 2, cores, 10.0, barrier))
+        guarded("config4", lambda: config4(E, target, reads, 2, cores, 10.0, barrier, peak, peak_src))
         del reads
         genome = target if args.target == "ecoli" else workloads.ecoli_genome()
         guarded("config3", lambda: config3(E, genome, args.config3_pairs, 2, cores, 10.0, peak, peak_src, barrier))
