@@ -54,5 +54,6 @@ if has h2d; then echo "== h2d microbenchmark"; ./scripts/microbench/h2d 2048 2>&
 if has ref; then echo "== bench --impl reference"; timeout 900 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; cut -c1-400 $OUT/bench_ref_$TAG.json; fi
 if has stress; then
   echo "== stress (filter forced on for small targets)"
-  EDLIB_B200_FILTER_MIN_TARGET=128 EDLIB_B200_K1_MIN_GROUP=4 EDLIB_B200_STREAM_MIN_PAIRS=64 timeout 900 python scripts/stress.py ${STRESS_MIN:-3} 2>&1 | tail -2 | tee $OUT/stress_$TAG.txt
+  EDLIB_B200_FILTER_MIN_TARGET=128 EDLIB_B200_FILTER_MIN_LEVEL_READS=0 EDLIB_B200_K1_MIN_GROUP=4 EDLIB_B200_STREAM_MIN_PAIRS=64 EDLIB_B200_LONG_HW_MIN_TARGET=2000 \
+      timeout 900 python scripts/stress.py ${STRESS_MIN:-3} 2>&1 | tail -2 | tee $OUT/stress_$TAG.txt
 fi
