@@ -88,6 +88,7 @@ EngineTunables::EngineTunables() {
     filterSeedBucket = env_int("EDLIB_B200_FILTER_SEED_BUCKET", filterSeedBucket);
     filterSeedSlack = env_int("EDLIB_B200_FILTER_SEED_SLACK", filterSeedSlack);
     filterMinLevelReads = env_int("EDLIB_B200_FILTER_MIN_LEVEL_READS", filterMinLevelReads);
+    tinySweepReads = env_int("EDLIB_B200_TINY_SWEEP_READS", tinySweepReads);
     filterSeedLevels = std::min(SEED_LEVELS, env_int("EDLIB_B200_FILTER_SEED_LEVELS", filterSeedLevels));
     filterMaxWindows = env_int("EDLIB_B200_FILTER_MAX_WINDOWS", filterMaxWindows);
     filterMinLen = env_int("EDLIB_B200_FILTER_MIN_LEN", filterMinLen);
