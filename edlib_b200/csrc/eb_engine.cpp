@@ -546,7 +546,6 @@ void Engine::compute(Prepared* p) {
     Backend* be = be_;
     p->computed = false;
     be->reset_timing();
-    const int N = p->N;
     const int mode = p->mode;
     reset_results(p);
     stats.k1Cells = stats.wCells = 0;
