@@ -660,7 +660,10 @@ EB_HD void k1b_sweep(const WAcc& acc, const uint8_t* tsyms, int ws, int m, int o
     for (; j <= hi && (j & 15); ++j) b.template column<true>(j, tsyms[j]);  // up to the next multiple of 16
     if (j + 15 <= hi) {
         Sym16 v = load_sym16(tsyms + j);
-        bool checked = checkAfter < 0;
+        // (t == 0: the one alignment of interest runs along the window's TOP diagonal, whose cell of the column just
+        // swept is not part of the frame window_min() looks at -- the cell below it costs 1 > t, so the test would
+        // discard an exact occurrence; with t >= 1 that neighbour is within t whenever the path still can be)
+        bool checked = checkAfter < 0 || t == 0;
         for (; j + 15 < lo; j += 16) {  // lead-in groups: no column of them is tracked
             if (!checked && j >= dhi + checkAfter) {
                 checked = true;

@@ -22,7 +22,7 @@ plan = [("single", cases.single_pair_cases, 400, parity.run_single), ("batch", c
         ("long", cases.long_cases, 12, parity.run_single), ("path", cases.path_cases, 20, parity.run_single),
         ("stream", cases.stream_cases, 6, parity.run_batches), ("tied_ends", cases.tied_ends_cases, 6, parity.run_batches),
         ("band", cases.band_cases, 6, parity.run_batches), ("long_hw", cases.long_hw_cases, 3, parity.run_batches),
-        ("equalities", cases.equality_read_cases, 6, parity.run_batches)]
+        ("equalities", cases.equality_read_cases, 6, parity.run_batches), ("small_k", cases.small_k_cases, 8, parity.run_batches)]
 counts = {}
 while time.time() - t0 < budget:
     for name, gen, n, runner in plan:

@@ -406,3 +406,29 @@ def equality_read_cases(seed, count):
         if it % 3 == 2:
             eqs += [(b"N", b"A"), (b"N", b"C"), (b"N", b"a"), (b"N", b"c")]
         yield dict(qs=qs, ts=[t] * len(qs), k=rng.choice([-1, -1, 6, 20]), mode=2, task=(it + seed) % 3, eqs=eqs)
+
+
+def small_k_cases(seed, count):
+    """HW read sets with the tightest bounds (k = 0, 1, 2): exact and nearly exact copies of target substrings, so the
+    filter works with thresholds t = 0, 1, 2 -- at t = 0 the only alignment of interest runs along the TOP diagonal of
+    its verification window (regression: the early exit of hopeless windows once discarded exactly those)."""
+    from helpers import mutate, rand_seq
+    rng = random.Random(seed)
+    for it in range(count):
+        alpha = rng.choice([b"ACGT", b"ACGT", b"ACGTN", b"ABCDEFGHIJKLMNOPQRST"])
+        t = rand_seq(rng, rng.randrange(400, 6000), alpha)
+        qs = []
+        for _ in range(rng.randrange(30, 90)):
+            m = rng.choice([20, 33, 64, 100, 148, 150, 200, 256])
+            s = rng.randrange(0, len(t) - m)
+            q = bytearray(t[s:s + m])
+            for _ in range(rng.choice([0, 0, 0, 1, 2, 3])):   # a few single-symbol edits
+                kind, at = rng.randrange(3), rng.randrange(len(q))
+                if kind == 0:
+                    q[at] = rng.choice(alpha)
+                elif kind == 1:
+                    q.insert(at, rng.choice(alpha))
+                elif len(q) > 1:
+                    del q[at]
+            qs.append(bytes(q))
+        yield dict(qs=qs, ts=[t] * len(qs), k=[0, 1, 2, 0][it % 4], mode=2, task=(it + seed) % 3, eqs=None)

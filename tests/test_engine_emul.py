@@ -108,6 +108,23 @@ def test_candidate_filter_all_branches():
         assert int(out.stdout.strip().splitlines()[-1]) > 500
 
 
+def test_tightest_bounds_through_every_filter_path():
+    """k = 0, 1, 2 (thresholds t = 0, 1, 2): exact and nearly exact reads through the device-driven seed level (staged and
+    streamed), the host-driven seed levels, the prefix stages alone and the plain sweep."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 101, 12, gen=cases.small_k_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra in ({}, {"EDLIB_B200_STREAM_MIN_PAIRS": "8"}, {"EDLIB_B200_DEVICE_STAGE": "0"},
+                  {"EDLIB_B200_FILTER_SEED_K": "0"}, {"EDLIB_B200_FILTER_SEED_K": "0", "EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "0"},
+                  {"EDLIB_B200_WINDOW_CHECK": "0"}, {"EDLIB_B200_WINDOW_CHECK": "-1"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_K1_MIN_GROUP="4", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 400
+
+
 def test_reads_that_tie_on_many_end_columns():
     """Homopolymer / tandem stretches: windows with more end columns than a record holds inline (overflow list of the
     window sweeps), through the device-driven first seed level (streamed and staged), the host-driven seed levels and

@@ -72,6 +72,23 @@ def test_banded_nw_of_long_queries_on_the_band_kernel(lib):
     assert parity.run_batches(lib, 61, 24, gen=cases.band_cases) >= 80
 
 
+def test_tightest_bounds_through_every_filter_path():
+    """k = 0, 1, 2: exact and nearly exact reads through the seed levels (device- and host-driven), the prefix stages and
+    the plain sweep, filter forced on for small targets (regression of the t = 0 early exit)."""
+    import subprocess
+    from edlib_b200._ffi import REPO
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases\n"
+        "from helpers import product\n"
+        "print(parity.run_batches(product(), 101, 16, gen=cases.small_k_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    for extra in ({}, {"EDLIB_B200_STREAM_MIN_PAIRS": "8"}, {"EDLIB_B200_DEVICE_STAGE": "0"}, {"EDLIB_B200_FILTER_SEED_K": "0"}):
+        env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_K1_MIN_GROUP="4", **extra)
+        out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 500
+
+
 def test_reads_that_tie_on_many_end_columns():
     """Homopolymer / tandem stretches (overflow list of the window sweeps), filter forced on for small targets: streamed
     device stage, host-driven seed levels, prefix stages alone."""
