@@ -364,12 +364,12 @@ def band_cases(seed, count):
     rng = random.Random(seed)
     for it in range(count):
         alpha = rng.choice([b"ACGT", b"ACGT", b"ACGTN", b"ACDEFGHIKLMNPQRSTVWY"])
-        k = rng.choice([-1, 40, 90, 200, 500, 900])
+        k = rng.choice([-1, 0, 1, 40, 90, 200, 500, 900])
         qs, ts = [], []
         for _ in range(rng.randrange(3, 9)):
             m = rng.choice([2100, 3000, 4097, 6000, 10000, 12000])
             q = rand_seq(rng, m, alpha)
-            t = mutate(rng, q, rng.choice([0.0, 0.005, 0.02, 0.03, 0.06]), alpha)
+            t = mutate(rng, q, rng.choice([0.0, 0.005, 0.02, 0.03, 0.06]) if k > 1 or k < 0 else rng.choice([0.0, 0.0, 0.0002]), alpha)
             shift = rng.choice([0, 0, 0, 17, 150, 400])
             if shift and rng.random() < 0.5:
                 at = rng.randrange(0, len(t))
