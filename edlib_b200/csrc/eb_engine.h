@@ -121,7 +121,8 @@ struct EngineTunables {
     int filterSeedK = 20;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 128;   // seed stage: longest index range looked at, level 0: twice this; x8 per level (longer: repeat, read passed on)
     int filterSeedLevels = 4;     // seed stage: levels tried (seed length L, L-2, L-4, L-5 for DNA; at most SEED_LEVELS)
-    int tinySweepReads = 8;       // plain sweeps of at most this many reads run as (read, chunk) jobs of the per-job lane kernel
+    int tinySweepReads = 0;       // plain sweeps of at most this many reads run as (read, chunk) jobs of the per-job lane kernel
+                                  // (off: the device time it saves, 0.4 ms, is less than the host time its job lists cost)
     int filterMinLevelReads = 64; // seed levels 2 and later: fewest undecided reads worth the level (else: plain sweep)
     int filterSeedSlack = 4;      // seed stage: seed length L is the shortest with sigma^L >= slack * target length
     int filterK1 = 8;

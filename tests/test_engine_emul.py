@@ -102,6 +102,7 @@ def test_candidate_filter_all_branches():
                   {"EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "0", "EDLIB_B200_FILTER_SEED_K": "40",
                    "EDLIB_B200_FILTER_SEED_LEVELS": "3", "EDLIB_B200_FILTER_SEED_SLACK": "100000"},
                   {"EDLIB_B200_DEVICE_STAGE": "0"},                                   # every stage host-driven
+                  {"EDLIB_B200_TINY_SWEEP_READS": "8", "EDLIB_B200_FILTER_SEED_K": "2"},  # few undecided reads: (read, chunk) lane jobs
                   {"EDLIB_B200_SLICE_READS": "64", "EDLIB_B200_FILTER_SEED_LEVELS": "1"}):  # many slices, one seed level
         env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
@@ -119,7 +120,7 @@ def test_tightest_bounds_through_every_filter_path():
     ) % (REPO, os.path.join(REPO, "tests"))
     for extra in ({}, {"EDLIB_B200_STREAM_MIN_PAIRS": "8"}, {"EDLIB_B200_DEVICE_STAGE": "0"},
                   {"EDLIB_B200_FILTER_SEED_K": "0"}, {"EDLIB_B200_FILTER_SEED_K": "0", "EDLIB_B200_FILTER_K0": "0", "EDLIB_B200_FILTER_K1": "0"},
-                  {"EDLIB_B200_WINDOW_CHECK": "0"}, {"EDLIB_B200_WINDOW_CHECK": "-1"}):
+                  {"EDLIB_B200_WINDOW_CHECK": "0"}, {"EDLIB_B200_WINDOW_CHECK": "-1"}, {"EDLIB_B200_TINY_SWEEP_READS": "8"}):
         env = dict(os.environ, EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_K1_MIN_GROUP="4", **extra)
         out = subprocess.run(["python", "-c", code], env=env, check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 400
