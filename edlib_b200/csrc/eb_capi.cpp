@@ -47,7 +47,8 @@ SideEngine g_side[kMaxSide];
 int g_numSide = -1;  // -1: not decided yet
 std::atomic<unsigned> g_nextSide{0};
 constexpr int kSmallBatch = 256;  // pairs; larger batches fill the device on their own and use the main engine
-thread_local eb::Engine* t_lastEngine = nullptr;  // engine the calling thread used last (LastError / LastStats)
+thread_local eb::Engine* t_lastEngine = nullptr;  // engine the calling thread used last (LastStats / LastKernelReport)
+thread_local std::string t_lastError;              // text of the last failure of a call made by this thread
 
 eb::Engine* engine_locked() {
     if (!g_initTried) {
@@ -146,6 +147,7 @@ EDLIB_API int edlibAlignBatch(const char* const* queries, const int* queryLength
         if (SideEngine* s = side_engine_acquire()) {
             t_lastEngine = s->eng;
             const int rc = s->eng->align_batch(in, results);
+            if (rc != EDLIB_STATUS_OK) t_lastError = s->eng->lastError;  // (copied while the engine is still ours)
             s->mu.unlock();
             return rc;
         }
@@ -157,7 +159,9 @@ EDLIB_API int edlibAlignBatch(const char* const* queries, const int* queryLength
         return EDLIB_STATUS_ERROR;
     }
     t_lastEngine = e;
-    return e->align_batch(in, results);
+    const int rc = e->align_batch(in, results);
+    if (rc != EDLIB_STATUS_OK) t_lastError = e->lastError;
+    return rc;
 }
 
 // ref edlib.cpp:146-301
@@ -213,8 +217,10 @@ EDLIB_API const char* edlibB200LastError(void) {
     // every calling thread reads its own copy: a later call on another thread cannot change it under the reader
     static thread_local std::string copy;
     std::lock_guard<std::mutex> lock(g_mu);
-    eb::Engine* e = t_lastEngine ? t_lastEngine : g_engine;  // (a side engine is only written by calls of its own users)
-    copy = e ? e->lastError : g_initError;
+    // failures of edlibAlign / edlibAlignBatch are recorded per calling thread (side engines run concurrently); the
+    // staged / handle entry points all use the main engine under this lock
+    if (t_lastEngine && t_lastEngine != g_engine) copy = t_lastError;
+    else copy = g_engine ? g_engine->lastError : g_initError;
     return copy.c_str();
 }
 
