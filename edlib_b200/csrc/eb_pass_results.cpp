@@ -530,7 +530,9 @@ void Pass::paths_device() {
         const uint64_t maxN = (uint64_t)res_max_path_n(nw);  // target slice of a path: at most m + distance symbols
         const uint64_t matStride = maxN * (uint64_t)nw, opsStride = (uint64_t)32 * nw + maxN;
         const size_t perJob = (size_t)matStride * sizeof(U2) + (size_t)opsStride + sizeof(LJob) + sizeof(TbJob) + sizeof(Rec) + 64;
-        const int S = (int)std::max<size_t>(64, std::min<size_t>((size_t)N, tun.pathSliceBytes / perJob));
+        // pairs per slice: the stored matrices fit the budget, and the scripts of a slice stay countable in an int
+        const size_t byScripts = (size_t)0x7fffffff / (size_t)std::max<uint64_t>(opsStride, 1);
+        const int S = (int)std::max<size_t>(64, std::min<size_t>(std::min<size_t>((size_t)N, byScripts), tun.pathSliceBytes / perJob));
         DevBuf<int> dCnt(be, (size_t)S + 1), dLen(be, (size_t)S + 1);
         for (int first = 0; first < N; first += S) {
             const int last = std::min(N, first + S), span = last - first;
