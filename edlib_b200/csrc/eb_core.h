@@ -472,14 +472,14 @@ EB_HD K1Chunk k1_chunk(const K1Params& p, int chunk) {
 
 // Whole K1 work item for one thread when the target is directly addressable (host emulation,
 // and the reference shape for the device kernel, which adds shared-memory tiling around it).
-template <int NW, class Acc>
+template <int NW, class Acc, bool BUILD = true>
 EB_HD void k1_thread(const K1Params& p, int slot, int chunk, Acc& acc) {
     const int pair = p.readList[slot];
     const int m = p.prefixLen > 0 ? p.prefixLen : p.qlen[pair];
     const uint8_t* q = p.qcodes + p.qoff[pair];
     const int recIdx = chunk * p.numReads + slot;
     Rec* rec = p.rangeMode ? nullptr : p.recs + recIdx;
-    k1_build_peq<NW>(acc, q, m, p.mode, p.ncodes, p.eqtab);
+    if (BUILD) k1_build_peq<NW>(acc, q, m, p.mode, p.ncodes, p.eqtab);  // (else: the caller built the profile, shared by a warp)
     K1State<NW> st;
     k1_init<NW>(st, m, p.kInit[slot]);
     const K1Chunk g = k1_chunk(p, chunk);

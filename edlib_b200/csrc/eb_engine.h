@@ -58,6 +58,8 @@ struct Backend {
     virtual void launch_alpha_len(const uint32_t* masks, const int* qset, const int* tset, int numPairs, int* out) = 0;
     virtual void launch_encode(const EncodeParams& p) = 0;
     virtual void launch_k1(const K1Params& p, int nw32) = 0;
+    // The same sweep for a HANDFUL of reads: one warp per (read, 32 chunks), lanes = chunks of that read, one profile per warp.
+    virtual void launch_k1t(const K1Params& p, int nw32) = 0;
     virtual void launch_k1w(const K1WParams& p, int nw32) = 0;
     // lane-per-alignment sweeps with per-job targets; one launch = one class (mode / reversed / storing)
     virtual void launch_lane(const LParams& p, int nw32, int mode, bool reversed, bool store) = 0;
@@ -121,8 +123,8 @@ struct EngineTunables {
     int filterSeedK = 20;         // seed stage: largest threshold (needs (t+1) seeds inside the read); 0 disables
     int filterSeedBucket = 128;   // seed stage: longest index range looked at, level 0: twice this; x8 per level (longer: repeat, read passed on)
     int filterSeedLevels = 4;     // seed stage: levels tried (seed length L, L-2, L-4, L-5 for DNA; at most SEED_LEVELS)
-    int tinySweepReads = 0;       // plain sweeps of at most this many reads run as (read, chunk) jobs of the per-job lane kernel
-                                  // (off: the device time it saves, 0.4 ms, is less than the host time its job lists cost)
+    int tinySweepReads = 8;       // plain sweeps of at most this many reads: one warp per (read, 32 chunks) instead of one lane
+                                  // per read (k1t_kernel; 0: always the tile kernel)
     int filterMinLevelReads = 64; // seed levels 2 and later: fewest undecided reads worth the level (else: plain sweep)
     int filterSeedSlack = 4;      // seed stage: seed length L is the shortest with sigma^L >= slack * target length
     int filterK1 = 8;

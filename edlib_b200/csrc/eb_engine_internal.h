@@ -660,6 +660,7 @@ struct Pass {
 
     // The plain lane-per-alignment sweep of the reads in c.direct over the whole target.
     void plain_sweep(LaneGroup& c);
+    bool useK1t = false;  // the next lane_sweep launches the warp-per-read kernel (a handful of reads)
 
     // Distance pass of one group of pairs that share target `t` and word class `nw` (queries <= 256
     // rows), host-driven: the stages of the candidate filter (HW over a long target), each on

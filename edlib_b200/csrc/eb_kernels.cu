@@ -263,6 +263,34 @@ __global__ void k1_kernel(const K1Params p) {
 // Word-addressable per-thread profile rows for K1W: word w of code c of thread t at base + (c * WORDS + w) *
 // 4 * THREADS + 4 * t -- consecutive threads in consecutive banks whatever word each of them reads, and (CTA size
 // and row length being compile-time constants) every offset an immediate of the shared-memory instruction.
+// K1T: the plain sweep for a handful of reads.  The tile kernel gives every read ONE lane per chunk-CTA, so three
+// reads occupy three lanes of every warp and walk thousands of columns each; here a warp belongs to one read, its lanes
+// take 32 consecutive chunks (each behind its own 2m halo, symbols straight from global memory / L2), and the read's
+// profile sits once per warp in shared memory (rows of different codes fall into different banks, equal codes broadcast).
+template <int NW>
+struct WarpPeqAcc {
+    uint32_t* w;  // [ncodes][NW]
+    EB_D void store(int code, int word, uint32_t bits) { w[code * NW + word] = bits; }
+    EB_D void or_word(int code, int word, uint32_t bits) { w[code * NW + word] |= bits; }
+    EB_D void load(uint32_t code, uint32_t (&Eq)[NW]) const {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) Eq[i] = w[code * NW + i];
+    }
+};
+template <int NW>
+__global__ void __launch_bounds__(32) k1t_kernel(const K1Params p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    WarpPeqAcc<NW> acc{reinterpret_cast<uint32_t*>(smem)};
+    const int slot = blockIdx.y;
+    const int chunk = blockIdx.x * 32 + threadIdx.x;
+    if (threadIdx.x == 0) {
+        const int pair = p.readList[slot];
+        k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], p.qlen[pair], p.mode, p.ncodes, p.eqtab);
+    }
+    __syncwarp();
+    if (chunk < p.chunks) k1_thread<NW, WarpPeqAcc<NW>, false>(p, slot, chunk, acc);
+}
+
 template <int THREADS, int WORDS>
 struct SmemWordAcc {
     uint32_t base;  // shared address of this thread's word 0 of code 0
@@ -887,6 +915,28 @@ struct CudaBackend : Backend {
         if (p.mode == MODE_HW) launch_k1_t<NW, MODE_HW>(p);
         else if (p.mode == MODE_SHW) launch_k1_t<NW, MODE_SHW>(p);
         else launch_k1_t<NW, MODE_NW>(p);
+    }
+    template <int NW>
+    void launch_k1t_t(const K1Params& p) {
+        const size_t smem = (size_t)p.ncodes * NW * sizeof(uint32_t);
+        if (smem > 48 * 1024) EB_CUDA(cudaFuncSetAttribute(k1t_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1t_kernel<NW><<<dim3((unsigned)((p.chunks + 31) / 32), (unsigned)p.numReads), 32, smem, stream>>>(p);
+        check_launch("k1t");
+    }
+    void launch_k1t(const K1Params& p, int nw) override {
+        Scope s(this, "k1");
+        if (p.rangeMode || p.prefixLen > 0) throw std::runtime_error("k1t: plain sweeps only");
+        switch (nw) {
+            case 1: launch_k1t_t<1>(p); break;
+            case 2: launch_k1t_t<2>(p); break;
+            case 3: launch_k1t_t<3>(p); break;
+            case 4: launch_k1t_t<4>(p); break;
+            case 5: launch_k1t_t<5>(p); break;
+            case 6: launch_k1t_t<6>(p); break;
+            case 7: launch_k1t_t<7>(p); break;
+            case 8: launch_k1t_t<8>(p); break;
+            default: throw std::runtime_error("bad K1 word class");
+        }
     }
     void launch_k1(const K1Params& p, int nw) override {
         Scope s(this, p.rangeMode ? "k1_prefix" : "k1");

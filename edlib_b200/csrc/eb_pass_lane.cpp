@@ -204,7 +204,8 @@ void Pass::lane_sweep(LaneGroup& c, const std::vector<int>& sub, const std::vect
         be->zero(dCount.p, sizeof(int));
         kp.ovf = dOvf.p;
         kp.ovfCap = cap;
-        be->launch_k1(kp, nwL);
+        if (useK1t && !rangeMode && prefixLen == 0) be->launch_k1t(kp, nwL);
+        else be->launch_k1(kp, nwL);
         outOvf.clear();
         if (cap <= 0) break;
         int count = 0;
@@ -710,42 +711,18 @@ void Pass::plain_sweep(LaneGroup& c) {
     std::vector<Ovf> ovf;
     std::vector<int> incomplete;
     long long missing = 0;
-    if (mode == MODE_HW && (int)direct.size() <= tun.tinySweepReads && c.n >= tun.filterMinTarget && lane_ok(32 * c.nw)) {
+    if (mode == MODE_HW && (int)direct.size() <= tun.tinySweepReads && c.n >= tun.filterMinTarget) {
         // A handful of reads over a long target: the tile kernel would run one wave of CTAs with a few active lanes
-        // each, every lane walking thousands of columns (0.5 ms whatever the count).  Instead every (read, chunk) is
-        // one job of the per-job lane kernel -- full warps, chunks of a few hundred columns behind their 2m halos.
+        // each, every lane walking thousands of columns (0.5 ms whatever the count).  k1t_kernel gives every read whole
+        // warps whose lanes take chunks of a few hundred columns behind their 2m halos.
         const int g = (int)direct.size();
-        const int halo = 64 * c.nw;
-        chunkLen = (int)round_up((size_t)std::max<long long>(256, (long long)c.n * g / 65536), 16);
+        const long long want = std::max<long long>(1, std::min<long long>(c.n / 256, 32768 / g));
+        chunkLen = (int)round_up((size_t)ceil_div(c.n, (int)want), 16);
         chunks = ceil_div(c.n, chunkLen);
-        std::vector<LJob> jobs((size_t)g * chunks);
-        std::vector<int> hsOf((size_t)chunks);
-        for (int ch = 0; ch < chunks; ++ch) {
-            const long long cs = (long long)ch * chunkLen, ce = std::min<long long>(cs + chunkLen, c.n);
-            const long long hs = std::max<long long>(0, cs - halo);
-            hsOf[(size_t)ch] = (int)hs;
-            for (int s = 0; s < g; ++s) {
-                const int pair = list[direct[s]];
-                LJob& j = jobs[(size_t)ch * g + s];
-                memset(&j, 0, sizeof(j));
-                j.qOff = p->qoff[pair];
-                j.tOff = c.tg.off + (uint64_t)hs;
-                j.m = p->qlen[pair];
-                j.n = (int)(ce - hs);
-                j.kInit = kInit[s];
-                j.trackFrom = (int)(cs - hs);
-            }
-        }
-        lane_launch(jobs, c.nw, MODE_HW, false, recs);
-        for (int ch = 0; ch < chunks; ++ch)  // columns of a job count from its first symbol
-            for (int s = 0; s < g; ++s) {
-                Rec& r = recs[(size_t)ch * g + s];
-                for (int q = 0; q < KPOS; ++q) r.pos[q] += hsOf[(size_t)ch];
-                r.last += hsOf[(size_t)ch];
-            }
-    } else {
-        lane_sweep(c, direct, kInit, c.nw, chunks, chunkLen, 0, 0, 0, recs, ovf);
+        useK1t = true;
     }
+    lane_sweep(c, direct, kInit, c.nw, chunks, chunkLen, 0, 0, 0, recs, ovf);
+    useK1t = false;
     lane_merge(c, direct, chunks, recs, nullptr, incomplete, missing);
     if (incomplete.empty()) return;
     // Second pass over the few reads with more than KPOS end positions in one chunk: start from the

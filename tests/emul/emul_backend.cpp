@@ -194,6 +194,7 @@ struct EmulBackend : Backend {
         ++launchesCount;
         for (int i = 0; i < p.numReads; ++i) win_reduce_read(p, i);
     }
+    void launch_k1t(const K1Params& p, int nw) override { launch_k1(p, nw); }  // same work items, other mapping
     void launch_k1(const K1Params& p, int nw) override {
         ++launchesCount;
         switch (nw) {
