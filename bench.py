@@ -268,6 +268,7 @@ class Engine:
         L.edlibB200LastError.restype = C.c_char_p
         L.edlibB200LastKernelReport.argtypes = [C.c_char_p, C.c_int]
         L.edlibB200AlignmentsToCigar.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.edlibB200FreeCigars.argtypes = [C.c_void_p, C.c_int]
         L.edlibB200TargetPrepare.restype = C.c_void_p
         L.edlibB200TargetPrepare.argtypes = [C.c_void_p, C.c_int]
         L.edlibB200TargetFree.argtypes = [C.c_void_p]
@@ -302,9 +303,7 @@ class Engine:
         return out
 
     def free_cigars(self, cg):
-        for p in cg:
-            if p:
-                self.libc.free(p)
+        self.L.edlibB200FreeCigars(cg, len(cg))
 
 
 def resident_steps(E, ptrs, n, cfg, steps, warmup, flush, barrier):

@@ -83,6 +83,9 @@ EDLIB_API void edlibB200TargetFree(EdlibB200Target* target);
  * EDLIB_STATUS_OK, or EDLIB_STATUS_ERROR on a bad format / operation code (then every cigars[i] is NULL). */
 EDLIB_API int edlibB200AlignmentsToCigar(const EdlibAlignResult* results, int n, EdlibCigarFormat cigarFormat, char** cigars);
 
+/* free() n strings of edlibB200AlignmentsToCigar at once (on the engine's host threads, like edlibB200FreeResults). */
+EDLIB_API void edlibB200FreeCigars(char** cigars, int n);
+
 /* Stats of the most recent edlibAlign / edlibAlignBatch / BatchCompute on this process. */
 EDLIB_API void edlibB200LastStats(EdlibB200Stats* statsOut);
 
