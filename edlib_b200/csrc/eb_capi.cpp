@@ -192,6 +192,22 @@ static inline int cigar_run_end(const unsigned char* a, int i, int len, unsigned
     return j;
 }
 
+// STANDARD format: MATCH (0) and MISMATCH (3) both print 'M' -- the two codes whose low bits agree.  Any other byte
+// (I, D, or a bad code) ends the run.
+static inline int cigar_m_run_end(const unsigned char* a, int i, int len) {
+    int j = i + 1;
+    const uint64_t ones = 0x0101010101010101ull;
+    while (j + 8 <= len) {
+        uint64_t w;
+        memcpy(&w, a + j, 8);
+        const uint64_t x = ((w ^ (w >> 1)) & ones) | (w & ~(3 * ones));  // per byte: bit0 != bit1, or a bit above them
+        if (x) return j + (__builtin_ctzll(x) >> 3);
+        j += 8;
+    }
+    while (j < len && (a[j] == 0 || a[j] == 3)) ++j;
+    return j;
+}
+
 EDLIB_API char* edlibAlignmentToCigar(const unsigned char* alignment, int alignmentLength, EdlibCigarFormat cigarFormat) {
     if (cigarFormat != EDLIB_CIGAR_EXTENDED && cigarFormat != EDLIB_CIGAR_STANDARD) return NULL;
     const bool ext = cigarFormat == EDLIB_CIGAR_EXTENDED;
@@ -210,13 +226,8 @@ EDLIB_API char* edlibAlignmentToCigar(const unsigned char* alignment, int alignm
             break;
         }
         const char c = sym[op];
-        int j;
-        if (ext) {
-            j = cigar_run_end(alignment, i, len, op);
-        } else {  // STANDARD: MATCH and MISMATCH share 'M' (ref cpp:311-314)
-            j = i + 1;
-            while (j < len && alignment[j] <= 3 && sym[alignment[j]] == c) ++j;
-        }
+        // STANDARD: MATCH and MISMATCH share 'M' (ref cpp:311-314); insertions and deletions are plain runs in both formats
+        const int j = (ext || c != 'M') ? cigar_run_end(alignment, i, len, op) : cigar_m_run_end(alignment, i, len);
         int run = j - i;
         char digits[12];
         int nd = 0;
