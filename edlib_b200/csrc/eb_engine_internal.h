@@ -184,6 +184,7 @@ inline size_t host_parts(size_t n, size_t grain) {
 // fn(begin, end) over [0, n) on the host workers (only when every part gets >= grain items).
 template <class F>
 void parallel_ranges(size_t n, size_t grain, F fn) {
+    if (n == 0) return;  // nothing to do (and callers may hold a null data() for an empty vector)
     const size_t nthr = host_parts(n, grain);
     if (nthr <= 1) {
         fn((size_t)0, n);

@@ -432,3 +432,40 @@ def small_k_cases(seed, count):
                     del q[at]
             qs.append(bytes(q))
         yield dict(qs=qs, ts=[t] * len(qs), k=[0, 1, 2, 0][it % 4], mode=2, task=(it + seed) % 3, eqs=None)
+
+
+BOUNDARY_LENGTHS = [0, 1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 127, 128, 129, 255, 256, 257, 300, 511, 512, 513, 1000, 2049]
+
+
+def boundary_mix_cases(seed, count):
+    """Batches whose query AND target lengths sit on the 32/64-bit word boundaries (0, 1, 31..33, 63..65, ... 2049), over
+    one shared target (up to 70 kbp) or one target per query, with alphabets of 1, 2, 4, 27 and 256 symbols, every mode
+    and task, bounds from 0 to 1000 and now and then a few equality pairs: queries are random, mutated substrings, or
+    mutated prefixes / suffixes of their target."""
+    from helpers import mutate, rand_seq
+    rng = random.Random(seed)
+    for _ in range(count):
+        alpha = rng.choice([b"ACGT", b"AC", b"A", bytes(range(33, 60)), bytes(range(256))])
+        n = rng.choice([1, 2, 7, 40, 130, 300])
+        if rng.random() < 0.5:
+            ts = [rand_seq(rng, rng.choice(BOUNDARY_LENGTHS + [5000, 20000, 70000]), alpha)] * n
+        else:
+            ts = [rand_seq(rng, rng.choice(BOUNDARY_LENGTHS), alpha) for _ in range(n)]
+        qs = []
+        for t in ts:
+            style = rng.randrange(4)
+            m = rng.choice(BOUNDARY_LENGTHS[:rng.choice([12, 18, len(BOUNDARY_LENGTHS)])])
+            if style == 0 or not t:
+                q = rand_seq(rng, m, alpha)
+            elif style == 1:
+                at = rng.randrange(len(t))
+                q = mutate(rng, t[at:at + m], rng.choice([0, 0.02, 0.1, 0.3]), alpha)
+            elif style == 2:
+                q = mutate(rng, t[:m], 0.05, alpha)
+            else:
+                q = mutate(rng, t[-m:] if m else b"", 0.05, alpha)
+            qs.append(q)
+        eqs = None
+        if rng.random() < 0.15:
+            eqs = [(bytes([rng.choice(alpha)]), bytes([rng.choice(alpha)])) for _ in range(rng.randrange(1, 5))]
+        yield dict(qs=qs, ts=ts, k=rng.choice([-1, -1, 0, 1, 2, 5, 20, 64, 100, 1000]), mode=rng.randrange(3), task=rng.randrange(3), eqs=eqs)

@@ -485,3 +485,58 @@ def test_many_end_locations(emul):
     st, res = emul.align_batch(qs, [t] * 40, -1, 2, 1)
     exp = chk.align(qs[0], t, -1, 2, 1)
     assert st == 0 and all(r == exp for r in res)
+
+
+def test_very_large_bounds_and_full_byte_alphabets(emul):
+    """k far above any possible distance (single calls and batches), byte values 0..255, hundreds of equality pairs.  Up to
+    INT_MAX - 64 the reference's band arithmetic stays inside an int (edlib.cpp:563, 610, 634: k + 1, k + WORD_SIZE) and
+    every field must agree with it; above that its result is undefined, and "at most k" must give what k = -1 gives."""
+    import random
+    chk = parity.checker()
+    rng = random.Random(77)
+
+    def rs(n, alphabet=b"ACGT"):
+        return bytes(rng.choice(alphabet) for _ in range(n))
+
+    int_max = 2**31 - 1
+    pairs = [(rs(10), rs(30)), (rs(150), rs(3000)), (rs(300), rs(300)), (rs(700), rs(900)), (rs(70), b""), (b"", rs(20)), (rs(33), rs(31))]
+    for q, t in pairs:
+        for mode in (0, 1, 2):
+            for task in (0, 1, 2):
+                for k in (int_max - 64, 2**30 + 5, 2**24, 65536):
+                    assert emul.align(q, t, k, mode, task) == chk.align(q, t, k, mode, task), (len(q), len(t), k, mode, task)
+                free = emul.align(q, t, -1, mode, task)
+                for k in (int_max, int_max - 1, int_max - 63):
+                    assert emul.align(q, t, k, mode, task) == free, (len(q), len(t), k, mode, task)
+    t = rs(3000)
+    qs = [rs(rng.randrange(1, 300)) for _ in range(150)]
+    for mode in (0, 1, 2):
+        for task in (0, 1, 2):
+            st, res = emul.align_batch(qs, [t] * len(qs), int_max - 64, mode, task)
+            assert st == 0 and res == [chk.align(q, t, int_max - 64, mode, task) for q in qs]
+            st, top = emul.align_batch(qs, [t] * len(qs), int_max, mode, task)
+            assert st == 0 and top == res
+    full = bytes(range(256))
+    for mode in (0, 1, 2):
+        for task in (0, 1, 2):
+            q = bytes(rng.randrange(256) for _ in range(400))
+            t = bytes(rng.randrange(256) for _ in range(900))
+            eqs = [(bytes([rng.randrange(256)]), bytes([rng.randrange(256)])) for _ in range(300)]
+            for args in ((q, t, -1, mode, task), (full, full[::-1], -1, mode, task), (q, t, -1, mode, task, eqs), (q, t, 5, mode, task, eqs)):
+                assert emul.align(*args) == chk.align(*args), (mode, task, len(args))
+
+
+def test_lengths_on_word_boundaries_in_mixed_batches():
+    """Query and target lengths on the 32/64-bit word boundaries, alphabets of 1..256 symbols, every mode, task and bound, in
+    batches over one shared or many targets: with the default thresholds and with the filter / streamed paths forced on."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, cases, test_engine_emul as T\n"
+        "lib = T.load_emul()\n"
+        "print(parity.run_batches(lib, 7, 60, gen=cases.boundary_mix_cases))\n"
+    ) % (REPO, os.path.join(REPO, "tests"))
+    forced = dict(EDLIB_B200_FILTER_MIN_TARGET="128", EDLIB_B200_FILTER_MIN_LEVEL_READS="0", EDLIB_B200_K1_MIN_GROUP="4",
+                  EDLIB_B200_STREAM_MIN_PAIRS="64", EDLIB_B200_LONG_HW_MIN_TARGET="2000")
+    for extra in ({}, forced):
+        out = subprocess.run(["python", "-c", code], env=dict(os.environ, **extra), check=True, capture_output=True, text=True)
+        assert int(out.stdout.strip().splitlines()[-1]) > 3000
