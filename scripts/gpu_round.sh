@@ -1,5 +1,5 @@
 #!/bin/bash
-# One evidence run on a B200 (gpurun -- 'bash scripts/gpu_round.sh <tag> [stages]'); stages: smoke tests bench trace launches ncu ref stress
+# One evidence run on a B200 (gpurun -- 'bash scripts/gpu_round.sh <tag> [stages]'); stages: smoke tests bench trace launches ncu ref stress memcheck
 TAG=${1:-r02a}
 STAGES=${2:-"smoke tests bench trace launches ncu"}
 OUT=gpurun_out; mkdir -p $OUT
@@ -56,4 +56,13 @@ if has stress; then
   echo "== stress (filter forced on for small targets)"
   EDLIB_B200_FILTER_MIN_TARGET=128 EDLIB_B200_FILTER_MIN_LEVEL_READS=0 EDLIB_B200_K1_MIN_GROUP=4 EDLIB_B200_STREAM_MIN_PAIRS=64 EDLIB_B200_LONG_HW_MIN_TARGET=2000 \
       timeout 900 python scripts/stress.py ${STRESS_MIN:-3} 2>&1 | tail -2 | tee $OUT/stress_$TAG.txt
+fi
+if has memcheck; then
+  # compute-sanitizer over a short stress plan of the real kernels (not run in round 2: no GPU minutes were left for it)
+  for TOOL in memcheck racecheck synccheck; do
+    echo "== compute-sanitizer --tool $TOOL"
+    EDLIB_B200_FILTER_MIN_TARGET=128 EDLIB_B200_FILTER_MIN_LEVEL_READS=0 EDLIB_B200_K1_MIN_GROUP=4 EDLIB_B200_STREAM_MIN_PAIRS=64 EDLIB_B200_LONG_HW_MIN_TARGET=2000 \
+        timeout 1200 compute-sanitizer --tool $TOOL --error-exitcode 9 --print-limit 20 python scripts/stress.py 0.2 > $OUT/sanitizer_${TOOL}_$TAG.txt 2>&1
+    echo "rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|stress ok" $OUT/sanitizer_${TOOL}_$TAG.txt | tail -3
+  done
 fi
