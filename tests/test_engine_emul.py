@@ -540,3 +540,43 @@ def test_lengths_on_word_boundaries_in_mixed_batches():
     for extra in ({}, forced):
         out = subprocess.run(["python", "-c", code], env=dict(os.environ, **extra), check=True, capture_output=True, text=True)
         assert int(out.stdout.strip().splitlines()[-1]) > 3000
+
+
+def test_batch_helpers_for_results_and_cigar_strings(emul):
+    """edlibB200AlignmentsToCigar / edlibB200FreeCigars / edlibB200FreeResults over the raw result structs of one
+    edlibAlignBatch (HW, PATH): every CIGAR string (both formats) equals the reference's edlibAlignmentToCigar of the
+    reference's own alignment; results without an alignment (bound exceeded) give NULL strings."""
+    import ctypes as C
+    import numpy as np
+    import bench
+    from edlib_b200 import workloads
+    from edlib_b200._ffi import AlignResult, make_config
+    L = emul.lib
+    target, reads = workloads.reads_vs_target(num_reads=600, read_len=150, target_len=20_000, seed=5)
+    reads = reads.copy()
+    reads[::50] = workloads.random_dna(150, 3)  # unrelated reads: beyond the bound, no alignment
+    qptr, qlen, tptr, tlen = bench.pointer_arrays(reads, target)
+    cfg, _ = make_config(30, 2, 2)
+    res = np.zeros(len(reads), dtype=bench.RESULT_DTYPE)
+    assert L.edlibAlignBatch(bench.as_pp(qptr), bench.as_pi(qlen), bench.as_pp(tptr), bench.as_pi(tlen), len(reads), cfg,
+                             C.cast(res.ctypes.data, C.POINTER(AlignResult))) == 0
+    chk = parity.checker()
+    t = target.tobytes()
+    exp = [chk.align(reads[i].tobytes(), t, 30, 2, 2) for i in range(len(reads))]
+    assert [bench.gpu_result_dict(res, i) for i in range(len(reads))] == exp
+    assert sum(e["editDistance"] < 0 for e in exp) >= 10
+    L.edlibB200AlignmentsToCigar.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.edlibB200FreeCigars.argtypes = [C.c_void_p, C.c_int]
+    L.edlibB200FreeResults.argtypes = [C.c_void_p, C.c_int]
+    for fmt in (0, 1):
+        cg = (C.c_void_p * len(reads))()
+        assert L.edlibB200AlignmentsToCigar(res.ctypes.data, len(reads), fmt, cg) == 0
+        for i, e in enumerate(exp):
+            if e["alignment"] is None:
+                assert not cg[i]
+            else:
+                assert C.string_at(cg[i]).decode() == chk.cigar(e["alignment"], fmt), (i, fmt)
+        L.edlibB200FreeCigars(cg, len(reads))
+        assert not any(cg)  # pointers are cleared
+    L.edlibB200FreeResults(res.ctypes.data, len(reads))
+    assert not res["endLocations"].any() and not res["alignment"].any()
