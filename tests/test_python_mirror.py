@@ -16,8 +16,7 @@ def test_nice_alignment_formatting_only():
         edlib_b200.getNiceAlignment({"locations": [(0, 1)], "cigar": None}, "A", "A")
 
 
-@pytest.mark.gpu
-def test_reference_binding_known_answers():
+def check_known_answers():
     a = edlib_b200.align
     assert a("telephone", "elephant")["editDistance"] == 3
     assert a(b"telephone", b"elephant")["editDistance"] == 3
@@ -39,9 +38,41 @@ def test_reference_binding_known_answers():
                                                         "cigar": "1I5=1X1=1X"}
 
 
-@pytest.mark.gpu
-def test_align_batch_matches_align():
+def check_batch_matches_align():
     t = "ACGTTGCAATGCCGTAAGGCTTAACGGATCCA" * 20
     qs = ["TTGCAATGC", "GGGGGGGG", "AAGGCTTAACGG", ""]
     got = edlib_b200.align_batch(qs, t, mode="HW", task="path")
     assert got == [edlib_b200.align(q, t, mode="HW", task="path") for q in qs]
+    # one target per query, sequences of arbitrary hashables (recoded over the joint alphabet), equalities
+    ts = [t, "GGGGAGGG", t[::-1], "ACGT"]
+    got = edlib_b200.align_batch(qs, ts, mode="NW", task="path")
+    assert got == [edlib_b200.align(q, x, mode="NW", task="path") for q, x in zip(qs, ts)]
+    words = [("tele", "phone", "x"), ("ele", "phant")]
+    r = edlib_b200.align(words[0], words[1], task="path", additionalEqualities=[("tele", "ele")])
+    assert r["editDistance"] == 2 and r["alphabetLength"] == 5 and r["cigar"] == "1=1X1I"
+
+
+@pytest.mark.gpu
+def test_reference_binding_known_answers():
+    check_known_answers()
+
+
+@pytest.mark.gpu
+def test_align_batch_matches_align():
+    check_batch_matches_align()
+
+
+def test_mirror_host_logic_over_the_emulated_kernels(monkeypatch):
+    """The same checks with the package's library handle pointed at the CPU emulation build (the marshalling, recoding
+    and result shaping of edlib_b200/__init__.py are host code; the product library itself needs the GPU)."""
+    import ctypes as C
+    from test_engine_emul import load_emul
+    lib = load_emul()
+    lib.lib.edlibB200LastError.restype = C.c_char_p
+    monkeypatch.setattr(edlib_b200, "_lib", lib)
+    check_known_answers()
+    check_batch_matches_align()
+    # an unknown mode name leaves the default (NW), as in edlib.pyx:102-104; more than 256 distinct values cannot be recoded
+    assert edlib_b200.align("AAAA", "AACA", mode="no-such-mode") == edlib_b200.align("AAAA", "AACA", mode="NW")
+    with pytest.raises(ValueError):
+        edlib_b200.align(list(range(200)), list(range(100, 400)))
