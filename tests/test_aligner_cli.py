@@ -14,7 +14,12 @@ from helpers import mutate, rand_seq
 REFBIN = os.path.join(REPO, "oracle", "_ref")
 OPTION_SETS = [["-m", "HW"], ["-m", "NW", "-l"], ["-m", "SHW", "-l", "-k", "30"], ["-m", "HW", "-p", "-f", "CIG_EXT"],
                ["-m", "HW", "-p"], ["-m", "NW", "-p", "-f", "CIG_STD"], ["-m", "HW", "-n", "5", "-l"],
-               ["-m", "HW", "-n", "3", "-k", "8", "-p", "-f", "CIG_EXT"], ["-m", "SHW", "-n", "2"]]
+               ["-m", "HW", "-n", "3", "-k", "8", "-p", "-f", "CIG_EXT"], ["-m", "SHW", "-n", "2"],
+               [], ["-s"], ["-m", "HW", "-s", "-p"], ["-m", "HW", "-r", "2", "-l"], ["-m", "SHW", "-p", "-f", "CIG_STD", "-k", "40"],
+               ["-m", "NW", "-p", "-f", "NICE", "-k", "0"], ["-m", "HW", "-k", "0", "-l"], ["-m", "NW", "-n", "1", "-p"]]
+# wrong usage: same messages and exit codes (argv[0] differs in the usage text)
+ERROR_SETS = [["-m", "XX"], ["-f", "SAM", "-p"], ["-m", "HW", "no-such-queries.fasta"], ["-m", "HW", "Q", "no-such-target.fasta"], ["-m", "HW", "onlyone"],
+              ["-z"]]
 
 
 def write_fasta(path, seqs):
@@ -52,6 +57,18 @@ def compare(mine, tmp_path):
     qf, tf = make_inputs(str(tmp_path))
     for opts in OPTION_SETS:
         assert normalised(mine, opts, qf, tf) == normalised(ref, opts, qf, tf), opts
+    for opts in ERROR_SETS:
+        runs = []
+        for exe in (mine, ref):
+            args = [qf if a == "Q" else a for a in opts]
+            if not any(a.endswith(".fasta") or a == "onlyone" for a in opts):
+                args += [qf, tf]
+            elif opts[-1] == "no-such-queries.fasta":
+                args += [tf]
+            r = subprocess.run([exe] + args, capture_output=True, text=True)
+            usage = [l for l in r.stderr.replace(exe, "PROG").splitlines() if l.startswith("Usage:")]  # the option help is worded differently
+            runs.append((r.returncode, r.stdout, usage))
+        assert runs[0] == runs[1], opts
 
 
 def test_aligner_matches_reference_on_emulated_kernels(tmp_path):
