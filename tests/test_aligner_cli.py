@@ -57,6 +57,24 @@ def compare(mine, tmp_path):
     qf, tf = make_inputs(str(tmp_path))
     for opts in OPTION_SETS:
         assert normalised(mine, opts, qf, tf) == normalised(ref, opts, qf, tf), opts
+    # FASTA reading: wrapped lines, blank lines, lower case and other letters, blanks inside a line, an empty record, CRLF line
+    # ends, no header, an empty file, a header alone, no newline at the end, several records in the target file
+    odd = {"odd": ">q1\nACGTACGTAC\nGTAC\n\n>q2 desc\nacgtnnACGT\n>q3\n\n>q4\nAC GT\tAC\n", "crlf": ">q1\r\nACGTAC\r\nGT\r\n>q2\r\nTTGACC\r\n",
+           "nohdr": "ACGT\nACGT\n", "empty": "", "hdr": ">only header\n", "noeol": ">q1\nACGT"}
+    small_t = os.path.join(str(tmp_path), "small_t.fasta")
+    with open(small_t, "w") as f:
+        f.write(">t\nACGTACGTACGTACGGTACCAGT\nACGTTTGACCA\n")
+    for name, text in odd.items():
+        path = os.path.join(str(tmp_path), name + ".fasta")
+        with open(path, "w", newline="") as f:
+            f.write(text)
+        for opts in (["-m", "HW", "-l"], ["-m", "NW", "-p", "-f", "CIG_EXT"]):
+            got, exp = [subprocess.run([exe] + opts + [path, small_t], capture_output=True, text=True) for exe in (mine, ref)]
+            strip = lambda r: [l for l in r.stdout.replace("\r", "\n").split("\n")  # noqa: E731
+                               if not l.startswith("Cpu time") and not (l and l.replace("/", "").isdigit())]
+            assert (got.returncode, strip(got)) == (exp.returncode, strip(exp)), (name, opts)
+    assert normalised(mine, ["-m", "HW"], small_t, os.path.join(str(tmp_path), "odd.fasta")) == \
+        normalised(ref, ["-m", "HW"], small_t, os.path.join(str(tmp_path), "odd.fasta"))  # first record of a multi-record target file
     for opts in ERROR_SETS:
         runs = []
         for exe in (mine, ref):
