@@ -54,6 +54,19 @@ void emul_k1(const K1Params& p) {
         for (int slot = 0; slot < p.numReads; ++slot) k1_thread<NW>(p, slot, chunk, acc);
 }
 
+// As k1t_kernel (eb_kernels.cu): the profile of a read is built ONCE (there: by lane 0 of the read's warp), every chunk then
+// sweeps with BUILD = false.  The profile starts as garbage so that a build that misses a row shows.
+template <int NW>
+void emul_k1t(const K1Params& p) {
+    HostPeqAcc<NW> acc;
+    for (int slot = 0; slot < p.numReads; ++slot) {
+        acc.w.assign((size_t)p.ncodes * NW, 0xdeadbeefu);
+        const int pair = p.readList[slot];
+        k1_build_peq<NW>(acc, p.qcodes + p.qoff[pair], p.qlen[pair], p.mode, p.ncodes, p.eqtab);
+        for (int chunk = p.chunks - 1; chunk >= 0; --chunk) k1_thread<NW, HostPeqAcc<NW>, false>(p, slot, chunk, acc);
+    }
+}
+
 // Word-addressable rows of NW + 4 words (K1W: banded and full sweeps share one profile).
 struct HostWordAcc {
     std::vector<uint32_t> w;
@@ -194,7 +207,20 @@ struct EmulBackend : Backend {
         ++launchesCount;
         for (int i = 0; i < p.numReads; ++i) win_reduce_read(p, i);
     }
-    void launch_k1t(const K1Params& p, int nw) override { launch_k1(p, nw); }  // same work items, other mapping
+    void launch_k1t(const K1Params& p, int nw) override {
+        ++launchesCount;
+        switch (nw) {
+            case 1: emul_k1t<1>(p); break;
+            case 2: emul_k1t<2>(p); break;
+            case 3: emul_k1t<3>(p); break;
+            case 4: emul_k1t<4>(p); break;
+            case 5: emul_k1t<5>(p); break;
+            case 6: emul_k1t<6>(p); break;
+            case 7: emul_k1t<7>(p); break;
+            case 8: emul_k1t<8>(p); break;
+            default: throw std::runtime_error("bad K1 word class");
+        }
+    }
     void launch_k1(const K1Params& p, int nw) override {
         ++launchesCount;
         switch (nw) {
